@@ -1,0 +1,214 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.npz from the repaired reference binary (oracle/_ref/lmp_serial).
+
+Runs HERE (needs /root/reference for the example inputs); the GPU box only sees the fixtures.
+Each fixture = inputs and outputs of ONE PairLJCutCoulLongPolarization::compute() call of the
+reference, dumped by the hooks of oracle/ref_shims/polb200_dump.h, keyed by local atom index
+(ghost forces folded onto their owners the way Verlet's reverse_comm does).
+
+Also transcribes the thermo tables of the reference's committed logs into thermo_logs.json.
+"""
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+from oracle import polref as P  # noqa: E402
+
+REF = Path(os.environ.get("POLB200_REFERENCE", "/root/reference"))
+EX = REF / "polarization" / "examples"
+LMP = ROOT / "oracle" / "_ref" / "lmp_serial"
+OUT = ROOT / "tests" / "golden"
+
+H2_STYLE = ("pair_style lj/cut/coul/long/polarization 2.5 10.797442 precision 0.00000000001 "
+            "max_iterations 100 damp_type exponential damp 2.1304 polar_gs_ranked yes debug no use_previous yes")
+
+# (case name, example dir, input file, replacement pair_style line or None, extra lines before run,
+#  steps to keep, run length)
+CASES = [
+    ("h2_default", "Bulk H2", "h2.input", None, [], [0, 1, 2, 3], 3),
+    ("h2_jacobi_fixed3", "Bulk H2", "h2.input",
+     H2_STYLE.replace("polar_gs_ranked yes", "polar_gs_ranked no fixed_iteration yes").replace(
+         "max_iterations 100", "max_iterations 3"), [], [0, 1], 1),
+    ("h2_jacobi_fixed30", "Bulk H2", "h2.input",
+     H2_STYLE.replace("polar_gs_ranked yes", "polar_gs_ranked no fixed_iteration yes").replace(
+         "max_iterations 100", "max_iterations 30"), [], [0], 0),
+    ("h2_jacobi_precision", "Bulk H2", "h2.input",
+     H2_STYLE.replace("polar_gs_ranked yes", "polar_gs_ranked no"), [], [0, 1], 1),
+    ("h2_gs", "Bulk H2", "h2.input",
+     H2_STYLE.replace("polar_gs_ranked yes", "polar_gs_ranked no polar_gs yes"), [], [0, 1], 1),
+    ("h2_gs_fixed3", "Bulk H2", "h2.input",
+     H2_STYLE.replace("polar_gs_ranked yes", "polar_gs_ranked no polar_gs yes fixed_iteration yes").replace(
+         "max_iterations 100", "max_iterations 3"), [], [0], 0),
+    ("h2_zodid", "Bulk H2", "h2.input",
+     H2_STYLE.replace("polar_gs_ranked yes", "polar_gs_ranked no zodid yes").replace("use_previous yes",
+                                                                                      "use_previous no"),
+     [], [0], 0),
+    ("h2_nodamp", "Bulk H2", "h2.input", H2_STYLE.replace("damp_type exponential", "damp_type none"),
+     [], [0], 0),
+    ("h2_noprev", "Bulk H2", "h2.input", H2_STYLE.replace("use_previous yes", "use_previous no"),
+     [], [0, 1], 1),
+    ("h2_diverge", "Bulk H2", "h2.input", H2_STYLE.replace("max_iterations 100", "max_iterations 3"),
+     [], [0], 0),
+    ("h2_notable", "Bulk H2", "h2.input", None, ["pair_modify table 0"], [0], 0),
+    ("methane_default", "MOF5+Methane", "MOF5+PCRC.restart.pdb.input", None, [], [0, 1, 2], 2),
+    # shipped input aborts in fix rigid; single-point compute() with the integrator swapped
+    ("co2_singlepoint", "MOF5+CO2", "co2_mof5.restart.pdb.input", None, ["__NVE__"], [0], 0),
+]
+
+
+def run_case(name, exdir, inp, style, extra, keep, nrun):
+    work = Path(tempfile.mkdtemp(prefix=f"polgold_{name}_"))
+    src = EX / exdir
+    for f in src.iterdir():
+        if f.suffix in (".data",) or f.name.endswith(".data"):
+            shutil.copy(f, work / f.name)
+    text = (src / inp).read_text()
+    text = text.replace("ewald/disp", "ewald")
+    text = re.sub(r"^dump\S* .*$", "", text, flags=re.M)
+    if style is not None:
+        text = re.sub(r"^pair_style .*$", style, text, flags=re.M)
+    text = re.sub(r"(variable\s+nstep\s+equal\s+)\d+", rf"\g<1>{nrun}", text)
+    nve = "__NVE__" in extra
+    extra = [e for e in extra if e != "__NVE__"]
+    if nve:
+        text = re.sub(r"^fix\s+rigid_nve.*$", "fix 1 moving nve", text, flags=re.M)
+    lines = text.splitlines()
+    idx = max(i for i, l in enumerate(lines) if l.strip().startswith("run"))
+    lines[idx:idx] = extra
+    (work / "in.case").write_text("\n".join(lines) + "\n")
+    env = dict(os.environ, POLB200_DUMP=str(work / "dump"), POLB200_DUMP_MAX=str(max(keep) + 1))
+    r = subprocess.run([str(LMP), "-in", "in.case", "-echo", "none"], cwd=work, env=env, capture_output=True,
+                       text=True)
+    if r.returncode != 0:
+        print(r.stdout[-3000:])
+        raise SystemExit(f"{name}: lmp_serial failed")
+    log = (work / "log.lammps").read_text()
+    pair_style = [l for l in lines if l.strip().startswith("pair_style")][0]
+    pair_coeffs = [l for l in lines if l.strip().startswith("pair_coeff")]
+    pair_modify = [l for l in lines if l.strip().startswith("pair_modify")]
+    m = re.search(r"G vector \(1/distance\) = (\S+)", log)
+    thermo = parse_thermo(log)
+    first = None
+    for step in range(max(keep) + 1):
+        d = P.read_refdump(work / f"dump.{step}.bin")
+        if step == 0:
+            first = d
+        if step not in keep:
+            continue
+        nl = int(d["nlocal"][0])
+        nt = int(d["ntypes"][0])
+        x = d["x"].reshape(-1, 3)
+        tag = d["tag"]
+        f_all = d["f"].reshape(-1, 3)
+        # fold ghost forces onto owners (tag -> local index)
+        loc = {int(t): i for i, t in enumerate(tag[:nl])}
+        f_own = f_all[:nl].copy()
+        for g in range(nl, len(tag)):
+            f_own[loc[int(tag[g])]] += f_all[g]
+        ms = int(d["maxspecial"][0]) if "maxspecial" in d else 0
+        fx = dict(
+            x=x[:nl], q=d["q"][:nl], type=d["type"][:nl], molecule=d["molecule"][:nl], alpha=d["alpha"][:nl],
+            tag=tag[:nl], boxlo=d["boxlo"], boxhi=d["boxhi"], ntypes=nt,
+            mu_in=d["mu_in"].reshape(nl, 3), mu_out=d["mu_out"].reshape(nl, 3),
+            ef_static=d["ef_static"].reshape(nl, 3), f=f_own,
+            eng_vdwl=d["eng_vdwl"][0], eng_coul=d["eng_coul"][0], eng_pol=d["eng_pol"][0],
+            virial=d["virial"], iterations=int(d["iterations"][0]), eflag=int(d["eflag"][0]),
+            vflag=int(d["vflag"][0]), g_ewald=d["g_ewald"][0], nghost=int(d["nghost"][0]),
+            special_lj=d["special_lj"], special_coul=d["special_coul"],
+            numneigh_half=d["numneigh"], npairs_half=len(d["neigh"]),
+            pair_style=pair_style, pair_coeff="\n".join(pair_coeffs), pair_modify="\n".join(pair_modify),
+            step=step, ncoultablebits=int(d["ncoultablebits"][0]),
+        )
+        if ms:
+            fx["nspecial"] = d["nspecial"].reshape(nl, 3)
+            fx["special"] = d["special"].reshape(nl, ms)
+        if step == 0 and name in ("h2_default",):
+            # full half list of the reference in canonical form: (i local idx, tag_j, shift code, special)
+            ii = np.repeat(np.arange(nl, dtype=np.int32), d["numneigh"])
+            jraw = d["neigh"]
+            sb = (jraw >> 30) & 3
+            j = jraw & 0x3FFFFFFF
+            prd = d["boxhi"] - d["boxlo"]
+            owner = np.array([loc[int(t)] for t in tag[j]], dtype=np.int32)
+            shift = np.rint((x[j] - x[owner]) / prd).astype(np.int8)
+            fx["half_i"] = ii.astype(np.int16)
+            fx["half_j"] = owner.astype(np.int16)
+            fx["half_shift"] = shift
+            fx["half_special"] = sb.astype(np.int8)
+            # tables of the reference (pins the table builder)
+            for k in ("rtable", "drtable", "ftable", "dftable", "ctable", "dctable", "etable", "detable"):
+                fx["tab_" + k] = first[k]
+            fx["ncoulmask"] = int(first["ncoulmask"][0])
+            fx["ncoulshiftbits"] = int(first["ncoulshiftbits"][0])
+            fx["tabinnersq"] = first["tabinnersq"][0]
+        np.savez_compressed(OUT / f"{name}_step{step}.npz", **fx)
+        print(f"{name} step {step}: nlocal {nl} iterations {fx['iterations']} E_pol {fx['eng_pol']:.10g}")
+    shutil.rmtree(work)
+    return thermo
+
+
+def parse_thermo(log):
+    rows = []
+    lines = log.splitlines()
+    for i, l in enumerate(lines):
+        if l.startswith("Step "):
+            cols = l.split()
+            for r in lines[i + 1:]:
+                v = r.split()
+                if len(v) != len(cols):
+                    break
+                try:
+                    rows.append(dict(zip(cols, [float(t) for t in v])))
+                except ValueError:
+                    break
+    return rows
+
+
+def shipped_logs():
+    """Thermo tables exactly as committed by the reference authors (strings, 8 significant digits)."""
+    out = {}
+    for key, rel in (("h2", "Bulk H2/log.lammps"), ("methane", "MOF5+Methane/log.lammps")):
+        text = (EX / rel).read_text(errors="replace")
+        lines = text.splitlines()
+        for i, l in enumerate(lines):
+            if l.startswith("Step "):
+                cols = l.split()
+                rows = []
+                for r in lines[i + 1:]:
+                    v = r.split()
+                    if len(v) != len(cols):
+                        break
+                    try:
+                        [float(t) for t in v]
+                    except ValueError:
+                        break
+                    rows.append(dict(zip(cols, v)))
+                out[key] = dict(source=f"polarization/examples/{rel}", columns=cols, rows=rows)
+    return out
+
+
+def main():
+    OUT.mkdir(parents=True, exist_ok=True)
+    only = sys.argv[1:]
+    ours = {}
+    for c in CASES:
+        if only and c[0] not in only:
+            continue
+        ours[c[0]] = run_case(*c)
+    if not only:
+        logs = shipped_logs()
+        logs["oracle_ref_runs"] = {k: v for k, v in ours.items()}
+        (OUT / "thermo_logs.json").write_text(json.dumps(logs, indent=1))
+
+
+if __name__ == "__main__":
+    main()
