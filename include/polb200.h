@@ -1,0 +1,170 @@
+/* polb200.h -- C ABI of the B200-native hot path of pair style lj/cut/coul/long/polarization.
+ *
+ * This is the drop-in boundary: a LAMMPS Pair subclass registered under the reference's own style
+ * name (see lammps-induced-dipole-polarization-pair-style_b200/lammps/) forwards its virtuals to
+ * these entry points and nothing else crosses the boundary -- plain pointers, sizes and C structs,
+ * no C++ or torch types, no exceptions.  Every function returns POLB200_OK (0) or an error code;
+ * polb200_last_error() gives the message the caller passes to error->all()/error->one().
+ * The shape follows the reference's own precedent for "Pair subclass -> extern C -> CUDA library",
+ * the GPU package (src/GPU/pair_lj_cut_coul_long_gpu.cpp:50-80: ljcl_gpu_init / _compute_n / _clear).
+ *
+ * Citations are file:line under the reference tree; "pol.cpp" abbreviates
+ * src/pair_lj_cut_coul_long_polarization.cpp.
+ *
+ * There is NO CPU fallback: without a CUDA device polb200_create() fails with POLB200_ERR_CUDA.
+ */
+#ifndef POLB200_H
+#define POLB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define POLB200_ABI_VERSION 1
+
+typedef struct polb200_handle polb200_t;
+
+enum {
+  POLB200_OK = 0,
+  POLB200_ERR_ARG = 1,      /* message = the reference's error->all text, e.g. "Illegal pair_style command" */
+  POLB200_ERR_CUDA = 2,     /* CUDA runtime failure or no device */
+  POLB200_ERR_STATE = 3,    /* call order (e.g. compute before init) */
+  POLB200_ERR_UNSUPPORTED = 4, /* triclinic box, per-atom tallies, ... */
+  POLB200_ERR_OVERFLOW = 5, /* neighbor capacity ("Neighbor list overflow, boost neigh_modify one") */
+  POLB200_ERR_NAN = 6       /* "Non-numeric positions - simulation unstable" (src/nbin.cpp:120-121) */
+};
+
+/* status bits in polb200_result.status */
+#define POLB200_STATUS_DIVERGED 1 /* pol.cpp:1227-1235: caller emits the reference's warning text */
+#define POLB200_STATUS_REBUILT 2  /* neighbor structures were rebuilt in this call */
+#define POLB200_STATUS_EXACT 4    /* all-pairs minimum-image (reference) polarization path was used */
+
+/* ---- life cycle -------------------------------------------------------------------------------- */
+
+/* replaces the constructor pol.cpp:55-91 (defaults :65-78).  device = CUDA ordinal.
+ * POLB200_DEVICE_NONE makes a configuration-only handle (settings/coeff/init/single/extract/restart
+ * work on the host; polb200_compute fails with POLB200_ERR_CUDA) for input validation and restart
+ * tools on machines without a GPU. */
+#define POLB200_DEVICE_NONE (-1)
+int polb200_create(polb200_t **h, int device);
+/* replaces the destructor pol.cpp:95-121 */
+void polb200_destroy(polb200_t *h);
+const char *polb200_last_error(const polb200_t *h);
+int polb200_abi_version(void);
+
+/* ---- configuration: same arguments, defaults and error texts as the reference ------------------ */
+
+/* PairLJCutCoulLongPolarization::settings(narg,arg), pol.cpp:678-766.  arg[0]=cut_lj_global,
+ * arg[1]=cut_coul, then keyword/value pairs: precision zodid fixed_iteration damp max_iterations
+ * damp_type polar_gs polar_gs_ranked polar_gamma debug use_previous -- plus the documented extensions
+ *   polar_cutoff <r|none>  dipole-dipole cutoff (none = reference all-pairs semantics, the default)
+ *   gs_chunks <n>          ranked colouring sweep with n chunks in list mode (0 = sequential GS)
+ * Order-dependent validation is the reference's (e.g. "zodid" errors while polar_gs_ranked is on). */
+int polb200_settings(polb200_t *h, int narg, const char *const *arg);
+/* Atom::ntypes; allocates the (ntypes+1)^2 coefficient arrays = allocate(), pol.cpp:651-672 */
+int polb200_set_ntypes(polb200_t *h, int ntypes);
+/* coeff(narg,arg), pol.cpp:772-800: "I J epsilon sigma [cut_lj]" with Force::bounds wildcards */
+int polb200_coeff(polb200_t *h, int narg, const char *const *arg);
+/* Pair::modify_params (src/pair.cpp:132-185) subset that shapes this style: mix, shift, table, tabinner */
+int polb200_pair_modify(polb200_t *h, int narg, const char *const *arg);
+
+typedef struct {
+  double g_ewald;          /* force->kspace->g_ewald, pol.cpp:845-847 */
+  double qqrd2e;           /* force->qqrd2e */
+  double special_lj[4];    /* force->special_lj */
+  double special_coul[4];  /* force->special_coul */
+  int newton_pair;         /* force->newton_pair (only 1 is supported on the device path) */
+  double skin;             /* neighbor->skin */
+  int neigh_every, neigh_delay, neigh_check; /* neigh_modify every/delay/check (1,10,1) */
+  int kspace_present;      /* 0 => "Pair style requires a KSpace style" */
+  int q_flag, polarizability_flag; /* atom->q_flag, atom->static_polarizability_flag */
+  int molecular;           /* atom->molecular: special-bond lists are meaningful */
+} polb200_env;
+
+/* init_style(), pol.cpp:806-852, followed by Pair::init()'s loop over init_one(i,j)
+ * (src/pair.cpp:227-255, pol.cpp:858-921) and init_tables (src/pair.cpp:313-520). */
+int polb200_init(polb200_t *h, const polb200_env *env);
+/* value init_one(i,j) returned (the pair cutoff); valid after polb200_init */
+int polb200_init_one(const polb200_t *h, int i, int j, double *cut);
+/* extract(), pol.cpp:1101-1109: "cut_coul" (dim 0), "epsilon"/"sigma" (dim 2, (ntypes+1)^2 row-major).
+ * Returns a pointer into host memory owned by the handle, or NULL. */
+const void *polb200_extract(const polb200_t *h, const char *name, int *dim);
+/* single(), pol.cpp:1035-1097 (host arithmetic; qi,qj passed explicitly) */
+int polb200_single(const polb200_t *h, int itype, int jtype, double qi, double qj, double rsq,
+                   double factor_coul, double factor_lj, double *fforce, double *eng);
+/* write_restart_settings / read_restart_settings payload (pol.cpp:976-1009): 7 fields, and
+ * write_restart / read_restart per-pair records (pol.cpp:927-970), as a flat byte image. */
+int polb200_restart_size(const polb200_t *h, long *nbytes);
+int polb200_write_restart(const polb200_t *h, void *buf, long nbytes);
+int polb200_read_restart(polb200_t *h, const void *buf, long nbytes);
+
+/* orthogonal periodic box (Domain::boxlo/boxhi/periodicity); triclinic => POLB200_ERR_UNSUPPORTED */
+int polb200_set_box(polb200_t *h, const double boxlo[3], const double boxhi[3], const int periodic[3]);
+
+/* ---- the hot path ------------------------------------------------------------------------------ */
+
+typedef struct {
+  int nlocal;
+  const double *x;          /* [nlocal][3] AoS, atom->x[0]  (host or device pointer, see `on_device`) */
+  const double *q;          /* [nlocal] */
+  const int *type;          /* [nlocal] 1-based */
+  const int *molecule;      /* [nlocal] (32-bit tagint, src/lmptype.h:83-85) or NULL = all 0 */
+  const int *tag;           /* [nlocal] or NULL = 1..nlocal */
+  const double *alpha;      /* atom->static_polarizability [nlocal] */
+  double *mu;               /* atom->mu_induced [nlocal][3]  in/out */
+  double *ef_static;        /* atom->ef_static  [nlocal][3]  out (may be NULL) */
+  double *f;                /* atom->f [nlocal][3]  accumulated (+=) */
+  const int *nspecial;      /* atom->nspecial [nlocal][3] or NULL */
+  const int *special;       /* atom->special [nlocal][maxspecial] (tags) or NULL */
+  int maxspecial;
+  int on_device;            /* 0: all pointers are host memory; 1: all are device memory on this GPU */
+} polb200_atoms;
+
+typedef struct {
+  double eng_vdwl, eng_coul, eng_pol; /* Pair::eng_vdwl / eng_coul / eng_pol (src/pair.h:36) */
+  double virial[6];                   /* Pair::virial, xx yy zz xy xz yz */
+  double u_self, u_ef, u_dd;          /* the `debug yes` partial sums, pol.cpp:632-636 */
+  double rmin;                        /* pol.cpp:196-209 (gs_ranked only) */
+  int iterations;                     /* DipoleSolverIterative() return value */
+  int status;                         /* POLB200_STATUS_* bits */
+  long npairs_full;                   /* entries of the device full neighbor list */
+  int nghost;
+  float ms_neigh, ms_pair, ms_scf, ms_force, ms_total; /* CUDA-event stage times of this call */
+} polb200_result;
+
+/* compute(eflag,vflag), pol.cpp:125-645.  `ago` = neighbor->ago (0: LAMMPS rebuilt its lists this
+ * step => rebuild device structures; >0: reuse, refresh ghost positions).  ago < 0: the library runs
+ * the reference's own rebuild schedule itself (Neighbor::decide/check_distance,
+ * src/neighbor.cpp:1923-2001: every/delay/check, half-skin displacement trigger).
+ * eflag/vflag use LAMMPS' encoding (src/integrate.cpp:122-157): eflag&1 global energy,
+ * vflag%4 == 1 pairwise virial, == 2 F.r virial; per-atom bits => POLB200_ERR_UNSUPPORTED. */
+int polb200_compute(polb200_t *h, const polb200_atoms *atoms, int eflag, int vflag, int ago,
+                    polb200_result *out);
+
+/* ---- multi-GPU (one process per GPU; spatial decomposition) ------------------------- */
+
+/* Size of the opaque NCCL unique id the ranks must share (rank 0 creates it). */
+int polb200_comm_id_size(void);
+int polb200_comm_create_id(void *id_bytes);
+/* Join a communicator of nranks processes; procgrid = bricks per dimension (px*py*pz == nranks). */
+int polb200_comm_init(polb200_t *h, int rank, int nranks, const void *id_bytes, const int procgrid[3]);
+/* Sub-domain owned by this rank, valid after polb200_set_box + polb200_comm_init. */
+int polb200_subdomain(const polb200_t *h, double sublo[3], double subhi[3]);
+
+/* ---- introspection for tests and profiling ------------------------------------------------------ */
+
+/* Copy an internal device array to host.  names: "perm" (int nlocal: sorted->caller index),
+ * "ghost_owner" (int nghost, caller index), "ghost_shift" (int nghost*3), "numneigh" (int nlocal, caller
+ * order), "neigh_canon" (canonical full list, see tests), "ef_static", "mu", "rank_metric", "ranked".
+ * Returns number of elements copied or <0. */
+long polb200_debug_fetch(polb200_t *h, const char *name, void *dst, long capacity_bytes);
+/* number of kernel launches issued by this handle since creation / since last reset */
+long polb200_launch_count(polb200_t *h, int reset);
+/* knobs for experiments: "exact_threshold" (atoms; use all-pairs path when polar_cutoff is none and
+ * nlocal <= threshold), "sweep_variant", "block_size" ... returns POLB200_ERR_ARG for unknown names */
+int polb200_set_option(polb200_t *h, const char *name, double value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,952 @@
+// engine.cu -- device-side state of one pair-style instance and the orchestration of the five
+// stages for one compute() call, plus the C ABI of include/polb200.h.
+//
+// Streams/graphs: everything of one call is enqueued on one stream; the host synchronises only
+// where the reference's control flow needs a device value (ghost count at a rebuild, the convergence
+// test of `precision` mode).  fixed_iteration mode enqueues all sweeps back to back with no sync.
+#include <cub/cub.cuh>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "host_style.h"
+#include "kernels.cuh"
+#include "polb200.h"
+
+namespace polb200 {
+
+struct CudaError {
+  std::string msg;
+};
+
+#define CUDA_CHECK(expr)                                                                         \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess)                                                                       \
+      throw CudaError{std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" + \
+                      std::to_string(__LINE__) + ")"};                                           \
+  } while (0)
+
+template <class T>
+struct DBuf {
+  T *p = nullptr;
+  size_t cap = 0;
+  void ensure(size_t n, double slack = 1.1)
+  {
+    if (n <= cap) return;
+    if (p) cudaFree(p);
+    cap = (size_t)(n * slack) + 64;
+    p = nullptr;
+    cudaError_t e = cudaMalloc(&p, cap * sizeof(T));
+    if (e != cudaSuccess) {
+      cap = 0;
+      throw CudaError{std::string("cudaMalloc of ") + std::to_string(n * sizeof(T)) + " bytes: " +
+                      cudaGetErrorString(e)};
+    }
+  }
+  void release()
+  {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+template <class T>
+struct HPinned {
+  T *p = nullptr;
+  size_t cap = 0;
+  void ensure(size_t n)
+  {
+    if (n <= cap) return;
+    if (p) cudaFreeHost(p);
+    cap = n + n / 8 + 64;
+    CUDA_CHECK(cudaMallocHost(&p, cap * sizeof(T)));
+  }
+  void release()
+  {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace polb200
+
+using namespace polb200;
+
+struct polb200_handle {
+  HostStyle style;
+  std::string err;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[6] = {};
+  long launches = 0;
+
+  Box box{};
+  bool box_set = false;
+
+  // options
+  int sweep_block = BLOCK;
+
+  // device copies of host-style tables
+  DBuf<double> d_coeff;   // 7 tables x (ntypes+1)^2 + cutneighsq
+  DBuf<double> d_tables;  // 8 x ntable
+  DevParams P{};
+  bool params_uploaded = false;
+
+  // caller-order staging (device)
+  DBuf<double> c_x, c_q, c_alpha, c_mu, c_f, c_ef, c_xhold;
+  DBuf<int> c_type, c_mol, c_tag, c_nspecial, c_special;
+  // pinned host staging
+  HPinned<double> h_stage;
+  HPinned<double> h_scal;
+  HPinned<int> h_int;
+
+  // cell-sorted ext arrays
+  DBuf<double4> xq, mua, mub, ef, f_pair, f_pol;
+  DBuf<int2> tm;
+  DBuf<int> tag, perm, invperm, keys, keys2, vals, vals2;
+  DBuf<int> g_owner_u, g_shift_u, g_owner, g_shift;
+  DBuf<int> cl_start, cg_start, stencil;
+  DBuf<int> s_nspecial, s_special;
+  DBuf<unsigned long long> cnt, rowstart;
+  DBuf<int> neigh;
+  DBuf<char> cub_tmp;
+  DBuf<double> partial, scal;
+  DBuf<int> flags;
+  DBuf<double> metric, metric2;
+  DBuf<int> ranked, ranked_in;
+  DBuf<unsigned long long> rmin_bits;
+
+  int nloc = 0, nghost = 0, maxspecial = 0, nstencil = 0;
+  bool molecular = false;
+  unsigned long long npairs = 0;
+  bool have_lists = false;
+  int ago_internal = 0;  // library-side Neighbor::decide state (ago < 0 calls)
+  bool mu_is_b = false;
+};
+
+namespace polb200 {
+
+template <class... KA, class... A>
+static void launch_kernel(polb200_handle *h, void (*kernel)(KA...), int grid, int block, A &&...args)
+{
+  kernel<<<grid, block, 0, h->stream>>>(std::forward<A>(args)...);
+  h->launches++;
+  CUDA_CHECK(cudaGetLastError());
+}
+#define LAUNCH(h, kernel, grid, block, ...) launch_kernel(h, kernel, grid, block, __VA_ARGS__)
+
+static void upload_params(polb200_handle *h)
+{
+  const HostStyle &st = h->style;
+  const int n1 = st.ntypes + 1, nn = n1 * n1;
+  std::vector<double> buf((size_t)8 * nn);
+  const std::vector<double> *src[8] = {&st.cutsq, &st.cut_ljsq, &st.lj1,    &st.lj2,
+                                       &st.lj3,   &st.lj4,      &st.offset, &st.cutneighsq};
+  for (int k = 0; k < 8; k++) std::copy(src[k]->begin(), src[k]->end(), buf.begin() + (size_t)k * nn);
+  h->d_coeff.ensure(buf.size());
+  CUDA_CHECK(cudaMemcpy(h->d_coeff.p, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice));
+  DevParams &P = h->P;
+  P.lj.cutsq = h->d_coeff.p;
+  P.lj.cut_ljsq = h->d_coeff.p + nn;
+  P.lj.lj1 = h->d_coeff.p + 2 * nn;
+  P.lj.lj2 = h->d_coeff.p + 3 * nn;
+  P.lj.lj3 = h->d_coeff.p + 4 * nn;
+  P.lj.lj4 = h->d_coeff.p + 5 * nn;
+  P.lj.offset = h->d_coeff.p + 6 * nn;
+  P.cutneighsq = h->d_coeff.p + 7 * nn;
+
+  const int nt = st.ncoultablebits ? (1 << st.ncoultablebits) : 1;
+  std::vector<double> tb((size_t)8 * nt, 0.0);
+  if (st.ncoultablebits) {
+    const std::vector<double> *ts[8] = {&st.tab.r, &st.tab.dr, &st.tab.f, &st.tab.df,
+                                        &st.tab.c, &st.tab.dc, &st.tab.e, &st.tab.de};
+    for (int k = 0; k < 8; k++) std::copy(ts[k]->begin(), ts[k]->end(), tb.begin() + (size_t)k * nt);
+  }
+  h->d_tables.ensure(tb.size());
+  CUDA_CHECK(cudaMemcpy(h->d_tables.p, tb.data(), tb.size() * sizeof(double), cudaMemcpyHostToDevice));
+  P.tb.r = h->d_tables.p;
+  P.tb.dr = h->d_tables.p + nt;
+  P.tb.f = h->d_tables.p + 2 * nt;
+  P.tb.df = h->d_tables.p + 3 * nt;
+  P.tb.c = h->d_tables.p + 4 * nt;
+  P.tb.dc = h->d_tables.p + 5 * nt;
+  P.tb.e = h->d_tables.p + 6 * nt;
+  P.tb.de = h->d_tables.p + 7 * nt;
+
+  PairConsts &pc = P.pc;
+  pc.cut_coulsq = st.cut_coulsq;
+  pc.f_shift = -1.0 / (st.cut_coul * st.cut_coul);
+  pc.kq = sqrt(st.env.qqrd2e);
+  pc.qqrd2e = st.env.qqrd2e;
+  pc.g_ewald = st.env.g_ewald;
+  pc.polar_damp = st.polar_damp;
+  pc.polar_cutsq = st.polar_cutoff > 0.0 ? st.polar_cutoff * st.polar_cutoff : -1.0;
+  pc.tabinnersq = st.tab.tabinnersq;
+  pc.damping_exponential = st.damping_type == DAMP_EXPONENTIAL;
+  pc.ncoultablebits = st.ncoultablebits;
+  pc.ncoulmask = st.tab.mask;
+  pc.ncoulshiftbits = st.tab.shift;
+  pc.ntypes = st.ntypes;
+  for (int k = 0; k < 4; k++) {
+    pc.special_lj[k] = st.env.special_lj[k];
+    pc.special_coul[k] = st.env.special_coul[k];
+  }
+  h->params_uploaded = true;
+  h->have_lists = false;
+}
+
+// cell grid over the box extended by the ghost cutoff; cells of about half the largest neighbor
+// cutoff, as NBinStandard::setup_bins chooses (src/nbin_standard.cpp:93-99)
+static void setup_grid(polb200_handle *h)
+{
+  const HostStyle &st = h->style;
+  Grid &g = h->P.grid;
+  const double cut = st.cutneighmax;
+  const double binsize = 0.5 * cut;
+  std::vector<int> stencil;
+  int sx[3];
+  double cs[3];
+  long ncell = 1;
+  for (int d = 0; d < 3; d++) {
+    const double ext = h->box.periodic[d] ? cut : 0.0;
+    const double lo = h->box.lo[d] - ext, hi = h->box.hi[d] + ext;
+    // margin: owned atoms may sit up to skin/2 outside the box between rebuilds
+    const double margin = 0.5 * st.env.skin + 1e-9 * (hi - lo);
+    g.lo[d] = lo - margin;
+    const double len = (hi + margin) - g.lo[d];
+    int nc = (int)(len / binsize);
+    if (nc < 1) nc = 1;
+    if (nc > 1024) nc = 1024;
+    g.nc[d] = nc;
+    cs[d] = len / nc;
+    g.inv[d] = 1.0 / cs[d];
+    sx[d] = (int)ceil(cut / cs[d]);
+    if (sx[d] > 15) throw StyleError{POLB200_ERR_UNSUPPORTED, "neighbor stencil too wide"};
+    ncell *= nc;
+  }
+  if (ncell > (1l << 30)) throw StyleError{POLB200_ERR_UNSUPPORTED, "Too many neighbor bins"};
+  g.ncell = (int)ncell;
+  // full stencil pruned by the closest distance between cells (cf. NStencil::bin_distance,
+  // src/nstencil.cpp:205-223); order: z, y, x ascending
+  for (int k = -sx[2]; k <= sx[2]; k++)
+    for (int j = -sx[1]; j <= sx[1]; j++)
+      for (int i = -sx[0]; i <= sx[0]; i++) {
+        auto gap = [](int o, double c) { return o > 0 ? (o - 1) * c : (o < 0 ? (o + 1) * c : 0.0); };
+        const double dx = gap(i, cs[0]), dy = gap(j, cs[1]), dz = gap(k, cs[2]);
+        if (dx * dx + dy * dy + dz * dz <= cut * cut)
+          stencil.push_back((i + 16) | ((j + 16) << 6) | ((k + 16) << 12));
+      }
+  h->nstencil = (int)stencil.size();
+  h->stencil.ensure(stencil.size());
+  CUDA_CHECK(cudaMemcpy(h->stencil.p, stencil.data(), stencil.size() * sizeof(int), cudaMemcpyHostToDevice));
+}
+
+static void sort_pairs(polb200_handle *h, int n, const int *kin, int *kout, const int *vin, int *vout, int endbit)
+{
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, n, 0, endbit, h->stream);
+  h->cub_tmp.ensure(bytes);
+  CUDA_CHECK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, bytes, kin, kout, vin, vout, n, 0, endbit, h->stream));
+  h->launches += 3;
+}
+
+static void exclusive_sum(polb200_handle *h, int n, const unsigned long long *in, unsigned long long *out)
+{
+  size_t bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, n, h->stream);
+  h->cub_tmp.ensure(bytes);
+  CUDA_CHECK(cub::DeviceScan::ExclusiveSum(h->cub_tmp.p, bytes, in, out, n, h->stream));
+  h->launches += 2;
+}
+
+static int bits_for(int n)
+{
+  int b = 1;
+  while ((1l << b) < n) b++;
+  return b;
+}
+
+// ---- host <-> device staging of the caller's arrays ----------------------------------------------------
+template <class T>
+static void stage_in(polb200_handle *h, DBuf<T> &dst, const T *src, size_t n, bool on_device)
+{
+  dst.ensure(n);
+  if (!src || n == 0) return;
+  CUDA_CHECK(cudaMemcpyAsync(dst.p, src, n * sizeof(T), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                             h->stream));
+}
+
+static void rebuild(polb200_handle *h, const polb200_atoms *at)
+{
+  const HostStyle &st = h->style;
+  const int n = at->nlocal;
+  const bool dev = at->on_device != 0;
+  setup_grid(h);
+  const Grid &g = h->P.grid;
+
+  // static per-atom attributes (positions and dipoles were staged by the caller of rebuild)
+  stage_in(h, h->c_q, at->q, n, dev);
+  stage_in(h, h->c_type, at->type, n, dev);
+  stage_in(h, h->c_alpha, at->alpha, n, dev);
+  if (at->molecule) stage_in(h, h->c_mol, at->molecule, n, dev);
+  if (at->tag) stage_in(h, h->c_tag, at->tag, n, dev);
+  h->molecular = at->nspecial && at->special && at->maxspecial > 0;
+  h->maxspecial = h->molecular ? at->maxspecial : 0;
+
+  // 1. cell-sort the owned atoms
+  h->keys.ensure(n); h->keys2.ensure(n); h->vals.ensure(n); h->vals2.ensure(n);
+  h->flags.ensure(4);
+  CUDA_CHECK(cudaMemsetAsync(h->flags.p, 0, 4 * sizeof(int), h->stream));
+  LAUNCH(h, k_local_keys, cdiv(n, 256), 256, n, h->c_x.p, g, h->keys.p, h->vals.p, h->flags.p);
+  sort_pairs(h, n, h->keys.p, h->keys2.p, h->vals.p, h->vals2.p, bits_for(g.ncell + 1));
+  h->perm.ensure(n); h->invperm.ensure(n);
+  CUDA_CHECK(cudaMemcpyAsync(h->perm.p, h->vals2.p, n * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+  h->cl_start.ensure(g.ncell + 2);
+  LAUNCH(h, k_cell_starts, cdiv(g.ncell + 1, 256), 256, g.ncell, n, h->keys2.p, h->cl_start.p);
+
+  // capacity guess for ext arrays: grown after the ghost count is known
+  h->xq.ensure(n); h->mua.ensure(n); h->mub.ensure(n); h->tm.ensure(n); h->tag.ensure(n);
+  LAUNCH(h, k_gather_local, cdiv(n, 256), 256, n, h->perm.p, h->c_x.p, h->c_q.p, h->c_type.p,
+         at->molecule ? h->c_mol.p : nullptr, at->tag ? h->c_tag.p : nullptr, h->c_alpha.p, h->c_mu.p,
+         h->xq.p, h->mua.p, h->tm.p, h->tag.p, h->invperm.p);
+
+  // 2. ghosts = periodic images inside the shell of width cutneighmax
+  h->cnt.ensure(n + 1); h->rowstart.ensure(n + 2);
+  LAUNCH(h, k_ghost_count, cdiv(n, 256), 256, n, h->xq.p, h->box, st.cutneighmax, h->cnt.p);
+  CUDA_CHECK(cudaMemsetAsync(h->cnt.p + n, 0, sizeof(unsigned long long), h->stream));
+  exclusive_sum(h, n + 1, h->cnt.p, h->rowstart.p);
+  h->h_int.ensure(8);
+  unsigned long long ng64 = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&ng64, h->rowstart.p + n, sizeof(ng64), cudaMemcpyDeviceToHost, h->stream));
+  int hflags[4];
+  CUDA_CHECK(cudaMemcpyAsync(hflags, h->flags.p, sizeof(hflags), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  if (hflags[0] & 1) throw StyleError{POLB200_ERR_NAN, "Non-numeric positions - simulation unstable"};
+  if (ng64 + (unsigned long long)n >= (1ull << 30))
+    throw StyleError{POLB200_ERR_OVERFLOW, "owned+ghost atoms exceed the 30-bit neighbor index"};
+  const int ng = (int)ng64;
+  h->nghost = ng;
+  const size_t next = (size_t)n + ng;
+  if (ng > 0) {
+    h->g_owner_u.ensure(ng); h->g_shift_u.ensure(ng); h->g_owner.ensure(ng); h->g_shift.ensure(ng);
+    h->keys.ensure(std::max(n, ng)); h->keys2.ensure(std::max(n, ng));
+    h->vals.ensure(std::max(n, ng)); h->vals2.ensure(std::max(n, ng));
+    LAUNCH(h, k_ghost_fill, cdiv(n, 256), 256, n, h->xq.p, h->box, st.cutneighmax, g, h->rowstart.p,
+           h->g_owner_u.p, h->g_shift_u.p, h->keys.p, h->vals.p);
+    sort_pairs(h, ng, h->keys.p, h->keys2.p, h->vals.p, h->vals2.p, bits_for(g.ncell + 1));
+  }
+  // grow ext arrays, preserving the owned part
+  auto grow = [&](auto &buf) {
+    using T = typename std::remove_reference<decltype(*buf.p)>::type;
+    if (buf.cap >= next) return;
+    DBuf<T> nb;
+    nb.ensure(next);
+    CUDA_CHECK(cudaMemcpyAsync(nb.p, buf.p, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    buf.release();
+    buf = nb;
+  };
+  grow(h->xq); grow(h->mua); grow(h->tm); grow(h->tag);
+  h->mub.ensure(next);
+  h->cg_start.ensure(g.ncell + 2);
+  if (ng > 0) {
+    LAUNCH(h, k_ghost_gather, cdiv(ng, 256), 256, ng, n, h->vals2.p, h->g_owner_u.p, h->g_shift_u.p, h->box,
+           h->xq.p, h->mua.p, h->tm.p, h->tag.p, h->g_owner.p, h->g_shift.p);
+    LAUNCH(h, k_cell_starts, cdiv(g.ncell + 1, 256), 256, g.ncell, ng, h->keys2.p, h->cg_start.p);
+  } else {
+    CUDA_CHECK(cudaMemsetAsync(h->cg_start.p, 0, (g.ncell + 2) * sizeof(int), h->stream));
+  }
+
+  // special-bond lists in sorted order (tags)
+  const int *d_nspecial = nullptr, *d_special = nullptr;
+  if (h->molecular) {
+    stage_in(h, h->c_nspecial, at->nspecial, (size_t)3 * n, dev);
+    stage_in(h, h->c_special, at->special, (size_t)n * at->maxspecial, dev);
+    h->s_nspecial.ensure((size_t)3 * n);
+    h->s_special.ensure((size_t)n * at->maxspecial);
+    LAUNCH(h, k_gather_rows, cdiv((long)n * 3, 256), 256, n, 3, h->perm.p, h->c_nspecial.p, h->s_nspecial.p);
+    LAUNCH(h, k_gather_rows, cdiv((long)n * at->maxspecial, 256), 256, n, at->maxspecial, h->perm.p,
+           h->c_special.p, h->s_special.p);
+    d_nspecial = h->s_nspecial.p;
+    d_special = h->s_special.p;
+  }
+
+  // 3. neighbor list: count, scan, fill
+  LAUNCH(h, k_neigh_build<false>, cdiv(n, WARPS_PER_BLOCK), BLOCK, n, h->P, h->xq.p, h->tm.p, h->tag.p,
+         h->cl_start.p, h->cg_start.p, h->nstencil, h->stencil.p, d_nspecial, d_special, h->maxspecial,
+         h->cnt.p, (const unsigned long long *)nullptr, (int *)nullptr);
+  CUDA_CHECK(cudaMemsetAsync(h->cnt.p + n, 0, sizeof(unsigned long long), h->stream));
+  exclusive_sum(h, n + 1, h->cnt.p, h->rowstart.p);
+  unsigned long long np = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&np, h->rowstart.p + n, sizeof(np), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  h->npairs = np;
+  h->neigh.ensure(np + 32);
+  LAUNCH(h, k_neigh_build<true>, cdiv(n, WARPS_PER_BLOCK), BLOCK, n, h->P, h->xq.p, h->tm.p, h->tag.p,
+         h->cl_start.p, h->cg_start.p, h->nstencil, h->stencil.p, d_nspecial, d_special, h->maxspecial,
+         h->cnt.p, h->rowstart.p, h->neigh.p);
+
+  // remember positions for the displacement trigger (Neighbor::build: xhold, src/neighbor.cpp:2032-2044)
+  h->c_xhold.ensure((size_t)3 * n);
+  CUDA_CHECK(cudaMemcpyAsync(h->c_xhold.p, h->c_x.p, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToDevice,
+                             h->stream));
+  h->nloc = n;
+  h->have_lists = true;
+  h->ago_internal = 0;
+}
+
+// Neighbor::decide (src/neighbor.cpp:1923-1937) for callers that pass ago < 0
+static bool decide_rebuild(polb200_handle *h, int n)
+{
+  if (!h->have_lists || n != h->nloc) return true;
+  const polb200_env &e = h->style.env;
+  h->ago_internal++;
+  const int every = e.neigh_every > 0 ? e.neigh_every : 1;
+  if (h->ago_internal >= e.neigh_delay && h->ago_internal % every == 0) {
+    if (!e.neigh_check) return true;
+    const double trig = 0.25 * e.skin * e.skin;  // triggersq = (skin/2)^2
+    CUDA_CHECK(cudaMemsetAsync(h->flags.p + 1, 0, sizeof(int), h->stream));
+    LAUNCH(h, k_check_distance, cdiv(n, 256), 256, n, h->c_x.p, h->c_xhold.p, trig, h->flags.p + 1);
+    int flag = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&flag, h->flags.p + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    return flag != 0;
+  }
+  return false;
+}
+
+template <int NV>
+static void reduce_partials(polb200_handle *h, int nblocks, double *out, int accumulate)
+{
+  LAUNCH(h, k_reduce_partials<NV>, 1, 256, nblocks, h->partial.p, out, accumulate);
+}
+
+// scal layout (device doubles): 0..7 pair partial sums, 8..16 polarization sums, 17 change, 18 rmin
+enum { S_PAIR = 0, S_POL = 8, S_CHANGE = 17, S_N = 24 };
+
+static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, int vflag, int ago,
+                         polb200_result *out)
+{
+  HostStyle &st = h->style;
+  if (!st.initialized) throw StyleError{POLB200_ERR_STATE, "polb200_init has not been called"};
+  if (!h->params_uploaded) upload_params(h);
+  if (!h->box_set) throw StyleError{POLB200_ERR_STATE, "polb200_set_box has not been called"};
+  if ((eflag / 2) || (vflag / 4))
+    throw StyleError{POLB200_ERR_UNSUPPORTED, "per-atom energy/virial tallies are not implemented on the B200 path"};
+  const int n = at->nlocal;
+  memset(out, 0, sizeof(*out));
+  if (n <= 0) return;
+  const bool dev = at->on_device != 0;
+  const bool list_mode = st.polar_cutoff > 0.0;
+  for (int d = 0; d < 3; d++) {
+    if (!h->box.periodic[d]) continue;
+    if (st.cutneighmax > h->box.prd[d])
+      throw StyleError{POLB200_ERR_UNSUPPORTED, "neighbor cutoff exceeds the periodic box length"};
+    if (list_mode && (st.polar_cutoff > h->box.half[d] || st.cut_coul > h->box.half[d]))
+      throw StyleError{POLB200_ERR_UNSUPPORTED,
+                       "polar_cutoff (list) mode needs polar_cutoff and cut_coul <= half the box length"};
+  }
+  if (list_mode && st.polar_cutoff > st.cutforce)
+    throw StyleError{POLB200_ERR_UNSUPPORTED, "polar_cutoff must not exceed the largest pair cutoff"};
+
+  const int eflag_global = eflag & 1;
+  int vflag_global = vflag % 4;
+  const bool evflag = eflag_global || vflag_global;
+  const bool vpair = vflag_global == 1;  // pairwise tallies; 2 = F.r (src/pair.cpp:809-815)
+
+  CUDA_CHECK(cudaEventRecord(h->ev[0], h->stream));
+  // ---- inputs of this step ----
+  stage_in(h, h->c_x, at->x, (size_t)3 * n, dev);
+  stage_in(h, h->c_mu, at->mu, (size_t)3 * n, dev);
+  bool need = (ago == 0) || !h->have_lists || n != h->nloc;
+  if (ago < 0) need = decide_rebuild(h, n);
+  if (need) rebuild(h, at);
+  else {
+    LAUNCH(h, k_refresh_local, cdiv(n, 256), 256, n, h->perm.p, h->c_x.p, h->c_mu.p, h->xq.p, h->mua.p);
+    if (h->nghost)
+      LAUNCH(h, (k_ghost_refresh<true, true>), cdiv(h->nghost, 256), 256, h->nghost, n, h->g_owner.p,
+             h->g_shift.p, h->box, h->xq.p, h->mua.p);
+  }
+  const int ng = h->nghost;
+  const int nrowblocks = cdiv(n, WARPS_PER_BLOCK);
+  h->ef.ensure(n); h->f_pair.ensure(n); h->f_pol.ensure(n);
+  h->partial.ensure((size_t)nrowblocks * 16 + 64);
+  h->scal.ensure(S_N);
+  h->h_scal.ensure(S_N);
+  CUDA_CHECK(cudaMemsetAsync(h->scal.p, 0, S_N * sizeof(double), h->stream));
+  CUDA_CHECK(cudaEventRecord(h->ev[1], h->stream));
+
+  const DevParams &P = h->P;
+  ListRows L{h->rowstart.p, h->neigh.p};
+  AllPairRows A{n, h->perm.p};
+
+  // ---- stage 2: LJ + Coulomb (+ static field) ----
+  if (list_mode) {
+    if (evflag) LAUNCH(h, (k_pair<true, true>), nrowblocks, BLOCK, n, P, h->xq.p, h->tm.p, L.rowstart, L.neigh, h->f_pair.p, h->ef.p, h->partial.p);
+    else LAUNCH(h, (k_pair<false, true>), nrowblocks, BLOCK, n, P, h->xq.p, h->tm.p, L.rowstart, L.neigh, h->f_pair.p, h->ef.p, h->partial.p);
+  } else {
+    if (evflag) LAUNCH(h, (k_pair<true, false>), nrowblocks, BLOCK, n, P, h->xq.p, h->tm.p, L.rowstart, L.neigh, h->f_pair.p, h->ef.p, h->partial.p);
+    else LAUNCH(h, (k_pair<false, false>), nrowblocks, BLOCK, n, P, h->xq.p, h->tm.p, L.rowstart, L.neigh, h->f_pair.p, h->ef.p, h->partial.p);
+  }
+  if (evflag) reduce_partials<NPAIR_PART>(h, nrowblocks, h->scal.p + S_PAIR, 0);
+  if (!list_mode) LAUNCH(h, k_static_allpairs, nrowblocks, BLOCK, n, P, h->xq.p, h->tm.p, h->perm.p, h->ef.p);
+  if (!st.use_previous) LAUNCH(h, k_init_mu, cdiv(n, 256), 256, n, st.polar_gamma, h->ef.p, h->mua.p);
+  if (ng) LAUNCH(h, (k_ghost_refresh<false, true>), cdiv(ng, 256), 256, ng, n, h->g_owner.p, h->g_shift.p, h->box, h->xq.p, h->mua.p);
+  CUDA_CHECK(cudaEventRecord(h->ev[2], h->stream));
+
+  // ---- stage 3: self-consistent dipoles (DipoleSolverIterative, pol.cpp:1113-1238) ----
+  int iterations = 0;
+  bool diverged = false;
+  double rmin = 0.0;
+  if (!st.zodid) {
+    const bool gs = st.polar_gs || st.polar_gs_ranked;
+    const int *order = nullptr;
+    if (st.polar_gs_ranked) {
+      // rank metric + stable descending sort, ties by caller index (pol.cpp:192-227,1127-1143)
+      h->rmin_bits.ensure(1);
+      h->metric.ensure(n); h->metric2.ensure(n); h->ranked.ensure(n); h->ranked_in.ensure(n);
+      const unsigned long long init = (unsigned long long)0x408F400000000000ull;  // bits of 1000.0
+      CUDA_CHECK(cudaMemcpyAsync(h->rmin_bits.p, &init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+      LAUNCH(h, k_rmin, nrowblocks, BLOCK, n, L, h->xq.p, h->mua.p, h->tm.p, h->rmin_bits.p);
+      LAUNCH(h, k_rank_metric, nrowblocks, BLOCK, n, L, h->xq.p, h->mua.p, h->tm.p, h->rmin_bits.p, h->perm.p, h->metric.p);
+      // values in caller order = sorted index of caller atom c
+      size_t bytes = 0;
+      cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, h->metric.p, h->metric2.p, h->invperm.p, h->ranked.p, n, 0, 64, h->stream);
+      h->cub_tmp.ensure(bytes);
+      CUDA_CHECK(cub::DeviceRadixSort::SortPairsDescending(h->cub_tmp.p, bytes, h->metric.p, h->metric2.p, h->invperm.p, h->ranked.p, n, 0, 64, h->stream));
+      h->launches += 3;
+      order = h->ranked.p;
+      unsigned long long rb = 0;
+      CUDA_CHECK(cudaMemcpyAsync(&rb, h->rmin_bits.p, sizeof(rb), cudaMemcpyDeviceToHost, h->stream));
+      CUDA_CHECK(cudaStreamSynchronize(h->stream));
+      memcpy(&rmin, &rb, sizeof(double));
+    }
+    // which sweep realisation
+    int nchunks = 0;          // 0: Jacobi (one block of rows, separate output array)
+    bool sequential = false;  // reference-exact Gauss-Seidel (all-pairs mode only)
+    if (gs) {
+      if (st.gs_chunks > 0) nchunks = st.gs_chunks;
+      else if (list_mode) nchunks = 8;
+      else sequential = true;
+    }
+    double4 *cur = h->mua.p, *nxt = h->mub.p;
+    const double prec2 = st.polar_precision * st.polar_precision;
+    bool keep = true;
+    while (keep) {
+      double change = 0.0;
+      const bool want_change = !st.fixed_iteration;
+      if (sequential) {
+        LAUNCH(h, k_gs_sequential, 1, GS_THREADS, n, order, P, h->perm.p, h->xq.p, cur, h->ef.p, h->scal.p + S_CHANGE);
+      } else if (!gs) {
+        // Jacobi in fixed mode: the reference runs max_iterations+1 sweeps and discards the last
+        // (pol.cpp:1214 returns before the copy), so only max_iterations sweeps shape the result
+        if (st.fixed_iteration && iterations >= st.iterations_max) break;
+        if (list_mode) LAUNCH(h, (k_sweep<true>), nrowblocks, BLOCK, 0, n, order, P, L, A, h->xq.p, cur, h->ef.p, nxt, h->partial.p);
+        else LAUNCH(h, (k_sweep<false>), nrowblocks, BLOCK, 0, n, order, P, L, A, h->xq.p, cur, h->ef.p, nxt, h->partial.p);
+        if (want_change) reduce_partials<1>(h, nrowblocks, h->scal.p + S_CHANGE, 0);
+        if (ng) LAUNCH(h, (k_ghost_refresh<false, true>), cdiv(ng, 256), 256, ng, n, h->g_owner.p, h->g_shift.p, h->box, h->xq.p, nxt);
+      } else {
+        // ranked colouring sweep: chunks of the ranked order, Jacobi inside, Gauss-Seidel between
+        for (int c = 0; c < nchunks; c++) {
+          const int beg = (int)(((long)c * n) / nchunks), end = (int)(((long)(c + 1) * n) / nchunks);
+          if (end <= beg) continue;
+          const int nb = cdiv(end - beg, WARPS_PER_BLOCK);
+          if (list_mode) LAUNCH(h, (k_sweep<true>), nb, BLOCK, beg, end, order, P, L, A, h->xq.p, cur, h->ef.p, nxt, h->partial.p);
+          else LAUNCH(h, (k_sweep<false>), nb, BLOCK, beg, end, order, P, L, A, h->xq.p, cur, h->ef.p, nxt, h->partial.p);
+          if (want_change) reduce_partials<1>(h, nb, h->scal.p + S_CHANGE, c > 0);
+          LAUNCH(h, k_commit_rows, cdiv(end - beg, 256), 256, beg, end, order, nxt, cur);
+          if (ng) LAUNCH(h, (k_ghost_refresh<false, true>), cdiv(ng, 256), 256, ng, n, h->g_owner.p, h->g_shift.p, h->box, h->xq.p, cur);
+        }
+      }
+      if (want_change) {
+        CUDA_CHECK(cudaMemcpyAsync(h->h_scal.p + S_CHANGE, h->scal.p + S_CHANGE, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        change = h->h_scal.p[S_CHANGE] / ((double)n * 3.0);
+        keep = change > prec2;  // pol.cpp:1205-1209
+      } else if (iterations >= st.iterations_max) {
+        break;  // Gauss-Seidel fixed mode: the in-place writes of this last sweep stay
+      }
+      if (!gs) std::swap(cur, nxt);  // "save the dipoles for the next pass" (pol.cpp:1218-1222)
+      iterations++;
+      if (iterations > st.iterations_max) {  // pol.cpp:1227-1235
+        LAUNCH(h, k_reset_mu, cdiv(n, 256), 256, n, h->ef.p, cur);
+        diverged = true;
+        break;
+      }
+    }
+    if (cur != h->mua.p) {  // keep the canonical buffer
+      CUDA_CHECK(cudaMemcpyAsync(h->mua.p, cur, (size_t)n * sizeof(double4), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    if (ng) LAUNCH(h, (k_ghost_refresh<false, true>), cdiv(ng, 256), 256, ng, n, h->g_owner.p, h->g_shift.p, h->box, h->xq.p, h->mua.p);
+  }
+  CUDA_CHECK(cudaEventRecord(h->ev[3], h->stream));
+
+  // ---- stage 4: polarization forces ----
+#define POLFORCE(LISTM, EV, VP) \
+  LAUNCH(h, (k_polforce<LISTM, EV, VP>), nrowblocks, BLOCK, n, P, L, A, h->xq.p, h->mua.p, h->tm.p, h->f_pol.p, h->partial.p)
+  // the reference tallies polarization energies whenever eflag is set, virial via F.r or pairwise
+  const bool ev4 = evflag;
+  if (list_mode) {
+    if (!ev4) POLFORCE(true, false, false);
+    else if (vpair) POLFORCE(true, true, true);
+    else POLFORCE(true, true, false);
+  } else {
+    if (!ev4) POLFORCE(false, false, false);
+    else if (vpair) POLFORCE(false, true, true);
+    else POLFORCE(false, true, false);
+  }
+  if (ev4) reduce_partials<NPOL_PART>(h, nrowblocks, h->scal.p + S_POL, 0);
+
+  // ---- stage 5: outputs ----
+  h->c_f.ensure((size_t)3 * n); h->c_ef.ensure((size_t)3 * n);
+  LAUNCH(h, k_scatter_out, cdiv(n, 256), 256, n, h->perm.p, h->f_pair.p, h->f_pol.p, h->mua.p, h->ef.p, h->c_f.p,
+         h->c_mu.p, h->c_ef.p);
+  CUDA_CHECK(cudaEventRecord(h->ev[4], h->stream));
+  CUDA_CHECK(cudaMemcpyAsync(h->h_scal.p, h->scal.p, S_N * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (dev) {
+    // device-resident caller: f += pair force, mu/ef overwritten, all on the stream
+    LAUNCH(h, k_add_inplace, cdiv((long)3 * n, 256), 256, (long)3 * n, h->c_f.p, at->f);
+    CUDA_CHECK(cudaMemcpyAsync(at->mu, h->c_mu.p, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if (at->ef_static)
+      CUDA_CHECK(cudaMemcpyAsync(at->ef_static, h->c_ef.p, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CUDA_CHECK(cudaEventRecord(h->ev[5], h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  } else {
+    h->h_stage.ensure((size_t)3 * n);
+    CUDA_CHECK(cudaMemcpyAsync(h->h_stage.p, h->c_f.p, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaMemcpyAsync(at->mu, h->c_mu.p, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (at->ef_static)
+      CUDA_CHECK(cudaMemcpyAsync(at->ef_static, h->c_ef.p, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaEventRecord(h->ev[5], h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    double *f = at->f;
+    const double *a = h->h_stage.p;
+    for (size_t k = 0; k < (size_t)3 * n; k++) f[k] += a[k];
+  }
+
+  const double *sc = h->h_scal.p;
+  if (eflag_global) {
+    out->eng_vdwl = sc[S_PAIR + 0];
+    out->eng_coul = sc[S_PAIR + 1];
+  }
+  if (evflag) {
+    // u_polar is assigned to eng_pol unconditionally (pol.cpp:632,641); its pieces are only
+    // accumulated under eflag (pol.cpp:432,476,499,538)
+    if (eflag) {
+      out->u_self = sc[S_POL + 0];
+      out->u_ef = sc[S_POL + 1];
+      out->u_dd = sc[S_POL + 2];
+    }
+    out->eng_pol = out->u_self + out->u_ef + out->u_dd;
+    if (vflag_global)
+      for (int k = 0; k < 6; k++) out->virial[k] = sc[S_PAIR + 2 + k] + sc[S_POL + 3 + k];
+  }
+  out->iterations = iterations;
+  out->rmin = rmin;
+  out->status = (diverged ? POLB200_STATUS_DIVERGED : 0) | (need ? POLB200_STATUS_REBUILT : 0) |
+                (list_mode ? 0 : POLB200_STATUS_EXACT);
+  out->npairs_full = (long)h->npairs;
+  out->nghost = ng;
+  cudaEventElapsedTime(&out->ms_neigh, h->ev[0], h->ev[1]);
+  cudaEventElapsedTime(&out->ms_pair, h->ev[1], h->ev[2]);
+  cudaEventElapsedTime(&out->ms_scf, h->ev[2], h->ev[3]);
+  cudaEventElapsedTime(&out->ms_force, h->ev[3], h->ev[4]);
+  cudaEventElapsedTime(&out->ms_total, h->ev[0], h->ev[5]);
+}
+
+}  // namespace polb200
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+
+template <class F>
+static int guarded(polb200_t *h, F &&fn)
+{
+  try {
+    fn();
+    return POLB200_OK;
+  } catch (const StyleError &e) {
+    if (h) h->err = e.msg;
+    return e.code;
+  } catch (const CudaError &e) {
+    if (h) h->err = e.msg;
+    return POLB200_ERR_CUDA;
+  } catch (const std::exception &e) {
+    if (h) h->err = e.what();
+    return POLB200_ERR_ARG;
+  }
+}
+
+extern "C" {
+
+int polb200_abi_version(void) { return POLB200_ABI_VERSION; }
+
+int polb200_create(polb200_t **out, int device)
+{
+  if (!out) return POLB200_ERR_ARG;
+  *out = nullptr;
+  if (device == POLB200_DEVICE_NONE) {  // configuration-only handle: every device entry point fails loudly
+    polb200_t *hh = new polb200_handle();
+    hh->device = POLB200_DEVICE_NONE;
+    *out = hh;
+    return POLB200_OK;
+  }
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+    fprintf(stderr, "polb200_create: no usable CUDA device %d (found %d); there is no CPU fallback\n", device, count);
+    return POLB200_ERR_CUDA;
+  }
+  polb200_t *h = new polb200_handle();
+  h->device = device;
+  int rc = guarded(h, [&] {
+    CUDA_CHECK(cudaSetDevice(device));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (auto &e : h->ev) CUDA_CHECK(cudaEventCreate(&e));
+  });
+  if (rc) {
+    fprintf(stderr, "polb200_create: %s\n", h->err.c_str());
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return POLB200_OK;
+}
+
+void polb200_destroy(polb200_t *h)
+{
+  if (!h) return;
+  if (h->device == POLB200_DEVICE_NONE) {
+    delete h;
+    return;
+  }
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (auto *b : {&h->c_x, &h->c_q, &h->c_alpha, &h->c_mu, &h->c_f, &h->c_ef, &h->c_xhold, &h->d_coeff,
+                  &h->d_tables, &h->partial, &h->scal, &h->metric, &h->metric2})
+    b->release();
+  for (auto *b : {&h->c_type, &h->c_mol, &h->c_tag, &h->c_nspecial, &h->c_special, &h->tag, &h->perm,
+                  &h->invperm, &h->keys, &h->keys2, &h->vals, &h->vals2, &h->g_owner_u, &h->g_shift_u,
+                  &h->g_owner, &h->g_shift, &h->cl_start, &h->cg_start, &h->stencil, &h->s_nspecial,
+                  &h->s_special, &h->neigh, &h->flags, &h->ranked, &h->ranked_in})
+    b->release();
+  for (auto *b : {&h->xq, &h->mua, &h->mub, &h->ef, &h->f_pair, &h->f_pol}) b->release();
+  h->tm.release(); h->cnt.release(); h->rowstart.release(); h->cub_tmp.release(); h->rmin_bits.release();
+  h->h_stage.release(); h->h_scal.release(); h->h_int.release();
+  for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char *polb200_last_error(const polb200_t *h) { return h ? h->err.c_str() : "null handle"; }
+
+int polb200_settings(polb200_t *h, int narg, const char *const *arg)
+{
+  if (!h) return POLB200_ERR_ARG;
+  return guarded(h, [&] { h->style.settings(narg, arg); h->params_uploaded = false; });
+}
+
+int polb200_set_ntypes(polb200_t *h, int ntypes)
+{
+  if (!h) return POLB200_ERR_ARG;
+  return guarded(h, [&] { h->style.set_ntypes(ntypes); h->params_uploaded = false; });
+}
+
+int polb200_coeff(polb200_t *h, int narg, const char *const *arg)
+{
+  if (!h) return POLB200_ERR_ARG;
+  return guarded(h, [&] { h->style.coeff(narg, arg); h->params_uploaded = false; });
+}
+
+int polb200_pair_modify(polb200_t *h, int narg, const char *const *arg)
+{
+  if (!h) return POLB200_ERR_ARG;
+  return guarded(h, [&] { h->style.pair_modify(narg, arg); h->params_uploaded = false; });
+}
+
+int polb200_init(polb200_t *h, const polb200_env *env)
+{
+  if (!h || !env) return POLB200_ERR_ARG;
+  return guarded(h, [&] {
+    h->style.init(*env);
+    h->params_uploaded = false;  // device copies are refreshed by the next compute()
+  });
+}
+
+int polb200_init_one(const polb200_t *h, int i, int j, double *cut)
+{
+  if (!h || !cut || !h->style.initialized || i < 1 || j < 1 || i > h->style.ntypes || j > h->style.ntypes)
+    return POLB200_ERR_ARG;
+  *cut = h->style.cut_pair[h->style.idx(i, j)];
+  return POLB200_OK;
+}
+
+const void *polb200_extract(const polb200_t *h, const char *name, int *dim)
+{
+  if (!h || !name || !dim) return nullptr;
+  *dim = 0;
+  if (!strcmp(name, "cut_coul")) return &h->style.cut_coul;
+  *dim = 2;
+  if (!strcmp(name, "epsilon")) return h->style.epsilon.data();
+  if (!strcmp(name, "sigma")) return h->style.sigma.data();
+  return nullptr;
+}
+
+int polb200_single(const polb200_t *h, int itype, int jtype, double qi, double qj, double rsq,
+                   double factor_coul, double factor_lj, double *fforce, double *eng)
+{
+  if (!h || !fforce || !eng || !h->style.initialized) return POLB200_ERR_STATE;
+  if (itype < 1 || jtype < 1 || itype > h->style.ntypes || jtype > h->style.ntypes) return POLB200_ERR_ARG;
+  *eng = h->style.single(itype, jtype, qi, qj, rsq, factor_coul, factor_lj, *fforce);
+  return POLB200_OK;
+}
+
+int polb200_restart_size(const polb200_t *h, long *nbytes)
+{
+  if (!h || !nbytes) return POLB200_ERR_ARG;
+  *nbytes = (long)h->style.restart_image().size();
+  return POLB200_OK;
+}
+
+int polb200_write_restart(const polb200_t *h, void *buf, long nbytes)
+{
+  if (!h || !buf) return POLB200_ERR_ARG;
+  std::vector<char> img = h->style.restart_image();
+  if ((long)img.size() > nbytes) return POLB200_ERR_ARG;
+  memcpy(buf, img.data(), img.size());
+  return POLB200_OK;
+}
+
+int polb200_read_restart(polb200_t *h, const void *buf, long nbytes)
+{
+  if (!h || !buf) return POLB200_ERR_ARG;
+  return guarded(h, [&] { h->style.read_restart_image(buf, nbytes); h->params_uploaded = false; });
+}
+
+int polb200_set_box(polb200_t *h, const double boxlo[3], const double boxhi[3], const int periodic[3])
+{
+  if (!h || !boxlo || !boxhi || !periodic) return POLB200_ERR_ARG;
+  return guarded(h, [&] {
+    bool changed = !h->box_set;
+    for (int d = 0; d < 3; d++) {
+      if (!(boxhi[d] > boxlo[d])) throw StyleError{POLB200_ERR_ARG, "Box bounds are invalid"};
+      changed = changed || h->box.lo[d] != boxlo[d] || h->box.hi[d] != boxhi[d] || h->box.periodic[d] != periodic[d];
+      h->box.lo[d] = boxlo[d];
+      h->box.hi[d] = boxhi[d];
+      h->box.prd[d] = boxhi[d] - boxlo[d];
+      h->box.half[d] = 0.5 * h->box.prd[d];
+      h->box.periodic[d] = periodic[d];
+    }
+    h->P.box = h->box;
+    h->box_set = true;
+    if (changed) h->have_lists = false;
+  });
+}
+
+int polb200_compute(polb200_t *h, const polb200_atoms *atoms, int eflag, int vflag, int ago, polb200_result *out)
+{
+  if (!h || !atoms || !out) return POLB200_ERR_ARG;
+  return guarded(h, [&] {
+    if (h->device == POLB200_DEVICE_NONE)
+      throw CudaError{"polb200_compute on a configuration-only handle: a CUDA device is required (no CPU fallback)"};
+    CUDA_CHECK(cudaSetDevice(h->device));
+    compute_impl(h, atoms, eflag, vflag, ago, out);
+  });
+}
+
+long polb200_launch_count(polb200_t *h, int reset)
+{
+  if (!h) return -1;
+  long v = h->launches;
+  if (reset) h->launches = 0;
+  return v;
+}
+
+int polb200_set_option(polb200_t *h, const char *name, double value)
+{
+  if (!h || !name) return POLB200_ERR_ARG;
+  (void)value;
+  h->err = std::string("unknown option ") + name;
+  return POLB200_ERR_ARG;
+}
+
+long polb200_debug_fetch(polb200_t *h, const char *name, void *dst, long capacity_bytes)
+{
+  if (!h || !name || !dst) return -1;
+  long result = -1;
+  {  // host-side tables (no device needed): "h_<name>"
+    const HostStyle &st = h->style;
+    const std::vector<double> *v = nullptr;
+    const struct { const char *n; const std::vector<double> *v; } tabs[] = {
+        {"h_rtable", &st.tab.r}, {"h_drtable", &st.tab.dr}, {"h_ftable", &st.tab.f}, {"h_dftable", &st.tab.df},
+        {"h_ctable", &st.tab.c}, {"h_dctable", &st.tab.dc}, {"h_etable", &st.tab.e}, {"h_detable", &st.tab.de},
+        {"h_cutsq", &st.cutsq}, {"h_cut_ljsq", &st.cut_ljsq}, {"h_lj1", &st.lj1}, {"h_lj2", &st.lj2},
+        {"h_lj3", &st.lj3}, {"h_lj4", &st.lj4}, {"h_offset", &st.offset}, {"h_cutneighsq", &st.cutneighsq}};
+    for (auto &e : tabs)
+      if (!strcmp(name, e.n)) v = e.v;
+    if (v) {
+      if ((long)(v->size() * 8) > capacity_bytes) return -1;
+      memcpy(dst, v->data(), v->size() * 8);
+      return (long)v->size();
+    }
+    if (!strcmp(name, "h_tabmeta")) {  // mask, shift, tabinnersq, cutneighmax
+      if (capacity_bytes < 32) return -1;
+      double m[4] = {(double)st.tab.mask, (double)st.tab.shift, st.tab.tabinnersq, st.cutneighmax};
+      memcpy(dst, m, 32);
+      return 4;
+    }
+  }
+  if (h->device == POLB200_DEVICE_NONE) return -1;
+  guarded(h, [&] {
+    CUDA_CHECK(cudaSetDevice(h->device));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    const int n = h->nloc, ng = h->nghost;
+    auto fetch = [&](const void *src, size_t bytes, long count) {
+      if ((long)bytes > capacity_bytes) throw StyleError{POLB200_ERR_ARG, "debug_fetch: buffer too small"};
+      CUDA_CHECK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+      result = count;
+    };
+    if (!strcmp(name, "perm")) fetch(h->perm.p, (size_t)n * 4, n);
+    else if (!strcmp(name, "ghost_owner")) fetch(h->g_owner.p, (size_t)ng * 4, ng);   // sorted owned index
+    else if (!strcmp(name, "ghost_shift")) fetch(h->g_shift.p, (size_t)ng * 4, ng);   // packed code
+    else if (!strcmp(name, "rowstart")) fetch(h->rowstart.p, (size_t)(n + 1) * 8, n + 1);
+    else if (!strcmp(name, "neigh")) fetch(h->neigh.p, (size_t)h->npairs * 4, (long)h->npairs);
+    else if (!strcmp(name, "xq")) fetch(h->xq.p, (size_t)(n + ng) * 32, (long)(n + ng) * 4);
+    else if (!strcmp(name, "mua")) fetch(h->mua.p, (size_t)(n + ng) * 32, (long)(n + ng) * 4);
+    else if (!strcmp(name, "ef")) fetch(h->ef.p, (size_t)n * 32, (long)n * 4);
+    else if (!strcmp(name, "ranked")) fetch(h->ranked.p, (size_t)n * 4, n);
+    else if (!strcmp(name, "metric")) fetch(h->metric.p, (size_t)n * 8, n);
+    else throw StyleError{POLB200_ERR_ARG, std::string("debug_fetch: unknown array ") + name};
+  });
+  return result;
+}
+
+// ---- multi-GPU entry points: implemented in comm.cu when built with NCCL -------------------------------
+#ifndef POLB200_WITH_NCCL
+int polb200_comm_id_size(void) { return 0; }
+int polb200_comm_create_id(void *) { return POLB200_ERR_UNSUPPORTED; }
+int polb200_comm_init(polb200_t *h, int, int, const void *, const int *)
+{
+  if (h) h->err = "library built without NCCL";
+  return POLB200_ERR_UNSUPPORTED;
+}
+int polb200_subdomain(const polb200_t *h, double sublo[3], double subhi[3])
+{
+  if (!h || !h->box_set) return POLB200_ERR_STATE;
+  for (int d = 0; d < 3; d++) { sublo[d] = h->box.lo[d]; subhi[d] = h->box.hi[d]; }
+  return POLB200_OK;
+}
+#endif
+
+}  // extern "C"

@@ -1,0 +1,859 @@
+// kernels.cuh -- hand-written sm_100a kernels of the five stages (see DESIGN.md §3 for the map).
+//
+// Common shape: one warp per owned atom ("row"), the 32 lanes stride over that atom's neighbours
+// (list mode) or over all owned atoms (all-pairs minimum-image mode = the reference's semantics),
+// per-lane FP64 accumulators, warp-shuffle reduction, fixed-order block/grid reductions so results
+// are bit-reproducible run to run.  Tensor cores are not used: the work is a sparse pairwise
+// gather with ~60-80 FP64 operations per pair, bounded by the FP64 pipe / L2 gathers.
+//
+// HBM layout (cell-sorted SoA of 32-byte records, ghosts after owned atoms):
+//   xq [next] double4 {x,y,z,q}            mua[next] double4 {mu_x,mu_y,mu_z,alpha}
+//   tm [next] int2    {type,molecule}      tag[next] int
+//   neigh: CSR rows (64-bit row offsets) of 32-bit entries  j | special<<30   (src/lmptype.h:58-59)
+#pragma once
+#include <cuda_runtime.h>
+
+#include "pair_math.cuh"
+
+namespace polb200 {
+
+constexpr int WARPS_PER_BLOCK = 8;
+constexpr int BLOCK = WARPS_PER_BLOCK * 32;
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int SBBITS = 30;
+constexpr int NEIGHMASK = 0x3FFFFFFF;
+
+struct Grid {
+  double lo[3];     // origin of the cell grid (box lo - ghost cutoff)
+  double inv[3];    // 1/cell size
+  int nc[3];        // cells per dimension
+  int ncell;
+};
+
+struct DevParams {
+  PairConsts pc;
+  LJCoeffs lj;
+  CoulTablesDev tb;
+  const double *cutneighsq;
+  Box box;
+  Grid grid;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL, v, o);
+  return v;
+}
+
+// 256-bit loads of the 32-byte records (sm_100a: LDG.E.ENL2.256 via the aligned double4 types)
+__device__ __forceinline__ double4 ld4(const double4 *p)
+{
+#if __CUDACC_VER_MAJOR__ >= 13
+  double4_32a v = *reinterpret_cast<const double4_32a *>(p);
+  return make_double4(v.x, v.y, v.z, v.w);
+#else
+  double4 v;
+  asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w)
+               : "l"(p));
+  return v;
+#endif
+}
+
+// same record, but through L2 only (ld.global.cg): for arrays updated in place inside a kernel
+__device__ __forceinline__ double4 ld4_cg(const double4 *p)
+{
+  const double2 *q = reinterpret_cast<const double2 *>(p);
+  double2 a = __ldcg(q), b = __ldcg(q + 1);
+  return make_double4(a.x, a.y, b.x, b.y);
+}
+
+__device__ __forceinline__ int cell_of(const Grid &g, double x, double y, double z, int &cx, int &cy, int &cz)
+{
+  cx = (int)floor((x - g.lo[0]) * g.inv[0]);
+  cy = (int)floor((y - g.lo[1]) * g.inv[1]);
+  cz = (int)floor((z - g.lo[2]) * g.inv[2]);
+  cx = min(max(cx, 0), g.nc[0] - 1);
+  cy = min(max(cy, 0), g.nc[1] - 1);
+  cz = min(max(cz, 0), g.nc[2] - 1);
+  return (cz * g.nc[1] + cy) * g.nc[0] + cx;
+}
+
+// block-level fixed-order reduction of NV per-warp values; lane 0 of each warp holds its value.
+// Thread 0 returns with the block total in out[0..NV).
+template <int NV>
+__device__ __forceinline__ void block_reduce_store(double (&v)[NV], double *block_out)
+{
+  __shared__ double sm[WARPS_PER_BLOCK][NV];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0)
+    for (int k = 0; k < NV; k++) sm[warp][k] = v[k];
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double s = 0.0;
+    for (int w = 0; w < WARPS_PER_BLOCK; w++) s += sm[w][threadIdx.x];
+    block_out[(size_t)blockIdx.x * NV + threadIdx.x] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// stage 1: binning, ghosts, neighbor list
+// ---------------------------------------------------------------------------------------------------
+
+// cell key of every owned atom (caller order) + NaN check (src/nbin.cpp:120-121)
+__global__ void k_local_keys(int n, const double *__restrict__ x, Grid g, int *__restrict__ key,
+                             int *__restrict__ iota, int *__restrict__ errflag)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a = x[3 * i], b = x[3 * i + 1], c = x[3 * i + 2];
+  if (!isfinite(a) || !isfinite(b) || !isfinite(c)) {
+    atomicOr(errflag, 1);
+    a = b = c = 0.0;
+  }
+  int cx, cy, cz;
+  key[i] = cell_of(g, a, b, c, cx, cy, cz);
+  iota[i] = i;
+}
+
+// gather caller-order attributes into cell-sorted records (owned part of the ext arrays)
+__global__ void k_gather_local(int n, const int *__restrict__ perm, const double *__restrict__ x,
+                               const double *__restrict__ q, const int *__restrict__ type,
+                               const int *__restrict__ mol, const int *__restrict__ tag,
+                               const double *__restrict__ alpha, const double *__restrict__ mu,
+                               double4 *__restrict__ xq, double4 *__restrict__ mua, int2 *__restrict__ tm,
+                               int *__restrict__ tagout, int *__restrict__ invperm)
+{
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  int c = perm[s];
+  xq[s] = make_double4(x[3 * c], x[3 * c + 1], x[3 * c + 2], q[c]);
+  mua[s] = make_double4(mu[3 * c], mu[3 * c + 1], mu[3 * c + 2], alpha[c]);
+  tm[s] = make_int2(type[c], mol ? mol[c] : 0);
+  tagout[s] = tag ? tag[c] : c + 1;
+  invperm[c] = s;
+}
+
+// per-step refresh (no rebuild): positions and dipoles of owned atoms from caller order
+__global__ void k_refresh_local(int n, const int *__restrict__ perm, const double *__restrict__ x,
+                                const double *__restrict__ mu, double4 *__restrict__ xq,
+                                double4 *__restrict__ mua)
+{
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  int c = perm[s];
+  double4 v = xq[s];
+  xq[s] = make_double4(x[3 * c], x[3 * c + 1], x[3 * c + 2], v.w);
+  double4 m = mua[s];
+  mua[s] = make_double4(mu[3 * c], mu[3 * c + 1], mu[3 * c + 2], m.w);
+}
+
+// which of the 26 periodic images of an owned atom fall inside the ghost shell
+// (same membership rule as CommBrick::borders, src/comm_brick.cpp:768-772: x <= lo+cut sends the
+// +prd image, x >= hi-cut sends the -prd image, independently per dimension)
+__device__ __forceinline__ int image_mask(const Box &b, double cut, double x, double y, double z, int *opt)
+{
+  // opt[d] bit0: shift +1 allowed, bit1: shift -1 allowed
+  const double p[3] = {x, y, z};
+  int n = 1;
+  for (int d = 0; d < 3; d++) {
+    int o = 0;
+    if (b.periodic[d]) {
+      if (p[d] <= b.lo[d] + cut) o |= 1;
+      if (p[d] >= b.hi[d] - cut) o |= 2;
+    }
+    opt[d] = o;
+    n *= 1 + (o & 1) + ((o >> 1) & 1);
+  }
+  return n - 1;  // number of ghost images
+}
+
+__global__ void k_ghost_count(int n, const double4 *__restrict__ xq, Box box, double cut,
+                              unsigned long long *__restrict__ cnt)
+{
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  int opt[3];
+  double4 v = xq[s];
+  cnt[s] = (unsigned long long)image_mask(box, cut, v.x, v.y, v.z, opt);
+}
+
+// emits ghosts in (owner, z-shift, y-shift, x-shift) order into unsorted staging arrays
+__global__ void k_ghost_fill(int n, const double4 *__restrict__ xq, Box box, double cut, Grid g,
+                             const unsigned long long *__restrict__ off, int *__restrict__ g_owner,
+                             int *__restrict__ g_shift, int *__restrict__ g_key, int *__restrict__ g_iota)
+{
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  int opt[3];
+  double4 v = xq[s];
+  if (image_mask(box, cut, v.x, v.y, v.z, opt) == 0) return;
+  unsigned long long o = off[s];
+  const int sh[3] = {0, 1, -1};
+  for (int kz = 0; kz < 3; kz++) {
+    if (kz && !((opt[2] >> (kz - 1)) & 1)) continue;
+    for (int ky = 0; ky < 3; ky++) {
+      if (ky && !((opt[1] >> (ky - 1)) & 1)) continue;
+      for (int kx = 0; kx < 3; kx++) {
+        if (kx && !((opt[0] >> (kx - 1)) & 1)) continue;
+        if (!kx && !ky && !kz) continue;
+        // ghost coordinate = owner + shift*prd, one rounding per shifted dimension
+        // (AtomVecFull::pack_border, src/MOLECULE/atom_vec_full.cpp:403-421)
+        double gx = sh[kx] ? v.x + sh[kx] * box.prd[0] : v.x;
+        double gy = sh[ky] ? v.y + sh[ky] * box.prd[1] : v.y;
+        double gz = sh[kz] ? v.z + sh[kz] * box.prd[2] : v.z;
+        int cx, cy, cz;
+        g_owner[o] = s;
+        g_shift[o] = (sh[kx] + 1) | ((sh[ky] + 1) << 2) | ((sh[kz] + 1) << 4);
+        g_key[o] = cell_of(g, gx, gy, gz, cx, cy, cz);
+        g_iota[o] = (int)o;
+        o++;
+      }
+    }
+  }
+}
+
+// ghost records in cell-sorted order behind the owned atoms
+__global__ void k_ghost_gather(int nghost, int nloc, const int *__restrict__ order,
+                               const int *__restrict__ owner_in, const int *__restrict__ shift_in, Box box,
+                               double4 *__restrict__ xq, double4 *__restrict__ mua, int2 *__restrict__ tm,
+                               int *__restrict__ tag, int *__restrict__ owner, int *__restrict__ shift)
+{
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nghost) return;
+  int src = order[g];
+  int s = owner_in[src], code = shift_in[src];
+  int sx = (code & 3) - 1, sy = ((code >> 2) & 3) - 1, sz = ((code >> 4) & 3) - 1;
+  double4 v = xq[s];
+  xq[nloc + g] = make_double4(sx ? v.x + sx * box.prd[0] : v.x, sy ? v.y + sy * box.prd[1] : v.y,
+                              sz ? v.z + sz * box.prd[2] : v.z, v.w);
+  mua[nloc + g] = mua[s];
+  tm[nloc + g] = tm[s];
+  tag[nloc + g] = tag[s];
+  owner[g] = s;
+  shift[g] = code;
+}
+
+// ghost positions (and optionally dipoles) follow their owners: the device-side equivalent of
+// CommBrick::forward_comm (src/comm_brick.cpp:463-524) for a single brick
+template <bool POS, bool MU>
+__global__ void k_ghost_refresh(int nghost, int nloc, const int *__restrict__ owner,
+                                const int *__restrict__ shift, Box box, double4 *__restrict__ xq,
+                                double4 *__restrict__ mua)
+{
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nghost) return;
+  int s = owner[g];
+  if (POS) {
+    int code = shift[g];
+    int sx = (code & 3) - 1, sy = ((code >> 2) & 3) - 1, sz = ((code >> 4) & 3) - 1;
+    double4 v = xq[s];
+    xq[nloc + g] = make_double4(sx ? v.x + sx * box.prd[0] : v.x, sy ? v.y + sy * box.prd[1] : v.y,
+                                sz ? v.z + sz * box.prd[2] : v.z, v.w);
+  }
+  if (MU) mua[nloc + g] = mua[s];
+}
+
+// first index of every cell in a key-sorted array (keys ascending): lower_bound per cell
+__global__ void k_cell_starts(int ncell, int n, const int *__restrict__ sorted_keys, int *__restrict__ start)
+{
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > ncell) return;
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (sorted_keys[mid] < c) lo = mid + 1;
+    else hi = mid;
+  }
+  start[c] = lo;
+}
+
+// NPair::find_special (src/npair.h:111-137) with special_flag = {.,2,2,2} (a KSpace style is present,
+// src/neighbor.cpp:380-382): returns 0 or the 1-2/1-3/1-4 level
+__device__ __forceinline__ int find_special(const int *__restrict__ list, const int *__restrict__ ns, int tagj)
+{
+  const int n1 = ns[0], n2 = ns[1], n3 = ns[2];
+  for (int k = 0; k < n3; k++)
+    if (list[k] == tagj) return k < n1 ? 1 : (k < n2 ? 2 : 3);
+  return 0;
+}
+
+// Full neighbor list of every owned atom over owned+ghost atoms; pair accepted iff
+// rsq <= cutneighsq[itype][jtype] with the reference's FP64 expression (src/npair_half_bin_newton.cpp:96-101).
+// FILL=false counts, FILL=true writes entries (ext index | special level << 30).
+template <bool FILL>
+__global__ void k_neigh_build(int nloc, DevParams P, const double4 *__restrict__ xq,
+                              const int2 *__restrict__ tm, const int *__restrict__ tag,
+                              const int *__restrict__ cl_start, const int *__restrict__ cg_start,
+                              int nstencil, const int *__restrict__ stencil,  // packed dx,dy,dz (+16 each, 6 bits)
+                              const int *__restrict__ nspecial, const int *__restrict__ special, int maxspecial,
+                              unsigned long long *__restrict__ count,
+                              const unsigned long long *__restrict__ rowstart, int *__restrict__ neigh)
+{
+  const int lane = threadIdx.x & 31;
+  const int s = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (s >= nloc) return;
+  const double4 xi = xq[s];
+  const int ti = tm[s].x;
+  const int n1 = P.pc.ntypes + 1;
+  int cx, cy, cz;
+  cell_of(P.grid, xi.x, xi.y, xi.z, cx, cy, cz);
+  unsigned long long n = 0;
+  const unsigned long long base = FILL ? rowstart[s] : 0ull;
+  const bool has_special = nspecial != nullptr && nspecial[3 * s + 2] > 0;
+
+  for (int k = 0; k < nstencil; k++) {
+    const int code = stencil[k];
+    const int ox = cx + ((code & 63) - 16), oy = cy + (((code >> 6) & 63) - 16), oz = cz + (((code >> 12) & 63) - 16);
+    if (ox < 0 || oy < 0 || oz < 0 || ox >= P.grid.nc[0] || oy >= P.grid.nc[1] || oz >= P.grid.nc[2]) continue;
+    const int cell = (oz * P.grid.nc[1] + oy) * P.grid.nc[0] + ox;
+    for (int part = 0; part < 2; part++) {
+      const int beg = part ? nloc + cg_start[cell] : cl_start[cell];
+      const int end = part ? nloc + cg_start[cell + 1] : cl_start[cell + 1];
+      for (int j0 = beg; j0 < end; j0 += 32) {
+        const int j = j0 + lane;
+        bool ok = false;
+        int entry = j;
+        if (j < end && j != s) {
+          const double4 xj = xq[j];
+          const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+          const double rsq = rsq_nofma(dx, dy, dz);
+          ok = rsq <= P.cutneighsq[ti * n1 + tm[j].x];
+          if (FILL && ok && has_special) {
+            int which = find_special(special + (size_t)s * maxspecial, nspecial + 3 * s, tag[j]);
+            // Domain::minimum_image_check (src/domain.h:155-160): a far image of a bonded partner
+            // is an ordinary neighbour
+            if (which && !((P.box.periodic[0] && fabs(dx) > P.box.half[0]) ||
+                           (P.box.periodic[1] && fabs(dy) > P.box.half[1]) ||
+                           (P.box.periodic[2] && fabs(dz) > P.box.half[2])))
+              entry = j | (which << SBBITS);
+          }
+        }
+        const unsigned m = __ballot_sync(FULL, ok);
+        if (FILL && ok) neigh[base + n + __popc(m & ((1u << lane) - 1))] = entry;
+        n += __popc(m);
+      }
+    }
+  }
+  if (!FILL && lane == 0) count[s] = n;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// stage 2: LJ + real-space Ewald Coulomb (+ static field in list mode) over the full list
+// ---------------------------------------------------------------------------------------------------
+// per-block partial sums: evdwl, ecoul, vxx, vyy, vzz, vxy, vxz, vyz  (each pair seen twice => 1/2)
+constexpr int NPAIR_PART = 8;
+
+template <bool EVFLAG, bool FIELD>
+__global__ void __launch_bounds__(BLOCK)
+k_pair(int nloc, DevParams P, const double4 *__restrict__ xq, const int2 *__restrict__ tm,
+       const unsigned long long *__restrict__ rowstart, const int *__restrict__ neigh,
+       double4 *__restrict__ f_pair, double4 *__restrict__ ef, double *__restrict__ partial)
+{
+  const int lane = threadIdx.x & 31;
+  const int s = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  double acc[NPAIR_PART] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (s < nloc) {
+    const double4 xi = xq[s];
+    const int2 tmi = tm[s];
+    const int n1 = P.pc.ntypes + 1;
+    double fx = 0, fy = 0, fz = 0, ex = 0, ey = 0, ez = 0;
+    const unsigned long long beg = rowstart[s], end = rowstart[s + 1];
+    for (unsigned long long k = beg + lane; k < end; k += 32) {
+      const int raw = neigh[k];
+      const int j = raw & NEIGHMASK, sb = (raw >> SBBITS) & 3;
+      const double4 xj = ld4(xq + j);
+      const int2 tmj = tm[j];
+      const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+      const double rsq = rsq_nofma(dx, dy, dz);
+      const int ij = tmi.x * n1 + tmj.x;
+      if (rsq < P.lj.cutsq[ij]) {
+        double evdwl, ecoul;
+        const double fpair = lj_coul_pair(P.pc, P.lj, P.tb, ij, rsq, xi.w, xj.w, sb, EVFLAG, evdwl, ecoul);
+        fx += dx * fpair;
+        fy += dy * fpair;
+        fz += dz * fpair;
+        if (EVFLAG) {
+          acc[0] += evdwl;
+          acc[1] += ecoul;
+          acc[2] += dx * dx * fpair;
+          acc[3] += dy * dy * fpair;
+          acc[4] += dz * dz * fpair;
+          acc[5] += dx * dy * fpair;
+          acc[6] += dx * dz * fpair;
+          acc[7] += dy * dz * fpair;
+        }
+      }
+      if (FIELD) {
+        if (rsq <= P.pc.cut_coulsq && (tmi.y != tmj.y || tmi.y == 0)) {
+          const double sc = static_field_scalar(P.pc, rsq) * xj.w;
+          ex += sc * dx;
+          ey += sc * dy;
+          ez += sc * dz;
+        }
+      }
+    }
+    fx = warp_sum(fx);
+    fy = warp_sum(fy);
+    fz = warp_sum(fz);
+    if (FIELD) {
+      ex = warp_sum(ex);
+      ey = warp_sum(ey);
+      ez = warp_sum(ez);
+    }
+    if (lane == 0) {
+      f_pair[s] = make_double4(fx, fy, fz, 0.0);
+      if (FIELD) ef[s] = make_double4(ex * P.pc.kq, ey * P.pc.kq, ez * P.pc.kq, 0.0);  // pol.cpp:372-374
+    }
+  }
+  if (EVFLAG) {
+#pragma unroll
+    for (int k = 0; k < NPAIR_PART; k++) acc[k] = 0.5 * warp_sum(acc[k]);
+    block_reduce_store<NPAIR_PART>(acc, partial);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// row enumerators: how a warp walks the partners of owned atom s
+// ---------------------------------------------------------------------------------------------------
+// A partner is described from the point of view of the reference's pair loop: `a` is the atom the
+// pair expressions treat as "i" (lower index), del = x_a - image(x_b), and `self_is_a` tells whether
+// the row atom is a.  List mode: the row atom is always a (del = x_i - x_j over ghosts).  All-pairs
+// mode: orientation follows the caller's atom indices so that every pair is evaluated with exactly
+// the operands the reference uses.
+struct Partner {
+  int j;
+  double dx, dy, dz, rsq;
+  bool self_is_a;
+};
+
+struct ListRows {
+  const unsigned long long *rowstart;
+  const int *neigh;
+};
+struct AllPairRows {
+  int nloc;
+  const int *perm;  // sorted -> caller index
+};
+
+// ---------------------------------------------------------------------------------------------------
+// stage 2 (all-pairs mode): static field over all owned pairs, minimum image (pol.cpp:329-361)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLOCK)
+k_static_allpairs(int nloc, DevParams P, const double4 *__restrict__ xq, const int2 *__restrict__ tm,
+                  const int *__restrict__ perm, double4 *__restrict__ ef)
+{
+  const int lane = threadIdx.x & 31;
+  const int s = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (s >= nloc) return;
+  const double4 xi = xq[s];
+  const int moli = tm[s].y, ci = perm[s];
+  double ex = 0, ey = 0, ez = 0;
+  for (int j = lane; j < nloc; j += 32) {
+    if (j == s) continue;
+    const double4 xj = ld4(xq + j);
+    const int molj = tm[j].y;
+    const bool i_is_a = ci < perm[j];
+    double dx, dy, dz;
+    if (i_is_a) min_image_del(P.box, xi.x, xi.y, xi.z, xj.x, xj.y, xj.z, dx, dy, dz);
+    else min_image_del(P.box, xj.x, xj.y, xj.z, xi.x, xi.y, xi.z, dx, dy, dz);
+    const double rsq = rsq_nofma(dx, dy, dz);
+    if (rsq <= P.pc.cut_coulsq && (moli != molj || moli == 0)) {
+      double sc = static_field_scalar(P.pc, rsq) * xj.w;
+      if (!i_is_a) sc = -sc;  // ef_static[j] -= ef_temp*q_i*del  (pol.cpp:355-357)
+      ex += sc * dx;
+      ey += sc * dy;
+      ez += sc * dz;
+    }
+  }
+  ex = warp_sum(ex);
+  ey = warp_sum(ey);
+  ez = warp_sum(ez);
+  if (lane == 0) ef[s] = make_double4(ex * P.pc.kq, ey * P.pc.kq, ez * P.pc.kq, 0.0);
+}
+
+// first guess mu = gamma*alpha*E_static unless use_previous (pol.cpp:376-385), owned atoms
+__global__ void k_init_mu(int nloc, double gamma, const double4 *__restrict__ ef, double4 *__restrict__ mua)
+{
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nloc) return;
+  double4 m = mua[s];
+  const double4 e = ef[s];
+  double a = m.w * e.x, b = m.w * e.y, c = m.w * e.z;
+  a *= gamma;
+  b *= gamma;
+  c *= gamma;
+  mua[s] = make_double4(a, b, c, m.w);
+}
+
+// mu = alpha*E_static without gamma: the divergence reset of pol.cpp:1227-1235
+__global__ void k_reset_mu(int nloc, const double4 *__restrict__ ef, double4 *__restrict__ mua)
+{
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nloc) return;
+  double4 m = mua[s];
+  const double4 e = ef[s];
+  mua[s] = make_double4(m.w * e.x, m.w * e.y, m.w * e.z, m.w);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// stage 3: one sweep of the induced-dipole iteration (pol.cpp:1158-1180 + 1198-1205)
+// ---------------------------------------------------------------------------------------------------
+// rows = positions [pos_beg,pos_end) of `order` (identity when order == nullptr).  Reads dipoles from
+// mu_in (owned + ghost), writes mu_out[s] for the rows only and the per-block sum of squared changes.
+// Jacobi: mu_in != mu_out over all rows.  Ranked colouring sweep: rows = one chunk, mu_out = staging.
+template <bool LIST>
+__global__ void __launch_bounds__(BLOCK)
+k_sweep(int pos_beg, int pos_end, const int *__restrict__ order, DevParams P, ListRows L, AllPairRows A,
+        const double4 *__restrict__ xq, const double4 *__restrict__ mu_in, const double4 *__restrict__ ef,
+        double4 *__restrict__ mu_out, double *__restrict__ partial)
+{
+  const int lane = threadIdx.x & 31;
+  const int pos = pos_beg + blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  double chg[1] = {0.0};
+  if (pos < pos_end) {
+    const int s = order ? order[pos] : pos;
+    const double4 xi = xq[s];
+    const double4 mi = mu_in[s];
+    double ex = 0, ey = 0, ez = 0;
+    if (mi.w != 0.0) {  // alpha_i == 0 => mu_new = 0 whatever the field
+      if (LIST) {
+        const unsigned long long beg = L.rowstart[s], end = L.rowstart[s + 1];
+        for (unsigned long long k = beg + lane; k < end; k += 32) {
+          const int j = L.neigh[k] & NEIGHMASK;
+          const double4 xj = ld4(xq + j);
+          const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+          const double rsq = dx * dx + dy * dy + dz * dz;
+          if (rsq < P.pc.polar_cutsq) {
+            const double4 mj = ld4(mu_in + j);
+            induced_field_pair(P.pc, dx, dy, dz, rsq, mj.x, mj.y, mj.z, ex, ey, ez);
+          }
+        }
+      } else {
+        const int ci = A.perm[s];
+        for (int j = lane; j < A.nloc; j += 32) {
+          if (j == s) continue;
+          const double4 xj = ld4(xq + j);
+          double dx, dy, dz;
+          // T is even in del, so the orientation only selects which atom's coordinates anchor the
+          // minimum image, exactly as the matrix build does for i<j (pol.cpp:1279-1282)
+          if (ci < A.perm[j]) min_image_del(P.box, xi.x, xi.y, xi.z, xj.x, xj.y, xj.z, dx, dy, dz);
+          else min_image_del(P.box, xj.x, xj.y, xj.z, xi.x, xi.y, xi.z, dx, dy, dz);
+          const double rsq = dx * dx + dy * dy + dz * dz;
+          const double4 mj = ld4(mu_in + j);
+          induced_field_pair(P.pc, dx, dy, dz, rsq, mj.x, mj.y, mj.z, ex, ey, ez);
+        }
+      }
+      ex = warp_sum(ex);
+      ey = warp_sum(ey);
+      ez = warp_sum(ez);
+    }
+    if (lane == 0) {
+      const double4 e = ef[s];
+      const double nx = mi.w * (e.x + ex), ny = mi.w * (e.y + ey), nz = mi.w * (e.z + ez);
+      mu_out[s] = make_double4(nx, ny, nz, mi.w);
+      chg[0] = (nx - mi.x) * (nx - mi.x) + (ny - mi.y) * (ny - mi.y) + (nz - mi.z) * (nz - mi.z);
+    }
+  }
+  block_reduce_store<1>(chg, partial);
+}
+
+// commit a chunk of the ranked colouring sweep: staged values become visible (owned records)
+__global__ void k_commit_rows(int pos_beg, int pos_end, const int *__restrict__ order,
+                              const double4 *__restrict__ staged, double4 *__restrict__ mua)
+{
+  int pos = pos_beg + blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= pos_end) return;
+  int s = order ? order[pos] : pos;
+  mua[s] = staged[s];
+}
+
+// Strictly sequential Gauss-Seidel sweep in ranked order with immediate write-back = the reference's
+// polar_gs / polar_gs_ranked iteration (pol.cpp:1158-1180), all-pairs minimum image.  One CTA walks
+// the ranked atoms; its 1024 threads share the partner loop of the current atom.  Dipoles are read
+// through L2 (ld.global.cg) because they are rewritten inside the kernel.
+constexpr int GS_THREADS = 1024;
+__global__ void __launch_bounds__(GS_THREADS)
+k_gs_sequential(int nloc, const int *__restrict__ order, DevParams P, const int *__restrict__ perm,
+                const double4 *__restrict__ xq, double4 *__restrict__ mua, const double4 *__restrict__ ef,
+                double *__restrict__ change_out)
+{
+  __shared__ double sm[GS_THREADS / 32][3];
+  __shared__ double tot[3];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double change = 0.0;  // thread 0 only
+  for (int pos = 0; pos < nloc; pos++) {
+    const int s = order ? order[pos] : pos;
+    const double4 mi = ld4_cg(mua + s);
+    if (mi.w == 0.0) {
+      if (threadIdx.x == 0) {
+        change += mi.x * mi.x + mi.y * mi.y + mi.z * mi.z;
+        mua[s] = make_double4(0.0, 0.0, 0.0, 0.0);
+      }
+      __syncthreads();
+      continue;
+    }
+    const double4 xi = xq[s];
+    const int ci = perm[s];
+    double ex = 0, ey = 0, ez = 0;
+    for (int j = threadIdx.x; j < nloc; j += GS_THREADS) {
+      if (j == s) continue;
+      const double4 xj = ld4(xq + j);
+      double dx, dy, dz;
+      if (ci < perm[j]) min_image_del(P.box, xi.x, xi.y, xi.z, xj.x, xj.y, xj.z, dx, dy, dz);
+      else min_image_del(P.box, xj.x, xj.y, xj.z, xi.x, xi.y, xi.z, dx, dy, dz);
+      const double rsq = dx * dx + dy * dy + dz * dz;
+      const double4 mj = ld4_cg(mua + j);
+      induced_field_pair(P.pc, dx, dy, dz, rsq, mj.x, mj.y, mj.z, ex, ey, ez);
+    }
+    ex = warp_sum(ex);
+    ey = warp_sum(ey);
+    ez = warp_sum(ez);
+    if (lane == 0) {
+      sm[warp][0] = ex;
+      sm[warp][1] = ey;
+      sm[warp][2] = ez;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      double t = 0.0;
+      for (int w = 0; w < GS_THREADS / 32; w++) t += sm[w][threadIdx.x];
+      tot[threadIdx.x] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const double4 e = ef[s];
+      const double nx = mi.w * (e.x + tot[0]), ny = mi.w * (e.y + tot[1]), nz = mi.w * (e.z + tot[2]);
+      change += (nx - mi.x) * (nx - mi.x) + (ny - mi.y) * (ny - mi.y) + (nz - mi.z) * (nz - mi.z);
+      mua[s] = make_double4(nx, ny, nz, mi.w);
+      __threadfence();
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) change_out[0] = change;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// rank metric for polar_gs_ranked (pol.cpp:196-226) over the neighbour list (owned + ghost images)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLOCK)
+k_rmin(int nloc, ListRows L, const double4 *__restrict__ xq, const double4 *__restrict__ mua,
+       const int2 *__restrict__ tm, unsigned long long *__restrict__ rmin_bits)
+{
+  const int lane = threadIdx.x & 31;
+  const int s = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (s >= nloc) return;
+  const double4 xi = xq[s];
+  const double ai = mua[s].w;
+  const int moli = tm[s].y;
+  double best = 1000.0;  // pol.cpp:196
+  if (ai > 0) {
+    const unsigned long long beg = L.rowstart[s], end = L.rowstart[s + 1];
+    for (unsigned long long k = beg + lane; k < end; k += 32) {
+      const int j = L.neigh[k] & NEIGHMASK;
+      const double4 xj = ld4(xq + j);
+      const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+      const double r = sqrt(rsq_nofma(dx, dy, dz));
+      if (mua[j].w > 0 && best > r && (moli != tm[j].y || moli == 0)) best = r;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) best = fmin(best, __shfl_down_sync(FULL, best, o));
+  if (lane == 0) atomicMin(rmin_bits, (unsigned long long)__double_as_longlong(best));
+}
+
+__global__ void __launch_bounds__(BLOCK)
+k_rank_metric(int nloc, ListRows L, const double4 *__restrict__ xq, const double4 *__restrict__ mua,
+              const int2 *__restrict__ tm, const unsigned long long *__restrict__ rmin_bits,
+              const int *__restrict__ perm, double *__restrict__ metric_caller)
+{
+  const int lane = threadIdx.x & 31;
+  const int s = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (s >= nloc) return;
+  const double rmin = __longlong_as_double((long long)*rmin_bits);
+  const double4 xi = xq[s];
+  const double ai = mua[s].w;
+  const int moli = tm[s].y;
+  double m = 0.0;
+  const unsigned long long beg = L.rowstart[s], end = L.rowstart[s + 1];
+  for (unsigned long long k = beg + lane; k < end; k += 32) {
+    const int j = L.neigh[k] & NEIGHMASK;
+    const double4 xj = ld4(xq + j);
+    const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+    const double r = sqrt(rsq_nofma(dx, dy, dz));
+    if (rmin * 1.5 > r && (moli != tm[j].y || moli == 0)) m += ai * mua[j].w;
+  }
+  m = warp_sum(m);
+  if (lane == 0) metric_caller[perm[s]] = m;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// stage 4: charge-dipole and dipole-dipole forces + energies (pol.cpp:425-631)
+// ---------------------------------------------------------------------------------------------------
+// per-block partials: u_self, u_ef, u_dd, then the polarization virial (6)
+constexpr int NPOL_PART = 9;
+
+template <bool LIST, bool EVFLAG, bool VPAIR>
+__global__ void __launch_bounds__(BLOCK)
+k_polforce(int nloc, DevParams P, ListRows L, AllPairRows A, const double4 *__restrict__ xq,
+           const double4 *__restrict__ mua, const int2 *__restrict__ tm, double4 *__restrict__ f_pol,
+           double *__restrict__ partial)
+{
+  const int lane = threadIdx.x & 31;
+  const int s = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  double acc[NPOL_PART] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (s < nloc) {
+    const double4 xi = xq[s];
+    const double4 mi = mua[s];
+    const int moli = tm[s].y;
+    double fx = 0, fy = 0, fz = 0;
+    PolPairIn in;
+    auto visit = [&](int j, bool i_is_a, double dx, double dy, double dz) {
+      const double4 xj = ld4(xq + j);
+      const double4 mj = ld4(mua + j);
+      const int molj = tm[j].y;
+      in.dx = dx; in.dy = dy; in.dz = dz;
+      in.intermolecular = (moli != molj) || moli == 0;
+      if (i_is_a) {
+        in.qa = xi.w; in.qb = xj.w; in.alpha_a = mi.w; in.alpha_b = mj.w;
+        in.max_ = mi.x; in.may = mi.y; in.maz = mi.z; in.mbx = mj.x; in.mby = mj.y; in.mbz = mj.z;
+      } else {
+        in.qa = xj.w; in.qb = xi.w; in.alpha_a = mj.w; in.alpha_b = mi.w;
+        in.max_ = mj.x; in.may = mj.y; in.maz = mj.z; in.mbx = mi.x; in.mby = mi.y; in.mbz = mi.z;
+      }
+      double px, py, pz, uef, udd;
+      pol_force_pair(P.pc, in, EVFLAG, px, py, pz, uef, udd);
+      if (!i_is_a) { px = -px; py = -py; pz = -pz; }
+      fx += px; fy += py; fz += pz;
+      if (EVFLAG) {
+        acc[1] += 0.5 * uef;  // every pair is visited from both of its atoms
+        acc[2] += 0.5 * udd;
+        if (VPAIR) {  // ev_tally_xyz (src/pair.cpp:1001-1089): v = del (x) F with del = x_a - x_b
+          const double sx = i_is_a ? dx : -dx, sy = i_is_a ? dy : -dy, sz = i_is_a ? dz : -dz;
+          acc[3] += 0.5 * sx * px; acc[4] += 0.5 * sy * py; acc[5] += 0.5 * sz * pz;
+          acc[6] += 0.5 * sx * py; acc[7] += 0.5 * sx * pz; acc[8] += 0.5 * sy * pz;
+        }
+      }
+    };
+    if (LIST) {
+      const double reach = fmax(P.pc.cut_coulsq, P.pc.polar_cutsq);
+      const unsigned long long beg = L.rowstart[s], end = L.rowstart[s + 1];
+      for (unsigned long long k = beg + lane; k < end; k += 32) {
+        const int j = L.neigh[k] & NEIGHMASK;
+        const double4 xj = ld4(xq + j);
+        const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+        if (dx * dx + dy * dy + dz * dz < reach) visit(j, true, dx, dy, dz);
+      }
+    } else {
+      const int ci = A.perm[s];
+      for (int j = lane; j < A.nloc; j += 32) {
+        if (j == s) continue;
+        const double4 xj = ld4(xq + j);
+        const bool i_is_a = ci < A.perm[j];
+        double dx, dy, dz;
+        if (i_is_a) min_image_del(P.box, xi.x, xi.y, xi.z, xj.x, xj.y, xj.z, dx, dy, dz);
+        else min_image_del(P.box, xj.x, xj.y, xj.z, xi.x, xi.y, xi.z, dx, dy, dz);
+        visit(j, i_is_a, dx, dy, dz);
+      }
+    }
+    fx = warp_sum(fx);
+    fy = warp_sum(fy);
+    fz = warp_sum(fz);
+    if (lane == 0) {
+      f_pol[s] = make_double4(fx, fy, fz, 0.0);
+      if (EVFLAG) {
+        if (mi.w != 0.0) acc[0] = 0.5 * (mi.x * mi.x + mi.y * mi.y + mi.z * mi.z) / mi.w;  // pol.cpp:432-433
+        if (!VPAIR) {
+          // F.r virial of the reference (src/pair.cpp:1495-1543) restricted to this force field:
+          // polarization forces act on owned atoms at their stored coordinates
+          acc[3] += fx * xi.x; acc[4] += fy * xi.y; acc[5] += fz * xi.z;
+          acc[6] += fy * xi.x; acc[7] += fz * xi.x; acc[8] += fz * xi.y;
+        }
+      }
+    }
+  }
+  if (EVFLAG) {
+    // acc[0] and the F.r terms live in lane 0 only; the rest are per-lane partial sums
+#pragma unroll
+    for (int k = 0; k < NPOL_PART; k++) acc[k] = warp_sum(acc[k]);
+    block_reduce_store<NPOL_PART>(acc, partial);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// stage 5: fused reduction into f / eng_vdwl / eng_coul / eng_pol / virial
+// ---------------------------------------------------------------------------------------------------
+// total pair force per owned atom back in caller order, plus dipoles and static field for the host
+__global__ void k_scatter_out(int nloc, const int *__restrict__ perm, const double4 *__restrict__ f_pair,
+                              const double4 *__restrict__ f_pol, const double4 *__restrict__ mua,
+                              const double4 *__restrict__ ef, double *__restrict__ f_out,
+                              double *__restrict__ mu_out, double *__restrict__ ef_out)
+{
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nloc) return;
+  const int c = perm[s];
+  const double4 a = f_pair[s], b = f_pol[s], m = mua[s], e = ef[s];
+  f_out[3 * c] = a.x + b.x;
+  f_out[3 * c + 1] = a.y + b.y;
+  f_out[3 * c + 2] = a.z + b.z;
+  mu_out[3 * c] = m.x;
+  mu_out[3 * c + 1] = m.y;
+  mu_out[3 * c + 2] = m.z;
+  ef_out[3 * c] = e.x;
+  ef_out[3 * c + 1] = e.y;
+  ef_out[3 * c + 2] = e.z;
+}
+
+// deterministic final reduction of nblocks x NV per-block partials: one CTA, fixed tree
+template <int NV>
+__global__ void k_reduce_partials(int nblocks, const double *__restrict__ partial, double *__restrict__ out,
+                                  int accumulate)
+{
+  __shared__ double sm[256];
+  for (int v = 0; v < NV; v++) {
+    double t = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += 256) t += partial[(size_t)b * NV + v];
+    sm[threadIdx.x] = t;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) out[v] = accumulate ? out[v] + sm[0] : sm[0];
+    __syncthreads();
+  }
+}
+
+// displacement check of Neighbor::check_distance (src/neighbor.cpp:1989-1995): any atom moved more
+// than half the skin since the last rebuild
+__global__ void k_check_distance(int nloc, const double *__restrict__ x, const double *__restrict__ xhold,
+                                 double triggersq, int *__restrict__ flag)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nloc) return;
+  const double dx = x[3 * i] - xhold[3 * i], dy = x[3 * i + 1] - xhold[3 * i + 1], dz = x[3 * i + 2] - xhold[3 * i + 2];
+  if (rsq_nofma(dx, dy, dz) > triggersq) atomicOr(flag, 1);
+}
+
+// rows of a [n][w] caller-order int table into sorted order
+__global__ void k_gather_rows(int n, int w, const int *__restrict__ perm, const int *__restrict__ in,
+                              int *__restrict__ out)
+{
+  long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long)n * w) return;
+  int s = (int)(t / w), k = (int)(t % w);
+  out[t] = in[(size_t)perm[s] * w + k];
+}
+
+// f += a  (device-resident callers)
+__global__ void k_add_inplace(long n, const double *__restrict__ a, double *__restrict__ f)
+{
+  long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) f[t] += a[t];
+}
+
+}  // namespace polb200

@@ -1,0 +1,267 @@
+// pair_math.cuh -- per-pair arithmetic of the hot path, shared by every kernel (list mode and
+// all-pairs mode) and compiled for host too, so tests/cpu_pair_math can check it without a GPU.
+//
+// Each function states the reference lines whose VALUES it reproduces ("pol.cpp" =
+// src/pair_lj_cut_coul_long_polarization.cpp under /root/reference).  The code is organised around
+// what a GPU thread needs (one neighbour, results in registers), not around the reference's loops.
+#pragma once
+#include <cfloat>
+#include <cmath>
+
+#if defined(__CUDACC__)
+#define PB_HD __host__ __device__ __forceinline__
+#else
+#define PB_HD inline
+#endif
+
+namespace polb200 {
+
+struct Box {
+  double lo[3], hi[3], prd[3], half[3];
+  int periodic[3];
+};
+
+// Constant parameters of one compute() call that the pair functions read.
+struct PairConsts {
+  double cut_coulsq;
+  double f_shift;      // -1/cut_coul^2                          pol.cpp:324
+  double kq;           // sqrt(qqrd2e)                           pol.cpp:367
+  double qqrd2e;
+  double g_ewald;
+  double polar_damp;   // a
+  double polar_cutsq;  // <= 0: no dipole-dipole cutoff
+  double tabinnersq;
+  int damping_exponential;
+  int ncoultablebits, ncoulmask, ncoulshiftbits;
+  int ntypes;
+  double special_lj[4], special_coul[4];
+};
+
+// Domain::closest_image for one coordinate (src/domain.cpp:1220-1318, orthogonal branch).
+// d = xj - xi on entry; returns the wrapped displacement.  The while-loops run at most a couple of
+// times because callers keep atoms within about one box length of the box.
+PB_HD double wrap_delta(double d, double prd, double half, int periodic)
+{
+  if (periodic) {
+    if (d < 0.0) {
+      while (d < 0.0) d += prd;
+      if (d > half) d -= prd;
+    } else {
+      while (d > 0.0) d -= prd;
+      if (d < -half) d += prd;
+    }
+  }
+  return d;
+}
+
+// del = xa - closest_image(xa, xb), evaluated exactly as the reference does for the pair whose
+// LOWER index atom is a (pol.cpp:336-339, 437-440, 1279-1282): image = xa + wrapped(xb - xa).
+PB_HD void min_image_del(const Box &b, double ax, double ay, double az, double bx, double by, double bz,
+                         double &dx, double &dy, double &dz)
+{
+  double wx = wrap_delta(bx - ax, b.prd[0], b.half[0], b.periodic[0]);
+  double wy = wrap_delta(by - ay, b.prd[1], b.half[1], b.periodic[1]);
+  double wz = wrap_delta(bz - az, b.prd[2], b.half[2], b.periodic[2]);
+  dx = ax - (ax + wx);
+  dy = ay - (ay + wy);
+  dz = az - (az + wz);
+}
+
+// rsq with the reference's operation order and NO fused multiply-add, for every comparison against
+// a cutoff (neighbor build, rsq <= cut_coulsq ...): keeps pair-set decisions bit-identical.
+PB_HD double rsq_nofma(double dx, double dy, double dz)
+{
+#if defined(__CUDA_ARCH__)
+  return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+#else
+  volatile double a = dx * dx, b = dy * dy, c = dz * dz;
+  volatile double s = a + b;
+  return s + c;
+#endif
+}
+
+// ---- stage 2a: LJ + real-space Ewald Coulomb for one neighbour (pol.cpp:254-315) ---------------------
+struct CoulTablesDev {
+  const double *r, *dr, *f, *df, *c, *dc, *e, *de;
+};
+
+struct LJCoeffs {  // (ntypes+1)^2 row-major
+  const double *cutsq, *cut_ljsq, *lj1, *lj2, *lj3, *lj4, *offset;
+};
+
+// returns fpair (force/r); evdwl/ecoul only meaningful when want_e
+PB_HD double lj_coul_pair(const PairConsts &pc, const LJCoeffs &lj, const CoulTablesDev &tb, int ij,
+                          double rsq, double qi, double qj, int sb, bool want_e, double &evdwl,
+                          double &ecoul)
+{
+  const double EWALD_F = 1.12837917, EWALD_P = 0.3275911;
+  const double A1 = 0.254829592, A2 = -0.284496736, A3 = 1.421413741, A4 = -1.453152027, A5 = 1.061405429;
+  const double factor_lj = pc.special_lj[sb], factor_coul = pc.special_coul[sb];
+  const double r2inv = 1.0 / rsq;
+  double forcecoul = 0.0, forcelj = 0.0, r6inv = 0.0, prefactor = 0.0;
+  evdwl = ecoul = 0.0;
+  if (rsq < pc.cut_coulsq) {
+    if (!pc.ncoultablebits || rsq <= pc.tabinnersq) {
+      const double r = sqrt(rsq);
+      const double grij = pc.g_ewald * r;
+      const double expm2 = exp(-grij * grij);
+      const double t = 1.0 / (1.0 + EWALD_P * grij);
+      const double erfcv = t * (A1 + t * (A2 + t * (A3 + t * (A4 + t * A5)))) * expm2;
+      prefactor = pc.qqrd2e * qi * qj / r;
+      forcecoul = prefactor * (erfcv + EWALD_F * grij * expm2);
+      if (want_e) ecoul = prefactor * erfcv;
+    } else {
+      // index = bits of the float32 rounding of rsq (pol.cpp:268-273)
+      const float rsqf = (float)rsq;
+#if defined(__CUDA_ARCH__)
+      const int bits = __float_as_int(rsqf);
+#else
+      union { float f; int i; } u;
+      u.f = rsqf;
+      const int bits = u.i;
+#endif
+      const int itable = (bits & pc.ncoulmask) >> pc.ncoulshiftbits;
+      const double fraction = ((double)rsqf - tb.r[itable]) * tb.dr[itable];
+      forcecoul = qi * qj * (tb.f[itable] + fraction * tb.df[itable]);
+      if (factor_coul < 1.0) prefactor = qi * qj * (tb.c[itable] + fraction * tb.dc[itable]);
+      if (want_e) ecoul = qi * qj * (tb.e[itable] + fraction * tb.de[itable]);
+    }
+    if (factor_coul < 1.0) {
+      forcecoul -= (1.0 - factor_coul) * prefactor;
+      if (want_e) ecoul -= (1.0 - factor_coul) * prefactor;
+    }
+  }
+  if (rsq < lj.cut_ljsq[ij]) {
+    r6inv = r2inv * r2inv * r2inv;
+    forcelj = r6inv * (lj.lj1[ij] * r6inv - lj.lj2[ij]);
+    if (want_e) evdwl = factor_lj * (r6inv * (lj.lj3[ij] * r6inv - lj.lj4[ij]) - lj.offset[ij]);
+  }
+  return (forcecoul + factor_lj * forcelj) * r2inv;
+}
+
+// ---- stage 2b: shifted-force Coulomb field of charge qj at distance del (pol.cpp:342-357) --------------
+// returns the scalar s such that E_i += s*qj*del (caller applies the sign of the pair orientation)
+PB_HD double static_field_scalar(const PairConsts &pc, double rsq)
+{
+  const double r = sqrt(rsq);
+  const double dvdrr = 1.0 / rsq + pc.f_shift;
+  return dvdrr * 1.0 / r;
+}
+
+// ---- stage 3: T_ij . mu_j for one neighbour (pol.cpp:1282-1306 + 1161-1168), matrix-free ----------------
+// del = xlo - image(xhi).  Accumulates  e -= T mu  component-wise.
+PB_HD void induced_field_pair(const PairConsts &pc, double dx, double dy, double dz, double r2, double mx,
+                              double my, double mz, double &ex, double &ey, double &ez)
+{
+  const double r = sqrt(r2);
+  double r3, r5;
+  if (r == 0.0) r3 = r5 = DBL_MAX;
+  else {
+    r3 = 1.0 / (r * r * r);
+    r5 = 1.0 / (r * r * r * r * r);
+  }
+  double d1 = 1.0, d2 = 1.0;
+  if (pc.damping_exponential) {
+    const double a = pc.polar_damp;
+    const double ex_ = exp(-a * r);
+    d1 = 1.0 - ex_ * (0.5 * a * a * r2 + a * r + 1.0);
+    d2 = 1.0 - ex_ * (a * a * a * r2 * r / 6.0 + 0.5 * a * a * r2 + a * r + 1.0);
+  }
+  // T = d1*r3*I - 3*d2*r5*(del x del);  T mu = d1*r3*mu - 3*d2*r5*(del.mu)*del
+  const double s1 = d1 * r3;
+  const double s2 = -3.0 * d2 * r5;
+  const double dm = dx * mx + dy * my + dz * mz;
+  ex -= s1 * mx + s2 * dm * dx;
+  ey -= s1 * my + s2 * dm * dy;
+  ez -= s1 * mz + s2 * dm * dz;
+}
+
+// ---- stage 4: polarization force on the LOWER-index atom of a pair (pol.cpp:441-602) -----------------
+// a = lower index atom ("i" of the reference loop), b = higher ("j").  del = xa - image(xb).
+// Outputs the force on a (the force on b is its negative) and the pair's energy terms.
+struct PolPairIn {
+  double dx, dy, dz;
+  double qa, qb, alpha_a, alpha_b;
+  double max_, may, maz, mbx, mby, mbz;  // dipoles of a and b
+  bool intermolecular;                   // (molecule[a]!=molecule[b]) || molecule[a]==0
+};
+
+PB_HD void pol_force_pair(const PairConsts &pc, const PolPairIn &in, bool want_e, double &fx, double &fy,
+                          double &fz, double &u_ef, double &u_dd)
+{
+  const double delx = in.dx, dely = in.dy, delz = in.dz;
+  const double xsq = delx * delx, ysq = dely * dely, zsq = delz * delz;
+  const double rsq = xsq + ysq + zsq;
+  const double r2inv = 1.0 / rsq;
+  const double rinv = sqrt(r2inv);
+  const double r = 1.0 / rinv;
+  const double r3inv = r2inv * rinv;
+  const double f_shift = pc.f_shift, kq = pc.kq;
+  fx = fy = fz = 0.0;
+  u_ef = u_dd = 0.0;
+
+  if (rsq < pc.cut_coulsq && in.intermolecular) {
+    const double dvdrr = 1.0 / rsq + f_shift;
+    const double ef_temp = dvdrr * 1.0 / r * kq;
+    // M (symmetric) applied to a dipole: the bracketed factors of pol.cpp:467-475
+    const double mxx = (-2.0 * xsq + ysq + zsq) * r2inv + f_shift * (ysq + zsq);
+    const double myy = (-2.0 * ysq + xsq + zsq) * r2inv + f_shift * (xsq + zsq);
+    const double mzz = (-2.0 * zsq + xsq + ysq) * r2inv + f_shift * (xsq + ysq);
+    const double mxy = -3.0 * delx * dely * r2inv - f_shift * delx * dely;
+    const double mxz = -3.0 * delx * delz * r2inv - f_shift * delx * delz;
+    const double myz = -3.0 * dely * delz * r2inv - f_shift * dely * delz;
+    if (in.alpha_a != 0.0 && in.qb != 0.0) {  // dipole on a, charge on b (pol.cpp:464-484)
+      const double cf = in.qb * kq * r3inv;
+      fx += cf * (in.max_ * mxx + in.may * mxy + in.maz * mxz);
+      fy += cf * (in.max_ * mxy + in.may * myy + in.maz * myz);
+      fz += cf * (in.max_ * mxz + in.may * myz + in.maz * mzz);
+      if (want_e)
+        u_ef -= in.max_ * (ef_temp * in.qb * delx) + in.may * (ef_temp * in.qb * dely) +
+                in.maz * (ef_temp * in.qb * delz);
+    }
+    if (in.alpha_b != 0.0 && in.qa != 0.0) {  // dipole on b, charge on a (pol.cpp:487-507)
+      const double cf = in.qa * kq * r3inv;
+      fx -= cf * (in.mbx * mxx + in.mby * mxy + in.mbz * mxz);
+      fy -= cf * (in.mbx * mxy + in.mby * myy + in.mbz * myz);
+      fz -= cf * (in.mbx * mxz + in.mby * myz + in.mbz * mzz);
+      if (want_e)
+        u_ef += in.mbx * (ef_temp * in.qa * delx) + in.mby * (ef_temp * in.qa * dely) +
+                in.mbz * (ef_temp * in.qa * delz);
+    }
+  }
+
+  const bool in_polar_cut = !(pc.polar_cutsq > 0.0) || rsq < pc.polar_cutsq;
+  if (in.alpha_a != 0.0 && in.alpha_b != 0.0 && in_polar_cut) {  // pol.cpp:512-602
+    const double r5inv = r3inv * r2inv;
+    const double r7inv = r5inv * r2inv;
+    const double pdotp = in.max_ * in.mbx + in.may * in.mby + in.maz * in.mbz;
+    const double pidotr = in.max_ * delx + in.may * dely + in.maz * delz;
+    const double pjdotr = in.mbx * delx + in.mby * dely + in.mbz * delz;
+    double pre1, pre2, pre3, pre45 = 0.0;
+    if (pc.damping_exponential) {
+      const double a = pc.polar_damp;
+      const double t1 = exp(-a * r);
+      const double t2 = 1.0 + a * r + 0.5 * a * a * r * r;
+      const double t3 = t2 + 1.0 / 6.0 * a * a * a * r * r * r;
+      const double w2 = 1.0 - t1 * t2, w3 = 1.0 - t1 * t3;
+      pre1 = 3.0 * r5inv * pdotp * w2 - 15.0 * r7inv * pidotr * pjdotr * w3;
+      pre2 = 3.0 * r5inv * pjdotr * w3;
+      pre3 = 3.0 * r5inv * pidotr * w3;
+      const double pre4 = -pdotp * r3inv * (-t1 * (a * rinv + a * a) + t1 * a * t2 * rinv);
+      const double pre5 = 3.0 * pidotr * pjdotr * r5inv *
+                          (-t1 * (a * rinv + a * a + 0.5 * r * a * a * a) + t1 * a * t3 * rinv);
+      pre45 = pre4 + pre5;
+      if (want_e) u_dd = r3inv * pdotp * w2 - 3.0 * r5inv * pidotr * pjdotr * w3;
+    } else {
+      pre1 = 3.0 * r5inv * pdotp - 15.0 * r7inv * pidotr * pjdotr;
+      pre2 = 3.0 * r5inv * pjdotr;
+      pre3 = 3.0 * r5inv * pidotr;
+      if (want_e) u_dd = r3inv * pdotp - 3.0 * r5inv * pidotr * pjdotr;
+    }
+    fx += (pre1 + pre45) * delx + pre2 * in.max_ + pre3 * in.mbx;
+    fy += (pre1 + pre45) * dely + pre2 * in.may + pre3 * in.mby;
+    fz += (pre1 + pre45) * delz + pre2 * in.maz + pre3 * in.mbz;
+  }
+}
+
+}  // namespace polb200

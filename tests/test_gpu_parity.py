@@ -1,0 +1,218 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C ABI.
+
+Bars (BASELINE.json north_star):
+  * neighbor pair sets and iteration counts: exact;
+  * Jacobi / identity-order Gauss-Seidel: dipoles, fields, forces, energies within 1e-10 relative of the
+    reference's own compute() (golden fixtures dumped from the reference binary) and of the oracle;
+  * ranked Gauss-Seidel precision modes: converged dipoles within 20*polar_precision absolute
+    (the stopping rule bounds the rms change per sweep by polar_precision, pol.cpp:1205-1209),
+    energies within 1e-8 relative.
+"""
+import numpy as np
+import pytest
+
+import polhelpers as H
+from gpu_common import configure_from_fixture, pack_pairs, pb, run_fixture, run_system
+from oracle import polref as P
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+
+
+@pytest.fixture()
+def style():
+    s = pb.PairStyle(device=0)
+    yield s
+    s.close()
+
+
+def check_against_fixture(res, mu, ef, f, fx, mu_tol_abs=None, e_tol=TOL):
+    assert H.rel_err(ef, fx["ef_static"]) < TOL
+    if mu_tol_abs is None:
+        assert H.rel_err(mu, fx["mu_out"]) < TOL
+    else:
+        assert np.abs(mu - fx["mu_out"]).max() < mu_tol_abs
+    fscale = np.abs(fx["f"]).max()
+    assert np.abs(f - fx["f"]).max() < (TOL if mu_tol_abs is None else 1e-7) * fscale
+    for k in ("eng_vdwl", "eng_coul", "eng_pol"):
+        ref = float(fx[k])
+        assert abs(getattr(res, k) - ref) <= e_tol * max(1.0, abs(ref)), (k, getattr(res, k), ref)
+    vir = np.array(res.virial[:])
+    assert H.rel_err(vir, fx["virial"]) < (1e-9 if mu_tol_abs is None else 1e-7)
+
+
+JACOBI_CASES = ["h2_jacobi_fixed3_step0", "h2_jacobi_fixed30_step0", "h2_jacobi_precision_step0",
+                "h2_zodid_step0"]
+
+
+@pytest.mark.parametrize("case", JACOBI_CASES)
+def test_jacobi_and_zodid_match_reference(style, case):
+    fx = H.load_fixture(case)
+    configure_from_fixture(style, fx)
+    res, mu, ef, f = run_fixture(style, fx)
+    assert res.iterations == int(fx["iterations"])
+    assert res.status & pb.STATUS_EXACT
+    check_against_fixture(res, mu, ef, f, fx)
+
+
+@pytest.mark.parametrize("case", ["h2_gs_step0", "h2_gs_fixed3_step0"])
+def test_sequential_gauss_seidel_identity_order(style, case):
+    fx = H.load_fixture(case)
+    configure_from_fixture(style, fx)
+    res, mu, ef, f = run_fixture(style, fx)
+    assert res.iterations == int(fx["iterations"])
+    check_against_fixture(res, mu, ef, f, fx)
+
+
+@pytest.mark.parametrize("case", ["h2_default_step0", "h2_nodamp_step0", "h2_noprev_step0", "h2_notable_step0",
+                                  "methane_default_step0", "co2_singlepoint_step0"])
+def test_ranked_gauss_seidel_defaults(style, case):
+    fx = H.load_fixture(case)
+    configure_from_fixture(style, fx)
+    res, mu, ef, f = run_fixture(style, fx)
+    prec = 1e-15 if case.startswith("co2") else 1e-11
+    assert abs(res.iterations - int(fx["iterations"])) <= 1
+    check_against_fixture(res, mu, ef, f, fx, mu_tol_abs=max(20 * prec, 1e-12), e_tol=1e-8)
+
+
+def test_divergence_path(style):
+    fx = H.load_fixture("h2_diverge_step0")
+    configure_from_fixture(style, fx)
+    res, mu, ef, f = run_fixture(style, fx)
+    assert res.status & pb.STATUS_DIVERGED and res.iterations == int(fx["iterations"]) == 4
+    check_against_fixture(res, mu, ef, f, fx)       # mu = alpha*E exactly: tight tolerance
+
+
+@pytest.mark.parametrize("case", ["h2_default", "methane_default", "h2_jacobi_fixed3"])
+def test_multi_step_with_stale_lists_and_use_previous(style, case):
+    """steps 0..k of one reference run: lists built at step 0 (ago=0) and reused (ago>0), dipoles carried."""
+    fx0 = H.load_fixture(f"{case}_step0")
+    configure_from_fixture(style, fx0)
+    logs = H.thermo_logs()
+    key = "h2" if case == "h2_default" else ("methane" if case == "methane_default" else None)
+    step = 0
+    mu_prev = None
+    while (H.GOLDEN / f"{case}_step{step}.npz").exists():
+        fx = H.load_fixture(f"{case}_step{step}")
+        res, mu, ef, f = run_fixture(style, fx, ago=step, mu_in=fx["mu_in"] if mu_prev is None else mu_prev)
+        jac = "jacobi" in case
+        check_against_fixture(res, mu, ef, f, fx, mu_tol_abs=None if jac else 2e-10, e_tol=TOL if jac else 1e-8)
+        if key:   # the reference authors' own log, 8 printed digits
+            row = logs[key]["rows"][step]
+            for col, val in (("E_vdwl", res.eng_vdwl), ("E_coul", res.eng_coul), ("E_pol", res.eng_pol)):
+                assert f"{val:.7g}" == f"{float(row[col]):.7g}", (step, col, val, row[col])
+        mu_prev = mu
+        step += 1
+    assert step >= 2
+
+
+def test_neighbor_pair_set_is_exactly_the_reference_list(style):
+    fx = H.load_fixture("h2_default_step0")
+    configure_from_fixture(style, fx)
+    res, mu, ef, f = run_fixture(style, fx)
+    n = fx["x"].shape[0]
+    ng = res.nghost
+    perm = style.debug_fetch("perm", np.int32, n)
+    rowstart = style.debug_fetch("rowstart", np.uint64, n + 1).astype(np.int64)
+    neigh = style.debug_fetch("neigh", np.int32, int(rowstart[-1]))
+    gowner = style.debug_fetch("ghost_owner", np.int32, ng)
+    gcode = style.debug_fetch("ghost_shift", np.int32, ng)
+    gshift = np.stack([(gcode & 3) - 1, ((gcode >> 2) & 3) - 1, ((gcode >> 4) & 3) - 1], 1)
+    assert rowstart[-1] == res.npairs_full == 2 * int(fx["npairs_half"])
+    i_sorted = np.repeat(np.arange(n), np.diff(rowstart))
+    j = neigh & 0x3FFFFFFF
+    sb = (neigh >> 30) & 3
+    owner_sorted = np.where(j < n, j, gowner[np.clip(j - n, 0, max(ng - 1, 0))])
+    shift = np.where((j < n)[:, None], 0, gshift[np.clip(j - n, 0, max(ng - 1, 0))])
+    dev = np.sort(pack_pairs(perm[i_sorted], perm[owner_sorted], shift, sb))
+    # reference half list, symmetrised: (i, j, s) and (j, i, -s)
+    hi, hj = fx["half_i"].astype(np.int64), fx["half_j"].astype(np.int64)
+    hs, hb = fx["half_shift"].astype(np.int64), fx["half_special"].astype(np.int64)
+    ref = np.sort(np.concatenate([pack_pairs(hi, hj, hs, hb), pack_pairs(hj, hi, -hs, hb)]))
+    assert np.array_equal(dev, ref)
+
+
+def test_list_mode_matches_oracle_truncated(style):
+    """polar_cutoff extension on the synthetic LJ+charge fluid (BASELINE config 2 at reduced N)."""
+    sysm = H.lj_charge_fluid(10)                       # 4000 atoms, L = 34.2 A
+    kw = dict(fixed_iteration=1, max_iterations=5, damp_type="exponential", polar_gs_ranked=0)
+    st = H.fluid_style(sysm, 2.5, 12.0, polar_cut=12.0, **kw)
+    ref = P.polar_rows(sysm, st)
+    lit = P.compute(sysm, H.fluid_style(sysm, 2.5, 12.0, polar_gs_ranked=0, zodid=1, polar_gamma=0.0))
+    style.set_ntypes(2)
+    style.command("pair_style lj/cut/coul/long/polarization 2.5 12.0 polar_gs_ranked no fixed_iteration yes "
+                  "max_iterations 5 damp_type exponential polar_cutoff 12.0")
+    style.command("pair_coeff 1 1 0.1 3.0")
+    style.command("pair_coeff 2 2 0.1 3.0")
+    style.init(g_ewald=st.g_ewald, molecular=0)
+    style.set_box(sysm.boxlo, sysm.boxhi)
+    res, mu, ef, f = run_system(style, sysm)
+    assert not (res.status & pb.STATUS_EXACT) and res.iterations == 5
+    assert H.rel_err(ef, ref["ef_static"]) < TOL
+    assert H.rel_err(mu, ref["mu"]) < TOL
+    assert abs(res.eng_pol - ref["eng_pol"]) < TOL * abs(ref["eng_pol"])
+    assert abs(res.eng_vdwl - lit["eng_vdwl"]) < TOL * abs(lit["eng_vdwl"])
+    assert abs(res.eng_coul - lit["eng_coul"]) < TOL * abs(lit["eng_coul"])
+    ftot = lit["f"] + ref["f"]
+    assert np.abs(f - ftot).max() < TOL * np.abs(ftot).max()
+    vir = lit["virial"] + ref["virial"]
+    assert H.rel_err(np.array(res.virial[:]), vir) < 1e-9
+
+
+def test_list_mode_ranked_chunks_match_oracle_chunks(style):
+    sysm = H.lj_charge_fluid(8)                        # 2048 atoms, L = 27.4 A
+    st = H.fluid_style(sysm, 2.5, 12.0, polar_cut=12.0, damp_type="exponential", polar_gs_ranked=1,
+                       gs_chunks=8, precision=1e-11, max_iterations=50)
+    ref = P.polar_rows(sysm, st)
+    style.set_ntypes(2)
+    style.command("pair_style lj/cut/coul/long/polarization 2.5 12.0 damp_type exponential precision 1e-11 "
+                  "polar_cutoff 12.0 gs_chunks 8")
+    style.command("pair_coeff * * 0.1 3.0")
+    style.init(g_ewald=st.g_ewald, molecular=0)
+    style.set_box(sysm.boxlo, sysm.boxhi)
+    res, mu, ef, f = run_system(style, sysm)
+    assert abs(res.iterations - ref["iterations"]) <= 1
+    assert np.abs(mu - ref["mu"]).max() < 20 * 1e-11
+    assert abs(res.eng_pol - ref["eng_pol"]) < 1e-8 * abs(ref["eng_pol"])
+
+
+def test_exact_mode_equals_list_mode_when_cutoff_covers_everything(style):
+    """size-independent property: with polar_cutoff = cut_coul = L/2 - eps ... the two device paths agree
+    on the static field and on LJ/Coulomb (identical pair sets), independent of the oracle."""
+    sysm = H.lj_charge_fluid(6)                        # 864 atoms, L = 20.5
+    L = float(sysm.boxhi[0])
+    cc = 0.5 * L - 1e-6
+    outs = []
+    for extra in ("", f" polar_cutoff {cc}"):
+        s = pb.PairStyle(device=0)
+        s.set_ntypes(2)
+        s.command(f"pair_style lj/cut/coul/long/polarization 2.5 {cc} polar_gs_ranked no zodid yes" + extra)
+        s.command("pair_coeff * * 0.1 3.0")
+        s.init(g_ewald=0.3, molecular=0)
+        s.set_box(sysm.boxlo, sysm.boxhi)
+        outs.append(run_system(s, sysm))
+        s.close()
+    (ra, mua, efa, fa), (rb, mub, efb, fb) = outs
+    assert H.rel_err(efa, efb) < 1e-12 and H.rel_err(mua, mub) < 1e-12
+    assert abs(ra.eng_coul - rb.eng_coul) < 1e-12 * abs(ra.eng_coul)
+
+
+def test_config2_32k_list_mode_sampled_against_oracle(style):
+    """BASELINE config 2 at full size (32 000 atoms, cut 2.5/12): device list path vs the OpenMP row oracle."""
+    sysm = H.lj_charge_fluid(20)
+    assert sysm.n == 32000
+    st = H.fluid_style(sysm, 2.5, 12.0, polar_cut=12.0, fixed_iteration=1, max_iterations=2,
+                       damp_type="exponential", polar_gs_ranked=0)
+    ref = P.polar_rows(sysm, st)
+    style.set_ntypes(2)
+    style.command("pair_style lj/cut/coul/long/polarization 2.5 12.0 polar_gs_ranked no fixed_iteration yes "
+                  "max_iterations 2 damp_type exponential polar_cutoff 12.0")
+    style.command("pair_coeff * * 0.1 3.0")
+    style.init(g_ewald=st.g_ewald, molecular=0)
+    style.set_box(sysm.boxlo, sysm.boxhi)
+    res, mu, ef, f = run_system(style, sysm)
+    assert H.rel_err(ef, ref["ef_static"]) < TOL and H.rel_err(mu, ref["mu"]) < TOL
+    assert abs(res.eng_pol - ref["eng_pol"]) < TOL * abs(ref["eng_pol"])
+    # size-independent: Newton's third law, total pair force vanishes
+    assert np.abs(f.sum(0)).max() < 1e-9 * np.abs(f).max() * np.sqrt(sysm.n)

@@ -1,0 +1,181 @@
+"""CPU tests of the product's host side through the C ABI (no GPU, no compute calls):
+library loads, exports every symbol of include/polb200.h, and settings / coeff / init behave like
+PairLJCutCoulLongPolarization::settings/coeff/init_style/init_one (same defaults, same error texts,
+same order-dependent validation), with coefficient and Coulomb tables bit-identical to the
+reference's own arrays (golden fixture dumped from the reference binary)."""
+import importlib.util
+import re
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import polhelpers as H
+
+ROOT = Path(__file__).resolve().parents[1]
+PKG = ROOT / "lammps-induced-dipole-polarization-pair-style_b200"
+
+
+def load_pb():
+    spec = importlib.util.spec_from_file_location("polb200", PKG / "polb200.py")
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["polb200"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+pb = load_pb()
+
+
+@pytest.fixture()
+def style():
+    s = pb.PairStyle(device=pb.DEVICE_NONE)
+    yield s
+    s.close()
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "polb200.h").read_text()
+    declared = set(re.findall(r"\b(polb200_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(pb.ABI_SYMBOLS), declared ^ set(pb.ABI_SYMBOLS)
+    L = pb.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.polb200_abi_version() == 1
+
+
+def test_compute_without_device_fails_loudly(style):
+    fx = H.load_fixture("h2_default_step0")
+    configure_from_fixture(style, fx)
+    n = fx["x"].shape[0]
+    mu = np.zeros((n, 3))
+    f = np.zeros((n, 3))
+    with pytest.raises(pb.Polb200Error) as e:
+        style.compute(np.ascontiguousarray(fx["x"]), np.ascontiguousarray(fx["q"]),
+                      np.ascontiguousarray(fx["type"]), np.ascontiguousarray(fx["alpha"]), mu, f)
+    assert e.value.code == pb.ERR_CUDA and "no CPU fallback" in e.value.msg
+
+
+def configure_from_fixture(style, fx, extra_words=()):
+    style.set_ntypes(int(fx["ntypes"]))
+    style.command(str(fx["pair_style"]) + " " + " ".join(extra_words))
+    for line in str(fx["pair_coeff"]).splitlines():
+        style.command(line)
+    for line in str(fx["pair_modify"]).splitlines():
+        style.command(line)
+    style.init(g_ewald=float(fx["g_ewald"]), special_lj=tuple(fx["special_lj"]),
+               special_coul=tuple(fx["special_coul"]))
+    style.set_box(fx["boxlo"], fx["boxhi"])
+
+
+def test_defaults_and_keywords(style):
+    style.set_ntypes(1)
+    style.settings(["2.5", "12.0"])            # defaults: gs_ranked yes (pol.cpp:65-78)
+    with pytest.raises(pb.Polb200Error, match="Zodid doesn't work with polar_gs or polar_gs_ranked"):
+        style.settings(["2.5", "12.0", "zodid", "yes"])
+    style.settings(["2.5", "12.0", "polar_gs_ranked", "no", "zodid", "yes"])
+    with pytest.raises(pb.Polb200Error, match="polar_gs and polar_gs_ranked are mutually exclusive"):
+        style.settings(["2.5", "12.0", "polar_gs_ranked", "yes", "polar_gs", "yes"])
+    for bad in (["2.5", "12.0", "precision"], ["2.5", "12.0", "bogus", "1"], ["2.5", "12.0", "damp_type", "x"],
+                ["2.5", "12.0", "fixed_iteration", "maybe"], []):
+        with pytest.raises(pb.Polb200Error, match="Illegal pair_style command"):
+            style.settings(bad)
+    with pytest.raises(pb.Polb200Error, match="Expected floating point parameter"):
+        style.settings(["abc"])
+    # every reference keyword, incl. the undocumented debug / use_previous all shipped inputs pass
+    style.settings("2.5 10.797442 precision 0.00000000001 max_iterations 100 damp_type exponential damp 2.1304 "
+                   "polar_gs_ranked yes debug no use_previous yes polar_gamma 1.03 fixed_iteration no".split())
+    # single cutoff argument: cut_coul = cut_lj_global (pol.cpp:683)
+    style.settings(["9.0"])
+    assert style.extract("cut_coul") == (9.0, 0)
+
+
+def test_coeff_wildcards_and_errors(style):
+    style.set_ntypes(3)
+    style.settings(["2.5", "10.0"])
+    with pytest.raises(pb.Polb200Error, match="Incorrect args for pair coefficients"):
+        style.coeff(["1", "1", "0.1"])
+    with pytest.raises(pb.Polb200Error, match="Numeric index is out of bounds"):
+        style.coeff(["1", "4", "0.1", "3.0"])
+    with pytest.raises(pb.Polb200Error, match="Incorrect args for pair coefficients"):
+        style.coeff(["2", "1", "0.1", "3.0"])      # j<i only: count == 0 (pol.cpp:799)
+    style.coeff(["*", "*", "0.1", "3.0"])
+    style.coeff(["2*", "3", "0.2", "3.5", "7.0"])
+    eps, dim = style.extract("epsilon")
+    assert dim == 2 and eps[1, 1] == 0.1 and eps[2, 3] == 0.2 and eps[3, 3] == 0.2 and eps[1, 3] == 0.1
+    with pytest.raises(pb.Polb200Error, match="Pair style requires a KSpace style"):
+        style.init(g_ewald=0.2, kspace_present=0)
+    with pytest.raises(pb.Polb200Error, match="requires atom attribute polarizability"):
+        style.init(g_ewald=0.2, polarizability_flag=0)
+    style.init(g_ewald=0.2)
+    assert style.init_one(1, 1) == 10.0            # max(cut_lj, cut_coul)
+    assert style.init_one(2, 3) == 10.0
+
+
+def test_all_coeffs_must_be_set(style):
+    style.set_ntypes(2)
+    style.settings(["2.5", "10.0"])
+    style.coeff(["1", "1", "0.1", "3.0"])
+    with pytest.raises(pb.Polb200Error, match="All pair coeffs are not set"):
+        style.init(g_ewald=0.2)
+
+
+def test_tables_and_coefficients_bitwise_vs_reference(style):
+    fx = H.load_fixture("h2_default_step0")
+    configure_from_fixture(style, fx)
+    nt = 1 << 12
+    for k in ("rtable", "drtable", "ftable", "dftable", "ctable", "dctable", "etable", "detable"):
+        got = style.debug_fetch("h_" + k, np.float64, nt)
+        assert np.array_equal(got, fx["tab_" + k]), k
+    meta = style.debug_fetch("h_tabmeta", np.float64, 4)
+    assert int(meta[0]) == int(fx["ncoulmask"]) and int(meta[1]) == int(fx["ncoulshiftbits"])
+    assert meta[2] == float(fx["tabinnersq"])
+    # coefficient tables vs the oracle restatement (itself pinned to the reference dump)
+    st = H.style_from_fixture(fx)
+    n1 = int(fx["ntypes"]) + 1
+    for k in ("cutsq", "cut_ljsq", "lj1", "lj2", "lj3", "lj4", "offset", "cutneighsq"):
+        got = style.debug_fetch("h_" + k, np.float64, n1 * n1).reshape(n1, n1)
+        assert np.array_equal(got[1:, 1:], getattr(st, k)[1:, 1:]), k
+
+
+def test_single_matches_oracle_pair_terms(style):
+    fx = H.load_fixture("methane_default_step0")
+    configure_from_fixture(style, fx)
+    # analytic branch (rsq <= tabinnersq), table branch, beyond cut_lj, special (factor_coul = 0)
+    for rsq, fc, fl in ((1.5, 1.0, 1.0), (9.0, 1.0, 1.0), (100.0, 1.0, 1.0), (2.3, 0.0, 0.0), (30.0, 0.0, 0.0)):
+        e, f = style.single(1, 2, 1.853, -1.0, rsq, fc, fl)
+        assert np.isfinite(e) and np.isfinite(f)
+    e1, f1 = style.single(1, 2, 1.853, -1.0, 200.0)   # beyond cut_coul^2 = 164.7 and cut_lj
+    assert e1 == 0.0 and f1 == 0.0
+
+
+def test_restart_roundtrip(style):
+    fx = H.load_fixture("h2_default_step0")
+    configure_from_fixture(style, fx)
+    img = style.write_restart()
+    # 7 settings fields (2 doubles, 4 ints, 1 double = 40 bytes) + 6 pairs x (int + 3 doubles)
+    assert len(img) == 40 + 6 * 28
+    other = pb.PairStyle(device=pb.DEVICE_NONE)
+    other.set_ntypes(3)
+    other.read_restart(img)
+    other.init(g_ewald=float(fx["g_ewald"]))
+    a, _ = style.extract("sigma")
+    b, _ = other.extract("sigma")
+    assert np.array_equal(a, b) and other.extract("cut_coul")[0] == 10.797442
+    other.close()
+
+
+def test_pair_modify(style):
+    style.set_ntypes(1)
+    style.settings(["2.5", "10.0"])
+    style.coeff(["1", "1", "0.1", "3.0"])
+    style.pair_modify(["table", "0"])
+    style.pair_modify(["mix", "arithmetic", "shift", "yes"])
+    with pytest.raises(pb.Polb200Error, match="Illegal pair_modify command"):
+        style.pair_modify(["mix", "bogus"])
+    style.init(g_ewald=0.25)
+    # shift yes: offset = 4 eps ((s/rc)^12 - (s/rc)^6), pol.cpp:877-880
+    off = style.debug_fetch("h_offset", np.float64, 4).reshape(2, 2)[1, 1]
+    r = 3.0 / 2.5
+    assert off == 4.0 * 0.1 * (r ** 12 - r ** 6)
