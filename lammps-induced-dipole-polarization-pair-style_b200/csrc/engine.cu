@@ -96,6 +96,11 @@ struct polb200_handle {
 
   // options
   int sweep_block = BLOCK;
+  bool time_sweeps = false;     // record CUDA events around every k_sweep launch (bench roofline)
+  std::vector<cudaEvent_t> sweep_ev;
+  size_t sweep_ev_used = 0;
+  double sweep_ms_accum = 0.0;
+  long sweep_launches = 0;
 
   // device copies of host-style tables
   DBuf<double> d_coeff;   // 7 tables x (ntypes+1)^2 + cutneighsq
@@ -426,6 +431,28 @@ static bool decide_rebuild(polb200_handle *h, int n)
   return false;
 }
 
+static void sweep_event(polb200_handle *h)
+{
+  if (!h->time_sweeps) return;
+  if (h->sweep_ev_used == h->sweep_ev.size()) {
+    cudaEvent_t e;
+    CUDA_CHECK(cudaEventCreate(&e));
+    h->sweep_ev.push_back(e);
+  }
+  CUDA_CHECK(cudaEventRecord(h->sweep_ev[h->sweep_ev_used++], h->stream));
+}
+
+static void sweep_events_collect(polb200_handle *h)
+{
+  for (size_t k = 0; k + 1 < h->sweep_ev_used; k += 2) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->sweep_ev[k], h->sweep_ev[k + 1]);
+    h->sweep_ms_accum += ms;
+    h->sweep_launches++;
+  }
+  h->sweep_ev_used = 0;
+}
+
 template <int NV>
 static void reduce_partials(polb200_handle *h, int nblocks, double *out, int accumulate)
 {
@@ -511,7 +538,9 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
   double rmin = 0.0;
   if (!st.zodid) {
     const bool gs = st.polar_gs || st.polar_gs_ranked;
-    const int *order = nullptr;
+    // Gauss-Seidel visits atoms in the CALLER's index order (ranked_array = identity, pol.cpp:1127),
+    // i.e. position c -> cell-sorted index invperm[c]; Jacobi does not care about the order.
+    const int *order = gs ? h->invperm.p : nullptr;
     if (st.polar_gs_ranked) {
       // rank metric + stable descending sort, ties by caller index (pol.cpp:192-227,1127-1143)
       h->rmin_bits.ensure(1);
@@ -519,7 +548,7 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
       const unsigned long long init = (unsigned long long)0x408F400000000000ull;  // bits of 1000.0
       CUDA_CHECK(cudaMemcpyAsync(h->rmin_bits.p, &init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
       LAUNCH(h, k_rmin, nrowblocks, BLOCK, n, L, h->xq.p, h->mua.p, h->tm.p, h->rmin_bits.p);
-      LAUNCH(h, k_rank_metric, nrowblocks, BLOCK, n, L, h->xq.p, h->mua.p, h->tm.p, h->rmin_bits.p, h->perm.p, h->metric.p);
+      LAUNCH(h, k_rank_metric, nrowblocks, BLOCK, n, L, h->xq.p, h->mua.p, h->tm.p, h->rmin_bits.p, h->perm.p, h->g_owner.p, h->g_shift.p, h->metric.p);
       // values in caller order = sorted index of caller atom c
       size_t bytes = 0;
       cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, h->metric.p, h->metric2.p, h->invperm.p, h->ranked.p, n, 0, 64, h->stream);
@@ -552,8 +581,10 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
         // Jacobi in fixed mode: the reference runs max_iterations+1 sweeps and discards the last
         // (pol.cpp:1214 returns before the copy), so only max_iterations sweeps shape the result
         if (st.fixed_iteration && iterations >= st.iterations_max) break;
+        sweep_event(h);
         if (list_mode) LAUNCH(h, (k_sweep<true>), nrowblocks, BLOCK, 0, n, order, P, L, A, h->xq.p, cur, h->ef.p, nxt, h->partial.p);
         else LAUNCH(h, (k_sweep<false>), nrowblocks, BLOCK, 0, n, order, P, L, A, h->xq.p, cur, h->ef.p, nxt, h->partial.p);
+        sweep_event(h);
         if (want_change) reduce_partials<1>(h, nrowblocks, h->scal.p + S_CHANGE, 0);
         if (ng) LAUNCH(h, (k_ghost_refresh<false, true>), cdiv(ng, 256), 256, ng, n, h->g_owner.p, h->g_shift.p, h->box, h->xq.p, nxt);
       } else {
@@ -635,6 +666,7 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
     for (size_t k = 0; k < (size_t)3 * n; k++) f[k] += a[k];
   }
 
+  sweep_events_collect(h);
   const double *sc = h->h_scal.p;
   if (eflag_global) {
     out->eng_vdwl = sc[S_PAIR + 0];
@@ -876,7 +908,12 @@ long polb200_launch_count(polb200_t *h, int reset)
 int polb200_set_option(polb200_t *h, const char *name, double value)
 {
   if (!h || !name) return POLB200_ERR_ARG;
-  (void)value;
+  if (!strcmp(name, "time_sweeps")) {
+    h->time_sweeps = value != 0.0;
+    h->sweep_ms_accum = 0.0;
+    h->sweep_launches = 0;
+    return POLB200_OK;
+  }
   h->err = std::string("unknown option ") + name;
   return POLB200_ERR_ARG;
 }
@@ -917,7 +954,21 @@ long polb200_debug_fetch(polb200_t *h, const char *name, void *dst, long capacit
       CUDA_CHECK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
       result = count;
     };
-    if (!strcmp(name, "perm")) fetch(h->perm.p, (size_t)n * 4, n);
+    if (!strcmp(name, "sweep_timing")) {  // {accumulated ms, launches} since time_sweeps was set
+      if (capacity_bytes < 16) throw StyleError{POLB200_ERR_ARG, "debug_fetch: buffer too small"};
+      double v[2] = {h->sweep_ms_accum, (double)h->sweep_launches};
+      memcpy(dst, v, 16);
+      result = 2;
+    } else if (!strcmp(name, "polar_pairs")) {  // ordered pairs inside the dipole cutoff (list mode)
+      if (capacity_bytes < 8) throw StyleError{POLB200_ERR_ARG, "debug_fetch: buffer too small"};
+      h->cnt.ensure(1);
+      CUDA_CHECK(cudaMemsetAsync(h->cnt.p, 0, 8, h->stream));
+      ListRows L{h->rowstart.p, h->neigh.p};
+      LAUNCH(h, k_count_polar_pairs, cdiv(n, WARPS_PER_BLOCK), BLOCK, n, h->P.pc.polar_cutsq, L, h->xq.p, h->cnt.p);
+      CUDA_CHECK(cudaMemcpyAsync(dst, h->cnt.p, 8, cudaMemcpyDeviceToHost, h->stream));
+      CUDA_CHECK(cudaStreamSynchronize(h->stream));
+      result = 1;
+    } else if (!strcmp(name, "perm")) fetch(h->perm.p, (size_t)n * 4, n);
     else if (!strcmp(name, "ghost_owner")) fetch(h->g_owner.p, (size_t)ng * 4, ng);   // sorted owned index
     else if (!strcmp(name, "ghost_shift")) fetch(h->g_shift.p, (size_t)ng * 4, ng);   // packed code
     else if (!strcmp(name, "rowstart")) fetch(h->rowstart.p, (size_t)(n + 1) * 8, n + 1);

@@ -666,29 +666,86 @@ k_rmin(int nloc, ListRows L, const double4 *__restrict__ xq, const double4 *__re
   if (lane == 0) atomicMin(rmin_bits, (unsigned long long)__double_as_longlong(best));
 }
 
+// Index the reference would give an owned or ghost atom: owned atoms keep the caller's index, ghosts
+// follow in CommBrick::borders creation order (src/comm_brick.cpp:726-790): dimension by dimension,
+// the +prd swap before the -prd swap, each swap scanning the atoms created so far in index order.
+// That order is the lexicographic order of (z stage, y stage, x stage, owner index), stage = 0 for
+// no shift, 1 for +prd, 2 for -prd.
+__device__ __forceinline__ unsigned long long reference_index_key(int j, int nloc, const int *__restrict__ perm,
+                                                                  const int *__restrict__ g_owner,
+                                                                  const int *__restrict__ g_shift)
+{
+  if (j < nloc) return (unsigned long long)perm[j];
+  const int code = g_shift[j - nloc];
+  const int sx = (code & 3) - 1, sy = ((code >> 2) & 3) - 1, sz = ((code >> 4) & 3) - 1;
+  const int cx = sx == 0 ? 0 : (sx > 0 ? 1 : 2), cy = sy == 0 ? 0 : (sy > 0 ? 1 : 2), cz = sz == 0 ? 0 : (sz > 0 ? 1 : 2);
+  return ((unsigned long long)((cz * 3 + cy) * 3 + cx + 1) << 32) | (unsigned long long)perm[g_owner[j - nloc]];
+}
+
+// rank_metric[i] = sum of alpha_i*alpha_j over partners closer than 1.5*rmin (pol.cpp:214-226).
+// Ties between metrics decide the Gauss-Seidel order, and metrics are sums of a few products whose
+// rounding depends on the summation order, so the terms are added in the reference's j order.
+constexpr int RANK_CAP = 64;
 __global__ void __launch_bounds__(BLOCK)
 k_rank_metric(int nloc, ListRows L, const double4 *__restrict__ xq, const double4 *__restrict__ mua,
               const int2 *__restrict__ tm, const unsigned long long *__restrict__ rmin_bits,
-              const int *__restrict__ perm, double *__restrict__ metric_caller)
+              const int *__restrict__ perm, const int *__restrict__ g_owner, const int *__restrict__ g_shift,
+              double *__restrict__ metric_caller)
 {
-  const int lane = threadIdx.x & 31;
-  const int s = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  __shared__ unsigned long long s_key[WARPS_PER_BLOCK][RANK_CAP];
+  __shared__ double s_term[WARPS_PER_BLOCK][RANK_CAP];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int s = blockIdx.x * WARPS_PER_BLOCK + warp;
   if (s >= nloc) return;
   const double rmin = __longlong_as_double((long long)*rmin_bits);
   const double4 xi = xq[s];
   const double ai = mua[s].w;
   const int moli = tm[s].y;
-  double m = 0.0;
+  int cnt = 0;
+  double overflow = 0.0;
   const unsigned long long beg = L.rowstart[s], end = L.rowstart[s + 1];
-  for (unsigned long long k = beg + lane; k < end; k += 32) {
-    const int j = L.neigh[k] & NEIGHMASK;
-    const double4 xj = ld4(xq + j);
-    const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
-    const double r = sqrt(rsq_nofma(dx, dy, dz));
-    if (rmin * 1.5 > r && (moli != tm[j].y || moli == 0)) m += ai * mua[j].w;
+  for (unsigned long long k0 = beg; k0 < end; k0 += 32) {
+    const unsigned long long k = k0 + lane;
+    bool ok = false;
+    int j = 0;
+    if (k < end) {
+      j = L.neigh[k] & NEIGHMASK;
+      const double4 xj = ld4(xq + j);
+      const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+      const double r = sqrt(rsq_nofma(dx, dy, dz));
+      ok = rmin * 1.5 > r && (moli != tm[j].y || moli == 0);
+    }
+    const unsigned m = __ballot_sync(FULL, ok);
+    if (ok) {
+      const int slot = cnt + __popc(m & ((1u << lane) - 1));
+      const double term = ai * mua[j].w;
+      if (slot < RANK_CAP) {
+        s_key[warp][slot] = reference_index_key(j, nloc, perm, g_owner, g_shift);
+        s_term[warp][slot] = term;
+      } else overflow += term;
+    }
+    cnt += __popc(m);
   }
-  m = warp_sum(m);
-  if (lane == 0) metric_caller[perm[s]] = m;
+  overflow = warp_sum(overflow);
+  __syncwarp();
+  if (lane == 0) {
+    const int n = cnt < RANK_CAP ? cnt : RANK_CAP;
+    for (int a = 1; a < n; a++) {  // insertion sort by reference index
+      const unsigned long long kk = s_key[warp][a];
+      const double tt = s_term[warp][a];
+      int b = a - 1;
+      while (b >= 0 && s_key[warp][b] > kk) {
+        s_key[warp][b + 1] = s_key[warp][b];
+        s_term[warp][b + 1] = s_term[warp][b];
+        b--;
+      }
+      s_key[warp][b + 1] = kk;
+      s_term[warp][b + 1] = tt;
+    }
+    double msum = 0.0;
+    for (int a = 0; a < n; a++) msum += s_term[warp][a];
+    metric_caller[perm[s]] = msum + overflow;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -837,6 +894,25 @@ __global__ void k_check_distance(int nloc, const double *__restrict__ x, const d
   if (i >= nloc) return;
   const double dx = x[3 * i] - xhold[3 * i], dy = x[3 * i + 1] - xhold[3 * i + 1], dz = x[3 * i + 2] - xhold[3 * i + 2];
   if (rsq_nofma(dx, dy, dz) > triggersq) atomicOr(flag, 1);
+}
+
+// number of list entries inside the dipole cutoff (the P of the roofline model)
+__global__ void __launch_bounds__(BLOCK)
+k_count_polar_pairs(int nloc, double cutsq, ListRows L, const double4 *__restrict__ xq,
+                    unsigned long long *__restrict__ total)
+{
+  const int lane = threadIdx.x & 31;
+  const int s = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (s >= nloc) return;
+  const double4 xi = xq[s];
+  unsigned long long c = 0;
+  for (unsigned long long k = L.rowstart[s] + lane; k < L.rowstart[s + 1]; k += 32) {
+    const double4 xj = ld4(xq + (L.neigh[k] & NEIGHMASK));
+    const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+    if (dx * dx + dy * dy + dz * dz < cutsq) c++;
+  }
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(FULL, c, o);
+  if (lane == 0) atomicAdd(total, c);
 }
 
 // rows of a [n][w] caller-order int table into sorted order

@@ -40,4 +40,5 @@ rm -f compute_dihedral.* compute_improper.* fix_nve_sphere.* fix_nh_sphere.* fix
 python3 "$HERE/patch_ref.py" "$W/src"
 make -j"$JOBS" serial > "$W/build.log" 2>&1 || { tail -40 "$W/build.log"; exit 1; }
 cp lmp_serial "$OUT/lmp_serial"
+strip "$OUT/lmp_serial"
 echo "build_ref: built $OUT/lmp_serial"

@@ -101,7 +101,9 @@ def test_multi_step_with_stale_lists_and_use_previous(style, case):
         if key:   # the reference authors' own log, 8 printed digits
             row = logs[key]["rows"][step]
             for col, val in (("E_vdwl", res.eng_vdwl), ("E_coul", res.eng_coul), ("E_pol", res.eng_pol)):
-                assert f"{val:.7g}" == f"{float(row[col]):.7g}", (step, col, val, row[col])
+                ref = float(row[col])
+                half_unit = 0.5 * 10.0 ** (np.floor(np.log10(abs(ref))) - 7)   # 8 printed digits
+                assert abs(val - ref) <= 1.02 * half_unit, (step, col, val, row[col])
         mu_prev = mu
         step += 1
     assert step >= 2
@@ -216,3 +218,21 @@ def test_config2_32k_list_mode_sampled_against_oracle(style):
     assert abs(res.eng_pol - ref["eng_pol"]) < TOL * abs(ref["eng_pol"])
     # size-independent: Newton's third law, total pair force vanishes
     assert np.abs(f.sum(0)).max() < 1e-9 * np.abs(f).max() * np.sqrt(sysm.n)
+
+
+@pytest.mark.parametrize("words", ["polar_gs_ranked yes fixed_iteration yes max_iterations 3",
+                                   "polar_gs_ranked no polar_gs yes fixed_iteration yes max_iterations 2"])
+def test_sequential_gs_is_iteration_for_iteration_the_oracle(style, words):
+    """Same visiting order, same in-place updates: after a FIXED number of Gauss-Seidel sweeps the device
+    dipoles equal the literal restatement's to 1e-10 (needs the rank order incl. tie-breaks to be identical)."""
+    fx = dict(H.load_fixture("h2_default_step0"))
+    base = "pair_style lj/cut/coul/long/polarization 2.5 10.797442 damp_type exponential damp 2.1304 use_previous yes "
+    fx["pair_style"] = np.array(base + words)
+    configure_from_fixture(style, fx)
+    res, mu, ef, f = run_fixture(style, fx)
+    sysm, st = H.system_from_fixture(fx), H.style_from_fixture(fx)
+    ref = P.compute(sysm, st, mu_in=fx["mu_in"], use_matrix=False)
+    assert res.iterations == ref["iterations"]
+    assert H.rel_err(mu, ref["mu"]) < TOL
+    assert abs(res.eng_pol - ref["eng_pol"]) < TOL * abs(ref["eng_pol"])
+    assert np.abs(f - ref["f"]).max() < TOL * np.abs(ref["f"]).max()
