@@ -96,6 +96,9 @@ struct polb200_handle {
 
   // options
   int sweep_block = BLOCK;
+  double bin_div = 4.0;          // neighbor cutoff / cell width
+  int sweep_variant = 20;        // 0: k_sweep<true> (first version), 1/2: k_sweep_list2 with PF = 1/2
+  bool use_tight = true;         // per-step tight list
   bool time_sweeps = false;     // record CUDA events around every k_sweep launch (bench roofline)
   std::vector<cudaEvent_t> sweep_ev;
   size_t sweep_ev_used = 0;
@@ -124,7 +127,9 @@ struct polb200_handle {
   DBuf<int> cl_start, cg_start, stencil;
   DBuf<int> s_nspecial, s_special;
   DBuf<unsigned long long> cnt, rowstart;
-  DBuf<int> neigh;
+  DBuf<int> neigh, tneigh, tcount;
+  DBuf<double2> s12;             // per-step radial cache aligned with the tight list
+  bool s12_valid = false;
   DBuf<char> cub_tmp;
   DBuf<double> partial, scal;
   DBuf<int> flags;
@@ -211,14 +216,17 @@ static void upload_params(polb200_handle *h)
   h->have_lists = false;
 }
 
-// cell grid over the box extended by the ghost cutoff; cells of about half the largest neighbor
-// cutoff, as NBinStandard::setup_bins chooses (src/nbin_standard.cpp:93-99)
+// Fine cell grid over the box extended by the ghost cutoff.  Cells are cut/bin_div wide (LAMMPS uses
+// cut/2, src/nbin_standard.cpp:93-99; a finer grid gives a tighter candidate set and, because atoms are
+// stored in cell order with x fastest, longer contiguous neighbour runs).  The stencil is a list of
+// (dy,dz) cell rows with the x half-extent that can still be within the cutoff (closest-approach
+// distance between cells, cf. NStencil::bin_distance, src/nstencil.cpp:205-223).
 static void setup_grid(polb200_handle *h)
 {
   const HostStyle &st = h->style;
   Grid &g = h->P.grid;
   const double cut = st.cutneighmax;
-  const double binsize = 0.5 * cut;
+  const double binsize = cut / h->bin_div;
   std::vector<int> stencil;
   int sx[3];
   double cs[3];
@@ -242,16 +250,17 @@ static void setup_grid(polb200_handle *h)
   }
   if (ncell > (1l << 30)) throw StyleError{POLB200_ERR_UNSUPPORTED, "Too many neighbor bins"};
   g.ncell = (int)ncell;
-  // full stencil pruned by the closest distance between cells (cf. NStencil::bin_distance,
-  // src/nstencil.cpp:205-223); order: z, y, x ascending
+  auto gap = [](int o, double c) { return o > 0 ? (o - 1) * c : (o < 0 ? (o + 1) * c : 0.0); };
   for (int k = -sx[2]; k <= sx[2]; k++)
-    for (int j = -sx[1]; j <= sx[1]; j++)
-      for (int i = -sx[0]; i <= sx[0]; i++) {
-        auto gap = [](int o, double c) { return o > 0 ? (o - 1) * c : (o < 0 ? (o + 1) * c : 0.0); };
-        const double dx = gap(i, cs[0]), dy = gap(j, cs[1]), dz = gap(k, cs[2]);
-        if (dx * dx + dy * dy + dz * dz <= cut * cut)
-          stencil.push_back((i + 16) | ((j + 16) << 6) | ((k + 16) << 12));
+    for (int j = -sx[1]; j <= sx[1]; j++) {
+      const double dy = gap(j, cs[1]), dz = gap(k, cs[2]);
+      int xext = -1;
+      for (int i = 0; i <= sx[0]; i++) {
+        const double dx = gap(i, cs[0]);
+        if (dx * dx + dy * dy + dz * dz <= cut * cut) xext = i;
       }
+      if (xext >= 0) stencil.push_back((j + 16) | ((k + 16) << 6) | (xext << 12));
+    }
   h->nstencil = (int)stencil.size();
   h->stencil.ensure(stencil.size());
   CUDA_CHECK(cudaMemcpy(h->stencil.p, stencil.data(), stencil.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -453,6 +462,101 @@ static void sweep_events_collect(polb200_handle *h)
   h->sweep_ev_used = 0;
 }
 
+// list-mode sweep over ranked positions [beg,end): picks the kernel variant.  Returns the number of
+// partial sums written to h->partial (rows for the v2 kernels, blocks for the first version).
+template <bool DAMP, int PF, int WPB, int MINB>
+static int launch_v2(polb200_handle *h, int beg, int end, const int *order, const DevParams &P, ListRows L,
+                     const double4 *cur, double4 *nxt, bool change)
+{
+  const int nb = cdiv(end - beg, WPB);
+  if (change)
+    LAUNCH(h, (k_sweep_list2<DAMP, PF, WPB, MINB, true>), nb, WPB * 32, beg, end, order, P, L, h->xq.p, cur, h->ef.p, nxt, h->partial.p);
+  else
+    LAUNCH(h, (k_sweep_list2<DAMP, PF, WPB, MINB, false>), nb, WPB * 32, beg, end, order, P, L, h->xq.p, cur, h->ef.p, nxt, h->partial.p);
+  return end - beg;
+}
+
+template <bool DAMP, int WPB, int MINB>
+static int launch_v3(polb200_handle *h, int beg, int end, const int *order, const DevParams &P, ListRows L,
+                     const double4 *cur, double4 *nxt, bool change)
+{
+  const int nb = cdiv(end - beg, WPB);
+  if (change)
+    LAUNCH(h, (k_sweep_list3<DAMP, WPB, MINB, true>), nb, WPB * 32, beg, end, order, P, L, h->xq.p, cur, h->ef.p, nxt, h->partial.p);
+  else
+    LAUNCH(h, (k_sweep_list3<DAMP, WPB, MINB, false>), nb, WPB * 32, beg, end, order, P, L, h->xq.p, cur, h->ef.p, nxt, h->partial.p);
+  return end - beg;
+}
+
+template <int WPB, int MINB>
+static int launch_cached(polb200_handle *h, int beg, int end, const int *order, ListRows L, const double4 *cur,
+                         double4 *nxt, bool change)
+{
+  const int nb = cdiv(end - beg, WPB);
+  if (change)
+    LAUNCH(h, (k_sweep_cached<WPB, MINB, true>), nb, WPB * 32, beg, end, order, L, h->s12.p, h->xq.p, cur, h->ef.p, nxt, h->partial.p);
+  else
+    LAUNCH(h, (k_sweep_cached<WPB, MINB, false>), nb, WPB * 32, beg, end, order, L, h->s12.p, h->xq.p, cur, h->ef.p, nxt, h->partial.p);
+  return end - beg;
+}
+
+static int launch_list_sweep(polb200_handle *h, int beg, int end, const int *order, const DevParams &P, ListRows L,
+                             AllPairRows A, const double4 *cur, double4 *nxt, bool change)
+{
+  const bool damp = P.pc.damping_exponential != 0;
+  h->partial.ensure((size_t)(end - beg) + 64);
+  if (h->sweep_variant >= 20 && !h->s12_valid && h->s12.cap < h->neigh.cap) {
+    // the radial cache costs 16 B per list entry: keep it only while it fits comfortably in free HBM
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    if ((double)h->neigh.cap * sizeof(double2) > 0.5 * (double)free_b) h->sweep_variant = 6;  // matrix-free
+  }
+  if (h->sweep_variant >= 20) {
+    if (!h->s12_valid) {  // first sweep of this step: build the radial cache
+      h->s12.ensure(h->neigh.cap);
+      const int nrb = cdiv(h->nloc, WARPS_PER_BLOCK);
+      if (damp) LAUNCH(h, (k_radial_cache<true>), nrb, BLOCK, h->nloc, P, L, h->xq.p, h->s12.p);
+      else LAUNCH(h, (k_radial_cache<false>), nrb, BLOCK, h->nloc, P, L, h->xq.p, h->s12.p);
+      h->s12_valid = true;
+    }
+    switch (h->sweep_variant) {
+      case 21: return launch_cached<8, 4>(h, beg, end, order, L, cur, nxt, change);
+      case 22: return launch_cached<4, 12>(h, beg, end, order, L, cur, nxt, change);
+      case 23: return launch_cached<8, 6>(h, beg, end, order, L, cur, nxt, change);
+      default: return launch_cached<4, 8>(h, beg, end, order, L, cur, nxt, change);
+    }
+  }
+#define V2(PF, WPB, MINB) \
+  return damp ? launch_v2<true, PF, WPB, MINB>(h, beg, end, order, P, L, cur, nxt, change) \
+              : launch_v2<false, PF, WPB, MINB>(h, beg, end, order, P, L, cur, nxt, change)
+  switch (h->sweep_variant) {
+    case 0: {
+      const int nb = cdiv(end - beg, WARPS_PER_BLOCK);
+      LAUNCH(h, (k_sweep<true>), nb, BLOCK, beg, end, order, P, L, A, h->xq.p, cur, h->ef.p, nxt, h->partial.p);
+      return nb;
+    }
+    case 2: V2(2, 8, 3);
+    case 3: V2(1, 4, 8);
+    case 4: V2(1, 8, 5);
+    case 5: V2(2, 8, 4);
+    case 6: V2(1, 4, 10);
+    case 7: V2(1, 2, 16);
+#define V3(WPB, MINB) \
+  return damp ? launch_v3<true, WPB, MINB>(h, beg, end, order, P, L, cur, nxt, change) \
+              : launch_v3<false, WPB, MINB>(h, beg, end, order, P, L, cur, nxt, change)
+    case 11: V3(4, 6);
+    case 12: V3(4, 8);
+    case 13: V3(8, 3);
+    case 14: V3(4, 5);
+#undef V3
+    case 8: V2(3, 4, 10);
+    case 9: V2(3, 8, 4);
+    case 10: V2(3, 4, 8);
+    default: V2(1, 8, 4);
+  }
+#undef V2
+}
+
 template <int NV>
 static void reduce_partials(polb200_handle *h, int nblocks, double *out, int accumulate)
 {
@@ -515,16 +619,25 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
   CUDA_CHECK(cudaEventRecord(h->ev[1], h->stream));
 
   const DevParams &P = h->P;
-  ListRows L{h->rowstart.p, h->neigh.p};
+  ListRows L{h->rowstart.p, h->neigh.p, nullptr};
   AllPairRows A{n, h->perm.p};
+  h->s12_valid = false;
+  if (h->use_tight) {
+    // every pair kernel of this step only needs partners within the largest interaction cutoff
+    double reach = st.cutforce > st.cut_coul ? st.cutforce : st.cut_coul;
+    h->tneigh.ensure(h->neigh.cap);
+    h->tcount.ensure(n);
+    LAUNCH(h, k_tighten, nrowblocks, BLOCK, n, reach * reach, h->rowstart.p, h->neigh.p, h->xq.p, h->tneigh.p, h->tcount.p);
+    L = ListRows{h->rowstart.p, h->tneigh.p, h->tcount.p};
+  }
 
   // ---- stage 2: LJ + Coulomb (+ static field) ----
   if (list_mode) {
-    if (evflag) LAUNCH(h, (k_pair<true, true>), nrowblocks, BLOCK, n, P, h->xq.p, h->tm.p, L.rowstart, L.neigh, h->f_pair.p, h->ef.p, h->partial.p);
-    else LAUNCH(h, (k_pair<false, true>), nrowblocks, BLOCK, n, P, h->xq.p, h->tm.p, L.rowstart, L.neigh, h->f_pair.p, h->ef.p, h->partial.p);
+    if (evflag) LAUNCH(h, (k_pair<true, true>), nrowblocks, BLOCK, n, P, h->xq.p, h->tm.p, L, h->f_pair.p, h->ef.p, h->partial.p);
+    else LAUNCH(h, (k_pair<false, true>), nrowblocks, BLOCK, n, P, h->xq.p, h->tm.p, L, h->f_pair.p, h->ef.p, h->partial.p);
   } else {
-    if (evflag) LAUNCH(h, (k_pair<true, false>), nrowblocks, BLOCK, n, P, h->xq.p, h->tm.p, L.rowstart, L.neigh, h->f_pair.p, h->ef.p, h->partial.p);
-    else LAUNCH(h, (k_pair<false, false>), nrowblocks, BLOCK, n, P, h->xq.p, h->tm.p, L.rowstart, L.neigh, h->f_pair.p, h->ef.p, h->partial.p);
+    if (evflag) LAUNCH(h, (k_pair<true, false>), nrowblocks, BLOCK, n, P, h->xq.p, h->tm.p, L, h->f_pair.p, h->ef.p, h->partial.p);
+    else LAUNCH(h, (k_pair<false, false>), nrowblocks, BLOCK, n, P, h->xq.p, h->tm.p, L, h->f_pair.p, h->ef.p, h->partial.p);
   }
   if (evflag) reduce_partials<NPAIR_PART>(h, nrowblocks, h->scal.p + S_PAIR, 0);
   if (!list_mode) LAUNCH(h, k_static_allpairs, nrowblocks, BLOCK, n, P, h->xq.p, h->tm.p, h->perm.p, h->ef.p);
@@ -547,8 +660,9 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
       h->metric.ensure(n); h->metric2.ensure(n); h->ranked.ensure(n); h->ranked_in.ensure(n);
       const unsigned long long init = (unsigned long long)0x408F400000000000ull;  // bits of 1000.0
       CUDA_CHECK(cudaMemcpyAsync(h->rmin_bits.p, &init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
-      LAUNCH(h, k_rmin, nrowblocks, BLOCK, n, L, h->xq.p, h->mua.p, h->tm.p, h->rmin_bits.p);
-      LAUNCH(h, k_rank_metric, nrowblocks, BLOCK, n, L, h->xq.p, h->mua.p, h->tm.p, h->rmin_bits.p, h->perm.p, h->g_owner.p, h->g_shift.p, h->metric.p);
+      ListRows Lfull{h->rowstart.p, h->neigh.p, nullptr};
+      LAUNCH(h, k_rmin, nrowblocks, BLOCK, n, Lfull, h->xq.p, h->mua.p, h->tm.p, h->rmin_bits.p);
+      LAUNCH(h, k_rank_metric, nrowblocks, BLOCK, n, Lfull, h->xq.p, h->mua.p, h->tm.p, h->rmin_bits.p, h->perm.p, h->g_owner.p, h->g_shift.p, h->metric.p);
       // values in caller order = sorted index of caller atom c
       size_t bytes = 0;
       cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, h->metric.p, h->metric2.p, h->invperm.p, h->ranked.p, n, 0, 64, h->stream);
@@ -582,10 +696,11 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
         // (pol.cpp:1214 returns before the copy), so only max_iterations sweeps shape the result
         if (st.fixed_iteration && iterations >= st.iterations_max) break;
         sweep_event(h);
-        if (list_mode) LAUNCH(h, (k_sweep<true>), nrowblocks, BLOCK, 0, n, order, P, L, A, h->xq.p, cur, h->ef.p, nxt, h->partial.p);
+        int nparts = nrowblocks;
+        if (list_mode) nparts = launch_list_sweep(h, 0, n, order, P, L, A, cur, nxt, want_change);
         else LAUNCH(h, (k_sweep<false>), nrowblocks, BLOCK, 0, n, order, P, L, A, h->xq.p, cur, h->ef.p, nxt, h->partial.p);
         sweep_event(h);
-        if (want_change) reduce_partials<1>(h, nrowblocks, h->scal.p + S_CHANGE, 0);
+        if (want_change) reduce_partials<1>(h, nparts, h->scal.p + S_CHANGE, 0);
         if (ng) LAUNCH(h, (k_ghost_refresh<false, true>), cdiv(ng, 256), 256, ng, n, h->g_owner.p, h->g_shift.p, h->box, h->xq.p, nxt);
       } else {
         // ranked colouring sweep: chunks of the ranked order, Jacobi inside, Gauss-Seidel between
@@ -593,9 +708,10 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
           const int beg = (int)(((long)c * n) / nchunks), end = (int)(((long)(c + 1) * n) / nchunks);
           if (end <= beg) continue;
           const int nb = cdiv(end - beg, WARPS_PER_BLOCK);
-          if (list_mode) LAUNCH(h, (k_sweep<true>), nb, BLOCK, beg, end, order, P, L, A, h->xq.p, cur, h->ef.p, nxt, h->partial.p);
+          int nparts = nb;
+          if (list_mode) nparts = launch_list_sweep(h, beg, end, order, P, L, A, cur, nxt, want_change);
           else LAUNCH(h, (k_sweep<false>), nb, BLOCK, beg, end, order, P, L, A, h->xq.p, cur, h->ef.p, nxt, h->partial.p);
-          if (want_change) reduce_partials<1>(h, nb, h->scal.p + S_CHANGE, c > 0);
+          if (want_change) reduce_partials<1>(h, nparts, h->scal.p + S_CHANGE, c > 0);
           LAUNCH(h, k_commit_rows, cdiv(end - beg, 256), 256, beg, end, order, nxt, cur);
           if (ng) LAUNCH(h, (k_ghost_refresh<false, true>), cdiv(ng, 256), 256, ng, n, h->g_owner.p, h->g_shift.p, h->box, h->xq.p, cur);
         }
@@ -742,6 +858,7 @@ int polb200_create(polb200_t **out, int device)
   }
   polb200_t *h = new polb200_handle();
   h->device = device;
+  if (const char *v = getenv("POLB200_SWEEP_VARIANT")) h->sweep_variant = atoi(v);  // experiments only
   int rc = guarded(h, [&] {
     CUDA_CHECK(cudaSetDevice(device));
     CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -771,9 +888,10 @@ void polb200_destroy(polb200_t *h)
   for (auto *b : {&h->c_type, &h->c_mol, &h->c_tag, &h->c_nspecial, &h->c_special, &h->tag, &h->perm,
                   &h->invperm, &h->keys, &h->keys2, &h->vals, &h->vals2, &h->g_owner_u, &h->g_shift_u,
                   &h->g_owner, &h->g_shift, &h->cl_start, &h->cg_start, &h->stencil, &h->s_nspecial,
-                  &h->s_special, &h->neigh, &h->flags, &h->ranked, &h->ranked_in})
+                  &h->s_special, &h->neigh, &h->tneigh, &h->tcount, &h->flags, &h->ranked, &h->ranked_in})
     b->release();
   for (auto *b : {&h->xq, &h->mua, &h->mub, &h->ef, &h->f_pair, &h->f_pol}) b->release();
+  h->s12.release();
   h->tm.release(); h->cnt.release(); h->rowstart.release(); h->cub_tmp.release(); h->rmin_bits.release();
   h->h_stage.release(); h->h_scal.release(); h->h_int.release();
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
@@ -908,6 +1026,20 @@ long polb200_launch_count(polb200_t *h, int reset)
 int polb200_set_option(polb200_t *h, const char *name, double value)
 {
   if (!h || !name) return POLB200_ERR_ARG;
+  if (!strcmp(name, "sweep_variant")) {
+    h->sweep_variant = (int)value;
+    return POLB200_OK;
+  }
+  if (!strcmp(name, "bin_div")) {
+    if (!(value >= 1.0 && value <= 12.0)) return POLB200_ERR_ARG;
+    h->bin_div = value;
+    h->have_lists = false;
+    return POLB200_OK;
+  }
+  if (!strcmp(name, "use_tight")) {
+    h->use_tight = value != 0.0;
+    return POLB200_OK;
+  }
   if (!strcmp(name, "time_sweeps")) {
     h->time_sweeps = value != 0.0;
     h->sweep_ms_accum = 0.0;
@@ -963,7 +1095,7 @@ long polb200_debug_fetch(polb200_t *h, const char *name, void *dst, long capacit
       if (capacity_bytes < 8) throw StyleError{POLB200_ERR_ARG, "debug_fetch: buffer too small"};
       h->cnt.ensure(1);
       CUDA_CHECK(cudaMemsetAsync(h->cnt.p, 0, 8, h->stream));
-      ListRows L{h->rowstart.p, h->neigh.p};
+      ListRows L{h->rowstart.p, h->neigh.p, nullptr};
       LAUNCH(h, k_count_polar_pairs, cdiv(n, WARPS_PER_BLOCK), BLOCK, n, h->P.pc.polar_cutsq, L, h->xq.p, h->cnt.p);
       CUDA_CHECK(cudaMemcpyAsync(dst, h->cnt.p, 8, cudaMemcpyDeviceToHost, h->stream));
       CUDA_CHECK(cudaStreamSynchronize(h->stream));

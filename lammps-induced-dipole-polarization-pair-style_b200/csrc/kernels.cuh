@@ -40,6 +40,35 @@ struct DevParams {
 };
 
 // ---------------------------------------------------------------------------------------------------
+// row enumerators: how a warp walks the partners of owned atom s
+// ---------------------------------------------------------------------------------------------------
+// A partner is described from the point of view of the reference's pair loop: `a` is the atom the
+// pair expressions treat as "i" (lower index), del = x_a - image(x_b), and `self_is_a` tells whether
+// the row atom is a.  List mode: the row atom is always a (del = x_i - x_j over ghosts).  All-pairs
+// mode: orientation follows the caller's atom indices so that every pair is evaluated with exactly
+// the operands the reference uses.
+struct Partner {
+  int j;
+  double dx, dy, dz, rsq;
+  bool self_is_a;
+};
+
+struct ListRows {
+  const unsigned long long *rowstart;
+  const int *neigh;
+  const int *rowcount;  // non-null: row s holds rowcount[s] entries from rowstart[s] (per-step tight list)
+  __device__ __forceinline__ unsigned long long begin(int s) const { return rowstart[s]; }
+  __device__ __forceinline__ unsigned long long end(int s) const
+  {
+    return rowcount ? rowstart[s] + (unsigned long long)rowcount[s] : rowstart[s + 1];
+  }
+};
+struct AllPairRows {
+  int nloc;
+  const int *perm;  // sorted -> caller index
+};
+
+// ---------------------------------------------------------------------------------------------------
 // small device helpers
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v)
@@ -289,7 +318,7 @@ template <bool FILL>
 __global__ void k_neigh_build(int nloc, DevParams P, const double4 *__restrict__ xq,
                               const int2 *__restrict__ tm, const int *__restrict__ tag,
                               const int *__restrict__ cl_start, const int *__restrict__ cg_start,
-                              int nstencil, const int *__restrict__ stencil,  // packed dx,dy,dz (+16 each, 6 bits)
+                              int nstencil, const int *__restrict__ stencil,  // rows: (dy+16) | (dz+16)<<6 | xext<<12
                               const int *__restrict__ nspecial, const int *__restrict__ special, int maxspecial,
                               unsigned long long *__restrict__ count,
                               const unsigned long long *__restrict__ rowstart, int *__restrict__ neigh)
@@ -306,14 +335,18 @@ __global__ void k_neigh_build(int nloc, DevParams P, const double4 *__restrict__
   const unsigned long long base = FILL ? rowstart[s] : 0ull;
   const bool has_special = nspecial != nullptr && nspecial[3 * s + 2] > 0;
 
+  // The atoms are sorted by fine cell with x fastest, so each stencil row (dy,dz) covers ONE contiguous
+  // index range per partition (owned / ghost): lanes walk long runs of consecutive records and the
+  // rows of the list come out ascending in index with long contiguous stretches (gather locality).
   for (int k = 0; k < nstencil; k++) {
     const int code = stencil[k];
-    const int ox = cx + ((code & 63) - 16), oy = cy + (((code >> 6) & 63) - 16), oz = cz + (((code >> 12) & 63) - 16);
-    if (ox < 0 || oy < 0 || oz < 0 || ox >= P.grid.nc[0] || oy >= P.grid.nc[1] || oz >= P.grid.nc[2]) continue;
-    const int cell = (oz * P.grid.nc[1] + oy) * P.grid.nc[0] + ox;
+    const int oy = cy + ((code & 63) - 16), oz = cz + (((code >> 6) & 63) - 16), xext = code >> 12;
+    if (oy < 0 || oz < 0 || oy >= P.grid.nc[1] || oz >= P.grid.nc[2]) continue;
+    const int xlo = max(cx - xext, 0), xhi = min(cx + xext, P.grid.nc[0] - 1);
+    const int rowbase = (oz * P.grid.nc[1] + oy) * P.grid.nc[0];
     for (int part = 0; part < 2; part++) {
-      const int beg = part ? nloc + cg_start[cell] : cl_start[cell];
-      const int end = part ? nloc + cg_start[cell + 1] : cl_start[cell + 1];
+      const int beg = part ? nloc + cg_start[rowbase + xlo] : cl_start[rowbase + xlo];
+      const int end = part ? nloc + cg_start[rowbase + xhi + 1] : cl_start[rowbase + xhi + 1];
       for (int j0 = beg; j0 < end; j0 += 32) {
         const int j = j0 + lane;
         bool ok = false;
@@ -342,6 +375,36 @@ __global__ void k_neigh_build(int nloc, DevParams P, const double4 *__restrict__
   if (!FILL && lane == 0) count[s] = n;
 }
 
+// Per-step "tight" list: the entries of the skin list that are inside the interaction range at the
+// CURRENT positions (rsq <= reach2, same no-FMA rsq the pair kernels test), compacted in place order
+// into a second array with the same row offsets.  One pass per step; every per-pair kernel of the
+// step (stage 2, the 30+ sweeps of stage 3, stage 4) then runs without cutoff divergence.
+__global__ void __launch_bounds__(BLOCK)
+k_tighten(int nloc, double reach2, const unsigned long long *__restrict__ rowstart, const int *__restrict__ neigh,
+          const double4 *__restrict__ xq, int *__restrict__ tneigh, int *__restrict__ tcount)
+{
+  const int lane = threadIdx.x & 31;
+  const int s = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (s >= nloc) return;
+  const double4 xi = xq[s];
+  const unsigned long long beg = rowstart[s], end = rowstart[s + 1];
+  int n = 0;
+  for (unsigned long long k0 = beg; k0 < end; k0 += 32) {
+    const unsigned long long k = k0 + lane;
+    bool ok = false;
+    int raw = 0;
+    if (k < end) {
+      raw = neigh[k];
+      const double4 xj = ld4(xq + (raw & NEIGHMASK));
+      ok = rsq_nofma(xi.x - xj.x, xi.y - xj.y, xi.z - xj.z) <= reach2;
+    }
+    const unsigned m = __ballot_sync(FULL, ok);
+    if (ok) tneigh[beg + n + __popc(m & ((1u << lane) - 1))] = raw;
+    n += __popc(m);
+  }
+  if (lane == 0) tcount[s] = n;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // stage 2: LJ + real-space Ewald Coulomb (+ static field in list mode) over the full list
 // ---------------------------------------------------------------------------------------------------
@@ -350,8 +413,7 @@ constexpr int NPAIR_PART = 8;
 
 template <bool EVFLAG, bool FIELD>
 __global__ void __launch_bounds__(BLOCK)
-k_pair(int nloc, DevParams P, const double4 *__restrict__ xq, const int2 *__restrict__ tm,
-       const unsigned long long *__restrict__ rowstart, const int *__restrict__ neigh,
+k_pair(int nloc, DevParams P, const double4 *__restrict__ xq, const int2 *__restrict__ tm, ListRows L,
        double4 *__restrict__ f_pair, double4 *__restrict__ ef, double *__restrict__ partial)
 {
   const int lane = threadIdx.x & 31;
@@ -362,9 +424,9 @@ k_pair(int nloc, DevParams P, const double4 *__restrict__ xq, const int2 *__rest
     const int2 tmi = tm[s];
     const int n1 = P.pc.ntypes + 1;
     double fx = 0, fy = 0, fz = 0, ex = 0, ey = 0, ez = 0;
-    const unsigned long long beg = rowstart[s], end = rowstart[s + 1];
+    const unsigned long long beg = L.begin(s), end = L.end(s);
     for (unsigned long long k = beg + lane; k < end; k += 32) {
-      const int raw = neigh[k];
+      const int raw = L.neigh[k];
       const int j = raw & NEIGHMASK, sb = (raw >> SBBITS) & 3;
       const double4 xj = ld4(xq + j);
       const int2 tmj = tm[j];
@@ -416,29 +478,6 @@ k_pair(int nloc, DevParams P, const double4 *__restrict__ xq, const int2 *__rest
     block_reduce_store<NPAIR_PART>(acc, partial);
   }
 }
-
-// ---------------------------------------------------------------------------------------------------
-// row enumerators: how a warp walks the partners of owned atom s
-// ---------------------------------------------------------------------------------------------------
-// A partner is described from the point of view of the reference's pair loop: `a` is the atom the
-// pair expressions treat as "i" (lower index), del = x_a - image(x_b), and `self_is_a` tells whether
-// the row atom is a.  List mode: the row atom is always a (del = x_i - x_j over ghosts).  All-pairs
-// mode: orientation follows the caller's atom indices so that every pair is evaluated with exactly
-// the operands the reference uses.
-struct Partner {
-  int j;
-  double dx, dy, dz, rsq;
-  bool self_is_a;
-};
-
-struct ListRows {
-  const unsigned long long *rowstart;
-  const int *neigh;
-};
-struct AllPairRows {
-  int nloc;
-  const int *perm;  // sorted -> caller index
-};
 
 // ---------------------------------------------------------------------------------------------------
 // stage 2 (all-pairs mode): static field over all owned pairs, minimum image (pol.cpp:329-361)
@@ -522,7 +561,7 @@ k_sweep(int pos_beg, int pos_end, const int *__restrict__ order, DevParams P, Li
     double ex = 0, ey = 0, ez = 0;
     if (mi.w != 0.0) {  // alpha_i == 0 => mu_new = 0 whatever the field
       if (LIST) {
-        const unsigned long long beg = L.rowstart[s], end = L.rowstart[s + 1];
+        const unsigned long long beg = L.begin(s), end = L.end(s);
         for (unsigned long long k = beg + lane; k < end; k += 32) {
           const int j = L.neigh[k] & NEIGHMASK;
           const double4 xj = ld4(xq + j);
@@ -560,6 +599,249 @@ k_sweep(int pos_beg, int pos_end, const int *__restrict__ order, DevParams P, Li
     }
   }
   block_reduce_store<1>(chg, partial);
+}
+
+// Optimised list-mode sweep (same mathematics as k_sweep<true>):
+//   * reciprocal square root instead of sqrt + two divisions, damping polynomials in Horner form;
+//   * neighbour indices prefetched two iterations ahead and (PF == 2) the 32-byte position and dipole
+//     records one iteration ahead, so the dependent index -> gather chain overlaps the FP64 work;
+//   * DAMP is a template parameter: no per-pair branch on the damping type.
+// radial part of T: s1 = d1/r^3, s2 = -3 d2/r^5  (T mu = s1 mu + s2 (del.mu) del)
+template <bool DAMP>
+__device__ __forceinline__ void radial_scalars(const PairConsts &pc, double r2, double &s1, double &s2)
+{
+  double rinv = rsqrt(r2);
+  if (r2 == 0.0) rinv = 0.0;  // coincident sites: the damped tensor vanishes (d1 = d2 = 0 at r = 0)
+  const double r = r2 * rinv;
+  const double rinv2 = rinv * rinv;
+  double r3 = rinv2 * rinv;
+  const double r5 = r3 * rinv2;
+  if (DAMP) {
+    const double ar = pc.polar_damp * r;
+    const double e = exp(-ar);
+    const double p2 = fma(ar, fma(0.5, ar, 1.0), 1.0);          // 1 + ar + (ar)^2/2
+    const double p3 = fma(ar * ar * ar, 1.0 / 6.0, p2);         // ... + (ar)^3/6
+    s1 = fma(-e, p2, 1.0) * r3;
+    s2 = -3.0 * fma(-e, p3, 1.0) * r5;
+  } else {
+    if (r2 == 0.0) r3 = DBL_MAX;  // undamped reference value (pol.cpp:1285-1286)
+    s1 = r3;
+    s2 = -3.0 * r5;
+  }
+}
+
+template <bool DAMP>
+__device__ __forceinline__ void induced_pair_fast(const PairConsts &pc, double dx, double dy, double dz, double r2,
+                                                  const double4 &mj, double &ex, double &ey, double &ez)
+{
+  double s1, s2;
+  radial_scalars<DAMP>(pc, r2, s1, s2);
+  const double t = s2 * (dx * mj.x + dy * mj.y + dz * mj.z);
+  ex -= fma(t, dx, s1 * mj.x);
+  ey -= fma(t, dy, s1 * mj.y);
+  ez -= fma(t, dz, s1 * mj.z);
+}
+
+// index stream: read once per sweep, keep it out of the way of the gathered records (ld.global.cs)
+__device__ __forceinline__ int ld_index(const int *p) { return __ldcs(p) & NEIGHMASK; }
+
+// WPB warps per block, MINB resident blocks per SM requested from ptxas.  CHANGE: also emit the squared
+// dipole change of each row (per-ROW partials, no block barrier; summed in fixed order afterwards).
+template <bool DAMP, int PF, int WPB, int MINB, bool CHANGE>
+__global__ void __launch_bounds__(WPB * 32, MINB)
+k_sweep_list2(int pos_beg, int pos_end, const int *__restrict__ order, DevParams P, ListRows L,
+              const double4 *__restrict__ xq, const double4 *__restrict__ mu_in, const double4 *__restrict__ ef,
+              double4 *__restrict__ mu_out, double *__restrict__ row_change)
+{
+  const int lane = threadIdx.x & 31;
+  const int pos = pos_beg + blockIdx.x * WPB + (threadIdx.x >> 5);
+  if (pos >= pos_end) return;
+  const int s = order ? order[pos] : pos;
+  const double4 xi = xq[s];
+  const double4 mi = mu_in[s];
+  double ex = 0, ey = 0, ez = 0;
+  if (mi.w != 0.0) {
+    const int *__restrict__ row = L.neigh + L.begin(s);
+    const int cnt = (int)(L.end(s) - L.begin(s));
+    const double cutsq = P.pc.polar_cutsq;
+    int jA = lane < cnt ? ld_index(row + lane) : -1;
+    int jB = lane + 32 < cnt ? ld_index(row + lane + 32) : -1;
+    double4 xj = make_double4(0, 0, 0, 0), mj = xj;
+    if (PF == 2 && jA >= 0) {
+      xj = ld4(xq + jA);
+      mj = ld4(mu_in + jA);
+    }
+    for (int k = lane; k < cnt; k += 32) {
+      const int jC = (k + 64 < cnt) ? ld_index(row + k + 64) : -1;
+      double4 xn = make_double4(0, 0, 0, 0), mn = xn;
+      if (PF == 3 && jB >= 0) {  // pull next iteration's records into L1 without holding registers
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(xq + jB));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(mu_in + jB));
+      }
+      if (PF == 2) {
+        if (jB >= 0) {
+          xn = ld4(xq + jB);
+          mn = ld4(mu_in + jB);
+        }
+      } else {
+        xj = ld4(xq + jA);
+        mj = ld4(mu_in + jA);
+      }
+      const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+      const double r2 = dx * dx + dy * dy + dz * dz;
+      if (r2 < cutsq) induced_pair_fast<DAMP>(P.pc, dx, dy, dz, r2, mj, ex, ey, ez);
+      jA = jB;
+      jB = jC;
+      if (PF == 2) {
+        xj = xn;
+        mj = mn;
+      }
+    }
+    ex = warp_sum(ex);
+    ey = warp_sum(ey);
+    ez = warp_sum(ez);
+  }
+  if (lane == 0) {
+    const double4 e = ef[s];
+    const double nx = mi.w * (e.x + ex), ny = mi.w * (e.y + ey), nz = mi.w * (e.z + ez);
+    mu_out[s] = make_double4(nx, ny, nz, mi.w);
+    if (CHANGE)
+      row_change[pos - pos_beg] = (nx - mi.x) * (nx - mi.x) + (ny - mi.y) * (ny - mi.y) + (nz - mi.z) * (nz - mi.z);
+  }
+}
+
+// Two neighbours per lane per trip: two independent dependency chains (rsqrt -> exp -> accumulate) in
+// flight per thread, half the loop and prefetch overhead per pair.
+template <bool DAMP, int WPB, int MINB, bool CHANGE>
+__global__ void __launch_bounds__(WPB * 32, MINB)
+k_sweep_list3(int pos_beg, int pos_end, const int *__restrict__ order, DevParams P, ListRows L,
+              const double4 *__restrict__ xq, const double4 *__restrict__ mu_in, const double4 *__restrict__ ef,
+              double4 *__restrict__ mu_out, double *__restrict__ row_change)
+{
+  const int lane = threadIdx.x & 31;
+  const int pos = pos_beg + blockIdx.x * WPB + (threadIdx.x >> 5);
+  if (pos >= pos_end) return;
+  const int s = order ? order[pos] : pos;
+  const double4 xi = xq[s];
+  const double4 mi = mu_in[s];
+  double ex = 0, ey = 0, ez = 0, fx = 0, fy = 0, fz = 0;
+  if (mi.w != 0.0) {
+    const int *__restrict__ row = L.neigh + L.begin(s);
+    const int cnt = (int)(L.end(s) - L.begin(s));
+    const double cutsq = P.pc.polar_cutsq;
+    // indices of the current trip (a0,a1) and the next one (b0,b1)
+    int a0 = lane < cnt ? ld_index(row + lane) : -1;
+    int a1 = lane + 32 < cnt ? ld_index(row + lane + 32) : -1;
+    int b0 = lane + 64 < cnt ? ld_index(row + lane + 64) : -1;
+    int b1 = lane + 96 < cnt ? ld_index(row + lane + 96) : -1;
+    for (int k = lane; k < cnt; k += 64) {
+      const int c0 = (k + 128 < cnt) ? ld_index(row + k + 128) : -1;
+      const int c1 = (k + 160 < cnt) ? ld_index(row + k + 160) : -1;
+      const double4 x0 = ld4(xq + a0), m0 = ld4(mu_in + a0);
+      double4 x1 = x0, m1 = m0;
+      if (a1 >= 0) {
+        x1 = ld4(xq + a1);
+        m1 = ld4(mu_in + a1);
+      }
+      {
+        const double dx = xi.x - x0.x, dy = xi.y - x0.y, dz = xi.z - x0.z;
+        const double r2 = dx * dx + dy * dy + dz * dz;
+        if (r2 < cutsq) induced_pair_fast<DAMP>(P.pc, dx, dy, dz, r2, m0, ex, ey, ez);
+      }
+      if (a1 >= 0) {
+        const double dx = xi.x - x1.x, dy = xi.y - x1.y, dz = xi.z - x1.z;
+        const double r2 = dx * dx + dy * dy + dz * dz;
+        if (r2 < cutsq) induced_pair_fast<DAMP>(P.pc, dx, dy, dz, r2, m1, fx, fy, fz);
+      }
+      a0 = b0;
+      a1 = b1;
+      b0 = c0;
+      b1 = c1;
+    }
+    ex = warp_sum(ex + fx);
+    ey = warp_sum(ey + fy);
+    ez = warp_sum(ez + fz);
+  }
+  if (lane == 0) {
+    const double4 e = ef[s];
+    const double nx = mi.w * (e.x + ex), ny = mi.w * (e.y + ey), nz = mi.w * (e.z + ez);
+    mu_out[s] = make_double4(nx, ny, nz, mi.w);
+    if (CHANGE)
+      row_change[pos - pos_beg] = (nx - mi.x) * (nx - mi.x) + (ny - mi.y) * (ny - mi.y) + (nz - mi.z) * (nz - mi.z);
+  }
+}
+
+// Per-step cache of the radial scalars of every tight-list entry (16 B per pair).  The geometry is
+// frozen during the SCF, so rsqrt/exp/damping are evaluated once per step instead of once per sweep;
+// the sweeps then stream 20 B per pair (index + scalars) and do 13 FP64 operations per pair.
+template <bool DAMP>
+__global__ void __launch_bounds__(BLOCK)
+k_radial_cache(int nloc, DevParams P, ListRows L, const double4 *__restrict__ xq, double2 *__restrict__ s12)
+{
+  const int lane = threadIdx.x & 31;
+  const int s = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (s >= nloc) return;
+  const double4 xi = xq[s];
+  const unsigned long long beg = L.begin(s), end = L.end(s);
+  for (unsigned long long k = beg + lane; k < end; k += 32) {
+    const double4 xj = ld4(xq + (L.neigh[k] & NEIGHMASK));
+    const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+    const double r2 = dx * dx + dy * dy + dz * dz;
+    double s1 = 0.0, s2 = 0.0;
+    if (r2 < P.pc.polar_cutsq) radial_scalars<DAMP>(P.pc, r2, s1, s2);
+    s12[k] = make_double2(s1, s2);
+  }
+}
+
+template <int WPB, int MINB, bool CHANGE>
+__global__ void __launch_bounds__(WPB * 32, MINB)
+k_sweep_cached(int pos_beg, int pos_end, const int *__restrict__ order, ListRows L,
+               const double2 *__restrict__ s12, const double4 *__restrict__ xq, const double4 *__restrict__ mu_in,
+               const double4 *__restrict__ ef, double4 *__restrict__ mu_out, double *__restrict__ row_change)
+{
+  const int lane = threadIdx.x & 31;
+  const int pos = pos_beg + blockIdx.x * WPB + (threadIdx.x >> 5);
+  if (pos >= pos_end) return;
+  const int s = order ? order[pos] : pos;
+  const double4 xi = xq[s];
+  const double4 mi = mu_in[s];
+  double ex = 0, ey = 0, ez = 0;
+  if (mi.w != 0.0) {
+    const unsigned long long beg = L.begin(s);
+    const int *__restrict__ row = L.neigh + beg;
+    const double2 *__restrict__ rs = s12 + beg;
+    const int cnt = (int)(L.end(s) - beg);
+    int jA = lane < cnt ? ld_index(row + lane) : -1;
+    int jB = lane + 32 < cnt ? ld_index(row + lane + 32) : -1;
+    double2 cA = lane < cnt ? __ldcs(rs + lane) : make_double2(0, 0);
+    double2 cB = lane + 32 < cnt ? __ldcs(rs + lane + 32) : make_double2(0, 0);
+    for (int k = lane; k < cnt; k += 32) {
+      const bool more = k + 64 < cnt;
+      const int jC = more ? ld_index(row + k + 64) : -1;
+      const double2 cC = more ? __ldcs(rs + k + 64) : make_double2(0, 0);
+      const double4 xj = ld4(xq + jA);
+      const double4 mj = ld4(mu_in + jA);
+      const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+      const double t = cA.y * (dx * mj.x + dy * mj.y + dz * mj.z);
+      ex -= fma(t, dx, cA.x * mj.x);
+      ey -= fma(t, dy, cA.x * mj.y);
+      ez -= fma(t, dz, cA.x * mj.z);
+      jA = jB;
+      jB = jC;
+      cA = cB;
+      cB = cC;
+    }
+    ex = warp_sum(ex);
+    ey = warp_sum(ey);
+    ez = warp_sum(ez);
+  }
+  if (lane == 0) {
+    const double4 e = ef[s];
+    const double nx = mi.w * (e.x + ex), ny = mi.w * (e.y + ey), nz = mi.w * (e.z + ez);
+    mu_out[s] = make_double4(nx, ny, nz, mi.w);
+    if (CHANGE)
+      row_change[pos - pos_beg] = (nx - mi.x) * (nx - mi.x) + (ny - mi.y) * (ny - mi.y) + (nz - mi.z) * (nz - mi.z);
+  }
 }
 
 // commit a chunk of the ranked colouring sweep: staged values become visible (owned records)
@@ -652,7 +934,7 @@ k_rmin(int nloc, ListRows L, const double4 *__restrict__ xq, const double4 *__re
   const int moli = tm[s].y;
   double best = 1000.0;  // pol.cpp:196
   if (ai > 0) {
-    const unsigned long long beg = L.rowstart[s], end = L.rowstart[s + 1];
+    const unsigned long long beg = L.begin(s), end = L.end(s);
     for (unsigned long long k = beg + lane; k < end; k += 32) {
       const int j = L.neigh[k] & NEIGHMASK;
       const double4 xj = ld4(xq + j);
@@ -703,7 +985,7 @@ k_rank_metric(int nloc, ListRows L, const double4 *__restrict__ xq, const double
   const int moli = tm[s].y;
   int cnt = 0;
   double overflow = 0.0;
-  const unsigned long long beg = L.rowstart[s], end = L.rowstart[s + 1];
+  const unsigned long long beg = L.begin(s), end = L.end(s);
   for (unsigned long long k0 = beg; k0 < end; k0 += 32) {
     const unsigned long long k = k0 + lane;
     bool ok = false;
@@ -798,7 +1080,7 @@ k_polforce(int nloc, DevParams P, ListRows L, AllPairRows A, const double4 *__re
     };
     if (LIST) {
       const double reach = fmax(P.pc.cut_coulsq, P.pc.polar_cutsq);
-      const unsigned long long beg = L.rowstart[s], end = L.rowstart[s + 1];
+      const unsigned long long beg = L.begin(s), end = L.end(s);
       for (unsigned long long k = beg + lane; k < end; k += 32) {
         const int j = L.neigh[k] & NEIGHMASK;
         const double4 xj = ld4(xq + j);
@@ -906,7 +1188,7 @@ k_count_polar_pairs(int nloc, double cutsq, ListRows L, const double4 *__restric
   if (s >= nloc) return;
   const double4 xi = xq[s];
   unsigned long long c = 0;
-  for (unsigned long long k = L.rowstart[s] + lane; k < L.rowstart[s + 1]; k += 32) {
+  for (unsigned long long k = L.begin(s) + lane; k < L.end(s); k += 32) {
     const double4 xj = ld4(xq + (L.neigh[k] & NEIGHMASK));
     const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
     if (dx * dx + dy * dy + dz * dz < cutsq) c++;
