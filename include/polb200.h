@@ -150,6 +150,14 @@ int polb200_comm_create_id(void *id_bytes);
 int polb200_comm_init(polb200_t *h, int rank, int nranks, const void *id_bytes, const int procgrid[3]);
 /* Sub-domain owned by this rank, valid after polb200_set_box + polb200_comm_init. */
 int polb200_subdomain(const polb200_t *h, double sublo[3], double subhi[3]);
+/* The decomposition plan as plain host arithmetic (no device, no communicator): for each of the 27
+ * directions d = (dz+1)*9 + (dy+1)*3 + (dx+1) the rank that receives what `rank` sends towards d
+ * (dest, -1 = none), the rank whose direction-d message `rank` receives (src), and the periodic image
+ * shift (units of the box length) the sender adds to coordinates (wrap[3*d+k]).  Used by callers that
+ * migrate atoms themselves and by the CPU (gloo) test of the decomposition. */
+int polb200_decomp_plan(int nranks, int rank, const int procgrid[3], const int periodic[3], const double boxlo[3],
+                        const double boxhi[3], int dest[27], int src[27], int wrap[81], double sublo[3],
+                        double subhi[3]);
 
 /* ---- introspection for tests and profiling ------------------------------------------------------ */
 

@@ -15,6 +15,7 @@
 #include <utility>
 #include <vector>
 
+#include "comm_types.h"
 #include "host_style.h"
 #include "kernels.cuh"
 #include "polb200.h"
@@ -37,10 +38,17 @@ template <class T>
 struct DBuf {
   T *p = nullptr;
   size_t cap = 0;
+  std::vector<void *> *graveyard = nullptr;  // set: replaced allocations are parked here instead of freed
+  void drop()
+  {
+    if (p && graveyard) graveyard->push_back(p);
+    else if (p) cudaFree(p);
+    p = nullptr;
+  }
   void ensure(size_t n, double slack = 1.1)
   {
     if (n <= cap) return;
-    if (p) cudaFree(p);
+    drop();
     cap = (size_t)(n * slack) + 64;
     p = nullptr;
     cudaError_t e = cudaMalloc(&p, cap * sizeof(T));
@@ -52,8 +60,7 @@ struct DBuf {
   }
   void release()
   {
-    if (p) cudaFree(p);
-    p = nullptr;
+    drop();
     cap = 0;
   }
 };
@@ -81,9 +88,38 @@ static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
 }  // namespace polb200
 
+namespace polb200 {
+
+// multi-GPU state (see comm.cuh)
+struct CommState {
+  bool active = false, geom_valid = false, want_push = true, flags_zeroed = false;
+  int rank = 0, nranks = 1;
+  int pg[3] = {1, 1, 1};
+  ncclComm_t nccl = nullptr;
+  DecompPlan plan{};
+  SendGeom geom{};
+  int send_cnt[NDIR] = {}, recv_cnt[NDIR] = {}, send_off[NDIR] = {}, recv_off[NDIR] = {};
+  int nsend = 0, nrecv = 0;
+  long nglobal = 0;
+  int nloc_of[64] = {};
+  DBuf<int> send_owner_u, send_owner, send_dir, slot_of_u, dir_start, gslot, counts_dev, push_rank, push_idx;
+  DBuf<unsigned long long> push_off, flags;
+  DBuf<double4> sbuf, rbuf;
+  DBuf<int4> sbufi, rbufi;
+  DBuf<char> ipc_dev;
+  void *peer_ptr[3][MAX_PEERS] = {};
+  void *mapped_ptr[3] = {};
+  PeerPush push{};
+  unsigned long long epoch = 0;
+  std::vector<void *> graveyard;  // dipole arrays replaced while peers may still map them
+};
+
+}  // namespace polb200
+
 using namespace polb200;
 
 struct polb200_handle {
+  CommState comm;
   HostStyle style;
   std::string err;
   int device = 0;
@@ -150,6 +186,7 @@ namespace polb200 {
 template <class... KA, class... A>
 static void launch_kernel(polb200_handle *h, void (*kernel)(KA...), int grid, int block, A &&...args)
 {
+  if (grid <= 0) return;  // empty range (e.g. a brick without ghosts)
   kernel<<<grid, block, 0, h->stream>>>(std::forward<A>(args)...);
   h->launches++;
   CUDA_CHECK(cudaGetLastError());
@@ -301,6 +338,43 @@ static void stage_in(polb200_handle *h, DBuf<T> &dst, const T *src, size_t n, bo
                              h->stream));
 }
 
+// grow the ext (owned + ghost) arrays to `next` records, preserving the owned part [0,n)
+static void grow_ext(polb200_handle *h, int n, size_t next)
+{
+  auto grow = [&](auto &buf) {
+    using T = typename std::remove_reference<decltype(*buf.p)>::type;
+    if (buf.cap >= next) return;
+    DBuf<T> nb;
+    nb.ensure(next, h->comm.active ? 1.3 : 1.1);
+    CUDA_CHECK(cudaMemcpyAsync(nb.p, buf.p, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    auto *gy = buf.graveyard;
+    buf.release();
+    buf = nb;
+    buf.graveyard = gy;
+  };
+  grow(h->xq); grow(h->mua); grow(h->tm); grow(h->tag);
+  h->mub.ensure(next, h->comm.active ? 1.3 : 1.1);
+}
+
+}  // namespace polb200
+#include "comm.cuh"
+namespace polb200 {
+
+// ghost copies follow their owners: positions (once per step) and/or one dipole array (once per sweep)
+static void ghost_update(polb200_handle *h, bool pos, double4 *mu)
+{
+  if (h->comm.active) {
+    comm_refresh(h, pos, mu);
+    return;
+  }
+  const int ng = h->nghost, n = h->nloc;
+  if (!ng) return;
+  if (pos && mu) LAUNCH(h, (k_ghost_refresh<true, true>), cdiv(ng, 256), 256, ng, n, h->g_owner.p, h->g_shift.p, h->box, h->xq.p, mu);
+  else if (pos) LAUNCH(h, (k_ghost_refresh<true, false>), cdiv(ng, 256), 256, ng, n, h->g_owner.p, h->g_shift.p, h->box, h->xq.p, mu);
+  else if (mu) LAUNCH(h, (k_ghost_refresh<false, true>), cdiv(ng, 256), 256, ng, n, h->g_owner.p, h->g_shift.p, h->box, h->xq.p, mu);
+}
+
 static void rebuild(polb200_handle *h, const polb200_atoms *at)
 {
   const HostStyle &st = h->style;
@@ -335,51 +409,44 @@ static void rebuild(polb200_handle *h, const polb200_atoms *at)
          at->molecule ? h->c_mol.p : nullptr, at->tag ? h->c_tag.p : nullptr, h->c_alpha.p, h->c_mu.p,
          h->xq.p, h->mua.p, h->tm.p, h->tag.p, h->invperm.p);
 
-  // 2. ghosts = periodic images inside the shell of width cutneighmax
-  h->cnt.ensure(n + 1); h->rowstart.ensure(n + 2);
-  LAUNCH(h, k_ghost_count, cdiv(n, 256), 256, n, h->xq.p, h->box, st.cutneighmax, h->cnt.p);
-  CUDA_CHECK(cudaMemsetAsync(h->cnt.p + n, 0, sizeof(unsigned long long), h->stream));
-  exclusive_sum(h, n + 1, h->cnt.p, h->rowstart.p);
-  h->h_int.ensure(8);
-  unsigned long long ng64 = 0;
-  CUDA_CHECK(cudaMemcpyAsync(&ng64, h->rowstart.p + n, sizeof(ng64), cudaMemcpyDeviceToHost, h->stream));
-  int hflags[4];
-  CUDA_CHECK(cudaMemcpyAsync(hflags, h->flags.p, sizeof(hflags), cudaMemcpyDeviceToHost, h->stream));
-  CUDA_CHECK(cudaStreamSynchronize(h->stream));
-  if (hflags[0] & 1) throw StyleError{POLB200_ERR_NAN, "Non-numeric positions - simulation unstable"};
-  if (ng64 + (unsigned long long)n >= (1ull << 30))
-    throw StyleError{POLB200_ERR_OVERFLOW, "owned+ghost atoms exceed the 30-bit neighbor index"};
-  const int ng = (int)ng64;
-  h->nghost = ng;
-  const size_t next = (size_t)n + ng;
-  if (ng > 0) {
-    h->g_owner_u.ensure(ng); h->g_shift_u.ensure(ng); h->g_owner.ensure(ng); h->g_shift.ensure(ng);
-    h->keys.ensure(std::max(n, ng)); h->keys2.ensure(std::max(n, ng));
-    h->vals.ensure(std::max(n, ng)); h->vals2.ensure(std::max(n, ng));
-    LAUNCH(h, k_ghost_fill, cdiv(n, 256), 256, n, h->xq.p, h->box, st.cutneighmax, g, h->rowstart.p,
-           h->g_owner_u.p, h->g_shift_u.p, h->keys.p, h->vals.p);
-    sort_pairs(h, ng, h->keys.p, h->keys2.p, h->vals.p, h->vals2.p, bits_for(g.ncell + 1));
-  }
-  // grow ext arrays, preserving the owned part
-  auto grow = [&](auto &buf) {
-    using T = typename std::remove_reference<decltype(*buf.p)>::type;
-    if (buf.cap >= next) return;
-    DBuf<T> nb;
-    nb.ensure(next);
-    CUDA_CHECK(cudaMemcpyAsync(nb.p, buf.p, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
-    CUDA_CHECK(cudaStreamSynchronize(h->stream));
-    buf.release();
-    buf = nb;
-  };
-  grow(h->xq); grow(h->mua); grow(h->tm); grow(h->tag);
-  h->mub.ensure(next);
-  h->cg_start.ensure(g.ncell + 2);
-  if (ng > 0) {
-    LAUNCH(h, k_ghost_gather, cdiv(ng, 256), 256, ng, n, h->vals2.p, h->g_owner_u.p, h->g_shift_u.p, h->box,
-           h->xq.p, h->mua.p, h->tm.p, h->tag.p, h->g_owner.p, h->g_shift.p);
-    LAUNCH(h, k_cell_starts, cdiv(g.ncell + 1, 256), 256, g.ncell, ng, h->keys2.p, h->cg_start.p);
+  // 2. ghosts: periodic images of this box (single GPU) or the boundary shells of the neighbour bricks
+  int ng = 0;
+  if (h->comm.active) {
+    comm_build_ghosts(h, n);
+    ng = h->nghost;
   } else {
-    CUDA_CHECK(cudaMemsetAsync(h->cg_start.p, 0, (g.ncell + 2) * sizeof(int), h->stream));
+    h->cnt.ensure(n + 1); h->rowstart.ensure(n + 2);
+    LAUNCH(h, k_ghost_count, cdiv(n, 256), 256, n, h->xq.p, h->box, st.cutneighmax, h->cnt.p);
+    CUDA_CHECK(cudaMemsetAsync(h->cnt.p + n, 0, sizeof(unsigned long long), h->stream));
+    exclusive_sum(h, n + 1, h->cnt.p, h->rowstart.p);
+    unsigned long long ng64 = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&ng64, h->rowstart.p + n, sizeof(ng64), cudaMemcpyDeviceToHost, h->stream));
+    int hflags[4];
+    CUDA_CHECK(cudaMemcpyAsync(hflags, h->flags.p, sizeof(hflags), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    if (hflags[0] & 1) throw StyleError{POLB200_ERR_NAN, "Non-numeric positions - simulation unstable"};
+    if (ng64 + (unsigned long long)n >= (1ull << 30))
+      throw StyleError{POLB200_ERR_OVERFLOW, "owned+ghost atoms exceed the 30-bit neighbor index"};
+    ng = (int)ng64;
+    h->nghost = ng;
+    const size_t next = (size_t)n + ng;
+    if (ng > 0) {
+      h->g_owner_u.ensure(ng); h->g_shift_u.ensure(ng); h->g_owner.ensure(ng); h->g_shift.ensure(ng);
+      h->keys.ensure(std::max(n, ng)); h->keys2.ensure(std::max(n, ng));
+      h->vals.ensure(std::max(n, ng)); h->vals2.ensure(std::max(n, ng));
+      LAUNCH(h, k_ghost_fill, cdiv(n, 256), 256, n, h->xq.p, h->box, st.cutneighmax, g, h->rowstart.p,
+             h->g_owner_u.p, h->g_shift_u.p, h->keys.p, h->vals.p);
+      sort_pairs(h, ng, h->keys.p, h->keys2.p, h->vals.p, h->vals2.p, bits_for(g.ncell + 1));
+    }
+    grow_ext(h, n, next);
+    h->cg_start.ensure(g.ncell + 2);
+    if (ng > 0) {
+      LAUNCH(h, k_ghost_gather, cdiv(ng, 256), 256, ng, n, h->vals2.p, h->g_owner_u.p, h->g_shift_u.p, h->box,
+             h->xq.p, h->mua.p, h->tm.p, h->tag.p, h->g_owner.p, h->g_shift.p);
+      LAUNCH(h, k_cell_starts, cdiv(g.ncell + 1, 256), 256, g.ncell, ng, h->keys2.p, h->cg_start.p);
+    } else {
+      CUDA_CHECK(cudaMemsetAsync(h->cg_start.p, 0, (g.ncell + 2) * sizeof(int), h->stream));
+    }
   }
 
   // special-bond lists in sorted order (tags)
@@ -423,7 +490,12 @@ static void rebuild(polb200_handle *h, const polb200_atoms *at)
 // Neighbor::decide (src/neighbor.cpp:1923-1937) for callers that pass ago < 0
 static bool decide_rebuild(polb200_handle *h, int n)
 {
-  if (!h->have_lists || n != h->nloc) return true;
+  if (!h->have_lists) return true;
+  if (n != h->nloc) {
+    // atoms only change bricks at a rebuild, and the bricks must take this decision together
+    if (h->comm.active) throw StyleError{POLB200_ERR_STATE, "number of owned atoms changed between neighbor rebuilds"};
+    return true;
+  }
   const polb200_env &e = h->style.env;
   h->ago_internal++;
   const int every = e.neigh_every > 0 ? e.neigh_every : 1;
@@ -432,6 +504,7 @@ static bool decide_rebuild(polb200_handle *h, int n)
     const double trig = 0.25 * e.skin * e.skin;  // triggersq = (skin/2)^2
     CUDA_CHECK(cudaMemsetAsync(h->flags.p + 1, 0, sizeof(int), h->stream));
     LAUNCH(h, k_check_distance, cdiv(n, 256), 256, n, h->c_x.p, h->c_xhold.p, trig, h->flags.p + 1);
+    if (h->comm.active) comm_allreduce(h, h->flags.p + 1, 1, ncclInt, ncclMax);  // any atom on any brick
     int flag = 0;
     CUDA_CHECK(cudaMemcpyAsync(&flag, h->flags.p + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
@@ -464,15 +537,30 @@ static void sweep_events_collect(polb200_handle *h)
 
 // list-mode sweep over ranked positions [beg,end): picks the kernel variant.  Returns the number of
 // partial sums written to h->partial (rows for the v2 kernels, blocks for the first version).
+// push: the kernel also stores each new dipole into the ghost slots other bricks hold for it.
+static PushArgs push_args(polb200_handle *h, const double4 *nxt)
+{
+  PushArgs Q{};
+  const CommState &c = h->comm;
+  Q.off = c.push_off.p;
+  Q.rank = c.push_rank.p;
+  Q.idx = c.push_idx.p;
+  const int par = nxt == h->mub.p ? 1 : 0;
+  for (int r = 0; r < MAX_PEERS; r++) Q.base[r] = c.push.mu[par][r];
+  return Q;
+}
+
 template <bool DAMP, int PF, int WPB, int MINB>
 static int launch_v2(polb200_handle *h, int beg, int end, const int *order, const DevParams &P, ListRows L,
-                     const double4 *cur, double4 *nxt, bool change)
+                     const double4 *cur, double4 *nxt, bool change, bool push)
 {
   const int nb = cdiv(end - beg, WPB);
-  if (change)
-    LAUNCH(h, (k_sweep_list2<DAMP, PF, WPB, MINB, true>), nb, WPB * 32, beg, end, order, P, L, h->xq.p, cur, h->ef.p, nxt, h->partial.p);
-  else
-    LAUNCH(h, (k_sweep_list2<DAMP, PF, WPB, MINB, false>), nb, WPB * 32, beg, end, order, P, L, h->xq.p, cur, h->ef.p, nxt, h->partial.p);
+  const PushArgs Q = push ? push_args(h, nxt) : PushArgs{};
+#define GO(CH, PU) \
+  LAUNCH(h, (k_sweep_list2<DAMP, PF, WPB, MINB, CH, PU>), nb, WPB * 32, beg, end, order, P, L, h->xq.p, cur, h->ef.p, nxt, h->partial.p, Q)
+  if (push) { if (change) GO(true, true); else GO(false, true); }
+  else { if (change) GO(true, false); else GO(false, false); }
+#undef GO
   return end - beg;
 }
 
@@ -490,18 +578,20 @@ static int launch_v3(polb200_handle *h, int beg, int end, const int *order, cons
 
 template <int WPB, int MINB>
 static int launch_cached(polb200_handle *h, int beg, int end, const int *order, ListRows L, const double4 *cur,
-                         double4 *nxt, bool change)
+                         double4 *nxt, bool change, bool push)
 {
   const int nb = cdiv(end - beg, WPB);
-  if (change)
-    LAUNCH(h, (k_sweep_cached<WPB, MINB, true>), nb, WPB * 32, beg, end, order, L, h->s12.p, h->xq.p, cur, h->ef.p, nxt, h->partial.p);
-  else
-    LAUNCH(h, (k_sweep_cached<WPB, MINB, false>), nb, WPB * 32, beg, end, order, L, h->s12.p, h->xq.p, cur, h->ef.p, nxt, h->partial.p);
+  const PushArgs Q = push ? push_args(h, nxt) : PushArgs{};
+#define GO(CH, PU) \
+  LAUNCH(h, (k_sweep_cached<WPB, MINB, CH, PU>), nb, WPB * 32, beg, end, order, L, h->s12.p, h->xq.p, cur, h->ef.p, nxt, h->partial.p, Q)
+  if (push) { if (change) GO(true, true); else GO(false, true); }
+  else { if (change) GO(true, false); else GO(false, false); }
+#undef GO
   return end - beg;
 }
 
 static int launch_list_sweep(polb200_handle *h, int beg, int end, const int *order, const DevParams &P, ListRows L,
-                             AllPairRows A, const double4 *cur, double4 *nxt, bool change)
+                             AllPairRows A, const double4 *cur, double4 *nxt, bool change, bool push)
 {
   const bool damp = P.pc.damping_exponential != 0;
   h->partial.ensure((size_t)(end - beg) + 64);
@@ -520,15 +610,14 @@ static int launch_list_sweep(polb200_handle *h, int beg, int end, const int *ord
       h->s12_valid = true;
     }
     switch (h->sweep_variant) {
-      case 21: return launch_cached<8, 4>(h, beg, end, order, L, cur, nxt, change);
-      case 22: return launch_cached<4, 12>(h, beg, end, order, L, cur, nxt, change);
-      case 23: return launch_cached<8, 6>(h, beg, end, order, L, cur, nxt, change);
-      default: return launch_cached<4, 8>(h, beg, end, order, L, cur, nxt, change);
+      case 21: return launch_cached<8, 4>(h, beg, end, order, L, cur, nxt, change, push);
+      case 22: return launch_cached<4, 12>(h, beg, end, order, L, cur, nxt, change, push);
+      default: return launch_cached<4, 8>(h, beg, end, order, L, cur, nxt, change, push);
     }
   }
 #define V2(PF, WPB, MINB) \
-  return damp ? launch_v2<true, PF, WPB, MINB>(h, beg, end, order, P, L, cur, nxt, change) \
-              : launch_v2<false, PF, WPB, MINB>(h, beg, end, order, P, L, cur, nxt, change)
+  return damp ? launch_v2<true, PF, WPB, MINB>(h, beg, end, order, P, L, cur, nxt, change, push) \
+              : launch_v2<false, PF, WPB, MINB>(h, beg, end, order, P, L, cur, nxt, change, push)
   switch (h->sweep_variant) {
     case 0: {
       const int nb = cdiv(end - beg, WARPS_PER_BLOCK);
@@ -536,23 +625,16 @@ static int launch_list_sweep(polb200_handle *h, int beg, int end, const int *ord
       return nb;
     }
     case 2: V2(2, 8, 3);
-    case 3: V2(1, 4, 8);
     case 4: V2(1, 8, 5);
-    case 5: V2(2, 8, 4);
     case 6: V2(1, 4, 10);
-    case 7: V2(1, 2, 16);
 #define V3(WPB, MINB) \
   return damp ? launch_v3<true, WPB, MINB>(h, beg, end, order, P, L, cur, nxt, change) \
               : launch_v3<false, WPB, MINB>(h, beg, end, order, P, L, cur, nxt, change)
     case 11: V3(4, 6);
     case 12: V3(4, 8);
-    case 13: V3(8, 3);
-    case 14: V3(4, 5);
 #undef V3
     case 8: V2(3, 4, 10);
-    case 9: V2(3, 8, 4);
-    case 10: V2(3, 4, 8);
-    default: V2(1, 8, 4);
+    default: V2(1, 4, 8);
   }
 #undef V2
 }
@@ -577,9 +659,17 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
     throw StyleError{POLB200_ERR_UNSUPPORTED, "per-atom energy/virial tallies are not implemented on the B200 path"};
   const int n = at->nlocal;
   memset(out, 0, sizeof(*out));
-  if (n <= 0) return;
+  const bool comm = h->comm.active;
+  if (n <= 0) {
+    if (comm) throw StyleError{POLB200_ERR_UNSUPPORTED, "a brick of the decomposition owns no atoms"};
+    return;
+  }
   const bool dev = at->on_device != 0;
   const bool list_mode = st.polar_cutoff > 0.0;
+  if (comm && !list_mode)
+    throw StyleError{POLB200_ERR_UNSUPPORTED,
+                     "spatial decomposition needs a dipole cutoff (polar_cutoff <r>): the reference's all-pairs "
+                     "minimum-image interaction set does not decompose into bricks"};
   for (int d = 0; d < 3; d++) {
     if (!h->box.periodic[d]) continue;
     if (st.cutneighmax > h->box.prd[d])
@@ -601,13 +691,13 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
   stage_in(h, h->c_x, at->x, (size_t)3 * n, dev);
   stage_in(h, h->c_mu, at->mu, (size_t)3 * n, dev);
   bool need = (ago == 0) || !h->have_lists || n != h->nloc;
+  if (comm && ago > 0 && h->have_lists && n != h->nloc)
+    throw StyleError{POLB200_ERR_STATE, "number of owned atoms changed between neighbor rebuilds"};
   if (ago < 0) need = decide_rebuild(h, n);
   if (need) rebuild(h, at);
   else {
     LAUNCH(h, k_refresh_local, cdiv(n, 256), 256, n, h->perm.p, h->c_x.p, h->c_mu.p, h->xq.p, h->mua.p);
-    if (h->nghost)
-      LAUNCH(h, (k_ghost_refresh<true, true>), cdiv(h->nghost, 256), 256, h->nghost, n, h->g_owner.p,
-             h->g_shift.p, h->box, h->xq.p, h->mua.p);
+    ghost_update(h, true, h->mua.p);
   }
   const int ng = h->nghost;
   const int nrowblocks = cdiv(n, WARPS_PER_BLOCK);
@@ -642,7 +732,7 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
   if (evflag) reduce_partials<NPAIR_PART>(h, nrowblocks, h->scal.p + S_PAIR, 0);
   if (!list_mode) LAUNCH(h, k_static_allpairs, nrowblocks, BLOCK, n, P, h->xq.p, h->tm.p, h->perm.p, h->ef.p);
   if (!st.use_previous) LAUNCH(h, k_init_mu, cdiv(n, 256), 256, n, st.polar_gamma, h->ef.p, h->mua.p);
-  if (ng) LAUNCH(h, (k_ghost_refresh<false, true>), cdiv(ng, 256), 256, ng, n, h->g_owner.p, h->g_shift.p, h->box, h->xq.p, h->mua.p);
+  ghost_update(h, false, h->mua.p);
   CUDA_CHECK(cudaEventRecord(h->ev[2], h->stream));
 
   // ---- stage 3: self-consistent dipoles (DipoleSolverIterative, pol.cpp:1113-1238) ----
@@ -662,7 +752,9 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
       CUDA_CHECK(cudaMemcpyAsync(h->rmin_bits.p, &init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
       ListRows Lfull{h->rowstart.p, h->neigh.p, nullptr};
       LAUNCH(h, k_rmin, nrowblocks, BLOCK, n, Lfull, h->xq.p, h->mua.p, h->tm.p, h->rmin_bits.p);
-      LAUNCH(h, k_rank_metric, nrowblocks, BLOCK, n, Lfull, h->xq.p, h->mua.p, h->tm.p, h->rmin_bits.p, h->perm.p, h->g_owner.p, h->g_shift.p, h->metric.p);
+      if (comm) comm_allreduce(h, h->rmin_bits.p, 1, ncclUint64, ncclMin);  // positive doubles order like their bits
+      LAUNCH(h, k_rank_metric, nrowblocks, BLOCK, n, Lfull, h->xq.p, h->mua.p, h->tm.p, h->rmin_bits.p, h->perm.p, h->g_owner.p, h->g_shift.p,
+             comm ? h->tag.p : (const int *)nullptr, h->metric.p);
       // values in caller order = sorted index of caller atom c
       size_t bytes = 0;
       cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, h->metric.p, h->metric2.p, h->invperm.p, h->ranked.p, n, 0, 64, h->stream);
@@ -683,6 +775,10 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
       else if (list_mode) nchunks = 8;
       else sequential = true;
     }
+    // fused sweep + halo: new dipoles go straight into the neighbour bricks' ghost slots (Jacobi sweeps)
+    const bool push = comm && h->comm.push.enabled && !gs && list_mode && h->sweep_variant != 0 &&
+                      !(h->sweep_variant >= 11 && h->sweep_variant <= 14);
+    const double natoms_norm = comm ? (double)h->comm.nglobal : (double)n;
     double4 *cur = h->mua.p, *nxt = h->mub.p;
     const double prec2 = st.polar_precision * st.polar_precision;
     bool keep = true;
@@ -697,11 +793,15 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
         if (st.fixed_iteration && iterations >= st.iterations_max) break;
         sweep_event(h);
         int nparts = nrowblocks;
-        if (list_mode) nparts = launch_list_sweep(h, 0, n, order, P, L, A, cur, nxt, want_change);
+        if (list_mode) nparts = launch_list_sweep(h, 0, n, order, P, L, A, cur, nxt, want_change, push);
         else LAUNCH(h, (k_sweep<false>), nrowblocks, BLOCK, 0, n, order, P, L, A, h->xq.p, cur, h->ef.p, nxt, h->partial.p);
         sweep_event(h);
         if (want_change) reduce_partials<1>(h, nparts, h->scal.p + S_CHANGE, 0);
-        if (ng) LAUNCH(h, (k_ghost_refresh<false, true>), cdiv(ng, 256), 256, ng, n, h->g_owner.p, h->g_shift.p, h->box, h->xq.p, nxt);
+        if (push) comm_signal_wait(h, want_change ? h->scal.p + S_CHANGE : nullptr);  // barrier (+ all-reduce)
+        else {
+          ghost_update(h, false, nxt);
+          if (comm && want_change) comm_allreduce(h, h->scal.p + S_CHANGE, 1, ncclDouble, ncclSum);
+        }
       } else {
         // ranked colouring sweep: chunks of the ranked order, Jacobi inside, Gauss-Seidel between
         for (int c = 0; c < nchunks; c++) {
@@ -709,17 +809,18 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
           if (end <= beg) continue;
           const int nb = cdiv(end - beg, WARPS_PER_BLOCK);
           int nparts = nb;
-          if (list_mode) nparts = launch_list_sweep(h, beg, end, order, P, L, A, cur, nxt, want_change);
+          if (list_mode) nparts = launch_list_sweep(h, beg, end, order, P, L, A, cur, nxt, want_change, false);
           else LAUNCH(h, (k_sweep<false>), nb, BLOCK, beg, end, order, P, L, A, h->xq.p, cur, h->ef.p, nxt, h->partial.p);
           if (want_change) reduce_partials<1>(h, nparts, h->scal.p + S_CHANGE, c > 0);
           LAUNCH(h, k_commit_rows, cdiv(end - beg, 256), 256, beg, end, order, nxt, cur);
-          if (ng) LAUNCH(h, (k_ghost_refresh<false, true>), cdiv(ng, 256), 256, ng, n, h->g_owner.p, h->g_shift.p, h->box, h->xq.p, cur);
+          ghost_update(h, false, cur);
         }
+        if (comm && want_change) comm_allreduce(h, h->scal.p + S_CHANGE, 1, ncclDouble, ncclSum);
       }
       if (want_change) {
         CUDA_CHECK(cudaMemcpyAsync(h->h_scal.p + S_CHANGE, h->scal.p + S_CHANGE, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         CUDA_CHECK(cudaStreamSynchronize(h->stream));
-        change = h->h_scal.p[S_CHANGE] / ((double)n * 3.0);
+        change = h->h_scal.p[S_CHANGE] / (natoms_norm * 3.0);
         keep = change > prec2;  // pol.cpp:1205-1209
       } else if (iterations >= st.iterations_max) {
         break;  // Gauss-Seidel fixed mode: the in-place writes of this last sweep stay
@@ -735,7 +836,7 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
     if (cur != h->mua.p) {  // keep the canonical buffer
       CUDA_CHECK(cudaMemcpyAsync(h->mua.p, cur, (size_t)n * sizeof(double4), cudaMemcpyDeviceToDevice, h->stream));
     }
-    if (ng) LAUNCH(h, (k_ghost_refresh<false, true>), cdiv(ng, 256), 256, ng, n, h->g_owner.p, h->g_shift.p, h->box, h->xq.p, h->mua.p);
+    ghost_update(h, false, h->mua.p);
   }
   CUDA_CHECK(cudaEventRecord(h->ev[3], h->stream));
 
@@ -882,6 +983,20 @@ void polb200_destroy(polb200_t *h)
   }
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  if (h->comm.active) {
+    CommState &c = h->comm;
+    comm_close_peers(h);
+    h->mua.graveyard = h->mub.graveyard = nullptr;
+    for (void *q : c.graveyard) cudaFree(q);
+    c.graveyard.clear();
+    for (auto *b : {&c.send_owner_u, &c.send_owner, &c.send_dir, &c.slot_of_u, &c.dir_start, &c.gslot, &c.counts_dev,
+                    &c.push_rank, &c.push_idx})
+      b->release();
+    c.push_off.release(); c.flags.release(); c.sbuf.release(); c.rbuf.release(); c.sbufi.release(); c.rbufi.release();
+    c.ipc_dev.release();
+    if (c.nccl) g_nccl.CommDestroy(c.nccl);
+    c.active = false;
+  }
   for (auto *b : {&h->c_x, &h->c_q, &h->c_alpha, &h->c_mu, &h->c_f, &h->c_ef, &h->c_xhold, &h->d_coeff,
                   &h->d_tables, &h->partial, &h->scal, &h->metric, &h->metric2})
     b->release();
@@ -1001,6 +1116,7 @@ int polb200_set_box(polb200_t *h, const double boxlo[3], const double boxhi[3], 
     h->P.box = h->box;
     h->box_set = true;
     if (changed) h->have_lists = false;
+    if (h->comm.active && (changed || !h->comm.geom_valid)) comm_setup_geom(h);
   });
 }
 
@@ -1033,6 +1149,12 @@ int polb200_set_option(polb200_t *h, const char *name, double value)
   if (!strcmp(name, "bin_div")) {
     if (!(value >= 1.0 && value <= 12.0)) return POLB200_ERR_ARG;
     h->bin_div = value;
+    h->have_lists = false;
+    return POLB200_OK;
+  }
+  if (!strcmp(name, "p2p_push")) {  // 0: NCCL halo per sweep; 1: fused sweep + peer-memory push (takes effect at the next rebuild)
+    h->comm.want_push = value != 0.0;
+    h->comm.mapped_ptr[0] = nullptr;
     h->have_lists = false;
     return POLB200_OK;
   }
@@ -1100,7 +1222,14 @@ long polb200_debug_fetch(polb200_t *h, const char *name, void *dst, long capacit
       CUDA_CHECK(cudaMemcpyAsync(dst, h->cnt.p, 8, cudaMemcpyDeviceToHost, h->stream));
       CUDA_CHECK(cudaStreamSynchronize(h->stream));
       result = 1;
-    } else if (!strcmp(name, "perm")) fetch(h->perm.p, (size_t)n * 4, n);
+    } else if (!strcmp(name, "comm_stats")) {  // {nsend, nrecv, nglobal, push enabled, nranks}
+      if (capacity_bytes < 40) throw StyleError{POLB200_ERR_ARG, "debug_fetch: buffer too small"};
+      double v[5] = {(double)h->comm.nsend, (double)h->comm.nrecv, (double)h->comm.nglobal,
+                     (double)h->comm.push.enabled, (double)h->comm.nranks};
+      memcpy(dst, v, 40);
+      result = 5;
+    } else if (!strcmp(name, "tag")) fetch(h->tag.p, (size_t)(n + ng) * 4, n + ng);
+    else if (!strcmp(name, "perm")) fetch(h->perm.p, (size_t)n * 4, n);
     else if (!strcmp(name, "ghost_owner")) fetch(h->g_owner.p, (size_t)ng * 4, ng);   // sorted owned index
     else if (!strcmp(name, "ghost_shift")) fetch(h->g_shift.p, (size_t)ng * 4, ng);   // packed code
     else if (!strcmp(name, "rowstart")) fetch(h->rowstart.p, (size_t)(n + 1) * 8, n + 1);
@@ -1115,21 +1244,80 @@ long polb200_debug_fetch(polb200_t *h, const char *name, void *dst, long capacit
   return result;
 }
 
-// ---- multi-GPU entry points: implemented in comm.cu when built with NCCL -------------------------------
-#ifndef POLB200_WITH_NCCL
-int polb200_comm_id_size(void) { return 0; }
-int polb200_comm_create_id(void *) { return POLB200_ERR_UNSUPPORTED; }
-int polb200_comm_init(polb200_t *h, int, int, const void *, const int *)
+// ---- multi-GPU entry points (comm.cuh) ---------------------------------------------------------------
+int polb200_comm_id_size(void) { return (int)sizeof(ncclUniqueId); }
+
+int polb200_comm_create_id(void *id_bytes)
 {
-  if (h) h->err = "library built without NCCL";
-  return POLB200_ERR_UNSUPPORTED;
-}
-int polb200_subdomain(const polb200_t *h, double sublo[3], double subhi[3])
-{
-  if (!h || !h->box_set) return POLB200_ERR_STATE;
-  for (int d = 0; d < 3; d++) { sublo[d] = h->box.lo[d]; subhi[d] = h->box.hi[d]; }
+  if (!id_bytes) return POLB200_ERR_ARG;
+  std::string err;
+  if (!g_nccl.load(err)) {
+    fprintf(stderr, "polb200_comm_create_id: %s\n", err.c_str());
+    return POLB200_ERR_UNSUPPORTED;
+  }
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) return POLB200_ERR_CUDA;
+  memcpy(id_bytes, &id, sizeof(id));
   return POLB200_OK;
 }
-#endif
+
+int polb200_comm_init(polb200_t *h, int rank, int nranks, const void *id_bytes, const int procgrid[3])
+{
+  if (!h || !id_bytes || !procgrid) return POLB200_ERR_ARG;
+  return guarded(h, [&] {
+    if (h->device == POLB200_DEVICE_NONE) throw CudaError{"polb200_comm_init needs a CUDA device"};
+    if (h->comm.active) throw StyleError{POLB200_ERR_STATE, "polb200_comm_init was already called"};
+    if (nranks < 1 || rank < 0 || rank >= nranks || procgrid[0] * procgrid[1] * procgrid[2] != nranks || nranks > 64)
+      throw StyleError{POLB200_ERR_ARG, "Bad grid of processors"};
+    std::string err;
+    if (!g_nccl.load(err)) throw StyleError{POLB200_ERR_UNSUPPORTED, err};
+    CUDA_CHECK(cudaSetDevice(h->device));
+    ncclUniqueId id;
+    memcpy(&id, id_bytes, sizeof(id));
+    CommState &c = h->comm;
+    NCCL_CHECK(g_nccl.CommInitRank(&c.nccl, nranks, id, rank));
+    c.rank = rank;
+    c.nranks = nranks;
+    for (int k = 0; k < 3; k++) c.pg[k] = procgrid[k];
+    c.active = true;
+    h->mua.graveyard = h->mub.graveyard = &c.graveyard;
+    if (const char *v = getenv("POLB200_P2P_PUSH")) c.want_push = atoi(v) != 0;
+    h->have_lists = false;
+    if (h->box_set) comm_setup_geom(h);
+  });
+}
+
+int polb200_subdomain(const polb200_t *h, double sublo[3], double subhi[3])
+{
+  if (!h || !h->box_set || !sublo || !subhi) return POLB200_ERR_STATE;
+  DecompPlan p;
+  const int one[3] = {1, 1, 1};
+  if (make_plan(h->comm.active ? h->comm.nranks : 1, h->comm.active ? h->comm.rank : 0, h->comm.active ? h->comm.pg : one,
+                h->box.periodic, h->box.lo, h->box.hi, p))
+    return POLB200_ERR_ARG;
+  for (int d = 0; d < 3; d++) {
+    sublo[d] = p.sublo[d];
+    subhi[d] = p.subhi[d];
+  }
+  return POLB200_OK;
+}
+
+int polb200_decomp_plan(int nranks, int rank, const int procgrid[3], const int periodic[3], const double boxlo[3],
+                        const double boxhi[3], int dest[27], int src[27], int wrap[81], double sublo[3], double subhi[3])
+{
+  if (!procgrid || !periodic || !boxlo || !boxhi || !dest || !src || !wrap || !sublo || !subhi) return POLB200_ERR_ARG;
+  DecompPlan p;
+  if (make_plan(nranks, rank, procgrid, periodic, boxlo, boxhi, p)) return POLB200_ERR_ARG;
+  for (int d = 0; d < NDIR; d++) {
+    dest[d] = p.dest[d];
+    src[d] = p.src[d];
+    for (int k = 0; k < 3; k++) wrap[3 * d + k] = p.wrap[d][k];
+  }
+  for (int k = 0; k < 3; k++) {
+    sublo[k] = p.sublo[k];
+    subhi[k] = p.subhi[k];
+  }
+  return POLB200_OK;
+}
 
 }  // extern "C"

@@ -13,6 +13,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "comm_types.h"
 #include "pair_math.cuh"
 
 namespace polb200 {
@@ -76,6 +77,23 @@ __device__ __forceinline__ double warp_sum(double v)
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL, v, o);
   return v;
+}
+
+// what the fused sweep needs to store a new dipole into the ghost copies held by other bricks
+struct PushArgs {
+  const unsigned long long *off;  // CSR over owned atoms (cell-sorted index) into rank/idx
+  const int *rank;
+  const int *idx;
+  double4 *base[MAX_PEERS];       // per rank: that rank's OUTPUT dipole array of this sweep (peer mapping)
+};
+
+__device__ __forceinline__ void push_row(const PushArgs &Q, int s, int lane, double nx, double ny, double nz, double a)
+{
+  nx = __shfl_sync(FULL, nx, 0);
+  ny = __shfl_sync(FULL, ny, 0);
+  nz = __shfl_sync(FULL, nz, 0);
+  const unsigned long long b = Q.off[s], e = Q.off[s + 1];
+  for (unsigned long long u = b + lane; u < e; u += 32) Q.base[Q.rank[u]][Q.idx[u]] = make_double4(nx, ny, nz, a);
 }
 
 // 256-bit loads of the 32-byte records (sm_100a: LDG.E.ENL2.256 via the aligned double4 types)
@@ -647,11 +665,11 @@ __device__ __forceinline__ int ld_index(const int *p) { return __ldcs(p) & NEIGH
 
 // WPB warps per block, MINB resident blocks per SM requested from ptxas.  CHANGE: also emit the squared
 // dipole change of each row (per-ROW partials, no block barrier; summed in fixed order afterwards).
-template <bool DAMP, int PF, int WPB, int MINB, bool CHANGE>
+template <bool DAMP, int PF, int WPB, int MINB, bool CHANGE, bool PUSH = false>
 __global__ void __launch_bounds__(WPB * 32, MINB)
 k_sweep_list2(int pos_beg, int pos_end, const int *__restrict__ order, DevParams P, ListRows L,
               const double4 *__restrict__ xq, const double4 *__restrict__ mu_in, const double4 *__restrict__ ef,
-              double4 *__restrict__ mu_out, double *__restrict__ row_change)
+              double4 *__restrict__ mu_out, double *__restrict__ row_change, PushArgs Q = PushArgs{})
 {
   const int lane = threadIdx.x & 31;
   const int pos = pos_beg + blockIdx.x * WPB + (threadIdx.x >> 5);
@@ -701,13 +719,15 @@ k_sweep_list2(int pos_beg, int pos_end, const int *__restrict__ order, DevParams
     ey = warp_sum(ey);
     ez = warp_sum(ez);
   }
+  double nx = 0, ny = 0, nz = 0;
   if (lane == 0) {
     const double4 e = ef[s];
-    const double nx = mi.w * (e.x + ex), ny = mi.w * (e.y + ey), nz = mi.w * (e.z + ez);
+    nx = mi.w * (e.x + ex), ny = mi.w * (e.y + ey), nz = mi.w * (e.z + ez);
     mu_out[s] = make_double4(nx, ny, nz, mi.w);
     if (CHANGE)
       row_change[pos - pos_beg] = (nx - mi.x) * (nx - mi.x) + (ny - mi.y) * (ny - mi.y) + (nz - mi.z) * (nz - mi.z);
   }
+  if (PUSH) push_row(Q, s, lane, nx, ny, nz, mi.w);
 }
 
 // Two neighbours per lane per trip: two independent dependency chains (rsqrt -> exp -> accumulate) in
@@ -793,11 +813,12 @@ k_radial_cache(int nloc, DevParams P, ListRows L, const double4 *__restrict__ xq
   }
 }
 
-template <int WPB, int MINB, bool CHANGE>
+template <int WPB, int MINB, bool CHANGE, bool PUSH = false>
 __global__ void __launch_bounds__(WPB * 32, MINB)
 k_sweep_cached(int pos_beg, int pos_end, const int *__restrict__ order, ListRows L,
                const double2 *__restrict__ s12, const double4 *__restrict__ xq, const double4 *__restrict__ mu_in,
-               const double4 *__restrict__ ef, double4 *__restrict__ mu_out, double *__restrict__ row_change)
+               const double4 *__restrict__ ef, double4 *__restrict__ mu_out, double *__restrict__ row_change,
+               PushArgs Q = PushArgs{})
 {
   const int lane = threadIdx.x & 31;
   const int pos = pos_beg + blockIdx.x * WPB + (threadIdx.x >> 5);
@@ -835,13 +856,15 @@ k_sweep_cached(int pos_beg, int pos_end, const int *__restrict__ order, ListRows
     ey = warp_sum(ey);
     ez = warp_sum(ez);
   }
+  double nx = 0, ny = 0, nz = 0;
   if (lane == 0) {
     const double4 e = ef[s];
-    const double nx = mi.w * (e.x + ex), ny = mi.w * (e.y + ey), nz = mi.w * (e.z + ez);
+    nx = mi.w * (e.x + ex), ny = mi.w * (e.y + ey), nz = mi.w * (e.z + ez);
     mu_out[s] = make_double4(nx, ny, nz, mi.w);
     if (CHANGE)
       row_change[pos - pos_beg] = (nx - mi.x) * (nx - mi.x) + (ny - mi.y) * (ny - mi.y) + (nz - mi.z) * (nz - mi.z);
   }
+  if (PUSH) push_row(Q, s, lane, nx, ny, nz, mi.w);
 }
 
 // commit a chunk of the ranked colouring sweep: staged values become visible (owned records)
@@ -953,15 +976,18 @@ k_rmin(int nloc, ListRows L, const double4 *__restrict__ xq, const double4 *__re
 // the +prd swap before the -prd swap, each swap scanning the atoms created so far in index order.
 // That order is the lexicographic order of (z stage, y stage, x stage, owner index), stage = 0 for
 // no shift, 1 for +prd, 2 for -prd.
+// Decomposed runs (tag != nullptr) have no global caller index: atoms are keyed by their tag instead.
 __device__ __forceinline__ unsigned long long reference_index_key(int j, int nloc, const int *__restrict__ perm,
                                                                   const int *__restrict__ g_owner,
-                                                                  const int *__restrict__ g_shift)
+                                                                  const int *__restrict__ g_shift,
+                                                                  const int *__restrict__ tag)
 {
-  if (j < nloc) return (unsigned long long)perm[j];
+  if (j < nloc) return (unsigned long long)(tag ? tag[j] : perm[j]);
   const int code = g_shift[j - nloc];
   const int sx = (code & 3) - 1, sy = ((code >> 2) & 3) - 1, sz = ((code >> 4) & 3) - 1;
   const int cx = sx == 0 ? 0 : (sx > 0 ? 1 : 2), cy = sy == 0 ? 0 : (sy > 0 ? 1 : 2), cz = sz == 0 ? 0 : (sz > 0 ? 1 : 2);
-  return ((unsigned long long)((cz * 3 + cy) * 3 + cx + 1) << 32) | (unsigned long long)perm[g_owner[j - nloc]];
+  return ((unsigned long long)((cz * 3 + cy) * 3 + cx + 1) << 32) |
+         (unsigned long long)(tag ? tag[j] : perm[g_owner[j - nloc]]);
 }
 
 // rank_metric[i] = sum of alpha_i*alpha_j over partners closer than 1.5*rmin (pol.cpp:214-226).
@@ -972,7 +998,7 @@ __global__ void __launch_bounds__(BLOCK)
 k_rank_metric(int nloc, ListRows L, const double4 *__restrict__ xq, const double4 *__restrict__ mua,
               const int2 *__restrict__ tm, const unsigned long long *__restrict__ rmin_bits,
               const int *__restrict__ perm, const int *__restrict__ g_owner, const int *__restrict__ g_shift,
-              double *__restrict__ metric_caller)
+              const int *__restrict__ tag, double *__restrict__ metric_caller)
 {
   __shared__ unsigned long long s_key[WARPS_PER_BLOCK][RANK_CAP];
   __shared__ double s_term[WARPS_PER_BLOCK][RANK_CAP];
@@ -1002,7 +1028,7 @@ k_rank_metric(int nloc, ListRows L, const double4 *__restrict__ xq, const double
       const int slot = cnt + __popc(m & ((1u << lane) - 1));
       const double term = ai * mua[j].w;
       if (slot < RANK_CAP) {
-        s_key[warp][slot] = reference_index_key(j, nloc, perm, g_owner, g_shift);
+        s_key[warp][slot] = reference_index_key(j, nloc, perm, g_owner, g_shift, tag);
         s_term[warp][slot] = term;
       } else overflow += term;
     }
@@ -1212,6 +1238,184 @@ __global__ void k_add_inplace(long n, const double *__restrict__ a, double *__re
 {
   long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) f[t] += a[t];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// multi-GPU halo: send lists, pack / unpack of the boundary shell
+// ---------------------------------------------------------------------------------------------------
+// directions (see decomp.h) in which an owned atom is a ghost of a neighbour brick: same membership
+// rule per dimension as CommBrick::borders (src/comm_brick.cpp:768-772): x <= lo+cut goes towards -1,
+// x >= hi-cut goes towards +1, and the rules of the three dimensions combine to edges and corners.
+__device__ __forceinline__ unsigned send_mask(const SendGeom &G, double x, double y, double z)
+{
+  const double p[3] = {x, y, z};
+  unsigned a[3];
+  for (int k = 0; k < 3; k++) a[k] = 2u | (p[k] <= G.lo[k] + G.cut ? 1u : 0u) | (p[k] >= G.hi[k] - G.cut ? 4u : 0u);
+  unsigned m = 0;
+  for (int d = 0; d < NDIR; d++) {
+    const int vx = d % 3, vy = (d / 3) % 3, vz = d / 9;
+    if (((a[0] >> vx) & 1u) && ((a[1] >> vy) & 1u) && ((a[2] >> vz) & 1u)) m |= 1u << d;
+  }
+  return m & G.valid;
+}
+
+__global__ void k_send_count(int n, const double4 *__restrict__ xq, SendGeom G, unsigned long long *__restrict__ cnt)
+{
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const double4 v = xq[s];
+  cnt[s] = (unsigned long long)__popc(send_mask(G, v.x, v.y, v.z));
+}
+
+// (owner, direction) of every send slot, in (owner, direction) order; a stable sort by direction then
+// gives direction-major segments with owners ascending inside each
+__global__ void k_send_fill(int n, const double4 *__restrict__ xq, SendGeom G, const unsigned long long *__restrict__ off,
+                            int *__restrict__ owner, int *__restrict__ dir, int *__restrict__ iota)
+{
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const double4 v = xq[s];
+  unsigned m = send_mask(G, v.x, v.y, v.z);
+  unsigned long long o = off[s];
+  while (m) {
+    const int d = __ffs(m) - 1;
+    m &= m - 1;
+    owner[o] = s;
+    dir[o] = d;
+    iota[o] = (int)o;
+    o++;
+  }
+}
+
+__global__ void k_gather_int(int n, const int *__restrict__ order, const int *__restrict__ in, int *__restrict__ out)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) out[t] = in[order[t]];
+}
+
+// positions of the send slots with the periodic image shift applied: one rounding per shifted
+// dimension, exactly the single-GPU ghost expression (k_ghost_gather) and AtomVecFull::pack_border
+__global__ void k_pack_pos(int ns, const int *__restrict__ owner, const int *__restrict__ dir, SendGeom G,
+                           const double4 *__restrict__ xq, double4 *__restrict__ sbuf)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ns) return;
+  const double4 v = xq[owner[t]];
+  const int d = dir[t];
+  sbuf[t] = make_double4(G.shift[d][0] != 0.0 ? v.x + G.shift[d][0] : v.x, G.shift[d][1] != 0.0 ? v.y + G.shift[d][1] : v.y,
+                         G.shift[d][2] != 0.0 ? v.z + G.shift[d][2] : v.z, v.w);
+}
+
+__global__ void k_pack_rec(int ns, const int *__restrict__ owner, const double4 *__restrict__ src,
+                           double4 *__restrict__ sbuf)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < ns) sbuf[t] = src[owner[t]];
+}
+
+__global__ void k_pack_meta(int ns, const int *__restrict__ owner, const int *__restrict__ dir, SendGeom G,
+                            const int2 *__restrict__ tm, const int *__restrict__ tag, int4 *__restrict__ sbuf)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ns) return;
+  const int s = owner[t];
+  const int2 a = tm[s];
+  sbuf[t] = make_int4(a.x, a.y, tag[s], G.code[dir[t]]);
+}
+
+// received records into the cell-sorted ghost section (dst points at ext index nloc)
+__global__ void k_unpack_rec(int ng, const int *__restrict__ gslot, const double4 *__restrict__ rbuf,
+                             double4 *__restrict__ dst)
+{
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < ng) dst[g] = rbuf[gslot[g]];
+}
+
+__global__ void k_unpack_meta(int ng, const int *__restrict__ gslot, const int4 *__restrict__ rbuf,
+                              int2 *__restrict__ tm, int *__restrict__ tag, int *__restrict__ code)
+{
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ng) return;
+  const int4 a = rbuf[gslot[g]];
+  tm[g] = make_int2(a.x, a.y);
+  tag[g] = a.z;
+  code[g] = a.w;
+}
+
+__global__ void k_ghost_keys(int ng, const double4 *__restrict__ rbuf, Grid g, int *__restrict__ key,
+                             int *__restrict__ iota)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ng) return;
+  const double4 v = rbuf[t];
+  int cx, cy, cz;
+  key[t] = cell_of(g, v.x, v.y, v.z, cx, cy, cz);
+  iota[t] = t;
+}
+
+__global__ void k_invert_perm(int n, const int *__restrict__ order, int *__restrict__ inv)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) inv[order[t]] = t;
+}
+
+// ext index (on THIS rank) of every receive slot: the answer the senders need for the peer push
+__global__ void k_ghost_ext_index(int ng, int nloc, const int *__restrict__ gslot, int *__restrict__ per_slot)
+{
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < ng) per_slot[gslot[g]] = nloc + g;
+}
+
+struct DirTable {
+  int v[NDIR];
+};
+
+// push tables in (owner, direction) order: destination rank and remote ext index of every send slot
+__global__ void k_push_tables(int ns, const int *__restrict__ slot_of_u, const int *__restrict__ dir_of_slot, DirTable dest,
+                              const int *__restrict__ remote_of_slot, int *__restrict__ push_rank,
+                              int *__restrict__ push_idx)
+{
+  int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= ns) return;
+  const int t = slot_of_u[u];
+  push_rank[u] = dest.v[dir_of_slot[t]];
+  push_idx[u] = remote_of_slot[t];
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Inter-GPU barrier + all-reduce of one double over peer memory, one warp.  flags layout per rank:
+// [0,MAX_PEERS) arrival epoch of each source rank, then two banks of MAX_PEERS partial sums (by epoch parity).
+// The dipoles pushed by the sweep kernel were stored by an EARLIER kernel of the same stream, so they are
+// performed before this kernel's release-store of the epoch.
+__global__ void k_signal_wait(int rank, int nranks, unsigned long long epoch, PeerPush P, double *__restrict__ change)
+{
+  const int r = threadIdx.x;
+  const int bank = (1 + (int)(epoch & 1ull)) * MAX_PEERS;
+  unsigned long long *mine = P.flag[rank];
+  if (r < nranks) {
+    unsigned long long *theirs = P.flag[r];
+    if (change) theirs[bank + rank] = (unsigned long long)__double_as_longlong(*change);
+    __threadfence_system();
+    st_release_sys(theirs + rank, epoch);
+    while (ld_acquire_sys(mine + r) < epoch) {
+    }
+  }
+  __syncwarp();
+  if (threadIdx.x == 0 && change) {
+    double s = 0.0;
+    for (int k = 0; k < nranks; k++) s += __longlong_as_double((long long)ld_acquire_sys(mine + bank + k));
+    *change = s;
+  }
 }
 
 }  // namespace polb200

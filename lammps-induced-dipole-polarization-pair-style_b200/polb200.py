@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "polb200_extract", "polb200_single", "polb200_restart_size", "polb200_write_restart",
     "polb200_read_restart", "polb200_set_box", "polb200_compute", "polb200_comm_id_size",
     "polb200_comm_create_id", "polb200_comm_init", "polb200_subdomain", "polb200_debug_fetch",
-    "polb200_launch_count", "polb200_set_option",
+    "polb200_launch_count", "polb200_set_option", "polb200_decomp_plan",
 ]
 
 
@@ -105,6 +105,10 @@ def lib():
         L.polb200_comm_create_id.argtypes = [C.c_void_p]
         L.polb200_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
         L.polb200_subdomain.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.polb200_decomp_plan.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                          C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int),
+                                          C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double),
+                                          C.POINTER(C.c_double)]
         _lib = L
     return _lib
 
@@ -115,6 +119,34 @@ def _argv(words):
 
 
 REAL_QQRD2E = 332.06371  # units real, src/update.cpp:157
+
+
+def decomp_plan(nranks, rank, procgrid, periodic, boxlo, boxhi):
+    """Host-side plan of the brick decomposition (no device needed): dict with dest[27], src[27],
+    wrap[27,3], sublo[3], subhi[3]; direction d = (dz+1)*9 + (dy+1)*3 + (dx+1)."""
+    dest = (C.c_int * 27)()
+    src = (C.c_int * 27)()
+    wrap = (C.c_int * 81)()
+    sublo = (C.c_double * 3)()
+    subhi = (C.c_double * 3)()
+    rc = lib().polb200_decomp_plan(nranks, rank, (C.c_int * 3)(*[int(v) for v in procgrid]),
+                                   (C.c_int * 3)(*[int(v) for v in periodic]),
+                                   (C.c_double * 3)(*[float(v) for v in boxlo]),
+                                   (C.c_double * 3)(*[float(v) for v in boxhi]), dest, src, wrap, sublo, subhi)
+    if rc != OK:
+        raise Polb200Error(rc, "Bad grid of processors")
+    return dict(dest=np.array(dest[:]), src=np.array(src[:]), wrap=np.array(wrap[:]).reshape(27, 3),
+                sublo=np.array(sublo[:]), subhi=np.array(subhi[:]))
+
+
+def comm_create_id():
+    """Opaque NCCL unique id (bytes) that rank 0 creates and every rank passes to PairStyle.comm_init."""
+    n = lib().polb200_comm_id_size()
+    buf = (C.c_char * n)()
+    rc = lib().polb200_comm_create_id(buf)
+    if rc != OK:
+        raise Polb200Error(rc, "polb200_comm_create_id failed (NCCL not loadable?)")
+    return bytes(buf)
 
 
 class PairStyle:
@@ -229,6 +261,20 @@ class PairStyle:
         hi = (C.c_double * 3)(*[float(v) for v in boxhi])
         per = (C.c_int * 3)(*[int(v) for v in periodic])
         self._check(lib().polb200_set_box(self._h, lo, hi, per))
+
+    # ---- multi-GPU: one process per GPU, bricks of the box ----
+    def comm_init(self, rank, nranks, id_bytes, procgrid):
+        buf = C.create_string_buffer(id_bytes, len(id_bytes))
+        self._check(lib().polb200_comm_init(self._h, rank, nranks, buf, (C.c_int * 3)(*[int(v) for v in procgrid])))
+
+    def subdomain(self):
+        lo = (C.c_double * 3)()
+        hi = (C.c_double * 3)()
+        self._check(lib().polb200_subdomain(self._h, lo, hi))
+        return np.array(lo[:]), np.array(hi[:])
+
+    def set_option(self, name, value):
+        self._check(lib().polb200_set_option(self._h, name.encode(), float(value)))
 
     # ---- hot path ----
     def compute(self, x, q, type_, alpha, mu, f, molecule=None, tag=None, ef_static=None, nspecial=None,

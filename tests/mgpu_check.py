@@ -1,0 +1,136 @@
+"""Multi-GPU parity check of the spatial decomposition.  Launch with
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tests/mgpu_check.py
+Every rank computes the WHOLE system on its own GPU with a plain single-GPU handle (the already
+parity-checked path) and its brick of the same system through the decomposed path; owned dipoles,
+fields and forces must agree, energies and virial after summing over ranks.
+
+Cases: Jacobi fixed-iteration (NCCL halo and fused peer push), Jacobi precision mode (iteration counts
+equal), ranked colouring sweep (tolerance), a step without rebuild after moving atoms, and a rebuild.
+Prints one line per case and exits non-zero on failure.  Used by tests/test_multi_gpu.py (gpu marker).
+"""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+for p in (str(ROOT), str(ROOT / "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch
+import torch.distributed as dist
+
+import polhelpers as H
+from gpu_common import c, pb
+from oracle import polref as P  # only ewald_g (host setup arithmetic)
+
+GRIDS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+
+
+def make_style(device, sysm, words, cut_coul):
+    g = P.ewald_g(1e-4, sysm.q, cut_coul, sysm.boxlo, sysm.boxhi)
+    s = pb.PairStyle(device=device)
+    s.set_ntypes(2)
+    s.command(f"pair_style lj/cut/coul/long/polarization 2.5 {cut_coul} {words} polar_cutoff {cut_coul}")
+    s.command("pair_coeff 1 1 0.1 3.0")
+    s.command("pair_coeff 2 2 0.1 3.0")
+    s.init(g_ewald=g, molecular=0)
+    s.set_box(sysm.boxlo, sysm.boxhi)
+    return s
+
+
+def run(style, x, q, typ, alpha, tag, mu, ago):
+    n = x.shape[0]
+    f = np.zeros((n, 3))
+    ef = np.zeros((n, 3))
+    mu = mu.copy()
+    res = style.compute(c(x, np.float64), c(q, np.float64), c(typ, np.int32), c(alpha, np.float64), mu, f,
+                        tag=c(tag, np.int32), ef_static=ef, eflag=1, vflag=2, ago=ago)
+    return res, mu, ef, f
+
+
+def main():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pg = GRIDS[world]
+    ncell = int(os.environ.get("MGPU_NCELL", "8"))
+    cut = float(os.environ.get("MGPU_CUT", "8.0"))
+    sysm = H.lj_charge_fluid(tuple(ncell * np.array(pg)), seed=777)
+    # the id travels through torch.distributed (the caller's own transport, MPI_Bcast in LAMMPS)
+    box = [pb.comm_create_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    nccl_id = box[0]
+    failures = []
+
+    def owned_mask(x, lo, hi):
+        return np.all((x >= lo) & (x < hi), axis=1)
+
+    cases = [("jacobi_fixed_nccl", "polar_gs_ranked no fixed_iteration yes max_iterations 12 damp_type exponential", 0, 1e-12),
+             ("jacobi_fixed_push", "polar_gs_ranked no fixed_iteration yes max_iterations 12 damp_type exponential", 1, 1e-12),
+             ("jacobi_precision_push", "polar_gs_ranked no precision 1e-9 max_iterations 60 damp_type exponential", 1, 1e-12),
+             ("jacobi_precision_nccl", "polar_gs_ranked no precision 1e-9 max_iterations 60 damp_type exponential", 0, 1e-12),
+             ("gs_ranked_chunks", "precision 1e-11 max_iterations 60 damp_type exponential", 1, 2e-10)]
+    for name, words, push, tol in cases:
+        ref = make_style(local, sysm, words, cut)
+        dec = make_style(local, sysm, words, cut)
+        dec.comm_init(rank, world, nccl_id, pg)
+        dec.set_option("p2p_push", push)
+        lo, hi = dec.subdomain()
+        x = sysm.x.copy()
+        mu_g = np.zeros((sysm.n, 3))
+        rng = np.random.default_rng(5)
+        ok = True
+        msgs = []
+        for step, ago in enumerate([0, 1, 2, 0]):
+            if step == 0:
+                mine = owned_mask(x, lo, hi)
+                idx = np.nonzero(mine)[0]
+            elif ago == 0:
+                # rebuild: atoms may have changed bricks (wrap first, like Domain::pbc + Comm::exchange)
+                x = sysm.boxlo + np.mod(x - sysm.boxlo, sysm.boxhi - sysm.boxlo)
+                mine = owned_mask(x, lo, hi)
+                idx = np.nonzero(mine)[0]
+            r0, mu0, ef0, f0 = run(ref, x, sysm.q, sysm.type, sysm.alpha, sysm.tag, mu_g, ago)
+            r1, mu1, ef1, f1 = run(dec, x[idx], sysm.q[idx], sysm.type[idx], sysm.alpha[idx], sysm.tag[idx], mu_g[idx], ago)
+            stats = dec.debug_fetch("comm_stats", np.float64, 5)
+            e = torch.tensor([r1.eng_vdwl, r1.eng_coul, r1.eng_pol] + list(r1.virial[:]), dtype=torch.float64, device="cuda")
+            dist.all_reduce(e)
+            e = e.cpu().numpy()
+            e0 = np.array([r0.eng_vdwl, r0.eng_coul, r0.eng_pol] + list(r0.virial[:]))
+            errs = dict(mu=H.rel_err(mu1, mu0[idx]), ef=H.rel_err(ef1, ef0[idx]),
+                        f=float(np.abs(f1 - f0[idx]).max() / np.abs(f0).max()),
+                        e=float(np.abs(e - e0).max() / np.abs(e0).max()))
+            it_ok = r1.iterations == r0.iterations if "gs_ranked" not in name else abs(r1.iterations - r0.iterations) <= 2
+            good = all(v < tol for v in errs.values()) and it_ok and int(stats[2]) == sysm.n
+            if push and "gs" not in name:
+                good = good and int(stats[3]) == 1
+            ok = ok and good
+            msgs.append(f"step{step}(ago={ago}) it {r1.iterations}/{r0.iterations} " +
+                        " ".join(f"{k}={v:.1e}" for k, v in errs.items()) + f" push={int(stats[3])}")
+            # move atoms a little (within the half-skin) for the next step; persistent dipoles follow
+            x = x + rng.uniform(-0.15, 0.15, size=x.shape)
+            mu_g = mu0
+        flag = torch.tensor([0 if ok else 1], device="cuda")
+        dist.all_reduce(flag)
+        if rank == 0:
+            print(f"[mgpu {world} ranks grid {pg}] {name}: {'OK' if int(flag) == 0 else 'FAIL'} | " + " | ".join(msgs), flush=True)
+        if int(flag):
+            failures.append(name)
+        ref.close()
+        dec.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    if failures:
+        print("FAILED:", failures)
+        sys.exit(1)
+    if rank == 0:
+        print("mgpu_check: all cases passed")
+
+
+if __name__ == "__main__":
+    main()

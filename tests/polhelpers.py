@@ -115,13 +115,17 @@ def rel_err(a, b):
 
 def lj_charge_fluid(ncell, seed=12345, rho=0.1, jitter=0.3):
     """BASELINE config 2 generator: fcc sites jittered by U(-jitter,jitter) A, density rho
-    atoms/A^3, two types with q=+-0.4 e alternating, alpha 1.0/0.5 A^3, molecule 0.  N = 4*ncell^3."""
+    atoms/A^3, two types with q=+-0.4 e alternating, alpha 1.0/0.5 A^3, molecule 0.  N = 4*ncell^3
+    (ncell may be a triple (nx,ny,nz) of fcc cells for the brick-shaped boxes of the multi-GPU runs)."""
     rng = np.random.default_rng(seed)
-    n = 4 * ncell ** 3
-    L = (n / rho) ** (1.0 / 3.0)
-    a = L / ncell
+    nc = np.array([ncell] * 3 if np.isscalar(ncell) else list(ncell), dtype=np.int64)
+    n = 4 * int(nc.prod())
+    a = (4.0 / rho) ** (1.0 / 3.0)
+    if np.isscalar(ncell):
+        a = ((n / rho) ** (1.0 / 3.0)) / ncell  # the historical expression (bit-identical fixtures)
+    L = a * nc
     base = np.array([[0, 0, 0], [0.5, 0.5, 0], [0.5, 0, 0.5], [0, 0.5, 0.5]])
-    g = np.stack(np.meshgrid(np.arange(ncell), np.arange(ncell), np.arange(ncell), indexing="ij"), -1).reshape(-1, 3)
+    g = np.stack(np.meshgrid(np.arange(nc[0]), np.arange(nc[1]), np.arange(nc[2]), indexing="ij"), -1).reshape(-1, 3)
     x = ((g[:, None, :] + base[None, :, :]) * a).reshape(-1, 3)
     x = x + rng.uniform(-jitter, jitter, size=x.shape)
     x = np.mod(x, L)
@@ -129,7 +133,7 @@ def lj_charge_fluid(ncell, seed=12345, rho=0.1, jitter=0.3):
     q = np.where(typ == 1, 0.4, -0.4)
     alpha = np.where(typ == 1, 1.0, 0.5)
     mol = np.zeros(n, dtype=np.int32)
-    return P.System(x, q, typ, mol, alpha, [0, 0, 0], [L, L, L], 2)
+    return P.System(x, q, typ, mol, alpha, [0, 0, 0], list(L), 2)
 
 
 def fluid_style(sysm, cut_lj=2.5, cut_coul=12.0, **kw):
