@@ -10,10 +10,13 @@ REBUILD_EVERY steps inside the timed region, as LAMMPS' delay-10 schedule would.
 
   value  : whole-job atom-steps/s with inputs resident in HBM (device pointers through the C ABI)
   e2e    : same metric through the C ABI with HOST buffers (pinned), H2D of x/mu and D2H of f/mu/E inside
-  roofline: dominant kernel k_sweep<list>: algorithmic bytes (52*P + 104*N per launch) over the
-            CUDA-event duration of its launches, against MEASURED_PEAKS.json hbm_gbs
+  roofline: dominant kernel k_sweep_cached (one dipole iteration): bytes it must move through HBM per launch
+            (20 B per pair streamed + the atom records once) over the CUDA-event duration of its
+            launches, against MEASURED_PEAKS.json hbm_gbs; SURVEY §8d's every-gather-from-HBM model beside it
   cpu_baseline: the reference binary (oracle/_ref/lmp_serial, 1 core: it is serial by design) on a bounded
             2048-atom sample of the same fluid, else the oracle port on all host threads
+  N > 1  : ONE periodic system of 32000*N atoms, spatially decomposed into N bricks (one process per GPU):
+            ghost positions once per step, ghost dipoles once per SCF sweep (weak scaling)
   --impl reference: times that CPU reference arm alone.
 """
 import argparse
@@ -54,12 +57,17 @@ def load_pb():
     return mod
 
 
+GRIDS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+
+
 def workload_config(n_gpus, parallelism):
-    return {"workload": f"synthetic polarizable LJ+charge fluid, {4 * NCELL ** 3} atoms, rho 0.1/A^3, "
+    return {"workload": f"synthetic polarizable LJ+charge fluid, {4 * NCELL ** 3} atoms per GPU "
+                        f"({4 * NCELL ** 3 * n_gpus} in total), rho 0.1/A^3, "
                         f"cut {CUT_LJ}/{CUT_COUL}, fixed_iteration yes max_iterations {ITER}, damp_type exponential, "
                         f"polar_gs_ranked no, polar_cutoff {CUT_COUL} (neighbor-list dipole sweep)",
-            "atoms_per_gpu": 4 * NCELL ** 3, "sweeps_per_step": ITER, "rebuild_every": REBUILD_EVERY,
-            "parallelism": parallelism, "l2_policy": "working set (neighbor list 146 MB + state) exceeds the 126 MB L2"}
+            "atoms_per_gpu": 4 * NCELL ** 3, "atoms_total": 4 * NCELL ** 3 * n_gpus, "sweeps_per_step": ITER,
+            "rebuild_every": REBUILD_EVERY, "parallelism": parallelism,
+            "l2_policy": "working set (neighbor list + radial cache ~600 MB per GPU) exceeds the 126 MB L2"}
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -228,21 +236,42 @@ def gpu_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    sysm = H.lj_charge_fluid(NCELL, seed=12345 + rank)  # replicas: every rank its own 32k-atom system
-    n = sysm.n
-    style = make_style(pb, sysm, local)
+    # N GPUs: ONE periodic system of 32000*N atoms cut into N bricks (spatial decomposition, weak scaling);
+    # every rank generates the same global system and keeps the atoms of its own brick
+    pg = GRIDS.get(world)
+    if pg is None:
+        raise SystemExit(f"bench.py: no brick grid defined for {world} GPUs (use 1, 2, 4 or 8)")
+    gsys = H.lj_charge_fluid(NCELL if world == 1 else tuple(NCELL * np.array(pg)), seed=12345)
+    style = make_style(pb, gsys, local)
     dev = torch.device("cuda", local)
+    if world > 1:
+        box = [pb.comm_create_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        style.comm_init(rank, world, box[0], pg)
+        lo, hi = style.subdomain()
+        own = np.nonzero(np.all((gsys.x >= lo) & (gsys.x < hi), axis=1))[0]
+    else:
+        own = np.arange(gsys.n)
+
+    class Owned:
+        pass
+    sysm = Owned()
+    sysm.x, sysm.q, sysm.type, sysm.alpha, sysm.tag = (np.ascontiguousarray(gsys.x[own]), np.ascontiguousarray(gsys.q[own]),
+                                                       np.ascontiguousarray(gsys.type[own]), np.ascontiguousarray(gsys.alpha[own]),
+                                                       np.ascontiguousarray(gsys.tag[own]))
+    n = sysm.n = len(own)
 
     # device-resident inputs
     t_x = torch.tensor(sysm.x, dtype=torch.float64, device=dev).contiguous()
     t_q = torch.tensor(sysm.q, dtype=torch.float64, device=dev)
     t_type = torch.tensor(sysm.type, dtype=torch.int32, device=dev)
     t_alpha = torch.tensor(sysm.alpha, dtype=torch.float64, device=dev)
+    t_tag = torch.tensor(sysm.tag, dtype=torch.int32, device=dev)
     t_mu = torch.zeros((n, 3), dtype=torch.float64, device=dev)
     t_f = torch.zeros((n, 3), dtype=torch.float64, device=dev)
     t_ef = torch.zeros((n, 3), dtype=torch.float64, device=dev)
     ptrs = dict(x=t_x.data_ptr(), q=t_q.data_ptr(), type=t_type.data_ptr(), alpha=t_alpha.data_ptr(),
-                mu=t_mu.data_ptr(), f=t_f.data_ptr(), ef_static=t_ef.data_ptr())
+                tag=t_tag.data_ptr(), mu=t_mu.data_ptr(), f=t_f.data_ptr(), ef_static=t_ef.data_ptr())
     torch.cuda.synchronize()
 
     def barrier():
@@ -260,6 +289,7 @@ def gpu_arm(args):
     for k in range(args.warmup):
         res = step_dev(k)
     polar_pairs = int(style.debug_fetch("polar_pairs", np.uint64, 1)[0])
+    comm_stats = style.debug_fetch("comm_stats", np.float64, 5)
     pb.lib().polb200_set_option(style._h, b"time_sweeps", 1.0)
     style.launch_count(reset=True)
     sampler = ClockSampler(local)
@@ -289,10 +319,11 @@ def gpu_arm(args):
     h_q = np.ascontiguousarray(sysm.q)
     h_type = np.ascontiguousarray(sysm.type)
     h_alpha = np.ascontiguousarray(sysm.alpha)
+    h_tag = np.ascontiguousarray(sysm.tag)
 
     def step_host(k):
         h_f[:] = 0.0
-        return style.compute(h_x, h_q, h_type, h_alpha, h_mu, h_f, ef_static=h_ef, eflag=1, vflag=2,
+        return style.compute(h_x, h_q, h_type, h_alpha, h_mu, h_f, tag=h_tag, ef_static=h_ef, eflag=1, vflag=2,
                              ago=k % REBUILD_EVERY)
 
     for k in range(max(1, args.warmup // 2)):
@@ -305,14 +336,18 @@ def gpu_arm(args):
     wall_e2e = time.perf_counter() - t1
     assert abs(r2.eng_pol - eng_pol) <= 1e-9 * abs(eng_pol)
 
-    # max over ranks
+    # max over ranks (times), sum over ranks (atoms, energy: per-rank partials by LAMMPS convention)
     times = torch.tensor([wall, wall_e2e], dtype=torch.float64, device=dev)
+    sums = torch.tensor([float(n), eng_pol, float(polar_pairs)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums)
     wall, wall_e2e = float(times[0]), float(times[1])
+    eng_pol_total = float(sums[1])
 
     if rank == 0:
-        total_atoms = n * world
+        total_atoms = int(sums[0])
+        assert total_atoms == gsys.n
         value = total_atoms * args.steps / wall
         e2e_value = total_atoms * args.steps / wall_e2e
         peaks = {}
@@ -321,8 +356,15 @@ def gpu_arm(args):
             peaks = json.loads(pk.read_text())
         peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
         sweep_ms = float(sweep[0]) / max(float(sweep[1]), 1.0)
-        alg_bytes = 52.0 * polar_pairs + 104.0 * n
+        # Bytes one launch of the dominant kernel (k_sweep_cached) must move through HBM:
+        # the per-pair streams -- 4 B neighbour index + 16 B cached radial scalars (s1,s2) -- are read exactly
+        # once; the 32-B position and dipole records of the owned+ghost atoms are gathered ~700x each but from
+        # L2/L1, so they count once; plus E_static in and the new dipole out per owned atom.
+        nghost = int(res.nghost)
+        alg_bytes = 20.0 * polar_pairs + 64.0 * (n + nghost) + 64.0 * n
         achieved = alg_bytes / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else None
+        # SURVEY §8d's matrix-free model (every gather charged to HBM): 52 B per pair + 104 B per atom
+        survey_bytes = 52.0 * polar_pairs + 104.0 * n
         # CPU baseline on a bounded sample (rank 0, N=1 only)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -343,7 +385,11 @@ def gpu_arm(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(world, "replicas" if world > 1 else "single"),
+            "config": workload_config(world, "single" if world == 1 else
+                                      f"spatial decomposition, {pg[0]}x{pg[1]}x{pg[2]} bricks, one process per GPU; ghost positions "
+                                      f"once per step (NCCL), ghost dipoles once per sweep ("
+                                      + ("stored by the sweep kernel into peer memory over NVLink + signal/wait barrier"
+                                         if int(comm_stats[3]) else "NCCL send/recv") + ")"),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 48 * n, "d2h_bytes_per_step": 72 * n + 192,
                     "ms_per_step": wall_e2e / args.steps * 1e3},
             "gpu_launches": int(launches),
@@ -351,14 +397,24 @@ def gpu_arm(args):
             "device_ms_per_step": dev_ms / args.steps,
             "stage_ms": {"neigh_refresh": stage[0] / args.steps, "pair_field": stage[1] / args.steps,
                          "scf": stage[2] / args.steps, "pol_force": stage[3] / args.steps},
-            "roofline": {"bound": "hbm", "kernel": "k_sweep<list>", "achieved": achieved, "peak": peak_gbs,
+            "roofline": {"bound": "hbm", "kernel": "k_sweep_cached (one dipole iteration over the neighbor list)",
+                         "achieved": achieved, "peak": peak_gbs,
                          "unit": "GB/s", "frac": achieved / peak_gbs if achieved else None, "traffic": None,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650",
-                         "algorithmic_bytes_per_launch": alg_bytes, "pairs_in_cutoff": polar_pairs,
-                         "launch_ms": sweep_ms, "fp64_gflops_at_80_per_pair": 80.0 * polar_pairs / (sweep_ms * 1e-3) / 1e9
-                         if sweep_ms > 0 else None},
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "bytes_model": "20 B/pair streamed (index + cached radial scalars) + 64 B per owned+ghost atom "
+                                        "(position and dipole records, read once) + 64 B per owned atom (E_static in, dipole out)",
+                         "pairs_in_cutoff": polar_pairs, "launch_ms": sweep_ms,
+                         "gpairs_per_s": polar_pairs / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else None,
+                         "survey_8d_model": {"bytes": survey_bytes,
+                                             "achieved": survey_bytes / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else None,
+                                             "note": "52 B/pair + 104 B/atom with every neighbour gather charged to HBM; "
+                                                     "exceeds the HBM peak because the gathers are L2/L1 hits"}},
             "cpu_baseline": cpu, "clocks": clocks,
-            "check": {"eng_pol": eng_pol, "iterations": res.iterations},
+            "halo": None if world == 1 else {"rank0_owned": n, "rank0_send_slots": int(comm_stats[0]),
+                                             "rank0_ghosts": int(comm_stats[1]), "bytes_per_sweep_rank0": 32 * int(comm_stats[0]),
+                                             "peer_push": bool(int(comm_stats[3]))},
+            "check": {"eng_pol": eng_pol_total, "iterations": res.iterations},
         }
         print(json.dumps(line))
     style.close()
