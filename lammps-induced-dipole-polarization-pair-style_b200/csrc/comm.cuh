@@ -119,7 +119,7 @@ static void comm_close_peers(polb200_handle *h)
 {
   CommState &c = h->comm;
   for (int r = 0; r < MAX_PEERS; r++)
-    for (int k = 0; k < 3; k++) {
+    for (int k = 0; k < NPEERBUF; k++) {
       if (c.peer_ptr[k][r] && r != c.rank) cudaIpcCloseMemHandle(c.peer_ptr[k][r]);
       c.peer_ptr[k][r] = nullptr;
     }
@@ -136,13 +136,13 @@ static void comm_map_peers(polb200_handle *h)
   c.mapped_ptr[0] = h->mua.p;
   c.mapped_ptr[1] = h->mub.p;
   c.mapped_ptr[2] = c.flags.p;
+  c.mapped_ptr[3] = h->xq.p;
   int ok = c.want_push && c.nranks <= MAX_PEERS ? 1 : 0;
-  cudaIpcMemHandle_t mine[3];
+  cudaIpcMemHandle_t mine[NPEERBUF];
   memset(mine, 0, sizeof(mine));
   if (ok) {
-    void *ptrs[3] = {h->mua.p, h->mub.p, c.flags.p};
-    for (int k = 0; k < 3; k++)
-      if (cudaIpcGetMemHandle(&mine[k], ptrs[k]) != cudaSuccess) {
+    for (int k = 0; k < NPEERBUF; k++)
+      if (cudaIpcGetMemHandle(&mine[k], c.mapped_ptr[k]) != cudaSuccess) {
         cudaGetLastError();
         ok = 0;
       }
@@ -156,7 +156,7 @@ static void comm_map_peers(polb200_handle *h)
   CUDA_CHECK(cudaStreamSynchronize(h->stream));
   if (ok) {
     for (int r = 0; r < c.nranks && ok; r++) {
-      for (int k = 0; k < 3 && ok; k++) {
+      for (int k = 0; k < NPEERBUF && ok; k++) {
         if (r == c.rank) {
           c.peer_ptr[k][r] = c.mapped_ptr[k];
           continue;
@@ -186,6 +186,7 @@ static void comm_map_peers(polb200_handle *h)
     c.push.mu[0][r] = static_cast<double4 *>(c.peer_ptr[0][r]);
     c.push.mu[1][r] = static_cast<double4 *>(c.peer_ptr[1][r]);
     c.push.flag[r] = static_cast<unsigned long long *>(c.peer_ptr[2][r]);
+    c.push.xq[r] = static_cast<double4 *>(c.peer_ptr[3][r]);
   }
   c.push.enabled = 1;
 }
@@ -220,8 +221,8 @@ static void comm_build_ghosts(polb200_handle *h, int n)
   const int nan_local = hflags[0] & 1;
   const int ns = (int)ns64;
   c.nsend = ns;
-  c.push_off.ensure(n + 2);
-  CUDA_CHECK(cudaMemcpyAsync(c.push_off.p, h->rowstart.p, (size_t)(n + 1) * sizeof(unsigned long long),
+  h->push_off.ensure(n + 2);
+  CUDA_CHECK(cudaMemcpyAsync(h->push_off.p, h->rowstart.p, (size_t)(n + 1) * sizeof(unsigned long long),
                              cudaMemcpyDeviceToDevice, h->stream));
   const int nmax = std::max(std::max(n, ns), 64);
   h->keys.ensure(nmax); h->keys2.ensure(nmax); h->vals.ensure(nmax); h->vals2.ensure(nmax);
@@ -286,8 +287,8 @@ static void comm_build_ghosts(polb200_handle *h, int n)
     CUDA_CHECK(cudaMemsetAsync(c.flags.p, 0, c.flags.cap * sizeof(unsigned long long), h->stream));
     c.flags_zeroed = true;
   }
-  int moved = (next > h->mua.cap || next > h->mub.cap || c.mapped_ptr[0] != h->mua.p || c.mapped_ptr[1] != h->mub.p ||
-               c.mapped_ptr[2] != c.flags.p) ? 1 : 0;
+  int moved = (next > h->mua.cap || next > h->mub.cap || next > h->xq.cap || c.mapped_ptr[0] != h->mua.p ||
+               c.mapped_ptr[1] != h->mub.p || c.mapped_ptr[2] != c.flags.p || c.mapped_ptr[3] != h->xq.p) ? 1 : 0;
   int *flag = h->flags.p + 2;
   CUDA_CHECK(cudaMemcpyAsync(flag, &moved, sizeof(int), cudaMemcpyHostToDevice, h->stream));
   comm_allreduce(h, flag, 1, ncclInt, ncclMax);
@@ -333,22 +334,45 @@ static void comm_build_ghosts(polb200_handle *h, int n)
   // 4. peer push tables: for every send slot the ext index it occupies on its destination rank,
   //    returned by the receivers, stored per owned atom (CSR push_off in (owner, direction) order)
   if (moved) comm_map_peers(h);
-  c.push_rank.ensure(ns + 1); c.push_idx.ensure(ns + 1);
+  h->push_ptr0.ensure(ns + 1); h->push_ptr1.ensure(ns + 1); c.push_ptrx.ensure(ns + 1); c.dir_of_u.ensure(ns + 1);
+  h->push_ready = false;
   if (ng) LAUNCH(h, k_ghost_ext_index, cdiv(ng, 256), 256, ng, n, c.gslot.p, (int *)c.rbufi.p);  // per recv slot
   comm_exchange_reverse(h, c.rbufi.p, c.sbufi.p, sizeof(int));
-  if (ns) {
+  if (c.push.enabled) {
     DirTable T;
     for (int d = 0; d < NDIR; d++) T.v[d] = c.plan.dest[d];
-    LAUNCH(h, k_push_tables, cdiv(ns, 256), 256, ns, c.slot_of_u.p, c.send_dir.p, T, (const int *)c.sbufi.p,
-           c.push_rank.p, c.push_idx.p);
+    if (ns)
+      LAUNCH(h, k_push_tables, cdiv(ns, 256), 256, ns, c.slot_of_u.p, c.send_dir.p, T, (const int *)c.sbufi.p, c.push,
+             h->push_ptr0.p, h->push_ptr1.p, c.push_ptrx.p, c.dir_of_u.p);
+    h->push_ready = true;
   }
 }
 
-// ghost refresh through NCCL: positions (shifted) and/or one dipole array
-static void comm_refresh(polb200_handle *h, bool pos, double4 *mu)
+// inter-GPU barrier of the peer-push path, optionally carrying this rank's partial squared change to
+// everybody: afterwards *change_inout holds the global sum (ranks added in rank order: identical everywhere)
+static void comm_signal_wait(polb200_handle *h, double *change_inout)
+{
+  CommState &c = h->comm;
+  c.epoch++;
+  LAUNCH(h, k_signal_wait, 1, 32, c.rank, c.nranks, c.epoch, c.push, change_inout);
+}
+
+// ghost refresh: positions (shifted) and/or one dipole array (mua or mub).
+//   peer push: one store kernel per array straight into the neighbours' ghost slots + one barrier kernel.
+//     `fence_before`: the targets may still be read by the peers' previous step (positions at the start of a
+//     step), so a barrier also precedes the stores;
+//   otherwise: pack -> grouped NCCL send/recv -> unpack.
+static void comm_refresh(polb200_handle *h, bool pos, double4 *mu, bool fence_before)
 {
   CommState &c = h->comm;
   const int n = h->nloc, ng = h->nghost, ns = c.nsend;
+  if (h->push_ready && c.push.enabled && (mu == nullptr || mu == h->mua.p || mu == h->mub.p)) {
+    if (fence_before) comm_signal_wait(h, nullptr);
+    if (pos && ns) LAUNCH(h, k_push_pos, cdiv(ns, 256), 256, ns, c.send_owner_u.p, c.dir_of_u.p, c.geom, h->xq.p, c.push_ptrx.p);
+    if (mu && ns) LAUNCH(h, k_push_rec, cdiv(ns, 256), 256, ns, c.send_owner_u.p, mu, mu == h->mub.p ? h->push_ptr1.p : h->push_ptr0.p);
+    comm_signal_wait(h, nullptr);
+    return;
+  }
   if (pos) {
     if (ns) LAUNCH(h, k_pack_pos, cdiv(ns, 256), 256, ns, c.send_owner.p, c.send_dir.p, c.geom, h->xq.p, c.sbuf.p);
     comm_exchange(h, c.sbuf.p, c.rbuf.p, sizeof(double4));
@@ -359,15 +383,6 @@ static void comm_refresh(polb200_handle *h, bool pos, double4 *mu)
     comm_exchange(h, c.sbuf.p, c.rbuf.p, sizeof(double4));
     if (ng) LAUNCH(h, k_unpack_rec, cdiv(ng, 256), 256, ng, c.gslot.p, c.rbuf.p, mu + n);
   }
-}
-
-// inter-GPU barrier of the peer-push path, carrying this rank's partial squared change to everybody:
-// afterwards scal[S_CHANGE] holds the global sum (ranks added in rank order: identical on all ranks)
-static void comm_signal_wait(polb200_handle *h, double *change_inout)
-{
-  CommState &c = h->comm;
-  c.epoch++;
-  LAUNCH(h, k_signal_wait, 1, 32, c.rank, c.nranks, c.epoch, c.push, change_inout);
 }
 
 }  // namespace polb200

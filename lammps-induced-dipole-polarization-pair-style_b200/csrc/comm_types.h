@@ -75,7 +75,9 @@ constexpr int MAX_PEERS = 8;
 struct PeerPush {
   int enabled;
   double4 *mu[2][MAX_PEERS];          // [buffer parity][rank]: base of that rank's dipole array (ext order)
+  double4 *xq[MAX_PEERS];             // [rank]: base of that rank's position+charge array (ext order)
   unsigned long long *flag[MAX_PEERS];  // [rank]: base of that rank's arrival counters (one per source rank)
 };
+constexpr int NPEERBUF = 4;  // mapped buffers per rank: mua, mub, arrival counters, xq
 
 }  // namespace polb200

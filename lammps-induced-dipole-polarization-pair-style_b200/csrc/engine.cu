@@ -102,13 +102,14 @@ struct CommState {
   int nsend = 0, nrecv = 0;
   long nglobal = 0;
   int nloc_of[64] = {};
-  DBuf<int> send_owner_u, send_owner, send_dir, slot_of_u, dir_start, gslot, counts_dev, push_rank, push_idx;
-  DBuf<unsigned long long> push_off, flags;
+  DBuf<int> send_owner_u, send_owner, send_dir, slot_of_u, dir_start, gslot, counts_dev, dir_of_u;
+  DBuf<double4 *> push_ptrx;
+  DBuf<unsigned long long> flags;
   DBuf<double4> sbuf, rbuf;
   DBuf<int4> sbufi, rbufi;
   DBuf<char> ipc_dev;
-  void *peer_ptr[3][MAX_PEERS] = {};
-  void *mapped_ptr[3] = {};
+  void *peer_ptr[NPEERBUF][MAX_PEERS] = {};
+  void *mapped_ptr[NPEERBUF] = {};
   PeerPush push{};
   unsigned long long epoch = 0;
   std::vector<void *> graveyard;  // dipole arrays replaced while peers may still map them
@@ -135,6 +136,7 @@ struct polb200_handle {
   double bin_div = 4.0;          // neighbor cutoff / cell width
   int sweep_variant = 20;        // 0: k_sweep<true> (first version), 1/2: k_sweep_list2 with PF = 1/2
   bool use_tight = true;         // per-step tight list
+  bool use_push = true;          // sweep kernel stores new dipoles into their ghost copies itself
   bool time_sweeps = false;     // record CUDA events around every k_sweep launch (bench roofline)
   std::vector<cudaEvent_t> sweep_ev;
   size_t sweep_ev_used = 0;
@@ -164,6 +166,10 @@ struct polb200_handle {
   DBuf<int> s_nspecial, s_special;
   DBuf<unsigned long long> cnt, rowstart;
   DBuf<int> neigh, tneigh, tcount;
+  // fused sweep + ghost update: per owned atom the addresses of its ghost copies in mua / mub
+  DBuf<unsigned long long> push_off;
+  DBuf<double4 *> push_ptr0, push_ptr1;
+  bool push_ready = false;
   DBuf<double2> s12;             // per-step radial cache aligned with the tight list
   bool s12_valid = false;
   DBuf<char> cub_tmp;
@@ -362,10 +368,10 @@ static void grow_ext(polb200_handle *h, int n, size_t next)
 namespace polb200 {
 
 // ghost copies follow their owners: positions (once per step) and/or one dipole array (once per sweep)
-static void ghost_update(polb200_handle *h, bool pos, double4 *mu)
+static void ghost_update(polb200_handle *h, bool pos, double4 *mu, bool fence_before = false)
 {
   if (h->comm.active) {
-    comm_refresh(h, pos, mu);
+    comm_refresh(h, pos, mu, fence_before);
     return;
   }
   const int ng = h->nghost, n = h->nloc;
@@ -438,7 +444,16 @@ static void rebuild(polb200_handle *h, const polb200_atoms *at)
              h->g_owner_u.p, h->g_shift_u.p, h->keys.p, h->vals.p);
       sort_pairs(h, ng, h->keys.p, h->keys2.p, h->vals.p, h->vals2.p, bits_for(g.ncell + 1));
     }
+    h->push_off.ensure(n + 2);  // the ghost count scan is also the CSR of every owned atom's images
+    CUDA_CHECK(cudaMemcpyAsync(h->push_off.p, h->rowstart.p, (size_t)(n + 1) * sizeof(unsigned long long),
+                               cudaMemcpyDeviceToDevice, h->stream));
     grow_ext(h, n, next);
+    h->push_ptr0.ensure(ng + 1); h->push_ptr1.ensure(ng + 1);
+    if (ng > 0) {
+      LAUNCH(h, k_invert_perm, cdiv(ng, 256), 256, ng, h->vals2.p, h->keys.p);  // keys is free again: sorted position of u
+      LAUNCH(h, k_push_tables_local, cdiv(ng, 256), 256, ng, n, h->keys.p, h->mua.p, h->mub.p, h->push_ptr0.p, h->push_ptr1.p);
+    }
+    h->push_ready = true;
     h->cg_start.ensure(g.ncell + 2);
     if (ng > 0) {
       LAUNCH(h, k_ghost_gather, cdiv(ng, 256), 256, ng, n, h->vals2.p, h->g_owner_u.p, h->g_shift_u.p, h->box,
@@ -541,12 +556,8 @@ static void sweep_events_collect(polb200_handle *h)
 static PushArgs push_args(polb200_handle *h, const double4 *nxt)
 {
   PushArgs Q{};
-  const CommState &c = h->comm;
-  Q.off = c.push_off.p;
-  Q.rank = c.push_rank.p;
-  Q.idx = c.push_idx.p;
-  const int par = nxt == h->mub.p ? 1 : 0;
-  for (int r = 0; r < MAX_PEERS; r++) Q.base[r] = c.push.mu[par][r];
+  Q.off = h->push_off.p;
+  Q.ptr = nxt == h->mub.p ? h->push_ptr1.p : h->push_ptr0.p;
   return Q;
 }
 
@@ -697,7 +708,8 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
   if (need) rebuild(h, at);
   else {
     LAUNCH(h, k_refresh_local, cdiv(n, 256), 256, n, h->perm.p, h->c_x.p, h->c_mu.p, h->xq.p, h->mua.p);
-    ghost_update(h, true, h->mua.p);
+    // (peer push: the neighbours may still be reading these ghosts in their previous step => barrier first)
+    ghost_update(h, true, h->mua.p, true);
   }
   const int ng = h->nghost;
   const int nrowblocks = cdiv(n, WARPS_PER_BLOCK);
@@ -776,7 +788,7 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
       else sequential = true;
     }
     // fused sweep + halo: new dipoles go straight into the neighbour bricks' ghost slots (Jacobi sweeps)
-    const bool push = comm && h->comm.push.enabled && !gs && list_mode && h->sweep_variant != 0 &&
+    const bool push = h->push_ready && h->use_push && !gs && list_mode && h->sweep_variant != 0 &&
                       !(h->sweep_variant >= 11 && h->sweep_variant <= 14);
     const double natoms_norm = comm ? (double)h->comm.nglobal : (double)n;
     double4 *cur = h->mua.p, *nxt = h->mub.p;
@@ -797,8 +809,9 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
         else LAUNCH(h, (k_sweep<false>), nrowblocks, BLOCK, 0, n, order, P, L, A, h->xq.p, cur, h->ef.p, nxt, h->partial.p);
         sweep_event(h);
         if (want_change) reduce_partials<1>(h, nparts, h->scal.p + S_CHANGE, 0);
-        if (push) comm_signal_wait(h, want_change ? h->scal.p + S_CHANGE : nullptr);  // barrier (+ all-reduce)
-        else {
+        if (push) {
+          if (comm) comm_signal_wait(h, want_change ? h->scal.p + S_CHANGE : nullptr);  // barrier (+ all-reduce)
+        } else {
           ghost_update(h, false, nxt);
           if (comm && want_change) comm_allreduce(h, h->scal.p + S_CHANGE, 1, ncclDouble, ncclSum);
         }
@@ -813,7 +826,7 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
           else LAUNCH(h, (k_sweep<false>), nb, BLOCK, beg, end, order, P, L, A, h->xq.p, cur, h->ef.p, nxt, h->partial.p);
           if (want_change) reduce_partials<1>(h, nparts, h->scal.p + S_CHANGE, c > 0);
           LAUNCH(h, k_commit_rows, cdiv(end - beg, 256), 256, beg, end, order, nxt, cur);
-          ghost_update(h, false, cur);
+          ghost_update(h, false, cur, true);  // in place: the neighbours must have finished reading this chunk's input
         }
         if (comm && want_change) comm_allreduce(h, h->scal.p + S_CHANGE, 1, ncclDouble, ncclSum);
       }
@@ -833,10 +846,13 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
         break;
       }
     }
+    // after fused sweeps the ghost copies of the final array are already current on every brick
+    const bool ghosts_current = push && !diverged;
     if (cur != h->mua.p) {  // keep the canonical buffer
-      CUDA_CHECK(cudaMemcpyAsync(h->mua.p, cur, (size_t)n * sizeof(double4), cudaMemcpyDeviceToDevice, h->stream));
+      CUDA_CHECK(cudaMemcpyAsync(h->mua.p, cur, (size_t)(ghosts_current ? n + ng : n) * sizeof(double4),
+                                 cudaMemcpyDeviceToDevice, h->stream));
     }
-    ghost_update(h, false, h->mua.p);
+    if (!ghosts_current) ghost_update(h, false, h->mua.p);
   }
   CUDA_CHECK(cudaEventRecord(h->ev[3], h->stream));
 
@@ -960,6 +976,7 @@ int polb200_create(polb200_t **out, int device)
   polb200_t *h = new polb200_handle();
   h->device = device;
   if (const char *v = getenv("POLB200_SWEEP_VARIANT")) h->sweep_variant = atoi(v);  // experiments only
+  if (const char *v = getenv("POLB200_USE_PUSH")) h->use_push = atoi(v) != 0;
   int rc = guarded(h, [&] {
     CUDA_CHECK(cudaSetDevice(device));
     CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -986,13 +1003,14 @@ void polb200_destroy(polb200_t *h)
   if (h->comm.active) {
     CommState &c = h->comm;
     comm_close_peers(h);
-    h->mua.graveyard = h->mub.graveyard = nullptr;
+    h->mua.graveyard = h->mub.graveyard = h->xq.graveyard = nullptr;
     for (void *q : c.graveyard) cudaFree(q);
     c.graveyard.clear();
     for (auto *b : {&c.send_owner_u, &c.send_owner, &c.send_dir, &c.slot_of_u, &c.dir_start, &c.gslot, &c.counts_dev,
-                    &c.push_rank, &c.push_idx})
+                    &c.dir_of_u})
       b->release();
-    c.push_off.release(); c.flags.release(); c.sbuf.release(); c.rbuf.release(); c.sbufi.release(); c.rbufi.release();
+    c.push_ptrx.release();
+    c.flags.release(); c.sbuf.release(); c.rbuf.release(); c.sbufi.release(); c.rbufi.release();
     c.ipc_dev.release();
     if (c.nccl) g_nccl.CommDestroy(c.nccl);
     c.active = false;
@@ -1006,7 +1024,7 @@ void polb200_destroy(polb200_t *h)
                   &h->s_special, &h->neigh, &h->tneigh, &h->tcount, &h->flags, &h->ranked, &h->ranked_in})
     b->release();
   for (auto *b : {&h->xq, &h->mua, &h->mub, &h->ef, &h->f_pair, &h->f_pol}) b->release();
-  h->s12.release();
+  h->s12.release(); h->push_off.release(); h->push_ptr0.release(); h->push_ptr1.release();
   h->tm.release(); h->cnt.release(); h->rowstart.release(); h->cub_tmp.release(); h->rmin_bits.release();
   h->h_stage.release(); h->h_scal.release(); h->h_int.release();
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
@@ -1158,6 +1176,10 @@ int polb200_set_option(polb200_t *h, const char *name, double value)
     h->have_lists = false;
     return POLB200_OK;
   }
+  if (!strcmp(name, "use_push")) {
+    h->use_push = value != 0.0;
+    return POLB200_OK;
+  }
   if (!strcmp(name, "use_tight")) {
     h->use_tight = value != 0.0;
     return POLB200_OK;
@@ -1280,7 +1302,7 @@ int polb200_comm_init(polb200_t *h, int rank, int nranks, const void *id_bytes, 
     c.nranks = nranks;
     for (int k = 0; k < 3; k++) c.pg[k] = procgrid[k];
     c.active = true;
-    h->mua.graveyard = h->mub.graveyard = &c.graveyard;
+    h->mua.graveyard = h->mub.graveyard = h->xq.graveyard = &c.graveyard;
     if (const char *v = getenv("POLB200_P2P_PUSH")) c.want_push = atoi(v) != 0;
     h->have_lists = false;
     if (h->box_set) comm_setup_geom(h);

@@ -79,21 +79,28 @@ __device__ __forceinline__ double warp_sum(double v)
   return v;
 }
 
-// what the fused sweep needs to store a new dipole into the ghost copies held by other bricks
+// what the fused sweep needs to store a new dipole into the ghost copies of its row atom: periodic images
+// in this GPU's own arrays and/or ghost slots of neighbour bricks (peer memory over NVLink)
 struct PushArgs {
-  const unsigned long long *off;  // CSR over owned atoms (cell-sorted index) into rank/idx
-  const int *rank;
-  const int *idx;
-  double4 *base[MAX_PEERS];       // per rank: that rank's OUTPUT dipole array of this sweep (peer mapping)
+  const unsigned long long *off;  // CSR over owned atoms (cell-sorted index) into ptr
+  double4 *const *ptr;            // absolute address of every copy in the OUTPUT dipole array of this sweep
 };
 
-__device__ __forceinline__ void push_row(const PushArgs &Q, int s, int lane, double nx, double ny, double nz, double a)
+// The address is fetched at the START of the row (push_prefetch) so that the two dependent loads
+// (offset -> address) are hidden behind the row's pair loop instead of sitting at the end of the warp's life.
+// An atom has at most 26 copies, so one address per lane covers every case.
+__device__ __forceinline__ double4 *push_prefetch(const PushArgs &Q, int s, int lane)
+{
+  const unsigned long long b = Q.off[s], e = Q.off[s + 1];
+  return b + lane < e ? Q.ptr[b + lane] : nullptr;
+}
+
+__device__ __forceinline__ void push_row(double4 *dst, double nx, double ny, double nz, double a)
 {
   nx = __shfl_sync(FULL, nx, 0);
   ny = __shfl_sync(FULL, ny, 0);
   nz = __shfl_sync(FULL, nz, 0);
-  const unsigned long long b = Q.off[s], e = Q.off[s + 1];
-  for (unsigned long long u = b + lane; u < e; u += 32) Q.base[Q.rank[u]][Q.idx[u]] = make_double4(nx, ny, nz, a);
+  if (dst) *dst = make_double4(nx, ny, nz, a);
 }
 
 // 256-bit loads of the 32-byte records (sm_100a: LDG.E.ENL2.256 via the aligned double4 types)
@@ -677,6 +684,8 @@ k_sweep_list2(int pos_beg, int pos_end, const int *__restrict__ order, DevParams
   const int s = order ? order[pos] : pos;
   const double4 xi = xq[s];
   const double4 mi = mu_in[s];
+  double4 *push_dst = nullptr;
+  if (PUSH) push_dst = push_prefetch(Q, s, lane);
   double ex = 0, ey = 0, ez = 0;
   if (mi.w != 0.0) {
     const int *__restrict__ row = L.neigh + L.begin(s);
@@ -727,7 +736,7 @@ k_sweep_list2(int pos_beg, int pos_end, const int *__restrict__ order, DevParams
     if (CHANGE)
       row_change[pos - pos_beg] = (nx - mi.x) * (nx - mi.x) + (ny - mi.y) * (ny - mi.y) + (nz - mi.z) * (nz - mi.z);
   }
-  if (PUSH) push_row(Q, s, lane, nx, ny, nz, mi.w);
+  if (PUSH) push_row(push_dst, nx, ny, nz, mi.w);
 }
 
 // Two neighbours per lane per trip: two independent dependency chains (rsqrt -> exp -> accumulate) in
@@ -826,6 +835,8 @@ k_sweep_cached(int pos_beg, int pos_end, const int *__restrict__ order, ListRows
   const int s = order ? order[pos] : pos;
   const double4 xi = xq[s];
   const double4 mi = mu_in[s];
+  double4 *push_dst = nullptr;
+  if (PUSH) push_dst = push_prefetch(Q, s, lane);
   double ex = 0, ey = 0, ez = 0;
   if (mi.w != 0.0) {
     const unsigned long long beg = L.begin(s);
@@ -864,7 +875,7 @@ k_sweep_cached(int pos_beg, int pos_end, const int *__restrict__ order, ListRows
     if (CHANGE)
       row_change[pos - pos_beg] = (nx - mi.x) * (nx - mi.x) + (ny - mi.y) * (ny - mi.y) + (nz - mi.z) * (nz - mi.z);
   }
-  if (PUSH) push_row(Q, s, lane, nx, ny, nz, mi.w);
+  if (PUSH) push_row(push_dst, nx, ny, nz, mi.w);
 }
 
 // commit a chunk of the ranked colouring sweep: staged values become visible (owned records)
@@ -1370,16 +1381,53 @@ struct DirTable {
   int v[NDIR];
 };
 
-// push tables in (owner, direction) order: destination rank and remote ext index of every send slot
+// push tables in (owner, direction) order: for every send slot the address of the ghost record it feeds on
+// its destination rank -- in both dipole arrays and in the position array (peer mappings; the rank's own
+// arrays for self images) -- and its direction (for the periodic shift of pushed positions)
 __global__ void k_push_tables(int ns, const int *__restrict__ slot_of_u, const int *__restrict__ dir_of_slot, DirTable dest,
-                              const int *__restrict__ remote_of_slot, int *__restrict__ push_rank,
-                              int *__restrict__ push_idx)
+                              const int *__restrict__ remote_of_slot, PeerPush P, double4 **__restrict__ ptr0,
+                              double4 **__restrict__ ptr1, double4 **__restrict__ ptrx, int *__restrict__ dir_of_u)
 {
   int u = blockIdx.x * blockDim.x + threadIdx.x;
   if (u >= ns) return;
   const int t = slot_of_u[u];
-  push_rank[u] = dest.v[dir_of_slot[t]];
-  push_idx[u] = remote_of_slot[t];
+  const int d = dir_of_slot[t];
+  const int r = dest.v[d];
+  const int idx = remote_of_slot[t];
+  ptr0[u] = P.mu[0][r] + idx;
+  ptr1[u] = P.mu[1][r] + idx;
+  ptrx[u] = P.xq[r] + idx;
+  dir_of_u[u] = d;
+}
+
+// once-per-step halo through peer memory: every send slot stores its (shifted) position / its dipole record
+// straight into the ghost slot of the brick that needs it
+__global__ void k_push_pos(int ns, const int *__restrict__ owner_u, const int *__restrict__ dir_of_u, SendGeom G,
+                           const double4 *__restrict__ xq, double4 *const *__restrict__ ptrx)
+{
+  int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= ns) return;
+  const double4 v = xq[owner_u[u]];
+  const int d = dir_of_u[u];
+  *ptrx[u] = make_double4(G.shift[d][0] != 0.0 ? v.x + G.shift[d][0] : v.x, G.shift[d][1] != 0.0 ? v.y + G.shift[d][1] : v.y,
+                          G.shift[d][2] != 0.0 ? v.z + G.shift[d][2] : v.z, v.w);
+}
+
+__global__ void k_push_rec(int ns, const int *__restrict__ owner_u, const double4 *__restrict__ src,
+                           double4 *const *__restrict__ ptr)
+{
+  int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u < ns) *ptr[u] = src[owner_u[u]];
+}
+
+// single GPU: the copies are the periodic images behind the owned atoms of the same arrays
+__global__ void k_push_tables_local(int ng, int nloc, const int *__restrict__ sorted_pos_of_u, double4 *mua,
+                                    double4 *mub, double4 **__restrict__ ptr0, double4 **__restrict__ ptr1)
+{
+  int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= ng) return;
+  ptr0[u] = mua + nloc + sorted_pos_of_u[u];
+  ptr1[u] = mub + nloc + sorted_pos_of_u[u];
 }
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
