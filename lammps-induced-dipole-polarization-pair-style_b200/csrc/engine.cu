@@ -1083,6 +1083,9 @@ const void *polb200_extract(const polb200_t *h, const char *name, int *dim)
   *dim = 2;
   if (!strcmp(name, "epsilon")) return h->style.epsilon.data();
   if (!strcmp(name, "sigma")) return h->style.sigma.data();
+  // integration-layer extras (not part of the reference's extract()): int setflag[(ntypes+1)^2], double cut_lj[...]
+  if (!strcmp(name, "setflag")) return h->style.setflag.data();
+  if (!strcmp(name, "cut_lj")) return h->style.cut_lj.data();
   return nullptr;
 }
 

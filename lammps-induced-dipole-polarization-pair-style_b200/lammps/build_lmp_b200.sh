@@ -1,0 +1,51 @@
+#!/bin/bash
+# Build a LAMMPS binary in which the reference's pair style is REPLACED by the B200 drop-in:
+#   lammps/_build/lmp_b200  =  reference host framework (LAMMPS 16Mar2018, from a scratch copy of
+#   $POLB200_REFERENCE/src, repaired exactly like the oracle build: oracle/build_ref.sh steps 1-3 without the
+#   dump hooks)  +  pair_lj_cut_coul_long_polarization_b200.{h,cpp}  +  libpolb200.so.
+# An unchanged input script (polarization/examples/*) then drives the CUDA path.  Nothing of the reference is
+# copied into this repository; the binary lands in lammps/_build/ (git-ignored, travels to the GPU box).
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+PKG="$(dirname "$HERE")"
+ROOT="$(dirname "$PKG")"
+REF="${POLB200_REFERENCE:-/root/reference}"
+OUT="$HERE/_build"
+W="${POLB200_LMP_SCRATCH:-/tmp/polb200_lmpbuild}"
+JOBS="${JOBS:-$(nproc)}"
+if [ ! -d "$REF/src" ]; then
+  echo "build_lmp_b200: $REF/src not present (GPU box?) - keeping prebuilt $OUT" >&2
+  exit 0
+fi
+[ -f "$PKG/libpolb200.so" ] || make -C "$PKG/csrc"
+mkdir -p "$OUT"
+if [ -x "$OUT/lmp_b200" ] && [ "$OUT/lmp_b200" -nt "$HERE/pair_lj_cut_coul_long_polarization_b200.cpp" ] \
+   && [ "$OUT/lmp_b200" -nt "$HERE/pair_lj_cut_coul_long_polarization_b200.h" ] && [ -z "${POLB200_LMP_REBUILD:-}" ]; then
+  echo "build_lmp_b200: $OUT/lmp_b200 is up to date"
+  exit 0
+fi
+if [ ! -f "$W/src/Obj_serial/lammps.o" ]; then
+  rm -rf "$W"; mkdir -p "$W"
+  cp -r "$REF/src" "$W/src"
+  chmod -R u+w "$W"
+  cd "$W/src"
+  rm -f STUBS/libmpi_stubs.a STUBS/*.o
+  make yes-kspace yes-molecule yes-rigid > "$W/install.log" 2>&1
+  (cd STUBS && make > "$W/stubs.log" 2>&1)
+  for f in accelerator_kokkos.h accelerator_omp.h atom_vec_ellipsoid.h dihedral_hybrid.h improper_hybrid.h; do
+    cp "$ROOT/oracle/ref_shims/$f" .
+  done
+  rm -f compute_dihedral.* compute_improper.* fix_nve_sphere.* fix_nh_sphere.* fix_nvt_sphere.* \
+        fix_npt_sphere.* fix_nph_sphere.* pair_lj_long_coul_long.* pair_buck_long_coul_long.* \
+        pair_lj_long_tip4p_long.* ewald_disp.*
+  POLB200_PATCH_ATOMVEC_ONLY=1 python3 "$ROOT/oracle/patch_ref.py" "$W/src"
+fi
+cd "$W/src"
+# the swap: the reference's implementation leaves, the drop-in takes its file names
+cp "$HERE/pair_lj_cut_coul_long_polarization_b200.h" pair_lj_cut_coul_long_polarization.h
+cp "$HERE/pair_lj_cut_coul_long_polarization_b200.cpp" pair_lj_cut_coul_long_polarization.cpp
+cp "$ROOT/include/polb200.h" .
+make -j"$JOBS" serial LIB="-L$PKG -lpolb200 -Wl,-rpath,'\$\$ORIGIN/../..'" > "$W/build.log" 2>&1 || { tail -40 "$W/build.log"; exit 1; }
+cp lmp_serial "$OUT/lmp_b200"
+strip "$OUT/lmp_b200"
+echo "build_lmp_b200: built $OUT/lmp_b200"

@@ -11,6 +11,7 @@ Never run on /root/reference (read-only).  Implements SURVEY.md Appendix A:
     so that per-atom dipoles / fields / forces, which the reference never exposes, can be
     written out for golden fixtures.  The numerics of compute() are untouched.
 """
+import os
 import re
 import sys
 from pathlib import Path
@@ -89,7 +90,8 @@ def main():
     if str(src.resolve()).startswith("/root/reference"):
         raise SystemExit("refusing to patch the read-only reference tree")
     patch_atom_vec_full(src / "atom_vec_full.cpp")
-    patch_pair(src / "pair_lj_cut_coul_long_polarization.cpp")
+    if not os.environ.get("POLB200_PATCH_ATOMVEC_ONLY"):  # the drop-in build replaces the pair style instead
+        patch_pair(src / "pair_lj_cut_coul_long_polarization.cpp")
     print("patched", src)
 
 
