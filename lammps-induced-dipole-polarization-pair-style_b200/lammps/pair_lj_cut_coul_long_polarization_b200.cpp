@@ -42,6 +42,10 @@ PairLJCutCoulLongPolarization::PairLJCutCoulLongPolarization(LAMMPS *lmp) : Pair
   respa_enable = 0;
   writedata = 1;
   ftable = NULL;
+  // the device returns the finished virial (pair part pairwise, polarization part as the reference's F.r sum
+  // over owned atoms), so ev_setup must keep vflag_global instead of deferring to
+  // virial_fdotr_compute() (src/pair.cpp:809-815)
+  no_virial_fdotr_compute = 1;
   handle = NULL;
   debug = 0;
   ntypes_set = 0;
@@ -218,9 +222,6 @@ void PairLJCutCoulLongPolarization::compute(int eflag, int vflag)
   eng_pol = res.eng_pol;
   if (vflag_global)
     for (int k = 0; k < 6; k++) virial[k] += res.virial[k];
-  // the device returns the finished virial (pair part pairwise, polarization part as the reference's
-  // F.r sum over owned atoms): nothing is left for Pair::virial_fdotr_compute()
-  vflag_fdotr = 0;
 
   if (debug) {
     fprintf(screen, "iterations: %d\n", res.iterations);
