@@ -235,7 +235,7 @@ static void comm_build_ghosts(polb200_handle *h, int n)
     sort_pairs(h, ns, h->keys.p, c.send_dir.p, h->vals.p, h->vals2.p, 5);  // stable: owners ascending per direction
     LAUNCH(h, k_gather_int, cdiv(ns, 256), 256, ns, h->vals2.p, c.send_owner_u.p, c.send_owner.p);
     LAUNCH(h, k_invert_perm, cdiv(ns, 256), 256, ns, h->vals2.p, c.slot_of_u.p);
-    LAUNCH(h, k_cell_starts, 1, 64, NDIR, ns, c.send_dir.p, c.dir_start.p);
+    LAUNCH(h, k_cell_starts, 1, 64, NDIR, ns, c.send_dir.p, c.dir_start.p, 0);
     CUDA_CHECK(cudaMemcpyAsync(dstart, c.dir_start.p, sizeof(dstart), cudaMemcpyDeviceToHost, h->stream));
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
   }
@@ -317,9 +317,9 @@ static void comm_build_ghosts(polb200_handle *h, int n)
   comm_exchange(h, c.sbuf.p, c.rbuf.p, sizeof(double4));
   if (ng) {
     LAUNCH(h, k_ghost_keys, cdiv(ng, 256), 256, ng, c.rbuf.p, g, h->keys.p, h->vals.p);
-    sort_pairs(h, ng, h->keys.p, h->keys2.p, h->vals.p, h->vals2.p, bits_for(g.ncell + 1));
+    sort_pairs(h, ng, h->keys.p, h->keys2.p, h->vals.p, h->vals2.p, bits_for(g.ncell + 1) + g.xbits);
     CUDA_CHECK(cudaMemcpyAsync(c.gslot.p, h->vals2.p, (size_t)ng * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
-    LAUNCH(h, k_cell_starts, cdiv(g.ncell + 1, 256), 256, g.ncell, ng, h->keys2.p, h->cg_start.p);
+    LAUNCH(h, k_cell_starts, cdiv(g.ncell + 1, 256), 256, g.ncell, ng, h->keys2.p, h->cg_start.p, g.xbits);
     LAUNCH(h, k_unpack_rec, cdiv(ng, 256), 256, ng, c.gslot.p, c.rbuf.p, h->xq.p + n);
   } else {
     CUDA_CHECK(cudaMemsetAsync(h->cg_start.p, 0, (g.ncell + 2) * sizeof(int), h->stream));

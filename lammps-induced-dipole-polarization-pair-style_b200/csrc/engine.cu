@@ -124,6 +124,7 @@ struct polb200_handle {
   HostStyle style;
   std::string err;
   int device = 0;
+  int num_sms = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[6] = {};
   long launches = 0;
@@ -134,7 +135,8 @@ struct polb200_handle {
   // options
   int sweep_block = BLOCK;
   double bin_div = 4.0;          // neighbor cutoff / cell width
-  int sweep_variant = 20;        // 0: k_sweep<true> (first version), 1/2: k_sweep_list2 with PF = 1/2
+  int xsort_bits = 10;           // resolution of the x position inside a cell in the sort key (0: cell order only)
+  int sweep_variant = 41;        // 41: TMA-fed pair-group sweep (Jacobi), 31: pair groups with register prefetch, 20: per-atom cached sweep, 6: matrix-free, 0: first version
   bool use_tight = true;         // per-step tight list
   bool use_push = true;          // sweep kernel stores new dipoles into their ghost copies itself
   bool time_sweeps = false;     // record CUDA events around every k_sweep launch (bench roofline)
@@ -170,6 +172,13 @@ struct polb200_handle {
   DBuf<unsigned long long> push_off;
   DBuf<double4 *> push_ptr0, push_ptr1;
   bool push_ready = false;
+  // pair groups (two cell-row neighbours per warp) for the Jacobi list sweep
+  DBuf<int> group_first, group_two, gneigh, gcount, tgneigh, tgcount;
+  DBuf<unsigned long long> growstart;
+  DBuf<double4> s12ab;           // per-step radial cache of the group rows: {s1a, s2a, s1b, s2b} per entry
+  int ngroups = 0;
+  unsigned long long gpairs = 0;
+  bool groups_built = false, group_cache_valid = false;
   DBuf<double2> s12;             // per-step radial cache aligned with the tight list
   bool s12_valid = false;
   DBuf<char> cub_tmp;
@@ -259,6 +268,13 @@ static void upload_params(polb200_handle *h)
   h->have_lists = false;
 }
 
+static int bits_for(int n)
+{
+  int b = 1;
+  while ((1l << b) < n) b++;
+  return b;
+}
+
 // Fine cell grid over the box extended by the ghost cutoff.  Cells are cut/bin_div wide (LAMMPS uses
 // cut/2, src/nbin_standard.cpp:93-99; a finer grid gives a tighter candidate set and, because atoms are
 // stored in cell order with x fastest, longer contiguous neighbour runs).  The stencil is a list of
@@ -293,6 +309,7 @@ static void setup_grid(polb200_handle *h)
   }
   if (ncell > (1l << 30)) throw StyleError{POLB200_ERR_UNSUPPORTED, "Too many neighbor bins"};
   g.ncell = (int)ncell;
+  g.xbits = std::max(0, std::min(h->xsort_bits, 31 - bits_for(g.ncell + 1)));
   auto gap = [](int o, double c) { return o > 0 ? (o - 1) * c : (o < 0 ? (o + 1) * c : 0.0); };
   for (int k = -sx[2]; k <= sx[2]; k++)
     for (int j = -sx[1]; j <= sx[1]; j++) {
@@ -327,12 +344,6 @@ static void exclusive_sum(polb200_handle *h, int n, const unsigned long long *in
   h->launches += 2;
 }
 
-static int bits_for(int n)
-{
-  int b = 1;
-  while ((1l << b) < n) b++;
-  return b;
-}
 
 // ---- host <-> device staging of the caller's arrays ----------------------------------------------------
 template <class T>
@@ -400,14 +411,14 @@ static void rebuild(polb200_handle *h, const polb200_atoms *at)
 
   // 1. cell-sort the owned atoms
   h->keys.ensure(n); h->keys2.ensure(n); h->vals.ensure(n); h->vals2.ensure(n);
-  h->flags.ensure(4);
-  CUDA_CHECK(cudaMemsetAsync(h->flags.p, 0, 4 * sizeof(int), h->stream));
+  h->flags.ensure(8);
+  CUDA_CHECK(cudaMemsetAsync(h->flags.p, 0, 8 * sizeof(int), h->stream));
   LAUNCH(h, k_local_keys, cdiv(n, 256), 256, n, h->c_x.p, g, h->keys.p, h->vals.p, h->flags.p);
-  sort_pairs(h, n, h->keys.p, h->keys2.p, h->vals.p, h->vals2.p, bits_for(g.ncell + 1));
+  sort_pairs(h, n, h->keys.p, h->keys2.p, h->vals.p, h->vals2.p, bits_for(g.ncell + 1) + g.xbits);
   h->perm.ensure(n); h->invperm.ensure(n);
   CUDA_CHECK(cudaMemcpyAsync(h->perm.p, h->vals2.p, n * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
   h->cl_start.ensure(g.ncell + 2);
-  LAUNCH(h, k_cell_starts, cdiv(g.ncell + 1, 256), 256, g.ncell, n, h->keys2.p, h->cl_start.p);
+  LAUNCH(h, k_cell_starts, cdiv(g.ncell + 1, 256), 256, g.ncell, n, h->keys2.p, h->cl_start.p, g.xbits);
 
   // capacity guess for ext arrays: grown after the ghost count is known
   h->xq.ensure(n); h->mua.ensure(n); h->mub.ensure(n); h->tm.ensure(n); h->tag.ensure(n);
@@ -442,7 +453,7 @@ static void rebuild(polb200_handle *h, const polb200_atoms *at)
       h->vals.ensure(std::max(n, ng)); h->vals2.ensure(std::max(n, ng));
       LAUNCH(h, k_ghost_fill, cdiv(n, 256), 256, n, h->xq.p, h->box, st.cutneighmax, g, h->rowstart.p,
              h->g_owner_u.p, h->g_shift_u.p, h->keys.p, h->vals.p);
-      sort_pairs(h, ng, h->keys.p, h->keys2.p, h->vals.p, h->vals2.p, bits_for(g.ncell + 1));
+      sort_pairs(h, ng, h->keys.p, h->keys2.p, h->vals.p, h->vals2.p, bits_for(g.ncell + 1) + g.xbits);
     }
     h->push_off.ensure(n + 2);  // the ghost count scan is also the CSR of every owned atom's images
     CUDA_CHECK(cudaMemcpyAsync(h->push_off.p, h->rowstart.p, (size_t)(n + 1) * sizeof(unsigned long long),
@@ -458,7 +469,7 @@ static void rebuild(polb200_handle *h, const polb200_atoms *at)
     if (ng > 0) {
       LAUNCH(h, k_ghost_gather, cdiv(ng, 256), 256, ng, n, h->vals2.p, h->g_owner_u.p, h->g_shift_u.p, h->box,
              h->xq.p, h->mua.p, h->tm.p, h->tag.p, h->g_owner.p, h->g_shift.p);
-      LAUNCH(h, k_cell_starts, cdiv(g.ncell + 1, 256), 256, g.ncell, ng, h->keys2.p, h->cg_start.p);
+      LAUNCH(h, k_cell_starts, cdiv(g.ncell + 1, 256), 256, g.ncell, ng, h->keys2.p, h->cg_start.p, g.xbits);
     } else {
       CUDA_CHECK(cudaMemsetAsync(h->cg_start.p, 0, (g.ncell + 2) * sizeof(int), h->stream));
     }
@@ -492,6 +503,37 @@ static void rebuild(polb200_handle *h, const polb200_atoms *at)
   LAUNCH(h, k_neigh_build<true>, cdiv(n, WARPS_PER_BLOCK), BLOCK, n, h->P, h->xq.p, h->tm.p, h->tag.p,
          h->cl_start.p, h->cg_start.p, h->nstencil, h->stencil.p, d_nspecial, d_special, h->maxspecial,
          h->cnt.p, h->rowstart.p, h->neigh.p);
+
+  // 4. pair groups for the Jacobi list sweep (union skin list of two cell-row neighbours per warp)
+  h->groups_built = false;
+  if (h->sweep_variant >= 30 && st.polar_cutoff > 0.0 && !st.zodid && !st.polar_gs && !st.polar_gs_ranked) {
+    const int nrows = g.nc[1] * g.nc[2];
+    h->cnt.ensure(std::max(n, nrows) + 1); h->growstart.ensure((size_t)n + nrows + 2);
+    LAUNCH(h, k_group_count, cdiv(nrows, 256), 256, nrows, g.nc[0], h->cl_start.p, h->cnt.p);
+    CUDA_CHECK(cudaMemsetAsync(h->cnt.p + nrows, 0, sizeof(unsigned long long), h->stream));
+    exclusive_sum(h, nrows + 1, h->cnt.p, h->growstart.p);
+    unsigned long long ngr = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&ngr, h->growstart.p + nrows, sizeof(ngr), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    h->ngroups = (int)ngr;
+    h->group_first.ensure(ngr + 1); h->group_two.ensure(ngr + 1);
+    LAUNCH(h, k_group_fill, cdiv(nrows, 256), 256, nrows, g.nc[0], h->cl_start.p, h->growstart.p, h->group_first.p, h->group_two.p);
+    const int ngb = cdiv(h->ngroups, WARPS_PER_BLOCK);
+    h->cnt.ensure(ngr + 1);
+    LAUNCH(h, k_group_build<false>, ngb, BLOCK, h->ngroups, n, h->P, h->xq.p, h->tm.p, h->group_first.p, h->group_two.p,
+           h->cl_start.p, h->cg_start.p, h->nstencil, h->stencil.p, h->cnt.p, (const unsigned long long *)nullptr, (int *)nullptr, (int *)nullptr);
+    CUDA_CHECK(cudaMemsetAsync(h->cnt.p + ngr, 0, sizeof(unsigned long long), h->stream));
+    exclusive_sum(h, (int)ngr + 1, h->cnt.p, h->growstart.p);
+    unsigned long long gp = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&gp, h->growstart.p + ngr, sizeof(gp), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    h->gpairs = gp;
+    h->gneigh.ensure(gp + 32);
+    h->gcount.ensure(ngr + 1);
+    LAUNCH(h, k_group_build<true>, ngb, BLOCK, h->ngroups, n, h->P, h->xq.p, h->tm.p, h->group_first.p, h->group_two.p,
+           h->cl_start.p, h->cg_start.p, h->nstencil, h->stencil.p, h->cnt.p, h->growstart.p, h->gneigh.p, h->gcount.p);
+    h->groups_built = true;
+  }
 
   // remember positions for the displacement trigger (Neighbor::build: xhold, src/neighbor.cpp:2032-2044)
   h->c_xhold.ensure((size_t)3 * n);
@@ -606,6 +648,76 @@ static int launch_list_sweep(polb200_handle *h, int beg, int end, const int *ord
 {
   const bool damp = P.pc.damping_exponential != 0;
   h->partial.ensure((size_t)(end - beg) + 64);
+  if (h->groups_built && order == nullptr && beg == 0 && end == h->nloc) {
+    // whole-system Jacobi sweep: two cell-row neighbours per warp
+    if (!h->group_cache_valid) {
+      bool fits = true;
+      if (h->s12ab.cap < h->gneigh.cap) {  // 32 B per group entry: only while it fits comfortably in free HBM
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        fits = (double)h->gneigh.cap * 36.0 < 0.6 * (double)free_b;
+      }
+      if (!fits) h->groups_built = false;
+      else {
+        h->tgneigh.ensure(h->gneigh.cap); h->tgcount.ensure(h->ngroups + 1); h->s12ab.ensure(h->gneigh.cap);
+        const int ngb = cdiv(h->ngroups, WARPS_PER_BLOCK);
+        if (damp) LAUNCH(h, (k_group_cache<true>), ngb, BLOCK, h->ngroups, P, h->group_first.p, h->group_two.p, h->growstart.p, h->gcount.p, h->gneigh.p, h->xq.p, h->tgneigh.p, h->tgcount.p, h->s12ab.p);
+        else LAUNCH(h, (k_group_cache<false>), ngb, BLOCK, h->ngroups, P, h->group_first.p, h->group_two.p, h->growstart.p, h->gcount.p, h->gneigh.p, h->xq.p, h->tgneigh.p, h->tgcount.p, h->s12ab.p);
+        h->group_cache_valid = true;
+      }
+    }
+    if (h->groups_built) {
+      const PushArgs Q = push ? push_args(h, nxt) : PushArgs{};
+#define GOG4(GW, MB, DP, CH, PU) \
+  LAUNCH(h, (k_sweep_group<GW, MB, CH, PU, DP>), cdiv(h->ngroups, GW), GW * 32, h->ngroups, h->group_first.p, h->group_two.p, h->growstart.p, \
+         h->tgneigh.p, h->tgcount.p, h->s12ab.p, h->xq.p, cur, h->ef.p, nxt, h->partial.p, Q)
+#define GOG(GW, MB, DP) \
+  do { if (push) { if (change) GOG4(GW, MB, DP, true, true); else GOG4(GW, MB, DP, false, true); } \
+       else { if (change) GOG4(GW, MB, DP, true, false); else GOG4(GW, MB, DP, false, false); } } while (0)
+#define GOT4(GW, NS, CK, CH, PU)                                                                                        \
+  do {                                                                                                                  \
+    auto kern = k_sweep_group_tma<GW, NS, CK, CH, PU>;                                                                  \
+    const int smem = GW * NS * CK * 36 + GW * NS * 8;                                                                   \
+    static bool attr_set = false;                                                                                       \
+    if (!attr_set) {                                                                                                    \
+      CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                        \
+      CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));                      \
+      attr_set = true;                                                                                                  \
+    }                                                                                                                   \
+    int per_sm = 0;                                                                                                     \
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GW * 32, smem));                            \
+    const int grid = std::min(cdiv(h->ngroups, GW), std::max(per_sm, 1) * h->num_sms);                                  \
+    kern<<<grid, GW * 32, smem, h->stream>>>(h->ngroups, h->group_first.p, h->group_two.p, h->growstart.p, h->tgneigh.p, \
+                                             h->tgcount.p, h->s12ab.p, h->xq.p, cur, h->ef.p, nxt, h->partial.p, Q, h->flags.p + 4);     \
+    h->launches++;                                                                                                      \
+    CUDA_CHECK(cudaGetLastError());                                                                                     \
+  } while (0)
+#define GOT(GW, NS, CK) \
+  do { if (push) { if (change) GOT4(GW, NS, CK, true, true); else GOT4(GW, NS, CK, false, true); } \
+       else { if (change) GOT4(GW, NS, CK, true, false); else GOT4(GW, NS, CK, false, false); } } while (0)
+      switch (h->sweep_variant) {
+        case 46: GOT(4, 4, 32); break;
+        case 47: GOT(2, 3, 64); break;
+        case 40: GOT(4, 4, 64); break;
+        case 41: GOT(4, 3, 64); break;
+        case 42: GOT(4, 6, 64); break;
+        case 43: GOT(4, 3, 128); break;
+        case 44: GOT(8, 4, 64); break;
+        case 45: GOT(4, 8, 32); break;
+        case 31: GOG(4, 5, true); break;
+        case 32: GOG(4, 6, true); break;
+        case 33: GOG(8, 2, true); break;
+        case 34: GOG(4, 4, true); break;
+        case 35: GOG(8, 3, false); break;
+        default: GOG(4, 6, false); break;
+      }
+#undef GOG4
+#undef GOT4
+#undef GOT
+#undef GOG
+      return end - beg;
+    }
+  }
   if (h->sweep_variant >= 20 && !h->s12_valid && h->s12.cap < h->neigh.cap) {
     // the radial cache costs 16 B per list entry: keep it only while it fits comfortably in free HBM
     size_t free_b = 0, total_b = 0;
@@ -724,6 +836,7 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
   ListRows L{h->rowstart.p, h->neigh.p, nullptr};
   AllPairRows A{n, h->perm.p};
   h->s12_valid = false;
+  h->group_cache_valid = false;
   if (h->use_tight) {
     // every pair kernel of this step only needs partners within the largest interaction cutoff
     double reach = st.cutforce > st.cut_coul ? st.cutforce : st.cut_coul;
@@ -977,8 +1090,11 @@ int polb200_create(polb200_t **out, int device)
   h->device = device;
   if (const char *v = getenv("POLB200_SWEEP_VARIANT")) h->sweep_variant = atoi(v);  // experiments only
   if (const char *v = getenv("POLB200_USE_PUSH")) h->use_push = atoi(v) != 0;
+  if (const char *v = getenv("POLB200_XSORT_BITS")) h->xsort_bits = atoi(v);
+  if (const char *v = getenv("POLB200_BIN_DIV")) h->bin_div = atof(v);
   int rc = guarded(h, [&] {
     CUDA_CHECK(cudaSetDevice(device));
+    CUDA_CHECK(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
     CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     for (auto &e : h->ev) CUDA_CHECK(cudaEventCreate(&e));
   });
@@ -1024,6 +1140,8 @@ void polb200_destroy(polb200_t *h)
                   &h->s_special, &h->neigh, &h->tneigh, &h->tcount, &h->flags, &h->ranked, &h->ranked_in})
     b->release();
   for (auto *b : {&h->xq, &h->mua, &h->mub, &h->ef, &h->f_pair, &h->f_pol}) b->release();
+  h->group_first.release(); h->group_two.release(); h->gneigh.release(); h->gcount.release(); h->tgneigh.release(); h->tgcount.release();
+  h->growstart.release(); h->s12ab.release();
   h->s12.release(); h->push_off.release(); h->push_ptr0.release(); h->push_ptr1.release();
   h->tm.release(); h->cnt.release(); h->rowstart.release(); h->cub_tmp.release(); h->rmin_bits.release();
   h->h_stage.release(); h->h_scal.release(); h->h_int.release();
@@ -1165,6 +1283,7 @@ int polb200_set_option(polb200_t *h, const char *name, double value)
   if (!h || !name) return POLB200_ERR_ARG;
   if (!strcmp(name, "sweep_variant")) {
     h->sweep_variant = (int)value;
+    h->have_lists = false;  // the pair groups are built with the neighbor structures
     return POLB200_OK;
   }
   if (!strcmp(name, "bin_div")) {
@@ -1176,6 +1295,11 @@ int polb200_set_option(polb200_t *h, const char *name, double value)
   if (!strcmp(name, "p2p_push")) {  // 0: NCCL halo per sweep; 1: fused sweep + peer-memory push (takes effect at the next rebuild)
     h->comm.want_push = value != 0.0;
     h->comm.mapped_ptr[0] = nullptr;
+    h->have_lists = false;
+    return POLB200_OK;
+  }
+  if (!strcmp(name, "xsort_bits")) {
+    h->xsort_bits = (int)value;
     h->have_lists = false;
     return POLB200_OK;
   }
@@ -1253,7 +1377,8 @@ long polb200_debug_fetch(polb200_t *h, const char *name, void *dst, long capacit
                      (double)h->comm.push.enabled, (double)h->comm.nranks};
       memcpy(dst, v, 40);
       result = 5;
-    } else if (!strcmp(name, "tag")) fetch(h->tag.p, (size_t)(n + ng) * 4, n + ng);
+    } else if (!strcmp(name, "flags")) fetch(h->flags.p, 32, 8);
+    else if (!strcmp(name, "tag")) fetch(h->tag.p, (size_t)(n + ng) * 4, n + ng);
     else if (!strcmp(name, "perm")) fetch(h->perm.p, (size_t)n * 4, n);
     else if (!strcmp(name, "ghost_owner")) fetch(h->g_owner.p, (size_t)ng * 4, ng);   // sorted owned index
     else if (!strcmp(name, "ghost_shift")) fetch(h->g_shift.p, (size_t)ng * 4, ng);   // packed code

@@ -29,6 +29,7 @@ struct Grid {
   double inv[3];    // 1/cell size
   int nc[3];        // cells per dimension
   int ncell;
+  int xbits;        // sort key = cell << xbits | position along x inside the cell (atoms of a cell row end up x-sorted)
 };
 
 struct DevParams {
@@ -137,6 +138,19 @@ __device__ __forceinline__ int cell_of(const Grid &g, double x, double y, double
   return (cz * g.nc[1] + cy) * g.nc[0] + cx;
 }
 
+// sort key: cell index (major) and the quantised x position inside the cell (minor).  Atoms of one (y,z)
+// cell row are therefore stored in ascending x across the whole row, and the partners of an atom inside
+// that row -- an x interval -- are one contiguous index run: neighbour gathers of a warp touch consecutive
+// 32-byte records (fewer L1 wavefronts per load instruction).
+__device__ __forceinline__ int sort_key_of(const Grid &g, double x, double y, double z)
+{
+  int cx, cy, cz;
+  const int cell = cell_of(g, x, y, z, cx, cy, cz);
+  double fx = (x - g.lo[0]) * g.inv[0] - (double)cx;
+  fx = fmin(fmax(fx, 0.0), 0.999999);
+  return (cell << g.xbits) | (int)(fx * (double)(1 << g.xbits));
+}
+
 // block-level fixed-order reduction of NV per-warp values; lane 0 of each warp holds its value.
 // Thread 0 returns with the block total in out[0..NV).
 template <int NV>
@@ -169,8 +183,7 @@ __global__ void k_local_keys(int n, const double *__restrict__ x, Grid g, int *_
     atomicOr(errflag, 1);
     a = b = c = 0.0;
   }
-  int cx, cy, cz;
-  key[i] = cell_of(g, a, b, c, cx, cy, cz);
+  key[i] = sort_key_of(g, a, b, c);
   iota[i] = i;
 }
 
@@ -260,10 +273,9 @@ __global__ void k_ghost_fill(int n, const double4 *__restrict__ xq, Box box, dou
         double gx = sh[kx] ? v.x + sh[kx] * box.prd[0] : v.x;
         double gy = sh[ky] ? v.y + sh[ky] * box.prd[1] : v.y;
         double gz = sh[kz] ? v.z + sh[kz] * box.prd[2] : v.z;
-        int cx, cy, cz;
         g_owner[o] = s;
         g_shift[o] = (sh[kx] + 1) | ((sh[ky] + 1) << 2) | ((sh[kz] + 1) << 4);
-        g_key[o] = cell_of(g, gx, gy, gz, cx, cy, cz);
+        g_key[o] = sort_key_of(g, gx, gy, gz);
         g_iota[o] = (int)o;
         o++;
       }
@@ -313,14 +325,14 @@ __global__ void k_ghost_refresh(int nghost, int nloc, const int *__restrict__ ow
 }
 
 // first index of every cell in a key-sorted array (keys ascending): lower_bound per cell
-__global__ void k_cell_starts(int ncell, int n, const int *__restrict__ sorted_keys, int *__restrict__ start)
+__global__ void k_cell_starts(int ncell, int n, const int *__restrict__ sorted_keys, int *__restrict__ start, int shift)
 {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c > ncell) return;
   int lo = 0, hi = n;
   while (lo < hi) {
     int mid = (lo + hi) >> 1;
-    if (sorted_keys[mid] < c) lo = mid + 1;
+    if ((sorted_keys[mid] >> shift) < c) lo = mid + 1;
     else hi = mid;
   }
   start[c] = lo;
@@ -1359,8 +1371,7 @@ __global__ void k_ghost_keys(int ng, const double4 *__restrict__ rbuf, Grid g, i
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= ng) return;
   const double4 v = rbuf[t];
-  int cx, cy, cz;
-  key[t] = cell_of(g, v.x, v.y, v.z, cx, cy, cz);
+  key[t] = sort_key_of(g, v.x, v.y, v.z);
   iota[t] = t;
 }
 
@@ -1463,6 +1474,407 @@ __global__ void k_signal_wait(int rank, int nranks, unsigned long long epoch, Pe
     double s = 0.0;
     for (int k = 0; k < nranks; k++) s += __longlong_as_double((long long)ld_acquire_sys(mine + bank + k));
     *change = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// stage 3, pair-group form of the Jacobi list sweep
+// ---------------------------------------------------------------------------------------------------
+// ncu shows the per-atom sweep bound by the L1 data pipe (l1tex__data_pipe_lsu_wavefronts 85 % of peak):
+// every pair costs two divergent 32-byte gathers (x_j, mu_j), ~17 wavefronts each per warp trip.  Two
+// atoms that are neighbours in the cell-sorted order (same (y,z) cell row, adjacent in x) share ~85 % of
+// their partners, so ONE warp serves both: each gathered record feeds two pair evaluations, halving the
+// wavefronts per pair.  A group row is the union of the two atoms' partner sets; the per-step cache holds
+// the radial scalars of both members for every entry (zeros where an entry belongs to one member only).
+
+// groups of one (y,z) cell row: atoms [rs,re) of the row pair up as (rs,rs+1),(rs+2,rs+3),...
+__global__ void k_group_count(int nrows, int ncx, const int *__restrict__ cl_start, unsigned long long *__restrict__ cnt)
+{
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrows) return;
+  const int c = cl_start[(size_t)(r + 1) * ncx] - cl_start[(size_t)r * ncx];
+  cnt[r] = (unsigned long long)((c + 1) / 2);
+}
+
+// first atom of every group; the second member is first+1 when group_two is set
+__global__ void k_group_fill(int nrows, int ncx, const int *__restrict__ cl_start, const unsigned long long *__restrict__ off,
+                             int *__restrict__ group_first, int *__restrict__ group_two)
+{
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrows) return;
+  const int rs = cl_start[(size_t)r * ncx], re = cl_start[(size_t)(r + 1) * ncx];
+  unsigned long long g = off[r];
+  for (int a = rs; a < re; a += 2, g++) {
+    group_first[g] = a;
+    group_two[g] = a + 1 < re ? 1 : 0;
+  }
+}
+
+// union skin list of every group straight from the cells (same acceptance test as k_neigh_build, for either
+// member).  The two members sit in the same cell row, so they share the stencil rows; only the x range widens.
+template <bool FILL>
+__global__ void __launch_bounds__(BLOCK)
+k_group_build(int ngroups, int nloc, DevParams P, const double4 *__restrict__ xq, const int2 *__restrict__ tm,
+              const int *__restrict__ group_first, const int *__restrict__ group_two,
+              const int *__restrict__ cl_start, const int *__restrict__ cg_start, int nstencil,
+              const int *__restrict__ stencil, unsigned long long *__restrict__ count,
+              const unsigned long long *__restrict__ rowstart, int *__restrict__ neigh, int *__restrict__ rowcount)
+{
+  const int lane = threadIdx.x & 31;
+  const int g = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (g >= ngroups) return;
+  const int a = group_first[g];
+  const bool two = group_two[g] != 0;
+  const int b = two ? a + 1 : a;
+  const double4 xa = xq[a], xb = xq[b];
+  const int ta = tm[a].x, tb = tm[b].x;
+  const int n1 = P.pc.ntypes + 1;
+  int cxa, cxb, cy, cz, t0, t1;
+  cell_of(P.grid, xa.x, xa.y, xa.z, cxa, cy, cz);
+  cell_of(P.grid, xb.x, xb.y, xb.z, cxb, t0, t1);
+  unsigned long long n = 0;
+  const unsigned long long base = FILL ? rowstart[g] : 0ull;
+  for (int k = 0; k < nstencil; k++) {
+    const int code = stencil[k];
+    const int oy = cy + ((code & 63) - 16), oz = cz + (((code >> 6) & 63) - 16), xext = code >> 12;
+    if (oy < 0 || oz < 0 || oy >= P.grid.nc[1] || oz >= P.grid.nc[2]) continue;
+    const int xlo = max(min(cxa, cxb) - xext, 0), xhi = min(max(cxa, cxb) + xext, P.grid.nc[0] - 1);
+    const int rowbase = (oz * P.grid.nc[1] + oy) * P.grid.nc[0];
+    for (int part = 0; part < 2; part++) {
+      const int beg = part ? nloc + cg_start[rowbase + xlo] : cl_start[rowbase + xlo];
+      const int end = part ? nloc + cg_start[rowbase + xhi + 1] : cl_start[rowbase + xhi + 1];
+      for (int j0 = beg; j0 < end; j0 += 32) {
+        const int j = j0 + lane;
+        bool ok = false;
+        if (j < end) {
+          const double4 xj = xq[j];
+          const int tj = tm[j].x;
+          const double ra = rsq_nofma(xa.x - xj.x, xa.y - xj.y, xa.z - xj.z);
+          const double rb = rsq_nofma(xb.x - xj.x, xb.y - xj.y, xb.z - xj.z);
+          ok = (j != a && ra <= P.cutneighsq[ta * n1 + tj]) || (two && j != b && rb <= P.cutneighsq[tb * n1 + tj]);
+        }
+        const unsigned m = __ballot_sync(FULL, ok);
+        if (FILL && ok) neigh[base + n + __popc(m & ((1u << lane) - 1))] = j;
+        n += __popc(m);
+      }
+    }
+  }
+  // rows start on 16-byte boundaries of the index array (bulk copies): the offsets are padded, the true
+  // length of the row is kept in rowcount
+  if (!FILL && lane == 0) count[g] = (n + 3ull) & ~3ull;
+  if (FILL && lane == 0) rowcount[g] = (int)n;
+}
+
+// per step: entries inside the dipole cutoff of either member at the current positions, compacted, with the
+// radial scalars {s1a, s2a, s1b, s2b} of both members (zero for a member the entry does not belong to)
+template <bool DAMP>
+__global__ void __launch_bounds__(BLOCK)
+k_group_cache(int ngroups, DevParams P, const int *__restrict__ group_first, const int *__restrict__ group_two,
+              const unsigned long long *__restrict__ rowstart, const int *__restrict__ rowcount,
+              const int *__restrict__ neigh, const double4 *__restrict__ xq, int *__restrict__ tneigh,
+              int *__restrict__ tcount, double4 *__restrict__ s12ab)
+{
+  const int lane = threadIdx.x & 31;
+  const int g = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (g >= ngroups) return;
+  const int a = group_first[g];
+  const bool two = group_two[g] != 0;
+  const int b = two ? a + 1 : a;
+  const double4 xa = xq[a], xb = xq[b];
+  const double cutsq = P.pc.polar_cutsq;
+  const unsigned long long beg = rowstart[g], end = beg + (unsigned long long)rowcount[g];
+  int n = 0;
+  for (unsigned long long k0 = beg; k0 < end; k0 += 32) {
+    const unsigned long long k = k0 + lane;
+    bool ok = false;
+    int j = 0;
+    double4 sc = make_double4(0, 0, 0, 0);
+    if (k < end) {
+      j = neigh[k];
+      const double4 xj = ld4(xq + j);
+      double dx = xa.x - xj.x, dy = xa.y - xj.y, dz = xa.z - xj.z;
+      const double ra = dx * dx + dy * dy + dz * dz;
+      dx = xb.x - xj.x, dy = xb.y - xj.y, dz = xb.z - xj.z;
+      const double rb = dx * dx + dy * dy + dz * dz;
+      const bool ina = j != a && ra < cutsq, inb = two && j != b && rb < cutsq;
+      ok = ina || inb;
+      if (ina) radial_scalars<DAMP>(P.pc, ra, sc.x, sc.y);
+      if (inb) radial_scalars<DAMP>(P.pc, rb, sc.z, sc.w);
+    }
+    const unsigned m = __ballot_sync(FULL, ok);
+    if (ok) {
+      const unsigned long long o = beg + n + __popc(m & ((1u << lane) - 1));
+      tneigh[o] = j;
+      s12ab[o] = sc;
+    }
+    n += __popc(m);
+  }
+  if (lane == 0) tcount[g] = n;
+}
+
+// one Jacobi dipole iteration, one warp per group of two atoms (rows in cell-sorted order only)
+template <int WPB, int MINB, bool CHANGE, bool PUSH, bool DEEP>
+__global__ void __launch_bounds__(WPB * 32, MINB)
+k_sweep_group(int ngroups, const int *__restrict__ group_first, const int *__restrict__ group_two,
+              const unsigned long long *__restrict__ rowstart, const int *__restrict__ tneigh,
+              const int *__restrict__ tcount, const double4 *__restrict__ s12ab, const double4 *__restrict__ xq,
+              const double4 *__restrict__ mu_in, const double4 *__restrict__ ef, double4 *__restrict__ mu_out,
+              double *__restrict__ row_change, PushArgs Q)
+{
+  const int lane = threadIdx.x & 31;
+  const int g = blockIdx.x * WPB + (threadIdx.x >> 5);
+  if (g >= ngroups) return;
+  const int a = group_first[g];
+  const bool two = group_two[g] != 0;
+  const int b = two ? a + 1 : a;
+  const double4 xa = xq[a], xb = xq[b];
+  double4 *push_a = nullptr, *push_b = nullptr;
+  if (PUSH) {
+    push_a = push_prefetch(Q, a, lane);
+    if (two) push_b = push_prefetch(Q, b, lane);
+  }
+  double eax = 0, eay = 0, eaz = 0, ebx = 0, eby = 0, ebz = 0;
+  {
+    const unsigned long long beg = rowstart[g];
+    const int *__restrict__ row = tneigh + beg;
+    const double4 *__restrict__ rs = s12ab + beg;
+    auto ldcs4 = [&](int k) {
+      double4 v;
+      asm volatile("ld.global.cs.v4.b64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(rs + k));
+      return v;
+    };
+    const int cnt = tcount[g];
+    int jA = lane < cnt ? __ldcs(row + lane) : -1;
+    int jB = lane + 32 < cnt ? __ldcs(row + lane + 32) : -1;
+    int jC = lane + 64 < cnt ? __ldcs(row + lane + 64) : -1;
+    double4 cA = lane < cnt ? ldcs4(lane) : make_double4(0, 0, 0, 0);
+    double4 cB = (DEEP && lane + 32 < cnt) ? ldcs4(lane + 32) : make_double4(0, 0, 0, 0);
+    for (int k = lane; k < cnt; k += 32) {
+      const int jD = k + 96 < cnt ? __ldcs(row + k + 96) : -1;
+      // cache scalars DEEP ? two : one trip(s) ahead: more bytes of the HBM stream in flight per warp
+      double4 cN;
+      if (DEEP) cN = k + 64 < cnt ? ldcs4(k + 64) : make_double4(0, 0, 0, 0);
+      else cN = k + 32 < cnt ? ldcs4(k + 32) : make_double4(0, 0, 0, 0);
+      const double4 xj = ld4(xq + jA);
+      const double4 mj = ld4(mu_in + jA);
+      {
+        const double dx = xa.x - xj.x, dy = xa.y - xj.y, dz = xa.z - xj.z;
+        const double t = cA.y * (dx * mj.x + dy * mj.y + dz * mj.z);
+        eax -= fma(t, dx, cA.x * mj.x);
+        eay -= fma(t, dy, cA.x * mj.y);
+        eaz -= fma(t, dz, cA.x * mj.z);
+      }
+      {
+        const double dx = xb.x - xj.x, dy = xb.y - xj.y, dz = xb.z - xj.z;
+        const double t = cA.w * (dx * mj.x + dy * mj.y + dz * mj.z);
+        ebx -= fma(t, dx, cA.z * mj.x);
+        eby -= fma(t, dy, cA.z * mj.y);
+        ebz -= fma(t, dz, cA.z * mj.z);
+      }
+      jA = jB;
+      jB = jC;
+      jC = jD;
+      if (DEEP) {
+        cA = cB;
+        cB = cN;
+      } else cA = cN;
+    }
+    eax = warp_sum(eax); eay = warp_sum(eay); eaz = warp_sum(eaz);
+    ebx = warp_sum(ebx); eby = warp_sum(eby); ebz = warp_sum(ebz);
+  }
+  double nax = 0, nay = 0, naz = 0, nbx = 0, nby = 0, nbz = 0, ala = 0, alb = 0;
+  if (lane == 0) {
+    const double4 ma = mu_in[a], e = ef[a];
+    ala = ma.w;
+    nax = ma.w * (e.x + eax), nay = ma.w * (e.y + eay), naz = ma.w * (e.z + eaz);
+    mu_out[a] = make_double4(nax, nay, naz, ma.w);
+    if (CHANGE) row_change[a] = (nax - ma.x) * (nax - ma.x) + (nay - ma.y) * (nay - ma.y) + (naz - ma.z) * (naz - ma.z);
+    if (two) {
+      const double4 mb = mu_in[b], eb = ef[b];
+      alb = mb.w;
+      nbx = mb.w * (eb.x + ebx), nby = mb.w * (eb.y + eby), nbz = mb.w * (eb.z + ebz);
+      mu_out[b] = make_double4(nbx, nby, nbz, mb.w);
+      if (CHANGE) row_change[b] = (nbx - mb.x) * (nbx - mb.x) + (nby - mb.y) * (nby - mb.y) + (nbz - mb.z) * (nbz - mb.z);
+    }
+  }
+  if (PUSH) {
+    ala = __shfl_sync(FULL, ala, 0);
+    push_row(push_a, nax, nay, naz, ala);
+    if (two) {
+      alb = __shfl_sync(FULL, alb, 0);
+      push_row(push_b, nbx, nby, nbz, alb);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// TMA-fed pair-group sweep
+// ---------------------------------------------------------------------------------------------------
+// With the gathers halved by the pair groups, ncu shows nothing saturated (HBM 52 %, L1 data pipe 53 %) and
+// 86 % long-scoreboard stalls: the sweep is limited by the bytes of the HBM stream (neighbour indices +
+// cached radial scalars, 36 B per entry) that register prefetching can keep in flight (~30 KB per SM against
+// the ~60 KB the latency-bandwidth product asks for).  Here each warp streams its row through a ring of
+// shared-memory stages filled by 1-D bulk async copies (cp.async.bulk, the TMA engine) that complete on
+// mbarriers: up to NSTAGE*CHUNK*36 B per warp are in flight without costing a single register, and the
+// indices of a whole chunk are available at once, so the gathers of all its trips are issued back to back.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+template <int WPB, int NSTAGE, int CHUNK, bool CHANGE, bool PUSH>
+__global__ void __launch_bounds__(WPB * 32)
+k_sweep_group_tma(int ngroups, const int *__restrict__ group_first, const int *__restrict__ group_two,
+                  const unsigned long long *__restrict__ rowstart, const int *__restrict__ tneigh,
+                  const int *__restrict__ tcount, const double4 *__restrict__ s12ab, const double4 *__restrict__ xq,
+                  const double4 *__restrict__ mu_in, const double4 *__restrict__ ef, double4 *__restrict__ mu_out,
+                  double *__restrict__ row_change, PushArgs Q, int *dbg)
+{
+  // stage layout: CHUNK x 32 B scalars {s1a,s2a,s1b,s2b}, then CHUNK x 4 B indices.  (Splitting the two members
+  // into separate 16-byte streams makes the LDS conflict free but needs a third bulk copy per chunk: measured slower.)
+  constexpr int STAGE_BYTES = CHUNK * 36;
+  constexpr int TRIPS = CHUNK / 32;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char *ring = smem + (size_t)warp * NSTAGE * STAGE_BYTES;
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + (size_t)WPB * NSTAGE * STAGE_BYTES) + warp * NSTAGE;
+  if (lane == 0) {
+#pragma unroll
+    for (int st = 0; st < NSTAGE; st++) mbar_init(bars + st, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+  unsigned cc = 0;  // chunks consumed by this warp so far: stage = cc % NSTAGE, parity = (cc / NSTAGE) & 1
+  const int nwarps = gridDim.x * WPB;
+  for (int g = blockIdx.x * WPB + warp; g < ngroups; g += nwarps) {
+    const int a = group_first[g];
+    const bool two = group_two[g] != 0;
+    const int b = two ? a + 1 : a;
+    const unsigned long long beg = rowstart[g];
+    const int cnt = tcount[g];
+    const int nchunks = (cnt + CHUNK - 1) / CHUNK;
+    const int *__restrict__ row = tneigh + beg;
+    const double4 *__restrict__ rs = s12ab + beg;
+    auto issue = [&](int c, unsigned slot) {  // lane 0: chunk c of this row into ring slot `slot`
+      const int e = min(CHUNK, cnt - c * CHUNK);
+      const unsigned e4 = (unsigned)((e + 3) & ~3);  // rows are padded to multiples of 4 entries (16-byte copies)
+      unsigned char *dst = ring + (size_t)slot * STAGE_BYTES;
+      mbar_expect_tx(bars + slot, e4 * 36u);
+      bulk_g2s(dst, rs + (size_t)c * CHUNK, e4 * 32u, bars + slot);
+      bulk_g2s(dst + CHUNK * 32, row + (size_t)c * CHUNK, e4 * 4u, bars + slot);
+    };
+    if (lane == 0) {
+      const int pre = min(NSTAGE, nchunks);
+      for (int c = 0; c < pre; c++) issue(c, (cc + c) % NSTAGE);
+    }
+    const double4 xa = xq[a], xb = xq[b];
+    double4 *push_a = nullptr, *push_b = nullptr;
+    if (PUSH) {
+      push_a = push_prefetch(Q, a, lane);
+      if (two) push_b = push_prefetch(Q, b, lane);
+    }
+    double eax = 0, eay = 0, eaz = 0, ebx = 0, eby = 0, ebz = 0;
+    for (int c = 0; c < nchunks; c++, cc++) {
+      const unsigned slot = cc % NSTAGE;
+      mbar_wait(bars + slot, (cc / NSTAGE) & 1u);
+      const double4 *sc_s = reinterpret_cast<const double4 *>(ring + (size_t)slot * STAGE_BYTES);
+      const int *ix_s = reinterpret_cast<const int *>(ring + (size_t)slot * STAGE_BYTES + CHUNK * 32);
+      int j[TRIPS];
+      double4 sc[TRIPS], xj[TRIPS], mj[TRIPS];
+#pragma unroll
+      for (int t = 0; t < TRIPS; t++) {
+        const bool live = c * CHUNK + t * 32 + lane < cnt;
+        j[t] = live ? ix_s[t * 32 + lane] : a;
+        sc[t] = live ? sc_s[t * 32 + lane] : make_double4(0, 0, 0, 0);
+#ifdef POLB200_TMA_DEBUG
+        if (live) {
+          const int jj = row[(size_t)c * CHUNK + t * 32 + lane];
+          const double4 ss = rs[(size_t)c * CHUNK + t * 32 + lane];
+          if (jj != j[t]) atomicAdd(dbg, 1);
+          if (ss.x != sc[t].x || ss.y != sc[t].y || ss.z != sc[t].z || ss.w != sc[t].w) atomicAdd(dbg + 1, 1);
+        }
+#endif
+      }
+#pragma unroll
+      for (int t = 0; t < TRIPS; t++) {
+        xj[t] = ld4(xq + j[t]);
+        mj[t] = ld4(mu_in + j[t]);
+      }
+#pragma unroll
+      for (int t = 0; t < TRIPS; t++) {
+        {
+          const double dx = xa.x - xj[t].x, dy = xa.y - xj[t].y, dz = xa.z - xj[t].z;
+          const double q = sc[t].y * (dx * mj[t].x + dy * mj[t].y + dz * mj[t].z);
+          eax -= fma(q, dx, sc[t].x * mj[t].x);
+          eay -= fma(q, dy, sc[t].x * mj[t].y);
+          eaz -= fma(q, dz, sc[t].x * mj[t].z);
+        }
+        {
+          const double dx = xb.x - xj[t].x, dy = xb.y - xj[t].y, dz = xb.z - xj[t].z;
+          const double q = sc[t].w * (dx * mj[t].x + dy * mj[t].y + dz * mj[t].z);
+          ebx -= fma(q, dx, sc[t].z * mj[t].x);
+          eby -= fma(q, dy, sc[t].z * mj[t].y);
+          ebz -= fma(q, dz, sc[t].z * mj[t].z);
+        }
+      }
+      // Refill only after the arithmetic that consumes this slot's scalars: the compiler is free to sink the
+      // shared-memory loads of sc[] down to their first use, behind the long wait for the gathers, and a bulk
+      // copy issued earlier could overwrite the slot before they execute (seen on hardware: wrong dipoles).
+      __syncwarp();
+      if (lane == 0 && c + NSTAGE < nchunks) issue(c + NSTAGE, slot);
+    }
+    eax = warp_sum(eax); eay = warp_sum(eay); eaz = warp_sum(eaz);
+    ebx = warp_sum(ebx); eby = warp_sum(eby); ebz = warp_sum(ebz);
+    double nax = 0, nay = 0, naz = 0, nbx = 0, nby = 0, nbz = 0, ala = 0, alb = 0;
+    if (lane == 0) {
+      const double4 ma = mu_in[a], e = ef[a];
+      ala = ma.w;
+      nax = ma.w * (e.x + eax), nay = ma.w * (e.y + eay), naz = ma.w * (e.z + eaz);
+      mu_out[a] = make_double4(nax, nay, naz, ma.w);
+      if (CHANGE) row_change[a] = (nax - ma.x) * (nax - ma.x) + (nay - ma.y) * (nay - ma.y) + (naz - ma.z) * (naz - ma.z);
+      if (two) {
+        const double4 mb = mu_in[b], eb = ef[b];
+        alb = mb.w;
+        nbx = mb.w * (eb.x + ebx), nby = mb.w * (eb.y + eby), nbz = mb.w * (eb.z + ebz);
+        mu_out[b] = make_double4(nbx, nby, nbz, mb.w);
+        if (CHANGE) row_change[b] = (nbx - mb.x) * (nbx - mb.x) + (nby - mb.y) * (nby - mb.y) + (nbz - mb.z) * (nbz - mb.z);
+      }
+    }
+    if (PUSH) {
+      ala = __shfl_sync(FULL, ala, 0);
+      push_row(push_a, nax, nay, naz, ala);
+      if (two) {
+        alb = __shfl_sync(FULL, alb, 0);
+        push_row(push_b, nbx, nby, nbz, alb);
+      }
+    }
   }
 }
 
