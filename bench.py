@@ -289,6 +289,7 @@ def gpu_arm(args):
     for k in range(args.warmup):
         res = step_dev(k)
     polar_pairs = int(style.debug_fetch("polar_pairs", np.uint64, 1)[0])
+    group_stats = style.debug_fetch("group_stats", np.float64, 4)
     comm_stats = style.debug_fetch("comm_stats", np.float64, 5)
     pb.lib().polb200_set_option(style._h, b"time_sweeps", 1.0)
     style.launch_count(reset=True)
@@ -356,12 +357,16 @@ def gpu_arm(args):
             peaks = json.loads(pk.read_text())
         peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
         sweep_ms = float(sweep[0]) / max(float(sweep[1]), 1.0)
-        # Bytes one launch of the dominant kernel (k_sweep_cached) must move through HBM:
-        # the per-pair streams -- 4 B neighbour index + 16 B cached radial scalars (s1,s2) -- are read exactly
-        # once; the 32-B position and dipole records of the owned+ghost atoms are gathered ~700x each but from
-        # L2/L1, so they count once; plus E_static in and the new dipole out per owned atom.
+        # Bytes one launch of the dominant kernel must move through HBM.  Default kernel
+        # k_sweep_group_tma: one warp per pair group (two cell-row neighbours); per group-row entry it streams,
+        # exactly once, 4 B of neighbour index + 32 B of cached radial scalars {s1a,s2a,s1b,s2b}; the 32-B position
+        # and dipole records of the owned+ghost atoms are gathered hundreds of times each but from L2/L1, so they
+        # count once; plus E_static in and the new dipole out per owned atom.  (Per-atom fallback kernel
+        # k_sweep_cached: 20 B per pair instead.)
         nghost = int(res.nghost)
-        alg_bytes = 20.0 * polar_pairs + 64.0 * (n + nghost) + 64.0 * n
+        grouped = bool(group_stats[3]) and group_stats[1] > 0
+        entries = float(group_stats[1]) if grouped else float(polar_pairs)
+        alg_bytes = (36.0 if grouped else 20.0) * entries + 64.0 * (n + nghost) + 64.0 * n
         achieved = alg_bytes / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else None
         # SURVEY §8d's matrix-free model (every gather charged to HBM): 52 B per pair + 104 B per atom
         survey_bytes = 52.0 * polar_pairs + 104.0 * n
@@ -397,13 +402,17 @@ def gpu_arm(args):
             "device_ms_per_step": dev_ms / args.steps,
             "stage_ms": {"neigh_refresh": stage[0] / args.steps, "pair_field": stage[1] / args.steps,
                          "scf": stage[2] / args.steps, "pol_force": stage[3] / args.steps},
-            "roofline": {"bound": "hbm", "kernel": "k_sweep_cached (one dipole iteration over the neighbor list)",
+            "roofline": {"bound": "hbm", "kernel": ("k_sweep_group_tma" if grouped else "k_sweep_cached") +
+                                                    " (one dipole iteration over the neighbor list)",
                          "achieved": achieved, "peak": peak_gbs,
                          "unit": "GB/s", "frac": achieved / peak_gbs if achieved else None, "traffic": None,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650",
                          "algorithmic_bytes_per_launch": alg_bytes,
-                         "bytes_model": "20 B/pair streamed (index + cached radial scalars) + 64 B per owned+ghost atom "
-                                        "(position and dipole records, read once) + 64 B per owned atom (E_static in, dipole out)",
+                         "bytes_model": ("36 B per group-row entry streamed (index + cached radial scalars of both members)"
+                                         if grouped else "20 B/pair streamed (index + cached radial scalars)") +
+                                        " + 64 B per owned+ghost atom (position and dipole records, read once) + 64 B per "
+                                        "owned atom (E_static in, dipole out)",
+                         "group_row_entries": entries if grouped else None,
                          "pairs_in_cutoff": polar_pairs, "launch_ms": sweep_ms,
                          "gpairs_per_s": polar_pairs / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else None,
                          "survey_8d_model": {"bytes": survey_bytes,

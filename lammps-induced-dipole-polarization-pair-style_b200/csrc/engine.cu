@@ -696,19 +696,10 @@ static int launch_list_sweep(polb200_handle *h, int beg, int end, const int *ord
   do { if (push) { if (change) GOT4(GW, NS, CK, true, true); else GOT4(GW, NS, CK, false, true); } \
        else { if (change) GOT4(GW, NS, CK, true, false); else GOT4(GW, NS, CK, false, false); } } while (0)
       switch (h->sweep_variant) {
-        case 46: GOT(4, 4, 32); break;
-        case 47: GOT(2, 3, 64); break;
         case 40: GOT(4, 4, 64); break;
         case 41: GOT(4, 3, 64); break;
-        case 42: GOT(4, 6, 64); break;
-        case 43: GOT(4, 3, 128); break;
         case 44: GOT(8, 4, 64); break;
-        case 45: GOT(4, 8, 32); break;
         case 31: GOG(4, 5, true); break;
-        case 32: GOG(4, 6, true); break;
-        case 33: GOG(8, 2, true); break;
-        case 34: GOG(4, 4, true); break;
-        case 35: GOG(8, 3, false); break;
         default: GOG(4, 6, false); break;
       }
 #undef GOG4
@@ -897,8 +888,12 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
     bool sequential = false;  // reference-exact Gauss-Seidel (all-pairs mode only)
     if (gs) {
       if (st.gs_chunks > 0) nchunks = st.gs_chunks;
-      else if (list_mode) nchunks = 8;
-      else sequential = true;
+      else if (list_mode) {
+        // default: chunks of ~4096 rows (one wave of warps on 148 SMs); more chunks = closer to true Gauss-Seidel
+        // = fewer iterations (water box: 77 iterations with 8 chunks, 39 with 64, 16 sequential)
+        const long per_brick = comm ? h->comm.nglobal / h->comm.nranks : (long)n;
+        nchunks = (int)std::min(128l, std::max(8l, per_brick / 4096));
+      } else sequential = true;
     }
     // fused sweep + halo: new dipoles go straight into the neighbour bricks' ghost slots (Jacobi sweeps)
     const bool push = h->push_ready && h->use_push && !gs && list_mode && h->sweep_variant != 0 &&
@@ -1377,6 +1372,16 @@ long polb200_debug_fetch(polb200_t *h, const char *name, void *dst, long capacit
                      (double)h->comm.push.enabled, (double)h->comm.nranks};
       memcpy(dst, v, 40);
       result = 5;
+    } else if (!strcmp(name, "group_stats")) {  // {groups, union entries inside the cutoff (last step), skin entries, built}
+      if (capacity_bytes < 32) throw StyleError{POLB200_ERR_ARG, "debug_fetch: buffer too small"};
+      double v[4] = {(double)h->ngroups, 0.0, (double)h->gpairs, h->groups_built ? 1.0 : 0.0};
+      if (h->groups_built && h->group_cache_valid && h->ngroups > 0) {
+        std::vector<int> tc(h->ngroups);
+        CUDA_CHECK(cudaMemcpy(tc.data(), h->tgcount.p, (size_t)h->ngroups * sizeof(int), cudaMemcpyDeviceToHost));
+        for (int c : tc) v[1] += c;
+      }
+      memcpy(dst, v, 32);
+      result = 4;
     } else if (!strcmp(name, "flags")) fetch(h->flags.p, 32, 8);
     else if (!strcmp(name, "tag")) fetch(h->tag.p, (size_t)(n + ng) * 4, n + ng);
     else if (!strcmp(name, "perm")) fetch(h->perm.p, (size_t)n * 4, n);

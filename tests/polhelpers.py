@@ -136,6 +136,43 @@ def lj_charge_fluid(ncell, seed=12345, rho=0.1, jitter=0.3):
     return P.System(x, q, typ, mol, alpha, [0, 0, 0], list(L), 2)
 
 
+def water_box(nmol_side, seed=2, rho=0.1):
+    """BASELINE config 3 generator: rigid 3-site water-like molecules on a jittered cubic
+    lattice with random orientations; r_OH = 0.9572 A, HOH = 104.52 deg; O: q -0.8 e, alpha 0.837 A^3 (type 1),
+    H: q +0.4 e, alpha 0.496 A^3 (type 2); molecule = molecule id (so the static field / charge-dipole terms skip
+    intramolecular pairs while dipole-dipole does not, exactly as the reference); rho atoms/A^3.
+    N = 3 * nmol_side^3 atoms."""
+    rng = np.random.default_rng(seed)
+    nmol = nmol_side ** 3
+    n = 3 * nmol
+    L = (n / rho) ** (1.0 / 3.0)
+    a = L / nmol_side
+    g = np.stack(np.meshgrid(*[np.arange(nmol_side)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    centre = (g + 0.5) * a + rng.uniform(-0.25, 0.25, size=(nmol, 3))
+    # random rotation per molecule (QR of a gaussian matrix, det fixed to +1)
+    q, r = np.linalg.qr(rng.normal(size=(nmol, 3, 3)))
+    q = q * np.sign(np.linalg.det(q))[:, None, None]
+    roh, half = 0.9572, np.deg2rad(104.52) / 2.0
+    local = np.array([[0.0, 0.0, 0.0], [roh * np.sin(half), roh * np.cos(half), 0.0],
+                      [-roh * np.sin(half), roh * np.cos(half), 0.0]])
+    x = centre[:, None, :] + np.einsum("mij,aj->mai", q, local)
+    x = np.mod(x.reshape(-1, 3), L)
+    typ = np.tile(np.array([1, 2, 2], dtype=np.int32), nmol)
+    qq = np.where(typ == 1, -0.8, 0.4)
+    alpha = np.where(typ == 1, 0.837, 0.496)
+    mol = np.repeat(np.arange(1, nmol + 1, dtype=np.int32), 3)
+    return P.System(x, qq, typ, mol, alpha, [0, 0, 0], [L, L, L], 2)
+
+
+def water_style(sysm, cut_lj=2.5, cut_coul=12.0, **kw):
+    g = P.ewald_g(1e-4, sysm.q, cut_coul, sysm.boxlo, sysm.boxhi)
+    st = P.Style(2, cut_lj, cut_coul, g_ewald=g, **kw)
+    st.coeff(1, 1, 0.155, 3.166)
+    st.coeff(2, 2, 0.0, 1.0)
+    st.init()
+    return st
+
+
 def fluid_style(sysm, cut_lj=2.5, cut_coul=12.0, **kw):
     g = P.ewald_g(1e-4, sysm.q, cut_coul, sysm.boxlo, sysm.boxhi)
     st = P.Style(2, cut_lj, cut_coul, g_ewald=g, **kw)

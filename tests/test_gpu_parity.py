@@ -236,3 +236,88 @@ def test_sequential_gs_is_iteration_for_iteration_the_oracle(style, words):
     assert H.rel_err(mu, ref["mu"]) < TOL
     assert abs(res.eng_pol - ref["eng_pol"]) < TOL * abs(ref["eng_pol"])
     assert np.abs(f - ref["f"]).max() < TOL * np.abs(ref["f"]).max()
+
+
+def _fluid_style_on_device(style, sysm, g_ewald, words):
+    style.set_ntypes(2)
+    style.command("pair_style lj/cut/coul/long/polarization 2.5 12.0 " + words)
+    style.command("pair_coeff * * 0.1 3.0")
+    style.init(g_ewald=g_ewald, molecular=0)
+    style.set_box(sysm.boxlo, sysm.boxhi)
+
+
+@pytest.mark.parametrize("drop", [0, 1])
+def test_every_sweep_kernel_gives_the_same_dipoles(drop):
+    """The list-mode sweep exists in several realisations (first version, matrix-free, per-atom radial cache,
+    pair groups with register prefetch, pair groups fed by TMA bulk copies = default).  All evaluate the same
+    pair terms; they must agree to rounding, also with an odd atom count (a one-member group) and in
+    precision mode (same iteration count)."""
+    sysm = H.lj_charge_fluid(10)
+    if drop:  # 3999 atoms: odd rows, single-member groups
+        keep = np.arange(sysm.n) != 1234
+        sysm = P.System(sysm.x[keep], sysm.q[keep], sysm.type[keep], sysm.molecule[keep], sysm.alpha[keep],
+                        sysm.boxlo, sysm.boxhi, 2)
+    g = P.ewald_g(1e-4, sysm.q, 12.0, sysm.boxlo, sysm.boxhi)
+    ref = None
+    for variant in (0, 6, 20, 31, 41):
+        for words in ("polar_gs_ranked no fixed_iteration yes max_iterations 6 damp_type exponential polar_cutoff 12.0",
+                      "polar_gs_ranked no precision 1e-9 max_iterations 80 damp_type exponential polar_cutoff 12.0"):
+            s = pb.PairStyle(device=0)
+            _fluid_style_on_device(s, sysm, g, words)
+            s.set_option("sweep_variant", variant)
+            res, mu, ef, f = run_system(s, sysm)
+            s.close()
+            key = words.split()[2]
+            if ref is None:
+                ref = {}
+            if key not in ref:
+                ref[key] = (res.iterations, mu, f, res.eng_pol)
+                continue
+            it0, mu0, f0, e0 = ref[key]
+            assert res.iterations == it0, (variant, key)
+            assert H.rel_err(mu, mu0) < 1e-12 and np.abs(f - f0).max() < 1e-12 * np.abs(f0).max(), (variant, key)
+            assert abs(res.eng_pol - e0) < 1e-12 * abs(e0)
+
+
+def _water_on_device(style, sysm, st, words):
+    style.set_ntypes(2)
+    style.command("pair_style lj/cut/coul/long/polarization 2.5 12.0 " + words)
+    style.command("pair_coeff 1 1 0.155 3.166")
+    style.command("pair_coeff 2 2 0.0 1.0")
+    style.init(g_ewald=st.g_ewald, molecular=0)
+    style.set_box(sysm.boxlo, sysm.boxhi)
+
+
+def test_water_box_jacobi_matches_oracle(style):
+    """BASELINE config 3 shape at reduced N (3000 atoms): molecule ids exclude intramolecular pairs from the
+    static field and the charge-dipole terms, but not from dipole-dipole (reference semantics)."""
+    sysm = H.water_box(10)
+    st = H.water_style(sysm, 2.5, 12.0, polar_cut=12.0, damp_type="exponential", polar_gs_ranked=0,
+                       fixed_iteration=1, max_iterations=10)
+    ref = P.polar_rows(sysm, st)
+    _water_on_device(style, sysm, st, "polar_gs_ranked no fixed_iteration yes max_iterations 10 damp_type exponential "
+                                       "polar_cutoff 12.0")
+    res, mu, ef, f = run_system(style, sysm)
+    assert res.iterations == 10
+    assert H.rel_err(ef, ref["ef_static"]) < TOL and H.rel_err(mu, ref["mu"]) < TOL
+    assert abs(res.eng_pol - ref["eng_pol"]) < TOL * abs(ref["eng_pol"])
+
+
+def test_water_box_ranked_colouring_sweep_converges_to_the_oracle(style):
+    """config 3 keywords (precision 1e-11, polar_gs_ranked yes, polar_gamma 1.03): ranked colouring sweep vs the
+    oracle's emulation of the same chunking -- same fixed point within 20*precision, iteration counts +-2; and
+    the fixed point equals the strictly sequential Gauss-Seidel one (the reference's order)."""
+    sysm = H.water_box(10)
+    kw = dict(polar_cut=12.0, damp_type="exponential", polar_gs_ranked=1, precision=1e-11, max_iterations=200,
+              polar_gamma=1.03)
+    st = H.water_style(sysm, 2.5, 12.0, gs_chunks=8, **kw)
+    ref = P.polar_rows(sysm, st)
+    seq = P.polar_rows(sysm, H.water_style(sysm, 2.5, 12.0, gs_chunks=0, **kw))
+    _water_on_device(style, sysm, st, "damp_type exponential precision 1e-11 max_iterations 200 polar_gamma 1.03 "
+                                       "polar_cutoff 12.0 gs_chunks 8")
+    res, mu, ef, f = run_system(style, sysm)
+    assert not (res.status & pb.STATUS_DIVERGED)
+    assert abs(res.iterations - ref["iterations"]) <= 2
+    assert np.abs(mu - ref["mu"]).max() < 20 * 1e-11
+    assert np.abs(mu - seq["mu"]).max() < 100 * 1e-11
+    assert abs(res.eng_pol - seq["eng_pol"]) < 1e-8 * abs(seq["eng_pol"])
