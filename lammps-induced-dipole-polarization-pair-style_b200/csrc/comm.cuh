@@ -137,7 +137,7 @@ static void comm_map_peers(polb200_handle *h)
   c.mapped_ptr[1] = h->mub.p;
   c.mapped_ptr[2] = c.flags.p;
   c.mapped_ptr[3] = h->xq.p;
-  int ok = c.want_push && c.nranks <= MAX_PEERS ? 1 : 0;
+  int ok = c.want_push && c.nranks <= MAX_PEERS && !c.shared_device ? 1 : 0;
   cudaIpcMemHandle_t mine[NPEERBUF];
   memset(mine, 0, sizeof(mine));
   if (ok) {
@@ -354,7 +354,7 @@ static void comm_signal_wait(polb200_handle *h, double *change_inout)
 {
   CommState &c = h->comm;
   c.epoch++;
-  LAUNCH(h, k_signal_wait, 1, 32, c.rank, c.nranks, c.epoch, c.push, change_inout);
+  LAUNCH(h, k_signal_wait, 1, 32, c.rank, c.nranks, c.epoch, c.push, change_inout, c.barrier_timeout_ns, h->flags.p + 6);
 }
 
 // ghost refresh: positions (shifted) and/or one dipole array (mua or mub).

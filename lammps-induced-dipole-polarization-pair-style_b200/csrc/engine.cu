@@ -93,6 +93,8 @@ namespace polb200 {
 // multi-GPU state (see comm.cuh)
 struct CommState {
   bool active = false, geom_valid = false, want_push = true, flags_zeroed = false;
+  bool shared_device = false;                          // two ranks on one GPU: spin barriers are not safe there
+  unsigned long long barrier_timeout_ns = 20000000000ull;  // 20 s
   int rank = 0, nranks = 1;
   int pg[3] = {1, 1, 1};
   ncclComm_t nccl = nullptr;
@@ -986,6 +988,8 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
          h->c_mu.p, h->c_ef.p);
   CUDA_CHECK(cudaEventRecord(h->ev[4], h->stream));
   CUDA_CHECK(cudaMemcpyAsync(h->h_scal.p, h->scal.p, S_N * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  h->h_int.ensure(8);
+  CUDA_CHECK(cudaMemcpyAsync(h->h_int.p, h->flags.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   if (dev) {
     // device-resident caller: f += pair force, mu/ef overwritten, all on the stream
     LAUNCH(h, k_add_inplace, cdiv((long)3 * n, 256), 256, (long)3 * n, h->c_f.p, at->f);
@@ -1008,6 +1012,11 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
   }
 
   sweep_events_collect(h);
+  if (comm) {
+    const int tflag = h->h_int.p[6];
+    if (tflag) throw CudaError{"a neighbour brick did not reach the inter-GPU barrier within the timeout "
+                               "(peer process gone, or several ranks on one GPU)"};
+  }
   const double *sc = h->h_scal.p;
   if (eflag_global) {
     out->eng_vdwl = sc[S_PAIR + 0];
@@ -1435,6 +1444,23 @@ int polb200_comm_init(polb200_t *h, int rank, int nranks, const void *id_bytes, 
     c.nranks = nranks;
     for (int k = 0; k < 3; k++) c.pg[k] = procgrid[k];
     c.active = true;
+    {  // ranks that share a GPU cannot wait on each other inside kernels (nothing guarantees co-scheduling):
+       // detect it once (all-gather of the PCI identity) and keep such runs on the NCCL halo
+      cudaDeviceProp prop;
+      CUDA_CHECK(cudaGetDeviceProperties(&prop, h->device));
+      int id[2] = {(prop.pciDomainID << 16) | (prop.pciBusID << 8) | prop.pciDeviceID, 0};
+      DBuf<int> d;
+      d.ensure((size_t)2 * (nranks + 1));
+      std::vector<int> all((size_t)2 * nranks);
+      CUDA_CHECK(cudaMemcpyAsync(d.p + 2 * nranks, id, sizeof(id), cudaMemcpyHostToDevice, h->stream));
+      NCCL_CHECK(g_nccl.AllGather(d.p + 2 * nranks, d.p, 2, ncclInt, c.nccl, h->stream));
+      CUDA_CHECK(cudaMemcpyAsync(all.data(), d.p, all.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CUDA_CHECK(cudaStreamSynchronize(h->stream));
+      for (int a = 0; a < nranks; a++)
+        for (int b = a + 1; b < nranks; b++)
+          if (all[2 * a] == all[2 * b]) c.shared_device = true;
+      d.release();
+    }
     h->mua.graveyard = h->mub.graveyard = h->xq.graveyard = &c.graveyard;
     if (const char *v = getenv("POLB200_P2P_PUSH")) c.want_push = atoi(v) != 0;
     h->have_lists = false;

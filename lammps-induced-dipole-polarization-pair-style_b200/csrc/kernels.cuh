@@ -1456,7 +1456,18 @@ __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned l
 // [0,MAX_PEERS) arrival epoch of each source rank, then two banks of MAX_PEERS partial sums (by epoch parity).
 // The dipoles pushed by the sweep kernel were stored by an EARLIER kernel of the same stream, so they are
 // performed before this kernel's release-store of the epoch.
-__global__ void k_signal_wait(int rank, int nranks, unsigned long long epoch, PeerPush P, double *__restrict__ change)
+__device__ __forceinline__ unsigned long long global_ns()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// A brick that never arrives (crashed peer, ranks sharing one GPU so that the kernels cannot run at the same
+// time) must not hang the device: the wait gives up after timeout_ns and raises *timeout_flag, which the host
+// turns into an error at the end of the step.
+__global__ void k_signal_wait(int rank, int nranks, unsigned long long epoch, PeerPush P, double *__restrict__ change,
+                              unsigned long long timeout_ns, int *__restrict__ timeout_flag)
 {
   const int r = threadIdx.x;
   const int bank = (1 + (int)(epoch & 1ull)) * MAX_PEERS;
@@ -1466,7 +1477,13 @@ __global__ void k_signal_wait(int rank, int nranks, unsigned long long epoch, Pe
     if (change) theirs[bank + rank] = (unsigned long long)__double_as_longlong(*change);
     __threadfence_system();
     st_release_sys(theirs + rank, epoch);
+    const unsigned long long t0 = global_ns();
+    unsigned spins = 0;
     while (ld_acquire_sys(mine + r) < epoch) {
+      if ((++spins & 1023u) == 0 && global_ns() - t0 > timeout_ns) {
+        atomicExch(timeout_flag, 1);
+        break;
+      }
     }
   }
   __syncwarp();
