@@ -140,6 +140,8 @@ struct polb200_handle {
   int xsort_bits = 10;           // resolution of the x position inside a cell in the sort key (0: cell order only)
   int sweep_variant = 41;        // 41: TMA-fed pair-group sweep (Jacobi), 31: pair groups with register prefetch, 20: per-atom cached sweep, 6: matrix-free, 0: first version
   bool use_tight = true;         // per-step tight list
+  bool alternate = true;         // sweeps walk the groups alternately forwards / backwards (L2 reuse of the stream tail)
+  unsigned sweep_parity = 0;
   bool use_push = true;          // sweep kernel stores new dipoles into their ghost copies itself
   bool time_sweeps = false;     // record CUDA events around every k_sweep launch (bench roofline)
   std::vector<cudaEvent_t> sweep_ev;
@@ -690,7 +692,8 @@ static int launch_list_sweep(polb200_handle *h, int beg, int end, const int *ord
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GW * 32, smem));                            \
     const int grid = std::min(cdiv(h->ngroups, GW), std::max(per_sm, 1) * h->num_sms);                                  \
     kern<<<grid, GW * 32, smem, h->stream>>>(h->ngroups, h->group_first.p, h->group_two.p, h->growstart.p, h->tgneigh.p, \
-                                             h->tgcount.p, h->s12ab.p, h->xq.p, cur, h->ef.p, nxt, h->partial.p, Q, h->flags.p + 4);     \
+                                             h->tgcount.p, h->s12ab.p, h->xq.p, cur, h->ef.p, nxt, h->partial.p, Q, h->flags.p + 4,     \
+                                             (h->alternate && (h->sweep_parity++ & 1)) ? 1 : 0);     \
     h->launches++;                                                                                                      \
     CUDA_CHECK(cudaGetLastError());                                                                                     \
   } while (0)
@@ -1305,6 +1308,10 @@ int polb200_set_option(polb200_t *h, const char *name, double value)
   if (!strcmp(name, "xsort_bits")) {
     h->xsort_bits = (int)value;
     h->have_lists = false;
+    return POLB200_OK;
+  }
+  if (!strcmp(name, "alternate")) {
+    h->alternate = value != 0.0;
     return POLB200_OK;
   }
   if (!strcmp(name, "use_push")) {

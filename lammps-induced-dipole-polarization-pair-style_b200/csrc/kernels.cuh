@@ -1771,7 +1771,7 @@ k_sweep_group_tma(int ngroups, const int *__restrict__ group_first, const int *_
                   const unsigned long long *__restrict__ rowstart, const int *__restrict__ tneigh,
                   const int *__restrict__ tcount, const double4 *__restrict__ s12ab, const double4 *__restrict__ xq,
                   const double4 *__restrict__ mu_in, const double4 *__restrict__ ef, double4 *__restrict__ mu_out,
-                  double *__restrict__ row_change, PushArgs Q, int *dbg)
+                  double *__restrict__ row_change, PushArgs Q, int *dbg, int reverse)
 {
   // stage layout: CHUNK x 32 B scalars {s1a,s2a,s1b,s2b}, then CHUNK x 4 B indices.  (Splitting the two members
   // into separate 16-byte streams makes the LDS conflict free but needs a third bulk copy per chunk: measured slower.)
@@ -1790,7 +1790,11 @@ k_sweep_group_tma(int ngroups, const int *__restrict__ group_first, const int *_
   __syncwarp();
   unsigned cc = 0;  // chunks consumed by this warp so far: stage = cc % NSTAGE, parity = (cc / NSTAGE) & 1
   const int nwarps = gridDim.x * WPB;
-  for (int g = blockIdx.x * WPB + warp; g < ngroups; g += nwarps) {
+  // `reverse` alternates from sweep to sweep: the 126 MB L2 still holds the tail of the stream the previous
+  // sweep read last, so walking the groups in the opposite direction turns the first ~quarter of this sweep's
+  // HBM stream into L2 hits (a Jacobi sweep does not care about the order of its rows)
+  for (int gi = blockIdx.x * WPB + warp; gi < ngroups; gi += nwarps) {
+    const int g = reverse ? ngroups - 1 - gi : gi;
     const int a = group_first[g];
     const bool two = group_two[g] != 0;
     const int b = two ? a + 1 : a;

@@ -23,12 +23,13 @@ def main():
     ty = np.ascontiguousarray(sysm.type); al = np.ascontiguousarray(sysm.alpha)
     ref_mu = None
     import os
-    spec = os.environ.get("VB_OPTS", "20:4:10,30:4:10,30:3:10,30:5:10,30:4:0")
+    spec = os.environ.get("VB_OPTS", "41:4:10:1,41:4:10:0")
     opts = [tuple(float(t) for t in o.split(":")) for o in spec.split(",")]
-    for variant, tight, xb in opts:
+    for variant, tight, xb, alt in opts:
         pb.lib().polb200_set_option(s._h, b"sweep_variant", float(variant))
         pb.lib().polb200_set_option(s._h, b"bin_div", float(tight))
         pb.lib().polb200_set_option(s._h, b"xsort_bits", float(xb))
+        pb.lib().polb200_set_option(s._h, b"alternate", float(alt))
         mu = np.zeros((n, 3)); f = np.zeros((n, 3))
         s.compute(x, q, ty, al, mu, f, ago=0)
         pb.lib().polb200_set_option(s._h, b"time_sweeps", 1.0)
@@ -46,7 +47,7 @@ def main():
         err = np.abs(mu - ref_mu).max() / np.abs(ref_mu).max()
         if os.environ.get("VB_FLAGS"):
             print("   debug flags:", s.debug_fetch("flags", np.int32, 8))
-        print(f"variant {variant:.0f} bin_div {tight} xsort_bits {xb:.0f}: sweep {sw[0] / sw[1] * 1e3:8.1f} us  neigh {acc[0]:.3f} pair {acc[1]:.3f} "
+        print(f"variant {variant:.0f} bin_div {tight} xsort_bits {xb:.0f} alternate {alt:.0f}: sweep {sw[0] / sw[1] * 1e3:8.1f} us  neigh {acc[0]:.3f} pair {acc[1]:.3f} "
               f"scf {acc[2]:.3f} force {acc[3]:.3f} total {acc[4]:.3f} ms   mu dev vs v0 {err:.2e}  E_pol {r.eng_pol:.10f}")
     s.close()
 
