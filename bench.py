@@ -368,6 +368,13 @@ def gpu_arm(args):
         entries = float(group_stats[1]) if grouped else float(polar_pairs)
         alg_bytes = (36.0 if grouped else 20.0) * entries + 64.0 * (n + nghost) + 64.0 * n
         achieved = alg_bytes / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else None
+        # measured DRAM traffic of the same kernel on the same workload (one `ncu --set full` capture, per launch)
+        traffic = None
+        tf = ROOT / "profiles" / "ncu_traffic.json"
+        if tf.exists() and world == 1:
+            t = json.loads(tf.read_text())
+            if t.get("kernel") == ("k_sweep_group_tma" if grouped else "k_sweep_cached") and t.get("atoms") == n:
+                traffic = t["dram_bytes_per_launch"]
         # SURVEY §8d's matrix-free model (every gather charged to HBM): 52 B per pair + 104 B per atom
         survey_bytes = 52.0 * polar_pairs + 104.0 * n
         # CPU baseline on a bounded sample (rank 0, N=1 only)
@@ -405,7 +412,7 @@ def gpu_arm(args):
             "roofline": {"bound": "hbm", "kernel": ("k_sweep_group_tma" if grouped else "k_sweep_cached") +
                                                     " (one dipole iteration over the neighbor list)",
                          "achieved": achieved, "peak": peak_gbs,
-                         "unit": "GB/s", "frac": achieved / peak_gbs if achieved else None, "traffic": None,
+                         "unit": "GB/s", "frac": achieved / peak_gbs if achieved else None, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650",
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "bytes_model": ("36 B per group-row entry streamed (index + cached radial scalars of both members)"
