@@ -219,6 +219,7 @@ static void comm_build_ghosts(polb200_handle *h, int n)
   CUDA_CHECK(cudaMemcpyAsync(hflags, h->flags.p, sizeof(hflags), cudaMemcpyDeviceToHost, h->stream));
   CUDA_CHECK(cudaStreamSynchronize(h->stream));
   const int nan_local = hflags[0] & 1;
+  h->P.pc.has_molecules = hflags[3] ? 1 : 0;
   const int ns = (int)ns64;
   c.nsend = ns;
   h->push_off.ensure(n + 2);

@@ -140,6 +140,7 @@ struct polb200_handle {
   int xsort_bits = 10;           // resolution of the x position inside a cell in the sort key (0: cell order only)
   int sweep_variant = 41;        // 41: TMA-fed pair-group sweep (Jacobi), 31: pair groups with register prefetch, 20: per-atom cached sweep, 6: matrix-free, 0: first version
   bool use_tight = true;         // per-step tight list
+  bool l2_evict_first = true;    // TMA row streams are marked evict-first in L2
   bool alternate = true;         // sweeps walk the groups alternately forwards / backwards (L2 reuse of the stream tail)
   unsigned sweep_parity = 0;
   bool use_push = true;          // sweep kernel stores new dipoles into their ghost copies itself
@@ -234,21 +235,15 @@ static void upload_params(polb200_handle *h)
 
   const int nt = st.ncoultablebits ? (1 << st.ncoultablebits) : 1;
   std::vector<double> tb((size_t)8 * nt, 0.0);
-  if (st.ncoultablebits) {
+  if (st.ncoultablebits) {  // interleave: {r, dr, f, df, e, de, c, dc} per entry
     const std::vector<double> *ts[8] = {&st.tab.r, &st.tab.dr, &st.tab.f, &st.tab.df,
-                                        &st.tab.c, &st.tab.dc, &st.tab.e, &st.tab.de};
-    for (int k = 0; k < 8; k++) std::copy(ts[k]->begin(), ts[k]->end(), tb.begin() + (size_t)k * nt);
+                                        &st.tab.e, &st.tab.de, &st.tab.c, &st.tab.dc};
+    for (int i = 0; i < nt; i++)
+      for (int k = 0; k < 8; k++) tb[(size_t)8 * i + k] = (*ts[k])[i];
   }
-  h->d_tables.ensure(tb.size());
+  h->d_tables.ensure(tb.size() + 8);
   CUDA_CHECK(cudaMemcpy(h->d_tables.p, tb.data(), tb.size() * sizeof(double), cudaMemcpyHostToDevice));
-  P.tb.r = h->d_tables.p;
-  P.tb.dr = h->d_tables.p + nt;
-  P.tb.f = h->d_tables.p + 2 * nt;
-  P.tb.df = h->d_tables.p + 3 * nt;
-  P.tb.c = h->d_tables.p + 4 * nt;
-  P.tb.dc = h->d_tables.p + 5 * nt;
-  P.tb.e = h->d_tables.p + 6 * nt;
-  P.tb.de = h->d_tables.p + 7 * nt;
+  P.tb.rec = reinterpret_cast<const CoulTabHalf *>(h->d_tables.p);
 
   PairConsts &pc = P.pc;
   pc.cut_coulsq = st.cut_coulsq;
@@ -264,6 +259,7 @@ static void upload_params(polb200_handle *h)
   pc.ncoulmask = st.tab.mask;
   pc.ncoulshiftbits = st.tab.shift;
   pc.ntypes = st.ntypes;
+  pc.has_molecules = 1;  // refined at every rebuild
   for (int k = 0; k < 4; k++) {
     pc.special_lj[k] = st.env.special_lj[k];
     pc.special_coul[k] = st.env.special_coul[k];
@@ -428,7 +424,7 @@ static void rebuild(polb200_handle *h, const polb200_atoms *at)
   h->xq.ensure(n); h->mua.ensure(n); h->mub.ensure(n); h->tm.ensure(n); h->tag.ensure(n);
   LAUNCH(h, k_gather_local, cdiv(n, 256), 256, n, h->perm.p, h->c_x.p, h->c_q.p, h->c_type.p,
          at->molecule ? h->c_mol.p : nullptr, at->tag ? h->c_tag.p : nullptr, h->c_alpha.p, h->c_mu.p,
-         h->xq.p, h->mua.p, h->tm.p, h->tag.p, h->invperm.p);
+         h->xq.p, h->mua.p, h->tm.p, h->tag.p, h->invperm.p, h->flags.p + 3);
 
   // 2. ghosts: periodic images of this box (single GPU) or the boundary shells of the neighbour bricks
   int ng = 0;
@@ -446,6 +442,7 @@ static void rebuild(polb200_handle *h, const polb200_atoms *at)
     CUDA_CHECK(cudaMemcpyAsync(hflags, h->flags.p, sizeof(hflags), cudaMemcpyDeviceToHost, h->stream));
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
     if (hflags[0] & 1) throw StyleError{POLB200_ERR_NAN, "Non-numeric positions - simulation unstable"};
+    h->P.pc.has_molecules = hflags[3] ? 1 : 0;
     if (ng64 + (unsigned long long)n >= (1ull << 30))
       throw StyleError{POLB200_ERR_OVERFLOW, "owned+ghost atoms exceed the 30-bit neighbor index"};
     ng = (int)ng64;
@@ -678,9 +675,9 @@ static int launch_list_sweep(polb200_handle *h, int beg, int end, const int *ord
 #define GOG(GW, MB, DP) \
   do { if (push) { if (change) GOG4(GW, MB, DP, true, true); else GOG4(GW, MB, DP, false, true); } \
        else { if (change) GOG4(GW, MB, DP, true, false); else GOG4(GW, MB, DP, false, false); } } while (0)
-#define GOT4(GW, NS, CK, CH, PU)                                                                                        \
+#define GOT4(GW, NS, CK, CH, PU, EV)                                                                                     \
   do {                                                                                                                  \
-    auto kern = k_sweep_group_tma<GW, NS, CK, CH, PU>;                                                                  \
+    auto kern = k_sweep_group_tma<GW, NS, CK, CH, PU, EV>;                                                               \
     const int smem = GW * NS * CK * 36 + GW * NS * 8;                                                                   \
     static bool attr_set = false;                                                                                       \
     if (!attr_set) {                                                                                                    \
@@ -697,9 +694,10 @@ static int launch_list_sweep(polb200_handle *h, int beg, int end, const int *ord
     h->launches++;                                                                                                      \
     CUDA_CHECK(cudaGetLastError());                                                                                     \
   } while (0)
-#define GOT(GW, NS, CK) \
-  do { if (push) { if (change) GOT4(GW, NS, CK, true, true); else GOT4(GW, NS, CK, false, true); } \
-       else { if (change) GOT4(GW, NS, CK, true, false); else GOT4(GW, NS, CK, false, false); } } while (0)
+#define GOT3(GW, NS, CK, EV) \
+  do { if (push) { if (change) GOT4(GW, NS, CK, true, true, EV); else GOT4(GW, NS, CK, false, true, EV); } \
+       else { if (change) GOT4(GW, NS, CK, true, false, EV); else GOT4(GW, NS, CK, false, false, EV); } } while (0)
+#define GOT(GW, NS, CK) do { if (h->l2_evict_first) GOT3(GW, NS, CK, true); else GOT3(GW, NS, CK, false); } while (0)
       switch (h->sweep_variant) {
         case 40: GOT(4, 4, 64); break;
         case 41: GOT(4, 3, 64); break;
@@ -709,6 +707,7 @@ static int launch_list_sweep(polb200_handle *h, int beg, int end, const int *ord
       }
 #undef GOG4
 #undef GOT4
+#undef GOT3
 #undef GOT
 #undef GOG
       return end - beg;
@@ -1308,6 +1307,10 @@ int polb200_set_option(polb200_t *h, const char *name, double value)
   if (!strcmp(name, "xsort_bits")) {
     h->xsort_bits = (int)value;
     h->have_lists = false;
+    return POLB200_OK;
+  }
+  if (!strcmp(name, "l2_evict_first")) {
+    h->l2_evict_first = value != 0.0;
     return POLB200_OK;
   }
   if (!strcmp(name, "alternate")) {

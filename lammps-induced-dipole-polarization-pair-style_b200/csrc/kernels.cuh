@@ -193,11 +193,12 @@ __global__ void k_gather_local(int n, const int *__restrict__ perm, const double
                                const int *__restrict__ mol, const int *__restrict__ tag,
                                const double *__restrict__ alpha, const double *__restrict__ mu,
                                double4 *__restrict__ xq, double4 *__restrict__ mua, int2 *__restrict__ tm,
-                               int *__restrict__ tagout, int *__restrict__ invperm)
+                               int *__restrict__ tagout, int *__restrict__ invperm, int *__restrict__ molflag)
 {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
   int c = perm[s];
+  if (mol && mol[c] != 0 && *molflag == 0) atomicOr(molflag, 1);
   xq[s] = make_double4(x[3 * c], x[3 * c + 1], x[3 * c + 2], q[c]);
   mua[s] = make_double4(mu[3 * c], mu[3 * c + 1], mu[3 * c + 2], alpha[c]);
   tm[s] = make_int2(type[c], mol ? mol[c] : 0);
@@ -449,7 +450,7 @@ k_tighten(int nloc, double reach2, const unsigned long long *__restrict__ rowsta
 constexpr int NPAIR_PART = 8;
 
 template <bool EVFLAG, bool FIELD>
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, 3)
 k_pair(int nloc, DevParams P, const double4 *__restrict__ xq, const int2 *__restrict__ tm, ListRows L,
        double4 *__restrict__ f_pair, double4 *__restrict__ ef, double *__restrict__ partial)
 {
@@ -461,9 +462,17 @@ k_pair(int nloc, DevParams P, const double4 *__restrict__ xq, const int2 *__rest
     const int2 tmi = tm[s];
     const int n1 = P.pc.ntypes + 1;
     double fx = 0, fy = 0, fz = 0, ex = 0, ey = 0, ez = 0;
-    const unsigned long long beg = L.begin(s), end = L.end(s);
-    for (unsigned long long k = beg + lane; k < end; k += 32) {
-      const int raw = L.neigh[k];
+    // neighbour entries are fetched two trips ahead so that the dependent index -> gather chain of the next
+    // trip overlaps this trip's arithmetic
+    const int *__restrict__ row = L.neigh + L.begin(s);
+    const int cnt = (int)(L.end(s) - L.begin(s));
+    int rawA = lane < cnt ? __ldcs(row + lane) : 0;
+    int rawB = lane + 32 < cnt ? __ldcs(row + lane + 32) : 0;
+    for (int k = lane; k < cnt; k += 32) {
+      const int rawC = k + 64 < cnt ? __ldcs(row + k + 64) : 0;
+      const int raw = rawA;
+      rawA = rawB;
+      rawB = rawC;
       const int j = raw & NEIGHMASK, sb = (raw >> SBBITS) & 3;
       const double4 xj = ld4(xq + j);
       const int2 tmj = tm[j];
@@ -1086,7 +1095,7 @@ k_rank_metric(int nloc, ListRows L, const double4 *__restrict__ xq, const double
 constexpr int NPOL_PART = 9;
 
 template <bool LIST, bool EVFLAG, bool VPAIR>
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, 3)
 k_polforce(int nloc, DevParams P, ListRows L, AllPairRows A, const double4 *__restrict__ xq,
            const double4 *__restrict__ mua, const int2 *__restrict__ tm, double4 *__restrict__ f_pol,
            double *__restrict__ partial)
@@ -1100,12 +1109,12 @@ k_polforce(int nloc, DevParams P, ListRows L, AllPairRows A, const double4 *__re
     const int moli = tm[s].y;
     double fx = 0, fy = 0, fz = 0;
     PolPairIn in;
-    auto visit = [&](int j, bool i_is_a, double dx, double dy, double dz) {
-      const double4 xj = ld4(xq + j);
+    const bool molecules = P.pc.has_molecules != 0;
+    auto visit = [&](int j, const double4 &xj, bool i_is_a, double dx, double dy, double dz) {
       const double4 mj = ld4(mua + j);
-      const int molj = tm[j].y;
       in.dx = dx; in.dy = dy; in.dz = dz;
-      in.intermolecular = (moli != molj) || moli == 0;
+      in.intermolecular = true;
+      if (molecules) in.intermolecular = (moli != tm[j].y) || moli == 0;
       if (i_is_a) {
         in.qa = xi.w; in.qb = xj.w; in.alpha_a = mi.w; in.alpha_b = mj.w;
         in.max_ = mi.x; in.may = mi.y; in.maz = mi.z; in.mbx = mj.x; in.mby = mj.y; in.mbz = mj.z;
@@ -1129,12 +1138,18 @@ k_polforce(int nloc, DevParams P, ListRows L, AllPairRows A, const double4 *__re
     };
     if (LIST) {
       const double reach = fmax(P.pc.cut_coulsq, P.pc.polar_cutsq);
-      const unsigned long long beg = L.begin(s), end = L.end(s);
-      for (unsigned long long k = beg + lane; k < end; k += 32) {
-        const int j = L.neigh[k] & NEIGHMASK;
+      const int *__restrict__ row = L.neigh + L.begin(s);
+      const int cnt = (int)(L.end(s) - L.begin(s));
+      int jA = lane < cnt ? (__ldcs(row + lane) & NEIGHMASK) : 0;
+      int jB = lane + 32 < cnt ? (__ldcs(row + lane + 32) & NEIGHMASK) : 0;
+      for (int k = lane; k < cnt; k += 32) {
+        const int jC = k + 64 < cnt ? (__ldcs(row + k + 64) & NEIGHMASK) : 0;
+        const int j = jA;
+        jA = jB;
+        jB = jC;
         const double4 xj = ld4(xq + j);
         const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
-        if (dx * dx + dy * dy + dz * dz < reach) visit(j, true, dx, dy, dz);
+        if (dx * dx + dy * dy + dz * dz < reach) visit(j, xj, true, dx, dy, dz);
       }
     } else {
       const int ci = A.perm[s];
@@ -1145,7 +1160,7 @@ k_polforce(int nloc, DevParams P, ListRows L, AllPairRows A, const double4 *__re
         double dx, dy, dz;
         if (i_is_a) min_image_del(P.box, xi.x, xi.y, xi.z, xj.x, xj.y, xj.z, dx, dy, dz);
         else min_image_del(P.box, xj.x, xj.y, xj.z, xi.x, xi.y, xi.z, dx, dy, dz);
-        visit(j, i_is_a, dx, dy, dz);
+        visit(j, xj, i_is_a, dx, dy, dz);
       }
     }
     fx = warp_sum(fx);
@@ -1750,6 +1765,22 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// same copy, marked evict-first in L2: the row streams are read once per sweep and must not push the
+// position / dipole records (gathered ~700 times each per sweep) out of the 126 MB L2
+__device__ __forceinline__ unsigned long long l2_evict_first_policy()
+{
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s_stream(void *dst, const void *src, unsigned bytes, unsigned long long *bar,
+                                                unsigned long long pol)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+               : "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
 {
   asm volatile(
@@ -1765,7 +1796,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
       : "memory");
 }
 
-template <int WPB, int NSTAGE, int CHUNK, bool CHANGE, bool PUSH>
+template <int WPB, int NSTAGE, int CHUNK, bool CHANGE, bool PUSH, bool EVICT>
 __global__ void __launch_bounds__(WPB * 32)
 k_sweep_group_tma(int ngroups, const int *__restrict__ group_first, const int *__restrict__ group_two,
                   const unsigned long long *__restrict__ rowstart, const int *__restrict__ tneigh,
@@ -1788,6 +1819,7 @@ k_sweep_group_tma(int ngroups, const int *__restrict__ group_first, const int *_
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncwarp();
+  const unsigned long long l2pol = EVICT ? l2_evict_first_policy() : 0ull;
   unsigned cc = 0;  // chunks consumed by this warp so far: stage = cc % NSTAGE, parity = (cc / NSTAGE) & 1
   const int nwarps = gridDim.x * WPB;
   // `reverse` alternates from sweep to sweep: the 126 MB L2 still holds the tail of the stream the previous
@@ -1808,8 +1840,13 @@ k_sweep_group_tma(int ngroups, const int *__restrict__ group_first, const int *_
       const unsigned e4 = (unsigned)((e + 3) & ~3);  // rows are padded to multiples of 4 entries (16-byte copies)
       unsigned char *dst = ring + (size_t)slot * STAGE_BYTES;
       mbar_expect_tx(bars + slot, e4 * 36u);
-      bulk_g2s(dst, rs + (size_t)c * CHUNK, e4 * 32u, bars + slot);
-      bulk_g2s(dst + CHUNK * 32, row + (size_t)c * CHUNK, e4 * 4u, bars + slot);
+      if (EVICT) {
+        bulk_g2s_stream(dst, rs + (size_t)c * CHUNK, e4 * 32u, bars + slot, l2pol);
+        bulk_g2s_stream(dst + CHUNK * 32, row + (size_t)c * CHUNK, e4 * 4u, bars + slot, l2pol);
+      } else {
+        bulk_g2s(dst, rs + (size_t)c * CHUNK, e4 * 32u, bars + slot);
+        bulk_g2s(dst + CHUNK * 32, row + (size_t)c * CHUNK, e4 * 4u, bars + slot);
+      }
     };
     if (lane == 0) {
       const int pre = min(NSTAGE, nchunks);

@@ -34,8 +34,19 @@ struct PairConsts {
   int damping_exponential;
   int ncoultablebits, ncoulmask, ncoulshiftbits;
   int ntypes;
+  int has_molecules;   // 0: no owned atom carries a molecule id, every pair is inter-molecular
   double special_lj[4], special_coul[4];
 };
+
+// 1/sqrt(x): one rsqrt on the device instead of a square root and a division
+PB_HD double pb_rsqrt(double x)
+{
+#if defined(__CUDA_ARCH__)
+  return rsqrt(x);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
 
 // Domain::closest_image for one coordinate (src/domain.cpp:1220-1318, orthogonal branch).
 // d = xj - xi on entry; returns the wrapped displacement.  The while-loops run at most a couple of
@@ -81,9 +92,25 @@ PB_HD double rsq_nofma(double dx, double dy, double dz)
 }
 
 // ---- stage 2a: LJ + real-space Ewald Coulomb for one neighbour (pol.cpp:254-315) ---------------------
-struct CoulTablesDev {
-  const double *r, *dr, *f, *df, *c, *dc, *e, *de;
+// One 64-byte record per table entry, {r, dr, f, df | e, de, c, dc}: the lookup of a pair is one (force only)
+// or two (energy / special-bond correction) 32-byte loads from ONE line instead of six scattered 8-byte
+// gathers from six arrays -- the table gathers dominated the L1 traffic of the LJ+Coulomb kernel.
+struct alignas(32) CoulTabHalf {
+  double a, b, c, d;
 };
+struct CoulTablesDev {
+  const CoulTabHalf *rec;  // 2 halves per entry
+};
+PB_HD CoulTabHalf load_tab(const CoulTabHalf *p)
+{
+#if defined(__CUDA_ARCH__)
+  CoulTabHalf v;  // one 256-bit read-only load
+  asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=d"(v.a), "=d"(v.b), "=d"(v.c), "=d"(v.d) : "l"(p));
+  return v;
+#else
+  return *p;
+#endif
+}
 
 struct LJCoeffs {  // (ntypes+1)^2 row-major
   const double *cutsq, *cut_ljsq, *lj1, *lj2, *lj3, *lj4, *offset;
@@ -121,10 +148,14 @@ PB_HD double lj_coul_pair(const PairConsts &pc, const LJCoeffs &lj, const CoulTa
       const int bits = u.i;
 #endif
       const int itable = (bits & pc.ncoulmask) >> pc.ncoulshiftbits;
-      const double fraction = ((double)rsqf - tb.r[itable]) * tb.dr[itable];
-      forcecoul = qi * qj * (tb.f[itable] + fraction * tb.df[itable]);
-      if (factor_coul < 1.0) prefactor = qi * qj * (tb.c[itable] + fraction * tb.dc[itable]);
-      if (want_e) ecoul = qi * qj * (tb.e[itable] + fraction * tb.de[itable]);
+      const CoulTabHalf t0 = load_tab(tb.rec + 2 * itable);  // r, dr, f, df
+      const double fraction = ((double)rsqf - t0.a) * t0.b;
+      forcecoul = qi * qj * (t0.c + fraction * t0.d);
+      if (factor_coul < 1.0 || want_e) {
+        const CoulTabHalf t1 = load_tab(tb.rec + 2 * itable + 1);  // e, de, c, dc
+        if (factor_coul < 1.0) prefactor = qi * qj * (t1.c + fraction * t1.d);
+        if (want_e) ecoul = qi * qj * (t1.a + fraction * t1.b);
+      }
     }
     if (factor_coul < 1.0) {
       forcecoul -= (1.0 - factor_coul) * prefactor;
@@ -192,17 +223,19 @@ PB_HD void pol_force_pair(const PairConsts &pc, const PolPairIn &in, bool want_e
   const double delx = in.dx, dely = in.dy, delz = in.dz;
   const double xsq = delx * delx, ysq = dely * dely, zsq = delz * delz;
   const double rsq = xsq + ysq + zsq;
-  const double r2inv = 1.0 / rsq;
-  const double rinv = sqrt(r2inv);
-  const double r = 1.0 / rinv;
+  // one reciprocal square root feeds every inverse power (the reference divides and takes roots separately,
+  // pol.cpp:441-452; the results agree to a few ulp, far inside the 1e-10 parity bar)
+  const double rinv = pb_rsqrt(rsq);
+  const double r2inv = rinv * rinv;
+  const double r = rsq * rinv;
   const double r3inv = r2inv * rinv;
   const double f_shift = pc.f_shift, kq = pc.kq;
   fx = fy = fz = 0.0;
   u_ef = u_dd = 0.0;
 
   if (rsq < pc.cut_coulsq && in.intermolecular) {
-    const double dvdrr = 1.0 / rsq + f_shift;
-    const double ef_temp = dvdrr * 1.0 / r * kq;
+    const double dvdrr = r2inv + f_shift;
+    const double ef_temp = dvdrr * rinv * kq;
     // M (symmetric) applied to a dipole: the bracketed factors of pol.cpp:467-475
     const double mxx = (-2.0 * xsq + ysq + zsq) * r2inv + f_shift * (ysq + zsq);
     const double myy = (-2.0 * ysq + xsq + zsq) * r2inv + f_shift * (xsq + zsq);
