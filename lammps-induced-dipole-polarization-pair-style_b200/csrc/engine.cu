@@ -130,6 +130,7 @@ struct polb200_handle {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[6] = {};
   long launches = 0;
+  size_t partial_off = 0;        // where the list sweeps write their per-row squared changes
 
   Box box{};
   bool box_set = false;
@@ -611,7 +612,7 @@ static int launch_v2(polb200_handle *h, int beg, int end, const int *order, cons
   const int nb = cdiv(end - beg, WPB);
   const PushArgs Q = push ? push_args(h, nxt) : PushArgs{};
 #define GO(CH, PU) \
-  LAUNCH(h, (k_sweep_list2<DAMP, PF, WPB, MINB, CH, PU>), nb, WPB * 32, beg, end, order, P, L, h->xq.p, cur, h->ef.p, nxt, h->partial.p, Q)
+  LAUNCH(h, (k_sweep_list2<DAMP, PF, WPB, MINB, CH, PU>), nb, WPB * 32, beg, end, order, P, L, h->xq.p, cur, h->ef.p, nxt, h->partial.p + h->partial_off, Q)
   if (push) { if (change) GO(true, true); else GO(false, true); }
   else { if (change) GO(true, false); else GO(false, false); }
 #undef GO
@@ -637,7 +638,7 @@ static int launch_cached(polb200_handle *h, int beg, int end, const int *order, 
   const int nb = cdiv(end - beg, WPB);
   const PushArgs Q = push ? push_args(h, nxt) : PushArgs{};
 #define GO(CH, PU) \
-  LAUNCH(h, (k_sweep_cached<WPB, MINB, CH, PU>), nb, WPB * 32, beg, end, order, L, h->s12.p, h->xq.p, cur, h->ef.p, nxt, h->partial.p, Q)
+  LAUNCH(h, (k_sweep_cached<WPB, MINB, CH, PU>), nb, WPB * 32, beg, end, order, L, h->s12.p, h->xq.p, cur, h->ef.p, nxt, h->partial.p + h->partial_off, Q)
   if (push) { if (change) GO(true, true); else GO(false, true); }
   else { if (change) GO(true, false); else GO(false, false); }
 #undef GO
@@ -671,7 +672,7 @@ static int launch_list_sweep(polb200_handle *h, int beg, int end, const int *ord
       const PushArgs Q = push ? push_args(h, nxt) : PushArgs{};
 #define GOG4(GW, MB, DP, CH, PU) \
   LAUNCH(h, (k_sweep_group<GW, MB, CH, PU, DP>), cdiv(h->ngroups, GW), GW * 32, h->ngroups, h->group_first.p, h->group_two.p, h->growstart.p, \
-         h->tgneigh.p, h->tgcount.p, h->s12ab.p, h->xq.p, cur, h->ef.p, nxt, h->partial.p, Q)
+         h->tgneigh.p, h->tgcount.p, h->s12ab.p, h->xq.p, cur, h->ef.p, nxt, h->partial.p + h->partial_off, Q)
 #define GOG(GW, MB, DP) \
   do { if (push) { if (change) GOG4(GW, MB, DP, true, true); else GOG4(GW, MB, DP, false, true); } \
        else { if (change) GOG4(GW, MB, DP, true, false); else GOG4(GW, MB, DP, false, false); } } while (0)
@@ -736,7 +737,7 @@ static int launch_list_sweep(polb200_handle *h, int beg, int end, const int *ord
 #define V2(PF, WPB, MINB) \
   return damp ? launch_v2<true, PF, WPB, MINB>(h, beg, end, order, P, L, cur, nxt, change, push) \
               : launch_v2<false, PF, WPB, MINB>(h, beg, end, order, P, L, cur, nxt, change, push)
-  switch (h->sweep_variant) {
+  switch (order ? 1 : h->sweep_variant) {  // chunked sweeps need per-row partials: never the first version
     case 0: {
       const int nb = cdiv(end - beg, WARPS_PER_BLOCK);
       LAUNCH(h, (k_sweep<true>), nb, BLOCK, beg, end, order, P, L, A, h->xq.p, cur, h->ef.p, nxt, h->partial.p);
@@ -929,17 +930,33 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
         }
       } else {
         // ranked colouring sweep: chunks of the ranked order, Jacobi inside, Gauss-Seidel between
+        const bool fused_commit = h->push_ready && h->use_push && (!comm || h->comm.push.enabled);
+        if (list_mode) h->partial.ensure((size_t)n + 64);
         for (int c = 0; c < nchunks; c++) {
           const int beg = (int)(((long)c * n) / nchunks), end = (int)(((long)(c + 1) * n) / nchunks);
           if (end <= beg) continue;
           const int nb = cdiv(end - beg, WARPS_PER_BLOCK);
-          int nparts = nb;
-          if (list_mode) nparts = launch_list_sweep(h, beg, end, order, P, L, A, cur, nxt, want_change, false);
-          else LAUNCH(h, (k_sweep<false>), nb, BLOCK, beg, end, order, P, L, A, h->xq.p, cur, h->ef.p, nxt, h->partial.p);
-          if (want_change) reduce_partials<1>(h, nparts, h->scal.p + S_CHANGE, c > 0);
-          LAUNCH(h, k_commit_rows, cdiv(end - beg, 256), 256, beg, end, order, nxt, cur);
-          ghost_update(h, false, cur, true);  // in place: the neighbours must have finished reading this chunk's input
+          if (list_mode) {
+            // per-row squared changes of every chunk land in one array: a single reduction per iteration
+            h->partial_off = (size_t)beg;
+            launch_list_sweep(h, beg, end, order, P, L, A, cur, nxt, want_change, false);
+            h->partial_off = 0;
+          } else {
+            LAUNCH(h, (k_sweep<false>), nb, BLOCK, beg, end, order, P, L, A, h->xq.p, cur, h->ef.p, nxt, h->partial.p);
+            if (want_change) reduce_partials<1>(h, nb, h->scal.p + S_CHANGE, c > 0);
+          }
+          if (fused_commit) {
+            // in place: the neighbour bricks must have finished reading this chunk's input before their ghost
+            // slots change, and must see the new values before the next chunk (two barriers around one kernel)
+            if (comm) comm_signal_wait(h, nullptr);
+            LAUNCH(h, k_commit_push, cdiv(end - beg, 256), 256, beg, end, order, nxt, cur, push_args(h, cur));
+            if (comm) comm_signal_wait(h, nullptr);
+          } else {
+            LAUNCH(h, k_commit_rows, cdiv(end - beg, 256), 256, beg, end, order, nxt, cur);
+            ghost_update(h, false, cur, true);
+          }
         }
+        if (list_mode && want_change) reduce_partials<1>(h, n, h->scal.p + S_CHANGE, 0);
         if (comm && want_change) comm_allreduce(h, h->scal.p + S_CHANGE, 1, ncclDouble, ncclSum);
       }
       if (want_change) {

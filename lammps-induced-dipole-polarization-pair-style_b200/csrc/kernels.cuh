@@ -899,6 +899,20 @@ k_sweep_cached(int pos_beg, int pos_end, const int *__restrict__ order, ListRows
   if (PUSH) push_row(push_dst, nx, ny, nz, mi.w);
 }
 
+// commit a chunk of the ranked colouring sweep AND refresh the ghost copies of the committed atoms in one pass
+// (own periodic images / neighbour bricks' ghost slots through the push tables)
+__global__ void k_commit_push(int pos_beg, int pos_end, const int *__restrict__ order, const double4 *__restrict__ staged,
+                              double4 *__restrict__ mua, PushArgs Q)
+{
+  int pos = pos_beg + blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= pos_end) return;
+  const int s = order ? order[pos] : pos;
+  const double4 v = staged[s];
+  mua[s] = v;
+  const unsigned long long b = Q.off[s], e = Q.off[s + 1];
+  for (unsigned long long u = b; u < e; u++) *Q.ptr[u] = v;
+}
+
 // commit a chunk of the ranked colouring sweep: staged values become visible (owned records)
 __global__ void k_commit_rows(int pos_beg, int pos_end, const int *__restrict__ order,
                               const double4 *__restrict__ staged, double4 *__restrict__ mua)
