@@ -139,7 +139,9 @@ struct polb200_handle {
   int sweep_block = BLOCK;
   double bin_div = 4.0;          // neighbor cutoff / cell width
   int xsort_bits = 10;           // resolution of the x position inside a cell in the sort key (0: cell order only)
-  int sweep_variant = 41;        // 41: TMA-fed pair-group sweep (Jacobi), 31: pair groups with register prefetch, 20: per-atom cached sweep, 6: matrix-free, 0: first version
+  // 41 (default) / 40 / 44: TMA-fed pair-group sweep (Jacobi list mode); 30 / 31: pair groups with register prefetch;
+  // 20 / 21: per-atom rows + radial cache (also the ranked colouring sweep); 6: matrix-free; 0: first version
+  int sweep_variant = 41;
   bool use_tight = true;         // per-step tight list
   bool l2_evict_first = true;    // TMA row streams are marked evict-first in L2
   bool alternate = true;         // sweeps walk the groups alternately forwards / backwards (L2 reuse of the stream tail)
@@ -619,18 +621,6 @@ static int launch_v2(polb200_handle *h, int beg, int end, const int *order, cons
   return end - beg;
 }
 
-template <bool DAMP, int WPB, int MINB>
-static int launch_v3(polb200_handle *h, int beg, int end, const int *order, const DevParams &P, ListRows L,
-                     const double4 *cur, double4 *nxt, bool change)
-{
-  const int nb = cdiv(end - beg, WPB);
-  if (change)
-    LAUNCH(h, (k_sweep_list3<DAMP, WPB, MINB, true>), nb, WPB * 32, beg, end, order, P, L, h->xq.p, cur, h->ef.p, nxt, h->partial.p);
-  else
-    LAUNCH(h, (k_sweep_list3<DAMP, WPB, MINB, false>), nb, WPB * 32, beg, end, order, P, L, h->xq.p, cur, h->ef.p, nxt, h->partial.p);
-  return end - beg;
-}
-
 template <int WPB, int MINB>
 static int launch_cached(polb200_handle *h, int beg, int end, const int *order, ListRows L, const double4 *cur,
                          double4 *nxt, bool change, bool push)
@@ -728,34 +718,17 @@ static int launch_list_sweep(polb200_handle *h, int beg, int end, const int *ord
       else LAUNCH(h, (k_radial_cache<false>), nrb, BLOCK, h->nloc, P, L, h->xq.p, h->s12.p);
       h->s12_valid = true;
     }
-    switch (h->sweep_variant) {
-      case 21: return launch_cached<8, 4>(h, beg, end, order, L, cur, nxt, change, push);
-      case 22: return launch_cached<4, 12>(h, beg, end, order, L, cur, nxt, change, push);
-      default: return launch_cached<4, 8>(h, beg, end, order, L, cur, nxt, change, push);
-    }
+    if (h->sweep_variant == 21) return launch_cached<8, 4>(h, beg, end, order, L, cur, nxt, change, push);
+    return launch_cached<4, 8>(h, beg, end, order, L, cur, nxt, change, push);
   }
-#define V2(PF, WPB, MINB) \
-  return damp ? launch_v2<true, PF, WPB, MINB>(h, beg, end, order, P, L, cur, nxt, change, push) \
-              : launch_v2<false, PF, WPB, MINB>(h, beg, end, order, P, L, cur, nxt, change, push)
-  switch (order ? 1 : h->sweep_variant) {  // chunked sweeps need per-row partials: never the first version
-    case 0: {
-      const int nb = cdiv(end - beg, WARPS_PER_BLOCK);
-      LAUNCH(h, (k_sweep<true>), nb, BLOCK, beg, end, order, P, L, A, h->xq.p, cur, h->ef.p, nxt, h->partial.p);
-      return nb;
-    }
-    case 2: V2(2, 8, 3);
-    case 4: V2(1, 8, 5);
-    case 6: V2(1, 4, 10);
-#define V3(WPB, MINB) \
-  return damp ? launch_v3<true, WPB, MINB>(h, beg, end, order, P, L, cur, nxt, change) \
-              : launch_v3<false, WPB, MINB>(h, beg, end, order, P, L, cur, nxt, change)
-    case 11: V3(4, 6);
-    case 12: V3(4, 8);
-#undef V3
-    case 8: V2(3, 4, 10);
-    default: V2(1, 4, 8);
+  if (!order && h->sweep_variant == 0) {  // first version (kept as the simplest statement of the sweep; per-block partials)
+    const int nb = cdiv(end - beg, WARPS_PER_BLOCK);
+    LAUNCH(h, (k_sweep<true>), nb, BLOCK, beg, end, order, P, L, A, h->xq.p, cur, h->ef.p, nxt, h->partial.p);
+    return nb;
   }
-#undef V2
+  // matrix-free: no per-pair cache (used when 16 B per pair do not fit in HBM, or on request: variant 6)
+  return damp ? launch_v2<true, 1, 4, 10>(h, beg, end, order, P, L, cur, nxt, change, push)
+              : launch_v2<false, 1, 4, 10>(h, beg, end, order, P, L, cur, nxt, change, push);
 }
 
 template <int NV>

@@ -649,8 +649,8 @@ k_sweep(int pos_beg, int pos_end, const int *__restrict__ order, DevParams P, Li
 
 // Optimised list-mode sweep (same mathematics as k_sweep<true>):
 //   * reciprocal square root instead of sqrt + two divisions, damping polynomials in Horner form;
-//   * neighbour indices prefetched two iterations ahead and (PF == 2) the 32-byte position and dipole
-//     records one iteration ahead, so the dependent index -> gather chain overlaps the FP64 work;
+//   * neighbour indices prefetched two iterations ahead, so the dependent index -> gather chain overlaps
+//     the FP64 work (PF is kept as a template parameter of the launch table; only PF == 1 is instantiated);
 //   * DAMP is a template parameter: no per-pair branch on the damping type.
 // radial part of T: s1 = d1/r^3, s2 = -3 d2/r^5  (T mu = s1 mu + s2 (del.mu) del)
 template <bool DAMP>
@@ -714,36 +714,15 @@ k_sweep_list2(int pos_beg, int pos_end, const int *__restrict__ order, DevParams
     const double cutsq = P.pc.polar_cutsq;
     int jA = lane < cnt ? ld_index(row + lane) : -1;
     int jB = lane + 32 < cnt ? ld_index(row + lane + 32) : -1;
-    double4 xj = make_double4(0, 0, 0, 0), mj = xj;
-    if (PF == 2 && jA >= 0) {
-      xj = ld4(xq + jA);
-      mj = ld4(mu_in + jA);
-    }
     for (int k = lane; k < cnt; k += 32) {
       const int jC = (k + 64 < cnt) ? ld_index(row + k + 64) : -1;
-      double4 xn = make_double4(0, 0, 0, 0), mn = xn;
-      if (PF == 3 && jB >= 0) {  // pull next iteration's records into L1 without holding registers
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(xq + jB));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(mu_in + jB));
-      }
-      if (PF == 2) {
-        if (jB >= 0) {
-          xn = ld4(xq + jB);
-          mn = ld4(mu_in + jB);
-        }
-      } else {
-        xj = ld4(xq + jA);
-        mj = ld4(mu_in + jA);
-      }
+      const double4 xj = ld4(xq + jA);
+      const double4 mj = ld4(mu_in + jA);
       const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
       const double r2 = dx * dx + dy * dy + dz * dz;
       if (r2 < cutsq) induced_pair_fast<DAMP>(P.pc, dx, dy, dz, r2, mj, ex, ey, ez);
       jA = jB;
       jB = jC;
-      if (PF == 2) {
-        xj = xn;
-        mj = mn;
-      }
     }
     ex = warp_sum(ex);
     ey = warp_sum(ey);
@@ -758,67 +737,6 @@ k_sweep_list2(int pos_beg, int pos_end, const int *__restrict__ order, DevParams
       row_change[pos - pos_beg] = (nx - mi.x) * (nx - mi.x) + (ny - mi.y) * (ny - mi.y) + (nz - mi.z) * (nz - mi.z);
   }
   if (PUSH) push_row(push_dst, nx, ny, nz, mi.w);
-}
-
-// Two neighbours per lane per trip: two independent dependency chains (rsqrt -> exp -> accumulate) in
-// flight per thread, half the loop and prefetch overhead per pair.
-template <bool DAMP, int WPB, int MINB, bool CHANGE>
-__global__ void __launch_bounds__(WPB * 32, MINB)
-k_sweep_list3(int pos_beg, int pos_end, const int *__restrict__ order, DevParams P, ListRows L,
-              const double4 *__restrict__ xq, const double4 *__restrict__ mu_in, const double4 *__restrict__ ef,
-              double4 *__restrict__ mu_out, double *__restrict__ row_change)
-{
-  const int lane = threadIdx.x & 31;
-  const int pos = pos_beg + blockIdx.x * WPB + (threadIdx.x >> 5);
-  if (pos >= pos_end) return;
-  const int s = order ? order[pos] : pos;
-  const double4 xi = xq[s];
-  const double4 mi = mu_in[s];
-  double ex = 0, ey = 0, ez = 0, fx = 0, fy = 0, fz = 0;
-  if (mi.w != 0.0) {
-    const int *__restrict__ row = L.neigh + L.begin(s);
-    const int cnt = (int)(L.end(s) - L.begin(s));
-    const double cutsq = P.pc.polar_cutsq;
-    // indices of the current trip (a0,a1) and the next one (b0,b1)
-    int a0 = lane < cnt ? ld_index(row + lane) : -1;
-    int a1 = lane + 32 < cnt ? ld_index(row + lane + 32) : -1;
-    int b0 = lane + 64 < cnt ? ld_index(row + lane + 64) : -1;
-    int b1 = lane + 96 < cnt ? ld_index(row + lane + 96) : -1;
-    for (int k = lane; k < cnt; k += 64) {
-      const int c0 = (k + 128 < cnt) ? ld_index(row + k + 128) : -1;
-      const int c1 = (k + 160 < cnt) ? ld_index(row + k + 160) : -1;
-      const double4 x0 = ld4(xq + a0), m0 = ld4(mu_in + a0);
-      double4 x1 = x0, m1 = m0;
-      if (a1 >= 0) {
-        x1 = ld4(xq + a1);
-        m1 = ld4(mu_in + a1);
-      }
-      {
-        const double dx = xi.x - x0.x, dy = xi.y - x0.y, dz = xi.z - x0.z;
-        const double r2 = dx * dx + dy * dy + dz * dz;
-        if (r2 < cutsq) induced_pair_fast<DAMP>(P.pc, dx, dy, dz, r2, m0, ex, ey, ez);
-      }
-      if (a1 >= 0) {
-        const double dx = xi.x - x1.x, dy = xi.y - x1.y, dz = xi.z - x1.z;
-        const double r2 = dx * dx + dy * dy + dz * dz;
-        if (r2 < cutsq) induced_pair_fast<DAMP>(P.pc, dx, dy, dz, r2, m1, fx, fy, fz);
-      }
-      a0 = b0;
-      a1 = b1;
-      b0 = c0;
-      b1 = c1;
-    }
-    ex = warp_sum(ex + fx);
-    ey = warp_sum(ey + fy);
-    ez = warp_sum(ez + fz);
-  }
-  if (lane == 0) {
-    const double4 e = ef[s];
-    const double nx = mi.w * (e.x + ex), ny = mi.w * (e.y + ey), nz = mi.w * (e.z + ez);
-    mu_out[s] = make_double4(nx, ny, nz, mi.w);
-    if (CHANGE)
-      row_change[pos - pos_beg] = (nx - mi.x) * (nx - mi.x) + (ny - mi.y) * (ny - mi.y) + (nz - mi.z) * (nz - mi.z);
-  }
 }
 
 // Per-step cache of the radial scalars of every tight-list entry (16 B per pair).  The geometry is
