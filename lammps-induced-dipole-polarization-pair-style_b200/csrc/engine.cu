@@ -184,6 +184,9 @@ struct polb200_handle {
   DBuf<int> group_first, group_two, gneigh, gcount, tgneigh, tgcount;
   DBuf<unsigned long long> growstart;
   DBuf<double4> s12ab;           // per-step radial cache of the group rows: {s1a, s2a, s1b, s2b} per entry
+  DBuf<unsigned long long> gcstart;  // chunk-record layout of the same (TMA sweep): first record of every group row
+  DBuf<unsigned char> gcrec;
+  unsigned long long gchunks = 0;
   int ngroups = 0;
   unsigned long long gpairs = 0;
   bool groups_built = false, group_cache_valid = false;
@@ -536,6 +539,15 @@ static void rebuild(polb200_handle *h, const polb200_atoms *at)
     h->gcount.ensure(ngr + 1);
     LAUNCH(h, k_group_build<true>, ngb, BLOCK, h->ngroups, n, h->P, h->xq.p, h->tm.p, h->group_first.p, h->group_two.p,
            h->cl_start.p, h->cg_start.p, h->nstencil, h->stencil.p, h->cnt.p, h->growstart.p, h->gneigh.p, h->gcount.p);
+    // chunk-record layout for the TMA sweep
+    h->cnt.ensure(ngr + 1); h->gcstart.ensure(ngr + 2);
+    LAUNCH(h, k_group_chunk_count, cdiv(h->ngroups, 256), 256, h->ngroups, h->gcount.p, h->cnt.p);
+    CUDA_CHECK(cudaMemsetAsync(h->cnt.p + ngr, 0, sizeof(unsigned long long), h->stream));
+    exclusive_sum(h, (int)ngr + 1, h->cnt.p, h->gcstart.p);
+    unsigned long long nch = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&nch, h->gcstart.p + ngr, sizeof(nch), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    h->gchunks = nch;
     h->groups_built = true;
   }
 
@@ -644,17 +656,25 @@ static int launch_list_sweep(polb200_handle *h, int beg, int end, const int *ord
     // whole-system Jacobi sweep: two cell-row neighbours per warp
     if (!h->group_cache_valid) {
       bool fits = true;
-      if (h->s12ab.cap < h->gneigh.cap) {  // 32 B per group entry: only while it fits comfortably in free HBM
+      const bool chunked = h->sweep_variant >= 40;
+      const size_t need_b = chunked ? (size_t)h->gchunks * GCHUNK_BYTES : (size_t)h->gneigh.cap * 36;
+      if (chunked ? h->gcrec.cap < need_b : h->s12ab.cap < h->gneigh.cap) {  // only while it fits comfortably in free HBM
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
-        fits = (double)h->gneigh.cap * 36.0 < 0.6 * (double)free_b;
+        fits = (double)need_b < 0.6 * (double)free_b;
       }
       if (!fits) h->groups_built = false;
       else {
-        h->tgneigh.ensure(h->gneigh.cap); h->tgcount.ensure(h->ngroups + 1); h->s12ab.ensure(h->gneigh.cap);
+        h->tgcount.ensure(h->ngroups + 1);
+        if (chunked) h->gcrec.ensure(need_b + 64, 1.0);
+        else { h->tgneigh.ensure(h->gneigh.cap); h->s12ab.ensure(h->gneigh.cap); }
         const int ngb = cdiv(h->ngroups, WARPS_PER_BLOCK);
-        if (damp) LAUNCH(h, (k_group_cache<true>), ngb, BLOCK, h->ngroups, P, h->group_first.p, h->group_two.p, h->growstart.p, h->gcount.p, h->gneigh.p, h->xq.p, h->tgneigh.p, h->tgcount.p, h->s12ab.p);
-        else LAUNCH(h, (k_group_cache<false>), ngb, BLOCK, h->ngroups, P, h->group_first.p, h->group_two.p, h->growstart.p, h->gcount.p, h->gneigh.p, h->xq.p, h->tgneigh.p, h->tgcount.p, h->s12ab.p);
+#define GC(DA, CK) \
+  LAUNCH(h, (k_group_cache<DA, CK>), ngb, BLOCK, h->ngroups, P, h->group_first.p, h->group_two.p, h->growstart.p, h->gcount.p, \
+         h->gneigh.p, h->xq.p, h->tgneigh.p, h->tgcount.p, h->s12ab.p, h->gcstart.p, h->gcrec.p)
+        if (damp) { if (chunked) GC(true, true); else GC(true, false); }
+        else { if (chunked) GC(false, true); else GC(false, false); }
+#undef GC
         h->group_cache_valid = true;
       }
     }
@@ -681,7 +701,7 @@ static int launch_list_sweep(polb200_handle *h, int beg, int end, const int *ord
     const int grid = std::min(cdiv(h->ngroups, GW), std::max(per_sm, 1) * h->num_sms);                                  \
     kern<<<grid, GW * 32, smem, h->stream>>>(h->ngroups, h->group_first.p, h->group_two.p, h->growstart.p, h->tgneigh.p, \
                                              h->tgcount.p, h->s12ab.p, h->xq.p, cur, h->ef.p, nxt, h->partial.p, Q, h->flags.p + 4,     \
-                                             (h->alternate && (h->sweep_parity++ & 1)) ? 1 : 0);     \
+                                             (h->alternate && (h->sweep_parity++ & 1)) ? 1 : 0, h->gcstart.p, h->gcrec.p);     \
     h->launches++;                                                                                                      \
     CUDA_CHECK(cudaGetLastError());                                                                                     \
   } while (0)
@@ -1137,7 +1157,7 @@ void polb200_destroy(polb200_t *h)
     b->release();
   for (auto *b : {&h->xq, &h->mua, &h->mub, &h->ef, &h->f_pair, &h->f_pol}) b->release();
   h->group_first.release(); h->group_two.release(); h->gneigh.release(); h->gcount.release(); h->tgneigh.release(); h->tgcount.release();
-  h->growstart.release(); h->s12ab.release();
+  h->growstart.release(); h->s12ab.release(); h->gcstart.release(); h->gcrec.release();
   h->s12.release(); h->push_off.release(); h->push_ptr0.release(); h->push_ptr1.release();
   h->tm.release(); h->cnt.release(); h->rowstart.release(); h->cub_tmp.release(); h->rmin_bits.release();
   h->h_stage.release(); h->h_scal.release(); h->h_int.release();

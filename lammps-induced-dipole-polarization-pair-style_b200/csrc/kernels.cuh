@@ -1529,14 +1529,26 @@ k_group_build(int ngroups, int nloc, DevParams P, const double4 *__restrict__ xq
   if (FILL && lane == 0) rowcount[g] = (int)n;
 }
 
+// chunk-record layout of the tight group rows (TMA sweep): a row is a sequence of 64-entry records of
+// GCHUNK*36 bytes = [64 x 32 B scalars][64 x 4 B indices], contiguous in memory, so that ONE bulk copy
+// fetches a whole chunk (indices included) as a single 2304-byte request
+constexpr int GCHUNK = 64;
+constexpr int GCHUNK_BYTES = GCHUNK * 36;
+__global__ void k_group_chunk_count(int ngroups, const int *__restrict__ rowcount, unsigned long long *__restrict__ cnt)
+{
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < ngroups) cnt[g] = (unsigned long long)((rowcount[g] + GCHUNK - 1) / GCHUNK);
+}
+
 // per step: entries inside the dipole cutoff of either member at the current positions, compacted, with the
 // radial scalars {s1a, s2a, s1b, s2b} of both members (zero for a member the entry does not belong to)
-template <bool DAMP>
+template <bool DAMP, bool CHUNKED>
 __global__ void __launch_bounds__(BLOCK)
 k_group_cache(int ngroups, DevParams P, const int *__restrict__ group_first, const int *__restrict__ group_two,
               const unsigned long long *__restrict__ rowstart, const int *__restrict__ rowcount,
               const int *__restrict__ neigh, const double4 *__restrict__ xq, int *__restrict__ tneigh,
-              int *__restrict__ tcount, double4 *__restrict__ s12ab)
+              int *__restrict__ tcount, double4 *__restrict__ s12ab, const unsigned long long *__restrict__ cstart,
+              unsigned char *__restrict__ crec)
 {
   const int lane = threadIdx.x & 31;
   const int g = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
@@ -1567,9 +1579,15 @@ k_group_cache(int ngroups, DevParams P, const int *__restrict__ group_first, con
     }
     const unsigned m = __ballot_sync(FULL, ok);
     if (ok) {
-      const unsigned long long o = beg + n + __popc(m & ((1u << lane) - 1));
-      tneigh[o] = j;
-      s12ab[o] = sc;
+      const int pos = n + __popc(m & ((1u << lane) - 1));
+      if (CHUNKED) {
+        unsigned char *rec = crec + (cstart[g] + (unsigned long long)(pos / GCHUNK)) * GCHUNK_BYTES;
+        reinterpret_cast<double4 *>(rec)[pos % GCHUNK] = sc;
+        reinterpret_cast<int *>(rec + GCHUNK * 32)[pos % GCHUNK] = j;
+      } else {
+        tneigh[beg + pos] = j;
+        s12ab[beg + pos] = sc;
+      }
     }
     n += __popc(m);
   }
@@ -1734,8 +1752,10 @@ k_sweep_group_tma(int ngroups, const int *__restrict__ group_first, const int *_
                   const unsigned long long *__restrict__ rowstart, const int *__restrict__ tneigh,
                   const int *__restrict__ tcount, const double4 *__restrict__ s12ab, const double4 *__restrict__ xq,
                   const double4 *__restrict__ mu_in, const double4 *__restrict__ ef, double4 *__restrict__ mu_out,
-                  double *__restrict__ row_change, PushArgs Q, int *dbg, int reverse)
+                  double *__restrict__ row_change, PushArgs Q, int *dbg, int reverse,
+                  const unsigned long long *__restrict__ cstart, const unsigned char *__restrict__ crec)
 {
+  static_assert(CHUNK == GCHUNK, "the chunk-record layout is built for 64-entry chunks");
   // stage layout: CHUNK x 32 B scalars {s1a,s2a,s1b,s2b}, then CHUNK x 4 B indices.  (Splitting the two members
   // into separate 16-byte streams makes the LDS conflict free but needs a third bulk copy per chunk: measured slower.)
   constexpr int STAGE_BYTES = CHUNK * 36;
@@ -1762,23 +1782,14 @@ k_sweep_group_tma(int ngroups, const int *__restrict__ group_first, const int *_
     const int a = group_first[g];
     const bool two = group_two[g] != 0;
     const int b = two ? a + 1 : a;
-    const unsigned long long beg = rowstart[g];
     const int cnt = tcount[g];
     const int nchunks = (cnt + CHUNK - 1) / CHUNK;
-    const int *__restrict__ row = tneigh + beg;
-    const double4 *__restrict__ rs = s12ab + beg;
-    auto issue = [&](int c, unsigned slot) {  // lane 0: chunk c of this row into ring slot `slot`
-      const int e = min(CHUNK, cnt - c * CHUNK);
-      const unsigned e4 = (unsigned)((e + 3) & ~3);  // rows are padded to multiples of 4 entries (16-byte copies)
+    const unsigned char *__restrict__ recs = crec + cstart[g] * GCHUNK_BYTES;
+    auto issue = [&](int c, unsigned slot) {  // lane 0: chunk record c of this row into ring slot `slot`
       unsigned char *dst = ring + (size_t)slot * STAGE_BYTES;
-      mbar_expect_tx(bars + slot, e4 * 36u);
-      if (EVICT) {
-        bulk_g2s_stream(dst, rs + (size_t)c * CHUNK, e4 * 32u, bars + slot, l2pol);
-        bulk_g2s_stream(dst + CHUNK * 32, row + (size_t)c * CHUNK, e4 * 4u, bars + slot, l2pol);
-      } else {
-        bulk_g2s(dst, rs + (size_t)c * CHUNK, e4 * 32u, bars + slot);
-        bulk_g2s(dst + CHUNK * 32, row + (size_t)c * CHUNK, e4 * 4u, bars + slot);
-      }
+      mbar_expect_tx(bars + slot, (unsigned)GCHUNK_BYTES);
+      if (EVICT) bulk_g2s_stream(dst, recs + (size_t)c * GCHUNK_BYTES, GCHUNK_BYTES, bars + slot, l2pol);
+      else bulk_g2s(dst, recs + (size_t)c * GCHUNK_BYTES, GCHUNK_BYTES, bars + slot);
     };
     if (lane == 0) {
       const int pre = min(NSTAGE, nchunks);
@@ -1803,14 +1814,6 @@ k_sweep_group_tma(int ngroups, const int *__restrict__ group_first, const int *_
         const bool live = c * CHUNK + t * 32 + lane < cnt;
         j[t] = live ? ix_s[t * 32 + lane] : a;
         sc[t] = live ? sc_s[t * 32 + lane] : make_double4(0, 0, 0, 0);
-#ifdef POLB200_TMA_DEBUG
-        if (live) {
-          const int jj = row[(size_t)c * CHUNK + t * 32 + lane];
-          const double4 ss = rs[(size_t)c * CHUNK + t * 32 + lane];
-          if (jj != j[t]) atomicAdd(dbg, 1);
-          if (ss.x != sc[t].x || ss.y != sc[t].y || ss.z != sc[t].z || ss.w != sc[t].w) atomicAdd(dbg + 1, 1);
-        }
-#endif
       }
 #pragma unroll
       for (int t = 0; t < TRIPS; t++) {
