@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define POLB200_ABI_VERSION 1
+#define POLB200_ABI_VERSION 2
 
 typedef struct polb200_handle polb200_t;
 
@@ -29,7 +29,7 @@ enum {
   POLB200_ERR_ARG = 1,      /* message = the reference's error->all text, e.g. "Illegal pair_style command" */
   POLB200_ERR_CUDA = 2,     /* CUDA runtime failure or no device */
   POLB200_ERR_STATE = 3,    /* call order (e.g. compute before init) */
-  POLB200_ERR_UNSUPPORTED = 4, /* triclinic box, per-atom tallies, ... */
+  POLB200_ERR_UNSUPPORTED = 4, /* triclinic box, newton_pair off, ... */
   POLB200_ERR_OVERFLOW = 5, /* neighbor capacity ("Neighbor list overflow, boost neigh_modify one") */
   POLB200_ERR_NAN = 6       /* "Non-numeric positions - simulation unstable" (src/nbin.cpp:120-121) */
 };
@@ -118,6 +118,10 @@ typedef struct {
   const int *special;       /* atom->special [nlocal][maxspecial] (tags) or NULL */
   int maxspecial;
   int on_device;            /* 0: all pointers are host memory; 1: all are device memory on this GPU */
+  /* per-atom tallies (Pair::eatom / Pair::vatom, src/pair.h:38), accumulated (+=); required when the
+   * per-atom bits of eflag / vflag are set (eflag & 2, vflag & 4), ignored otherwise.  ABI version 2. */
+  double *eatom;            /* [nlocal] */
+  double *vatom;            /* [nlocal][6]  xx yy zz xy xz yz */
 } polb200_atoms;
 
 typedef struct {
@@ -137,7 +141,9 @@ typedef struct {
  * the reference's own rebuild schedule itself (Neighbor::decide/check_distance,
  * src/neighbor.cpp:1923-2001: every/delay/check, half-skin displacement trigger).
  * eflag/vflag use LAMMPS' encoding (src/integrate.cpp:122-157): eflag&1 global energy,
- * vflag%4 == 1 pairwise virial, == 2 F.r virial; per-atom bits => POLB200_ERR_UNSUPPORTED. */
+ * vflag%4 == 1 pairwise virial, == 2 F.r virial; eflag & 2 / vflag & 4 request the per-atom tallies of
+ * Pair::ev_tally / ev_tally_xyz (half of every pair's energy and virial to each of its atoms; the
+ * polarization terms contribute to the per-atom virial only, as in the reference). */
 int polb200_compute(polb200_t *h, const polb200_atoms *atoms, int eflag, int vflag, int ago,
                     polb200_result *out);
 

@@ -194,6 +194,7 @@ struct polb200_handle {
   bool s12_valid = false;
   DBuf<char> cub_tmp;
   DBuf<double> partial, scal;
+  DBuf<double> ea_row, va_pair_row, va_pol_row, c_eatom, c_vatom;  // per-atom tallies (sorted order / caller order)
   DBuf<int> flags;
   DBuf<double> metric, metric2;
   DBuf<int> ranked, ranked_in;
@@ -767,8 +768,9 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
   if (!st.initialized) throw StyleError{POLB200_ERR_STATE, "polb200_init has not been called"};
   if (!h->params_uploaded) upload_params(h);
   if (!h->box_set) throw StyleError{POLB200_ERR_STATE, "polb200_set_box has not been called"};
-  if ((eflag / 2) || (vflag / 4))
-    throw StyleError{POLB200_ERR_UNSUPPORTED, "per-atom energy/virial tallies are not implemented on the B200 path"};
+  const bool eflag_atom = (eflag / 2) != 0, vflag_atom = (vflag / 4) != 0;  // src/pair.cpp:763-771
+  if ((eflag_atom && !at->eatom) || (vflag_atom && !at->vatom))
+    throw StyleError{POLB200_ERR_ARG, "per-atom tallies requested (eflag & 2 / vflag & 4) without eatom / vatom arrays"};
   const int n = at->nlocal;
   memset(out, 0, sizeof(*out));
   const bool comm = h->comm.active;
@@ -795,7 +797,7 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
 
   const int eflag_global = eflag & 1;
   int vflag_global = vflag % 4;
-  const bool evflag = eflag_global || vflag_global;
+  const bool evflag = eflag_global || vflag_global || eflag_atom || vflag_atom;
   const bool vpair = vflag_global == 1;  // pairwise tallies; 2 = F.r (src/pair.cpp:809-815)
 
   CUDA_CHECK(cudaEventRecord(h->ev[0], h->stream));
@@ -835,13 +837,19 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
     L = ListRows{h->rowstart.p, h->tneigh.p, h->tcount.p};
   }
 
+  double *ea_ptr = nullptr, *vp_ptr = nullptr, *vq_ptr = nullptr;
+  if (eflag_atom) { h->ea_row.ensure(n); ea_ptr = h->ea_row.p; }
+  if (vflag_atom) {
+    h->va_pair_row.ensure((size_t)6 * n); h->va_pol_row.ensure((size_t)6 * n);
+    vp_ptr = h->va_pair_row.p; vq_ptr = h->va_pol_row.p;
+  }
   // ---- stage 2: LJ + Coulomb (+ static field) ----
   if (list_mode) {
-    if (evflag) LAUNCH(h, (k_pair<true, true>), nrowblocks, BLOCK, n, P, h->xq.p, h->tm.p, L, h->f_pair.p, h->ef.p, h->partial.p);
-    else LAUNCH(h, (k_pair<false, true>), nrowblocks, BLOCK, n, P, h->xq.p, h->tm.p, L, h->f_pair.p, h->ef.p, h->partial.p);
+    if (evflag) LAUNCH(h, (k_pair<true, true>), nrowblocks, BLOCK, n, P, h->xq.p, h->tm.p, L, h->f_pair.p, h->ef.p, h->partial.p, ea_ptr, vp_ptr);
+    else LAUNCH(h, (k_pair<false, true>), nrowblocks, BLOCK, n, P, h->xq.p, h->tm.p, L, h->f_pair.p, h->ef.p, h->partial.p, ea_ptr, vp_ptr);
   } else {
-    if (evflag) LAUNCH(h, (k_pair<true, false>), nrowblocks, BLOCK, n, P, h->xq.p, h->tm.p, L, h->f_pair.p, h->ef.p, h->partial.p);
-    else LAUNCH(h, (k_pair<false, false>), nrowblocks, BLOCK, n, P, h->xq.p, h->tm.p, L, h->f_pair.p, h->ef.p, h->partial.p);
+    if (evflag) LAUNCH(h, (k_pair<true, false>), nrowblocks, BLOCK, n, P, h->xq.p, h->tm.p, L, h->f_pair.p, h->ef.p, h->partial.p, ea_ptr, vp_ptr);
+    else LAUNCH(h, (k_pair<false, false>), nrowblocks, BLOCK, n, P, h->xq.p, h->tm.p, L, h->f_pair.p, h->ef.p, h->partial.p, ea_ptr, vp_ptr);
   }
   if (evflag) reduce_partials<NPAIR_PART>(h, nrowblocks, h->scal.p + S_PAIR, 0);
   if (!list_mode) LAUNCH(h, k_static_allpairs, nrowblocks, BLOCK, n, P, h->xq.p, h->tm.p, h->perm.p, h->ef.p);
@@ -979,8 +987,15 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
   CUDA_CHECK(cudaEventRecord(h->ev[3], h->stream));
 
   // ---- stage 4: polarization forces ----
-#define POLFORCE(LISTM, EV, VP) \
-  LAUNCH(h, (k_polforce<LISTM, EV, VP>), nrowblocks, BLOCK, n, P, L, A, h->xq.p, h->mua.p, h->tm.p, h->f_pol.p, h->partial.p)
+#define POLFORCE(LISTM, EV, VP)                                                                                          \
+  do {                                                                                                                   \
+    if (vflag_atom)                                                                                                      \
+      LAUNCH(h, (k_polforce<LISTM, EV, VP, true>), nrowblocks, BLOCK, n, P, L, A, h->xq.p, h->mua.p, h->tm.p, h->f_pol.p, \
+             h->partial.p, vq_ptr);                                                                                      \
+    else                                                                                                                 \
+      LAUNCH(h, (k_polforce<LISTM, EV, VP, false>), nrowblocks, BLOCK, n, P, L, A, h->xq.p, h->mua.p, h->tm.p,            \
+             h->f_pol.p, h->partial.p, (double *)nullptr);                                                               \
+  } while (0)
   // the reference tallies polarization energies whenever eflag is set, virial via F.r or pairwise
   const bool ev4 = evflag;
   if (list_mode) {
@@ -992,12 +1007,19 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
     else if (vpair) POLFORCE(false, true, true);
     else POLFORCE(false, true, false);
   }
+#undef POLFORCE
   if (ev4) reduce_partials<NPOL_PART>(h, nrowblocks, h->scal.p + S_POL, 0);
 
   // ---- stage 5: outputs ----
   h->c_f.ensure((size_t)3 * n); h->c_ef.ensure((size_t)3 * n);
   LAUNCH(h, k_scatter_out, cdiv(n, 256), 256, n, h->perm.p, h->f_pair.p, h->f_pol.p, h->mua.p, h->ef.p, h->c_f.p,
          h->c_mu.p, h->c_ef.p);
+  if (eflag_atom || vflag_atom) {
+    if (eflag_atom) h->c_eatom.ensure(n);
+    if (vflag_atom) h->c_vatom.ensure((size_t)6 * n);
+    LAUNCH(h, k_scatter_atomev, cdiv(n, 256), 256, n, h->perm.p, ea_ptr, vp_ptr, vq_ptr, eflag_atom ? h->c_eatom.p : nullptr,
+           vflag_atom ? h->c_vatom.p : nullptr);
+  }
   CUDA_CHECK(cudaEventRecord(h->ev[4], h->stream));
   CUDA_CHECK(cudaMemcpyAsync(h->h_scal.p, h->scal.p, S_N * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   h->h_int.ensure(8);
@@ -1005,14 +1027,19 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
   if (dev) {
     // device-resident caller: f += pair force, mu/ef overwritten, all on the stream
     LAUNCH(h, k_add_inplace, cdiv((long)3 * n, 256), 256, (long)3 * n, h->c_f.p, at->f);
+    if (eflag_atom) LAUNCH(h, k_add_inplace, cdiv((long)n, 256), 256, (long)n, h->c_eatom.p, at->eatom);
+    if (vflag_atom) LAUNCH(h, k_add_inplace, cdiv((long)6 * n, 256), 256, (long)6 * n, h->c_vatom.p, at->vatom);
     CUDA_CHECK(cudaMemcpyAsync(at->mu, h->c_mu.p, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     if (at->ef_static)
       CUDA_CHECK(cudaMemcpyAsync(at->ef_static, h->c_ef.p, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     CUDA_CHECK(cudaEventRecord(h->ev[5], h->stream));
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
   } else {
-    h->h_stage.ensure((size_t)3 * n);
+    h->h_stage.ensure((size_t)3 * n + (eflag_atom ? n : 0) + (vflag_atom ? (size_t)6 * n : 0));
     CUDA_CHECK(cudaMemcpyAsync(h->h_stage.p, h->c_f.p, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    double *h_ea = h->h_stage.p + (size_t)3 * n, *h_va = h_ea + (eflag_atom ? n : 0);
+    if (eflag_atom) CUDA_CHECK(cudaMemcpyAsync(h_ea, h->c_eatom.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (vflag_atom) CUDA_CHECK(cudaMemcpyAsync(h_va, h->c_vatom.p, (size_t)6 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CUDA_CHECK(cudaMemcpyAsync(at->mu, h->c_mu.p, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     if (at->ef_static)
       CUDA_CHECK(cudaMemcpyAsync(at->ef_static, h->c_ef.p, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -1021,6 +1048,10 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
     double *f = at->f;
     const double *a = h->h_stage.p;
     for (size_t k = 0; k < (size_t)3 * n; k++) f[k] += a[k];
+    if (eflag_atom)
+      for (size_t k = 0; k < (size_t)n; k++) at->eatom[k] += h_ea[k];
+    if (vflag_atom)
+      for (size_t k = 0; k < (size_t)6 * n; k++) at->vatom[k] += h_va[k];
   }
 
   sweep_events_collect(h);
@@ -1148,7 +1179,8 @@ void polb200_destroy(polb200_t *h)
     c.active = false;
   }
   for (auto *b : {&h->c_x, &h->c_q, &h->c_alpha, &h->c_mu, &h->c_f, &h->c_ef, &h->c_xhold, &h->d_coeff,
-                  &h->d_tables, &h->partial, &h->scal, &h->metric, &h->metric2})
+                  &h->d_tables, &h->partial, &h->scal, &h->metric, &h->metric2, &h->ea_row, &h->va_pair_row,
+                  &h->va_pol_row, &h->c_eatom, &h->c_vatom})
     b->release();
   for (auto *b : {&h->c_type, &h->c_mol, &h->c_tag, &h->c_nspecial, &h->c_special, &h->tag, &h->perm,
                   &h->invperm, &h->keys, &h->keys2, &h->vals, &h->vals2, &h->g_owner_u, &h->g_shift_u,

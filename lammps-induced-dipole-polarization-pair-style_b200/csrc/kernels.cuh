@@ -452,7 +452,8 @@ constexpr int NPAIR_PART = 8;
 template <bool EVFLAG, bool FIELD>
 __global__ void __launch_bounds__(BLOCK, 3)
 k_pair(int nloc, DevParams P, const double4 *__restrict__ xq, const int2 *__restrict__ tm, ListRows L,
-       double4 *__restrict__ f_pair, double4 *__restrict__ ef, double *__restrict__ partial)
+       double4 *__restrict__ f_pair, double4 *__restrict__ ef, double *__restrict__ partial,
+       double *__restrict__ eatom_row, double *__restrict__ vatom_row)
 {
   const int lane = threadIdx.x & 31;
   const int s = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
@@ -521,6 +522,12 @@ k_pair(int nloc, DevParams P, const double4 *__restrict__ xq, const int2 *__rest
   if (EVFLAG) {
 #pragma unroll
     for (int k = 0; k < NPAIR_PART; k++) acc[k] = 0.5 * warp_sum(acc[k]);
+    // per-atom tallies (Pair::ev_tally, src/pair.cpp:888-947): the row atom's half of every pair it is in
+    if (lane == 0 && s < nloc) {
+      if (eatom_row) eatom_row[s] = acc[0] + acc[1];
+      if (vatom_row)
+        for (int k = 0; k < 6; k++) vatom_row[6 * (size_t)s + k] = acc[2 + k];
+    }
     block_reduce_store<NPAIR_PART>(acc, partial);
   }
 }
@@ -1026,11 +1033,11 @@ k_rank_metric(int nloc, ListRows L, const double4 *__restrict__ xq, const double
 // per-block partials: u_self, u_ef, u_dd, then the polarization virial (6)
 constexpr int NPOL_PART = 9;
 
-template <bool LIST, bool EVFLAG, bool VPAIR>
+template <bool LIST, bool EVFLAG, bool VPAIR, bool VATOM = false>
 __global__ void __launch_bounds__(BLOCK, 3)
 k_polforce(int nloc, DevParams P, ListRows L, AllPairRows A, const double4 *__restrict__ xq,
            const double4 *__restrict__ mua, const int2 *__restrict__ tm, double4 *__restrict__ f_pol,
-           double *__restrict__ partial)
+           double *__restrict__ partial, double *__restrict__ vatom_row = nullptr)
 {
   const int lane = threadIdx.x & 31;
   const int s = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
@@ -1040,6 +1047,7 @@ k_polforce(int nloc, DevParams P, ListRows L, AllPairRows A, const double4 *__re
     const double4 mi = mua[s];
     const int moli = tm[s].y;
     double fx = 0, fy = 0, fz = 0;
+    double va[6] = {0, 0, 0, 0, 0, 0};  // per-atom virial of the row atom (VATOM)
     PolPairIn in;
     const bool molecules = P.pc.has_molecules != 0;
     auto visit = [&](int j, const double4 &xj, bool i_is_a, double dx, double dy, double dz) {
@@ -1058,6 +1066,11 @@ k_polforce(int nloc, DevParams P, ListRows L, AllPairRows A, const double4 *__re
       pol_force_pair(P.pc, in, EVFLAG, px, py, pz, uef, udd);
       if (!i_is_a) { px = -px; py = -py; pz = -pz; }
       fx += px; fy += py; fz += pz;
+      if (VATOM) {  // ev_tally_xyz, per-atom part (src/pair.cpp:1041-1087): half of del (x) F to each atom
+        const double sx = i_is_a ? dx : -dx, sy = i_is_a ? dy : -dy, sz = i_is_a ? dz : -dz;
+        va[0] += 0.5 * sx * px; va[1] += 0.5 * sy * py; va[2] += 0.5 * sz * pz;
+        va[3] += 0.5 * sx * py; va[4] += 0.5 * sx * pz; va[5] += 0.5 * sy * pz;
+      }
       if (EVFLAG) {
         acc[1] += 0.5 * uef;  // every pair is visited from both of its atoms
         acc[2] += 0.5 * udd;
@@ -1098,6 +1111,12 @@ k_polforce(int nloc, DevParams P, ListRows L, AllPairRows A, const double4 *__re
     fx = warp_sum(fx);
     fy = warp_sum(fy);
     fz = warp_sum(fz);
+    if (VATOM) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) va[k] = warp_sum(va[k]);
+      if (lane == 0)
+        for (int k = 0; k < 6; k++) vatom_row[6 * (size_t)s + k] = va[k];
+    }
     if (lane == 0) {
       f_pol[s] = make_double4(fx, fy, fz, 0.0);
       if (EVFLAG) {
@@ -1141,6 +1160,20 @@ __global__ void k_scatter_out(int nloc, const int *__restrict__ perm, const doub
   ef_out[3 * c] = e.x;
   ef_out[3 * c + 1] = e.y;
   ef_out[3 * c + 2] = e.z;
+}
+
+// per-atom tallies back in caller order: eatom (pair part only: the reference passes zero energies to
+// ev_tally_xyz) and vatom = pair part + polarization part
+__global__ void k_scatter_atomev(int nloc, const int *__restrict__ perm, const double *__restrict__ eatom_row,
+                                 const double *__restrict__ vpair_row, const double *__restrict__ vpol_row,
+                                 double *__restrict__ eatom_out, double *__restrict__ vatom_out)
+{
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nloc) return;
+  const int c = perm[s];
+  if (eatom_out) eatom_out[c] = eatom_row[s];
+  if (vatom_out)
+    for (int k = 0; k < 6; k++) vatom_out[6 * (size_t)c + k] = vpair_row[6 * (size_t)s + k] + vpol_row[6 * (size_t)s + k];
 }
 
 // deterministic final reduction of nblocks x NV per-block partials: one CTA, fixed tree

@@ -209,6 +209,8 @@ void PairLJCutCoulLongPolarization::compute(int eflag, int vflag)
     }
   }
   a.on_device = 0;
+  a.eatom = eflag_atom ? eatom : NULL;           // Pair::eatom / vatom, zeroed by ev_setup (src/pair.cpp:789-804)
+  a.vatom = (vflag_atom && a.nlocal > 0) ? vatom[0] : NULL;
 
   polb200_result res;
   CHECK(polb200_compute(handle, &a, eflag, vflag, neighbor->ago, &res));

@@ -41,7 +41,8 @@ class Atoms(C.Structure):
     _fields_ = [("nlocal", C.c_int), ("x", C.c_void_p), ("q", C.c_void_p), ("type", C.c_void_p),
                 ("molecule", C.c_void_p), ("tag", C.c_void_p), ("alpha", C.c_void_p), ("mu", C.c_void_p),
                 ("ef_static", C.c_void_p), ("f", C.c_void_p), ("nspecial", C.c_void_p),
-                ("special", C.c_void_p), ("maxspecial", C.c_int), ("on_device", C.c_int)]
+                ("special", C.c_void_p), ("maxspecial", C.c_int), ("on_device", C.c_int),
+                ("eatom", C.c_void_p), ("vatom", C.c_void_p)]
 
 
 class Result(C.Structure):
@@ -278,7 +279,7 @@ class PairStyle:
 
     # ---- hot path ----
     def compute(self, x, q, type_, alpha, mu, f, molecule=None, tag=None, ef_static=None, nspecial=None,
-                special=None, eflag=1, vflag=2, ago=0):
+                special=None, eflag=1, vflag=2, ago=0, eatom=None, vatom=None):
         """One compute() call on HOST numpy buffers (mu and f updated in place).  Returns Result."""
         n = x.shape[0]
         a = Atoms()
@@ -297,6 +298,7 @@ class PairStyle:
         a.mu, a.f, a.ef_static = ptr(mu, np.float64), ptr(f, np.float64), ptr(ef_static, np.float64)
         a.nspecial, a.special = ptr(nspecial, np.int32), ptr(special, np.int32)
         a.maxspecial = special.shape[1] if special is not None else 0
+        a.eatom, a.vatom = ptr(eatom, np.float64), ptr(vatom, np.float64)
         a.on_device = 0
         res = Result()
         self._check(lib().polb200_compute(self._h, C.byref(a), eflag, vflag, ago, C.byref(res)))
@@ -306,7 +308,8 @@ class PairStyle:
         """compute() on DEVICE pointers (dict name -> int address), e.g. torch tensors' data_ptr()."""
         a = Atoms()
         a.nlocal = n
-        for k in ("x", "q", "type", "molecule", "tag", "alpha", "mu", "ef_static", "f", "nspecial", "special"):
+        for k in ("x", "q", "type", "molecule", "tag", "alpha", "mu", "ef_static", "f", "nspecial", "special", "eatom",
+                  "vatom"):
             setattr(a, k, ptrs.get(k))
         a.maxspecial = maxspecial
         a.on_device = 1

@@ -59,6 +59,13 @@ CASES = [
     ("h2_diverge", "Bulk H2", "h2.input", H2_STYLE.replace("max_iterations 100", "max_iterations 3"),
      [], [0], 0),
     ("h2_notable", "Bulk H2", "h2.input", None, ["pair_modify table 0"], [0], 0),
+    # per-atom energy / virial tallies (Pair::ev_tally, ev_tally_xyz): requested through pe/atom + stress/atom
+    ("h2_peratom", "Bulk H2", "h2.input",
+     H2_STYLE.replace("polar_gs_ranked yes", "polar_gs_ranked no fixed_iteration yes").replace(
+         "max_iterations 100", "max_iterations 5"),
+     ["compute pea all pe/atom pair", "compute sta all stress/atom NULL pair", "compute spe all reduce sum c_pea",
+      "compute sst all reduce sum c_sta[1] c_sta[2] c_sta[3] c_sta[4] c_sta[5] c_sta[6]",
+      "thermo_style custom step pe c_spe c_sst[1] c_sst[2] c_sst[3] c_sst[4] c_sst[5] c_sst[6]"], [0], 0),
     ("methane_default", "MOF5+Methane", "MOF5+PCRC.restart.pdb.input", None, [], [0, 1, 2], 2),
     # shipped input aborts in fix rigid; single-point compute() with the integrator swapped
     ("co2_singlepoint", "MOF5+CO2", "co2_mof5.restart.pdb.input", None, ["__NVE__"], [0], 0),
@@ -128,6 +135,13 @@ def run_case(name, exdir, inp, style, extra, keep, nrun):
             pair_style=pair_style, pair_coeff="\n".join(pair_coeffs), pair_modify="\n".join(pair_modify),
             step=step, ncoultablebits=int(d["ncoultablebits"][0]),
         )
+        for key, width in (("eatom", 1), ("vatom", 6)):
+            if key in d:  # fold ghost tallies onto their owners (what reverse_comm of the computes does)
+                a = d[key].reshape(-1, width)
+                own = a[:nl].copy()
+                for g in range(nl, len(tag)):
+                    own[loc[int(tag[g])]] += a[g]
+                fx[key] = own if width > 1 else own[:, 0]
         if ms:
             fx["nspecial"] = d["nspecial"].reshape(nl, 3)
             fx["special"] = d["special"].reshape(nl, ms)

@@ -759,6 +759,19 @@ int polref_compute(const polref_params *p, int nlocal, int nghost, const double 
           virial[4] += delx * delz * fpair;
           virial[5] += dely * delz * fpair;
         }
+        if (p->eatom) { /* src/pair.cpp:888-892 */
+          double epairhalf = 0.5 * (evdwl + ecoul);
+          p->eatom[i] += epairhalf;
+          p->eatom[j] += epairhalf;
+        }
+        if (p->vatom) { /* src/pair.cpp:894-947 */
+          double v[6] = {delx * delx * fpair, dely * dely * fpair, delz * delz * fpair,
+                         delx * dely * fpair, delx * delz * fpair, dely * delz * fpair};
+          for (int k = 0; k < 6; k++) {
+            p->vatom[6 * i + k] += 0.5 * v[k];
+            p->vatom[6 * j + k] += 0.5 * v[k];
+          }
+        }
       }
     }
   }
@@ -1011,6 +1024,14 @@ int polref_compute(const polref_params *p, int nlocal, int nghost, const double 
         virial[3] += delx * forcecouly;
         virial[4] += delx * forcecoulz;
         virial[5] += dely * forcecoulz;
+      }
+      if (p->vatom) { /* src/pair.cpp:1041-1087: energies passed as 0, so eatom is untouched */
+        double v[6] = {delx * forcecoulx, dely * forcecouly, delz * forcecoulz,
+                       delx * forcecouly, delx * forcecoulz, dely * forcecoulz};
+        for (int k = 0; k < 6; k++) {
+          p->vatom[6 * i + k] += 0.5 * v[k];
+          p->vatom[6 * j + k] += 0.5 * v[k];
+        }
       }
     }
   }

@@ -51,6 +51,10 @@ typedef struct {
   /* orthogonal box */
   double boxlo[3], boxhi[3];
   int periodic[3];
+  /* optional per-atom tallies of Pair::ev_tally / ev_tally_xyz (src/pair.cpp:854-949,1001-1089), newton on:
+   * half of every pair's energy and virial to each of its two atoms.  (nlocal+nghost) and (nlocal+nghost)*6
+   * doubles, accumulated (+=); NULL = off (eflag_atom / vflag_atom not set). */
+  double *eatom, *vatom;
 } polref_params;
 
 typedef struct {

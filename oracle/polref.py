@@ -37,6 +37,7 @@ class Params(C.Structure):
         ("polar_damp", C.c_double), ("polar_precision", C.c_double), ("polar_gamma", C.c_double),
         ("polar_cut", C.c_double), ("gs_chunks", C.c_int),
         ("boxlo", C.c_double * 3), ("boxhi", C.c_double * 3), ("periodic", C.c_int * 3),
+        ("eatom", dp), ("vatom", dp),
     ]
 
 
@@ -306,6 +307,12 @@ def compute(sysm, style, mu_in=None, eflag=1, vflag=2, use_matrix=False, trace_m
     ranked = np.zeros(n, dtype=np.int32)
     q_all, type_all = f64(sysm.q[allidx]), i32(sysm.type[allidx])
     mol_all, alpha_all = i32(sysm.molecule[allidx]), f64(sysm.alpha[allidx])
+    eatom = np.zeros(n + ng) if (eflag // 2) else None   # per-atom tallies (eflag_atom / vflag_atom)
+    vatom = np.zeros((n + ng, 6)) if (vflag // 4) else None
+    if eatom is not None:
+        p.eatom = _d(eatom)
+    if vatom is not None:
+        p.vatom = _d(vatom)
     rc = L.polref_compute(C.byref(p), n, ng, _d(f64(xall)), _d(q_all), _i(type_all), _i(mol_all),
                           _d(alpha_all), n, None, _i(numneigh), _l(first), _i(neigh), _d(mu), _d(ef), _d(f),
                           eflag, vflag, int(use_matrix), C.byref(res), _d(trace), trace_max, _i(ranked))
@@ -313,7 +320,16 @@ def compute(sysm, style, mu_in=None, eflag=1, vflag=2, use_matrix=False, trace_m
         raise RuntimeError("polref_compute failed")
     f_owner = f[:n].copy()
     np.add.at(f_owner, owner, f[n:])
-    return dict(mu=mu, ef_static=ef, f=f_owner, f_all=f, eng_vdwl=res.eng_vdwl, eng_coul=res.eng_coul,
+    extra = {}
+    if eatom is not None:
+        e_own = eatom[:n].copy()
+        np.add.at(e_own, owner, eatom[n:])
+        extra["eatom"] = e_own
+    if vatom is not None:
+        v_own = vatom[:n].copy()
+        np.add.at(v_own, owner, vatom[n:])
+        extra["vatom"] = v_own
+    return dict(**extra, mu=mu, ef_static=ef, f=f_owner, f_all=f, eng_vdwl=res.eng_vdwl, eng_coul=res.eng_coul,
                 eng_pol=res.eng_pol, virial=np.array(res.virial[:]), iterations=res.iterations,
                 diverged=res.diverged, u_self=res.u_self, u_ef=res.u_ef, u_dd=res.u_dd, rmin=res.rmin,
                 trace=trace[: min(trace_max, res.iterations + 1)], ranked=ranked,

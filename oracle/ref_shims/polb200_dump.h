@@ -78,6 +78,8 @@ static inline void post(LAMMPS_NS::Atom *atom, LAMMPS_NS::Domain *domain, LAMMPS
   rec(fp,"mu_in",'d',3LL*nlocal,mu_in.data());
   rec(fp,"mu_out",'d',3LL*nlocal,&atom->mu_induced[0][0]);
   rec(fp,"ef_static",'d',3LL*nlocal,&atom->ef_static[0][0]);
+  if (eflag / 2) rec(fp,"eatom",'d',(long long)nall,force->pair->eatom);
+  if (vflag / 4) rec(fp,"vatom",'d',6LL*nall,&force->pair->vatom[0][0]);
   rec(fp,"f",'d',3LL*nall,&atom->f[0][0]);
   int nn = (nt+1)*(nt+1);
   rec(fp,"cutsq",'d',nn,&cutsq[0][0]); rec(fp,"cut_ljsq",'d',nn,&cut_ljsq[0][0]);

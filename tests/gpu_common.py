@@ -48,18 +48,25 @@ def c(a, dt):
     return np.ascontiguousarray(a, dtype=dt)
 
 
-def run_fixture(style, fx, ago=0, mu_in=None):
-    """One compute() of the product on the fixture's inputs; returns (Result, mu, ef, f)."""
+def run_fixture(style, fx, ago=0, mu_in=None, peratom=None):
+    """One compute() of the product on the fixture's inputs; returns (Result, mu, ef, f).
+    peratom: dict that receives the per-atom tallies "eatom" / "vatom" when the fixture's flags ask for them."""
     n = fx["x"].shape[0]
     mu = c(fx["mu_in"] if mu_in is None else mu_in, np.float64).copy()
     f = np.zeros((n, 3))
     ef = np.zeros((n, 3))
+    kw = {}
+    if peratom is not None:
+        if int(fx["eflag"]) // 2:
+            kw["eatom"] = peratom["eatom"] = np.zeros(n)
+        if int(fx["vflag"]) // 4:
+            kw["vatom"] = peratom["vatom"] = np.zeros((n, 6))
     res = style.compute(c(fx["x"], np.float64), c(fx["q"], np.float64), c(fx["type"], np.int32),
                         c(fx["alpha"], np.float64), mu, f, molecule=c(fx["molecule"], np.int32),
                         tag=c(fx["tag"], np.int32), ef_static=ef,
                         nspecial=c(fx["nspecial"], np.int32) if "nspecial" in fx else None,
                         special=c(fx["special"], np.int32) if "special" in fx else None,
-                        eflag=int(fx["eflag"]), vflag=int(fx["vflag"]), ago=ago)
+                        eflag=int(fx["eflag"]), vflag=int(fx["vflag"]), ago=ago, **kw)
     return res, mu, ef, f
 
 
