@@ -86,6 +86,10 @@ typedef struct {
 int polb200_init(polb200_t *h, const polb200_env *env);
 /* value init_one(i,j) returned (the pair cutoff); valid after polb200_init */
 int polb200_init_one(const polb200_t *h, int i, int j, double *cut);
+/* pair_modify tail yes: etail_ij / ptail_ij of init_one (pol.cpp:897-918); count_i / count_j = number of atoms
+ * of types i and j over all ranks (the reference MPI_Allreduces them; the caller owns that sum).  Zero unless
+ * `pair_modify tail yes` was given. */
+int polb200_tail(const polb200_t *h, int i, int j, double count_i, double count_j, double *etail_ij, double *ptail_ij);
 /* extract(), pol.cpp:1101-1109: "cut_coul" (dim 0), "epsilon"/"sigma" (dim 2, (ntypes+1)^2 row-major).
  * Returns a pointer into host memory owned by the handle, or NULL. */
 const void *polb200_extract(const polb200_t *h, const char *name, int *dim);

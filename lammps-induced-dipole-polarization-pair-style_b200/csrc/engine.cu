@@ -1241,6 +1241,14 @@ int polb200_init_one(const polb200_t *h, int i, int j, double *cut)
   return POLB200_OK;
 }
 
+int polb200_tail(const polb200_t *h, int i, int j, double count_i, double count_j, double *etail_ij, double *ptail_ij)
+{
+  if (!h || !etail_ij || !ptail_ij || !h->style.initialized || i < 1 || j < 1 || i > h->style.ntypes || j > h->style.ntypes)
+    return POLB200_ERR_ARG;
+  h->style.tail_correction(i, j, count_i, count_j, *etail_ij, *ptail_ij);
+  return POLB200_OK;
+}
+
 const void *polb200_extract(const polb200_t *h, const char *name, int *dim)
 {
   if (!h || !name || !dim) return nullptr;

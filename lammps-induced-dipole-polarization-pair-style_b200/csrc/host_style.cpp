@@ -168,8 +168,7 @@ void HostStyle::pair_modify(int narg, const char *const *arg)
       if (ncoultablebits > (int)(sizeof(float) * CHAR_BIT)) fail("Too many total bits for bitmapped lookup table");
     } else if (!strcmp(key, "tabinner")) tabinner = numeric(val);
     else if (!strcmp(key, "tail")) {
-      tail_flag = yesno(val, illegal);
-      if (tail_flag) fail("pair_modify tail yes is not supported by the B200 path", POLB200_ERR_UNSUPPORTED);
+      tail_flag = yesno(val, illegal);  // consumed by tail_correction(); the pair loops do not depend on it
     } else fail(illegal);
   }
   initialized = false;
@@ -388,6 +387,20 @@ double HostStyle::single(int itype, int jtype, double qi, double qj, double rsq,
 }
 
 // Restart image = the bytes the reference fwrite()s, in its order: write_restart_settings
+// Long-range Lennard-Jones tail correction of one type pair (init_one, pol.cpp:897-918): the integral of the
+// LJ energy / virial over r > cut_lj for a uniform fluid, times the numbers of atoms of the two types.
+void HostStyle::tail_correction(int i, int j, double count_i, double count_j, double &etail_ij, double &ptail_ij) const
+{
+  etail_ij = ptail_ij = 0.0;
+  if (!tail_flag) return;
+  const double pi = 3.14159265358979323846;
+  const int ij = idx(i, j);
+  const double sig2 = sigma[ij] * sigma[ij], sig6 = sig2 * sig2 * sig2;
+  const double rc3 = cut_lj[ij] * cut_lj[ij] * cut_lj[ij], rc6 = rc3 * rc3, rc9 = rc3 * rc6;
+  etail_ij = 8.0 * pi * count_i * count_j * epsilon[ij] * sig6 * (sig6 - 3.0 * rc6) / (9.0 * rc9);
+  ptail_ij = 16.0 * pi * count_i * count_j * epsilon[ij] * sig6 * (2.0 * sig6 - 3.0 * rc6) / (9.0 * rc9);
+}
+
 // (cut_lj_global, cut_coul, offset_flag, mix_flag, tail_flag, ncoultablebits, tabinner; pol.cpp:976-985)
 // then per i<=j: setflag and, if set, epsilon, sigma, cut_lj (pol.cpp:931-940).
 std::vector<char> HostStyle::restart_image() const

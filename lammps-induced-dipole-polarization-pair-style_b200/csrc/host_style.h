@@ -36,6 +36,8 @@ class HostStyle {
   void init(const polb200_env &env);                       // Pair::init + init_style + init_one + tables
   double single(int itype, int jtype, double qi, double qj, double rsq, double factor_coul,
                 double factor_lj, double &fforce) const;   // pol.cpp:1035-1097
+  void tail_correction(int i, int j, double count_i, double count_j, double &etail_ij,
+                       double &ptail_ij) const;            // pol.cpp:897-918 (pair_modify tail yes)
   std::vector<char> restart_image() const;                 // pol.cpp:927-941,976-985
   void read_restart_image(const void *buf, long nbytes);   // pol.cpp:947-970,991-1009
 

@@ -176,6 +176,15 @@ double PairLJCutCoulLongPolarization::init_one(int i, int j)
   double cut = 0.0;
   CHECK(polb200_init_one(handle, i, j, &cut));
   setflag[i][j] = 1;  // mixed pairs are now defined, like the reference's init_one (:860-866)
+  if (tail_flag) {    // long-range LJ correction (:897-918): type populations summed over all ranks
+    double count[2] = {0.0, 0.0}, all[2];
+    for (int k = 0; k < atom->nlocal; k++) {
+      if (atom->type[k] == i) count[0] += 1.0;
+      if (atom->type[k] == j) count[1] += 1.0;
+    }
+    MPI_Allreduce(count, all, 2, MPI_DOUBLE, MPI_SUM, world);
+    CHECK(polb200_tail(handle, i, j, all[0], all[1], &etail_ij, &ptail_ij));
+  }
   return cut;
 }
 

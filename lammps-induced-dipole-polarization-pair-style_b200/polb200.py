@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "polb200_extract", "polb200_single", "polb200_restart_size", "polb200_write_restart",
     "polb200_read_restart", "polb200_set_box", "polb200_compute", "polb200_comm_id_size",
     "polb200_comm_create_id", "polb200_comm_init", "polb200_subdomain", "polb200_debug_fetch",
-    "polb200_launch_count", "polb200_set_option", "polb200_decomp_plan",
+    "polb200_launch_count", "polb200_set_option", "polb200_decomp_plan", "polb200_tail",
 ]
 
 
@@ -95,6 +95,8 @@ def lib():
         L.polb200_extract.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int)]
         L.polb200_single.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
                                      C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.polb200_tail.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double),
+                                   C.POINTER(C.c_double)]
         L.polb200_restart_size.argtypes = [C.c_void_p, C.POINTER(C.c_long)]
         L.polb200_write_restart.argtypes = [C.c_void_p, C.c_void_p, C.c_long]
         L.polb200_read_restart.argtypes = [C.c_void_p, C.c_void_p, C.c_long]
@@ -229,6 +231,11 @@ class PairStyle:
         cut = C.c_double()
         self._check(lib().polb200_init_one(self._h, i, j, C.byref(cut)))
         return cut.value
+
+    def tail(self, i, j, count_i, count_j):
+        e, p = C.c_double(), C.c_double()
+        self._check(lib().polb200_tail(self._h, i, j, count_i, count_j, C.byref(e), C.byref(p)))
+        return e.value, p.value
 
     def extract(self, name):
         dim = C.c_int()

@@ -179,3 +179,26 @@ def test_pair_modify(style):
     off = style.debug_fetch("h_offset", np.float64, 4).reshape(2, 2)[1, 1]
     r = 3.0 / 2.5
     assert off == 4.0 * 0.1 * (r ** 12 - r ** 6)
+
+
+def test_tail_correction(style):
+    """pair_modify tail yes: etail_ij / ptail_ij of init_one (pol.cpp:897-918) against the closed-form integrals
+    of the LJ energy and virial beyond the cutoff; zero without the keyword; shift+tail is refused like the reference."""
+    style.set_ntypes(2)
+    style.settings(["2.5", "10.0"])
+    style.coeff(["1", "1", "0.1", "3.0"])
+    style.coeff(["2", "2", "0.2", "2.0", "6.0"])
+    style.init(g_ewald=0.25)
+    assert style.tail(1, 1, 100.0, 100.0) == (0.0, 0.0)
+    style.pair_modify(["tail", "yes"])
+    style.init(g_ewald=0.25)
+    for (i, j, eps, sig, rc, ni, nj) in [(1, 1, 0.1, 3.0, 2.5, 120.0, 120.0), (2, 2, 0.2, 2.0, 6.0, 40.0, 40.0),
+                                         (1, 2, np.sqrt(0.1 * 0.2), np.sqrt(3.0 * 2.0), np.sqrt(2.5 * 6.0), 120.0, 40.0)]:
+        e, p = style.tail(i, j, ni, nj)
+        s6, rc3 = sig ** 6, rc ** 3
+        e_ref = 8.0 * np.pi * ni * nj * eps * s6 * (s6 - 3.0 * rc3 ** 2) / (9.0 * rc3 ** 3)
+        p_ref = 16.0 * np.pi * ni * nj * eps * s6 * (2.0 * s6 - 3.0 * rc3 ** 2) / (9.0 * rc3 ** 3)
+        assert abs(e - e_ref) <= 1e-13 * abs(e_ref) and abs(p - p_ref) <= 1e-13 * abs(p_ref)
+    style.pair_modify(["shift", "yes"])
+    with pytest.raises(pb.Polb200Error, match="Cannot have both pair_modify shift and tail"):
+        style.init(g_ewald=0.25)
