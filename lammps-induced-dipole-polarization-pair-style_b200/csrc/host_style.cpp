@@ -196,7 +196,8 @@ void HostStyle::init(const polb200_env &e)
   if (!env.polarizability_flag)
     fail("Pair style lj/cut/coul/long/polarization requires atom attribute polarizability");
   if (!env.kspace_present) fail("Pair style requires a KSpace style");
-  if (!env.newton_pair) fail("B200 path requires newton_pair on (the LAMMPS default)", POLB200_ERR_UNSUPPORTED);
+  // newton_pair off needs no special path: every owned atom computes all of its pairs itself (full list), which is
+  // what the reference's newton-off half list adds up to; LAMMPS then asks for the pairwise virial (vflag = 1)
   // Pair::init(), src/pair.cpp:189-255
   if (offset_flag && tail_flag) fail("Cannot have both pair_modify shift and tail set to yes");
   if (!allocated) fail("All pair coeffs are not set");

@@ -59,6 +59,10 @@ CASES = [
     ("h2_diverge", "Bulk H2", "h2.input", H2_STYLE.replace("max_iterations 100", "max_iterations 3"),
      [], [0], 0),
     ("h2_notable", "Bulk H2", "h2.input", None, ["pair_modify table 0"], [0], 0),
+    # newton_pair off: half/bin/newtoff list, no ghost forces, pairwise virial (vflag = 1)
+    ("h2_newtonoff", "Bulk H2", "h2.input",
+     H2_STYLE.replace("polar_gs_ranked yes", "polar_gs_ranked no fixed_iteration yes").replace(
+         "max_iterations 100", "max_iterations 5"), ["__NEWTON_OFF__"], [0], 0),
     # per-atom energy / virial tallies (Pair::ev_tally, ev_tally_xyz): requested through pe/atom + stress/atom
     ("h2_peratom", "Bulk H2", "h2.input",
      H2_STYLE.replace("polar_gs_ranked yes", "polar_gs_ranked no fixed_iteration yes").replace(
@@ -85,7 +89,9 @@ def run_case(name, exdir, inp, style, extra, keep, nrun):
         text = re.sub(r"^pair_style .*$", style, text, flags=re.M)
     text = re.sub(r"(variable\s+nstep\s+equal\s+)\d+", rf"\g<1>{nrun}", text)
     nve = "__NVE__" in extra
-    extra = [e for e in extra if e != "__NVE__"]
+    if "__NEWTON_OFF__" in extra:
+        text = re.sub(r"^(atom_style.*)$", r"\1\nnewton off", text, count=1, flags=re.M)
+    extra = [e for e in extra if e not in ("__NVE__", "__NEWTON_OFF__")]
     if nve:
         text = re.sub(r"^fix\s+rigid_nve.*$", "fix 1 moving nve", text, flags=re.M)
     lines = text.splitlines()

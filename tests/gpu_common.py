@@ -32,7 +32,7 @@ def have_gpu():
         return False
 
 
-def configure_from_fixture(style, fx, extra_words=()):
+def configure_from_fixture(style, fx, extra_words=(), **init_kw):
     style.set_ntypes(int(fx["ntypes"]))
     style.command(str(fx["pair_style"]) + " " + " ".join(extra_words))
     for line in str(fx["pair_coeff"]).splitlines():
@@ -40,7 +40,7 @@ def configure_from_fixture(style, fx, extra_words=()):
     for line in str(fx["pair_modify"]).splitlines():
         style.command(line)
     style.init(g_ewald=float(fx["g_ewald"]), special_lj=tuple(fx["special_lj"]),
-               special_coul=tuple(fx["special_coul"]))
+               special_coul=tuple(fx["special_coul"]), **init_kw)
     style.set_box(fx["boxlo"], fx["boxhi"])
 
 

@@ -367,3 +367,13 @@ def test_per_atom_tallies_list_mode_equal_exact_mode():
     # pairwise global virial (vflag & 3 == 1) equals the sum of the per-atom virials, in either mode
     assert H.rel_err(va.sum(0), np.array(ra.virial[:])) < 1e-10
     assert H.rel_err(vb.sum(0), np.array(rb.virial[:])) < 1e-10
+
+
+def test_newton_pair_off_matches_reference(style):
+    """`newton off`: the reference switches to the half/bin/newtoff list, skips ghost forces and tallies the virial
+    pairwise (vflag = 1); the owner-computes device path needs no second code path to reproduce it."""
+    fx = H.load_fixture("h2_newtonoff_step0")
+    assert int(fx["vflag"]) == 1
+    configure_from_fixture(style, fx, newton_pair=0)
+    res, mu, ef, f = run_fixture(style, fx)
+    check_against_fixture(res, mu, ef, f, fx)
