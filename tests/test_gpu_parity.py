@@ -377,3 +377,31 @@ def test_newton_pair_off_matches_reference(style):
     configure_from_fixture(style, fx, newton_pair=0)
     res, mu, ef, f = run_fixture(style, fx)
     check_against_fixture(res, mu, ef, f, fx)
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 33])
+def test_tiny_systems(n):
+    """Edge sizes: fewer atoms than a warp, a single atom (no partner at all), odd group counts; exact mode against the
+    literal oracle, list mode against the row oracle."""
+    rng = np.random.default_rng(100 + n)
+    L = 30.0
+    x = rng.uniform(2.0, L - 2.0, size=(n, 3))
+    typ = (np.arange(n) % 2 + 1).astype(np.int32)
+    q = np.where(typ == 1, 0.4, -0.4) * (1.0 if n > 1 else 0.0)
+    alpha = np.where(typ == 1, 1.0, 0.5)
+    sysm = P.System(x, q, typ, np.zeros(n, dtype=np.int32), alpha, [0, 0, 0], [L, L, L], 2)
+    kw = dict(fixed_iteration=1, max_iterations=4, damp_type="exponential", polar_gs_ranked=0)
+    for polar_cut in (0.0, 12.0):
+        st = H.fluid_style(sysm, 2.5, 12.0, polar_cut=polar_cut, **kw)
+        lit = P.compute(sysm, st)
+        s = pb.PairStyle(device=0)
+        _fluid_style_on_device(s, sysm, st.g_ewald, "polar_gs_ranked no fixed_iteration yes max_iterations 4 damp_type exponential"
+                               + (f" polar_cutoff {polar_cut}" if polar_cut else ""))
+        res, mu, ef, f = run_system(s, sysm)
+        s.close()
+        scale = max(np.abs(lit["mu"]).max(), 1e-30)
+        assert np.abs(mu - lit["mu"]).max() <= 1e-10 * scale
+        assert np.abs(ef - lit["ef_static"]).max() <= 1e-10 * max(np.abs(lit["ef_static"]).max(), 1e-30)
+        assert np.abs(f - lit["f"]).max() <= 1e-10 * max(np.abs(lit["f"]).max(), 1e-30)
+        assert abs(res.eng_pol - lit["eng_pol"]) <= 1e-10 * max(abs(lit["eng_pol"]), 1e-30)
+        assert abs(res.eng_coul - lit["eng_coul"]) <= 1e-10 * max(abs(lit["eng_coul"]), 1e-30)
