@@ -143,6 +143,8 @@ struct polb200_handle {
   // 20 / 21: per-atom rows + radial cache (also the ranked colouring sweep); 6: matrix-free; 0: first version
   int sweep_variant = 41;
   bool use_tight = true;         // per-step tight list
+  bool gs_blocked = true;        // exact-mode Gauss-Seidel as blocked forward substitution (false: one atom at a time)
+  DBuf<double4> gsR;
   bool l2_evict_first = true;    // TMA row streams are marked evict-first in L2
   bool alternate = true;         // sweeps walk the groups alternately forwards / backwards (L2 reuse of the stream tail)
   unsigned sweep_parity = 0;
@@ -911,7 +913,18 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
     while (keep) {
       double change = 0.0;
       const bool want_change = !st.fixed_iteration;
-      if (sequential) {
+      if (sequential && h->gs_blocked) {
+        // blocked forward substitution = the same sweep, N/32 dependent steps instead of N (kernels.cuh)
+        h->gsR.ensure(n);
+        LAUNCH(h, k_gsb_upper, nrowblocks, BLOCK, n, order, P, h->perm.p, h->xq.p, cur, h->ef.p, h->gsR.p);
+        const int nblk = cdiv(n, GSB);
+        for (int b = 0; b < nblk; b++) {
+          LAUNCH(h, k_gsb_solve, 1, GSB * 32, n, b, order, P, h->perm.p, h->xq.p, cur, h->gsR.p, h->scal.p + S_CHANGE, b == 0 ? 1 : 0);
+          const int rows_after = n - (b + 1) * GSB;
+          if (rows_after > 0)
+            LAUNCH(h, k_gsb_update, cdiv(rows_after, WARPS_PER_BLOCK), BLOCK, n, b, order, P, h->perm.p, h->xq.p, cur, h->gsR.p);
+        }
+      } else if (sequential) {
         LAUNCH(h, k_gs_sequential, 1, GS_THREADS, n, order, P, h->perm.p, h->xq.p, cur, h->ef.p, h->scal.p + S_CHANGE);
       } else if (!gs) {
         // Jacobi in fixed mode: the reference runs max_iterations+1 sweeps and discards the last
@@ -1189,7 +1202,7 @@ void polb200_destroy(polb200_t *h)
     b->release();
   for (auto *b : {&h->xq, &h->mua, &h->mub, &h->ef, &h->f_pair, &h->f_pol}) b->release();
   h->group_first.release(); h->group_two.release(); h->gneigh.release(); h->gcount.release(); h->tgneigh.release(); h->tgcount.release();
-  h->growstart.release(); h->s12ab.release(); h->gcstart.release(); h->gcrec.release();
+  h->gsR.release(); h->growstart.release(); h->s12ab.release(); h->gcstart.release(); h->gcrec.release();
   h->s12.release(); h->push_off.release(); h->push_ptr0.release(); h->push_ptr1.release();
   h->tm.release(); h->cnt.release(); h->rowstart.release(); h->cub_tmp.release(); h->rmin_bits.release();
   h->h_stage.release(); h->h_scal.release(); h->h_int.release();
@@ -1357,6 +1370,10 @@ int polb200_set_option(polb200_t *h, const char *name, double value)
   if (!strcmp(name, "xsort_bits")) {
     h->xsort_bits = (int)value;
     h->have_lists = false;
+    return POLB200_OK;
+  }
+  if (!strcmp(name, "gs_blocked")) {
+    h->gs_blocked = value != 0.0;
     return POLB200_OK;
   }
   if (!strcmp(name, "l2_evict_first")) {

@@ -1904,4 +1904,136 @@ k_sweep_group_tma(int ngroups, const int *__restrict__ group_first, const int *_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// exact mode: sequential-equivalent Gauss-Seidel as a blocked forward substitution
+// ---------------------------------------------------------------------------------------------------
+// The reference's polar_gs / polar_gs_ranked sweep (pol.cpp:1158-1180) visits the atoms one by one in ranked
+// order, each using the NEW dipoles of the atoms before it and the OLD dipoles of the atoms after it: one sweep
+// solves the lower-triangular system  (I + alpha L) mu_new = alpha (E - U mu_old)  in ranked order.  Done atom by
+// atom that is N dependent steps (k_gs_sequential: one CTA, 8 ms per sweep set at 750 atoms).  Blocked:
+//   k_gsb_upper : R[p] = E[p] - sum over partners in LATER blocks of T mu_old          (all SMs, once per sweep)
+//   per block b : k_gsb_solve  - the 32x32 diagonal block: T of the block's pairs into shared memory, then one warp
+//                                substitutes sequentially (new dipoles of earlier atoms, old of later ones)
+//                 k_gsb_update - R[p] -= sum over the atoms of block b of T mu_new, for every p in later blocks
+// Same operands per atom as the sequential sweep; only the order of the additions inside one field sum differs.
+constexpr int GSB = 32;
+
+// del of the pair (row atom s, partner j) with the reference's anchoring rule (lower caller index anchors the image)
+__device__ __forceinline__ void pair_del(const Box &box, const int *__restrict__ perm, int s, int j, const double4 &xs,
+                                         const double4 &xj, double &dx, double &dy, double &dz)
+{
+  if (perm[s] < perm[j]) min_image_del(box, xs.x, xs.y, xs.z, xj.x, xj.y, xj.z, dx, dy, dz);
+  else min_image_del(box, xj.x, xj.y, xj.z, xs.x, xs.y, xs.z, dx, dy, dz);
+}
+
+__global__ void __launch_bounds__(BLOCK)
+k_gsb_upper(int n, const int *__restrict__ order, DevParams P, const int *__restrict__ perm,
+            const double4 *__restrict__ xq, const double4 *__restrict__ mua, const double4 *__restrict__ ef,
+            double4 *__restrict__ R)
+{
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (p >= n) return;
+  const int s = order ? order[p] : p;
+  const double4 xs = xq[s];
+  double ex = 0, ey = 0, ez = 0;
+  const int q0 = (p / GSB + 1) * GSB;  // first position of the next block
+  if (mua[s].w != 0.0)
+    for (int q = q0 + lane; q < n; q += 32) {
+      const int j = order ? order[q] : q;
+      const double4 xj = ld4(xq + j);
+      double dx, dy, dz;
+      pair_del(P.box, perm, s, j, xs, xj, dx, dy, dz);
+      const double4 mj = ld4_cg(mua + j);
+      induced_field_pair(P.pc, dx, dy, dz, dx * dx + dy * dy + dz * dz, mj.x, mj.y, mj.z, ex, ey, ez);
+    }
+  ex = warp_sum(ex);
+  ey = warp_sum(ey);
+  ez = warp_sum(ez);
+  if (lane == 0) {
+    const double4 e = ef[s];
+    R[p] = make_double4(e.x + ex, e.y + ey, e.z + ez, 0.0);
+  }
+}
+
+// one CTA of GSB warps: thread (w, v) owns the pair (block atom w, block atom v)
+__global__ void __launch_bounds__(GSB * 32)
+k_gsb_solve(int n, int b, const int *__restrict__ order, DevParams P, const int *__restrict__ perm,
+            const double4 *__restrict__ xq, double4 *__restrict__ mua, const double4 *__restrict__ R,
+            double *__restrict__ change_out, int first_block)
+{
+  __shared__ double sT[GSB][GSB][5];  // s1, s2, dx, dy, dz of every pair of the block
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int p0 = b * GSB, cnt = min(GSB, n - p0);
+  if (warp < cnt && lane < cnt && warp != lane) {
+    const int s = order ? order[p0 + warp] : p0 + warp, j = order ? order[p0 + lane] : p0 + lane;
+    const double4 xs = xq[s], xj = xq[j];
+    double dx, dy, dz, s1, s2;
+    pair_del(P.box, perm, s, j, xs, xj, dx, dy, dz);
+    induced_field_scalars(P.pc, dx * dx + dy * dy + dz * dz, s1, s2);
+    sT[warp][lane][0] = s1; sT[warp][lane][1] = s2;
+    sT[warp][lane][2] = dx; sT[warp][lane][3] = dy; sT[warp][lane][4] = dz;
+  }
+  __syncthreads();
+  if (warp != 0) return;
+  // forward substitution: lane v carries the dipole of block atom v (old until its turn, new afterwards)
+  const int sv = lane < cnt ? (order ? order[p0 + lane] : p0 + lane) : 0;
+  double4 mv = lane < cnt ? ld4_cg(mua + sv) : make_double4(0, 0, 0, 0);
+  const double4 rv = lane < cnt ? R[p0 + lane] : make_double4(0, 0, 0, 0);
+  double change = 0.0;
+  for (int w = 0; w < cnt; w++) {
+    double ex = 0, ey = 0, ez = 0;
+    if (lane < cnt && lane != w) {
+      const double s1 = sT[w][lane][0], s2 = sT[w][lane][1];
+      const double dx = sT[w][lane][2], dy = sT[w][lane][3], dz = sT[w][lane][4];
+      const double dm = dx * mv.x + dy * mv.y + dz * mv.z;
+      ex = -(s1 * mv.x + s2 * dm * dx);
+      ey = -(s1 * mv.y + s2 * dm * dy);
+      ez = -(s1 * mv.z + s2 * dm * dz);
+    }
+    ex = warp_sum(ex);
+    ey = warp_sum(ey);
+    ez = warp_sum(ez);
+    ex = __shfl_sync(FULL, ex, 0);
+    ey = __shfl_sync(FULL, ey, 0);
+    ez = __shfl_sync(FULL, ez, 0);
+    if (lane == w) {
+      // alpha == 0: the field sum is skipped by the sequential kernel too; the product is zero either way
+      const double nx = mv.w * (rv.x + ex), ny = mv.w * (rv.y + ey), nz = mv.w * (rv.z + ez);
+      change += (nx - mv.x) * (nx - mv.x) + (ny - mv.y) * (ny - mv.y) + (nz - mv.z) * (nz - mv.z);
+      mv = make_double4(nx, ny, nz, mv.w);
+    }
+  }
+  if (lane < cnt) mua[sv] = mv;
+  change = warp_sum(change);
+  if (lane == 0) change_out[0] = first_block ? change : change_out[0] + change;
+}
+
+__global__ void __launch_bounds__(BLOCK)
+k_gsb_update(int n, int b, const int *__restrict__ order, DevParams P, const int *__restrict__ perm,
+             const double4 *__restrict__ xq, const double4 *__restrict__ mua, double4 *__restrict__ R)
+{
+  const int lane = threadIdx.x & 31;
+  const int p = (b + 1) * GSB + blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (p >= n) return;
+  const int s = order ? order[p] : p;
+  const int q = b * GSB + lane;  // block b is complete: GSB atoms (only the last block can be short, and it has no later rows)
+  const int j = order ? order[q] : q;
+  const double4 xs = xq[s], xj = ld4(xq + j);
+  double ex = 0, ey = 0, ez = 0;
+  if (mua[s].w != 0.0) {
+    double dx, dy, dz;
+    pair_del(P.box, perm, s, j, xs, xj, dx, dy, dz);
+    const double4 mj = ld4_cg(mua + j);
+    induced_field_pair(P.pc, dx, dy, dz, dx * dx + dy * dy + dz * dz, mj.x, mj.y, mj.z, ex, ey, ez);
+  }
+  ex = warp_sum(ex);
+  ey = warp_sum(ey);
+  ez = warp_sum(ez);
+  if (lane == 0) {
+    double4 r = R[p];
+    R[p] = make_double4(r.x + ex, r.y + ey, r.z + ez, 0.0);
+  }
+}
+
 }  // namespace polb200

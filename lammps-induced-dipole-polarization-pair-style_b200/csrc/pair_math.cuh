@@ -181,8 +181,8 @@ PB_HD double static_field_scalar(const PairConsts &pc, double rsq)
 
 // ---- stage 3: T_ij . mu_j for one neighbour (pol.cpp:1282-1306 + 1161-1168), matrix-free ----------------
 // del = xlo - image(xhi).  Accumulates  e -= T mu  component-wise.
-PB_HD void induced_field_pair(const PairConsts &pc, double dx, double dy, double dz, double r2, double mx,
-                              double my, double mz, double &ex, double &ey, double &ez)
+// radial part of T in the reference's own operation order (pol.cpp:1282-1306): s1 = d1/r^3, s2 = -3 d2/r^5
+PB_HD void induced_field_scalars(const PairConsts &pc, double r2, double &s1, double &s2)
 {
   const double r = sqrt(r2);
   double r3, r5;
@@ -199,8 +199,15 @@ PB_HD void induced_field_pair(const PairConsts &pc, double dx, double dy, double
     d2 = 1.0 - ex_ * (a * a * a * r2 * r / 6.0 + 0.5 * a * a * r2 + a * r + 1.0);
   }
   // T = d1*r3*I - 3*d2*r5*(del x del);  T mu = d1*r3*mu - 3*d2*r5*(del.mu)*del
-  const double s1 = d1 * r3;
-  const double s2 = -3.0 * d2 * r5;
+  s1 = d1 * r3;
+  s2 = -3.0 * d2 * r5;
+}
+
+PB_HD void induced_field_pair(const PairConsts &pc, double dx, double dy, double dz, double r2, double mx,
+                              double my, double mz, double &ex, double &ey, double &ez)
+{
+  double s1, s2;
+  induced_field_scalars(pc, r2, s1, s2);
   const double dm = dx * mx + dy * my + dz * mz;
   ex -= s1 * mx + s2 * dm * dx;
   ey -= s1 * my + s2 * dm * dy;

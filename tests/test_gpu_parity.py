@@ -405,3 +405,21 @@ def test_tiny_systems(n):
         assert np.abs(f - lit["f"]).max() <= 1e-10 * max(np.abs(lit["f"]).max(), 1e-30)
         assert abs(res.eng_pol - lit["eng_pol"]) <= 1e-10 * max(abs(lit["eng_pol"]), 1e-30)
         assert abs(res.eng_coul - lit["eng_coul"]) <= 1e-10 * max(abs(lit["eng_coul"]), 1e-30)
+
+
+@pytest.mark.parametrize("case", ["h2_default_step0", "methane_default_step0"])
+def test_blocked_gauss_seidel_equals_atom_by_atom(case):
+    """exact-mode Gauss-Seidel: the blocked forward substitution against the one-atom-at-a-time kernel (same operands,
+    different order of additions inside a field sum): same iteration count, dipoles to rounding."""
+    fx = H.load_fixture(case)
+    outs = []
+    for blocked in (0, 1):
+        s = pb.PairStyle(device=0)
+        configure_from_fixture(s, fx)
+        s.set_option("gs_blocked", blocked)
+        outs.append(run_fixture(s, fx))
+        s.close()
+    (ra, mua, efa, fa), (rb, mub, efb, fb) = outs
+    assert ra.iterations == rb.iterations == int(fx["iterations"]) or abs(rb.iterations - int(fx["iterations"])) <= 1
+    assert H.rel_err(mua, mub) < 1e-9 and H.rel_err(fa, fb) < 1e-9
+    assert abs(ra.eng_pol - rb.eng_pol) < 1e-10 * abs(ra.eng_pol)
