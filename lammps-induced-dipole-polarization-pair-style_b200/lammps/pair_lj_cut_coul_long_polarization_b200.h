@@ -24,26 +24,32 @@ namespace LAMMPS_NS {
 
 class PairLJCutCoulLongPolarization : public Pair {
  public:
-  PairLJCutCoulLongPolarization(class LAMMPS *);
-  virtual ~PairLJCutCoulLongPolarization();
-  virtual void compute(int, int);
-  virtual void settings(int, char **);
-  void coeff(int, char **);
-  virtual void init_style();
-  virtual double init_one(int, int);
-  void write_restart(FILE *);
-  void read_restart(FILE *);
-  virtual void write_restart_settings(FILE *);
-  virtual void read_restart_settings(FILE *);
-  void write_data(FILE *);
-  void write_data_all(FILE *);
-  virtual double single(int, int, int, int, double, double, double, double &);
-  virtual void *extract(const char *, int &);
+  explicit PairLJCutCoulLongPolarization(class LAMMPS *);
+  ~PairLJCutCoulLongPolarization();
 
- protected:
-  struct polb200_handle *handle;   // opaque library state (device arrays, kernels' parameters)
-  int device;                      // CUDA ordinal, environment POLB200_DEVICE (default 0)
-  int debug;                       // `debug yes`: per-step prints like the reference (:391,:635-639)
+  // configuration (forwarded to the host-side mirror behind the C ABI)
+  void settings(int narg, char **arg);
+  void coeff(int narg, char **arg);
+  void init_style();
+  double init_one(int itype, int jtype);
+
+  // the hot path
+  void compute(int eflag, int vflag);
+
+  // queries, restart and data files
+  double single(int i, int j, int itype, int jtype, double rsq, double factor_coul, double factor_lj, double &fforce);
+  void *extract(const char *name, int &dim);
+  void write_restart(FILE *fp);
+  void write_restart_settings(FILE *fp);
+  void read_restart(FILE *fp);
+  void read_restart_settings(FILE *fp);
+  void write_data(FILE *fp);
+  void write_data_all(FILE *fp);
+
+ private:
+  struct polb200_handle *handle;        // opaque library state (device arrays, kernels' parameters)
+  int device;                           // CUDA ordinal, environment POLB200_DEVICE (default 0)
+  int debug;                            // `debug yes`: per-step prints like the reference (:391,:635-639)
   int ntypes_set;
   double **epsilon_rows, **sigma_rows;  // row tables over the library's flat arrays, for extract()
 
