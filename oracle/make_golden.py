@@ -219,6 +219,8 @@ def shipped_logs():
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     only = sys.argv[1:]
+    if only == ["ewald"]:
+        return ewald_goldens()
     ours = {}
     for c in CASES:
         if only and c[0] not in only:
@@ -228,6 +230,77 @@ def main():
         logs = shipped_logs()
         logs["oracle_ref_runs"] = {k: v for k, v in ours.items()}
         (OUT / "thermo_logs.json").write_text(json.dumps(logs, indent=1))
+
+
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# KSpace: reciprocal-space Ewald of the reference (src/KSPACE/ewald.cpp) as golden vectors.
+# Forces and virial of KSpace alone = difference of two otherwise identical runs, with and without
+# `kspace_modify compute no` (the pair forces of both runs are bit-identical).
+# ---------------------------------------------------------------------------------------------------------------
+NKTV2P_REAL = 68568.415  # src/update.cpp:161 (units real)
+
+
+def ewald_case(name, data_text, cut_coul, accuracy, extra=()):
+    work = Path(tempfile.mkdtemp(prefix=f"polgold_{name}_"))
+    (work / "sys.data").write_text(data_text)
+    outs = {}
+    for tag, mod in (("on", ""), ("off", "kspace_modify compute no")):
+        lines = ["units real", "boundary p p p", "atom_style full", "read_data sys.data", "mass * 1.0",
+                 f"pair_style lj/cut/coul/long 2.5 {cut_coul}", "pair_coeff * * 0.0 1.0",
+                 f"kspace_style ewald {accuracy}", mod, *extra,
+                 "thermo_style custom step elong ecoul pxx pyy pzz pxy pxz pyz vol",
+                 "thermo_modify format float %.16g", f"dump d all custom 1 f_{tag}.dump id fx fy fz",
+                 "dump_modify d format float %.17g sort id", "run 0"]
+        (work / f"in.{tag}").write_text("\n".join(lines) + "\n")
+        r = subprocess.run([str(LMP), "-in", f"in.{tag}", "-echo", "none", "-log", f"log.{tag}"], cwd=work,
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            print(r.stdout[-2000:])
+            raise SystemExit(f"{name}: lmp_serial failed")
+        log = (work / f"log.{tag}").read_text()
+        th = parse_thermo(log)[0]
+        rows = [l.split() for l in (work / f"f_{tag}.dump").read_text().splitlines()[9:]]
+        f = np.array([[float(v) for v in r_[1:4]] for r_ in rows])
+        outs[tag] = (th, f, log)
+    th_on, f_on, log = outs["on"]
+    th_off, f_off, _ = outs["off"]
+    vol = th_on["Volume"]
+    press = np.array([th_on[k] - th_off[k] for k in ("Pxx", "Pyy", "Pzz", "Pxy", "Pxz", "Pyz")])
+    m = re.search(r"G vector \(1/distance\) = (\S+)", log)
+    kv = re.search(r"KSpace vectors: actual max1d max3d = (\d+) (\d+) (\d+)", log)
+    km = re.search(r"kxmax kymax kzmax\s+= (\d+) (\d+) (\d+)", log)
+    shutil.rmtree(work)
+    return dict(elong=th_on["E_long"], f_kspace=f_on - f_off, virial_kspace=press * vol / NKTV2P_REAL,
+                g_ewald_printed=float(m.group(1)), kcount=int(kv.group(1)), kmax=int(kv.group(2)),
+                kxyzmax=np.array([int(km.group(i)) for i in (1, 2, 3)]), accuracy=accuracy, cut_coul=cut_coul)
+
+
+def ewald_goldens():
+    sys.path.insert(0, str(ROOT / "tests"))
+    import polhelpers as H
+
+    def data_of(x, q, typ, lo, hi):
+        n = len(q)
+        t = [f"ewald golden\n\n{n} atoms\n{int(typ.max())} atom types\n"]
+        for d, c in enumerate("xyz"):
+            t.append(f"{lo[d]:.17g} {hi[d]:.17g} {c}lo {c}hi")
+        t.append("\nAtoms\n")
+        t += [f"{i + 1} 0 {int(typ[i])} {q[i]:.17g} {x[i, 0]:.17g} {x[i, 1]:.17g} {x[i, 2]:.17g}" for i in range(n)]
+        return "\n".join(t) + "\n"
+
+    fx = H.load_fixture("h2_default_step0")
+    cases = {"ewald_h2": (fx["x"], fx["q"], fx["type"], fx["boxlo"], fx["boxhi"], 10.797442, 1e-4),
+             "ewald_methane": None, "ewald_brick": None}
+    fm = H.load_fixture("methane_default_step0")
+    cases["ewald_methane"] = (fm["x"], fm["q"], fm["type"], fm["boxlo"], fm["boxhi"], 12.8345, 1e-6)
+    fl = H.lj_charge_fluid((6, 4, 3), seed=31)  # non-cubic box, 288 atoms
+    cases["ewald_brick"] = (fl.x, fl.q, fl.type, fl.boxlo, fl.boxhi, 5.0, 1e-5)
+    for name, (x, q, typ, lo, hi, cut, acc) in cases.items():
+        g = ewald_case(name, data_of(x, q, typ, lo, hi), cut, acc)
+        np.savez_compressed(OUT / f"{name}.npz", x=x, q=q, boxlo=lo, boxhi=hi, **g)
+        print(f"{name}: n {len(q)} E_long {g['elong']:.12g} kcount {g['kcount']} kmax {g['kxyzmax']} g {g['g_ewald_printed']}")
 
 
 if __name__ == "__main__":

@@ -1607,3 +1607,119 @@ double polref_bench_rows(const polref_params *p, int nlocal, const double *x, co
   free(pl.idx);
   return t1 - t0;
 }
+
+
+/* ===================================================================================================
+ * KSpace: reciprocal-space Ewald
+ * =================================================================================================== */
+
+static double ewald_rms(int km, double prd, long natoms, double q2, double g)
+{ /* ewald.cpp:343-351 */
+  if (natoms == 0) natoms = 1;
+  return 2.0 * q2 * g / prd * sqrt(1.0 / (M_PI * km * natoms)) * exp(-M_PI * M_PI * km * km / (g * g * prd * prd));
+}
+
+/* the half-space k set of Ewald::coeffs: the first non-zero component (x, then y, then z) is positive; axis
+ * vectors run to kmax, the others to the per-dimension maxima; all inside |k|^2 <= gsqmx */
+static int ewald_in_set(const polref_ewald_plan *p, const double unitk[3], int kx, int ky, int kz, double *sqk_out)
+{
+  if (kx < 0 || (kx == 0 && ky < 0) || (kx == 0 && ky == 0 && kz <= 0)) return 0;
+  const int nz = (kx != 0) + (ky != 0) + (kz != 0);
+  if (nz == 1) {
+    if (abs(kx) > p->kmax || abs(ky) > p->kmax || abs(kz) > p->kmax) return 0;
+  } else if (abs(kx) > p->kxmax || abs(ky) > p->kymax || abs(kz) > p->kzmax) return 0;
+  const double sqk = (kx * unitk[0]) * (kx * unitk[0]) + (ky * unitk[1]) * (ky * unitk[1]) + (kz * unitk[2]) * (kz * unitk[2]);
+  if (sqk > p->gsqmx) return 0;
+  *sqk_out = sqk;
+  return 1;
+}
+
+int polref_ewald_plan_make(double accuracy_relative, double qqrd2e, double two_charge_force, double qsqsum,
+                           long natoms, double cutoff, const double prd[3], double g_ewald_in,
+                           polref_ewald_plan *plan)
+{
+  const double accuracy = accuracy_relative * two_charge_force; /* ewald.cpp:131-132 */
+  const double q2 = qsqsum * qqrd2e;                            /* kspace.cpp:293 */
+  double g = g_ewald_in;
+  if (!(g > 0.0)) { /* ewald.cpp:153-160 */
+    if (accuracy <= 0.0 || q2 == 0.0) return 1;
+    g = accuracy * sqrt(natoms * cutoff * prd[0] * prd[1] * prd[2]) / (2.0 * q2);
+    if (g >= 1.0) g = (1.35 - 0.15 * log(accuracy)) / cutoff;
+    else g = sqrt(-log(g)) / cutoff;
+  }
+  plan->g_ewald = g;
+  int km[3];
+  for (int d = 0; d < 3; d++) { /* ewald.cpp:241-258 */
+    km[d] = 1;
+    while (ewald_rms(km[d], prd[d], natoms, q2, g) > accuracy) km[d]++;
+  }
+  plan->kxmax = km[0]; plan->kymax = km[1]; plan->kzmax = km[2];
+  plan->kmax = km[0] > km[1] ? km[0] : km[1];
+  if (km[2] > plan->kmax) plan->kmax = km[2];
+  double gs = 0.0;
+  for (int d = 0; d < 3; d++) {
+    const double u = 2.0 * M_PI / prd[d], v = u * u * km[d] * km[d];
+    if (v > gs) gs = v;
+  }
+  plan->gsqmx = gs * 1.00001; /* ewald.cpp:311 */
+  const double unitk[3] = {2.0 * M_PI / prd[0], 2.0 * M_PI / prd[1], 2.0 * M_PI / prd[2]};
+  int cnt = 0;
+  double sqk;
+  for (int kx = 0; kx <= plan->kmax; kx++)
+    for (int ky = -plan->kmax; ky <= plan->kmax; ky++)
+      for (int kz = -plan->kmax; kz <= plan->kmax; kz++) cnt += ewald_in_set(plan, unitk, kx, ky, kz, &sqk);
+  plan->kcount = cnt;
+  return 0;
+}
+
+int polref_ewald_compute(const polref_ewald_plan *plan, int n, const double *x, const double *q,
+                         const double prd[3], double qqrd2e, double *f, double *energy, double virial[6])
+{
+  const double g = plan->g_ewald, volume = prd[0] * prd[1] * prd[2];
+  const double unitk[3] = {2.0 * M_PI / prd[0], 2.0 * M_PI / prd[1], 2.0 * M_PI / prd[2]};
+  const double ginv2 = 1.0 / (g * g), preu = 4.0 * M_PI / volume;
+  double qsum = 0.0, qsqsum = 0.0;
+  for (int i = 0; i < n; i++) { qsum += q[i]; qsqsum += q[i] * q[i]; }
+  double e = 0.0, v[6] = {0, 0, 0, 0, 0, 0};
+  double *fk = (double *)calloc((size_t)3 * (n > 0 ? n : 1), sizeof(double));
+  const int K = plan->kmax;
+#pragma omp parallel for collapse(2) schedule(dynamic) reduction(+ : e)
+  for (int kx = 0; kx <= K; kx++)
+    for (int ky = -K; ky <= K; ky++)
+      for (int kz = -K; kz <= K; kz++) {
+        double sqk;
+        if (!ewald_in_set(plan, unitk, kx, ky, kz, &sqk)) continue;
+        const double kv[3] = {kx * unitk[0], ky * unitk[1], kz * unitk[2]};
+        double sre = 0.0, sim = 0.0; /* structure factor, ewald.cpp:501-680 */
+        for (int i = 0; i < n; i++) {
+          const double ph = kv[0] * x[3 * i] + kv[1] * x[3 * i + 1] + kv[2] * x[3 * i + 2];
+          sre += q[i] * cos(ph);
+          sim += q[i] * sin(ph);
+        }
+        const double ug = preu * exp(-0.25 * sqk * ginv2) / sqk; /* ewald.cpp:776 */
+        const double uk = ug * (sre * sre + sim * sim);
+        e += uk;                                                 /* ewald.cpp:455-457 */
+        const double vterm = -2.0 * (1.0 / sqk + 0.25 * ginv2);  /* ewald.cpp:781-788 */
+        const double vk[6] = {1.0 + vterm * kv[0] * kv[0], 1.0 + vterm * kv[1] * kv[1], 1.0 + vterm * kv[2] * kv[2],
+                              vterm * kv[0] * kv[1], vterm * kv[0] * kv[2], vterm * kv[1] * kv[2]};
+#pragma omp critical
+        {
+          for (int a = 0; a < 6; a++) v[a] += uk * vk[a];
+          for (int i = 0; i < n; i++) { /* field, ewald.cpp:417-431: partial = Im(e^{ikr} conj(S)) */
+            const double ph = kv[0] * x[3 * i] + kv[1] * x[3 * i + 1] + kv[2] * x[3 * i + 2];
+            const double partial = sin(ph) * sre - cos(ph) * sim;
+            fk[3 * i] += partial * 2.0 * ug * kv[0];
+            fk[3 * i + 1] += partial * 2.0 * ug * kv[1];
+            fk[3 * i + 2] += partial * 2.0 * ug * kv[2];
+          }
+        }
+      }
+  for (int i = 0; i < n; i++) /* ewald.cpp:443-449 */
+    for (int d = 0; d < 3; d++) f[3 * i + d] += qqrd2e * q[i] * fk[3 * i + d];
+  free(fk);
+  /* ewald.cpp:459-461: self energy and neutralising background */
+  e -= g * qsqsum / sqrt(M_PI) + 0.5 * M_PI * qsum * qsum / (g * g * volume);
+  *energy = e * qqrd2e;
+  for (int a = 0; a < 6; a++) virial[a] = v[a] * qqrd2e;
+  return 0;
+}

@@ -84,6 +84,27 @@ int polref_init_coeffs(int ntypes, double *epsilon, double *sigma, double *cut_l
 double polref_ewald_g(double accuracy_relative, double qqrd2e, double two_charge_force, double q2sum,
                       long natoms, double cutoff, double xprd, double yprd, double zprd);
 
+/* ---- KSpace: reciprocal-space Ewald (src/KSPACE/ewald.cpp) ---- */
+
+typedef struct {
+  double g_ewald;
+  int kxmax, kymax, kzmax, kmax; /* per-dimension and overall integer bounds, ewald.cpp:241-266 */
+  double gsqmx;                  /* |k|^2 cutoff incl. the 1.00001 factor, ewald.cpp:267-275,311 */
+  int kcount;                    /* number of half-space k-vectors, ewald.cpp:760-1026 */
+} polref_ewald_plan;
+
+/* Ewald::init + setup (ewald.cpp:87-340): g_ewald from the relative accuracy unless g_ewald_in > 0
+ * (kspace_modify gewald), kmax per dimension from the rms() criterion (:343-351). */
+int polref_ewald_plan_make(double accuracy_relative, double qqrd2e, double two_charge_force, double qsqsum,
+                           long natoms, double cutoff, const double prd[3], double g_ewald_in,
+                           polref_ewald_plan *plan);
+
+/* Ewald::compute (ewald.cpp:357-497) with eik_dot_r (:501-680) and coeffs (:760-1026), orthogonal box, no slab
+ * correction: structure factors over the half-space k set, energy incl. self and neutralising terms, forces (+=
+ * into f) and virial.  Direct evaluation of exp(i k.r) (no recurrences): an independent statement of the sums. */
+int polref_ewald_compute(const polref_ewald_plan *plan, int n, const double *x, const double *q,
+                         const double prd[3], double qqrd2e, double *f, double *energy, double virial[6]);
+
 /* ---- ghost atoms + half neighbor list, single process ---- */
 
 /* src/comm_brick.cpp:164-411,712-880 (one proc, mode SINGLE, uniform layout).

@@ -237,6 +237,38 @@ def ewald_g(accuracy, q, cut_coul, boxlo, boxhi, qqrd2e=REAL_QQRD2E, two_charge_
                                       C.c_double(prd[0]), C.c_double(prd[1]), C.c_double(prd[2])))
 
 
+class EwaldPlan(C.Structure):
+    _fields_ = [("g_ewald", C.c_double), ("kxmax", C.c_int), ("kymax", C.c_int), ("kzmax", C.c_int), ("kmax", C.c_int),
+                ("gsqmx", C.c_double), ("kcount", C.c_int)]
+
+
+def ewald_plan(accuracy, q, cutoff, prd, g_ewald=0.0, qqrd2e=REAL_QQRD2E, two_charge_force=REAL_QQRD2E):
+    """Ewald::init/setup of the reference (g_ewald, kmax per dimension, |k|^2 cutoff, k count)."""
+    q = f64(q)
+    p = EwaldPlan()
+    prd3 = (C.c_double * 3)(*[float(v) for v in prd])
+    rc = lib().polref_ewald_plan_make(C.c_double(accuracy), C.c_double(qqrd2e), C.c_double(two_charge_force),
+                                      C.c_double(float(np.cumsum(q * q)[-1])), C.c_long(len(q)), C.c_double(cutoff), prd3,
+                                      C.c_double(g_ewald), C.byref(p))
+    if rc:
+        raise RuntimeError("polref_ewald_plan_make failed")
+    return p
+
+
+def ewald_compute(plan, x, q, prd, qqrd2e=REAL_QQRD2E):
+    """Reciprocal-space Ewald energy, forces, virial (the reference's KSpace::compute for kspace_style ewald)."""
+    x, q = f64(x).reshape(-1, 3), f64(q)
+    n = len(q)
+    f = np.zeros((n, 3))
+    e = C.c_double()
+    v = (C.c_double * 6)()
+    prd3 = (C.c_double * 3)(*[float(t) for t in prd])
+    rc = lib().polref_ewald_compute(C.byref(plan), n, _d(x), _d(q), prd3, C.c_double(qqrd2e), _d(f), C.byref(e), v)
+    if rc:
+        raise RuntimeError("polref_ewald_compute failed")
+    return dict(energy=e.value, f=f, virial=np.array(v[:]))
+
+
 def build_ghosts(sysm, cutghost):
     L = lib()
     n = sysm.n
