@@ -19,7 +19,7 @@ def test_ewald_oracle_matches_reference(case, golden_dir):
     plan = P.ewald_plan(float(g["accuracy"]), g["q"], float(g["cut_coul"]), prd)
     assert plan.kcount == int(g["kcount"])                                  # k-vector set: exact
     assert (plan.kxmax, plan.kymax, plan.kzmax) == tuple(int(v) for v in g["kxyzmax"])
-    assert abs(plan.g_ewald - float(g["g_ewald_printed"])) < 1e-6 * plan.g_ewald  # printed with 6 digits
+    assert abs(plan.g_ewald - float(g["g_ewald_printed"])) < 5e-6 * plan.g_ewald  # printed with 6 significant digits
     r = P.ewald_compute(plan, g["x"], g["q"], prd)
     assert abs(r["energy"] - float(g["elong"])) < 1e-12 * abs(float(g["elong"]))
     # forces / virial of the reference are differences of two runs: ~1e-12 relative noise
