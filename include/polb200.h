@@ -169,6 +169,41 @@ int polb200_decomp_plan(int nranks, int rank, const int procgrid[3], const int p
                         const double boxhi[3], int dest[27], int src[27], int wrap[81], double sublo[3],
                         double subhi[3]);
 
+/* ---- KSpace: reciprocal-space Ewald ------------------------------------------------
+ * Replaces class Ewald of the reference (src/KSPACE/ewald.{h,cpp}, `kspace_style ewald <accuracy>`), the
+ * long-range partner every input of the pair style needs: same g_ewald / kmax selection, same half-space k set,
+ * same energy (incl. self and neutralising terms), forces and virial.  Orthogonal, fully periodic boxes; no slab
+ * correction, no per-atom tallies, no group/group.  A separate handle: LAMMPS owns Pair and KSpace separately. */
+typedef struct polb200_ewald polb200_ewald_t;
+
+typedef struct {
+  double accuracy_relative;   /* the argument of kspace_style ewald (KSpace::accuracy_relative) */
+  double g_ewald;             /* > 0: kspace_modify gewald; <= 0: estimate as Ewald::init (ewald.cpp:153-160) */
+  double qqrd2e;              /* force->qqrd2e */
+  double two_charge_force;    /* KSpace::two_charge_force (src/kspace.cpp:79-81) */
+  double qsum, qsqsum;        /* KSpace::qsum_qsq over all atoms (src/kspace.cpp:271-306) */
+  long natoms;                /* atom->natoms */
+  double cutoff;              /* the pair style's cut_coul (extract("cut_coul")) */
+  double boxlo[3], boxhi[3];
+  int periodic[3];
+} polb200_ewald_setup;
+
+typedef struct {
+  double g_ewald, gsqmx;
+  int kxmax, kymax, kzmax, kmax, kcount;  /* what Ewald::init prints (ewald.cpp:186-205) */
+} polb200_ewald_info;
+
+int polb200_ewald_create(polb200_ewald_t **e, int device);
+void polb200_ewald_destroy(polb200_ewald_t *e);
+const char *polb200_ewald_last_error(const polb200_ewald_t *e);
+/* Ewald::init + setup (ewald.cpp:87-340); call again when the box or the charges change (Ewald::setup) */
+int polb200_ewald_init(polb200_ewald_t *e, const polb200_ewald_setup *in, polb200_ewald_info *info);
+/* Ewald::compute (ewald.cpp:357-497): f[nlocal][3] += KSpace forces; *energy / virial[6] set when the global bits
+ * of eflag / vflag ask for them.  on_device: x, q, f are device pointers on this GPU. */
+int polb200_ewald_compute(polb200_ewald_t *e, int nlocal, const double *x, const double *q, double *f, int eflag,
+                          int vflag, int on_device, double *energy, double virial[6]);
+double polb200_ewald_last_ms(const polb200_ewald_t *e);  /* CUDA-event time of the last compute */
+
 /* ---- introspection for tests and profiling ------------------------------------------------------ */
 
 /* Copy an internal device array to host.  names: "perm" (int nlocal: sorted->caller index),

@@ -1106,6 +1106,67 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
 }  // namespace polb200
 
 // =====================================================================================================
+// reciprocal-space Ewald
+// =====================================================================================================
+#include "ewald.cuh"
+
+struct polb200_ewald {
+  std::string err;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[2] = {};
+  long launches = 0;
+  bool ready = false;
+  // plan (Ewald::init + setup, ewald.cpp:87-340)
+  double g_ewald = 0.0, gsqmx = 0.0, accuracy = 0.0, qqrd2e = 0.0, qsum = 0.0, qsqsum = 0.0, volume = 0.0;
+  double unitk[3] = {0, 0, 0};
+  int kxmax = 0, kymax = 0, kzmax = 0, kmax = 0, nk = 0, slots = 0;
+  DBuf<EwaldK> kv;
+  DBuf<double2> S, phase;
+  DBuf<double> c_x, c_q, c_f, out;
+  HPinned<double> h_out, h_f;
+  int sfac_smem_set = 0, force_smem_set = 0;
+  float ms_last = 0.f;
+};
+
+namespace polb200 {
+
+static double ewald_rms(int km, double prd, long natoms, double q2, double g)
+{
+  if (natoms == 0) natoms = 1;  // ewald.cpp:345
+  const double pi = 3.14159265358979323846;
+  return 2.0 * q2 * g / prd * sqrt(1.0 / (pi * km * natoms)) * exp(-pi * pi * km * km / (g * g * prd * prd));
+}
+
+// host: the half-space k set, kx fastest inside (kz, ky) so that warps of the structure-factor kernel read
+// consecutive shared-memory slots.  Same membership as Ewald::coeffs (ewald.cpp:760-1026): first non-zero
+// component positive; axis vectors up to kmax, others up to the per-dimension maxima; |k|^2 <= gsqmx.
+static void ewald_build_kset(polb200_ewald *e, std::vector<EwaldK> &out)
+{
+  const double pi = 3.14159265358979323846;
+  const double ginv2 = 1.0 / (e->g_ewald * e->g_ewald), preu = 4.0 * pi / e->volume;
+  out.clear();
+  for (int kz = -e->kmax; kz <= e->kmax; kz++)
+    for (int ky = -e->kmax; ky <= e->kmax; ky++)
+      for (int kx = 0; kx <= e->kmax; kx++) {
+        if (kx == 0 && (ky < 0 || (ky == 0 && kz <= 0))) continue;
+        const int nz = (kx != 0) + (ky != 0) + (kz != 0);
+        if (nz == 1) {
+          if (abs(kx) > e->kmax || abs(ky) > e->kmax || abs(kz) > e->kmax) continue;
+        } else if (abs(kx) > e->kxmax || abs(ky) > e->kymax || abs(kz) > e->kzmax) continue;
+        const double a = kx * e->unitk[0], b = ky * e->unitk[1], c = kz * e->unitk[2];
+        const double sqk = a * a + b * b + c * c;
+        if (sqk > e->gsqmx) continue;
+        EwaldK k;
+        k.kx = kx; k.ky = ky; k.kz = kz; k.pad = 0;
+        k.ug = preu * exp(-0.25 * sqk * ginv2) / sqk;
+        out.push_back(k);
+      }
+}
+
+}  // namespace polb200
+
+// =====================================================================================================
 // C ABI
 // =====================================================================================================
 
@@ -1123,6 +1184,24 @@ static int guarded(polb200_t *h, F &&fn)
     return POLB200_ERR_CUDA;
   } catch (const std::exception &e) {
     if (h) h->err = e.what();
+    return POLB200_ERR_ARG;
+  }
+}
+
+template <class F>
+static int ewald_guarded(polb200_ewald *e, F &&fn)
+{
+  try {
+    fn();
+    return POLB200_OK;
+  } catch (const StyleError &x) {
+    e->err = x.msg;
+    return x.code;
+  } catch (const CudaError &x) {
+    e->err = x.msg;
+    return POLB200_ERR_CUDA;
+  } catch (const std::exception &x) {
+    e->err = x.what();
     return POLB200_ERR_ARG;
   }
 }
@@ -1577,5 +1656,184 @@ int polb200_decomp_plan(int nranks, int rank, const int procgrid[3], const int p
   }
   return POLB200_OK;
 }
+
+
+// ---- reciprocal-space Ewald ------------------------------------------------------------------------------
+int polb200_ewald_create(polb200_ewald_t **out, int device)
+{
+  if (!out) return POLB200_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+    fprintf(stderr, "polb200_ewald_create: no usable CUDA device %d (found %d); there is no CPU fallback\n", device, count);
+    return POLB200_ERR_CUDA;
+  }
+  polb200_ewald *e = new polb200_ewald();
+  e->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&e->ev[0]) != cudaSuccess || cudaEventCreate(&e->ev[1]) != cudaSuccess) {
+    delete e;
+    return POLB200_ERR_CUDA;
+  }
+  *out = e;
+  return POLB200_OK;
+}
+
+void polb200_ewald_destroy(polb200_ewald_t *e)
+{
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  e->kv.release(); e->S.release(); e->phase.release();
+  e->c_x.release(); e->c_q.release(); e->c_f.release(); e->out.release();
+  e->h_out.release(); e->h_f.release();
+  cudaEventDestroy(e->ev[0]); cudaEventDestroy(e->ev[1]);
+  cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+const char *polb200_ewald_last_error(const polb200_ewald_t *e) { return e ? e->err.c_str() : "null handle"; }
+
+int polb200_ewald_init(polb200_ewald_t *e, const polb200_ewald_setup *in, polb200_ewald_info *info)
+{
+  if (!e || !in) return POLB200_ERR_ARG;
+  return ewald_guarded(e, [&] {
+    CUDA_CHECK(cudaSetDevice(e->device));
+    const double pi = 3.14159265358979323846;
+    double prd[3];
+    for (int d = 0; d < 3; d++) {
+      prd[d] = in->boxhi[d] - in->boxlo[d];
+      if (!(prd[d] > 0.0)) throw StyleError{POLB200_ERR_ARG, "Box bounds are invalid"};
+      if (!in->periodic[d]) throw StyleError{POLB200_ERR_UNSUPPORTED, "Cannot use nonperiodic boundaries with Ewald"};
+    }
+    e->qqrd2e = in->qqrd2e;
+    e->qsum = in->qsum;
+    e->qsqsum = in->qsqsum;
+    e->accuracy = in->accuracy_relative * in->two_charge_force;  // ewald.cpp:131-132
+    const double q2 = in->qsqsum * in->qqrd2e;                   // kspace.cpp:293
+    double g = in->g_ewald;
+    if (!(g > 0.0)) {  // ewald.cpp:153-160
+      if (e->accuracy <= 0.0) throw StyleError{POLB200_ERR_ARG, "KSpace accuracy must be > 0"};
+      if (q2 == 0.0) throw StyleError{POLB200_ERR_ARG, "Must use 'kspace_modify gewald' for uncharged system"};
+      g = e->accuracy * sqrt((double)in->natoms * in->cutoff * prd[0] * prd[1] * prd[2]) / (2.0 * q2);
+      if (g >= 1.0) g = (1.35 - 0.15 * log(e->accuracy)) / in->cutoff;
+      else g = sqrt(-log(g)) / in->cutoff;
+    }
+    e->g_ewald = g;
+    e->volume = prd[0] * prd[1] * prd[2];
+    int km[3];
+    double gs = 0.0;
+    for (int d = 0; d < 3; d++) {  // ewald.cpp:241-275
+      e->unitk[d] = 2.0 * pi / prd[d];
+      km[d] = 1;
+      while (ewald_rms(km[d], prd[d], in->natoms, q2, g) > e->accuracy) km[d]++;
+      gs = std::max(gs, e->unitk[d] * e->unitk[d] * km[d] * km[d]);
+    }
+    e->kxmax = km[0]; e->kymax = km[1]; e->kzmax = km[2];
+    e->kmax = std::max(km[0], std::max(km[1], km[2]));
+    e->gsqmx = gs * 1.00001;  // ewald.cpp:311
+    std::vector<EwaldK> ks;
+    ewald_build_kset(e, ks);
+    e->nk = (int)ks.size();
+    e->slots = ew_row_slots(e->kmax);
+    e->kv.ensure(ks.size() + 1);
+    e->S.ensure(ks.size() + 1);
+    e->out.ensure(8);
+    e->h_out.ensure(8);
+    if (!ks.empty()) CUDA_CHECK(cudaMemcpy(e->kv.p, ks.data(), ks.size() * sizeof(EwaldK), cudaMemcpyHostToDevice));
+    e->ready = true;
+    if (info) {
+      info->g_ewald = g;
+      info->kxmax = km[0]; info->kymax = km[1]; info->kzmax = km[2];
+      info->kmax = e->kmax;
+      info->kcount = e->nk;
+      info->gsqmx = e->gsqmx;
+    }
+  });
+}
+
+int polb200_ewald_compute(polb200_ewald_t *e, int nlocal, const double *x, const double *q, double *f, int eflag, int vflag,
+                          int on_device, double *energy, double virial[6])
+{
+  if (!e || nlocal < 0 || (nlocal > 0 && (!x || !q || !f))) return POLB200_ERR_ARG;
+  return ewald_guarded(e, [&] {
+    if (!e->ready) throw StyleError{POLB200_ERR_STATE, "polb200_ewald_init has not been called"};
+    if ((eflag / 2) || (vflag / 4)) throw StyleError{POLB200_ERR_UNSUPPORTED, "per-atom KSpace tallies are not implemented on the device"};
+    CUDA_CHECK(cudaSetDevice(e->device));
+    if (energy) *energy = 0.0;
+    if (virial) for (int k = 0; k < 6; k++) virial[k] = 0.0;
+    const int n = nlocal, nk = e->nk;
+    if (e->qsqsum == 0.0 || n == 0 || nk == 0) return;  // ewald.cpp:376
+    const double pi = 3.14159265358979323846;
+    CUDA_CHECK(cudaEventRecord(e->ev[0], e->stream));
+    const double *dx = x, *dq = q;
+    double *df = f;
+    if (!on_device) {
+      e->c_x.ensure((size_t)3 * n); e->c_q.ensure(n); e->c_f.ensure((size_t)3 * n);
+      CUDA_CHECK(cudaMemcpyAsync(e->c_x.p, x, (size_t)3 * n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+      CUDA_CHECK(cudaMemcpyAsync(e->c_q.p, q, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+      CUDA_CHECK(cudaMemsetAsync(e->c_f.p, 0, (size_t)3 * n * sizeof(double), e->stream));
+      dx = e->c_x.p; dq = e->c_q.p; df = e->c_f.p;
+    }
+    const int slots = e->slots;
+    e->phase.ensure((size_t)3 * n * slots);
+    k_ewald_phase<<<cdiv((long)3 * n, 256), 256, 0, e->stream>>>(n, dx, e->unitk[0], e->unitk[1], e->unitk[2], e->kxmax, e->kymax,
+                                                                 e->kzmax, slots, e->phase.p);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemsetAsync(e->S.p, 0, (size_t)nk * sizeof(double2), e->stream));
+    // structure factors: k-vectors x atom slices (enough CTAs to fill the machine, few enough atomics)
+    const int kblocks = cdiv(nk, EW_KTHREADS);
+    int slices = std::max(1, std::min(cdiv(n, 4 * EW_TILE), cdiv(4 * 148, kblocks)));
+    const int sfac_smem = (3 * EW_TILE * slots + EW_TILE) * (int)sizeof(double2);
+    if (sfac_smem > e->sfac_smem_set) {
+      CUDA_CHECK(cudaFuncSetAttribute(k_ewald_sfac, cudaFuncAttributeMaxDynamicSharedMemorySize, sfac_smem));
+      e->sfac_smem_set = sfac_smem;
+    }
+    k_ewald_sfac<<<dim3(kblocks, slices), EW_KTHREADS, sfac_smem, e->stream>>>(n, nk, e->kv.p, dq, e->phase.p, slots, e->S.p);
+    CUDA_CHECK(cudaGetLastError());
+    // forces: one thread per atom with its phase rows in shared memory
+    int athreads = EW_ATHREADS;
+    const int tile_b = EW_KTILE * (int)(sizeof(EwaldK) + sizeof(double2));
+    while (athreads > 32 && athreads * 3 * slots * (int)sizeof(double2) + tile_b > 200 * 1024) athreads -= 32;
+    const int force_smem = athreads * 3 * slots * (int)sizeof(double2) + tile_b;
+    if (force_smem > 220 * 1024) throw StyleError{POLB200_ERR_UNSUPPORTED, "Ewald kmax too large for the device force kernel"};
+    if (force_smem > e->force_smem_set) {
+      CUDA_CHECK(cudaFuncSetAttribute(k_ewald_force, cudaFuncAttributeMaxDynamicSharedMemorySize, force_smem));
+      e->force_smem_set = force_smem;
+    }
+    k_ewald_force<<<cdiv(n, athreads), athreads, force_smem, e->stream>>>(n, nk, e->kv.p, e->S.p, dq, e->phase.p, slots, e->unitk[0],
+                                                                          e->unitk[1], e->unitk[2], e->qqrd2e, df);
+    CUDA_CHECK(cudaGetLastError());
+    e->launches += 3;
+    const bool ev = (eflag & 1) || (vflag % 4);
+    if (ev) {
+      k_ewald_energy<<<1, 256, 0, e->stream>>>(nk, e->kv.p, e->S.p, e->unitk[0], e->unitk[1], e->unitk[2],
+                                               1.0 / (e->g_ewald * e->g_ewald), e->out.p);
+      CUDA_CHECK(cudaGetLastError());
+      e->launches++;
+      CUDA_CHECK(cudaMemcpyAsync(e->h_out.p, e->out.p, 7 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    }
+    if (!on_device) {
+      e->h_f.ensure((size_t)3 * n);
+      CUDA_CHECK(cudaMemcpyAsync(e->h_f.p, e->c_f.p, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    }
+    CUDA_CHECK(cudaEventRecord(e->ev[1], e->stream));
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    cudaEventElapsedTime(&e->ms_last, e->ev[0], e->ev[1]);
+    if (!on_device)
+      for (size_t k = 0; k < (size_t)3 * n; k++) f[k] += e->h_f.p[k];
+    if (ev) {
+      if ((eflag & 1) && energy) {  // ewald.cpp:455-462
+        double en = e->h_out.p[0];
+        en -= e->g_ewald * e->qsqsum / sqrt(pi) + 0.5 * pi * e->qsum * e->qsum / (e->g_ewald * e->g_ewald * e->volume);
+        *energy = en * e->qqrd2e;
+      }
+      if ((vflag % 4) && virial)
+        for (int k = 0; k < 6; k++) virial[k] = e->h_out.p[1 + k] * e->qqrd2e;  // ewald.cpp:466-474
+    }
+  });
+}
+
+double polb200_ewald_last_ms(const polb200_ewald_t *e) { return e ? (double)e->ms_last : 0.0; }
 
 }  // extern "C"

@@ -26,6 +26,8 @@ ABI_SYMBOLS = [
     "polb200_read_restart", "polb200_set_box", "polb200_compute", "polb200_comm_id_size",
     "polb200_comm_create_id", "polb200_comm_init", "polb200_subdomain", "polb200_debug_fetch",
     "polb200_launch_count", "polb200_set_option", "polb200_decomp_plan", "polb200_tail",
+    "polb200_ewald_create", "polb200_ewald_destroy", "polb200_ewald_last_error", "polb200_ewald_init",
+    "polb200_ewald_compute", "polb200_ewald_last_ms",
 ]
 
 
@@ -52,6 +54,17 @@ class Result(C.Structure):
                 ("npairs_full", C.c_long), ("nghost", C.c_int), ("ms_neigh", C.c_float),
                 ("ms_pair", C.c_float), ("ms_scf", C.c_float), ("ms_force", C.c_float),
                 ("ms_total", C.c_float)]
+
+
+class EwaldSetup(C.Structure):
+    _fields_ = [("accuracy_relative", C.c_double), ("g_ewald", C.c_double), ("qqrd2e", C.c_double),
+                ("two_charge_force", C.c_double), ("qsum", C.c_double), ("qsqsum", C.c_double), ("natoms", C.c_long),
+                ("cutoff", C.c_double), ("boxlo", C.c_double * 3), ("boxhi", C.c_double * 3), ("periodic", C.c_int * 3)]
+
+
+class EwaldInfo(C.Structure):
+    _fields_ = [("g_ewald", C.c_double), ("gsqmx", C.c_double), ("kxmax", C.c_int), ("kymax", C.c_int),
+                ("kzmax", C.c_int), ("kmax", C.c_int), ("kcount", C.c_int)]
 
 
 class Polb200Error(RuntimeError):
@@ -108,6 +121,15 @@ def lib():
         L.polb200_comm_create_id.argtypes = [C.c_void_p]
         L.polb200_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
         L.polb200_subdomain.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.polb200_ewald_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        L.polb200_ewald_destroy.argtypes = [C.c_void_p]
+        L.polb200_ewald_last_error.argtypes = [C.c_void_p]
+        L.polb200_ewald_last_error.restype = C.c_char_p
+        L.polb200_ewald_init.argtypes = [C.c_void_p, C.POINTER(EwaldSetup), C.POINTER(EwaldInfo)]
+        L.polb200_ewald_compute.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                            C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.polb200_ewald_last_ms.argtypes = [C.c_void_p]
+        L.polb200_ewald_last_ms.restype = C.c_double
         L.polb200_decomp_plan.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                           C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int),
                                           C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double),
@@ -333,3 +355,64 @@ class PairStyle:
 
     def launch_count(self, reset=False):
         return lib().polb200_launch_count(self._h, int(reset))
+
+
+class Ewald:
+    """`kspace_style ewald <accuracy>` on one GPU: the device counterpart of the reference's class Ewald
+    (src/KSPACE/ewald.cpp).  init() = Ewald::init + setup, compute() = Ewald::compute."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        rc = lib().polb200_ewald_create(C.byref(self._h), device)
+        if rc != OK:
+            raise Polb200Error(rc, "polb200_ewald_create failed (no CUDA device? there is no CPU fallback)")
+
+    def close(self):
+        if self._h:
+            lib().polb200_ewald_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != OK:
+            raise Polb200Error(rc, lib().polb200_ewald_last_error(self._h).decode())
+
+    def init(self, accuracy, q, cutoff, boxlo, boxhi, g_ewald=0.0, qqrd2e=REAL_QQRD2E, two_charge_force=REAL_QQRD2E,
+             periodic=(1, 1, 1), natoms=None):
+        q = np.asarray(q, dtype=np.float64)
+        s = EwaldSetup()
+        s.accuracy_relative, s.g_ewald, s.qqrd2e, s.two_charge_force = accuracy, g_ewald, qqrd2e, two_charge_force
+        s.qsum, s.qsqsum = float(np.cumsum(q)[-1]) if len(q) else 0.0, float(np.cumsum(q * q)[-1]) if len(q) else 0.0
+        s.natoms = len(q) if natoms is None else natoms
+        s.cutoff = cutoff
+        s.boxlo = (C.c_double * 3)(*[float(v) for v in boxlo])
+        s.boxhi = (C.c_double * 3)(*[float(v) for v in boxhi])
+        s.periodic = (C.c_int * 3)(*[int(v) for v in periodic])
+        info = EwaldInfo()
+        self._check(lib().polb200_ewald_init(self._h, C.byref(s), C.byref(info)))
+        return info
+
+    def compute(self, x, q, f, eflag=1, vflag=1):
+        """f (n,3) += KSpace forces; returns (energy, virial[6]).  Host numpy buffers."""
+        n = x.shape[0]
+        for a in (x, q, f):
+            assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+        e = C.c_double()
+        v = (C.c_double * 6)()
+        self._check(lib().polb200_ewald_compute(self._h, n, x.ctypes.data, q.ctypes.data, f.ctypes.data, eflag, vflag, 0,
+                                                C.byref(e), v))
+        return e.value, np.array(v[:])
+
+    def compute_device(self, n, x_ptr, q_ptr, f_ptr, eflag=1, vflag=1):
+        e = C.c_double()
+        v = (C.c_double * 6)()
+        self._check(lib().polb200_ewald_compute(self._h, n, x_ptr, q_ptr, f_ptr, eflag, vflag, 1, C.byref(e), v))
+        return e.value, np.array(v[:])
+
+    def last_ms(self):
+        return lib().polb200_ewald_last_ms(self._h)
