@@ -20,7 +20,9 @@ fi
 [ -f "$PKG/libpolb200.so" ] || make -C "$PKG/csrc"
 mkdir -p "$OUT"
 if [ -x "$OUT/lmp_b200" ] && [ "$OUT/lmp_b200" -nt "$HERE/pair_lj_cut_coul_long_polarization_b200.cpp" ] \
-   && [ "$OUT/lmp_b200" -nt "$HERE/pair_lj_cut_coul_long_polarization_b200.h" ] && [ -z "${POLB200_LMP_REBUILD:-}" ]; then
+   && [ "$OUT/lmp_b200" -nt "$HERE/pair_lj_cut_coul_long_polarization_b200.h" ] \
+   && [ "$OUT/lmp_b200" -nt "$HERE/ewald_b200.cpp" ] && [ "$OUT/lmp_b200" -nt "$HERE/ewald_b200.h" ] \
+   && [ "$OUT/lmp_b200" -nt "$ROOT/include/polb200.h" ] && [ -z "${POLB200_LMP_REBUILD:-}" ]; then
   echo "build_lmp_b200: $OUT/lmp_b200 is up to date"
   exit 0
 fi
@@ -44,6 +46,9 @@ cd "$W/src"
 # the swap: the reference's implementation leaves, the drop-in takes its file names
 cp "$HERE/pair_lj_cut_coul_long_polarization_b200.h" pair_lj_cut_coul_long_polarization.h
 cp "$HERE/pair_lj_cut_coul_long_polarization_b200.cpp" pair_lj_cut_coul_long_polarization.cpp
+# ... and so does the KSpace style every input of the pair style uses
+cp "$HERE/ewald_b200.h" ewald.h
+cp "$HERE/ewald_b200.cpp" ewald.cpp
 cp "$ROOT/include/polb200.h" .
 make -j"$JOBS" serial LIB="-L$PKG -lpolb200 -Wl,-rpath,'\$\$ORIGIN/../..'" > "$W/build.log" 2>&1 || { tail -40 "$W/build.log"; exit 1; }
 cp lmp_serial "$OUT/lmp_b200"
