@@ -1120,7 +1120,7 @@ struct polb200_ewald {
   // plan (Ewald::init + setup, ewald.cpp:87-340)
   double g_ewald = 0.0, gsqmx = 0.0, accuracy = 0.0, qqrd2e = 0.0, qsum = 0.0, qsqsum = 0.0, volume = 0.0;
   double unitk[3] = {0, 0, 0};
-  int kxmax = 0, kymax = 0, kzmax = 0, kmax = 0, nk = 0, slots = 0;
+  int kxmax = 0, kymax = 0, kzmax = 0, kmax = 0, nk = 0, nquads = 0, slots = 0;
   DBuf<EwaldK> kv;
   DBuf<double2> S, phase;
   DBuf<double> c_x, c_q, c_f, out;
@@ -1141,27 +1141,50 @@ static double ewald_rms(int km, double prd, long natoms, double q2, double g)
 // host: the half-space k set, kx fastest inside (kz, ky) so that warps of the structure-factor kernel read
 // consecutive shared-memory slots.  Same membership as Ewald::coeffs (ewald.cpp:760-1026): first non-zero
 // component positive; axis vectors up to kmax, others up to the per-dimension maxima; |k|^2 <= gsqmx.
-static void ewald_build_kset(polb200_ewald *e, std::vector<EwaldK> &out)
+static bool ewald_in_set(const polb200_ewald *e, int kx, int ky, int kz, double &sqk)
+{
+  if (kx < 0 || (kx == 0 && (ky < 0 || (ky == 0 && kz <= 0)))) return false;
+  const int nz = (kx != 0) + (ky != 0) + (kz != 0);
+  if (nz == 1) {
+    if (abs(kx) > e->kmax || abs(ky) > e->kmax || abs(kz) > e->kmax) return false;
+  } else if (abs(kx) > e->kxmax || abs(ky) > e->kymax || abs(kz) > e->kzmax) return false;
+  const double a = kx * e->unitk[0], b = ky * e->unitk[1], c = kz * e->unitk[2];
+  sqk = a * a + b * b + c * c;
+  return sqk <= e->gsqmx;
+}
+
+// quads of four consecutive kx per (ky,kz) row; slots of a row's last quad that fall outside the set get ug = 0.
+// Returns the number of real k-vectors (Ewald::kcount).
+static int ewald_build_kset(polb200_ewald *e, std::vector<EwaldK> &out)
 {
   const double pi = 3.14159265358979323846;
   const double ginv2 = 1.0 / (e->g_ewald * e->g_ewald), preu = 4.0 * pi / e->volume;
   out.clear();
+  int real = 0;
   for (int kz = -e->kmax; kz <= e->kmax; kz++)
-    for (int ky = -e->kmax; ky <= e->kmax; ky++)
-      for (int kx = 0; kx <= e->kmax; kx++) {
-        if (kx == 0 && (ky < 0 || (ky == 0 && kz <= 0))) continue;
-        const int nz = (kx != 0) + (ky != 0) + (kz != 0);
-        if (nz == 1) {
-          if (abs(kx) > e->kmax || abs(ky) > e->kmax || abs(kz) > e->kmax) continue;
-        } else if (abs(kx) > e->kxmax || abs(ky) > e->kymax || abs(kz) > e->kzmax) continue;
-        const double a = kx * e->unitk[0], b = ky * e->unitk[1], c = kz * e->unitk[2];
-        const double sqk = a * a + b * b + c * c;
-        if (sqk > e->gsqmx) continue;
+    for (int ky = -e->kmax; ky <= e->kmax; ky++) {
+      int lo = -1, hi = -1;
+      double sqk;
+      for (int kx = 0; kx <= e->kmax; kx++)
+        if (ewald_in_set(e, kx, ky, kz, sqk)) {
+          if (lo < 0) lo = kx;
+          hi = kx;
+        }
+      if (lo < 0) continue;
+      for (int q0 = lo; q0 <= hi; q0 += 4) {
         EwaldK k;
-        k.kx = kx; k.ky = ky; k.kz = kz; k.pad = 0;
-        k.ug = preu * exp(-0.25 * sqk * ginv2) / sqk;
+        k.kx0 = q0; k.ky = ky; k.kz = kz; k.pad = 0;
+        for (int j = 0; j < 4; j++) {
+          k.ug[j] = 0.0;
+          if (q0 + j <= hi && ewald_in_set(e, q0 + j, ky, kz, sqk)) {
+            k.ug[j] = preu * exp(-0.25 * sqk * ginv2) / sqk;
+            real++;
+          }
+        }
         out.push_back(k);
       }
+    }
+  return real;
 }
 
 }  // namespace polb200
@@ -1733,11 +1756,11 @@ int polb200_ewald_init(polb200_ewald_t *e, const polb200_ewald_setup *in, polb20
     e->kmax = std::max(km[0], std::max(km[1], km[2]));
     e->gsqmx = gs * 1.00001;  // ewald.cpp:311
     std::vector<EwaldK> ks;
-    ewald_build_kset(e, ks);
-    e->nk = (int)ks.size();
+    e->nk = ewald_build_kset(e, ks);
+    e->nquads = (int)ks.size();
     e->slots = ew_row_slots(e->kmax);
     e->kv.ensure(ks.size() + 1);
-    e->S.ensure(ks.size() + 1);
+    e->S.ensure(4 * ks.size() + 4);
     e->out.ensure(8);
     e->h_out.ensure(8);
     if (!ks.empty()) CUDA_CHECK(cudaMemcpy(e->kv.p, ks.data(), ks.size() * sizeof(EwaldK), cudaMemcpyHostToDevice));
@@ -1762,7 +1785,7 @@ int polb200_ewald_compute(polb200_ewald_t *e, int nlocal, const double *x, const
     CUDA_CHECK(cudaSetDevice(e->device));
     if (energy) *energy = 0.0;
     if (virial) for (int k = 0; k < 6; k++) virial[k] = 0.0;
-    const int n = nlocal, nk = e->nk;
+    const int n = nlocal, nk = e->nquads;  // the kernels walk quads of four k-vectors
     if (e->qsqsum == 0.0 || n == 0 || nk == 0) return;  // ewald.cpp:376
     const double pi = 3.14159265358979323846;
     CUDA_CHECK(cudaEventRecord(e->ev[0], e->stream));
@@ -1777,10 +1800,9 @@ int polb200_ewald_compute(polb200_ewald_t *e, int nlocal, const double *x, const
     }
     const int slots = e->slots;
     e->phase.ensure((size_t)3 * n * slots);
-    k_ewald_phase<<<cdiv((long)3 * n, 256), 256, 0, e->stream>>>(n, dx, e->unitk[0], e->unitk[1], e->unitk[2], e->kxmax, e->kymax,
-                                                                 e->kzmax, slots, e->phase.p);
+    k_ewald_phase<<<cdiv((long)3 * n, 256), 256, 0, e->stream>>>(n, dx, e->unitk[0], e->unitk[1], e->unitk[2], slots, e->phase.p);
     CUDA_CHECK(cudaGetLastError());
-    CUDA_CHECK(cudaMemsetAsync(e->S.p, 0, (size_t)nk * sizeof(double2), e->stream));
+    CUDA_CHECK(cudaMemsetAsync(e->S.p, 0, (size_t)4 * nk * sizeof(double2), e->stream));
     // structure factors: k-vectors x atom slices (enough CTAs to fill the machine, few enough atomics)
     const int kblocks = cdiv(nk, EW_KTHREADS);
     int slices = std::max(1, std::min(cdiv(n, 4 * EW_TILE), cdiv(4 * 148, kblocks)));
@@ -1793,7 +1815,7 @@ int polb200_ewald_compute(polb200_ewald_t *e, int nlocal, const double *x, const
     CUDA_CHECK(cudaGetLastError());
     // forces: one thread per atom with its phase rows in shared memory
     int athreads = EW_ATHREADS;
-    const int tile_b = EW_KTILE * (int)(sizeof(EwaldK) + sizeof(double2));
+    const int tile_b = EW_KTILE * (int)(sizeof(EwaldK) + 4 * sizeof(double2));
     while (athreads > 32 && athreads * 3 * slots * (int)sizeof(double2) + tile_b > 200 * 1024) athreads -= 32;
     const int force_smem = athreads * 3 * slots * (int)sizeof(double2) + tile_b;
     if (force_smem > 220 * 1024) throw StyleError{POLB200_ERR_UNSUPPORTED, "Ewald kmax too large for the device force kernel"};
