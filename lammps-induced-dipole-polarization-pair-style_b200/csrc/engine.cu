@@ -1122,7 +1122,7 @@ struct polb200_ewald {
   double unitk[3] = {0, 0, 0};
   int kxmax = 0, kymax = 0, kzmax = 0, kmax = 0, nk = 0, nquads = 0, slots = 0;
   DBuf<EwaldK> kv;
-  DBuf<double2> S, phase;
+  DBuf<double2> S, Spart, phase;
   DBuf<double> c_x, c_q, c_f, out;
   HPinned<double> h_out, h_f;
   int sfac_smem_set = 0, force_smem_set = 0;
@@ -1707,7 +1707,7 @@ void polb200_ewald_destroy(polb200_ewald_t *e)
   if (!e) return;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
-  e->kv.release(); e->S.release(); e->phase.release();
+  e->kv.release(); e->S.release(); e->Spart.release(); e->phase.release();
   e->c_x.release(); e->c_q.release(); e->c_f.release(); e->out.release();
   e->h_out.release(); e->h_f.release();
   cudaEventDestroy(e->ev[0]); cudaEventDestroy(e->ev[1]);
@@ -1802,7 +1802,7 @@ int polb200_ewald_compute(polb200_ewald_t *e, int nlocal, const double *x, const
     e->phase.ensure((size_t)3 * n * slots);
     k_ewald_phase<<<cdiv((long)3 * n, 256), 256, 0, e->stream>>>(n, dx, e->unitk[0], e->unitk[1], e->unitk[2], slots, e->phase.p);
     CUDA_CHECK(cudaGetLastError());
-    CUDA_CHECK(cudaMemsetAsync(e->S.p, 0, (size_t)4 * nk * sizeof(double2), e->stream));
+
     // structure factors: k-vectors x atom slices (enough CTAs to fill the machine, few enough atomics)
     const int kblocks = cdiv(nk, EW_KTHREADS);
     int slices = std::max(1, std::min(cdiv(n, 4 * EW_TILE), cdiv(4 * 148, kblocks)));
@@ -1811,8 +1811,12 @@ int polb200_ewald_compute(polb200_ewald_t *e, int nlocal, const double *x, const
       CUDA_CHECK(cudaFuncSetAttribute(k_ewald_sfac, cudaFuncAttributeMaxDynamicSharedMemorySize, sfac_smem));
       e->sfac_smem_set = sfac_smem;
     }
-    k_ewald_sfac<<<dim3(kblocks, slices), EW_KTHREADS, sfac_smem, e->stream>>>(n, nk, e->kv.p, dq, e->phase.p, slots, e->S.p);
+    e->Spart.ensure((size_t)slices * 4 * nk + 4);
+    k_ewald_sfac<<<dim3(kblocks, slices), EW_KTHREADS, sfac_smem, e->stream>>>(n, nk, e->kv.p, dq, e->phase.p, slots, e->Spart.p);
     CUDA_CHECK(cudaGetLastError());
+    k_ewald_sum_slices<<<cdiv((long)4 * nk, 256), 256, 0, e->stream>>>(4 * nk, slices, e->Spart.p, e->S.p);
+    CUDA_CHECK(cudaGetLastError());
+    e->launches++;
     // forces: one thread per atom with its phase rows in shared memory
     int athreads = EW_ATHREADS;
     const int tile_b = EW_KTILE * (int)(sizeof(EwaldK) + 4 * sizeof(double2));

@@ -60,7 +60,7 @@ __global__ void k_ewald_phase(int n, const double *__restrict__ x, double ux, do
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ double2 conj_if(double2 a, bool neg) { return make_double2(a.x, neg ? -a.y : a.y); }
 
-// grid = (ceil(nquads / EW_KTHREADS), nslices); S (4 per quad) must be zeroed before the launch.
+// grid = (ceil(nquads / EW_KTHREADS), nslices); S here = per-slice partial sums [nslices][4 * nquads].
 // Register tile: per atom one product P = q Ey Ez serves the four kx of the quad.
 __global__ void __launch_bounds__(EW_KTHREADS)
 k_ewald_sfac(int n, int nquads, const EwaldK *__restrict__ kv, const double *__restrict__ q, const double2 *__restrict__ phase,
@@ -103,12 +103,25 @@ k_ewald_sfac(int n, int nquads, const EwaldK *__restrict__ kv, const double *__r
       }
     }
   }
+  // every (slice, quad) owns its slot: no atomics, and k_ewald_sum_slices adds the slices in a fixed order, so the
+  // structure factors (and with them energy and forces) are bit-reproducible run to run
   if (k < nquads)
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      atomicAdd(&S[4 * (size_t)k + j].x, acc[j].x);
-      atomicAdd(&S[4 * (size_t)k + j].y, acc[j].y);
-    }
+    for (int j = 0; j < 4; j++) S[((size_t)blockIdx.y * nquads + k) * 4 + j] = acc[j];
+}
+
+// S[k] = sum over slices of Spart[slice][k], slices in ascending order
+__global__ void k_ewald_sum_slices(int nslots, int nslices, const double2 *__restrict__ Spart, double2 *__restrict__ S)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nslots) return;
+  double2 a = make_double2(0.0, 0.0);
+  for (int s = 0; s < nslices; s++) {
+    const double2 v = Spart[(size_t)s * nslots + t];
+    a.x += v.x;
+    a.y += v.y;
+  }
+  S[t] = a;
 }
 
 // ek_i = sum_k 2 ug k Im(exp(i k.r_i) conj S(k));  f_i += qscale q_i ek_i   (ewald.cpp:417-449)

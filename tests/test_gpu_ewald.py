@@ -63,3 +63,17 @@ def test_device_ewald_properties_at_bench_size():
     ek = energy + self_term                                      # neutral system: no background term
     assert ek > 0 and virial[:3].sum() < 3 * ek                  # each vg diagonal < 1
     print(f"device Ewald, 32000 atoms, kcount {info.kcount}: {ms:.3f} ms per compute")
+
+
+def test_device_ewald_is_bit_reproducible():
+    sysm = H.lj_charge_fluid(10)
+    outs = []
+    for _ in range(3):
+        e = pb.Ewald(device=0)
+        e.init(1e-4, sysm.q, 12.0, sysm.boxlo, sysm.boxhi)
+        f = np.zeros((sysm.n, 3))
+        energy, virial = e.compute(np.ascontiguousarray(sysm.x), np.ascontiguousarray(sysm.q), f)
+        e.close()
+        outs.append((energy, f.copy(), virial))
+    for energy, f, virial in outs[1:]:
+        assert energy == outs[0][0] and np.array_equal(f, outs[0][1]) and np.array_equal(virial, outs[0][2])

@@ -202,3 +202,18 @@ def test_tail_correction(style):
     style.pair_modify(["shift", "yes"])
     with pytest.raises(pb.Polb200Error, match="Cannot have both pair_modify shift and tail"):
         style.init(g_ewald=0.25)
+
+
+def test_device_entry_points_fail_loudly_without_a_gpu():
+    """No CUDA device => no handle: the product never falls back to a CPU implementation (pair path and KSpace)."""
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(pb.Polb200Error):
+        pb.PairStyle(device=0)
+    with pytest.raises(pb.Polb200Error):
+        pb.Ewald(device=0)
