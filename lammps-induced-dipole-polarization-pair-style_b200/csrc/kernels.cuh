@@ -1563,8 +1563,9 @@ k_group_build(int ngroups, int nloc, DevParams P, const double4 *__restrict__ xq
 }
 
 // chunk-record layout of the tight group rows (TMA sweep): a row is a sequence of 64-entry records of
-// GCHUNK*36 bytes = [64 x 32 B scalars][64 x 4 B indices], contiguous in memory, so that ONE bulk copy
-// fetches a whole chunk (indices included) as a single 2304-byte request
+// GCHUNK*36 bytes = [64 x 16 B scalars of member a][64 x 16 B of member b][64 x 4 B indices], contiguous in memory,
+// so that ONE bulk copy fetches a whole chunk (indices included) as a single 2304-byte request and the sweep's
+// LDS.128 of either member have a lane stride of 16 B (conflict free; {s1a,s2a,s1b,s2b} per entry was 2-way)
 constexpr int GCHUNK = 64;
 constexpr int GCHUNK_BYTES = GCHUNK * 36;
 __global__ void k_group_chunk_count(int ngroups, const int *__restrict__ rowcount, unsigned long long *__restrict__ cnt)
@@ -1615,7 +1616,8 @@ k_group_cache(int ngroups, DevParams P, const int *__restrict__ group_first, con
       const int pos = n + __popc(m & ((1u << lane) - 1));
       if (CHUNKED) {
         unsigned char *rec = crec + (cstart[g] + (unsigned long long)(pos / GCHUNK)) * GCHUNK_BYTES;
-        reinterpret_cast<double4 *>(rec)[pos % GCHUNK] = sc;
+        reinterpret_cast<double2 *>(rec)[pos % GCHUNK] = make_double2(sc.x, sc.y);                 // member a
+        reinterpret_cast<double2 *>(rec + GCHUNK * 16)[pos % GCHUNK] = make_double2(sc.z, sc.w);   // member b
         reinterpret_cast<int *>(rec + GCHUNK * 32)[pos % GCHUNK] = j;
       } else {
         tneigh[beg + pos] = j;
@@ -1838,7 +1840,8 @@ k_sweep_group_tma(int ngroups, const int *__restrict__ group_first, const int *_
     for (int c = 0; c < nchunks; c++, cc++) {
       const unsigned slot = cc % NSTAGE;
       mbar_wait(bars + slot, (cc / NSTAGE) & 1u);
-      const double4 *sc_s = reinterpret_cast<const double4 *>(ring + (size_t)slot * STAGE_BYTES);
+      const double2 *sa_s = reinterpret_cast<const double2 *>(ring + (size_t)slot * STAGE_BYTES);
+      const double2 *sb_s = sa_s + CHUNK;
       const int *ix_s = reinterpret_cast<const int *>(ring + (size_t)slot * STAGE_BYTES + CHUNK * 32);
       int j[TRIPS];
       double4 sc[TRIPS], xj[TRIPS], mj[TRIPS];
@@ -1846,7 +1849,9 @@ k_sweep_group_tma(int ngroups, const int *__restrict__ group_first, const int *_
       for (int t = 0; t < TRIPS; t++) {
         const bool live = c * CHUNK + t * 32 + lane < cnt;
         j[t] = live ? ix_s[t * 32 + lane] : a;
-        sc[t] = live ? sc_s[t * 32 + lane] : make_double4(0, 0, 0, 0);
+        const double2 ua = live ? sa_s[t * 32 + lane] : make_double2(0, 0);
+        const double2 ub = live ? sb_s[t * 32 + lane] : make_double2(0, 0);
+        sc[t] = make_double4(ua.x, ua.y, ub.x, ub.y);
       }
 #pragma unroll
       for (int t = 0; t < TRIPS; t++) {
