@@ -4,6 +4,8 @@
 // Streams/graphs: everything of one call is enqueued on one stream; the host synchronises only
 // where the reference's control flow needs a device value (ghost count at a rebuild, the convergence
 // test of `precision` mode).  fixed_iteration mode enqueues all sweeps back to back with no sync.
+// Also in this translation unit: the multi-GPU layer (comm.cuh, included after the handle definition) and the
+// reciprocal-space Ewald (ewald.cuh + polb200_ewald_* at the end of the C ABI block).
 #include <cub/cub.cuh>
 #include <cuda_runtime.h>
 

@@ -5,6 +5,12 @@
 // per-lane FP64 accumulators, warp-shuffle reduction, fixed-order block/grid reductions so results
 // are bit-reproducible run to run.  Tensor cores are not used: the work is a sparse pairwise
 // gather with ~60-80 FP64 operations per pair, bounded by the FP64 pipe / L2 gathers.
+// The dominant kernel (one Jacobi dipole iteration in list mode) departs from that shape where ncu said so:
+// two cell-row neighbours per warp (pair groups) and a TMA bulk-copy / mbarrier shared-memory ring for the
+// per-pair stream -- see "pair-group form" and "TMA-fed pair-group sweep" below and DESIGN.md §4.
+// File map: stage 1 binning/ghosts/lists -> stage 2 LJ+Coulomb+field -> stage 3 sweeps (first version,
+// matrix-free, cached, sequential GS, rank metric) -> stage 4 forces -> stage 5 reductions -> multi-GPU halo
+// (send lists, pack/unpack, peer push, signal/wait) -> pair groups -> TMA sweep -> blocked exact-mode GS.
 //
 // HBM layout (cell-sorted SoA of 32-byte records, ghosts after owned atoms):
 //   xq [next] double4 {x,y,z,q}            mua[next] double4 {mu_x,mu_y,mu_z,alpha}
