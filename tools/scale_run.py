@@ -74,6 +74,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--mode", default="precision", choices=["precision", "ranked", "fixed"])
     ap.add_argument("--samples", type=int, default=48)
+    ap.add_argument("--global-ncell", type=int, default=0, help="strong scaling: 4*G^3 atoms in total, whatever the GPU count")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -83,7 +84,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pg = GRIDS[world]
     t0 = time.time()
-    gsys = H.lj_charge_fluid(tuple(args.ncell * np.array(pg)), seed=4242)
+    cells = (args.global_ncell,) * 3 if args.global_ncell else tuple(args.ncell * np.array(pg))
+    gsys = H.lj_charge_fluid(cells, seed=4242)
     words = {"precision": "polar_gs_ranked no precision 1e-8 max_iterations 200 damp_type exponential",
              "ranked": "precision 1e-11 max_iterations 200 polar_gamma 1.03 damp_type exponential",
              "fixed": "polar_gs_ranked no fixed_iteration yes max_iterations 30 damp_type exponential"}[args.mode]
