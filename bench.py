@@ -49,12 +49,26 @@ STYLE_WORDS = (f"{CUT_LJ} {CUT_COUL} polar_gs_ranked no fixed_iteration yes max_
                "damp_type exponential")
 
 
-def load_pb():
-    spec = importlib.util.spec_from_file_location("polb200", ROOT / "lammps-induced-dipole-polarization-pair-style_b200" / "polb200.py")
+PKG = ROOT / "lammps-induced-dipole-polarization-pair-style_b200"
+
+
+def _load(name, filename):
+    if name in sys.modules:
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, PKG / filename)
     mod = importlib.util.module_from_spec(spec)
-    sys.modules["polb200"] = mod
+    sys.modules[name] = mod
     spec.loader.exec_module(mod)
     return mod
+
+
+def load_pb():
+    return _load("polb200", "polb200.py")
+
+
+def workloads():
+    """the synthetic systems (numpy only): the GPU arm never touches oracle/"""
+    return _load("polb200_workloads", "workloads.py")
 
 
 GRIDS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
@@ -136,11 +150,10 @@ run {steps}
 
 def run_reference_binary(steps, warmup):
     """Times oracle/_ref/lmp_serial (the repaired, otherwise unmodified reference) on the 2048-atom sample."""
-    import polhelpers as H
     lmp = ROOT / "oracle" / "_ref" / "lmp_serial"
     if not lmp.exists():
         return None
-    sysm = H.lj_charge_fluid(SAMPLE_NCELL)
+    sysm = workloads().lj_charge_fluid(SAMPLE_NCELL)
     work = Path(tempfile.mkdtemp(prefix="polb200_refarm_"))
     try:
         write_lammps_case(work, sysm, None, steps + warmup)
@@ -208,9 +221,10 @@ def reference_arm(args):
 # GPU arm
 # ----------------------------------------------------------------------------------------------------
 def make_style(pb, sysm, device):
-    import polhelpers as H
-    from oracle import polref as P  # only for the g_ewald formula of `kspace_style ewald 1e-4` (host setup)
-    g = P.ewald_g(1e-4, sysm.q, CUT_COUL, sysm.boxlo, sysm.boxhi)
+    # g_ewald as `kspace_style ewald 1e-4` would set it: the product's own Ewald::init (polb200_ewald_init)
+    ew = pb.Ewald(device=device)
+    g = ew.init(1e-4, sysm.q, CUT_COUL, sysm.boxlo, sysm.boxhi).g_ewald
+    ew.close()
     s = pb.PairStyle(device=device)
     s.set_ntypes(2)
     s.command(f"pair_style lj/cut/coul/long/polarization {STYLE_WORDS} polar_cutoff {CUT_COUL}")
@@ -225,7 +239,6 @@ def gpu_arm(args):
     import torch
     import torch.distributed as dist
 
-    import polhelpers as H
     pb = load_pb()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -241,7 +254,7 @@ def gpu_arm(args):
     pg = GRIDS.get(world)
     if pg is None:
         raise SystemExit(f"bench.py: no brick grid defined for {world} GPUs (use 1, 2, 4 or 8)")
-    gsys = H.lj_charge_fluid(NCELL if world == 1 else tuple(NCELL * np.array(pg)), seed=12345)
+    gsys = workloads().lj_charge_fluid(NCELL if world == 1 else tuple(NCELL * np.array(pg)), seed=12345)
     style = make_style(pb, gsys, local)
     dev = torch.device("cuda", local)
     if world > 1:

@@ -10,7 +10,8 @@ GOLDEN = Path(__file__).resolve().parent / "golden"
 
 
 def golden_cases():
-    return sorted(p.stem for p in GOLDEN.glob("*.npz"))
+    """fixtures of single compute() calls of the pair style (the ewald_* fixtures belong to the KSpace tests)"""
+    return sorted(p.stem for p in GOLDEN.glob("*.npz") if not p.stem.startswith("ewald_"))
 
 
 def load_fixture(name):
@@ -113,55 +114,31 @@ def rel_err(a, b):
     return float(np.abs(a - b).max()) / scale
 
 
+def _workloads():
+    import importlib.util
+    import sys
+    if "polb200_workloads" in sys.modules:
+        return sys.modules["polb200_workloads"]
+    path = Path(__file__).resolve().parents[1] / "lammps-induced-dipole-polarization-pair-style_b200" / "workloads.py"
+    spec = importlib.util.spec_from_file_location("polb200_workloads", path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["polb200_workloads"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _as_system(w):
+    return P.System(w.x, w.q, w.type, w.molecule, w.alpha, w.boxlo, w.boxhi, w.ntypes)
+
+
 def lj_charge_fluid(ncell, seed=12345, rho=0.1, jitter=0.3):
-    """BASELINE config 2 generator: fcc sites jittered by U(-jitter,jitter) A, density rho
-    atoms/A^3, two types with q=+-0.4 e alternating, alpha 1.0/0.5 A^3, molecule 0.  N = 4*ncell^3
-    (ncell may be a triple (nx,ny,nz) of fcc cells for the brick-shaped boxes of the multi-GPU runs)."""
-    rng = np.random.default_rng(seed)
-    nc = np.array([ncell] * 3 if np.isscalar(ncell) else list(ncell), dtype=np.int64)
-    n = 4 * int(nc.prod())
-    a = (4.0 / rho) ** (1.0 / 3.0)
-    if np.isscalar(ncell):
-        a = ((n / rho) ** (1.0 / 3.0)) / ncell  # the historical expression (bit-identical fixtures)
-    L = a * nc
-    base = np.array([[0, 0, 0], [0.5, 0.5, 0], [0.5, 0, 0.5], [0, 0.5, 0.5]])
-    g = np.stack(np.meshgrid(np.arange(nc[0]), np.arange(nc[1]), np.arange(nc[2]), indexing="ij"), -1).reshape(-1, 3)
-    x = ((g[:, None, :] + base[None, :, :]) * a).reshape(-1, 3)
-    x = x + rng.uniform(-jitter, jitter, size=x.shape)
-    x = np.mod(x, L)
-    typ = (np.arange(n) % 2 + 1).astype(np.int32)
-    q = np.where(typ == 1, 0.4, -0.4)
-    alpha = np.where(typ == 1, 1.0, 0.5)
-    mol = np.zeros(n, dtype=np.int32)
-    return P.System(x, q, typ, mol, alpha, [0, 0, 0], list(L), 2)
+    """BASELINE config 2 generator (lammps-..._b200/workloads.py) as an oracle System."""
+    return _as_system(_workloads().lj_charge_fluid(ncell, seed, rho, jitter))
 
 
 def water_box(nmol_side, seed=2, rho=0.1):
-    """BASELINE config 3 generator: rigid 3-site water-like molecules on a jittered cubic
-    lattice with random orientations; r_OH = 0.9572 A, HOH = 104.52 deg; O: q -0.8 e, alpha 0.837 A^3 (type 1),
-    H: q +0.4 e, alpha 0.496 A^3 (type 2); molecule = molecule id (so the static field / charge-dipole terms skip
-    intramolecular pairs while dipole-dipole does not, exactly as the reference); rho atoms/A^3.
-    N = 3 * nmol_side^3 atoms."""
-    rng = np.random.default_rng(seed)
-    nmol = nmol_side ** 3
-    n = 3 * nmol
-    L = (n / rho) ** (1.0 / 3.0)
-    a = L / nmol_side
-    g = np.stack(np.meshgrid(*[np.arange(nmol_side)] * 3, indexing="ij"), -1).reshape(-1, 3)
-    centre = (g + 0.5) * a + rng.uniform(-0.25, 0.25, size=(nmol, 3))
-    # random rotation per molecule (QR of a gaussian matrix, det fixed to +1)
-    q, r = np.linalg.qr(rng.normal(size=(nmol, 3, 3)))
-    q = q * np.sign(np.linalg.det(q))[:, None, None]
-    roh, half = 0.9572, np.deg2rad(104.52) / 2.0
-    local = np.array([[0.0, 0.0, 0.0], [roh * np.sin(half), roh * np.cos(half), 0.0],
-                      [-roh * np.sin(half), roh * np.cos(half), 0.0]])
-    x = centre[:, None, :] + np.einsum("mij,aj->mai", q, local)
-    x = np.mod(x.reshape(-1, 3), L)
-    typ = np.tile(np.array([1, 2, 2], dtype=np.int32), nmol)
-    qq = np.where(typ == 1, -0.8, 0.4)
-    alpha = np.where(typ == 1, 0.837, 0.496)
-    mol = np.repeat(np.arange(1, nmol + 1, dtype=np.int32), 3)
-    return P.System(x, qq, typ, mol, alpha, [0, 0, 0], [L, L, L], 2)
+    """BASELINE config 3 generator (lammps-..._b200/workloads.py) as an oracle System."""
+    return _as_system(_workloads().water_box(nmol_side, seed, rho))
 
 
 def water_style(sysm, cut_lj=2.5, cut_coul=12.0, **kw):

@@ -10,13 +10,13 @@ import numpy as np
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
 import torch
-import polhelpers as H
-from gpu_common import pb
-from oracle import polref as P
+import bench
+
+pb = bench.load_pb()
 
 ncell = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-sysm = H.lj_charge_fluid(ncell)
+sysm = bench.workloads().lj_charge_fluid(ncell)
 e = pb.Ewald(device=0)
 info = e.init(1e-4, sysm.q, 12.0, sysm.boxlo, sysm.boxhi)
 dev = torch.device("cuda", 0)
@@ -32,7 +32,8 @@ for k in range(reps + 3):
         ms.append(e.last_ms())
 print(f"device Ewald: {sysm.n} atoms, kcount {info.kcount}, kmax {info.kmax}, g {info.g_ewald:.6f}: "
       f"{np.mean(ms):.3f} ms per compute (min {np.min(ms):.3f}), E_long {energy:.10f}")
-if len(sys.argv) > 3:
+if len(sys.argv) > 3:  # optional: the oracle's direct sums on the host cores beside it
+    from oracle import polref as P
     prd = sysm.boxhi - sysm.boxlo
     plan = P.ewald_plan(1e-4, sysm.q, 12.0, prd)
     t0 = time.time()

@@ -10,11 +10,10 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
 import bench
-import polhelpers as H
 
 ncell = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 50
-sysm = H.lj_charge_fluid(ncell)
+sysm = bench.workloads().lj_charge_fluid(ncell)
 work = Path(tempfile.mkdtemp(prefix="polb200_e2e_"))
 bench.write_lammps_case(work, sysm, None, steps)
 text = (work / "in.fluid").read_text().replace(bench.STYLE_WORDS, bench.STYLE_WORDS + f" polar_cutoff {bench.CUT_COUL}")

@@ -31,9 +31,9 @@ for p in (str(ROOT), str(ROOT / "tests")):
 import torch
 import torch.distributed as dist
 
-import polhelpers as H
-from gpu_common import pb
-from oracle import polref as P  # ewald_g only (host setup arithmetic)
+import bench  # product-side helpers only: C-ABI binding, workloads (no oracle)
+
+pb = bench.load_pb()
 
 GRIDS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
 CUT = 12.0
@@ -85,11 +85,13 @@ def main():
     pg = GRIDS[world]
     t0 = time.time()
     cells = (args.global_ncell,) * 3 if args.global_ncell else tuple(args.ncell * np.array(pg))
-    gsys = H.lj_charge_fluid(cells, seed=4242)
+    gsys = bench.workloads().lj_charge_fluid(cells, seed=4242)
     words = {"precision": "polar_gs_ranked no precision 1e-8 max_iterations 200 damp_type exponential",
              "ranked": "precision 1e-11 max_iterations 200 polar_gamma 1.03 damp_type exponential",
              "fixed": "polar_gs_ranked no fixed_iteration yes max_iterations 30 damp_type exponential"}[args.mode]
-    g = P.ewald_g(1e-4, gsys.q, CUT, gsys.boxlo, gsys.boxhi)
+    ew = pb.Ewald(device=local)  # g_ewald as `kspace_style ewald 1e-4` sets it
+    g = ew.init(1e-4, gsys.q, CUT, gsys.boxlo, gsys.boxhi).g_ewald
+    ew.close()
     s = pb.PairStyle(device=local)
     s.set_ntypes(2)
     s.command(f"pair_style lj/cut/coul/long/polarization 2.5 {CUT} {words} polar_cutoff {CUT}")

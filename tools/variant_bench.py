@@ -9,14 +9,13 @@ ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 import bench  # noqa: E402
-import polhelpers as H  # noqa: E402
 
 
 def main():
     import torch
     pb = bench.load_pb()
     ncell = int(sys.argv[1]) if len(sys.argv) > 1 else bench.NCELL
-    sysm = H.lj_charge_fluid(ncell)
+    sysm = bench.workloads().lj_charge_fluid(ncell)
     n = sysm.n
     s = bench.make_style(pb, sysm, 0)
     x = np.ascontiguousarray(sysm.x); q = np.ascontiguousarray(sysm.q)
