@@ -58,7 +58,8 @@ int polb200_abi_version(void);
  * arg[1]=cut_coul, then keyword/value pairs: precision zodid fixed_iteration damp max_iterations
  * damp_type polar_gs polar_gs_ranked polar_gamma debug use_previous -- plus the documented extensions
  *   polar_cutoff <r|none>  dipole-dipole cutoff (none = reference all-pairs semantics, the default)
- *   gs_chunks <n>          ranked colouring sweep with n chunks in list mode (0 = sequential GS)
+ *   gs_chunks <n>          ranked colouring sweep in list mode: n > 0 contiguous chunks of the ranked order,
+ *                          n < 0 |n| interleaved chunks, 0 (default) = 8 interleaved chunks
  * Order-dependent validation is the reference's (e.g. "zodid" errors while polar_gs_ranked is on). */
 int polb200_settings(polb200_t *h, int narg, const char *const *arg);
 /* Atom::ntypes; allocates the (ntypes+1)^2 coefficient arrays = allocate(), pol.cpp:651-672 */

@@ -897,13 +897,18 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
     int nchunks = 0;          // 0: Jacobi (one block of rows, separate output array)
     bool sequential = false;  // reference-exact Gauss-Seidel (all-pairs mode only)
     if (gs) {
-      if (st.gs_chunks > 0) nchunks = st.gs_chunks;
+      if (st.gs_chunks != 0) nchunks = abs(st.gs_chunks);
       else if (list_mode) {
-        // default: chunks of ~4096 rows (one wave of warps on 148 SMs); more chunks = closer to true Gauss-Seidel
-        // = fewer iterations (water box: 77 iterations with 8 chunks, 39 with 64, 16 sequential)
-        const long per_brick = comm ? h->comm.nglobal / h->comm.nranks : (long)n;
-        nchunks = (int)std::min(128l, std::max(8l, per_brick / 4096));
+        // default: 8 INTERLEAVED chunks.  Interleaving makes the colouring as good as the sequential sweep where it
+        // matters (water box: 17 iterations against 77 with 8 contiguous chunks and 16 strictly sequential; atomic
+        // fluid: 16 / 16 / 13), so a handful of chunks -- few launches, few halo barriers -- is enough.
+        nchunks = std::min(8, n);
       } else sequential = true;
+    }
+    if (gs && nchunks > 1 && st.gs_chunks <= 0 && !sequential) {
+      h->ranked_in.ensure(n);
+      LAUNCH(h, k_interleave_order, cdiv(n, 256), 256, n, nchunks, order, h->ranked_in.p);
+      order = h->ranked_in.p;
     }
     // fused sweep + halo: new dipoles go straight into the neighbour bricks' ghost slots (Jacobi sweeps)
     const bool push = h->push_ready && h->use_push && !gs && list_mode && h->sweep_variant != 0 &&

@@ -99,8 +99,7 @@ void HostStyle::settings(int narg, const char *const *arg)
         if (polar_cutoff <= 0.0) fail(illegal);
       }
     } else if (!strcmp(key, "gs_chunks")) {
-      gs_chunks = inumeric(val);
-      if (gs_chunks < 0) fail(illegal);
+      gs_chunks = inumeric(val);  // n > 0: contiguous chunks of the ranked order; n < 0: |n| interleaved chunks; 0: default
     } else fail(illegal);
   }
 

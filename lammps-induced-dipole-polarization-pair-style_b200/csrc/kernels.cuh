@@ -830,6 +830,17 @@ k_sweep_cached(int pos_beg, int pos_end, const int *__restrict__ order, ListRows
   if (PUSH) push_row(push_dst, nx, ny, nz, mi.w);
 }
 
+// interleaved colouring: chunk c of the sweep holds the ranked positions c, c+C, c+2C, ... (atoms that are neighbours
+// in the ranked order -- typically the sites of one molecule -- land in different chunks and see each other's new
+// dipoles within the sweep).  Realised as a re-ordering of the visiting order: out = concat_c in[c::C].
+__global__ void k_interleave_order(int n, int C, const int *__restrict__ in, int *__restrict__ out)
+{
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const int c = p % C, m = p / C;
+  out[c * (n / C) + min(c, n % C) + m] = in[p];
+}
+
 // commit a chunk of the ranked colouring sweep AND refresh the ghost copies of the committed atoms in one pass
 // (own periodic images / neighbour bricks' ghost slots through the push tables)
 __global__ void k_commit_push(int pos_beg, int pos_end, const int *__restrict__ order, const double4 *__restrict__ staged,

@@ -1443,7 +1443,18 @@ int polref_polar_rows(const polref_params *p, int nlocal, const double *x, const
     double *mu_new = (double *)malloc(sizeof(double) * 3 * (size_t)nlocal);
     double *mu_old = (double *)malloc(sizeof(double) * 3 * (size_t)nlocal);
     int gs = p->polar_gs || p->polar_gs_ranked;
-    int nchunks = (gs && p->gs_chunks > 0) ? p->gs_chunks : 0;
+    int nchunks = (gs && p->gs_chunks != 0) ? abs(p->gs_chunks) : 0;
+    if (gs && p->gs_chunks < 0) {
+      /* EXTENSION: interleaved colouring -- chunk c holds the ranked positions c, c+C, c+2C, ... so that atoms
+       * that are neighbours in the ranked order (typically the sites of one molecule) fall into DIFFERENT chunks
+       * and see each other's new dipoles within the sweep.  Realised by re-ordering the visiting order. */
+      int *tmp = (int *)malloc(sizeof(int) * (size_t)nlocal);
+      int k = 0;
+      for (int c = 0; c < nchunks; c++)
+        for (int pos = c; pos < nlocal; pos += nchunks) tmp[k++] = ranked[pos];
+      memcpy(ranked, tmp, sizeof(int) * (size_t)nlocal);
+      free(tmp);
+    }
     int keep_iterating = 1;
     while (keep_iterating) {
       memcpy(mu_old, mu, sizeof(double) * 3 * (size_t)nlocal);

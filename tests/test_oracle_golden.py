@@ -140,3 +140,18 @@ def test_chunked_gs_converges_to_sequential_gs():
     # both stop when the rms change drops below precision=1e-11; fixed points agree to ~precision
     assert np.abs(seq["mu"] - chk["mu"]).max() < 50 * 1e-11
     assert abs(seq["eng_pol"] - chk["eng_pol"]) < 1e-9 * abs(seq["eng_pol"])
+
+
+def test_interleaved_colouring_converges_like_sequential_gs():
+    """oracle-level statement of the device default: 8 interleaved chunks reach the sequential sweep's fixed point in
+    about as many iterations, contiguous chunks need several times more (rigid water box, strong intramolecular
+    coupling)."""
+    sysm = H.water_box(6)
+    kw = dict(polar_cut=9.0, damp_type="exponential", polar_gs_ranked=1, precision=1e-11, max_iterations=300,
+              polar_gamma=1.03)
+    seq = P.polar_rows(sysm, H.water_style(sysm, 2.5, 9.0, gs_chunks=0, **kw))
+    il = P.polar_rows(sysm, H.water_style(sysm, 2.5, 9.0, gs_chunks=-8, **kw))
+    co = P.polar_rows(sysm, H.water_style(sysm, 2.5, 9.0, gs_chunks=8, **kw))
+    assert not il["diverged"] and not co["diverged"]
+    assert il["iterations"] <= seq["iterations"] + 4 and co["iterations"] >= il["iterations"] + 10
+    assert np.abs(il["mu"] - seq["mu"]).max() < 1e-9 and np.abs(co["mu"] - seq["mu"]).max() < 1e-9
