@@ -41,7 +41,7 @@ DAMP = 2.1304
 KQ = np.sqrt(332.06371)
 
 
-def sample_check(x, q, alpha, mu, ef, boxlen, samples, rng):
+def sample_check(x, q, alpha, mu, ef, boxlen, samples, rng, mol=None):
     """numpy recomputation for `samples` random atoms against all atoms (minimum image)."""
     n = x.shape[0]
     idx = rng.choice(n, samples, replace=False)
@@ -53,8 +53,9 @@ def sample_check(x, q, alpha, mu, ef, boxlen, samples, rng):
         m = (r2 < CUT * CUT) & (r2 > 0)
         dd, rr2 = d[m], r2[m]
         r = np.sqrt(rr2)
-        # static field: k * sum q_j (1/r^2 - 1/rc^2)/r * del   (r <= rc; molecule 0 => every pair)
-        e_s = KQ * (((1.0 / rr2 - 1.0 / (CUT * CUT)) / r * q[m])[:, None] * dd).sum(0)
+        # static field: k * sum q_j (1/r^2 - 1/rc^2)/r * del   (r <= rc; inter-molecular pairs only)
+        w = q[m] if mol is None or mol[i] == 0 else np.where(mol[m] != mol[i], q[m], 0.0)
+        e_s = KQ * (((1.0 / rr2 - 1.0 / (CUT * CUT)) / r * w)[:, None] * dd).sum(0)
         ar = DAMP * r
         ex = np.exp(-ar)
         d1 = 1.0 - ex * (1.0 + ar + 0.5 * ar * ar)
@@ -75,6 +76,7 @@ def main():
     ap.add_argument("--mode", default="precision", choices=["precision", "ranked", "fixed"])
     ap.add_argument("--samples", type=int, default=48)
     ap.add_argument("--global-ncell", type=int, default=0, help="strong scaling: 4*G^3 atoms in total, whatever the GPU count")
+    ap.add_argument("--water", type=int, default=0, help="BASELINE config 3: rigid water box of 3*W^3 atoms instead of the fluid")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -85,7 +87,7 @@ def main():
     pg = GRIDS[world]
     t0 = time.time()
     cells = (args.global_ncell,) * 3 if args.global_ncell else tuple(args.ncell * np.array(pg))
-    gsys = bench.workloads().lj_charge_fluid(cells, seed=4242)
+    gsys = bench.workloads().water_box(args.water) if args.water else bench.workloads().lj_charge_fluid(cells, seed=4242)
     words = {"precision": "polar_gs_ranked no precision 1e-8 max_iterations 200 damp_type exponential",
              "ranked": "precision 1e-11 max_iterations 200 polar_gamma 1.03 damp_type exponential",
              "fixed": "polar_gs_ranked no fixed_iteration yes max_iterations 30 damp_type exponential"}[args.mode]
@@ -95,7 +97,11 @@ def main():
     s = pb.PairStyle(device=local)
     s.set_ntypes(2)
     s.command(f"pair_style lj/cut/coul/long/polarization 2.5 {CUT} {words} polar_cutoff {CUT}")
-    s.command("pair_coeff * * 0.1 3.0")
+    if args.water:
+        s.command("pair_coeff 1 1 0.155 3.166")
+        s.command("pair_coeff 2 2 0.0 1.0")
+    else:
+        s.command("pair_coeff * * 0.1 3.0")
     s.init(g_ewald=g, molecular=0)
     s.set_box(gsys.boxlo, gsys.boxhi)
     if world > 1:
@@ -109,7 +115,7 @@ def main():
     n = len(own)
     x = np.ascontiguousarray(gsys.x[own]); q = np.ascontiguousarray(gsys.q[own])
     ty = np.ascontiguousarray(gsys.type[own]); al = np.ascontiguousarray(gsys.alpha[own])
-    tag = np.ascontiguousarray(gsys.tag[own])
+    tag = np.ascontiguousarray(gsys.tag[own]); molecule = np.ascontiguousarray(gsys.molecule[own])
     mu = np.zeros((n, 3)); f = np.zeros((n, 3)); ef = np.zeros((n, 3))
     t_setup = time.time() - t0
     rows = []
@@ -119,7 +125,7 @@ def main():
         if world > 1:
             dist.barrier()
         t1 = time.perf_counter()
-        r = s.compute(x, q, ty, al, mu, f, tag=tag, ef_static=ef, eflag=1, vflag=2, ago=k)
+        r = s.compute(x, q, ty, al, mu, f, molecule=molecule, tag=tag, ef_static=ef, eflag=1, vflag=2, ago=k)
         torch.cuda.synchronize()
         rows.append(dict(step=k, ms=(time.perf_counter() - t1) * 1e3, iterations=r.iterations, ms_neigh=r.ms_neigh,
                          ms_pair=r.ms_pair, ms_scf=r.ms_scf, ms_force=r.ms_force, diverged=bool(r.status & pb.STATUS_DIVERGED),
@@ -146,9 +152,10 @@ def main():
             seen[p_["own"]] += 1
         rng = np.random.default_rng(11)
         tc = time.time()
-        worst_ef, worst_res = sample_check(gsys.x, gsys.q, gsys.alpha, MU, EF, gsys.boxhi - gsys.boxlo, args.samples, rng)
+        worst_ef, worst_res = sample_check(gsys.x, gsys.q, gsys.alpha, MU, EF, gsys.boxhi - gsys.boxlo, args.samples, rng,
+                                           gsys.molecule if args.water else None)
         fsum = np.abs(F.sum(0)).max() / (np.abs(F).max() * np.sqrt(N))
-        line = dict(what="scale_run", n_gpus=world, grid=pg, atoms_total=N, atoms_per_gpu=N // world, mode=args.mode,
+        line = dict(what="scale_run", system="water" if args.water else "fluid", n_gpus=world, grid=pg, atoms_total=N, atoms_per_gpu=N // world, mode=args.mode,
                     pair_style=words + f" polar_cutoff {CUT}", steps=rows, ms_per_step_max_over_ranks=list(map(float, times)),
                     atom_steps_per_s_last=N / (times[-1] * 1e-3), eng_pol_total=epol, every_atom_owned_once=bool(np.all(seen == 1)),
                     check=dict(samples=args.samples, static_field_rel_err=worst_ef, scf_residual_abs=worst_res,
