@@ -69,6 +69,35 @@ def sample_check(x, q, alpha, mu, ef, boxlen, samples, rng, mol=None):
     return worst_ef, worst_res
 
 
+def mof_supercell(R):
+    """BASELINE config 4 shape: the reference's MOF-5 + CO2 example cell (tests/golden/co2_singlepoint_step0.npz: 924 atoms,
+    10 atom types, bond topology as special lists, 101 molecules) replicated R x R x R like LAMMPS `replicate` would
+    (new atom ids and molecule ids per image)."""
+    from types import SimpleNamespace
+    fx = dict(np.load(ROOT / "tests" / "golden" / "co2_singlepoint_step0.npz", allow_pickle=False))
+    n0 = fx["x"].shape[0]
+    prd = fx["boxhi"] - fx["boxlo"]
+    nmol0 = int(fx["molecule"].max())
+    xs, tags, mols, specs = [], [], [], []
+    r = 0
+    for ix in range(R):
+        for iy in range(R):
+            for iz in range(R):
+                xs.append(fx["x"] - fx["boxlo"] + np.array([ix, iy, iz]) * prd)
+                tags.append(fx["tag"] + r * n0)
+                mols.append(np.where(fx["molecule"] > 0, fx["molecule"] + r * nmol0, 0))
+                specs.append(np.where(fx["special"] > 0, fx["special"] + r * n0, 0))
+                r += 1
+    rep = R ** 3
+    sysm = SimpleNamespace(x=np.ascontiguousarray(np.concatenate(xs)), q=np.tile(fx["q"], rep), type=np.tile(fx["type"], rep).astype(np.int32),
+                           alpha=np.tile(fx["alpha"], rep), tag=np.concatenate(tags).astype(np.int32),
+                           molecule=np.concatenate(mols).astype(np.int32), nspecial=np.tile(fx["nspecial"], (rep, 1)).astype(np.int32),
+                           special=np.concatenate(specs).astype(np.int32), boxlo=np.zeros(3), boxhi=prd * R,
+                           ntypes=int(fx["ntypes"]), n=n0 * rep)
+    # the device expects tags in caller order only for lookups: keep arrays in tag order (already are)
+    return dict(sys=sysm, cut=12.8345, pair_coeff=str(fx["pair_coeff"]).splitlines())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ncell", type=int, default=32)
@@ -77,6 +106,8 @@ def main():
     ap.add_argument("--samples", type=int, default=48)
     ap.add_argument("--global-ncell", type=int, default=0, help="strong scaling: 4*G^3 atoms in total, whatever the GPU count")
     ap.add_argument("--water", type=int, default=0, help="BASELINE config 3: rigid water box of 3*W^3 atoms instead of the fluid")
+    ap.add_argument("--mof", type=int, default=0, help="BASELINE config 4: the MOF-5 + CO2 cell of the golden fixture (924 atoms, "
+                    "bond topology, 10 atom types) replicated R^3 times")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -87,7 +118,14 @@ def main():
     pg = GRIDS[world]
     t0 = time.time()
     cells = (args.global_ncell,) * 3 if args.global_ncell else tuple(args.ncell * np.array(pg))
-    gsys = bench.workloads().water_box(args.water) if args.water else bench.workloads().lj_charge_fluid(cells, seed=4242)
+    global CUT
+    mof = None
+    if args.mof:
+        mof = mof_supercell(args.mof)
+        gsys = mof["sys"]
+        CUT = mof["cut"]
+    else:
+        gsys = bench.workloads().water_box(args.water) if args.water else bench.workloads().lj_charge_fluid(cells, seed=4242)
     words = {"precision": "polar_gs_ranked no precision 1e-8 max_iterations 200 damp_type exponential",
              "ranked": "precision 1e-11 max_iterations 200 polar_gamma 1.03 damp_type exponential",
              "fixed": "polar_gs_ranked no fixed_iteration yes max_iterations 30 damp_type exponential"}[args.mode]
@@ -95,14 +133,17 @@ def main():
     g = ew.init(1e-4, gsys.q, CUT, gsys.boxlo, gsys.boxhi).g_ewald
     ew.close()
     s = pb.PairStyle(device=local)
-    s.set_ntypes(2)
+    s.set_ntypes(int(gsys.ntypes))
     s.command(f"pair_style lj/cut/coul/long/polarization 2.5 {CUT} {words} polar_cutoff {CUT}")
-    if args.water:
+    if mof:
+        for line in mof["pair_coeff"]:
+            s.command(line)
+    elif args.water:
         s.command("pair_coeff 1 1 0.155 3.166")
         s.command("pair_coeff 2 2 0.0 1.0")
     else:
         s.command("pair_coeff * * 0.1 3.0")
-    s.init(g_ewald=g, molecular=0)
+    s.init(g_ewald=g, molecular=1 if mof else 0)
     s.set_box(gsys.boxlo, gsys.boxhi)
     if world > 1:
         box = [pb.comm_create_id() if rank == 0 else None]
@@ -116,6 +157,8 @@ def main():
     x = np.ascontiguousarray(gsys.x[own]); q = np.ascontiguousarray(gsys.q[own])
     ty = np.ascontiguousarray(gsys.type[own]); al = np.ascontiguousarray(gsys.alpha[own])
     tag = np.ascontiguousarray(gsys.tag[own]); molecule = np.ascontiguousarray(gsys.molecule[own])
+    nspecial = np.ascontiguousarray(gsys.nspecial[own]) if gsys.nspecial is not None else None
+    special = np.ascontiguousarray(gsys.special[own]) if gsys.special is not None else None
     mu = np.zeros((n, 3)); f = np.zeros((n, 3)); ef = np.zeros((n, 3))
     t_setup = time.time() - t0
     rows = []
@@ -125,7 +168,8 @@ def main():
         if world > 1:
             dist.barrier()
         t1 = time.perf_counter()
-        r = s.compute(x, q, ty, al, mu, f, molecule=molecule, tag=tag, ef_static=ef, eflag=1, vflag=2, ago=k)
+        r = s.compute(x, q, ty, al, mu, f, molecule=molecule, tag=tag, ef_static=ef, eflag=1, vflag=2, ago=k,
+                      nspecial=nspecial, special=special)
         torch.cuda.synchronize()
         rows.append(dict(step=k, ms=(time.perf_counter() - t1) * 1e3, iterations=r.iterations, ms_neigh=r.ms_neigh,
                          ms_pair=r.ms_pair, ms_scf=r.ms_scf, ms_force=r.ms_force, diverged=bool(r.status & pb.STATUS_DIVERGED),
@@ -153,9 +197,9 @@ def main():
         rng = np.random.default_rng(11)
         tc = time.time()
         worst_ef, worst_res = sample_check(gsys.x, gsys.q, gsys.alpha, MU, EF, gsys.boxhi - gsys.boxlo, args.samples, rng,
-                                           gsys.molecule if args.water else None)
+                                           gsys.molecule if (args.water or mof) else None)
         fsum = np.abs(F.sum(0)).max() / (np.abs(F).max() * np.sqrt(N))
-        line = dict(what="scale_run", system="water" if args.water else "fluid", n_gpus=world, grid=pg, atoms_total=N, atoms_per_gpu=N // world, mode=args.mode,
+        line = dict(what="scale_run", system="mof5+co2" if mof else ("water" if args.water else "fluid"), n_gpus=world, grid=pg, atoms_total=N, atoms_per_gpu=N // world, mode=args.mode,
                     pair_style=words + f" polar_cutoff {CUT}", steps=rows, ms_per_step_max_over_ranks=list(map(float, times)),
                     atom_steps_per_s_last=N / (times[-1] * 1e-3), eng_pol_total=epol, every_atom_owned_once=bool(np.all(seen == 1)),
                     check=dict(samples=args.samples, static_field_rel_err=worst_ef, scf_residual_abs=worst_res,
