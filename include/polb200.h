@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define POLB200_ABI_VERSION 2
+#define POLB200_ABI_VERSION 3
 
 typedef struct polb200_handle polb200_t;
 
@@ -204,6 +204,83 @@ int polb200_ewald_init(polb200_ewald_t *e, const polb200_ewald_setup *in, polb20
 int polb200_ewald_compute(polb200_ewald_t *e, int nlocal, const double *x, const double *q, double *f, int eflag,
                           int vflag, int on_device, double *energy, double virial[6]);
 double polb200_ewald_last_ms(const polb200_ewald_t *e);  /* CUDA-event time of the last compute */
+
+/* ---- Rigid-body integrator -----------------------------------------------------------
+ * Replaces `fix rigid/nve molecule` and `fix rigid/nvt molecule` of the reference's RIGID package, the integrator of
+ * every shipped polarization example (src/RIGID/fix_rigid_nh.{h,cpp} on top of fix_rigid.{h,cpp}): bodies = molecules
+ * of the fix group, point particles, orthogonal periodic box.  Body state (centre of mass, quaternion, conjugate
+ * quaternion momentum, principal axes, thermostat chains) lives on the device; every per-step entry point accepts
+ * host pointers (atom->x / v / f of a LAMMPS Fix) or device pointers (on_device = 1: positions, velocities and forces
+ * stay in HBM across steps together with polb200_compute / polb200_ewald_compute).  Per-atom body data is keyed by
+ * atom id, so the caller may reorder its atoms between calls (atom sorting) as long as it passes the matching `tag`.
+ * Not offered (clean errors): single/group/custom bodies, extended particles, force/torque keywords, langevin,
+ * infile, rigid/npt|nph, triclinic boxes, 2d. */
+typedef struct polb200_rigid polb200_rigid_t;
+
+typedef struct {
+  int thermostat;                    /* 0 = rigid/nve, 1 = rigid/nvt (FixRigidNH::tstat_flag) */
+  double t_start, t_stop, t_period;  /* `temp Tstart Tstop Tdamp` (fix_rigid.cpp:418-427) */
+  int t_chain, t_iter, t_order;      /* `tparam` (defaults 10 1 3, fix_rigid.cpp:323-325); order 3 or 5 */
+  double dt;                         /* update->dt */
+  double ftm2v, mvv2e, boltz;        /* force->ftm2v / mvv2e / boltz */
+  double boxlo[3], boxhi[3];
+  int periodic[3];
+} polb200_rigid_params;
+
+typedef struct {
+  int nbody;       /* FixRigid::nbody */
+  int nlinear;     /* bodies with a zero principal moment */
+  int nf_t, nf_r;  /* FixRigidNH::nf_t / nf_r (fix_rigid_nh.cpp:232-244) */
+  int maxmembers;  /* atoms of the largest body */
+} polb200_rigid_info;
+
+typedef struct {
+  int nlocal;
+  const int *tag;   /* atom->tag [nlocal] */
+  double *x;        /* atom->x [nlocal][3], in/out */
+  double *v;        /* atom->v [nlocal][3], in/out */
+  const double *f;  /* atom->f [nlocal][3] */
+  int on_device;    /* 0: host pointers (copied in and out inside the call); 1: device pointers on this GPU */
+} polb200_rigid_atoms;
+
+int polb200_rigid_create(polb200_rigid_t **r, int device);
+void polb200_rigid_destroy(polb200_rigid_t *r);
+const char *polb200_rigid_last_error(const polb200_rigid_t *r);
+/* constructor body numbering (fix_rigid.cpp:130-220: molecules of the group in ascending id) + FixRigid::init
+ * (:701-765: setup_bodies_static :1605-2112 incl. the Jacobi diagonalisation and the "Bad principal moments" checks,
+ * setup_bodies_dynamic :2120-2211) + FixRigidNH::init (fix_rigid_nh.cpp:208-262).  Host pointers: mass = per-atom
+ * mass (rmass[i] or mass[type[i]]), image = atom->image (packed 10-bit fields, src/lmptype.h:96-103),
+ * ingroup = 1 where mask[i] & groupbit (NULL = all atoms). */
+int polb200_rigid_init(polb200_rigid_t *r, const polb200_rigid_params *p, int nlocal, const int *tag, const int *molecule,
+                       const int *ingroup, const double *mass, const int *image, const double *x, const double *v,
+                       polb200_rigid_info *info);
+/* FixRigid::dof (fix_rigid.cpp:1181-1262); tgroup = 1 where the atom is in the temperature group (NULL = all) */
+int polb200_rigid_dof(polb200_rigid_t *r, int nlocal, const int *tag, const int *tgroup, int *dof);
+/* FixRigid::setup + FixRigidNH::setup (fix_rigid.cpp:782-889, fix_rigid_nh.cpp:323-421): body force and torque from
+ * the current forces, velocities made rigid-consistent (v is written), doubled virial, conjugate momenta, thermostat
+ * masses.  vflag != 0 tallies the fix's virial. */
+int polb200_rigid_setup(polb200_rigid_t *r, const polb200_rigid_atoms *a, int vflag);
+/* FixRigidNH::initial_integrate (fix_rigid_nh.cpp:428-603): x and v are written; f = the forces the last force call
+ * left (set_xv's constraint virial reads them).  run_fraction = (ntimestep - beginstep) / (endstep - beginstep), the
+ * argument of compute_temp_target (:1109-1115; ignored by rigid/nve). */
+int polb200_rigid_initial_integrate(polb200_rigid_t *r, const polb200_rigid_atoms *a, int vflag, double run_fraction);
+/* FixRigidNH::final_integrate (fix_rigid_nh.cpp:607-790): v is written; f = forces at the new positions */
+int polb200_rigid_final_integrate(polb200_rigid_t *r, const polb200_rigid_atoms *a);
+/* FixRigid::pre_neighbor (fix_rigid.cpp:1137-1175) after the caller wrapped its atoms (Domain::pbc): bodies are
+ * remapped into the box, the atoms' body-relative image flags are recomputed from `image` (atom->image). */
+int polb200_rigid_pre_neighbor(polb200_rigid_t *r, int nlocal, const int *tag, const int *image, int on_device);
+/* Fix::virial of the last step (set_xv + set_v halves), xx yy zz xy xz yz */
+int polb200_rigid_virial(polb200_rigid_t *r, double virial[6]);
+/* FixRigidNH::compute_scalar (fix_rigid_nh.cpp:991-1016; = FixRigid::compute_scalar :2595-2622 for rigid/nve),
+ * FixRigid::extract_ke (:2650-2659) and extract_erotational (:2665-2689); any pointer may be NULL */
+int polb200_rigid_scalar(polb200_rigid_t *r, double *scalar, double *ke_translational, double *ke_rotational);
+/* FixRigid::reset_dt (fix_rigid.cpp:2553-2558) */
+int polb200_rigid_reset_dt(polb200_rigid_t *r, double dt);
+/* body arrays for tests / compute_array: "xcm" "vcm" "fcm" "torque" "angmom" "omega" "ex" "ey" "ez" "inertia" [nbody][3],
+ * "quat" "conjqm" [nbody][4], "masstotal" [nbody]; returns the number of doubles copied or < 0 */
+long polb200_rigid_fetch(polb200_rigid_t *r, const char *name, double *dst, long capacity);
+long polb200_rigid_launch_count(polb200_rigid_t *r, int reset);
+double polb200_rigid_last_ms(const polb200_rigid_t *r); /* CUDA-event time of the last per-step call */
 
 /* ---- introspection for tests and profiling ------------------------------------------------------ */
 

@@ -2,7 +2,8 @@
 # Build a LAMMPS binary in which the reference's pair style is REPLACED by the B200 drop-in:
 #   lammps/_build/lmp_b200  =  reference host framework (LAMMPS 16Mar2018, from a scratch copy of
 #   $POLB200_REFERENCE/src, repaired exactly like the oracle build: oracle/build_ref.sh steps 1-3 without the
-#   dump hooks)  +  pair_lj_cut_coul_long_polarization_b200.{h,cpp}  +  libpolb200.so.
+#   dump hooks)  +  pair_lj_cut_coul_long_polarization_b200.{h,cpp}  +  ewald_b200.{h,cpp}  +
+#   fix_rigid_nh_b200.{h,cpp}  +  libpolb200.so.
 # An unchanged input script (polarization/examples/*) then drives the CUDA path.  Nothing of the reference is
 # copied into this repository; the binary lands in lammps/_build/ (git-ignored, travels to the GPU box).
 set -euo pipefail
@@ -22,6 +23,7 @@ mkdir -p "$OUT"
 if [ -x "$OUT/lmp_b200" ] && [ "$OUT/lmp_b200" -nt "$HERE/pair_lj_cut_coul_long_polarization_b200.cpp" ] \
    && [ "$OUT/lmp_b200" -nt "$HERE/pair_lj_cut_coul_long_polarization_b200.h" ] \
    && [ "$OUT/lmp_b200" -nt "$HERE/ewald_b200.cpp" ] && [ "$OUT/lmp_b200" -nt "$HERE/ewald_b200.h" ] \
+   && [ "$OUT/lmp_b200" -nt "$HERE/fix_rigid_nh_b200.cpp" ] && [ "$OUT/lmp_b200" -nt "$HERE/fix_rigid_nh_b200.h" ] \
    && [ "$OUT/lmp_b200" -nt "$ROOT/include/polb200.h" ] && [ -z "${POLB200_LMP_REBUILD:-}" ]; then
   echo "build_lmp_b200: $OUT/lmp_b200 is up to date"
   exit 0
@@ -49,6 +51,10 @@ cp "$HERE/pair_lj_cut_coul_long_polarization_b200.cpp" pair_lj_cut_coul_long_pol
 # ... and so does the KSpace style every input of the pair style uses
 cp "$HERE/ewald_b200.h" ewald.h
 cp "$HERE/ewald_b200.cpp" ewald.cpp
+# ... and the integrator of every shipped example, fix rigid/nve|nvt: one class under both style names
+cp "$HERE/fix_rigid_nh_b200.h" fix_rigid_nve.h
+cp "$HERE/fix_rigid_nh_b200.cpp" fix_rigid_nve.cpp
+rm -f fix_rigid_nvt.h fix_rigid_nvt.cpp
 cp "$ROOT/include/polb200.h" .
 make -j"$JOBS" serial LIB="-L$PKG -lpolb200 -Wl,-rpath,'\$\$ORIGIN/../..'" > "$W/build.log" 2>&1 || { tail -40 "$W/build.log"; exit 1; }
 cp lmp_serial "$OUT/lmp_b200"

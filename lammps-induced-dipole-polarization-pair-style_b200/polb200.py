@@ -28,6 +28,10 @@ ABI_SYMBOLS = [
     "polb200_launch_count", "polb200_set_option", "polb200_decomp_plan", "polb200_tail",
     "polb200_ewald_create", "polb200_ewald_destroy", "polb200_ewald_last_error", "polb200_ewald_init",
     "polb200_ewald_compute", "polb200_ewald_last_ms",
+    "polb200_rigid_create", "polb200_rigid_destroy", "polb200_rigid_last_error", "polb200_rigid_init",
+    "polb200_rigid_dof", "polb200_rigid_setup", "polb200_rigid_initial_integrate", "polb200_rigid_final_integrate",
+    "polb200_rigid_pre_neighbor", "polb200_rigid_virial", "polb200_rigid_scalar", "polb200_rigid_reset_dt",
+    "polb200_rigid_fetch", "polb200_rigid_launch_count", "polb200_rigid_last_ms",
 ]
 
 
@@ -65,6 +69,22 @@ class EwaldSetup(C.Structure):
 class EwaldInfo(C.Structure):
     _fields_ = [("g_ewald", C.c_double), ("gsqmx", C.c_double), ("kxmax", C.c_int), ("kymax", C.c_int),
                 ("kzmax", C.c_int), ("kmax", C.c_int), ("kcount", C.c_int)]
+
+
+class RigidParams(C.Structure):
+    _fields_ = [("thermostat", C.c_int), ("t_start", C.c_double), ("t_stop", C.c_double), ("t_period", C.c_double),
+                ("t_chain", C.c_int), ("t_iter", C.c_int), ("t_order", C.c_int), ("dt", C.c_double),
+                ("ftm2v", C.c_double), ("mvv2e", C.c_double), ("boltz", C.c_double), ("boxlo", C.c_double * 3),
+                ("boxhi", C.c_double * 3), ("periodic", C.c_int * 3)]
+
+
+class RigidInfo(C.Structure):
+    _fields_ = [("nbody", C.c_int), ("nlinear", C.c_int), ("nf_t", C.c_int), ("nf_r", C.c_int), ("maxmembers", C.c_int)]
+
+
+class RigidAtoms(C.Structure):
+    _fields_ = [("nlocal", C.c_int), ("tag", C.c_void_p), ("x", C.c_void_p), ("v", C.c_void_p), ("f", C.c_void_p),
+                ("on_device", C.c_int)]
 
 
 class Polb200Error(RuntimeError):
@@ -130,6 +150,25 @@ def lib():
                                             C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.polb200_ewald_last_ms.argtypes = [C.c_void_p]
         L.polb200_ewald_last_ms.restype = C.c_double
+        L.polb200_rigid_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        L.polb200_rigid_destroy.argtypes = [C.c_void_p]
+        L.polb200_rigid_last_error.argtypes = [C.c_void_p]
+        L.polb200_rigid_last_error.restype = C.c_char_p
+        L.polb200_rigid_init.argtypes = [C.c_void_p, C.POINTER(RigidParams), C.c_int] + [C.c_void_p] * 7 + [C.POINTER(RigidInfo)]
+        L.polb200_rigid_dof.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+        L.polb200_rigid_setup.argtypes = [C.c_void_p, C.POINTER(RigidAtoms), C.c_int]
+        L.polb200_rigid_initial_integrate.argtypes = [C.c_void_p, C.POINTER(RigidAtoms), C.c_int, C.c_double]
+        L.polb200_rigid_final_integrate.argtypes = [C.c_void_p, C.POINTER(RigidAtoms)]
+        L.polb200_rigid_pre_neighbor.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.polb200_rigid_virial.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.polb200_rigid_scalar.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.polb200_rigid_reset_dt.argtypes = [C.c_void_p, C.c_double]
+        L.polb200_rigid_fetch.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_long]
+        L.polb200_rigid_fetch.restype = C.c_long
+        L.polb200_rigid_launch_count.argtypes = [C.c_void_p, C.c_int]
+        L.polb200_rigid_launch_count.restype = C.c_long
+        L.polb200_rigid_last_ms.argtypes = [C.c_void_p]
+        L.polb200_rigid_last_ms.restype = C.c_double
         L.polb200_decomp_plan.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                           C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int),
                                           C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double),
@@ -416,3 +455,147 @@ class Ewald:
 
     def last_ms(self):
         return lib().polb200_ewald_last_ms(self._h)
+
+
+# real units (src/update.cpp:150-170)
+REAL_FTM2V = 1.0 / 48.88821291 / 48.88821291
+REAL_MVV2E = 48.88821291 * 48.88821291
+REAL_BOLTZ = 0.0019872067
+REAL_NKTV2P = 68568.415
+
+
+def pack_image(image3):
+    """(n,3) integer image flags -> LAMMPS' packed 32-bit imageint (src/lmptype.h:96-103)"""
+    im = np.asarray(image3, dtype=np.int64) + 512
+    return ((im[:, 2] << 20) | (im[:, 1] << 10) | im[:, 0]).astype(np.int32)
+
+
+class Rigid:
+    """`fix ID group rigid/nve molecule` / `rigid/nvt molecule temp ... tparam ...` on one GPU: the device counterpart
+    of the reference's FixRigidNH (src/RIGID/fix_rigid_nh.cpp).  Methods mirror the Fix interface: init, dof, setup,
+    initial_integrate, final_integrate, pre_neighbor, compute_scalar."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        rc = lib().polb200_rigid_create(C.byref(self._h), device)
+        if rc != OK:
+            raise Polb200Error(rc, "polb200_rigid_create failed (no CUDA device? there is no CPU fallback)")
+        self.info = None
+
+    def close(self):
+        if self._h:
+            lib().polb200_rigid_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != OK:
+            raise Polb200Error(rc, lib().polb200_rigid_last_error(self._h).decode())
+
+    def init(self, tag, molecule, mass, image, x, v, boxlo, boxhi, dt, ingroup=None, temp=None, tparam=(10, 1, 3),
+             ftm2v=REAL_FTM2V, mvv2e=REAL_MVV2E, boltz=REAL_BOLTZ, periodic=(1, 1, 1)):
+        """image: packed imageint [n] or (n,3) flags.  temp = (Tstart, Tstop, Tdamp) selects rigid/nvt."""
+        p = RigidParams()
+        p.thermostat = 0 if temp is None else 1
+        if temp is not None:
+            p.t_start, p.t_stop, p.t_period = [float(t) for t in temp]
+        p.t_chain, p.t_iter, p.t_order = [int(t) for t in tparam]
+        p.dt, p.ftm2v, p.mvv2e, p.boltz = float(dt), ftm2v, mvv2e, boltz
+        p.boxlo = (C.c_double * 3)(*[float(t) for t in boxlo])
+        p.boxhi = (C.c_double * 3)(*[float(t) for t in boxhi])
+        p.periodic = (C.c_int * 3)(*[int(t) for t in periodic])
+        image = np.asarray(image)
+        if image.ndim == 2:
+            image = pack_image(image)
+        arrs = [np.ascontiguousarray(tag, dtype=np.int32), np.ascontiguousarray(molecule, dtype=np.int32),
+                None if ingroup is None else np.ascontiguousarray(ingroup, dtype=np.int32),
+                np.ascontiguousarray(mass, dtype=np.float64), np.ascontiguousarray(image, dtype=np.int32),
+                np.ascontiguousarray(x, dtype=np.float64), np.ascontiguousarray(v, dtype=np.float64)]
+        info = RigidInfo()
+        self._check(lib().polb200_rigid_init(self._h, C.byref(p), len(arrs[0]),
+                                             *[None if a is None else a.ctypes.data for a in arrs], C.byref(info)))
+        self.info = info
+        return info
+
+    def dof(self, tag, tgroup=None):
+        tag = np.ascontiguousarray(tag, dtype=np.int32)
+        tg = None if tgroup is None else np.ascontiguousarray(tgroup, dtype=np.int32)
+        out = C.c_int()
+        self._check(lib().polb200_rigid_dof(self._h, len(tag), tag.ctypes.data, None if tg is None else tg.ctypes.data,
+                                            C.byref(out)))
+        return out.value
+
+    @staticmethod
+    def _atoms(tag, x, v, f):
+        for a in (x, v, f):
+            assert a is None or (a.dtype == np.float64 and a.flags["C_CONTIGUOUS"])
+        assert tag.dtype == np.int32 and tag.flags["C_CONTIGUOUS"]
+        return RigidAtoms(len(tag), tag.ctypes.data, None if x is None else x.ctypes.data, v.ctypes.data,
+                          None if f is None else f.ctypes.data, 0)
+
+    def setup(self, tag, x, v, f, vflag=1):
+        """host numpy buffers; v is updated in place"""
+        a = self._atoms(tag, x, v, f)
+        self._check(lib().polb200_rigid_setup(self._h, C.byref(a), vflag))
+
+    def initial_integrate(self, tag, x, v, f, vflag=1, run_fraction=0.0):
+        a = self._atoms(tag, x, v, f)
+        self._check(lib().polb200_rigid_initial_integrate(self._h, C.byref(a), vflag, run_fraction))
+
+    def final_integrate(self, tag, x, v, f):
+        a = self._atoms(tag, x, v, f)
+        self._check(lib().polb200_rigid_final_integrate(self._h, C.byref(a)))
+
+    # device-resident variants: integer addresses of device buffers (e.g. torch.Tensor.data_ptr())
+    def setup_device(self, n, tag_ptr, x_ptr, v_ptr, f_ptr, vflag=1):
+        a = RigidAtoms(n, tag_ptr, x_ptr, v_ptr, f_ptr, 1)
+        self._check(lib().polb200_rigid_setup(self._h, C.byref(a), vflag))
+
+    def initial_integrate_device(self, n, tag_ptr, x_ptr, v_ptr, f_ptr, vflag=1, run_fraction=0.0):
+        a = RigidAtoms(n, tag_ptr, x_ptr, v_ptr, f_ptr, 1)
+        self._check(lib().polb200_rigid_initial_integrate(self._h, C.byref(a), vflag, run_fraction))
+
+    def final_integrate_device(self, n, tag_ptr, x_ptr, v_ptr, f_ptr):
+        a = RigidAtoms(n, tag_ptr, x_ptr, v_ptr, f_ptr, 1)
+        self._check(lib().polb200_rigid_final_integrate(self._h, C.byref(a)))
+
+    def pre_neighbor(self, tag, image):
+        tag = np.ascontiguousarray(tag, dtype=np.int32)
+        image = np.asarray(image)
+        if image.ndim == 2:
+            image = pack_image(image)
+        image = np.ascontiguousarray(image, dtype=np.int32)
+        self._check(lib().polb200_rigid_pre_neighbor(self._h, len(tag), tag.ctypes.data, image.ctypes.data, 0))
+
+    def virial(self):
+        v = (C.c_double * 6)()
+        self._check(lib().polb200_rigid_virial(self._h, v))
+        return np.array(v[:])
+
+    def scalars(self):
+        """(compute_scalar, translational KE, rotational KE) -- KE in mass*velocity^2 units (multiply by mvv2e)"""
+        s, kt, kr = C.c_double(), C.c_double(), C.c_double()
+        self._check(lib().polb200_rigid_scalar(self._h, C.byref(s), C.byref(kt), C.byref(kr)))
+        return s.value, kt.value, kr.value
+
+    def reset_dt(self, dt):
+        self._check(lib().polb200_rigid_reset_dt(self._h, float(dt)))
+
+    def fetch(self, name):
+        width = 4 if name in ("quat", "conjqm") else 1 if name == "masstotal" else 3
+        out = np.zeros((self.info.nbody, width))
+        n = lib().polb200_rigid_fetch(self._h, name.encode(), out.ctypes.data, out.size)
+        if n < 0:
+            raise Polb200Error(ERR_ARG, f"polb200_rigid_fetch({name}) = {n}")
+        return out
+
+    def launch_count(self, reset=False):
+        return lib().polb200_rigid_launch_count(self._h, 1 if reset else 0)
+
+    def last_ms(self):
+        return lib().polb200_rigid_last_ms(self._h)

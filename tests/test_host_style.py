@@ -42,7 +42,7 @@ def test_library_exports_every_declared_symbol():
     L = pb.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.polb200_abi_version() == 2
+    assert L.polb200_abi_version() == 3
 
 
 def test_compute_without_device_fails_loudly(style):
@@ -205,7 +205,7 @@ def test_tail_correction(style):
 
 
 def test_device_entry_points_fail_loudly_without_a_gpu():
-    """No CUDA device => no handle: the product never falls back to a CPU implementation (pair path and KSpace)."""
+    """No CUDA device => no handle: the product never falls back to a CPU implementation (pair path, KSpace, rigid-body integrator)."""
     try:
         import torch
         has_gpu = torch.cuda.is_available()
@@ -217,3 +217,5 @@ def test_device_entry_points_fail_loudly_without_a_gpu():
         pb.PairStyle(device=0)
     with pytest.raises(pb.Polb200Error):
         pb.Ewald(device=0)
+    with pytest.raises(pb.Polb200Error):
+        pb.Rigid(device=0)

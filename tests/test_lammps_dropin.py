@@ -97,3 +97,111 @@ def test_same_script_same_thermo(tmp_path, words, tol):
     for col, name in enumerate(["step", "pe", "evdwl", "ecoul", "elong", "epol", "press"]):
         scale = max(np.abs(ref[:, col]).max(), 1.0)
         assert np.abs(ref[:, col] - new[:, col]).max() <= tol * scale, (name, ref[:, col], new[:, col])
+
+
+# ---- fix rigid/nve|nvt on the device -------------------------------------------------------
+
+def thermo_rows(log):
+    """last thermo table of a log as (columns, float rows)"""
+    cols, rows, on = None, [], False
+    for line in log.splitlines():
+        if line.startswith("Step "):
+            cols, rows, on = line.split(), [], True
+            continue
+        if on:
+            if line.startswith("Loop time"):
+                on = False
+                continue
+            t = line.split()
+            if len(t) == len(cols):
+                try:
+                    rows.append([float(v) for v in t])
+                except ValueError:
+                    pass
+    return cols, np.array(rows)
+
+
+def run_log(binary, work, name):
+    r = subprocess.run([str(binary), "-in", "in.case", "-echo", "none", "-log", f"log.{name}"], cwd=work,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    return thermo_rows((work / f"log.{name}").read_text())
+
+
+@pytest.mark.parametrize("fix_line,scalar", [
+    ("fix rig all rigid/nve molecule", False),
+    ("fix rig all rigid/nvt molecule temp 298.15 250.0 100.0 tparam 50 1 3", True),
+])
+def test_rigid_fix_same_script_same_thermo(tmp_path, fix_line, scalar):
+    """a rigid water box under the stock lj/cut/coul/long pair style: in lmp_b200 the fix (and Ewald) run on the GPU,
+    in the reference binary on the host; temperature, energies, pressure and the fix's scalar agree step by step"""
+    if not LMP_REF.exists() or not LMP_B200.exists():
+        pytest.skip("LAMMPS binaries not built (need the reference tree at build time)")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_rigid", ROOT / "oracle" / "make_golden_rigid.py")
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    data, _ = mg.water_data(4)
+    (tmp_path / "water.data").write_text(data)
+    text = mg.water_input(fix_line, 8, 1.0)
+    th = "thermo_style custom step temp ke pe press" + (" f_rig" if scalar else "")
+    text += "\n".join([th, "thermo_modify format float %.14g", "thermo 1", "run 8"]) + "\n"
+    (tmp_path / "in.case").write_text(text)
+    cols_r, ref = run_log(LMP_REF, tmp_path, "ref")
+    cols_n, new = run_log(LMP_B200, tmp_path, "b200")
+    assert cols_r == cols_n and ref.shape == new.shape and ref.shape[0] == 9
+    for c, name in enumerate(cols_r):
+        scale = max(np.abs(ref[:, c]).max(), 1.0)
+        assert np.abs(ref[:, c] - new[:, c]).max() <= 1e-8 * scale, (name, ref[:, c], new[:, c])
+
+
+def test_shipped_h2_example_reproduces_the_committed_log(tmp_path):
+    """The reference's Bulk H2 example AS SHIPPED -- polarization pair style, Ewald and `fix rigid/nve molecule` all
+    replaced by their device counterparts in lmp_b200 -- against the thermo table of the reference's own committed
+    log (polarization/examples/Bulk H2/log.lammps:92-100, 8 printed digits; tests/golden/thermo_logs.json)."""
+    if not LMP_B200.exists():
+        pytest.skip("lmp_b200 not built (needs the reference tree at build time)")
+    fx = H.load_fixture("h2_default_step0")
+    n = fx["x"].shape[0]
+    tag, mol, typ = fx["tag"], fx["molecule"], fx["type"]
+    L = fx["boxhi"] - fx["boxlo"]
+    # unwrap every molecule around its first atom: read_data wraps and sets the image flags fix rigid needs
+    order = np.argsort(tag)
+    x = fx["x"].copy()
+    first = {}
+    for i in order:
+        m = int(mol[i])
+        if m not in first:
+            first[m] = x[i].copy()
+        x[i] = first[m] + (x[i] - first[m]) - L * np.rint((x[i] - first[m]) / L)
+    nsp, sp = fx["nspecial"], fx["special"]
+    bonds = sorted({(min(int(tag[i]), int(sp[i, k])), max(int(tag[i]), int(sp[i, k]))) for i in range(n)
+                    for k in range(int(nsp[i, 0]))})
+    with open(tmp_path / "h2.data", "w") as fh:
+        fh.write(f"Bulk H2 from golden fixture\n\n{n} atoms\n3 atom types\n{len(bonds)} bonds\n1 bond types\n\n")
+        for d, c in enumerate("xyz"):
+            fh.write(f"{float(fx['boxlo'][d]):.17g} {float(fx['boxhi'][d]):.17g} {c}lo {c}hi\n")
+        fh.write("\nAtoms\n\n")
+        for i in order:
+            fh.write(f"{int(tag[i])} {int(mol[i])} {int(typ[i])} {float(fx['q'][i]):.17g} {x[i, 0]:.17g} {x[i, 1]:.17g} {x[i, 2]:.17g}\n")
+        fh.write("\nBonds\n\n")
+        for k, (a, b) in enumerate(bonds):
+            fh.write(f"{k + 1} 1 {a} {b}\n")
+    # the shipped input, line for line where it matters (its `timestep 2` precedes `units real`, so dt = 1 fs)
+    lines = ["timestep 2", "units real", "boundary p p p", "atom_style full", "read_data h2.data", "bond_style zero", "bond_coeff *",
+             "mass 1 0.00001", "mass 2 1.00800", "mass 3 0.00001",
+             "set type 1 static_polarizability 0.69380", "set type 2 static_polarizability 0.00044",
+             "set type 3 static_polarizability 0.00000", "kspace_style ewald 1.0e-4", str(fx["pair_style"])]
+    lines += str(fx["pair_coeff"]).splitlines()
+    lines += ["special_bonds lj/coul 0.0 0.0 0.0",
+              "thermo_style custom step etotal ke pe evdwl ecoul elong epol temp press", "thermo 1",
+              "velocity all create 298.15 12345 rot yes mom yes dist gaussian",
+              "fix rigid_nve all rigid/nve molecule", "run 7"]
+    (tmp_path / "in.case").write_text("\n".join(lines) + "\n")
+    cols, new = run_log(LMP_B200, tmp_path, "b200")
+    ref = H.thermo_logs()["h2"]
+    assert cols == ref["columns"] and new.shape[0] == len(ref["rows"]) == 8   # the committed log ends inside step 8
+    for r in range(8):
+        for c, name in enumerate(cols):
+            want = float(ref["rows"][r][name])
+            assert abs(new[r, c] - want) <= 3e-7 * max(abs(want), 1.0), (r, name, new[r, c], want)
