@@ -413,11 +413,18 @@ __global__ void k_rigid_remap(int nbody, RigidConst rc, BodyFrame *__restrict__ 
   for (int d = 0; d < 3; d++) {
     double c = frame[b].xcm[d];
     int im = imagebody[3 * b + d];
-    while (c < rc.lo[d]) { c += rc.prd[d]; im = (im - 1) & IMGMASK; }
-    while (c >= rc.hi[d]) { c -= rc.prd[d]; im = (im + 1) & IMGMASK; }
+    if (!isfinite(c)) continue;  // a blown-up trajectory must not hang the device; the caller sees it in x
+    // the reference loops `while (c < lo) c += prd` / `while (c >= hi) c -= prd`; one period (the only case a sane
+    // trajectory produces between two rebuilds) is done the same way, bit for bit; more periods in one multiply
+    const double nper = floor((c - rc.lo[d]) / rc.prd[d]);
+    if (nper == -1.0) { c += rc.prd[d]; im -= 1; }
+    else if (nper == 1.0) { c -= rc.prd[d]; im += 1; }
+    else if (nper != 0.0 && fabs(nper) < 1.0e6) { c -= nper * rc.prd[d]; im += (int)nper; }
+    if (c < rc.lo[d]) { c += rc.prd[d]; im -= 1; }
+    if (c >= rc.hi[d]) { c -= rc.prd[d]; im += 1; }
     c = fmax(c, rc.lo[d]);
     frame[b].xcm[d] = c;
-    imagebody[3 * b + d] = im;
+    imagebody[3 * b + d] = im & IMGMASK;
   }
 }
 
@@ -768,6 +775,9 @@ int polb200_rigid_init(polb200_rigid_t *r, const polb200_rigid_params *p, int nl
     // ---- body numbering: molecules of the group in ascending id (fix_rigid.cpp:184-220)
     int maxmol = -1, maxtag = 0;
     for (int i = 0; i < n; i++) {
+      for (int k = 0; k < 3; k++)
+        if (!std::isfinite(x[3 * i + k]) || !std::isfinite(v[3 * i + k]))
+          throw StyleError{POLB200_ERR_NAN, "Non-numeric positions - simulation unstable"};
       if (tag[i] <= 0) throw StyleError{POLB200_ERR_ARG, "polb200_rigid: atom ids must be positive"};
       maxtag = std::max(maxtag, tag[i]);
       if (!ingroup || ingroup[i]) {
@@ -787,7 +797,11 @@ int polb200_rigid_init(polb200_rigid_t *r, const polb200_rigid_params *p, int nl
     r->nbody = nbody;
     r->maxtag = maxtag;
 
-    // ---- setup_bodies_static (fix_rigid.cpp:1605-2112), point particles
+    // ---- setup_bodies_static (fix_rigid.cpp:1605-2112), point particles.  The reference sums over atoms in local order;
+    // here every sum runs in atom-id order, so the bodies do not depend on how the caller has its atoms sorted.
+    std::vector<int> order(n);
+    for (int i = 0; i < n; i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int p, int q) { return tag[p] < tag[q]; });
     const double *prd = rc.prd;
     auto unwrap = [&](int i, int img, double *u) {
       u[0] = x[3 * i] + ((img & IMGMASK) - IMGMAX) * prd[0];
@@ -800,7 +814,8 @@ int polb200_rigid_init(polb200_rigid_t *r, const polb200_rigid_params *p, int nl
     memset(frame.data(), 0, sizeof(BodyFrame) * nbody);
     memset(dyn.data(), 0, sizeof(BodyDyn) * nbody);
     std::vector<double> sum((size_t)6 * nbody, 0.0);
-    for (int i = 0; i < n; i++) {
+    for (int ii = 0; ii < n; ii++) {
+      const int i = order[ii];
       if (body[i] < 0) continue;
       xcmimage[i] = image[i];
       double u[3];
@@ -823,7 +838,8 @@ int polb200_rigid_init(polb200_rigid_t *r, const polb200_rigid_params *p, int nl
         frame[b].xcm[d] = std::max(c, rc.lo[d]);
         imagebody[3 * b + d] = im;
       }
-    for (int i = 0; i < n; i++) {
+    for (int ii = 0; ii < n; ii++) {
+      const int i = order[ii];
       if (body[i] < 0) continue;
       const int b = body[i], im = image[i];
       const int xd = IMGMAX + (im & IMGMASK) - imagebody[3 * b], yd = IMGMAX + ((im >> IMGBITS) & IMGMASK) - imagebody[3 * b + 1];
@@ -831,7 +847,8 @@ int polb200_rigid_init(polb200_rigid_t *r, const polb200_rigid_params *p, int nl
       xcmimage[i] = (zd << IMG2BITS) | (yd << IMGBITS) | xd;
     }
     std::fill(sum.begin(), sum.end(), 0.0);
-    for (int i = 0; i < n; i++) {
+    for (int ii = 0; ii < n; ii++) {
+      const int i = order[ii];
       if (body[i] < 0) continue;
       double u[3];
       unwrap(i, xcmimage[i], u);
@@ -861,7 +878,8 @@ int polb200_rigid_init(polb200_rigid_t *r, const polb200_rigid_params *p, int nl
     }
     std::vector<AtomRec> arec_local(n);
     std::fill(sum.begin(), sum.end(), 0.0);
-    for (int i = 0; i < n; i++) {
+    for (int ii = 0; ii < n; ii++) {
+      const int i = order[ii];
       AtomRec &a = arec_local[i];
       a.d[0] = a.d[1] = a.d[2] = 0.0;
       a.mass = mass[i];
@@ -888,7 +906,8 @@ int polb200_rigid_init(polb200_rigid_t *r, const polb200_rigid_params *p, int nl
     }
     // ---- setup_bodies_dynamic (fix_rigid.cpp:2120-2211)
     std::fill(sum.begin(), sum.end(), 0.0);
-    for (int i = 0; i < n; i++) {
+    for (int ii = 0; ii < n; ii++) {
+      const int i = order[ii];
       if (body[i] < 0) continue;
       double u[3];
       unwrap(i, xcmimage[i], u);

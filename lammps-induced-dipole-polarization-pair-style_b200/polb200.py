@@ -572,6 +572,10 @@ class Rigid:
         image = np.ascontiguousarray(image, dtype=np.int32)
         self._check(lib().polb200_rigid_pre_neighbor(self._h, len(tag), tag.ctypes.data, image.ctypes.data, 0))
 
+    def pre_neighbor_device(self, n, tag_ptr, image_ptr):
+        """device int32 arrays: atom ids and packed image flags"""
+        self._check(lib().polb200_rigid_pre_neighbor(self._h, n, tag_ptr, image_ptr, 1))
+
     def virial(self):
         v = (C.c_double * 6)()
         self._check(lib().polb200_rigid_virial(self._h, v))

@@ -214,6 +214,7 @@ def test_config3_water_box_properties():
     # device-resident continuation vs host-buffer continuation with the same random forces
     xt, vt = torch.from_numpy(x).cuda(), torch.from_numpy(v).cuda()
     tagt = torch.from_numpy(s.tag).cuda()
+    torch.cuda.synchronize()
     R2 = pb.Rigid(device=0)
     R2.init(s.tag, s.molecule, mass, image, s.x, v0, s.boxlo, s.boxhi, 1.0)
     x2, v2 = np.ascontiguousarray(s.x), np.ascontiguousarray(v0)
@@ -226,6 +227,7 @@ def test_config3_water_box_properties():
     for _ in range(10):
         f = rng.normal(scale=2.0, size=(n, 3))
         ft_prev, ft = torch.from_numpy(fprev).cuda(), torch.from_numpy(f).cuda()
+        torch.cuda.synchronize()   # the library runs on its own stream: torch's copies must have landed
         R.initial_integrate_device(n, tagt.data_ptr(), xt.data_ptr(), vt.data_ptr(), ft_prev.data_ptr(), vflag=1)
         R.final_integrate_device(n, tagt.data_ptr(), xt.data_ptr(), vt.data_ptr(), ft.data_ptr())
         R2.initial_integrate(s.tag, x2, v2, np.ascontiguousarray(fprev), vflag=1)
