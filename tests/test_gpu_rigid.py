@@ -201,7 +201,7 @@ def test_config3_water_box_properties():
         cosang = (a * b).sum(1) / np.linalg.norm(a, axis=1) / np.linalg.norm(b, axis=1)
         return np.linalg.norm(a, axis=1), np.linalg.norm(b, axis=1), np.degrees(np.arccos(cosang))
 
-    x, v = np.ascontiguousarray(s.x), np.ascontiguousarray(v0)
+    x, v = s.x.copy(), v0.copy()      # the integrator works in place: keep the initial state for the second handle
     zero = np.zeros((n, 3))
     R.setup(s.tag, x, v, zero, vflag=0)
     p0 = (mass[:, None] * v).sum(0)
@@ -217,7 +217,7 @@ def test_config3_water_box_properties():
     torch.cuda.synchronize()
     R2 = pb.Rigid(device=0)
     R2.init(s.tag, s.molecule, mass, image, s.x, v0, s.boxlo, s.boxhi, 1.0)
-    x2, v2 = np.ascontiguousarray(s.x), np.ascontiguousarray(v0)
+    x2, v2 = s.x.copy(), v0.copy()
     R2.setup(s.tag, x2, v2, zero, vflag=0)
     for _ in range(10):
         R2.initial_integrate(s.tag, x2, v2, zero, vflag=0)

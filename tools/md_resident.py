@@ -61,7 +61,7 @@ def make_pair(s, g_ewald):
     p.set_ntypes(2)
     p.command(f"pair_style lj/cut/coul/long/polarization 2.5 {CUT} precision 1e-11 max_iterations 200 polar_gamma 1.03 "
               f"damp_type exponential use_previous yes polar_cutoff {CUT}")
-    p.command("pair_coeff 1 1 0.155 3.166")
+    p.command("pair_coeff 1 1 0.155 3.166 10.0")   # a physical O-O LJ cutoff (the bench configs' 2.5 A leaves no repulsion)
     p.command("pair_coeff 2 2 0.0 1.0")
     p.init(g_ewald=g_ewald, special_lj=(1.0, 0.0, 0.0, 0.0), special_coul=(1.0, 0.0, 0.0, 0.0), molecular=1)
     p.set_box(s.boxlo, s.boxhi)
