@@ -274,6 +274,10 @@ int polb200_rigid_virial(polb200_rigid_t *r, double virial[6]);
 /* FixRigidNH::compute_scalar (fix_rigid_nh.cpp:991-1016; = FixRigid::compute_scalar :2595-2622 for rigid/nve),
  * FixRigid::extract_ke (:2650-2659) and extract_erotational (:2665-2689); any pointer may be NULL */
 int polb200_rigid_scalar(polb200_rigid_t *r, double *scalar, double *ke_translational, double *ke_rotational);
+/* The thermostat state FixRigidNH::write_restart / restart carry (fix_rigid_nh.cpp:1171-1267): per chain link
+ * eta_t, eta_r, eta_dot_t, eta_dot_r, interleaved in that order (4 * t_chain doubles).  set before polb200_rigid_setup. */
+int polb200_rigid_get_chain(polb200_rigid_t *r, double *state, int capacity, int *t_chain);
+int polb200_rigid_set_chain(polb200_rigid_t *r, const double *state, int t_chain);
 /* FixRigid::reset_dt (fix_rigid.cpp:2553-2558) */
 int polb200_rigid_reset_dt(polb200_rigid_t *r, double dt);
 /* body arrays for tests / compute_array: "xcm" "vcm" "fcm" "torque" "angmom" "omega" "ex" "ey" "ez" "inertia" [nbody][3],

@@ -1145,6 +1145,49 @@ int polb200_rigid_scalar(polb200_rigid_t *r, double *scalar, double *ke_t, doubl
   });
 }
 
+int polb200_rigid_get_chain(polb200_rigid_t *r, double *state, int capacity, int *t_chain)
+{
+  if (!r || !state || !t_chain) return POLB200_ERR_ARG;
+  return rigid_guarded(r, [&] {
+    if (!r->ready) throw StyleError{POLB200_ERR_STATE, "polb200_rigid_init has not been called"};
+    const int nc = r->rc.tstat ? r->rc.t_chain : 0;
+    *t_chain = nc;
+    if (capacity < 4 * nc) throw StyleError{POLB200_ERR_ARG, "polb200_rigid_get_chain: buffer too small"};
+    if (!nc) return;
+    CUDA_CHECK(cudaSetDevice(r->device));
+    Chain c;
+    CUDA_CHECK(cudaMemcpyAsync(&c, r->chain.p, sizeof(Chain), cudaMemcpyDeviceToHost, r->stream));
+    CUDA_CHECK(cudaStreamSynchronize(r->stream));
+    for (int i = 0; i < nc; i++) {
+      state[4 * i] = c.eta_t[i];
+      state[4 * i + 1] = c.eta_r[i];
+      state[4 * i + 2] = c.eta_dot_t[i];
+      state[4 * i + 3] = c.eta_dot_r[i];
+    }
+  });
+}
+
+int polb200_rigid_set_chain(polb200_rigid_t *r, const double *state, int t_chain)
+{
+  if (!r || !state) return POLB200_ERR_ARG;
+  return rigid_guarded(r, [&] {
+    if (!r->ready) throw StyleError{POLB200_ERR_STATE, "polb200_rigid_init has not been called"};
+    if (!r->rc.tstat || t_chain != r->rc.t_chain) return;  // the reference skips a record of another chain length too
+    CUDA_CHECK(cudaSetDevice(r->device));
+    Chain c;
+    CUDA_CHECK(cudaMemcpyAsync(&c, r->chain.p, sizeof(Chain), cudaMemcpyDeviceToHost, r->stream));
+    CUDA_CHECK(cudaStreamSynchronize(r->stream));
+    for (int i = 0; i < t_chain; i++) {
+      c.eta_t[i] = state[4 * i];
+      c.eta_r[i] = state[4 * i + 1];
+      c.eta_dot_t[i] = state[4 * i + 2];
+      c.eta_dot_r[i] = state[4 * i + 3];
+    }
+    CUDA_CHECK(cudaMemcpyAsync(r->chain.p, &c, sizeof(Chain), cudaMemcpyHostToDevice, r->stream));
+    CUDA_CHECK(cudaStreamSynchronize(r->stream));
+  });
+}
+
 int polb200_rigid_reset_dt(polb200_rigid_t *r, double dt)
 {
   if (!r) return POLB200_ERR_ARG;

@@ -3,7 +3,8 @@
 #   lammps/_build/lmp_b200  =  reference host framework (LAMMPS 16Mar2018, from a scratch copy of
 #   $POLB200_REFERENCE/src, repaired exactly like the oracle build: oracle/build_ref.sh steps 1-3 without the
 #   dump hooks)  +  pair_lj_cut_coul_long_polarization_b200.{h,cpp}  +  ewald_b200.{h,cpp}  +
-#   fix_rigid_nh_b200.{h,cpp}  +  libpolb200.so.
+#   fix_rigid_nh_b200.{h,cpp}  +  atom_vec_full_polar_b200.{h,cpp}  +  compute_polarization_atom_b200.{h,cpp}  +  libpolb200.so.
+#   (the oracle's 12-line AtomVecFull patch is NOT used here: the committed atom style replaces it)
 # An unchanged input script (polarization/examples/*) then drives the CUDA path.  Nothing of the reference is
 # copied into this repository; the binary lands in lammps/_build/ (git-ignored, travels to the GPU box).
 set -euo pipefail
@@ -23,6 +24,8 @@ mkdir -p "$OUT"
 if [ -x "$OUT/lmp_b200" ] && [ "$OUT/lmp_b200" -nt "$HERE/pair_lj_cut_coul_long_polarization_b200.cpp" ] \
    && [ "$OUT/lmp_b200" -nt "$HERE/pair_lj_cut_coul_long_polarization_b200.h" ] \
    && [ "$OUT/lmp_b200" -nt "$HERE/ewald_b200.cpp" ] && [ "$OUT/lmp_b200" -nt "$HERE/ewald_b200.h" ] \
+   && [ "$OUT/lmp_b200" -nt "$HERE/atom_vec_full_polar_b200.cpp" ] && [ "$OUT/lmp_b200" -nt "$HERE/atom_vec_full_polar_b200.h" ] \
+   && [ "$OUT/lmp_b200" -nt "$HERE/compute_polarization_atom_b200.cpp" ] && [ "$OUT/lmp_b200" -nt "$HERE/compute_polarization_atom_b200.h" ] \
    && [ "$OUT/lmp_b200" -nt "$HERE/fix_rigid_nh_b200.cpp" ] && [ "$OUT/lmp_b200" -nt "$HERE/fix_rigid_nh_b200.h" ] \
    && [ "$OUT/lmp_b200" -nt "$ROOT/include/polb200.h" ] && [ -z "${POLB200_LMP_REBUILD:-}" ]; then
   echo "build_lmp_b200: $OUT/lmp_b200 is up to date"
@@ -42,9 +45,15 @@ if [ ! -f "$W/src/Obj_serial/lammps.o" ]; then
   rm -f compute_dihedral.* compute_improper.* fix_nve_sphere.* fix_nh_sphere.* fix_nvt_sphere.* \
         fix_npt_sphere.* fix_nph_sphere.* pair_lj_long_coul_long.* pair_buck_long_coul_long.* \
         pair_lj_long_tip4p_long.* ewald_disp.*
-  POLB200_PATCH_ATOMVEC_ONLY=1 python3 "$ROOT/oracle/patch_ref.py" "$W/src"
 fi
 cd "$W/src"
+# atom_style full that carries the polarization arrays: the stock class stays as the base and gives up
+# its style name; our subclass registers as `full`.  compute polarization/atom exposes dipoles and fields.
+cp "$REF/src/MOLECULE/atom_vec_full.h" "$REF/src/MOLECULE/atom_vec_full.cpp" .
+chmod u+w atom_vec_full.h atom_vec_full.cpp
+sed -i 's|^AtomStyle(full,AtomVecFull)|AtomStyle(full/stock,AtomVecFull)|' atom_vec_full.h
+cp "$HERE/atom_vec_full_polar_b200.h" "$HERE/atom_vec_full_polar_b200.cpp" .
+cp "$HERE/compute_polarization_atom_b200.h" "$HERE/compute_polarization_atom_b200.cpp" .
 # the swap: the reference's implementation leaves, the drop-in takes its file names
 cp "$HERE/pair_lj_cut_coul_long_polarization_b200.h" pair_lj_cut_coul_long_polarization.h
 cp "$HERE/pair_lj_cut_coul_long_polarization_b200.cpp" pair_lj_cut_coul_long_polarization.cpp

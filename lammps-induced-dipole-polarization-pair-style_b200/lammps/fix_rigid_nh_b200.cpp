@@ -23,7 +23,7 @@ using namespace LAMMPS_NS;
 using namespace FixConst;
 
 FixRigidNHB200::FixRigidNHB200(LAMMPS *lmp, int narg, char **arg) :
-  Fix(lmp, narg, arg), handle(NULL), ingroup(NULL), massone(NULL)
+  Fix(lmp, narg, arg), handle(NULL), ingroup(NULL), massone(NULL), nchain_restart(0), chain_restart(NULL)
 {
   // the flags FixRigid's constructor sets (src/RIGID/fix_rigid.cpp:75-83)
   scalar_flag = 1;
@@ -72,6 +72,7 @@ FixRigidNHB200::FixRigidNHB200(LAMMPS *lmp, int narg, char **arg) :
   }
   if (strcmp(style,"rigid/nvt") == 0) {            // fix_rigid_nvt.cpp:29-49
     scalar_flag = 1;
+    restart_global = 1;
     extscalar = 1;
     if (tstat_flag == 0) error->all(FLERR,"Did not set temperature for fix rigid/nvt");
     if (t_start < 0.0 || t_stop <= 0.0)
@@ -119,6 +120,7 @@ FixRigidNHB200::~FixRigidNHB200()
   if (handle) polb200_rigid_destroy(handle);
   memory->destroy(ingroup);
   memory->destroy(massone);
+  delete [] chain_restart;
 }
 
 void FixRigidNHB200::fail()
@@ -179,6 +181,11 @@ void FixRigidNHB200::init()
   nbody = info.nbody;
   setupflag = 1;
   t_target = t_start;
+  if (chain_restart) {   // FixRigidNH::restart ran before the first init: the chains start from the stored state
+    if (polb200_rigid_set_chain(handle, chain_restart, nchain_restart) != POLB200_OK) fail();
+    delete [] chain_restart;
+    chain_restart = NULL;
+  }
 }
 
 void FixRigidNHB200::setup_pre_neighbor()
@@ -264,6 +271,44 @@ void *FixRigidNHB200::extract(const char *str, int &dim)
     return &t_target;
   }
   return NULL;
+}
+
+/* the record FixRigidNH::write_restart writes (fix_rigid_nh.cpp:1171-1224): tstat_flag, t_chain, 4 doubles per chain
+   link, pstat_flag = 0 -- restart files move freely between the reference and the drop-in */
+
+void FixRigidNHB200::write_restart(FILE *fp)
+{
+  if (tstat_flag == 0) return;
+  const int nsize = 2 + 1 + 4*t_chain;
+  double *list = new double[nsize];
+  int n = 0, nc = 0;
+  list[n++] = tstat_flag;
+  list[n++] = t_chain;
+  if (polb200_rigid_get_chain(handle, list+n, 4*t_chain, &nc) != POLB200_OK) fail();
+  if (nc != t_chain) for (int i = 0; i < 4*t_chain; i++) list[n+i] = 0.0;   // before the first init: chains at rest
+  n += 4*t_chain;
+  list[n++] = 0;
+  if (comm->me == 0) {
+    int size = nsize*sizeof(double);
+    fwrite(&size,sizeof(int),1,fp);
+    fwrite(list,sizeof(double),nsize,fp);
+  }
+  delete [] list;
+}
+
+void FixRigidNHB200::restart(char *buf)
+{
+  double *list = (double *) buf;
+  int n = 0;
+  const int flag = static_cast<int> (list[n++]);
+  if (!flag) return;
+  const int m = static_cast<int> (list[n++]);
+  if (tstat_flag && m == t_chain) {
+    delete [] chain_restart;
+    chain_restart = new double[4*m];
+    for (int i = 0; i < 4*m; i++) chain_restart[i] = list[n++];
+    nchain_restart = m;
+  }
 }
 
 double FixRigidNHB200::memory_usage()

@@ -19,6 +19,7 @@ FixStyle(rigid/nvt,FixRigidNHB200)
 #ifndef LMP_FIX_RIGID_NH_B200_H
 #define LMP_FIX_RIGID_NH_B200_H
 
+#include <cstdio>
 #include "fix.h"
 
 struct polb200_rigid;
@@ -42,12 +43,16 @@ class FixRigidNHB200 : public Fix {
   double compute_scalar();
   double memory_usage();
   void *extract(const char *, int &);
+  void write_restart(FILE *);
+  void restart(char *);
 
  private:
   struct polb200_rigid *handle;
   int tstat_flag, t_chain, t_iter, t_order, nbody, setupflag;
   double t_start, t_stop, t_period, t_target;
   int nmax_work;
+  int nchain_restart;    // thermostat state read from a restart file, handed to the library at the next init()
+  double *chain_restart;
   int *ingroup;          // work: 1 where mask & groupbit
   double *massone;       // work: per-atom mass
 

@@ -31,6 +31,7 @@ ABI_SYMBOLS = [
     "polb200_rigid_create", "polb200_rigid_destroy", "polb200_rigid_last_error", "polb200_rigid_init",
     "polb200_rigid_dof", "polb200_rigid_setup", "polb200_rigid_initial_integrate", "polb200_rigid_final_integrate",
     "polb200_rigid_pre_neighbor", "polb200_rigid_virial", "polb200_rigid_scalar", "polb200_rigid_reset_dt",
+    "polb200_rigid_get_chain", "polb200_rigid_set_chain",
     "polb200_rigid_fetch", "polb200_rigid_launch_count", "polb200_rigid_last_ms",
 ]
 
@@ -163,6 +164,8 @@ def lib():
         L.polb200_rigid_virial.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.polb200_rigid_scalar.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.polb200_rigid_reset_dt.argtypes = [C.c_void_p, C.c_double]
+        L.polb200_rigid_get_chain.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        L.polb200_rigid_set_chain.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.polb200_rigid_fetch.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_long]
         L.polb200_rigid_fetch.restype = C.c_long
         L.polb200_rigid_launch_count.argtypes = [C.c_void_p, C.c_int]
@@ -589,6 +592,17 @@ class Rigid:
 
     def reset_dt(self, dt):
         self._check(lib().polb200_rigid_reset_dt(self._h, float(dt)))
+
+    def get_chain(self):
+        """thermostat state as FixRigidNH::write_restart stores it: (t_chain, 4) = eta_t, eta_r, eta_dot_t, eta_dot_r"""
+        buf = np.zeros(4 * 64)
+        nc = C.c_int()
+        self._check(lib().polb200_rigid_get_chain(self._h, buf.ctypes.data, buf.size, C.byref(nc)))
+        return buf[:4 * nc.value].reshape(nc.value, 4).copy()
+
+    def set_chain(self, state):
+        state = np.ascontiguousarray(state, dtype=np.float64)
+        self._check(lib().polb200_rigid_set_chain(self._h, state.ctypes.data, state.shape[0]))
 
     def fetch(self, name):
         width = 4 if name in ("quat", "conjqm") else 1 if name == "masstotal" else 3

@@ -240,3 +240,36 @@ def test_config3_water_box_properties():
     assert np.abs(r1 - 0.9572).max() < 1e-11 and np.abs(r2 - 0.9572).max() < 1e-11 and np.abs(ang - 104.52).max() < 1e-9
     print(f"rigid step at {n} atoms: initial+final {R.last_ms():.3f} ms (final half), launches {R.launch_count()}")
     R.close(), R2.close()
+
+
+def test_thermostat_chain_round_trip():
+    """FixRigidNH::write_restart / restart: stop a rigid/nvt run after 3 steps, carry the chain state (and x, v) into a
+    fresh handle, continue -- same trajectory as the uninterrupted run"""
+    fx = RC.load("rigid_water_nvt")
+    nrun = float(fx["nrun"])
+    A = DeviceDriver(fx)
+    A.setup(fx["f"][0])
+    for s in range(3):
+        A.initial(fx["f"][s], (s + 1) / nrun)
+        A.final(fx["f"][s + 1])
+    chain = A.R.get_chain()
+    assert chain.shape == (50, 4) and np.abs(chain[:, 2]).max() > 0.0
+    # "restart": a new handle initialised from the stored positions / velocities / image flags + the chain
+    fx2 = dict(fx)
+    L = fx["boxhi"] - fx["boxlo"]
+    # true image flags of A's positions (A never wraps its atoms): x3 + image3 * L = A.x + img * L
+    img = fx["image"][3] - np.rint((A.x - fx["x"][3]) / L).astype(np.int64)
+    fx2["x"] = np.stack([A.x] * fx["x"].shape[0])
+    fx2["image"] = np.stack([img] * fx["x"].shape[0]).astype(np.int32)
+    fx2["v_init"] = A.v
+    B = DeviceDriver(fx2)
+    B.R.set_chain(chain)
+    B.setup(fx["f"][3])
+    for s in range(3, 6):
+        for D in (A, B):
+            D.initial(fx["f"][s], (s + 1) / nrun)
+            D.final(fx["f"][s + 1])
+        assert np.abs(RC.minimg(A.x - B.x, L)).max() < 1e-11 * L.max() and np.abs(A.v - B.v).max() < 1e-10 * np.abs(A.v).max()
+    assert np.abs(A.R.get_chain() - B.R.get_chain()).max() < 1e-10 * np.abs(chain).max()
+    assert np.abs(RC.minimg(A.x - fx["x"][6], L)).max() < 1e-11 * L.max()   # and both are still the reference's trajectory
+    A.R.close(), B.R.close()

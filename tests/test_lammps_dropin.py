@@ -101,31 +101,7 @@ def test_same_script_same_thermo(tmp_path, words, tol):
 
 # ---- fix rigid/nve|nvt on the device -------------------------------------------------------
 
-def thermo_rows(log):
-    """last thermo table of a log as (columns, float rows)"""
-    cols, rows, on = None, [], False
-    for line in log.splitlines():
-        if line.startswith("Step "):
-            cols, rows, on = line.split(), [], True
-            continue
-        if on:
-            if line.startswith("Loop time"):
-                on = False
-                continue
-            t = line.split()
-            if len(t) == len(cols):
-                try:
-                    rows.append([float(v) for v in t])
-                except ValueError:
-                    pass
-    return cols, np.array(rows)
-
-
-def run_log(binary, work, name):
-    r = subprocess.run([str(binary), "-in", "in.case", "-echo", "none", "-log", f"log.{name}"], cwd=work,
-                       capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    return thermo_rows((work / f"log.{name}").read_text())
+from lammps_cases import H2_DYNAMICS, check_against_shipped_log, h2_shipped_lines, run_log, write_h2_data  # noqa: E402
 
 
 @pytest.mark.parametrize("fix_line,scalar", [
@@ -161,47 +137,8 @@ def test_shipped_h2_example_reproduces_the_committed_log(tmp_path):
     log (polarization/examples/Bulk H2/log.lammps:92-100, 8 printed digits; tests/golden/thermo_logs.json)."""
     if not LMP_B200.exists():
         pytest.skip("lmp_b200 not built (needs the reference tree at build time)")
-    fx = H.load_fixture("h2_default_step0")
-    n = fx["x"].shape[0]
-    tag, mol, typ = fx["tag"], fx["molecule"], fx["type"]
-    L = fx["boxhi"] - fx["boxlo"]
-    # unwrap every molecule around its first atom: read_data wraps and sets the image flags fix rigid needs
-    order = np.argsort(tag)
-    x = fx["x"].copy()
-    first = {}
-    for i in order:
-        m = int(mol[i])
-        if m not in first:
-            first[m] = x[i].copy()
-        x[i] = first[m] + (x[i] - first[m]) - L * np.rint((x[i] - first[m]) / L)
-    nsp, sp = fx["nspecial"], fx["special"]
-    bonds = sorted({(min(int(tag[i]), int(sp[i, k])), max(int(tag[i]), int(sp[i, k]))) for i in range(n)
-                    for k in range(int(nsp[i, 0]))})
-    with open(tmp_path / "h2.data", "w") as fh:
-        fh.write(f"Bulk H2 from golden fixture\n\n{n} atoms\n3 atom types\n{len(bonds)} bonds\n1 bond types\n\n")
-        for d, c in enumerate("xyz"):
-            fh.write(f"{float(fx['boxlo'][d]):.17g} {float(fx['boxhi'][d]):.17g} {c}lo {c}hi\n")
-        fh.write("\nAtoms\n\n")
-        for i in order:
-            fh.write(f"{int(tag[i])} {int(mol[i])} {int(typ[i])} {float(fx['q'][i]):.17g} {x[i, 0]:.17g} {x[i, 1]:.17g} {x[i, 2]:.17g}\n")
-        fh.write("\nBonds\n\n")
-        for k, (a, b) in enumerate(bonds):
-            fh.write(f"{k + 1} 1 {a} {b}\n")
-    # the shipped input, line for line where it matters (its `timestep 2` precedes `units real`, so dt = 1 fs)
-    lines = ["timestep 2", "units real", "boundary p p p", "atom_style full", "read_data h2.data", "bond_style zero", "bond_coeff *",
-             "mass 1 0.00001", "mass 2 1.00800", "mass 3 0.00001",
-             "set type 1 static_polarizability 0.69380", "set type 2 static_polarizability 0.00044",
-             "set type 3 static_polarizability 0.00000", "kspace_style ewald 1.0e-4", str(fx["pair_style"])]
-    lines += str(fx["pair_coeff"]).splitlines()
-    lines += ["special_bonds lj/coul 0.0 0.0 0.0",
-              "thermo_style custom step etotal ke pe evdwl ecoul elong epol temp press", "thermo 1",
-              "velocity all create 298.15 12345 rot yes mom yes dist gaussian",
-              "fix rigid_nve all rigid/nve molecule", "run 7"]
-    (tmp_path / "in.case").write_text("\n".join(lines) + "\n")
+    fx = write_h2_data(tmp_path)
+    (tmp_path / "in.case").write_text("\n".join(h2_shipped_lines(fx) + H2_DYNAMICS + ["run 7"]) + "\n")
     cols, new = run_log(LMP_B200, tmp_path, "b200")
-    ref = H.thermo_logs()["h2"]
-    assert cols == ref["columns"] and new.shape[0] == len(ref["rows"]) == 8   # the committed log ends inside step 8
-    for r in range(8):
-        for c, name in enumerate(cols):
-            want = float(ref["rows"][r][name])
-            assert abs(new[r, c] - want) <= 3e-7 * max(abs(want), 1.0), (r, name, new[r, c], want)
+    assert new.shape[0] == 8
+    check_against_shipped_log(cols, new)
