@@ -243,33 +243,50 @@ def test_config3_water_box_properties():
 
 
 def test_thermostat_chain_round_trip():
-    """FixRigidNH::write_restart / restart: stop a rigid/nvt run after 3 steps, carry the chain state (and x, v) into a
-    fresh handle, continue -- same trajectory as the uninterrupted run"""
-    fx = RC.load("rigid_water_nvt")
-    nrun = float(fx["nrun"])
+    """FixRigidNH::write_restart / restart: stop a rigid/nvt run after 2 steps, carry the chain state (and x, v) into a
+    fresh handle, continue.  The restarted device run is compared with the equally restarted ORACLE run (1e-11): a
+    restart rebuilds the principal axes from the current positions, and the NO_SQUISH splitting is not invariant under
+    relabelling the axes, so neither the reference nor we continue the uninterrupted trajectory bit for bit (the
+    oracle shows 5e-5 A after one 2 fs step) -- what must hold exactly is the thermostat state and the fix's scalar."""
+    import sys
+    sys.path.insert(0, str(RC.ROOT))
+    from oracle import rigidref as RR
+    fx = RC.load("rigid_water_nvt5")
+    nrun, half = float(fx["nrun"]), 2
     A = DeviceDriver(fx)
     A.setup(fx["f"][0])
-    for s in range(3):
+    for s in range(half):
         A.initial(fx["f"][s], (s + 1) / nrun)
         A.final(fx["f"][s + 1])
     chain = A.R.get_chain()
-    assert chain.shape == (50, 4) and np.abs(chain[:, 2]).max() > 0.0
-    # "restart": a new handle initialised from the stored positions / velocities / image flags + the chain
-    fx2 = dict(fx)
+    assert chain.shape == (4, 4) and np.abs(chain[:, 2]).max() > 0.0
     L = fx["boxhi"] - fx["boxlo"]
-    # true image flags of A's positions (A never wraps its atoms): x3 + image3 * L = A.x + img * L
-    img = fx["image"][3] - np.rint((A.x - fx["x"][3]) / L).astype(np.int64)
+    # true image flags of A's positions (A never wraps its atoms): x_h + image_h * L = A.x + img * L
+    img = fx["image"][half] - np.rint((A.x - fx["x"][half]) / L).astype(np.int64)
+    fx2 = dict(fx)
     fx2["x"] = np.stack([A.x] * fx["x"].shape[0])
     fx2["image"] = np.stack([img] * fx["x"].shape[0]).astype(np.int32)
     fx2["v_init"] = A.v
     B = DeviceDriver(fx2)
     B.R.set_chain(chain)
-    B.setup(fx["f"][3])
-    for s in range(3, 6):
-        for D in (A, B):
-            D.initial(fx["f"][s], (s + 1) / nrun)
-            D.final(fx["f"][s + 1])
-        assert np.abs(RC.minimg(A.x - B.x, L)).max() < 1e-11 * L.max() and np.abs(A.v - B.v).max() < 1e-10 * np.abs(A.v).max()
-    assert np.abs(A.R.get_chain() - B.R.get_chain()).max() < 1e-10 * np.abs(chain).max()
-    assert np.abs(RC.minimg(A.x - fx["x"][6], L)).max() < 1e-11 * L.max()   # and both are still the reference's trajectory
+    assert np.array_equal(B.R.get_chain(), chain)
+    _, temp, tparam = RC.fix_args(fx)
+    O = RR.RigidRef(A.x, A.v, img, fx["mass"], fx["molecule"], RC.ingroup(fx), fx["boxlo"], fx["boxhi"], float(fx["dt"]),
+                    float(fx["ftm2v"]), float(fx["mvv2e"]), float(fx["boltz"]), temp=temp, tparam=tparam)
+    O.eta_t[:], O.eta_r[:], O.eta_dot_t[:], O.eta_dot_r[:] = chain[:, 0], chain[:, 1], chain[:, 2], chain[:, 3]
+    scalar_before = A.scalar()
+    B.setup(fx["f"][half])
+    O.setup(fx["f"][half])
+    assert abs(B.scalar() - scalar_before) < 1e-10 * abs(scalar_before)      # kinetic + chain energy carried over
+    for s in range(half, int(nrun)):
+        B.initial(fx["f"][s], (s + 1) / nrun)
+        O.initial_integrate(fx["f"][s], 1, (s + 1) / nrun)
+        B.final(fx["f"][s + 1])
+        O.final_integrate(fx["f"][s + 1])
+        assert np.abs(RC.minimg(B.x - O.x, L)).max() < 1e-11 * L.max() and np.abs(B.v - O.v).max() < 1e-10 * np.abs(O.v).max()
+    got = B.R.get_chain()
+    ref = np.stack([O.eta_t, O.eta_r, O.eta_dot_t, O.eta_dot_r], 1)
+    assert np.abs(got - ref).max() < 1e-10 * np.abs(ref).max()
+    # and the restarted run stays within the integrator's truncation error of the reference's uninterrupted trajectory
+    assert np.abs(RC.minimg(B.x - fx["x"][int(nrun)], L)).max() < 1e-3
     A.R.close(), B.R.close()
