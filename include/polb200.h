@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define POLB200_ABI_VERSION 3
+#define POLB200_ABI_VERSION 4
 
 typedef struct polb200_handle polb200_t;
 
@@ -103,6 +103,20 @@ int polb200_restart_size(const polb200_t *h, long *nbytes);
 int polb200_write_restart(const polb200_t *h, void *buf, long nbytes);
 int polb200_read_restart(polb200_t *h, const void *buf, long nbytes);
 
+/* `neigh_modify exclude ...` (src/neighbor.cpp:2276-2333): the rules of NPair::exclusion (src/npair.cpp:173-203), at most 8.
+ * The reference removes excluded pairs from the list its LJ / real-space Coulomb loop walks (pol.cpp:232-321) and from
+ * nothing else -- static field, dipole solve and dipole forces loop over all pairs -- and so does the device path.
+ *   POLB200_EXCL_TYPE       exclude type a b            (pairs of atom types a and b, either order)
+ *   POLB200_EXCL_GROUP      exclude group g1 g2         a, b = the groups' bitmasks (Group::bitmask)
+ *   POLB200_EXCL_MOL_INTRA  exclude molecule/intra g    a = bitmask; both atoms in g and in the same molecule
+ *   POLB200_EXCL_MOL_INTER  exclude molecule/inter g    a = bitmask; both atoms in g and in different molecules
+ * nrules = 0 clears them (`exclude none`).  Takes effect at the next rebuild. */
+enum { POLB200_EXCL_TYPE = 0, POLB200_EXCL_GROUP = 1, POLB200_EXCL_MOL_INTRA = 2, POLB200_EXCL_MOL_INTER = 3 };
+typedef struct {
+  int kind, a, b;
+} polb200_exclusion;
+int polb200_set_exclusions(polb200_t *h, int nrules, const polb200_exclusion *rules);
+
 /* orthogonal periodic box (Domain::boxlo/boxhi/periodicity); triclinic => POLB200_ERR_UNSUPPORTED */
 int polb200_set_box(polb200_t *h, const double boxlo[3], const double boxhi[3], const int periodic[3]);
 
@@ -127,6 +141,8 @@ typedef struct {
    * per-atom bits of eflag / vflag are set (eflag & 2, vflag & 4), ignored otherwise.  ABI version 2. */
   double *eatom;            /* [nlocal] */
   double *vatom;            /* [nlocal][6]  xx yy zz xy xz yz */
+  /* ABI version 4 */
+  const int *mask;          /* atom->mask [nlocal] (group bits); needed only by group / molecule exclusion rules, else NULL */
 } polb200_atoms;
 
 typedef struct {

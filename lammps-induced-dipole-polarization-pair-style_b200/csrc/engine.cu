@@ -98,7 +98,8 @@ struct polb200_handle {
 
   // caller-order staging (device)
   DBuf<double> c_x, c_q, c_alpha, c_mu, c_f, c_ef, c_xhold;
-  DBuf<int> c_type, c_mol, c_tag, c_nspecial, c_special;
+  DBuf<int> c_type, c_mol, c_tag, c_nspecial, c_special, c_mask, exb;
+  ExclRules excl{};  // neigh_modify exclude rules (polb200_set_exclusions)
   // pinned host staging
   HPinned<double> h_stage;
   HPinned<double> h_scal;
@@ -369,6 +370,16 @@ static void rebuild(polb200_handle *h, const polb200_atoms *at)
   LAUNCH(h, k_gather_local, cdiv(n, 256), 256, n, h->perm.p, h->c_x.p, h->c_q.p, h->c_type.p,
          at->molecule ? h->c_mol.p : nullptr, at->tag ? h->c_tag.p : nullptr, h->c_alpha.p, h->c_mu.p,
          h->xq.p, h->mua.p, h->tm.p, h->tag.p, h->invperm.p, h->flags.p + 3);
+
+  if (h->excl.n > 0) {  // group-membership bits of the exclusion rules, cell-sorted order
+    bool need_mask = false;
+    for (int r = 0; r < h->excl.n; r++) need_mask |= h->excl.kind[r] != EXCL_TYPE;
+    if (need_mask && !at->mask) throw StyleError{POLB200_ERR_ARG, "neigh_modify exclude group/molecule rules need polb200_atoms.mask"};
+    if (h->comm.active) throw StyleError{POLB200_ERR_UNSUPPORTED, "neigh_modify exclude is not supported with the multi-GPU decomposition"};
+    if (need_mask) stage_in(h, h->c_mask, at->mask, n, dev);
+    h->exb.ensure(n);
+    LAUNCH(h, k_exbits, cdiv(n, 256), 256, n, h->perm.p, need_mask ? h->c_mask.p : (const int *)nullptr, h->excl, h->exb.p);
+  }
 
   // 2. ghosts: periodic images of this box (single GPU) or the boundary shells of the neighbour bricks
   int ng = 0;
@@ -781,13 +792,23 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
     vp_ptr = h->va_pair_row.p; vq_ptr = h->va_pol_row.p;
   }
   // ---- stage 2: LJ + Coulomb (+ static field) ----
-  if (list_mode) {
-    if (evflag) LAUNCH(h, (k_pair<true, true>), nrowblocks, BLOCK, n, P, h->xq.p, h->tm.p, L, h->f_pair.p, h->ef.p, h->partial.p, ea_ptr, vp_ptr);
-    else LAUNCH(h, (k_pair<false, true>), nrowblocks, BLOCK, n, P, h->xq.p, h->tm.p, L, h->f_pair.p, h->ef.p, h->partial.p, ea_ptr, vp_ptr);
+#define PAIR_ARGS n, P, h->xq.p, h->tm.p, L, h->f_pair.p, h->ef.p, h->partial.p, ea_ptr, vp_ptr, h->excl, h->exb.p, h->g_owner.p
+  if (h->excl.n > 0) {  // neigh_modify exclude: separate instantiations, the default kernels are untouched
+    if (list_mode) {
+      if (evflag) LAUNCH(h, (k_pair<true, true, true>), nrowblocks, BLOCK, PAIR_ARGS);
+      else LAUNCH(h, (k_pair<false, true, true>), nrowblocks, BLOCK, PAIR_ARGS);
+    } else {
+      if (evflag) LAUNCH(h, (k_pair<true, false, true>), nrowblocks, BLOCK, PAIR_ARGS);
+      else LAUNCH(h, (k_pair<false, false, true>), nrowblocks, BLOCK, PAIR_ARGS);
+    }
+  } else if (list_mode) {
+    if (evflag) LAUNCH(h, (k_pair<true, true, false>), nrowblocks, BLOCK, PAIR_ARGS);
+    else LAUNCH(h, (k_pair<false, true, false>), nrowblocks, BLOCK, PAIR_ARGS);
   } else {
-    if (evflag) LAUNCH(h, (k_pair<true, false>), nrowblocks, BLOCK, n, P, h->xq.p, h->tm.p, L, h->f_pair.p, h->ef.p, h->partial.p, ea_ptr, vp_ptr);
-    else LAUNCH(h, (k_pair<false, false>), nrowblocks, BLOCK, n, P, h->xq.p, h->tm.p, L, h->f_pair.p, h->ef.p, h->partial.p, ea_ptr, vp_ptr);
+    if (evflag) LAUNCH(h, (k_pair<true, false, false>), nrowblocks, BLOCK, PAIR_ARGS);
+    else LAUNCH(h, (k_pair<false, false, false>), nrowblocks, BLOCK, PAIR_ARGS);
   }
+#undef PAIR_ARGS
   if (evflag) reduce_partials<NPAIR_PART>(h, nrowblocks, h->scal.p + S_PAIR, 0);
   if (!list_mode) LAUNCH(h, k_static_allpairs, nrowblocks, BLOCK, n, P, h->xq.p, h->tm.p, h->perm.p, h->ef.p);
   if (!st.use_previous) LAUNCH(h, k_init_mu, cdiv(n, 256), 256, n, st.polar_gamma, h->ef.p, h->mua.p);
@@ -1378,6 +1399,24 @@ int polb200_compute(polb200_t *h, const polb200_atoms *atoms, int eflag, int vfl
       throw CudaError{"polb200_compute on a configuration-only handle: a CUDA device is required (no CPU fallback)"};
     CUDA_CHECK(cudaSetDevice(h->device));
     compute_impl(h, atoms, eflag, vflag, ago, out);
+  });
+}
+
+int polb200_set_exclusions(polb200_t *h, int nrules, const polb200_exclusion *rules)
+{
+  if (!h || nrules < 0 || (nrules > 0 && !rules)) return POLB200_ERR_ARG;
+  return guarded(h, [&] {
+    if (nrules > MAX_EXCL) throw StyleError{POLB200_ERR_UNSUPPORTED, "more than 8 neigh_modify exclude rules"};
+    ExclRules X{};
+    X.n = nrules;
+    for (int r = 0; r < nrules; r++) {
+      if (rules[r].kind < EXCL_TYPE || rules[r].kind > EXCL_MOL_INTER) throw StyleError{POLB200_ERR_ARG, "Illegal neigh_modify command"};
+      X.kind[r] = rules[r].kind;
+      X.a[r] = rules[r].a;
+      X.b[r] = rules[r].b;
+    }
+    h->excl = X;
+    h->have_lists = false;  // the membership bits are rebuilt with the neighbor structures
   });
 }
 

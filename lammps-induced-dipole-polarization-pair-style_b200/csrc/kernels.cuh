@@ -455,11 +455,60 @@ k_tighten(int nloc, double reach2, const unsigned long long *__restrict__ rowsta
 // per-block partial sums: evdwl, ecoul, vxx, vyy, vzz, vxy, vxz, vyz  (each pair seen twice => 1/2)
 constexpr int NPAIR_PART = 8;
 
-template <bool EVFLAG, bool FIELD>
+// `neigh_modify exclude` (NPair::exclusion, src/npair.cpp:173-203).  The reference drops excluded pairs while it builds
+// the list its LJ/Coulomb loop walks; its polarization loops never look at that list.  Here the device list stays
+// complete (rank metric, list-mode polarization need every pair) and the LJ/Coulomb part of k_pair skips the pair.
+// Per-atom group membership is pre-digested into exb[s]: bit r = mask & rule[r].a, bit 8+r = mask & rule[r].b.
+constexpr int MAX_EXCL = 8;
+enum { EXCL_TYPE = 0, EXCL_GROUP = 1, EXCL_MOL_INTRA = 2, EXCL_MOL_INTER = 3 };
+struct ExclRules {
+  int n;
+  int kind[MAX_EXCL], a[MAX_EXCL], b[MAX_EXCL];
+};
+
+__device__ __forceinline__ bool excl_pair(const ExclRules &X, int2 tmi, int2 tmj, int ei, int ej)
+{
+  for (int r = 0; r < X.n; r++) {
+    const int ai = (ei >> r) & 1, aj = (ej >> r) & 1;
+    switch (X.kind[r]) {
+      case EXCL_TYPE:
+        if ((tmi.x == X.a[r] && tmj.x == X.b[r]) || (tmi.x == X.b[r] && tmj.x == X.a[r])) return true;
+        break;
+      case EXCL_GROUP: {
+        const int bi = (ei >> (8 + r)) & 1, bj = (ej >> (8 + r)) & 1;
+        if ((ai && bj) || (bi && aj)) return true;
+        break;
+      }
+      case EXCL_MOL_INTRA:
+        if (ai && aj && tmi.y == tmj.y) return true;
+        break;
+      default:
+        if (ai && aj && tmi.y != tmj.y) return true;
+    }
+  }
+  return false;
+}
+
+__global__ void k_exbits(int nloc, const int *__restrict__ perm, const int *__restrict__ mask, ExclRules X, int *__restrict__ exb)
+{
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nloc) return;
+  const int m = mask ? mask[perm[s]] : 0;
+  int e = 0;
+  for (int r = 0; r < X.n; r++) {
+    if (X.kind[r] == EXCL_TYPE) continue;
+    if (m & X.a[r]) e |= 1 << r;
+    if (X.kind[r] == EXCL_GROUP && (m & X.b[r])) e |= 1 << (8 + r);
+  }
+  exb[s] = e;
+}
+
+template <bool EVFLAG, bool FIELD, bool EXCL>
 __global__ void __launch_bounds__(BLOCK, 3)
 k_pair(int nloc, DevParams P, const double4 *__restrict__ xq, const int2 *__restrict__ tm, ListRows L,
        double4 *__restrict__ f_pair, double4 *__restrict__ ef, double *__restrict__ partial,
-       double *__restrict__ eatom_row, double *__restrict__ vatom_row)
+       double *__restrict__ eatom_row, double *__restrict__ vatom_row, ExclRules X, const int *__restrict__ exb,
+       const int *__restrict__ g_owner)
 {
   const int lane = threadIdx.x & 31;
   const int s = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
@@ -468,6 +517,7 @@ k_pair(int nloc, DevParams P, const double4 *__restrict__ xq, const int2 *__rest
     const double4 xi = xq[s];
     const int2 tmi = tm[s];
     const int n1 = P.pc.ntypes + 1;
+    const int exi = EXCL ? exb[s] : 0;
     double fx = 0, fy = 0, fz = 0, ex = 0, ey = 0, ez = 0;
     // neighbour entries are fetched two trips ahead so that the dependent index -> gather chain of the next
     // trip overlaps this trip's arithmetic
@@ -486,7 +536,9 @@ k_pair(int nloc, DevParams P, const double4 *__restrict__ xq, const int2 *__rest
       const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
       const double rsq = rsq_nofma(dx, dy, dz);
       const int ij = tmi.x * n1 + tmj.x;
-      if (rsq < P.lj.cutsq[ij]) {
+      bool skip = false;
+      if (EXCL) skip = excl_pair(X, tmi, tmj, exi, exb[j < nloc ? j : g_owner[j - nloc]]);
+      if (!skip && rsq < P.lj.cutsq[ij]) {
         double evdwl, ecoul;
         const double fpair = lj_coul_pair(P.pc, P.lj, P.tb, ij, rsq, xi.w, xj.w, sb, EVFLAG, evdwl, ecoul);
         fx += dx * fpair;

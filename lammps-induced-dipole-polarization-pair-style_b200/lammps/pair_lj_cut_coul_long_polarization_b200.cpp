@@ -24,6 +24,7 @@
 #include "domain.h"
 #include "error.h"
 #include "force.h"
+#include "group.h"
 #include "kspace.h"
 #include "memory.h"
 #include "neighbor.h"
@@ -49,6 +50,7 @@ PairLJCutCoulLongPolarization::PairLJCutCoulLongPolarization(LAMMPS *lmp) : Pair
   handle = NULL;
   debug = 0;
   ntypes_set = 0;
+  nexclude_sent = 0;
   epsilon_rows = sigma_rows = NULL;
   const char *dev = getenv("POLB200_DEVICE");
   device = dev ? atoi(dev) : 0;
@@ -218,6 +220,23 @@ void PairLJCutCoulLongPolarization::compute(int eflag, int vflag)
     }
   }
   a.on_device = 0;
+  // `neigh_modify exclude` (src/neighbor.cpp:2276-2333): LAMMPS' own pair list is not used, so the rules travel to the
+  // device list on every re-neighboring step (NPair::exclusion, src/npair.cpp:173-203)
+  if (neighbor->ago == 0) {
+    std::vector<polb200_exclusion> rules;
+    for (int m = 0; m < neighbor->nex_type; m++)
+      rules.push_back({POLB200_EXCL_TYPE, neighbor->ex1_type[m], neighbor->ex2_type[m]});
+    for (int m = 0; m < neighbor->nex_group; m++)
+      rules.push_back({POLB200_EXCL_GROUP, group->bitmask[neighbor->ex1_group[m]], group->bitmask[neighbor->ex2_group[m]]});
+    for (int m = 0; m < neighbor->nex_mol; m++)
+      rules.push_back({neighbor->ex_mol_intra[m] ? POLB200_EXCL_MOL_INTRA : POLB200_EXCL_MOL_INTER,
+                       group->bitmask[neighbor->ex_mol_group[m]], 0});
+    if (!rules.empty() || nexclude_sent > 0) {
+      CHECK(polb200_set_exclusions(handle, (int) rules.size(), rules.empty() ? NULL : rules.data()));
+      nexclude_sent = (int) rules.size();
+    }
+  }
+  a.mask = atom->mask;
   a.eatom = eflag_atom ? eatom : NULL;           // Pair::eatom / vatom, zeroed by ev_setup (src/pair.cpp:789-804)
   a.vatom = (vflag_atom && a.nlocal > 0) ? vatom[0] : NULL;
 

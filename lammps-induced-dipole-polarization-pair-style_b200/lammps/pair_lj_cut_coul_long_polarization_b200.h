@@ -51,6 +51,7 @@ class PairLJCutCoulLongPolarization : public Pair {
   int device;                           // CUDA ordinal, environment POLB200_DEVICE (default 0)
   int debug;                            // `debug yes`: per-step prints like the reference (:391,:635-639)
   int ntypes_set;
+  int nexclude_sent;                    // neigh_modify exclude rules last handed to the library
   double **epsilon_rows, **sigma_rows;  // row tables over the library's flat arrays, for extract()
 
   void ensure_types();

@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "polb200_extract", "polb200_single", "polb200_restart_size", "polb200_write_restart",
     "polb200_read_restart", "polb200_set_box", "polb200_compute", "polb200_comm_id_size",
     "polb200_comm_create_id", "polb200_comm_init", "polb200_subdomain", "polb200_debug_fetch",
-    "polb200_launch_count", "polb200_set_option", "polb200_decomp_plan", "polb200_tail",
+    "polb200_launch_count", "polb200_set_option", "polb200_decomp_plan", "polb200_tail", "polb200_set_exclusions",
     "polb200_ewald_create", "polb200_ewald_destroy", "polb200_ewald_last_error", "polb200_ewald_init",
     "polb200_ewald_compute", "polb200_ewald_last_ms",
     "polb200_rigid_create", "polb200_rigid_destroy", "polb200_rigid_last_error", "polb200_rigid_init",
@@ -49,7 +49,14 @@ class Atoms(C.Structure):
                 ("molecule", C.c_void_p), ("tag", C.c_void_p), ("alpha", C.c_void_p), ("mu", C.c_void_p),
                 ("ef_static", C.c_void_p), ("f", C.c_void_p), ("nspecial", C.c_void_p),
                 ("special", C.c_void_p), ("maxspecial", C.c_int), ("on_device", C.c_int),
-                ("eatom", C.c_void_p), ("vatom", C.c_void_p)]
+                ("eatom", C.c_void_p), ("vatom", C.c_void_p), ("mask", C.c_void_p)]
+
+
+class Exclusion(C.Structure):
+    _fields_ = [("kind", C.c_int), ("a", C.c_int), ("b", C.c_int)]
+
+
+EXCL_KINDS = {"type": 0, "group": 1, "molecule/intra": 2, "molecule/inter": 3}
 
 
 class Result(C.Structure):
@@ -139,6 +146,7 @@ def lib():
         L.polb200_debug_fetch.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_long]
         L.polb200_launch_count.argtypes = [C.c_void_p, C.c_int]
         L.polb200_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+        L.polb200_set_exclusions.argtypes = [C.c_void_p, C.c_int, C.POINTER(Exclusion)]
         L.polb200_comm_create_id.argtypes = [C.c_void_p]
         L.polb200_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
         L.polb200_subdomain.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -345,12 +353,20 @@ class PairStyle:
         self._check(lib().polb200_subdomain(self._h, lo, hi))
         return np.array(lo[:]), np.array(hi[:])
 
+    def set_exclusions(self, rules):
+        """`neigh_modify exclude` rules as tuples: ("type", i, j), ("group", bit1, bit2), ("molecule/intra", bit),
+        ("molecule/inter", bit); [] clears them"""
+        arr = (Exclusion * max(len(rules), 1))()
+        for k, r in enumerate(rules):
+            arr[k].kind, arr[k].a, arr[k].b = EXCL_KINDS[r[0]], int(r[1]), int(r[2]) if len(r) > 2 else 0
+        self._check(lib().polb200_set_exclusions(self._h, len(rules), arr))
+
     def set_option(self, name, value):
         self._check(lib().polb200_set_option(self._h, name.encode(), float(value)))
 
     # ---- hot path ----
     def compute(self, x, q, type_, alpha, mu, f, molecule=None, tag=None, ef_static=None, nspecial=None,
-                special=None, eflag=1, vflag=2, ago=0, eatom=None, vatom=None):
+                special=None, eflag=1, vflag=2, ago=0, eatom=None, vatom=None, mask=None):
         """One compute() call on HOST numpy buffers (mu and f updated in place).  Returns Result."""
         n = x.shape[0]
         a = Atoms()
@@ -370,6 +386,7 @@ class PairStyle:
         a.nspecial, a.special = ptr(nspecial, np.int32), ptr(special, np.int32)
         a.maxspecial = special.shape[1] if special is not None else 0
         a.eatom, a.vatom = ptr(eatom, np.float64), ptr(vatom, np.float64)
+        a.mask = ptr(mask, np.int32)
         a.on_device = 0
         res = Result()
         self._check(lib().polb200_compute(self._h, C.byref(a), eflag, vflag, ago, C.byref(res)))
@@ -380,7 +397,7 @@ class PairStyle:
         a = Atoms()
         a.nlocal = n
         for k in ("x", "q", "type", "molecule", "tag", "alpha", "mu", "ef_static", "f", "nspecial", "special", "eatom",
-                  "vatom"):
+                  "vatom", "mask"):
             setattr(a, k, ptrs.get(k))
         a.maxspecial = maxspecial
         a.on_device = 1

@@ -70,6 +70,15 @@ CASES = [
      ["compute pea all pe/atom pair", "compute sta all stress/atom NULL pair", "compute spe all reduce sum c_pea",
       "compute sst all reduce sum c_sta[1] c_sta[2] c_sta[3] c_sta[4] c_sta[5] c_sta[6]",
       "thermo_style custom step pe c_spe c_sst[1] c_sst[2] c_sst[3] c_sst[4] c_sst[5] c_sst[6]"], [0], 0),
+    # neigh_modify exclude: the pair loop only sees what the list holds; the polarization loops do not care
+    ("h2_exclude_intra", "Bulk H2", "h2.input",
+     H2_STYLE.replace("polar_gs_ranked yes", "polar_gs_ranked no fixed_iteration yes").replace(
+         "max_iterations 100", "max_iterations 5"), ["neigh_modify exclude molecule/intra all"], [0], 0),
+    ("h2_exclude_mixed", "Bulk H2", "h2.input",
+     H2_STYLE.replace("polar_gs_ranked yes", "polar_gs_ranked no fixed_iteration yes").replace(
+         "max_iterations 100", "max_iterations 5"),
+     ["group gsite type 1", "group esite type 2", "neigh_modify exclude type 1 3",
+      "neigh_modify exclude group gsite esite exclude molecule/intra esite"], [0], 0),
     ("methane_default", "MOF5+Methane", "MOF5+PCRC.restart.pdb.input", None, [], [0, 1, 2], 2),
     # shipped input aborts in fix rigid; single-point compute() with the integrator swapped
     ("co2_singlepoint", "MOF5+CO2", "co2_mof5.restart.pdb.input", None, ["__NVE__"], [0], 0),
@@ -141,6 +150,18 @@ def run_case(name, exdir, inp, style, extra, keep, nrun):
             pair_style=pair_style, pair_coeff="\n".join(pair_coeffs), pair_modify="\n".join(pair_modify),
             step=step, ncoultablebits=int(d["ncoultablebits"][0]),
         )
+        nm = [l for l in lines if l.strip().startswith("neigh_modify") and "exclude" in l]
+        if nm:  # exclusion rules + the group masks they refer to (groups of these cases are defined by type)
+            bits, mask = {"all": 1}, np.ones(nl, dtype=np.int32)
+            for l in lines:
+                w = l.split()
+                if len(w) == 4 and w[0] == "group" and w[2] == "type":
+                    bits[w[1]] = 1 << len(bits)
+                    mask[d["type"][:nl] == int(w[3])] |= bits[w[1]]
+            fx["neigh_modify"] = "\n".join(nm)
+            fx["mask"] = mask
+            fx["group_names"] = np.array(list(bits.keys()))
+            fx["group_bits"] = np.array(list(bits.values()), dtype=np.int32)
         for key, width in (("eatom", 1), ("vatom", 6)):
             if key in d:  # fold ghost tallies onto their owners (what reverse_comm of the computes does)
                 a = d[key].reshape(-1, width)

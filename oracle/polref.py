@@ -317,6 +317,67 @@ def build_half_list(sysm, style, xall, owner):
         return numneigh, first, neigh[:np_].copy()
 
 
+def parse_exclusions(text, group_bits):
+    """`neigh_modify exclude ...` lines (src/neighbor.cpp:2276-2333) -> rule tuples; group_bits maps group names to bitmasks"""
+    rules = []
+    for line in str(text).splitlines():
+        w = line.split()
+        if len(w) < 3 or w[0] != "neigh_modify":
+            continue
+        i = 1
+        while i < len(w):
+            if w[i] != "exclude":
+                raise ValueError("only neigh_modify exclude is restated: " + line)
+            kind = w[i + 1]
+            if kind == "type":
+                rules.append(("type", int(w[i + 2]), int(w[i + 3])))
+                i += 4
+            elif kind == "group":
+                rules.append(("group", group_bits[w[i + 2]], group_bits[w[i + 3]]))
+                i += 4
+            elif kind in ("molecule/intra", "molecule/inter"):
+                rules.append((kind, group_bits[w[i + 2]]))
+                i += 3
+            elif kind == "none":
+                rules = []
+                i += 2
+            else:
+                raise ValueError("Illegal neigh_modify command")
+    return rules
+
+
+def excluded_pairs(rules, itype, jtype, imask, jmask, imol, jmol):
+    """NPair::exclusion (src/npair.cpp:173-203), vectorised over pairs"""
+    ex = np.zeros(len(itype), dtype=bool)
+    for r in rules:
+        if r[0] == "type":   # ex_type is symmetric (src/neighbor.cpp:448-452)
+            ex |= ((itype == r[1]) & (jtype == r[2])) | ((itype == r[2]) & (jtype == r[1]))
+        elif r[0] == "group":
+            ex |= ((imask & r[1]) != 0) & ((jmask & r[2]) != 0)
+            ex |= ((imask & r[2]) != 0) & ((jmask & r[1]) != 0)
+        elif r[0] == "molecule/intra":
+            ex |= ((imask & r[1]) != 0) & ((jmask & r[1]) != 0) & (imol == jmol)
+        elif r[0] == "molecule/inter":
+            ex |= ((imask & r[1]) != 0) & ((jmask & r[1]) != 0) & (imol != jmol)
+    return ex
+
+
+def apply_exclusions(sysm, lists, rules, mask):
+    """Drop the excluded pairs from a half list: the reference tests `exclusion()` before the distance test while it
+    builds the list (src/npair_half_bin_newton.cpp:94), which leaves exactly this list."""
+    xall, owner, shift, numneigh, first, neigh = lists
+    n = sysm.n
+    allidx = np.concatenate([np.arange(n, dtype=np.int64), owner])
+    ii = np.repeat(np.arange(n), numneigh)
+    jj = allidx[neigh & 0x3FFFFFFF]
+    mask = np.asarray(mask)
+    ex = excluded_pairs(rules, sysm.type[ii], sysm.type[jj], mask[ii], mask[jj], sysm.molecule[ii], sysm.molecule[jj])
+    keep = ~ex
+    numneigh2 = np.bincount(ii[keep], minlength=n).astype(np.int32)
+    first2 = np.concatenate([[0], np.cumsum(numneigh2)[:-1]]).astype(np.int64)
+    return xall, owner, shift, numneigh2, first2, np.ascontiguousarray(neigh[keep])
+
+
 def compute(sysm, style, mu_in=None, eflag=1, vflag=2, use_matrix=False, trace_max=0, lists=None):
     """Full literal compute() on one configuration.  Returns dict of outputs (forces folded onto owners)."""
     L = lib()

@@ -42,6 +42,8 @@ def configure_from_fixture(style, fx, extra_words=(), **init_kw):
     style.init(g_ewald=float(fx["g_ewald"]), special_lj=tuple(fx["special_lj"]),
                special_coul=tuple(fx["special_coul"]), **init_kw)
     style.set_box(fx["boxlo"], fx["boxhi"])
+    if "neigh_modify" in fx:   # neigh_modify exclude rules of the reference run
+        style.set_exclusions(H.exclusion_rules(fx))
 
 
 def c(a, dt):
@@ -61,6 +63,8 @@ def run_fixture(style, fx, ago=0, mu_in=None, peratom=None):
             kw["eatom"] = peratom["eatom"] = np.zeros(n)
         if int(fx["vflag"]) // 4:
             kw["vatom"] = peratom["vatom"] = np.zeros((n, 6))
+    if "mask" in fx:
+        kw["mask"] = c(fx["mask"], np.int32)
     res = style.compute(c(fx["x"], np.float64), c(fx["q"], np.float64), c(fx["type"], np.int32),
                         c(fx["alpha"], np.float64), mu, f, molecule=c(fx["molecule"], np.int32),
                         tag=c(fx["tag"], np.int32), ef_static=ef,

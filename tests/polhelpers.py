@@ -159,6 +159,12 @@ def fluid_style(sysm, cut_lj=2.5, cut_coul=12.0, **kw):
     return st
 
 
+def exclusion_rules(fx):
+    """rule tuples of the fixture's `neigh_modify exclude` lines (groups by name -> bitmask)"""
+    bits = {str(k): int(v) for k, v in zip(fx["group_names"], fx["group_bits"])}
+    return P.parse_exclusions(str(fx["neigh_modify"]), bits)
+
+
 def reference_lists(fx, sysm, st, case):
     """Ghosts + half list as the reference holds them at this step: built from the positions of the
     last reneighboring (step 0 of the same run: delay 10, src/neighbor.cpp:1923-1937), ghost
@@ -167,7 +173,10 @@ def reference_lists(fx, sysm, st, case):
     if step == 0:
         xall, owner, shift = P.build_ghosts(sysm, st.cutneighmax)
         numneigh, first, neigh = P.build_half_list(sysm, st, xall, owner)
-        return xall, owner, shift, numneigh, first, neigh
+        lists = (xall, owner, shift, numneigh, first, neigh)
+        if "neigh_modify" in fx:
+            lists = P.apply_exclusions(sysm, lists, exclusion_rules(fx), fx["mask"])
+        return lists
     fx0 = load_fixture(case.rsplit("_step", 1)[0] + "_step0")
     sys0 = system_from_fixture(fx0)
     xall0, owner, shift = P.build_ghosts(sys0, st.cutneighmax)

@@ -43,7 +43,9 @@ def check_against_fixture(res, mu, ef, f, fx, mu_tol_abs=None, e_tol=TOL):
 
 
 JACOBI_CASES = ["h2_jacobi_fixed3_step0", "h2_jacobi_fixed30_step0", "h2_jacobi_precision_step0",
-                "h2_zodid_step0"]
+                "h2_zodid_step0",
+                # neigh_modify exclude molecule/intra | type + group + molecule/intra of a sub-group
+                "h2_exclude_intra_step0", "h2_exclude_mixed_step0"]
 
 
 @pytest.mark.parametrize("case", JACOBI_CASES)
@@ -442,3 +444,47 @@ def test_interleaved_colouring_matches_oracle_and_converges_like_sequential(styl
     assert res.iterations <= seq["iterations"] + 4
     assert np.abs(mu - ref["mu"]).max() < 20 * 1e-11 and np.abs(mu - seq["mu"]).max() < 100 * 1e-11
     assert abs(res.eng_pol - seq["eng_pol"]) < 1e-8 * abs(seq["eng_pol"])
+
+
+def test_exclusions_in_list_mode_match_oracle(style):
+    """neigh_modify exclude with polar_cutoff (neighbor-list polarization): LJ / Coulomb drop the excluded pairs, static
+    field, dipoles and dipole forces keep them -- type rule + group rule + molecule/intra rule on random group masks"""
+    sysm = H.lj_charge_fluid(10)                       # 4000 atoms, L = 34.2 A
+    rng = np.random.default_rng(17)
+    mask = (1 | (2 * (rng.random(sysm.n) < 0.3)) | (4 * (rng.random(sysm.n) < 0.3)) | (8 * (rng.random(sysm.n) < 0.2))).astype(np.int32)
+    rules = [("type", 1, 1), ("group", 2, 4), ("molecule/intra", 8)]
+    kw = dict(fixed_iteration=1, max_iterations=5, damp_type="exponential", polar_gs_ranked=0)
+    st = H.fluid_style(sysm, 2.5, 12.0, polar_cut=12.0, **kw)
+    ref = P.polar_rows(sysm, st)
+    st0 = H.fluid_style(sysm, 2.5, 12.0, polar_gs_ranked=0, zodid=1, polar_gamma=0.0)
+    xall, owner, shift = P.build_ghosts(sysm, st0.cutneighmax)
+    nn, first, neigh = P.build_half_list(sysm, st0, xall, owner)
+    full = P.compute(sysm, st0, lists=(xall, owner, shift, nn, first, neigh))
+    lit = P.compute(sysm, st0, lists=P.apply_exclusions(sysm, (xall, owner, shift, nn, first, neigh), rules, mask))
+    assert abs(lit["eng_coul"] - full["eng_coul"]) > 1e-3 * abs(full["eng_coul"])   # the rules bite
+    style.set_ntypes(2)
+    style.command("pair_style lj/cut/coul/long/polarization 2.5 12.0 polar_gs_ranked no fixed_iteration yes "
+                  "max_iterations 5 damp_type exponential polar_cutoff 12.0")
+    style.command("pair_coeff 1 1 0.1 3.0")
+    style.command("pair_coeff 2 2 0.1 3.0")
+    style.init(g_ewald=st.g_ewald, molecular=0)
+    style.set_box(sysm.boxlo, sysm.boxhi)
+    style.set_exclusions(rules)
+    n = sysm.n
+    mu, f, ef = np.zeros((n, 3)), np.zeros((n, 3)), np.zeros((n, 3))
+    c = np.ascontiguousarray
+    res = style.compute(c(sysm.x), c(sysm.q), c(sysm.type), c(sysm.alpha), mu, f, molecule=c(sysm.molecule), tag=c(sysm.tag),
+                        ef_static=ef, mask=mask)
+    assert not (res.status & pb.STATUS_EXACT)
+    assert H.rel_err(ef, ref["ef_static"]) < TOL and H.rel_err(mu, ref["mu"]) < TOL
+    assert abs(res.eng_pol - ref["eng_pol"]) < TOL * abs(ref["eng_pol"])
+    assert abs(res.eng_vdwl - lit["eng_vdwl"]) < TOL * abs(lit["eng_vdwl"])
+    assert abs(res.eng_coul - lit["eng_coul"]) < TOL * abs(lit["eng_coul"])
+    ftot = lit["f"] + ref["f"]
+    assert np.abs(f - ftot).max() < TOL * np.abs(ftot).max()
+    # clearing the rules restores the full interaction
+    style.set_exclusions([])
+    mu[:], f[:] = 0.0, 0.0
+    res2 = style.compute(c(sysm.x), c(sysm.q), c(sysm.type), c(sysm.alpha), mu, f, molecule=c(sysm.molecule), tag=c(sysm.tag),
+                         ef_static=ef, mask=mask)
+    assert abs(res2.eng_coul - full["eng_coul"]) < TOL * abs(full["eng_coul"])

@@ -42,7 +42,7 @@ def test_library_exports_every_declared_symbol():
     L = pb.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.polb200_abi_version() == 3
+    assert L.polb200_abi_version() == 4
 
 
 def test_compute_without_device_fails_loudly(style):

@@ -25,7 +25,7 @@ LMP_B200 = ROOT / "lammps-induced-dipole-polarization-pair-style_b200" / "lammps
 pytestmark = pytest.mark.gpu
 
 
-def write_case(work, fx, style_words, steps):
+def write_case(work, fx, style_words, steps, extra=()):
     n = fx["x"].shape[0]
     tag, mol, typ = fx["tag"], fx["molecule"], fx["type"]
     nsp, sp = fx["nspecial"], fx["special"]
@@ -52,7 +52,7 @@ def write_case(work, fx, style_words, steps):
     lines += [f"set type {t} static_polarizability {a:.17g}" for t, a in alpha_of_type.items()]
     lines += ["kspace_style ewald 1.0e-4", style_words]
     lines += str(fx["pair_coeff"]).splitlines()
-    lines += ["special_bonds lj/coul 0.0 0.0 0.0",
+    lines += ["special_bonds lj/coul 0.0 0.0 0.0"] + list(extra) + [
               "thermo_style custom step pe evdwl ecoul elong epol press",
               "thermo_modify format float %.12g", "thermo 1", "timestep 0.25", "fix 1 all nve", f"run {steps}"]
     (work / "in.case").write_text("\n".join(lines) + "\n")
@@ -80,17 +80,23 @@ def run(binary, work, name):
     return thermo_table((work / f"log.{name}").read_text()), r.stdout
 
 
-@pytest.mark.parametrize("words,tol", [
-    ("polar_gs_ranked no fixed_iteration yes max_iterations 20 damp_type exponential damp 2.1304", 1e-9),
+EXCLUDE = ("group gsite type 1", "group esite type 2", "neigh_modify exclude molecule/intra all exclude type 1 3",
+           "neigh_modify exclude group gsite esite")
+
+
+@pytest.mark.parametrize("words,tol,extra", [
+    ("polar_gs_ranked no fixed_iteration yes max_iterations 20 damp_type exponential damp 2.1304", 1e-9, ()),
     ("precision 0.00000000001 max_iterations 100 damp_type exponential damp 2.1304 polar_gs_ranked yes debug no "
-     "use_previous yes", 2e-8),
+     "use_previous yes", 2e-8, ()),
+    # neigh_modify exclude in the script: the Pair subclass forwards Neighbor's rules to the device list
+    ("polar_gs_ranked no fixed_iteration yes max_iterations 20 damp_type exponential damp 2.1304", 1e-9, EXCLUDE),
 ])
-def test_same_script_same_thermo(tmp_path, words, tol):
+def test_same_script_same_thermo(tmp_path, words, tol, extra):
     if not LMP_REF.exists() or not LMP_B200.exists():
         pytest.skip("LAMMPS binaries not built (need the reference tree at build time)")
     fx = H.load_fixture("h2_default_step0")
     style = "pair_style lj/cut/coul/long/polarization 2.5 10.797442 " + words
-    write_case(tmp_path, fx, style, steps=4)
+    write_case(tmp_path, fx, style, steps=4, extra=extra)
     ref, _ = run(LMP_REF, tmp_path, "ref")
     new, out = run(LMP_B200, tmp_path, "b200")
     assert ref.shape == new.shape and ref.shape[0] == 5
