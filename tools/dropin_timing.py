@@ -24,3 +24,19 @@ for case, words in (("h2_default_step0", "precision 0.00000000001 max_iterations
         pair = float(re.search(r"^Pair\s*\|\s*([0-9.eE+-]+)", log, flags=re.M).group(1))
         loop = float(re.search(r"Loop time of ([0-9.eE+-]+)", log).group(1))
         print(f"{case} n={fx['x'].shape[0]} {name}: Pair {pair / steps * 1e3:.2f} ms/step, loop {loop / steps * 1e3:.2f} ms/step, E_pol(last) {tab[-1][5]:.8f}")
+
+# the example AS SHIPPED (fix rigid/nve molecule, its masses and velocities): in lmp_b200 pair style, KSpace and the integrator
+# all run on the device; LAMMPS' own timing breakdown per step
+import lammps_cases as LC
+
+work = Path(tempfile.mkdtemp())
+fx = LC.write_h2_data(work)
+(work / "in.case").write_text("\n".join(LC.h2_shipped_lines(fx) + LC.H2_DYNAMICS + [f"run {steps}"]) + "\n")
+for name, binary in (("reference", T.LMP_REF), ("b200", T.LMP_B200)):
+    cols, rows = LC.run_log(binary, work, name)
+    log = (work / f"log.{name}").read_text()
+    loop = float(re.search(r"Loop time of ([0-9.eE+-]+)", log).group(1))
+    parts = {k: float(re.search(rf"^{k}\s*\|\s*([0-9.eE+-]+)", log, flags=re.M).group(1)) / steps * 1e3
+             for k in ("Pair", "Kspace", "Neigh", "Comm", "Modify")}
+    print(f"shipped h2.input ({fx['x'].shape[0]} atoms, rigid/nve molecule) {name}: loop {loop / steps * 1e3:.2f} ms/step  "
+          + "  ".join(f"{k} {v:.3f}" for k, v in parts.items()) + f"  TotEng(last) {rows[-1][cols.index('TotEng')]:.6f}")
