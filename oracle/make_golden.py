@@ -242,6 +242,8 @@ def main():
     only = sys.argv[1:]
     if only == ["ewald"]:
         return ewald_goldens()
+    if only == ["pppm"]:
+        return ewald_goldens(kstyle="pppm")
     ours = {}
     for c in CASES:
         if only and c[0] not in only:
@@ -263,14 +265,14 @@ def main():
 NKTV2P_REAL = 68568.415  # src/update.cpp:161 (units real)
 
 
-def ewald_case(name, data_text, cut_coul, accuracy, extra=()):
+def ewald_case(name, data_text, cut_coul, accuracy, extra=(), kstyle="ewald"):
     work = Path(tempfile.mkdtemp(prefix=f"polgold_{name}_"))
     (work / "sys.data").write_text(data_text)
     outs = {}
     for tag, mod in (("on", ""), ("off", "kspace_modify compute no")):
         lines = ["units real", "boundary p p p", "atom_style full", "read_data sys.data", "mass * 1.0",
                  f"pair_style lj/cut/coul/long 2.5 {cut_coul}", "pair_coeff * * 0.0 1.0",
-                 f"kspace_style ewald {accuracy}", mod, *extra,
+                 f"kspace_style {kstyle} {accuracy}", mod, *extra,
                  "thermo_style custom step elong ecoul pxx pyy pzz pxy pxz pyz vol",
                  "thermo_modify format float %.16g", f"dump d all custom 1 f_{tag}.dump id fx fy fz",
                  "dump_modify d format float %.17g sort id", "run 0"]
@@ -290,6 +292,13 @@ def ewald_case(name, data_text, cut_coul, accuracy, extra=()):
     vol = th_on["Volume"]
     press = np.array([th_on[k] - th_off[k] for k in ("Pxx", "Pyy", "Pzz", "Pxy", "Pxz", "Pyz")])
     m = re.search(r"G vector \(1/distance\) = (\S+)", log)
+    if kstyle == "pppm":
+        gr = re.search(r"grid = (\d+) (\d+) (\d+)", log)
+        so = re.search(r"stencil order = (\d+)", log)
+        shutil.rmtree(work)
+        return dict(elong=th_on["E_long"], f_kspace=f_on - f_off, virial_kspace=press * vol / NKTV2P_REAL,
+                    g_ewald_printed=float(m.group(1)), grid=np.array([int(gr.group(i)) for i in (1, 2, 3)]),
+                    order=int(so.group(1)), accuracy=accuracy, cut_coul=cut_coul)
     kv = re.search(r"KSpace vectors: actual max1d max3d = (\d+) (\d+) (\d+)", log)
     km = re.search(r"kxmax kymax kzmax\s+= (\d+) (\d+) (\d+)", log)
     shutil.rmtree(work)
@@ -298,7 +307,9 @@ def ewald_case(name, data_text, cut_coul, accuracy, extra=()):
                 kxyzmax=np.array([int(km.group(i)) for i in (1, 2, 3)]), accuracy=accuracy, cut_coul=cut_coul)
 
 
-def ewald_goldens():
+def ewald_goldens(kstyle="ewald"):
+    """kstyle = "pppm": the same three systems through `kspace_style pppm` (src/KSPACE/pppm.cpp), plus an order-4 /
+    explicit-mesh case; fixtures pppm_*.npz"""
     sys.path.insert(0, str(ROOT / "tests"))
     import polhelpers as H
 
@@ -318,6 +329,14 @@ def ewald_goldens():
     cases["ewald_methane"] = (fm["x"], fm["q"], fm["type"], fm["boxlo"], fm["boxhi"], 12.8345, 1e-6)
     fl = H.lj_charge_fluid((6, 4, 3), seed=31)  # non-cubic box, 288 atoms
     cases["ewald_brick"] = (fl.x, fl.q, fl.type, fl.boxlo, fl.boxhi, 5.0, 1e-5)
+    if kstyle == "pppm":
+        cases = {k.replace("ewald_", "pppm_"): v + ((),) for k, v in cases.items()}
+        cases["pppm_brick_order4"] = cases["pppm_brick"][:-1] + (("kspace_modify order 4 mesh 12 9 8 gewald 0.6",),)
+        for name, (x, q, typ, lo, hi, cut, acc, extra) in cases.items():
+            g = ewald_case(name, data_of(x, q, typ, lo, hi), cut, acc, extra=extra, kstyle="pppm")
+            np.savez_compressed(OUT / f"{name}.npz", x=x, q=q, boxlo=lo, boxhi=hi, kspace_modify=np.array(" ".join(extra)), **g)
+            print(f"{name}: n {len(q)} E_long {g['elong']:.12g} grid {g['grid']} order {g['order']} g {g['g_ewald_printed']}")
+        return
     for name, (x, q, typ, lo, hi, cut, acc) in cases.items():
         g = ewald_case(name, data_of(x, q, typ, lo, hi), cut, acc)
         np.savez_compressed(OUT / f"{name}.npz", x=x, q=q, boxlo=lo, boxhi=hi, **g)
