@@ -221,6 +221,42 @@ int polb200_ewald_compute(polb200_ewald_t *e, int nlocal, const double *x, const
                           int vflag, int on_device, double *energy, double virial[6]);
 double polb200_ewald_last_ms(const polb200_ewald_t *e);  /* CUDA-event time of the last compute */
 
+/* ---- KSpace: PPPM (second half) ---------------------------------------------------------
+ * Replaces class PPPM of the reference (src/KSPACE/pppm.{h,cpp}, `kspace_style pppm <accuracy>`): ik differentiation, no
+ * stagger, orthogonal fully periodic box, one GPU.  Same g_ewald and grid selection (set_grid_global :985-1135,
+ * adjust_gewald :1287-1340), same optimal influence function (compute_gf_ik :1549-1627), same order-n charge assignment
+ * (:1951-1995, :2844-2952), energy incl. self and neutralising terms, forces, virial (:622-765).  FFTs by cuFFT (loaded at
+ * run time).  Not offered: `kspace_modify diff ad`, stagger, slab, triclinic, per-atom tallies, group/group, TIP4P. */
+typedef struct polb200_pppm polb200_pppm_t;
+
+typedef struct {
+  double accuracy_relative;   /* the argument of kspace_style pppm */
+  double g_ewald;             /* > 0: kspace_modify gewald; <= 0: estimate and refine as the reference */
+  int order;                  /* kspace_modify order (2..7); <= 0: 5 */
+  int mesh[3];                /* kspace_modify mesh nx ny nz; any <= 0: choose from the accuracy */
+  double qqrd2e, two_charge_force;
+  double qsum, qsqsum;        /* KSpace::qsum_qsq */
+  long natoms;
+  double cutoff;              /* the pair style's cut_coul */
+  double boxlo[3], boxhi[3];
+  int periodic[3];
+} polb200_pppm_setup;
+
+typedef struct {
+  double g_ewald;
+  int nx, ny, nz, order;      /* what PPPM::init prints (pppm.cpp:340-365) */
+} polb200_pppm_info;
+
+int polb200_pppm_create(polb200_pppm_t **p, int device);
+void polb200_pppm_destroy(polb200_pppm_t *p);
+const char *polb200_pppm_last_error(const polb200_pppm_t *p);
+/* PPPM::init + setup (pppm.cpp:184-395, 400-495) */
+int polb200_pppm_init(polb200_pppm_t *p, const polb200_pppm_setup *in, polb200_pppm_info *info);
+/* PPPM::compute (pppm.cpp:622-765): f[nlocal][3] += KSpace forces; *energy / virial[6] as the global bits of eflag / vflag ask */
+int polb200_pppm_compute(polb200_pppm_t *p, int nlocal, const double *x, const double *q, double *f, int eflag, int vflag,
+                         int on_device, double *energy, double virial[6]);
+double polb200_pppm_last_ms(const polb200_pppm_t *p);
+
 /* ---- Rigid-body integrator -----------------------------------------------------------
  * Replaces `fix rigid/nve molecule` and `fix rigid/nvt molecule` of the reference's RIGID package, the integrator of
  * every shipped polarization example (src/RIGID/fix_rigid_nh.{h,cpp} on top of fix_rigid.{h,cpp}): bodies = molecules

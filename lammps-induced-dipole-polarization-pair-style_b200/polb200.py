@@ -28,6 +28,8 @@ ABI_SYMBOLS = [
     "polb200_launch_count", "polb200_set_option", "polb200_decomp_plan", "polb200_tail", "polb200_set_exclusions",
     "polb200_ewald_create", "polb200_ewald_destroy", "polb200_ewald_last_error", "polb200_ewald_init",
     "polb200_ewald_compute", "polb200_ewald_last_ms",
+    "polb200_pppm_create", "polb200_pppm_destroy", "polb200_pppm_last_error", "polb200_pppm_init", "polb200_pppm_compute",
+    "polb200_pppm_last_ms",
     "polb200_rigid_create", "polb200_rigid_destroy", "polb200_rigid_last_error", "polb200_rigid_init",
     "polb200_rigid_dof", "polb200_rigid_setup", "polb200_rigid_initial_integrate", "polb200_rigid_final_integrate",
     "polb200_rigid_pre_neighbor", "polb200_rigid_virial", "polb200_rigid_scalar", "polb200_rigid_reset_dt",
@@ -77,6 +79,17 @@ class EwaldSetup(C.Structure):
 class EwaldInfo(C.Structure):
     _fields_ = [("g_ewald", C.c_double), ("gsqmx", C.c_double), ("kxmax", C.c_int), ("kymax", C.c_int),
                 ("kzmax", C.c_int), ("kmax", C.c_int), ("kcount", C.c_int)]
+
+
+class PppmSetup(C.Structure):
+    _fields_ = [("accuracy_relative", C.c_double), ("g_ewald", C.c_double), ("order", C.c_int), ("mesh", C.c_int * 3),
+                ("qqrd2e", C.c_double), ("two_charge_force", C.c_double), ("qsum", C.c_double), ("qsqsum", C.c_double),
+                ("natoms", C.c_long), ("cutoff", C.c_double), ("boxlo", C.c_double * 3), ("boxhi", C.c_double * 3),
+                ("periodic", C.c_int * 3)]
+
+
+class PppmInfo(C.Structure):
+    _fields_ = [("g_ewald", C.c_double), ("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int), ("order", C.c_int)]
 
 
 class RigidParams(C.Structure):
@@ -159,6 +172,15 @@ def lib():
                                             C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.polb200_ewald_last_ms.argtypes = [C.c_void_p]
         L.polb200_ewald_last_ms.restype = C.c_double
+        L.polb200_pppm_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        L.polb200_pppm_destroy.argtypes = [C.c_void_p]
+        L.polb200_pppm_last_error.argtypes = [C.c_void_p]
+        L.polb200_pppm_last_error.restype = C.c_char_p
+        L.polb200_pppm_init.argtypes = [C.c_void_p, C.POINTER(PppmSetup), C.POINTER(PppmInfo)]
+        L.polb200_pppm_compute.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                           C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.polb200_pppm_last_ms.argtypes = [C.c_void_p]
+        L.polb200_pppm_last_ms.restype = C.c_double
         L.polb200_rigid_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
         L.polb200_rigid_destroy.argtypes = [C.c_void_p]
         L.polb200_rigid_last_error.argtypes = [C.c_void_p]
@@ -475,6 +497,68 @@ class Ewald:
 
     def last_ms(self):
         return lib().polb200_ewald_last_ms(self._h)
+
+
+class PPPM:
+    """`kspace_style pppm <accuracy>` on one GPU: the device counterpart of the reference's class PPPM
+    (src/KSPACE/pppm.cpp).  init() = PPPM::init + setup, compute() = PPPM::compute."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        rc = lib().polb200_pppm_create(C.byref(self._h), device)
+        if rc != OK:
+            raise Polb200Error(rc, "polb200_pppm_create failed (no CUDA device? there is no CPU fallback)")
+
+    def close(self):
+        if self._h:
+            lib().polb200_pppm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != OK:
+            raise Polb200Error(rc, lib().polb200_pppm_last_error(self._h).decode())
+
+    def init(self, accuracy, q, cutoff, boxlo, boxhi, g_ewald=0.0, order=0, mesh=(0, 0, 0), qqrd2e=REAL_QQRD2E,
+             two_charge_force=REAL_QQRD2E, periodic=(1, 1, 1), natoms=None):
+        q = np.asarray(q, dtype=np.float64)
+        s = PppmSetup()
+        s.accuracy_relative, s.g_ewald, s.order = accuracy, g_ewald, order
+        s.mesh = (C.c_int * 3)(*[int(v) for v in mesh])
+        s.qqrd2e, s.two_charge_force = qqrd2e, two_charge_force
+        s.qsum, s.qsqsum = float(np.cumsum(q)[-1]) if len(q) else 0.0, float(np.cumsum(q * q)[-1]) if len(q) else 0.0
+        s.natoms = len(q) if natoms is None else natoms
+        s.cutoff = cutoff
+        s.boxlo = (C.c_double * 3)(*[float(v) for v in boxlo])
+        s.boxhi = (C.c_double * 3)(*[float(v) for v in boxhi])
+        s.periodic = (C.c_int * 3)(*[int(v) for v in periodic])
+        info = PppmInfo()
+        self._check(lib().polb200_pppm_init(self._h, C.byref(s), C.byref(info)))
+        return info
+
+    def compute(self, x, q, f, eflag=1, vflag=1):
+        """f (n,3) += KSpace forces; returns (energy, virial[6]).  Host numpy buffers."""
+        for a in (x, q, f):
+            assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+        e = C.c_double()
+        v = (C.c_double * 6)()
+        self._check(lib().polb200_pppm_compute(self._h, x.shape[0], x.ctypes.data, q.ctypes.data, f.ctypes.data, eflag, vflag, 0,
+                                               C.byref(e), v))
+        return e.value, np.array(v[:])
+
+    def compute_device(self, n, x_ptr, q_ptr, f_ptr, eflag=1, vflag=1):
+        e = C.c_double()
+        v = (C.c_double * 6)()
+        self._check(lib().polb200_pppm_compute(self._h, n, x_ptr, q_ptr, f_ptr, eflag, vflag, 1, C.byref(e), v))
+        return e.value, np.array(v[:])
+
+    def last_ms(self):
+        return lib().polb200_pppm_last_ms(self._h)
 
 
 # real units (src/update.cpp:150-170)

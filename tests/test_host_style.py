@@ -219,3 +219,5 @@ def test_device_entry_points_fail_loudly_without_a_gpu():
         pb.Ewald(device=0)
     with pytest.raises(pb.Polb200Error):
         pb.Rigid(device=0)
+    with pytest.raises(pb.Polb200Error):
+        pb.PPPM(device=0)

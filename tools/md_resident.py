@@ -10,7 +10,7 @@ kspace_style ewald 1e-4.  Prints one JSON line: ms per step by stage (CUDA event
 loop through HOST buffers (what a LAMMPS Fix/Pair/KSpace triple pays) for comparison, and the conserved energy
 KE_trans + KE_rot + E_vdwl + E_coul + E_long + E_pol over the run (an NVE trajectory must hold it).
 
-usage: md_resident.py [nside=44] [steps=40] [dt=1.0] [--host-too]
+usage: md_resident.py [nside=44] [steps=40] [dt=1.0] [--host-too] [--pppm]
 """
 import json
 import sys
@@ -68,14 +68,15 @@ def make_pair(s, g_ewald):
     return p
 
 
-def run(nside, steps, dt, resident, budget_s=150.0):
+def run(nside, steps, dt, resident, budget_s=150.0, kspace="ewald"):
     t_start = time.time()
     s, image, mass, v0 = build(nside)
     n = s.n
     L = s.boxhi - s.boxlo
     nspecial, special = water_topology(n)
-    ew = pb.Ewald(device=0)
-    g = ew.init(1e-4, s.q, CUT, s.boxlo, s.boxhi).g_ewald
+    ew = pb.PPPM(device=0) if kspace == "pppm" else pb.Ewald(device=0)   # same interface: init -> g_ewald, compute(_device)
+    kinfo = ew.init(1e-4, s.q, CUT, s.boxlo, s.boxhi)
+    g = kinfo.g_ewald
     pair = make_pair(s, g)
     rig = pb.Rigid(device=0)
     info = rig.init(s.tag, s.molecule, mass, image, s.x, v0, s.boxlo, s.boxhi, dt)
@@ -168,7 +169,8 @@ def run(nside, steps, dt, resident, budget_s=150.0):
         if k % 10 == 0:
             print(f"step {k}: etotal {rows[-1]['etotal']:.6f} ke {rows[-1]['ke']:.4f} it {rows[-1]['iterations']} "
                   f"wall {stage['wall'][-1]:.1f} ms", file=sys.stderr, flush=True)
-    out = dict(resident=resident, atoms=n, bodies=info.nbody, steps=steps, dt_fs=dt, rebuild_every=REBUILD,
+    out = dict(resident=resident, kspace=kspace + (f" grid {kinfo.nx}x{kinfo.ny}x{kinfo.nz} order {kinfo.order}" if kspace == "pppm"
+                                                   else f" kcount {kinfo.kcount}"), atoms=n, bodies=info.nbody, steps=steps, dt_fs=dt, rebuild_every=REBUILD,
                ms_per_step={k: float(np.mean(v[2:])) for k, v in stage.items()},
                ms_per_step_no_rebuild={k: float(np.mean([t for i, t in enumerate(v, start=1) if i % REBUILD])) for k, v in stage.items()},
                atom_steps_per_s=n / (float(np.mean(stage["wall"][2:])) * 1e-3),
@@ -185,11 +187,12 @@ def main():
     nside = int(args[0]) if len(args) > 0 else 44
     steps = int(args[1]) if len(args) > 1 else 40
     dt = float(args[2]) if len(args) > 2 else 1.0
-    res = run(nside, steps, dt, resident=True)
+    kspace = "pppm" if "--pppm" in sys.argv else "ewald"
+    res = run(nside, steps, dt, resident=True, kspace=kspace)
     line = dict(what="md_resident", workload=f"rigid polarizable water box, {res['atoms']} atoms, rigid/nve + polarization pair "
-                f"style (precision 1e-11 GS-ranked) + ewald 1e-4, all device-resident through the C ABI", resident=res)
+                f"style (precision 1e-11 GS-ranked) + {kspace} 1e-4, all device-resident through the C ABI", resident=res)
     if "--host-too" in sys.argv:
-        line["host_buffers"] = run(nside, max(12, steps // 3), dt, resident=False)
+        line["host_buffers"] = run(nside, max(12, steps // 3), dt, resident=False, kspace=kspace)
     print(json.dumps(line))
 
 
