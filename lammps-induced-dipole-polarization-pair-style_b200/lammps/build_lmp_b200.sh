@@ -2,7 +2,7 @@
 # Build a LAMMPS binary in which the reference's pair style is REPLACED by the B200 drop-in:
 #   lammps/_build/lmp_b200  =  reference host framework (LAMMPS 16Mar2018, from a scratch copy of
 #   $POLB200_REFERENCE/src, repaired exactly like the oracle build: oracle/build_ref.sh steps 1-3 without the
-#   dump hooks)  +  pair_lj_cut_coul_long_polarization_b200.{h,cpp}  +  ewald_b200.{h,cpp}  +
+#   dump hooks)  +  pair_lj_cut_coul_long_polarization_b200.{h,cpp}  +  ewald_b200.{h,cpp}  +  pppm_b200.{h,cpp}  +
 #   fix_rigid_nh_b200.{h,cpp}  +  atom_vec_full_polar_b200.{h,cpp}  +  compute_polarization_atom_b200.{h,cpp}  +  libpolb200.so.
 #   (the oracle's 12-line AtomVecFull patch is NOT used here: the committed atom style replaces it)
 # An unchanged input script (polarization/examples/*) then drives the CUDA path.  Nothing of the reference is
@@ -26,6 +26,7 @@ if [ -x "$OUT/lmp_b200" ] && [ "$OUT/lmp_b200" -nt "$HERE/pair_lj_cut_coul_long_
    && [ "$OUT/lmp_b200" -nt "$HERE/ewald_b200.cpp" ] && [ "$OUT/lmp_b200" -nt "$HERE/ewald_b200.h" ] \
    && [ "$OUT/lmp_b200" -nt "$HERE/atom_vec_full_polar_b200.cpp" ] && [ "$OUT/lmp_b200" -nt "$HERE/atom_vec_full_polar_b200.h" ] \
    && [ "$OUT/lmp_b200" -nt "$HERE/compute_polarization_atom_b200.cpp" ] && [ "$OUT/lmp_b200" -nt "$HERE/compute_polarization_atom_b200.h" ] \
+   && [ "$OUT/lmp_b200" -nt "$HERE/pppm_b200.cpp" ] && [ "$OUT/lmp_b200" -nt "$HERE/pppm_b200.h" ] \
    && [ "$OUT/lmp_b200" -nt "$HERE/fix_rigid_nh_b200.cpp" ] && [ "$OUT/lmp_b200" -nt "$HERE/fix_rigid_nh_b200.h" ] \
    && [ "$OUT/lmp_b200" -nt "$ROOT/include/polb200.h" ] && [ -z "${POLB200_LMP_REBUILD:-}" ]; then
   echo "build_lmp_b200: $OUT/lmp_b200 is up to date"
@@ -60,6 +61,9 @@ cp "$HERE/pair_lj_cut_coul_long_polarization_b200.cpp" pair_lj_cut_coul_long_pol
 # ... and so does the KSpace style every input of the pair style uses
 cp "$HERE/ewald_b200.h" ewald.h
 cp "$HERE/ewald_b200.cpp" ewald.cpp
+cp "$HERE/pppm_b200.h" pppm.h
+cp "$HERE/pppm_b200.cpp" pppm.cpp
+rm -f pppm_cg.* pppm_stagger.* pppm_tip4p.*     # derived from the reference's class PPPM
 # ... and the integrator of every shipped example, fix rigid/nve|nvt: one class under both style names
 cp "$HERE/fix_rigid_nh_b200.h" fix_rigid_nve.h
 cp "$HERE/fix_rigid_nh_b200.cpp" fix_rigid_nve.cpp

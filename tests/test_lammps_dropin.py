@@ -110,11 +110,14 @@ def test_same_script_same_thermo(tmp_path, words, tol, extra):
 from lammps_cases import H2_DYNAMICS, check_against_shipped_log, h2_shipped_lines, run_log, write_h2_data  # noqa: E402
 
 
-@pytest.mark.parametrize("fix_line,scalar", [
-    ("fix rig all rigid/nve molecule", False),
-    ("fix rig all rigid/nvt molecule temp 298.15 250.0 100.0 tparam 50 1 3", True),
+@pytest.mark.parametrize("fix_line,scalar,kspace", [
+    ("fix rig all rigid/nve molecule", False, "ewald 1.0e-5"),
+    ("fix rig all rigid/nvt molecule temp 298.15 250.0 100.0 tparam 50 1 3", True, "ewald 1.0e-5"),
+    # kspace_style pppm (+ kspace_modify) on the device: polb200_pppm_* behind lammps/pppm_b200.{h,cpp}
+    ("fix rig all rigid/nve molecule", False, "pppm 1.0e-5"),
+    ("fix rig all rigid/nve molecule", False, "pppm 1.0e-4\nkspace_modify order 4 mesh 16 15 18 gewald 0.45"),
 ])
-def test_rigid_fix_same_script_same_thermo(tmp_path, fix_line, scalar):
+def test_rigid_fix_same_script_same_thermo(tmp_path, fix_line, scalar, kspace):
     """a rigid water box under the stock lj/cut/coul/long pair style: in lmp_b200 the fix (and Ewald) run on the GPU,
     in the reference binary on the host; temperature, energies, pressure and the fix's scalar agree step by step"""
     if not LMP_REF.exists() or not LMP_B200.exists():
@@ -125,8 +128,9 @@ def test_rigid_fix_same_script_same_thermo(tmp_path, fix_line, scalar):
     spec.loader.exec_module(mg)
     data, _ = mg.water_data(4)
     (tmp_path / "water.data").write_text(data)
-    text = mg.water_input(fix_line, 8, 1.0)
-    th = "thermo_style custom step temp ke pe press" + (" f_rig" if scalar else "")
+    text = mg.water_input(fix_line, 8, 1.0).replace("kspace_style ewald 1.0e-5", "kspace_style " + kspace)
+    assert "kspace_style " + kspace in text
+    th = "thermo_style custom step temp ke pe elong press" + (" f_rig" if scalar else "")
     text += "\n".join([th, "thermo_modify format float %.14g", "thermo 1", "run 8"]) + "\n"
     (tmp_path / "in.case").write_text(text)
     cols_r, ref = run_log(LMP_REF, tmp_path, "ref")
