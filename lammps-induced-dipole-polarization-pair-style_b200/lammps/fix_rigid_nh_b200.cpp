@@ -284,8 +284,9 @@ void FixRigidNHB200::write_restart(FILE *fp)
   int n = 0, nc = 0;
   list[n++] = tstat_flag;
   list[n++] = t_chain;
-  if (polb200_rigid_get_chain(handle, list+n, 4*t_chain, &nc) != POLB200_OK) fail();
-  if (nc != t_chain) for (int i = 0; i < 4*t_chain; i++) list[n+i] = 0.0;   // before the first init: chains at rest
+  if (!setupflag) nc = -1;                                                  // before the first init: chains at rest
+  else if (polb200_rigid_get_chain(handle, list+n, 4*t_chain, &nc) != POLB200_OK) fail();
+  if (nc != t_chain) for (int i = 0; i < 4*t_chain; i++) list[n+i] = 0.0;
   n += 4*t_chain;
   list[n++] = 0;
   if (comm->me == 0) {
