@@ -569,7 +569,6 @@ struct polb200_rigid {
   DBuf<AtomRec> arec;
   DBuf<double2> akin;
   DBuf<double> vpart, virial, c_x, c_v, c_f, sums;
-  HPinned<double> h_buf;
 };
 
 namespace polb200 {
@@ -660,7 +659,7 @@ static void stage_out(polb200_rigid *r, const polb200_rigid_atoms *a, bool x_wri
   cudaEventElapsedTime(&r->ms_last, r->ev[0], r->ev[1]);
 }
 
-static void check_tags(polb200_rigid *r, int n)
+static void check_atom_count(polb200_rigid *r, int n)
 {
   if (n < r->natoms_body)
     throw StyleError{POLB200_ERR_ARG, "polb200_rigid: fewer atoms than the rigid bodies hold (atoms of a body must stay on this process)"};
@@ -729,7 +728,7 @@ void polb200_rigid_destroy(polb200_rigid_t *r)
   r->frame.release(); r->dyn.release(); r->chain.release(); r->abody.release(); r->xcmimage.release();
   r->member_first.release(); r->member_tag.release(); r->idx_of_tag.release(); r->imagebody.release();
   r->c_tag.release(); r->c_image.release(); r->arec.release(); r->akin.release(); r->vpart.release();
-  r->virial.release(); r->c_x.release(); r->c_v.release(); r->c_f.release(); r->sums.release(); r->h_buf.release();
+  r->virial.release(); r->c_x.release(); r->c_v.release(); r->c_f.release(); r->sums.release();
   cudaEventDestroy(r->ev[0]); cudaEventDestroy(r->ev[1]);
   cudaStreamDestroy(r->stream);
   delete r;
@@ -858,7 +857,6 @@ int polb200_rigid_init(polb200_rigid_t *r, const polb200_rigid_params *p, int nl
       s[0] += m * (dy * dy + dz * dz); s[1] += m * (dx * dx + dz * dz); s[2] += m * (dx * dx + dy * dy);
       s[3] -= m * dy * dz; s[4] -= m * dx * dz; s[5] -= m * dx * dy;
     }
-    int nlinear = 0;
     std::vector<char> linear(nbody, 0);
     for (int b = 0; b < nbody; b++) {
       const double *s = &sum[(size_t)6 * b];
@@ -874,7 +872,7 @@ int polb200_rigid_init(polb200_rigid_t *r, const polb200_rigid_params *p, int nl
       if (cr[0] * F.ez[0] + cr[1] * F.ez[1] + cr[2] * F.ez[2] < 0.0)
         for (int k = 0; k < 3; k++) F.ez[k] = -F.ez[k];
       exyz_to_q(F.ex, F.ey, F.ez, D.quat);
-      if (D.inertia[0] == 0.0 || D.inertia[1] == 0.0 || D.inertia[2] == 0.0) { linear[b] = 1; nlinear++; }
+      if (D.inertia[0] == 0.0 || D.inertia[1] == 0.0 || D.inertia[2] == 0.0) linear[b] = 1;
     }
     std::vector<AtomRec> arec_local(n);
     std::fill(sum.begin(), sum.end(), 0.0);
@@ -960,7 +958,6 @@ int polb200_rigid_init(polb200_rigid_t *r, const polb200_rigid_params *p, int nl
     r->h_abody = abody_t;
     r->h_nrigid = nrigid;
     r->h_linear = linear;
-    (void)nlinear;
 
     auto up = [&](auto &dbuf, const auto &vec) {
       dbuf.ensure(vec.size());
@@ -1023,7 +1020,7 @@ int polb200_rigid_setup(polb200_rigid_t *r, const polb200_rigid_atoms *a, int vf
     if (!r->ready) throw StyleError{POLB200_ERR_STATE, "polb200_rigid_init has not been called"};
     CUDA_CHECK(cudaSetDevice(r->device));
     const int n = a->nlocal;
-    check_tags(r, n);
+    check_atom_count(r, n);
     CUDA_CHECK(cudaEventRecord(r->ev[0], r->stream));
     StepArrays s = stage_in(r, a, true, true);
     launch_bodies<MODE_SETUP>(r, s, n);
@@ -1045,7 +1042,7 @@ int polb200_rigid_initial_integrate(polb200_rigid_t *r, const polb200_rigid_atom
     if (!r->setup_done) throw StyleError{POLB200_ERR_STATE, "polb200_rigid_setup has not been called"};
     CUDA_CHECK(cudaSetDevice(r->device));
     const int n = a->nlocal;
-    check_tags(r, n);
+    check_atom_count(r, n);
     CUDA_CHECK(cudaEventRecord(r->ev[0], r->stream));
     r->evflag = vflag ? 1 : 0;
     StepArrays s = stage_in(r, a, true, r->evflag != 0);
@@ -1068,7 +1065,7 @@ int polb200_rigid_final_integrate(polb200_rigid_t *r, const polb200_rigid_atoms 
     if (!r->setup_done) throw StyleError{POLB200_ERR_STATE, "polb200_rigid_setup has not been called"};
     CUDA_CHECK(cudaSetDevice(r->device));
     const int n = a->nlocal;
-    check_tags(r, n);
+    check_atom_count(r, n);
     CUDA_CHECK(cudaEventRecord(r->ev[0], r->stream));
     StepArrays s = stage_in(r, a, true, true);
     launch_bodies<MODE_FINAL>(r, s, n);
