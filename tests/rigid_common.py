@@ -95,3 +95,28 @@ def check_trajectory(fx, D, tol_x, tol_v, tol_vir):
         D.final(fx["f"][n + 1])
         assert np.abs(D.v - fx["v"][n + 1]).max() < tol_v * vscale, n
         check_scalars(n + 1)
+
+
+CO2_MASS = {1: 65.39, 2: 15.999, 3: 15.999, 4: 1.0079, 5: 12.011, 6: 12.011, 7: 12.011, 8: 12.01, 9: 16.0, 10: 0.000001}
+
+
+def shipped_co2_system():
+    """the reference's MOF5+CO2 example (polarization/examples/MOF5+CO2, masses of its input script) from the golden
+    fixture co2_singlepoint_step0: positions, per-atom masses, molecule ids, image flags that make every molecule whole,
+    and the rigid group `molecule > 1` of the script.  The reference aborts on this input with
+    "Fix rigid: Bad principal moments" (fix_rigid.cpp:2099): the CO2 model's two 1e-6 amu off-axis sites leave a smallest
+    principal moment of 2.4e-6, which is zeroed (< 1e-7 of the largest) and then fails the 1e-6 consistency check."""
+    import polhelpers as H
+    fx = H.load_fixture("co2_singlepoint_step0")
+    x, mol, tag = fx["x"], fx["molecule"], fx["tag"]
+    L = fx["boxhi"] - fx["boxlo"]
+    mass = np.array([CO2_MASS[int(t)] for t in fx["type"]])
+    image = np.zeros((len(tag), 3), dtype=np.int64)
+    first = {}
+    for i in np.argsort(tag):
+        m = int(mol[i])
+        if m not in first:
+            first[m] = x[i]
+        image[i] = -np.rint((x[i] - first[m]) / L).astype(np.int64)
+    return dict(x=np.ascontiguousarray(x), tag=np.ascontiguousarray(tag, dtype=np.int32), molecule=np.ascontiguousarray(mol, dtype=np.int32),
+                mass=mass, image=image, ingroup=mol > 1, boxlo=fx["boxlo"], boxhi=fx["boxhi"])

@@ -290,3 +290,15 @@ def test_thermostat_chain_round_trip():
     # and the restarted run stays within the integrator's truncation error of the reference's uninterrupted trajectory
     assert np.abs(RC.minimg(B.x - fx["x"][int(nrun)], L)).max() < 1e-3
     A.R.close(), B.R.close()
+
+
+def test_shipped_co2_example_aborts_like_the_reference():
+    """error-behaviour parity: the reference stops on its MOF5+CO2 example with "Fix rigid: Bad principal moments"
+    (fix_rigid.cpp:2099); polb200_rigid_init returns the same message"""
+    s = RC.shipped_co2_system()
+    R = pb.Rigid(device=0)
+    with pytest.raises(pb.Polb200Error, match="Fix rigid: Bad principal moments") as e:
+        R.init(s["tag"], s["molecule"], s["mass"], s["image"], s["x"], np.zeros_like(s["x"]), s["boxlo"], s["boxhi"], 1.0,
+               ingroup=s["ingroup"].astype(np.int32))
+    assert e.value.code == pb.ERR_ARG
+    R.close()

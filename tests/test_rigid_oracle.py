@@ -56,3 +56,15 @@ def test_wrapping_atoms_and_pre_neighbor_do_not_change_the_trajectory():
         for R in (A, B):
             R.final_integrate(fx["f"][n + 1])
         assert np.abs(A.v - B.v).max() < 1e-12 * np.abs(A.v).max()
+
+
+def test_shipped_co2_example_aborts_like_the_reference():
+    """MOF5+CO2 as shipped stops in the reference with "Fix rigid: Bad principal moments" (SURVEY §4); the restated
+    setup_bodies_static reaches the same verdict"""
+    import sys
+    sys.path.insert(0, str(RC.ROOT))
+    from oracle import rigidref as RR
+    s = RC.shipped_co2_system()
+    with pytest.raises(RuntimeError, match="Fix rigid: Bad principal moments"):
+        RR.RigidRef(s["x"], np.zeros_like(s["x"]), s["image"], s["mass"], s["molecule"], s["ingroup"], s["boxlo"], s["boxhi"],
+                    1.0, 1.0, 1.0, 1.0)
