@@ -302,3 +302,28 @@ def test_shipped_co2_example_aborts_like_the_reference():
                ingroup=s["ingroup"].astype(np.int32))
     assert e.value.code == pb.ERR_ARG
     R.close()
+
+
+def test_reneighboring_every_step_with_the_reference_image_flags():
+    """the device integrator driven exactly as LAMMPS drives its fix through a hot 50-step reference run that
+    re-neighbors on every step (21 face crossings): wrap as Domain::pbc, the true image flags must equal the dumped
+    ones, the wrapped coordinates the dumped coordinates, pre_neighbor gets the flags"""
+    fx = RC.load("rigid_water_nve_wrap")
+    D = DeviceDriver(fx)
+    lo, hi = fx["boxlo"], fx["boxhi"]
+    L = hi - lo
+    image = fx["image"][0].astype(np.int64).copy()
+    D.setup(fx["f"][0])
+    vs = np.abs(fx["v"][0]).max()
+    assert np.abs(D.v - fx["v"][0]).max() < 1e-10 * vs
+    for n in range(fx["x"].shape[0] - 1):
+        D.initial(fx["f"][n], 0.0)
+        below, above = D._x < lo, D._x >= hi
+        D._x = np.ascontiguousarray(np.where(below, D._x + L, np.where(above, D._x - L, D._x)))
+        image = image - below.astype(np.int64) + above.astype(np.int64)
+        assert np.array_equal(image, fx["image"][n + 1]), n
+        assert np.abs(D.x - fx["x"][n + 1]).max() < 1e-10 * L.max(), n
+        D.R.pre_neighbor(D.tag, image)
+        D.final(fx["f"][n + 1])
+        assert np.abs(D.v - fx["v"][n + 1]).max() < 1e-9 * vs, n
+    D.R.close()

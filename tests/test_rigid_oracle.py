@@ -68,3 +68,29 @@ def test_shipped_co2_example_aborts_like_the_reference():
     with pytest.raises(RuntimeError, match="Fix rigid: Bad principal moments"):
         RR.RigidRef(s["x"], np.zeros_like(s["x"]), s["image"], s["mass"], s["molecule"], s["ingroup"], s["boxlo"], s["boxhi"],
                     1.0, 1.0, 1.0, 1.0)
+
+
+def test_reneighboring_every_step_with_the_reference_image_flags():
+    """A hot 50-step reference run that re-neighbors on every step (21 face crossings): after each initial_integrate
+    the atoms are wrapped the way Domain::pbc does it, the resulting TRUE image flags must equal the reference's dump,
+    the wrapped coordinates must equal the dumped ones (not just modulo the box), and pre_neighbor gets the flags --
+    the bookkeeping of xcmimage / imagebody exactly as LAMMPS drives it."""
+    fx = RC.load("rigid_water_nve_wrap")
+    assert int((np.abs(np.diff(fx["image"], axis=0)) > 0).any(axis=2).sum()) >= 10
+    R = RC.make_oracle(fx)
+    lo, hi = fx["boxlo"], fx["boxhi"]
+    L = hi - lo
+    image = fx["image"][0].astype(np.int64).copy()
+    R.setup(fx["f"][0])
+    assert np.abs(R.v - fx["v"][0]).max() < 1e-10 * np.abs(fx["v"][0]).max()
+    for n in range(fx["x"].shape[0] - 1):
+        R.initial_integrate(fx["f"][n])
+        # Domain::pbc (domain.cpp:520-600): one period per call is all a step can need
+        below, above = R.x < lo, R.x >= hi
+        R.x = np.where(below, R.x + L, np.where(above, R.x - L, R.x))
+        image = image - below.astype(np.int64) + above.astype(np.int64)
+        assert np.array_equal(image, fx["image"][n + 1]), n
+        assert np.abs(R.x - fx["x"][n + 1]).max() < 1e-11 * L.max(), n
+        R.pre_neighbor(image)
+        R.final_integrate(fx["f"][n + 1])
+        assert np.abs(R.v - fx["v"][n + 1]).max() < 1e-10 * np.abs(fx["v"][0]).max(), n
