@@ -355,7 +355,7 @@ static void comm_signal_wait(polb200_handle *h, double *change_inout)
 {
   CommState &c = h->comm;
   c.epoch++;
-  LAUNCH(h, k_signal_wait, 1, 32, c.rank, c.nranks, c.epoch, c.push, change_inout, c.barrier_timeout_ns, h->flags.p + 6);
+  LAUNCH(h, k_signal_wait, 1, 32, c.rank, c.nranks, c.epoch, c.push, change_inout, c.barrier_timeout_ns, h->flags.p + 6, h->scf_stop);
 }
 
 // ghost refresh: positions (shifted) and/or one dipole array (mua or mub).
@@ -370,7 +370,7 @@ static void comm_refresh(polb200_handle *h, bool pos, double4 *mu, bool fence_be
   if (h->push_ready && c.push.enabled && (mu == nullptr || mu == h->mua.p || mu == h->mub.p)) {
     if (fence_before) comm_signal_wait(h, nullptr);
     if (pos && ns) LAUNCH(h, k_push_pos, cdiv(ns, 256), 256, ns, c.send_owner_u.p, c.dir_of_u.p, c.geom, h->xq.p, c.push_ptrx.p);
-    if (mu && ns) LAUNCH(h, k_push_rec, cdiv(ns, 256), 256, ns, c.send_owner_u.p, mu, mu == h->mub.p ? h->push_ptr1.p : h->push_ptr0.p);
+    if (mu && ns) LAUNCH(h, k_push_rec, cdiv(ns, 256), 256, ns, c.send_owner_u.p, mu, mu == h->mub.p ? h->push_ptr1.p : h->push_ptr0.p, h->scf_stop);
     comm_signal_wait(h, nullptr);
     return;
   }

@@ -128,6 +128,21 @@ struct polb200_handle {
   int ngroups = 0;
   unsigned long long gpairs = 0;
   bool groups_built = false, group_cache_valid = false;
+  // group-coloured Gauss-Seidel sweep (list mode polar_gs / polar_gs_ranked): colouring of the pair groups
+  DBuf<int> gof, gadj, gadjn, gcolour, glist, cstart_dev, col_export;
+  DBuf<float> gmetric;
+  int ncolours = 8;              // colours = chunks of one sweep
+  double gs_strong_m = 6.0;      // groups closer than the radius that holds this many atoms on average get different colours
+  int chunk_beg[33] = {};
+  int colour_rounds = 0;
+  bool colours_valid = false;
+  // device-side convergence test: ctl = {stop, iterations, diverged, ticket}
+  DBuf<int> ctl;
+  HPinned<int> h_ctl;
+  DBuf<double> slice;
+  cudaEvent_t ev_it[2] = {};
+  const int *scf_stop = nullptr; // non-null while the iterations of a precision-mode solve are being enqueued
+  int scf_lag = 1;               // iterations enqueued ahead of the host's look at the stop flag (0: test every iteration)
   DBuf<double2> s12;             // per-step radial cache aligned with the tight list
   bool s12_valid = false;
   DBuf<char> cub_tmp;
@@ -332,9 +347,10 @@ static void ghost_update(polb200_handle *h, bool pos, double4 *mu, bool fence_be
   }
   const int ng = h->nghost, n = h->nloc;
   if (!ng) return;
-  if (pos && mu) LAUNCH(h, (k_ghost_refresh<true, true>), cdiv(ng, 256), 256, ng, n, h->g_owner.p, h->g_shift.p, h->box, h->xq.p, mu);
-  else if (pos) LAUNCH(h, (k_ghost_refresh<true, false>), cdiv(ng, 256), 256, ng, n, h->g_owner.p, h->g_shift.p, h->box, h->xq.p, mu);
-  else if (mu) LAUNCH(h, (k_ghost_refresh<false, true>), cdiv(ng, 256), 256, ng, n, h->g_owner.p, h->g_shift.p, h->box, h->xq.p, mu);
+  const int *stop = h->scf_stop;
+  if (pos && mu) LAUNCH(h, (k_ghost_refresh<true, true>), cdiv(ng, 256), 256, stop, ng, n, h->g_owner.p, h->g_shift.p, h->box, h->xq.p, mu);
+  else if (pos) LAUNCH(h, (k_ghost_refresh<true, false>), cdiv(ng, 256), 256, stop, ng, n, h->g_owner.p, h->g_shift.p, h->box, h->xq.p, mu);
+  else if (mu) LAUNCH(h, (k_ghost_refresh<false, true>), cdiv(ng, 256), 256, stop, ng, n, h->g_owner.p, h->g_shift.p, h->box, h->xq.p, mu);
 }
 
 static void rebuild(polb200_handle *h, const polb200_atoms *at)
@@ -462,7 +478,12 @@ static void rebuild(polb200_handle *h, const polb200_atoms *at)
 
   // 4. pair groups for the Jacobi list sweep (union skin list of two cell-row neighbours per warp)
   h->groups_built = false;
-  if (h->sweep_variant >= 30 && st.polar_cutoff > 0.0 && !st.zodid && !st.polar_gs && !st.polar_gs_ranked) {
+  h->colours_valid = false;
+  const bool gs_mode = st.polar_gs || st.polar_gs_ranked;
+  // Jacobi sweeps: any pair-group variant; Gauss-Seidel: the group-coloured sweep runs on the TMA kernel only, and an
+  // explicit gs_chunks setting asks for the per-atom chunks the oracle emulates
+  if (h->sweep_variant >= 30 && st.polar_cutoff > 0.0 && !st.zodid &&
+      (!gs_mode || (h->sweep_variant >= 40 && st.gs_chunks == 0))) {
     const int nrows = g.nc[1] * g.nc[2];
     h->cnt.ensure(std::max(n, nrows) + 1); h->growstart.ensure((size_t)n + nrows + 2);
     LAUNCH(h, k_group_count, cdiv(nrows, 256), 256, nrows, g.nc[0], h->cl_start.p, h->cnt.p);
@@ -575,7 +596,7 @@ static int launch_v2(polb200_handle *h, int beg, int end, const int *order, cons
   const int nb = cdiv(end - beg, WPB);
   const PushArgs Q = push ? push_args(h, nxt) : PushArgs{};
 #define GO(CH, PU) \
-  LAUNCH(h, (k_sweep_list2<DAMP, PF, WPB, MINB, CH, PU>), nb, WPB * 32, beg, end, order, P, L, h->xq.p, cur, h->ef.p, nxt, h->partial.p + h->partial_off, Q)
+  LAUNCH(h, (k_sweep_list2<DAMP, PF, WPB, MINB, CH, PU>), nb, WPB * 32, beg, end, order, P, L, h->xq.p, cur, h->ef.p, nxt, h->partial.p + h->partial_off, Q, h->scf_stop)
   if (push) { if (change) GO(true, true); else GO(false, true); }
   else { if (change) GO(true, false); else GO(false, false); }
 #undef GO
@@ -589,11 +610,108 @@ static int launch_cached(polb200_handle *h, int beg, int end, const int *order, 
   const int nb = cdiv(end - beg, WPB);
   const PushArgs Q = push ? push_args(h, nxt) : PushArgs{};
 #define GO(CH, PU) \
-  LAUNCH(h, (k_sweep_cached<WPB, MINB, CH, PU>), nb, WPB * 32, beg, end, order, L, h->s12.p, h->xq.p, cur, h->ef.p, nxt, h->partial.p + h->partial_off, Q)
+  LAUNCH(h, (k_sweep_cached<WPB, MINB, CH, PU>), nb, WPB * 32, beg, end, order, L, h->s12.p, h->xq.p, cur, h->ef.p, nxt, h->partial.p + h->partial_off, Q, h->scf_stop)
   if (push) { if (change) GO(true, true); else GO(false, true); }
   else { if (change) GO(true, false); else GO(false, false); }
 #undef GO
   return end - beg;
+}
+
+// per-step radial cache of the pair-group rows (k_group_cache), built by the first sweep of a step.  Returns false
+// (and drops the groups) when the cache does not fit comfortably in free HBM.
+static bool ensure_group_cache(polb200_handle *h, const DevParams &P)
+{
+  if (!h->groups_built) return false;
+  if (h->group_cache_valid) return true;
+  const bool damp = P.pc.damping_exponential != 0;
+  bool fits = true;
+  const bool chunked = h->sweep_variant >= 40;
+  const size_t need_b = chunked ? (size_t)h->gchunks * GCHUNK_BYTES : (size_t)h->gneigh.cap * 36;
+  if (chunked ? h->gcrec.cap < need_b : h->s12ab.cap < h->gneigh.cap) {  // only while it fits comfortably in free HBM
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    fits = (double)need_b < 0.6 * (double)free_b;
+  }
+  if (!fits) {
+    h->groups_built = false;
+    return false;
+  }
+  h->tgcount.ensure(h->ngroups + 1);
+  if (chunked) h->gcrec.ensure(need_b + 64, 1.0);
+  else { h->tgneigh.ensure(h->gneigh.cap); h->s12ab.ensure(h->gneigh.cap); }
+  const int ngb = cdiv(h->ngroups, WARPS_PER_BLOCK);
+#define GC(DA, CK) \
+  LAUNCH(h, (k_group_cache<DA, CK>), ngb, BLOCK, h->ngroups, P, h->group_first.p, h->group_two.p, h->growstart.p, h->gcount.p, \
+         h->gneigh.p, h->xq.p, h->tgneigh.p, h->tgcount.p, h->s12ab.p, h->gcstart.p, h->gcrec.p)
+  if (damp) { if (chunked) GC(true, true); else GC(true, false); }
+  else { if (chunked) GC(false, true); else GC(false, false); }
+#undef GC
+  h->group_cache_valid = true;
+  return true;
+}
+
+// launch of the TMA-fed pair-group sweep: whole-system Jacobi sweep (gsc == nullptr) or one colour of the
+// group-coloured Gauss-Seidel sweep
+template <int GW, int NS, int CK, bool CH, bool PU, bool EV, bool GS>
+static void launch_tma(polb200_handle *h, const double4 *cur, double4 *nxt, const PushArgs &Q, const GsChunk &gsc)
+{
+  auto kern = k_sweep_group_tma<GW, NS, CK, CH, PU, EV, GS>;
+  const int smem = GW * NS * CK * 36 + GW * NS * 8;
+  static bool attr_set = false;
+  static int per_sm = 0;
+  if (!attr_set) {
+    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GW * 32, smem));
+    attr_set = true;
+  }
+  const int rows = GS ? gsc.end - gsc.beg : h->ngroups;
+  if (rows <= 0) return;
+  const int grid = std::min(cdiv(rows, GW), std::max(per_sm, 1) * h->num_sms);
+  const int reverse = (!GS && h->alternate && (h->sweep_parity++ & 1)) ? 1 : 0;
+  kern<<<grid, GW * 32, smem, h->stream>>>(h->ngroups, h->group_first.p, h->group_two.p, h->growstart.p, h->tgneigh.p,
+                                           h->tgcount.p, h->s12ab.p, h->xq.p, cur, h->ef.p, nxt, h->partial.p, Q, h->flags.p + 4,
+                                           reverse, h->gcstart.p, h->gcrec.p, h->scf_stop, gsc);
+  h->launches++;
+  CUDA_CHECK(cudaGetLastError());
+}
+
+template <int GW, int NS, int CK, bool GS>
+static void launch_tma_flags(polb200_handle *h, const double4 *cur, double4 *nxt, bool change, bool push, const GsChunk &gsc)
+{
+  const PushArgs Q = push ? push_args(h, nxt) : PushArgs{};
+#define T4(CH, PU) \
+  do { if (h->l2_evict_first) launch_tma<GW, NS, CK, CH, PU, true, GS>(h, cur, nxt, Q, gsc); \
+       else launch_tma<GW, NS, CK, CH, PU, false, GS>(h, cur, nxt, Q, gsc); } while (0)
+  if (push) { if (change) T4(true, true); else T4(false, true); }
+  else { if (change) T4(true, false); else T4(false, false); }
+#undef T4
+}
+
+// one colour of the group-coloured Gauss-Seidel sweep: rows = the groups glist[chunk_beg[c] .. chunk_beg[c+1])
+static void launch_group_gs_chunk(polb200_handle *h, int c, const DevParams &P, const double4 *cur, double4 *staging, bool change)
+{
+  GsChunk gsc{};
+  gsc.glist = h->glist.p;
+  gsc.beg = h->chunk_beg[c];
+  gsc.end = h->chunk_beg[c + 1];
+  gsc.polar_damp = P.pc.polar_damp;
+  gsc.polar_cutsq = P.pc.polar_cutsq;
+  gsc.damping_exponential = P.pc.damping_exponential;
+  switch (h->sweep_variant) {
+    case 40: launch_tma_flags<4, 4, 64, true>(h, cur, staging, change, false, gsc); break;
+    case 44: launch_tma_flags<8, 4, 64, true>(h, cur, staging, change, false, gsc); break;
+    default: launch_tma_flags<4, 3, 64, true>(h, cur, staging, change, false, gsc); break;
+  }
+}
+
+static GsChunk gs_chunk_args(polb200_handle *h, int c)
+{
+  GsChunk gsc{};
+  gsc.glist = h->glist.p;
+  gsc.beg = h->chunk_beg[c];
+  gsc.end = h->chunk_beg[c + 1];
+  return gsc;
 }
 
 static int launch_list_sweep(polb200_handle *h, int beg, int end, const int *order, const DevParams &P, ListRows L,
@@ -603,72 +721,23 @@ static int launch_list_sweep(polb200_handle *h, int beg, int end, const int *ord
   h->partial.ensure((size_t)(end - beg) + 64);
   if (h->groups_built && order == nullptr && beg == 0 && end == h->nloc) {
     // whole-system Jacobi sweep: two cell-row neighbours per warp
-    if (!h->group_cache_valid) {
-      bool fits = true;
-      const bool chunked = h->sweep_variant >= 40;
-      const size_t need_b = chunked ? (size_t)h->gchunks * GCHUNK_BYTES : (size_t)h->gneigh.cap * 36;
-      if (chunked ? h->gcrec.cap < need_b : h->s12ab.cap < h->gneigh.cap) {  // only while it fits comfortably in free HBM
-        size_t free_b = 0, total_b = 0;
-        cudaMemGetInfo(&free_b, &total_b);
-        fits = (double)need_b < 0.6 * (double)free_b;
-      }
-      if (!fits) h->groups_built = false;
-      else {
-        h->tgcount.ensure(h->ngroups + 1);
-        if (chunked) h->gcrec.ensure(need_b + 64, 1.0);
-        else { h->tgneigh.ensure(h->gneigh.cap); h->s12ab.ensure(h->gneigh.cap); }
-        const int ngb = cdiv(h->ngroups, WARPS_PER_BLOCK);
-#define GC(DA, CK) \
-  LAUNCH(h, (k_group_cache<DA, CK>), ngb, BLOCK, h->ngroups, P, h->group_first.p, h->group_two.p, h->growstart.p, h->gcount.p, \
-         h->gneigh.p, h->xq.p, h->tgneigh.p, h->tgcount.p, h->s12ab.p, h->gcstart.p, h->gcrec.p)
-        if (damp) { if (chunked) GC(true, true); else GC(true, false); }
-        else { if (chunked) GC(false, true); else GC(false, false); }
-#undef GC
-        h->group_cache_valid = true;
-      }
-    }
-    if (h->groups_built) {
+    if (ensure_group_cache(h, P)) {
       const PushArgs Q = push ? push_args(h, nxt) : PushArgs{};
 #define GOG4(GW, MB, DP, CH, PU) \
   LAUNCH(h, (k_sweep_group<GW, MB, CH, PU, DP>), cdiv(h->ngroups, GW), GW * 32, h->ngroups, h->group_first.p, h->group_two.p, h->growstart.p, \
-         h->tgneigh.p, h->tgcount.p, h->s12ab.p, h->xq.p, cur, h->ef.p, nxt, h->partial.p + h->partial_off, Q)
+         h->tgneigh.p, h->tgcount.p, h->s12ab.p, h->xq.p, cur, h->ef.p, nxt, h->partial.p + h->partial_off, Q, h->scf_stop)
 #define GOG(GW, MB, DP) \
   do { if (push) { if (change) GOG4(GW, MB, DP, true, true); else GOG4(GW, MB, DP, false, true); } \
        else { if (change) GOG4(GW, MB, DP, true, false); else GOG4(GW, MB, DP, false, false); } } while (0)
-#define GOT4(GW, NS, CK, CH, PU, EV)                                                                                     \
-  do {                                                                                                                  \
-    auto kern = k_sweep_group_tma<GW, NS, CK, CH, PU, EV>;                                                               \
-    const int smem = GW * NS * CK * 36 + GW * NS * 8;                                                                   \
-    static bool attr_set = false;                                                                                       \
-    if (!attr_set) {                                                                                                    \
-      CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                        \
-      CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));                      \
-      attr_set = true;                                                                                                  \
-    }                                                                                                                   \
-    int per_sm = 0;                                                                                                     \
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GW * 32, smem));                            \
-    const int grid = std::min(cdiv(h->ngroups, GW), std::max(per_sm, 1) * h->num_sms);                                  \
-    kern<<<grid, GW * 32, smem, h->stream>>>(h->ngroups, h->group_first.p, h->group_two.p, h->growstart.p, h->tgneigh.p, \
-                                             h->tgcount.p, h->s12ab.p, h->xq.p, cur, h->ef.p, nxt, h->partial.p, Q, h->flags.p + 4,     \
-                                             (h->alternate && (h->sweep_parity++ & 1)) ? 1 : 0, h->gcstart.p, h->gcrec.p);     \
-    h->launches++;                                                                                                      \
-    CUDA_CHECK(cudaGetLastError());                                                                                     \
-  } while (0)
-#define GOT3(GW, NS, CK, EV) \
-  do { if (push) { if (change) GOT4(GW, NS, CK, true, true, EV); else GOT4(GW, NS, CK, false, true, EV); } \
-       else { if (change) GOT4(GW, NS, CK, true, false, EV); else GOT4(GW, NS, CK, false, false, EV); } } while (0)
-#define GOT(GW, NS, CK) do { if (h->l2_evict_first) GOT3(GW, NS, CK, true); else GOT3(GW, NS, CK, false); } while (0)
+      const GsChunk none{};
       switch (h->sweep_variant) {
-        case 40: GOT(4, 4, 64); break;
-        case 41: GOT(4, 3, 64); break;
-        case 44: GOT(8, 4, 64); break;
+        case 40: launch_tma_flags<4, 4, 64, false>(h, cur, nxt, change, push, none); break;
+        case 41: launch_tma_flags<4, 3, 64, false>(h, cur, nxt, change, push, none); break;
+        case 44: launch_tma_flags<8, 4, 64, false>(h, cur, nxt, change, push, none); break;
         case 31: GOG(4, 5, true); break;
         default: GOG(4, 6, false); break;
       }
 #undef GOG4
-#undef GOT4
-#undef GOT3
-#undef GOT
 #undef GOG
       return end - beg;
     }
@@ -692,7 +761,7 @@ static int launch_list_sweep(polb200_handle *h, int beg, int end, const int *ord
   }
   if (!order && h->sweep_variant == 0) {  // first version (kept as the simplest statement of the sweep; per-block partials)
     const int nb = cdiv(end - beg, WARPS_PER_BLOCK);
-    LAUNCH(h, (k_sweep<true>), nb, BLOCK, beg, end, order, P, L, A, h->xq.p, cur, h->ef.p, nxt, h->partial.p);
+    LAUNCH(h, (k_sweep<true>), nb, BLOCK, beg, end, order, P, L, A, h->xq.p, cur, h->ef.p, nxt, h->partial.p, h->scf_stop);
     return nb;
   }
   // matrix-free: no per-pair cache (used when 16 B per pair do not fit in HBM, or on request: variant 6)
@@ -700,14 +769,60 @@ static int launch_list_sweep(polb200_handle *h, int beg, int end, const int *ord
               : launch_v2<false, 1, 4, 10>(h, beg, end, order, P, L, cur, nxt, change, push);
 }
 
+// Colouring of the pair groups for the group-coloured Gauss-Seidel sweep (kernels.cuh), once per rebuild:
+// strong-coupling adjacency -> parallel greedy colouring in priority order (rank metric, then a hash) -> the groups
+// sorted by colour (glist) and the start of every colour's slice (chunk_beg).
+static void build_colouring(polb200_handle *h, const double *metric_caller)
+{
+  const int ngr = h->ngroups, n = h->nloc, C = h->ncolours;
+  h->gof.ensure(n); h->gmetric.ensure(ngr); h->gadj.ensure((size_t)ngr * GS_MAXADJ); h->gadjn.ensure(ngr);
+  h->gcolour.ensure(ngr); h->glist.ensure(ngr); h->cstart_dev.ensure(C + 2);
+  LAUNCH(h, k_group_of, cdiv(ngr, 256), 256, ngr, h->group_first.p, h->group_two.p, h->perm.p, metric_caller, h->gof.p, h->gmetric.p);
+  // radius of a "strong" coupling: the sphere that holds gs_strong_m atoms at the mean density of the system
+  const double pi = 3.14159265358979323846;
+  const double natoms = h->comm.active ? (double)h->comm.nglobal : (double)n;
+  const double rho = natoms / (h->box.prd[0] * h->box.prd[1] * h->box.prd[2]);
+  double rs = cbrt(3.0 * h->gs_strong_m / (4.0 * pi * rho));
+  rs = std::min(rs, h->style.cutneighmax);
+  LAUNCH(h, k_group_adjacency, cdiv(ngr, WARPS_PER_BLOCK), BLOCK, ngr, n, rs * rs, h->group_first.p, h->group_two.p, h->growstart.p,
+         h->gcount.p, h->gneigh.p, h->xq.p, h->gof.p, (h->comm.active || h->nghost == 0) ? (const int *)nullptr : h->g_owner.p,
+         h->gadj.p, h->gadjn.p);
+  CUDA_CHECK(cudaMemsetAsync(h->gcolour.p, 0xFF, (size_t)ngr * sizeof(int), h->stream));
+  int *remaining = h->flags.p + 7;
+  h->colour_rounds = 0;
+  for (int batch = 0; batch < 4096; batch++) {
+    for (int r = 0; r < 8; r++) {
+      if (r == 7) CUDA_CHECK(cudaMemsetAsync(remaining, 0, sizeof(int), h->stream));
+      LAUNCH(h, k_colour_round, cdiv(ngr, 256), 256, ngr, C, h->gadj.p, h->gadjn.p, h->gmetric.p, h->gcolour.p, remaining);
+    }
+    h->colour_rounds += 8;
+    int left = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&left, remaining, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    if (left == 0) break;
+    if (batch == 4095) throw CudaError{"group colouring did not terminate"};
+  }
+  // groups by colour (stable: ascending group index inside a colour, i.e. the cell-sorted streaming order)
+  const int m = std::max(ngr, 64);
+  h->keys.ensure(m); h->keys2.ensure(m); h->vals.ensure(m);
+  CUDA_CHECK(cudaMemcpyAsync(h->keys.p, h->gcolour.p, (size_t)ngr * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+  LAUNCH(h, k_iota, cdiv(ngr, 256), 256, ngr, h->vals.p);
+  sort_pairs(h, ngr, h->keys.p, h->keys2.p, h->vals.p, h->glist.p, 6);
+  LAUNCH(h, k_cell_starts, 1, 64, C, ngr, h->keys2.p, h->cstart_dev.p, 0);
+  CUDA_CHECK(cudaMemcpyAsync(h->chunk_beg, h->cstart_dev.p, (size_t)(C + 1) * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  h->chunk_beg[C] = ngr;
+  h->colours_valid = true;
+}
+
 template <int NV>
 static void reduce_partials(polb200_handle *h, int nblocks, double *out, int accumulate)
 {
-  LAUNCH(h, k_reduce_partials<NV>, 1, 256, nblocks, h->partial.p, out, accumulate);
+  LAUNCH(h, k_reduce_partials<NV>, 1, 256, nblocks, h->partial.p, out, accumulate, (const int *)nullptr);
 }
 
 // scal layout (device doubles): 0..7 pair partial sums, 8..16 polarization sums, 17 change, 18 rmin
-enum { S_PAIR = 0, S_POL = 8, S_CHANGE = 17, S_N = 24 };
+enum { S_PAIR = 0, S_POL = 8, S_CHANGE = 17, S_RMIN = 18, S_N = 24 };
 
 static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, int vflag, int ago,
                          polb200_result *out)
@@ -818,9 +933,12 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
   // ---- stage 3: self-consistent dipoles (DipoleSolverIterative, pol.cpp:1113-1238) ----
   int iterations = 0;
   bool diverged = false;
-  double rmin = 0.0;
   if (!st.zodid) {
     const bool gs = st.polar_gs || st.polar_gs_ranked;
+    // list-mode Gauss-Seidel: group-coloured sweep on the TMA pair-group kernel (default), or -- with an explicit
+    // gs_chunks setting, without pair groups, or when their cache does not fit -- per-atom chunks of the ranked order
+    const bool coloured = gs && list_mode && st.gs_chunks == 0 && h->groups_built && h->sweep_variant >= 40 &&
+                          ensure_group_cache(h, P);
     // Gauss-Seidel visits atoms in the CALLER's index order (ranked_array = identity, pol.cpp:1127),
     // i.e. position c -> cell-sorted index invperm[c]; Jacobi does not care about the order.
     const int *order = gs ? h->invperm.p : nullptr;
@@ -833,33 +951,33 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
       ListRows Lfull{h->rowstart.p, h->neigh.p, nullptr};
       LAUNCH(h, k_rmin, nrowblocks, BLOCK, n, Lfull, h->xq.p, h->mua.p, h->tm.p, h->rmin_bits.p);
       if (comm) comm_allreduce(h, h->rmin_bits.p, 1, ncclUint64, ncclMin);  // positive doubles order like their bits
-      LAUNCH(h, k_rank_metric, nrowblocks, BLOCK, n, Lfull, h->xq.p, h->mua.p, h->tm.p, h->rmin_bits.p, h->perm.p, h->g_owner.p, h->g_shift.p,
-             comm ? h->tag.p : (const int *)nullptr, h->metric.p);
-      // values in caller order = sorted index of caller atom c
-      size_t bytes = 0;
-      cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, h->metric.p, h->metric2.p, h->invperm.p, h->ranked.p, n, 0, 64, h->stream);
-      h->cub_tmp.ensure(bytes);
-      CUDA_CHECK(cub::DeviceRadixSort::SortPairsDescending(h->cub_tmp.p, bytes, h->metric.p, h->metric2.p, h->invperm.p, h->ranked.p, n, 0, 64, h->stream));
-      h->launches += 3;
-      order = h->ranked.p;
-      unsigned long long rb = 0;
-      CUDA_CHECK(cudaMemcpyAsync(&rb, h->rmin_bits.p, sizeof(rb), cudaMemcpyDeviceToHost, h->stream));
-      CUDA_CHECK(cudaStreamSynchronize(h->stream));
-      memcpy(&rmin, &rb, sizeof(double));
+      // (rmin travels to the host with the step's scalars: no synchronisation here)
+      CUDA_CHECK(cudaMemcpyAsync(h->scal.p + S_RMIN, h->rmin_bits.p, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+      // the coloured sweep uses the metric as the priority of its colouring, fixed between two rebuilds
+      if (!coloured || !h->colours_valid)
+        LAUNCH(h, k_rank_metric, nrowblocks, BLOCK, n, Lfull, h->xq.p, h->mua.p, h->tm.p, h->rmin_bits.p, h->perm.p, h->g_owner.p, h->g_shift.p,
+               comm ? h->tag.p : (const int *)nullptr, h->metric.p);
+      if (!coloured) {
+        // values in caller order = sorted index of caller atom c
+        size_t bytes = 0;
+        cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, h->metric.p, h->metric2.p, h->invperm.p, h->ranked.p, n, 0, 64, h->stream);
+        h->cub_tmp.ensure(bytes);
+        CUDA_CHECK(cub::DeviceRadixSort::SortPairsDescending(h->cub_tmp.p, bytes, h->metric.p, h->metric2.p, h->invperm.p, h->ranked.p, n, 0, 64, h->stream));
+        h->launches += 3;
+        order = h->ranked.p;
+      }
     }
+    if (coloured && !h->colours_valid) build_colouring(h, st.polar_gs_ranked ? h->metric.p : nullptr);
     // which sweep realisation
     int nchunks = 0;          // 0: Jacobi (one block of rows, separate output array)
     bool sequential = false;  // reference-exact Gauss-Seidel (all-pairs mode only)
     if (gs) {
-      if (st.gs_chunks != 0) nchunks = abs(st.gs_chunks);
-      else if (list_mode) {
-        // default: 8 INTERLEAVED chunks.  Interleaving makes the colouring as good as the sequential sweep where it
-        // matters (water box: 17 iterations against 77 with 8 contiguous chunks and 16 strictly sequential; atomic
-        // fluid: 16 / 16 / 13), so a handful of chunks -- few launches, few halo barriers -- is enough.
-        nchunks = std::min(8, n);
-      } else sequential = true;
+      if (coloured) nchunks = h->ncolours;
+      else if (st.gs_chunks != 0) nchunks = abs(st.gs_chunks);
+      else if (list_mode) nchunks = std::min(8, n);  // per-atom fallback: 8 INTERLEAVED chunks of the ranked order
+      else sequential = true;
     }
-    if (gs && nchunks > 1 && st.gs_chunks <= 0 && !sequential) {
+    if (gs && !coloured && nchunks > 1 && st.gs_chunks <= 0 && !sequential) {
       h->ranked_in.ensure(n);
       LAUNCH(h, k_interleave_order, cdiv(n, 256), 256, n, nchunks, order, h->ranked_in.p);
       order = h->ranked_in.p;
@@ -867,46 +985,80 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
     // fused sweep + halo: new dipoles go straight into the neighbour bricks' ghost slots (Jacobi sweeps)
     const bool push = h->push_ready && h->use_push && !gs && list_mode && h->sweep_variant != 0 &&
                       !(h->sweep_variant >= 11 && h->sweep_variant <= 14);
+    const bool fused_commit = h->push_ready && h->use_push && (!comm || h->comm.push.enabled);
     const double natoms_norm = comm ? (double)h->comm.nglobal : (double)n;
-    double4 *cur = h->mua.p, *nxt = h->mub.p;
     const double prec2 = st.polar_precision * st.polar_precision;
-    bool keep = true;
-    while (keep) {
-      double change = 0.0;
-      const bool want_change = !st.fixed_iteration;
+    const bool want_change = !st.fixed_iteration;
+    const int itmax = st.iterations_max;
+    if (list_mode) h->partial.ensure((size_t)n + 64);
+    h->slice.ensure(SCF_SUM_BLOCKS);
+
+    // precision mode: the convergence test runs on the device and raises a stop flag that every kernel of the loop
+    // honours, so the host may enqueue iterations ahead of its (lagged) look at the flag
+    int *ctl = nullptr;
+    if (want_change) {
+      h->ctl.ensure(4);
+      h->h_ctl.ensure(8);
+      if (!h->ev_it[0])
+        for (auto &e : h->ev_it) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ctl = h->ctl.p;
+      CUDA_CHECK(cudaMemsetAsync(ctl, 0, 4 * sizeof(int), h->stream));
+    }
+    h->scf_stop = ctl;
+    const int *stop = ctl;
+
+    // one iteration `it` of the solver (Jacobi: reads the buffer of parity it, writes the other one)
+    auto enqueue_iteration = [&](int it) {
+      double4 *cur = h->mua.p, *nxt = h->mub.p;
+      if (!gs && (it & 1)) std::swap(cur, nxt);
+      double *chg = h->scal.p + S_CHANGE;
+      bool summed = false;  // the squared change is already in *chg
+      int nparts = 0;
       if (sequential && h->gs_blocked) {
         // blocked forward substitution = the same sweep, N/32 dependent steps instead of N (kernels.cuh)
         h->gsR.ensure(n);
-        LAUNCH(h, k_gsb_upper, nrowblocks, BLOCK, n, order, P, h->perm.p, h->xq.p, cur, h->ef.p, h->gsR.p);
+        LAUNCH(h, k_gsb_upper, nrowblocks, BLOCK, n, order, P, h->perm.p, h->xq.p, cur, h->ef.p, h->gsR.p, stop);
         const int nblk = cdiv(n, GSB);
         for (int b = 0; b < nblk; b++) {
-          LAUNCH(h, k_gsb_solve, 1, GSB * 32, n, b, order, P, h->perm.p, h->xq.p, cur, h->gsR.p, h->scal.p + S_CHANGE, b == 0 ? 1 : 0);
+          LAUNCH(h, k_gsb_solve, 1, GSB * 32, n, b, order, P, h->perm.p, h->xq.p, cur, h->gsR.p, chg, b == 0 ? 1 : 0, stop);
           const int rows_after = n - (b + 1) * GSB;
           if (rows_after > 0)
-            LAUNCH(h, k_gsb_update, cdiv(rows_after, WARPS_PER_BLOCK), BLOCK, n, b, order, P, h->perm.p, h->xq.p, cur, h->gsR.p);
+            LAUNCH(h, k_gsb_update, cdiv(rows_after, WARPS_PER_BLOCK), BLOCK, n, b, order, P, h->perm.p, h->xq.p, cur, h->gsR.p, stop);
         }
+        summed = true;
       } else if (sequential) {
-        LAUNCH(h, k_gs_sequential, 1, GS_THREADS, n, order, P, h->perm.p, h->xq.p, cur, h->ef.p, h->scal.p + S_CHANGE);
+        LAUNCH(h, k_gs_sequential, 1, GS_THREADS, n, order, P, h->perm.p, h->xq.p, cur, h->ef.p, chg, stop);
+        summed = true;
       } else if (!gs) {
-        // Jacobi in fixed mode: the reference runs max_iterations+1 sweeps and discards the last
-        // (pol.cpp:1214 returns before the copy), so only max_iterations sweeps shape the result
-        if (st.fixed_iteration && iterations >= st.iterations_max) break;
         sweep_event(h);
-        int nparts = nrowblocks;
+        nparts = nrowblocks;
         if (list_mode) nparts = launch_list_sweep(h, 0, n, order, P, L, A, cur, nxt, want_change, push);
-        else LAUNCH(h, (k_sweep<false>), nrowblocks, BLOCK, 0, n, order, P, L, A, h->xq.p, cur, h->ef.p, nxt, h->partial.p);
+        else LAUNCH(h, (k_sweep<false>), nrowblocks, BLOCK, 0, n, order, P, L, A, h->xq.p, cur, h->ef.p, nxt, h->partial.p, stop);
         sweep_event(h);
-        if (want_change) reduce_partials<1>(h, nparts, h->scal.p + S_CHANGE, 0);
-        if (push) {
-          if (comm) comm_signal_wait(h, want_change ? h->scal.p + S_CHANGE : nullptr);  // barrier (+ all-reduce)
-        } else {
-          ghost_update(h, false, nxt);
-          if (comm && want_change) comm_allreduce(h, h->scal.p + S_CHANGE, 1, ncclDouble, ncclSum);
+      } else if (coloured) {
+        // group-coloured sweep: the colours in turn; Jacobi inside a colour (staging array + commit)
+        sweep_event(h);
+        for (int c = 0; c < nchunks; c++) {
+          if (h->chunk_beg[c + 1] <= h->chunk_beg[c]) continue;
+          launch_group_gs_chunk(h, c, P, cur, nxt, want_change);
+          const int nthreads = 2 * (h->chunk_beg[c + 1] - h->chunk_beg[c]);
+          if (fused_commit) {
+            // in place: the neighbour bricks must have finished reading this chunk's input before their ghost
+            // slots change, and must see the new values before the next chunk (two barriers around one kernel)
+            if (comm) comm_signal_wait(h, nullptr);
+            LAUNCH(h, k_commit_groups, cdiv(nthreads, 256), 256, gs_chunk_args(h, c), h->group_first.p, h->group_two.p, nxt, cur,
+                   push_args(h, cur), 1, stop);
+            if (comm) comm_signal_wait(h, nullptr);
+          } else {
+            LAUNCH(h, k_commit_groups, cdiv(nthreads, 256), 256, gs_chunk_args(h, c), h->group_first.p, h->group_two.p, nxt, cur,
+                   PushArgs{}, 0, stop);
+            ghost_update(h, false, cur, true);
+          }
         }
+        sweep_event(h);
+        nparts = n;
       } else {
-        // ranked colouring sweep: chunks of the ranked order, Jacobi inside, Gauss-Seidel between
-        const bool fused_commit = h->push_ready && h->use_push && (!comm || h->comm.push.enabled);
-        if (list_mode) h->partial.ensure((size_t)n + 64);
+        // per-atom chunks of the ranked order, Jacobi inside, Gauss-Seidel between
         for (int c = 0; c < nchunks; c++) {
           const int beg = (int)(((long)c * n) / nchunks), end = (int)(((long)(c + 1) * n) / nchunks);
           if (end <= beg) continue;
@@ -917,39 +1069,82 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
             launch_list_sweep(h, beg, end, order, P, L, A, cur, nxt, want_change, false);
             h->partial_off = 0;
           } else {
-            LAUNCH(h, (k_sweep<false>), nb, BLOCK, beg, end, order, P, L, A, h->xq.p, cur, h->ef.p, nxt, h->partial.p);
-            if (want_change) reduce_partials<1>(h, nb, h->scal.p + S_CHANGE, c > 0);
+            LAUNCH(h, (k_sweep<false>), nb, BLOCK, beg, end, order, P, L, A, h->xq.p, cur, h->ef.p, nxt, h->partial.p, stop);
+            if (want_change) LAUNCH(h, k_reduce_partials<1>, 1, 256, nb, h->partial.p, chg, c > 0 ? 1 : 0, stop);
+            summed = true;
           }
           if (fused_commit) {
-            // in place: the neighbour bricks must have finished reading this chunk's input before their ghost
-            // slots change, and must see the new values before the next chunk (two barriers around one kernel)
             if (comm) comm_signal_wait(h, nullptr);
-            LAUNCH(h, k_commit_push, cdiv(end - beg, 256), 256, beg, end, order, nxt, cur, push_args(h, cur));
+            LAUNCH(h, k_commit_push, cdiv(end - beg, 256), 256, beg, end, order, nxt, cur, push_args(h, cur), stop);
             if (comm) comm_signal_wait(h, nullptr);
           } else {
-            LAUNCH(h, k_commit_rows, cdiv(end - beg, 256), 256, beg, end, order, nxt, cur);
+            LAUNCH(h, k_commit_rows, cdiv(end - beg, 256), 256, beg, end, order, nxt, cur, stop);
             ghost_update(h, false, cur, true);
           }
         }
-        if (list_mode && want_change) reduce_partials<1>(h, n, h->scal.p + S_CHANGE, 0);
-        if (comm && want_change) comm_allreduce(h, h->scal.p + S_CHANGE, 1, ncclDouble, ncclSum);
+        nparts = n;
       }
+      // squared change of this iteration -> (all-reduce) -> test
       if (want_change) {
-        CUDA_CHECK(cudaMemcpyAsync(h->h_scal.p + S_CHANGE, h->scal.p + S_CHANGE, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        CUDA_CHECK(cudaStreamSynchronize(h->stream));
-        change = h->h_scal.p[S_CHANGE] / (natoms_norm * 3.0);
-        keep = change > prec2;  // pol.cpp:1205-1209
-      } else if (iterations >= st.iterations_max) {
-        break;  // Gauss-Seidel fixed mode: the in-place writes of this last sweep stay
+        const double norm3n = natoms_norm * 3.0;
+        if (!summed)
+          LAUNCH(h, k_change_sum, SCF_SUM_BLOCKS, 256, nparts, h->partial.p, h->slice.p, chg, ctl, comm ? 0 : 1, prec2, norm3n,
+                 itmax, stop);
+        if (!gs) {
+          if (push) {
+            if (comm) comm_signal_wait(h, chg);  // barrier (+ all-reduce)
+          } else {
+            ghost_update(h, false, nxt);
+            if (comm) comm_allreduce(h, chg, 1, ncclDouble, ncclSum);
+          }
+        } else if (comm) {
+          comm_allreduce(h, chg, 1, ncclDouble, ncclSum);
+        }
+        if (summed || comm) LAUNCH(h, k_scf_check, 1, 32, chg, ctl, prec2, norm3n, itmax);
+      } else if (!gs) {
+        if (push) {
+          if (comm) comm_signal_wait(h, nullptr);
+        } else ghost_update(h, false, nxt);
       }
-      if (!gs) std::swap(cur, nxt);  // "save the dipoles for the next pass" (pol.cpp:1218-1222)
-      iterations++;
-      if (iterations > st.iterations_max) {  // pol.cpp:1227-1235
-        LAUNCH(h, k_reset_mu, cdiv(n, 256), 256, n, h->ef.p, cur);
-        diverged = true;
-        break;
+    };
+
+    const size_t ev_base = h->sweep_ev_used;
+    if (!want_change) {
+      // fixed_iteration: Jacobi runs max_iterations+1 sweeps in the reference and discards the last (pol.cpp:1214
+      // returns before the copy), so only max_iterations sweeps shape the result; the in-place writes of the
+      // Gauss-Seidel modes' extra sweep stay
+      const int nsweeps = gs ? itmax + 1 : itmax;
+      for (int it = 0; it < nsweeps; it++) enqueue_iteration(it);
+      iterations = itmax;
+    } else {
+      const int lag = (comm && !h->comm.push.enabled) ? 0 : h->scf_lag;
+      int it = 0;
+      const int *seen = nullptr;
+      while (!seen) {
+        enqueue_iteration(it);
+        int *slot = h->h_ctl.p + 4 * (it & 1);
+        CUDA_CHECK(cudaMemcpyAsync(slot, ctl, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_CHECK(cudaEventRecord(h->ev_it[it & 1], h->stream));
+        it++;
+        const int w = it - 1 - lag;  // the iteration whose test the host looks at now
+        if (w >= 0) {
+          CUDA_CHECK(cudaEventSynchronize(h->ev_it[w & 1]));
+          if (h->h_ctl.p[4 * (w & 1)]) seen = h->h_ctl.p + 4 * (w & 1);
+        }
+        if (!seen && it > itmax + 1) {  // the device stops at max_iterations+1 at the latest (divergence path)
+          CUDA_CHECK(cudaStreamSynchronize(h->stream));
+          seen = h->h_ctl.p + 4 * ((it - 1) & 1);
+          if (!seen[0]) throw CudaError{"SCF stop flag was not raised after max_iterations + 1 iterations"};
+        }
       }
+      iterations = seen[1];
+      diverged = seen[2] != 0;
+      // events of the iterations that were enqueued past the stop are not sweeps
+      h->sweep_ev_used = std::min(h->sweep_ev_used, ev_base + (size_t)2 * iterations);
     }
+    h->scf_stop = nullptr;
+    double4 *cur = (!gs && (iterations & 1)) ? h->mub.p : h->mua.p;
+    if (diverged) LAUNCH(h, k_reset_mu, cdiv(n, 256), 256, n, h->ef.p, cur);  // pol.cpp:1227-1235
     // after fused sweeps the ghost copies of the final array are already current on every brick
     const bool ghosts_current = push && !diverged;
     if (cur != h->mua.p) {  // keep the canonical buffer
@@ -1052,7 +1247,7 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
       for (int k = 0; k < 6; k++) out->virial[k] = sc[S_PAIR + 2 + k] + sc[S_POL + 3 + k];
   }
   out->iterations = iterations;
-  out->rmin = rmin;
+  out->rmin = sc[S_RMIN];
   out->status = (diverged ? POLB200_STATUS_DIVERGED : 0) | (need ? POLB200_STATUS_REBUILT : 0) |
                 (list_mode ? 0 : POLB200_STATUS_EXACT);
   out->npairs_full = (long)h->npairs;
@@ -1267,6 +1462,9 @@ void polb200_destroy(polb200_t *h)
   h->group_first.release(); h->group_two.release(); h->gneigh.release(); h->gcount.release(); h->tgneigh.release(); h->tgcount.release();
   h->gsR.release(); h->growstart.release(); h->s12ab.release(); h->gcstart.release(); h->gcrec.release();
   h->s12.release(); h->push_off.release(); h->push_ptr0.release(); h->push_ptr1.release();
+  h->gof.release(); h->gadj.release(); h->gadjn.release(); h->gcolour.release(); h->glist.release(); h->cstart_dev.release();
+  h->col_export.release(); h->gmetric.release(); h->ctl.release(); h->h_ctl.release(); h->slice.release();
+  for (auto &e : h->ev_it) if (e) cudaEventDestroy(e);
   h->tm.release(); h->cnt.release(); h->rowstart.release(); h->cub_tmp.release(); h->rmin_bits.release();
   h->h_stage.release(); h->h_scal.release(); h->h_int.release();
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
@@ -1473,6 +1671,22 @@ int polb200_set_option(polb200_t *h, const char *name, double value)
     h->use_tight = value != 0.0;
     return POLB200_OK;
   }
+  if (!strcmp(name, "gs_colours")) {  // colours (= chunks per sweep) of the group-coloured Gauss-Seidel sweep
+    if (!(value >= 1.0 && value <= 32.0)) return POLB200_ERR_ARG;
+    h->ncolours = (int)value;
+    h->colours_valid = false;
+    return POLB200_OK;
+  }
+  if (!strcmp(name, "gs_strong_m")) {  // atoms inside the "strong coupling" radius of the colouring (mean density)
+    if (!(value >= 0.0 && value <= 64.0)) return POLB200_ERR_ARG;
+    h->gs_strong_m = value;
+    h->colours_valid = false;
+    return POLB200_OK;
+  }
+  if (!strcmp(name, "scf_lag")) {  // 1: one iteration enqueued ahead of the host's look at the stop flag; 0: none
+    h->scf_lag = value != 0.0 ? 1 : 0;
+    return POLB200_OK;
+  }
   if (!strcmp(name, "time_sweeps")) {
     h->time_sweeps = value != 0.0;
     h->sweep_ms_accum = 0.0;
@@ -1560,6 +1774,18 @@ long polb200_debug_fetch(polb200_t *h, const char *name, void *dst, long capacit
     else if (!strcmp(name, "mua")) fetch(h->mua.p, (size_t)(n + ng) * 32, (long)(n + ng) * 4);
     else if (!strcmp(name, "ef")) fetch(h->ef.p, (size_t)n * 32, (long)n * 4);
     else if (!strcmp(name, "ranked")) fetch(h->ranked.p, (size_t)n * 4, n);
+    else if (!strcmp(name, "gs_colouring")) {
+      // group-coloured sweep: {colour, in-group predecessor (caller index or -1)} of every owned atom, caller order;
+      // then {number of colours, rounds of the greedy colouring, groups}
+      if (!h->colours_valid) throw StyleError{POLB200_ERR_STATE, "debug_fetch: no group colouring (not a list-mode Gauss-Seidel run)"};
+      h->col_export.ensure((size_t)2 * n + 4);
+      LAUNCH(h, k_colour_export, cdiv(h->ngroups, 256), 256, h->ngroups, h->group_first.p, h->group_two.p, h->gcolour.p, h->perm.p,
+             h->col_export.p, h->col_export.p + n);
+      const int tail[3] = {h->ncolours, h->colour_rounds, h->ngroups};
+      CUDA_CHECK(cudaMemcpyAsync(h->col_export.p + 2 * (size_t)n, tail, sizeof(tail), cudaMemcpyHostToDevice, h->stream));
+      CUDA_CHECK(cudaStreamSynchronize(h->stream));
+      fetch(h->col_export.p, ((size_t)2 * n + 3) * 4, (long)2 * n + 3);
+    }
     else if (!strcmp(name, "metric")) fetch(h->metric.p, (size_t)n * 8, n);
     else throw StyleError{POLB200_ERR_ARG, std::string("debug_fetch: unknown array ") + name};
   });

@@ -1240,7 +1240,28 @@ static void row_static(const polref_params *p, const box_t *box, const partners_
   Ei[2] = e2;
 }
 
-/* induced-field row (:1161-1168) with on-the-fly T blocks */
+/* induced-field row (:1161-1168) with on-the-fly T blocks; ov >= 0: partner ov contributes ovmu instead of its
+ * entry of mu (the in-group Gauss-Seidel step of the group-coloured sweep) */
+static void row_induced_ov(const polref_params *p, const box_t *box, const partners_t *pl, int r, int i,
+                           const double *x, const double *mu, double polar_cutsq, int ov, const double *ovmu, double *Ei)
+{
+  double e[3] = {0, 0, 0};
+  int n = partner_count(pl, r);
+  for (int k = 0; k < n; k++) {
+    int j = partner_at(pl, r, i, k);
+    int lo = i < j ? i : j, hi = i < j ? j : i;
+    double T[3][3], r2;
+    t_block(p, box, &x[3 * lo], &x[3 * hi], T, &r2);
+    if (polar_cutsq > 0.0 && !(r2 < polar_cutsq)) continue;
+    const double *mj = (j == ov) ? ovmu : &mu[3 * j];
+    for (int pp = 0; pp < 3; pp++)
+      for (int qq = 0; qq < 3; qq++) e[pp] -= T[pp][qq] * mj[qq];
+  }
+  Ei[0] = e[0];
+  Ei[1] = e[1];
+  Ei[2] = e[2];
+}
+
 static void row_induced(const polref_params *p, const box_t *box, const partners_t *pl, int r, int i,
                         const double *x, const double *mu, double polar_cutsq, double *Ei)
 {
@@ -1459,7 +1480,31 @@ int polref_polar_rows(const polref_params *p, int nlocal, const double *x, const
     while (keep_iterating) {
       memcpy(mu_old, mu, sizeof(double) * 3 * (size_t)nlocal);
       int nblk = !gs ? 1 : (nchunks ? nchunks : nlocal);
-      if (nblk == nlocal) {
+      if (gs && p->gs_colour) {
+        /* EXTENSION: explicit colouring (the group-coloured sweep of the CUDA list path).  Colours in turn; inside a
+         * colour every atom is updated from the dipoles as they stand before the colour (Jacobi), except that an atom
+         * with gs_after[i] = a >= 0 (the second member of a pair group) sees the NEW dipole of a. */
+        for (int cb = 0; cb < p->gs_ncolours; cb++) {
+#pragma omp parallel for schedule(dynamic, 64)
+          for (int i = 0; i < nlocal; i++) {
+            if (p->gs_colour[i] != cb || p->gs_after[i] >= 0) continue;
+            double E[3];
+            row_induced(p, &box, &pl, i, i, x, mu, polar_cutsq, E);
+            for (int c = 0; c < 3; c++) mu_new[3 * i + c] = alpha[i] * (ef_static[3 * i + c] + E[c]);
+          }
+#pragma omp parallel for schedule(dynamic, 64)
+          for (int i = 0; i < nlocal; i++) {
+            if (p->gs_colour[i] != cb || p->gs_after[i] < 0) continue;
+            int a = p->gs_after[i];
+            double E[3];
+            row_induced_ov(p, &box, &pl, i, i, x, mu, polar_cutsq, a, &mu_new[3 * a], E);
+            for (int c = 0; c < 3; c++) mu_new[3 * i + c] = alpha[i] * (ef_static[3 * i + c] + E[c]);
+          }
+          for (int i = 0; i < nlocal; i++)
+            if (p->gs_colour[i] == cb)
+              for (int c = 0; c < 3; c++) mu[3 * i + c] = mu_new[3 * i + c];
+        }
+      } else if (nblk == nlocal) {
         for (int pos = 0; pos < nlocal; pos++) {
           int i = ranked[pos];
           double E[3];

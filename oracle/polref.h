@@ -55,6 +55,12 @@ typedef struct {
    * half of every pair's energy and virial to each of its two atoms.  (nlocal+nghost) and (nlocal+nghost)*6
    * doubles, accumulated (+=); NULL = off (eflag_atom / vflag_atom not set). */
   double *eatom, *vatom;
+  /* EXTENSION (polref_polar_rows only): explicit colouring of the Gauss-Seidel sweep, as the CUDA list path's
+   * group-coloured sweep chooses it (exported by the device, tests only).  gs_colour[i] in [0, gs_ncolours): the
+   * colours are visited in turn, Jacobi inside a colour; gs_after[i] = a >= 0: atom i (second member of a pair group)
+   * is updated right after atom a of the same colour and sees its new dipole.  NULL = off. */
+  const int *gs_colour, *gs_after;
+  int gs_ncolours;
 } polref_params;
 
 typedef struct {

@@ -38,6 +38,7 @@ class Params(C.Structure):
         ("polar_cut", C.c_double), ("gs_chunks", C.c_int),
         ("boxlo", C.c_double * 3), ("boxhi", C.c_double * 3), ("periodic", C.c_int * 3),
         ("eatom", dp), ("vatom", dp),
+        ("gs_colour", ip), ("gs_after", ip), ("gs_ncolours", C.c_int),
     ]
 
 
@@ -429,13 +430,18 @@ def compute(sysm, style, mu_in=None, eflag=1, vflag=2, use_matrix=False, trace_m
                 lists=(xall, owner, shift, numneigh, first, neigh))
 
 
-def polar_rows(sysm, style, mu_in=None, eflag=1, trace_max=0, nthreads=0):
-    """Row-gather polarization part (static field, SCF, dipole forces) with OpenMP."""
+def polar_rows(sysm, style, mu_in=None, eflag=1, trace_max=0, nthreads=0, colouring=None):
+    """Row-gather polarization part (static field, SCF, dipole forces) with OpenMP.
+    colouring = (colour[n], after[n], ncolours): replay the device's group-coloured Gauss-Seidel sweep."""
     L = lib()
     if not style._init:
         style.init()
     n = sysm.n
     p = style.params(sysm)
+    if colouring is not None:
+        col, aft = i32(colouring[0]), i32(colouring[1])
+        assert col.shape == (n,) and aft.shape == (n,)
+        p.gs_colour, p.gs_after, p.gs_ncolours = _i(col), _i(aft), int(colouring[2])
     mu = np.zeros((n, 3)) if mu_in is None else f64(mu_in).reshape(n, 3).copy()
     ef = np.zeros((n, 3))
     f = np.zeros((n, 3))

@@ -428,9 +428,10 @@ def test_blocked_gauss_seidel_equals_atom_by_atom(case):
 
 
 def test_interleaved_colouring_matches_oracle_and_converges_like_sequential(style):
-    """default list-mode Gauss-Seidel = 8 interleaved chunks (chunk c = ranked positions c, c+8, ...): against the
-    oracle's emulation of the same colouring (gs_chunks -8) and against the strictly sequential sweep: same fixed
-    point, and nearly the sequential iteration count (contiguous chunks need ~5x more on this system)."""
+    """per-atom interleaved colouring (`gs_chunks -8`: chunk c = ranked positions c, c+8, ...; the list-mode default of
+    round 1, still the fallback without pair groups): against the oracle's emulation of the same colouring and against
+    the strictly sequential sweep: same fixed point, and nearly the sequential iteration count (contiguous chunks need
+    ~5x more on this system)."""
     sysm = H.water_box(10)
     kw = dict(polar_cut=12.0, damp_type="exponential", polar_gs_ranked=1, precision=1e-11, max_iterations=200,
               polar_gamma=1.03)
@@ -438,12 +439,94 @@ def test_interleaved_colouring_matches_oracle_and_converges_like_sequential(styl
     seq = P.polar_rows(sysm, H.water_style(sysm, 2.5, 12.0, gs_chunks=0, **kw))
     st = H.water_style(sysm, 2.5, 12.0, **kw)
     _water_on_device(style, sysm, st, "damp_type exponential precision 1e-11 max_iterations 200 polar_gamma 1.03 "
-                                       "polar_cutoff 12.0")
+                                       "polar_cutoff 12.0 gs_chunks -8")
     res, mu, ef, f = run_system(style, sysm)
     assert abs(res.iterations - ref["iterations"]) <= 2
     assert res.iterations <= seq["iterations"] + 4
     assert np.abs(mu - ref["mu"]).max() < 20 * 1e-11 and np.abs(mu - seq["mu"]).max() < 100 * 1e-11
     assert abs(res.eng_pol - seq["eng_pol"]) < 1e-8 * abs(seq["eng_pol"])
+
+
+def _colouring(style, n):
+    raw = style.debug_fetch("gs_colouring", np.int32, 2 * n + 3)
+    colour, after, (ncol, rounds, ngroups) = raw[:n], raw[n:2 * n], raw[2 * n:2 * n + 3]
+    return colour, after, int(ncol), int(rounds), int(ngroups)
+
+
+@pytest.mark.parametrize("system", ["water", "fluid"])
+def test_group_coloured_gauss_seidel_is_iteration_for_iteration_the_oracle(style, system):
+    """DEFAULT list-mode Gauss-Seidel (polar_gs_ranked yes, precision mode): the group-coloured sweep on the TMA pair-group
+    kernel with the device-side stop flag.  The oracle replays the colouring the device chose (colour of every atom +
+    in-group order): dipoles after 1, 2, 3 sweeps to 1e-10 relative, the converged run with the SAME iteration count and
+    the dipoles to 1e-10; and against the reference's own order (strictly sequential ranked sweep): same fixed point
+    within 20*precision (BASELINE.json's tolerance for the GS modes), no more iterations than the sequential sweep + 2."""
+    if system == "water":
+        sysm = H.water_box(10)
+        mk, on_device = H.water_style, _water_on_device
+    else:
+        sysm = H.lj_charge_fluid(9)
+        mk = H.fluid_style
+        on_device = lambda s, sy, st, words: _fluid_style_on_device(s, sy, st.g_ewald, words)
+    n = sysm.n
+    kw = dict(polar_cut=12.0, damp_type="exponential", polar_gs_ranked=1, precision=1e-11, max_iterations=200,
+              polar_gamma=1.03)
+    st = mk(sysm, 2.5, 12.0, **kw)
+    words = "damp_type exponential precision 1e-11 max_iterations 200 polar_gamma 1.03 polar_cutoff 12.0"
+    on_device(style, sysm, st, words)
+    res, mu, ef, f = run_system(style, sysm)
+    assert not (res.status & pb.STATUS_DIVERGED)
+    colour, after, ncol, rounds, ngroups = _colouring(style, n)
+    # the colouring is a partition into ncol colours; second members follow a first member of the same colour
+    assert colour.min() >= 0 and colour.max() < ncol and (n + 1) // 2 <= ngroups <= n
+    second = after >= 0
+    assert np.all(colour[second] == colour[after[second]]) and np.all(after[after[second]] == -1)
+    ref = P.polar_rows(sysm, st, colouring=(colour, after, ncol))
+    assert res.iterations == ref["iterations"], (res.iterations, ref["iterations"])
+    assert H.rel_err(mu, ref["mu"]) < TOL
+    assert abs(res.eng_pol - ref["eng_pol"]) < TOL * abs(ref["eng_pol"])
+    seq = P.polar_rows(sysm, mk(sysm, 2.5, 12.0, gs_chunks=0, **kw))
+    assert res.iterations <= seq["iterations"] + 2, (res.iterations, seq["iterations"])
+    assert np.abs(mu - seq["mu"]).max() < 20 * 1e-11
+    assert abs(res.eng_pol - seq["eng_pol"]) < 1e-8 * abs(seq["eng_pol"])
+    # per-sweep parity: fixed number of sweeps (Gauss-Seidel keeps the extra sweep, SURVEY H6)
+    for nsweeps in (1, 3):
+        s2 = pb.PairStyle(device=0)
+        on_device(s2, sysm, st, f"damp_type exponential fixed_iteration yes max_iterations {nsweeps} polar_gamma 1.03 polar_cutoff 12.0")
+        r2, mu2, _, _ = run_system(s2, sysm)
+        c2, a2, nc2, _, _ = _colouring(s2, n)
+        s2.close()
+        assert np.array_equal(c2, colour) and np.array_equal(a2, after)  # the colouring does not depend on the solver keywords
+        kw2 = dict(kw, fixed_iteration=1, max_iterations=nsweeps)
+        ref2 = P.polar_rows(sysm, mk(sysm, 2.5, 12.0, **kw2), colouring=(colour, after, ncol))
+        assert r2.iterations == ref2["iterations"] == nsweeps
+        assert H.rel_err(mu2, ref2["mu"]) < TOL
+
+
+def test_group_coloured_sweep_stop_flag_and_lag_do_not_change_the_result():
+    """the host looks at the device's stop flag one iteration late (the iteration enqueued meanwhile is skipped by every
+    kernel): identical dipoles, iteration counts and energies with and without the lag, in Jacobi and Gauss-Seidel
+    precision modes, and over repeated steps with use_previous."""
+    sysm = H.water_box(8)
+    outs = {}
+    for words in ("polar_gs_ranked no precision 1e-9 max_iterations 300", "precision 1e-11 max_iterations 200 polar_gamma 1.03",
+                  "polar_gs_ranked no precision 1e-9 max_iterations 5"):
+        for lag in (0, 1):
+            s = pb.PairStyle(device=0)
+            _water_on_device(s, sysm, H.water_style(sysm, 2.5, 12.0), words + " damp_type exponential polar_cutoff 12.0 use_previous yes")
+            s.set_option("scf_lag", lag)
+            res, mu, ef, f = run_system(s, sysm)
+            res2, mu2, _, f2 = run_system(s, sysm, mu_in=mu, ago=1)
+            s.close()
+            key = words
+            if key in outs:
+                r0, m0, r20, m20, f20 = outs[key]
+                assert res.iterations == r0.iterations and res2.iterations == r20.iterations
+                assert (res.status & pb.STATUS_DIVERGED) == (r0.status & pb.STATUS_DIVERGED)
+                assert np.array_equal(mu, m0) and np.array_equal(mu2, m20) and np.array_equal(f2, f20)
+                assert res.eng_pol == r0.eng_pol
+            else:
+                outs[key] = (res, mu, res2, mu2, f2)
+    assert outs["polar_gs_ranked no precision 1e-9 max_iterations 5"][0].status & pb.STATUS_DIVERGED
 
 
 def test_exclusions_in_list_mode_match_oracle(style):
