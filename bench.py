@@ -1,22 +1,37 @@
 #!/usr/bin/env python3
 """bench.py -- atom-steps/s (incl. the dipole SCF) of the lj/cut/coul/long/polarization hot path.
 
-Workload (BASELINE.json configs[1]): synthetic polarizable LJ+charge fluid, 32 000 atoms, rho = 0.1 /A^3,
-pair_style lj/cut/coul/long/polarization 2.5 12 fixed_iteration yes max_iterations 30
-damp_type exponential polar_gs_ranked no, dipole-dipole over the neighbor list (polar_cutoff 12).
-A "step" = one compute() call = one pass of the whole hot path (neighbor refresh, LJ+Coulomb+static field,
-30 Jacobi dipole sweeps, polarization forces, reductions); the device structures are rebuilt every
-REBUILD_EVERY steps inside the timed region, as LAMMPS' delay-10 schedule would.
+Workloads = BASELINE.json's configs, selected with --config:
+
+  5 (default, every N): weak-scaled polarizable LJ+charge fluid, 1 000 188 atoms PER GPU (8.0 M on 8 GPUs), rho 0.1/A^3,
+       pair_style lj/cut/coul/long/polarization 2.5 12 fixed_iteration yes max_iterations 30 damp_type exponential
+       polar_gs_ranked no, dipole-dipole over the neighbor list (polar_cutoff 12).  One periodic system cut into N
+       bricks (one process per GPU): ghost positions once per step, ghost dipoles once per sweep.  This is the series
+       the metric "atom-steps/s at 1/2/4/8 B200" is quoted on; the same per-GPU workload at every N makes the driver's
+       v_N / (N v_1) a true weak-scaling efficiency.
+  2: the same fluid and keywords at 32 000 atoms per GPU (round-1 headline; at N = 1 it is ALSO measured by the default
+       run and reported under "also.config2", with its roofline, for continuity)
+  3: rigid water-like box, 255 552 atoms in total (strong scaling over N), precision 1e-11, polar_gs_ranked yes (the
+       reference's default solver: group-coloured Gauss-Seidel sweep), polar_gamma 1.03; at N = 1 also measured by the
+       default run ("also.config3")
+  4: MOF-5 + CO2 supercell (the reference's example cell x 10^3 = 924 000 atoms, 10 atom types, bond topology),
+       damp 2.1304, polar_gs_ranked yes precision 1e-11 -- strong scaling over N
+
+A "step" = one compute() call = one pass of the whole hot path (neighbor refresh, LJ+Coulomb+static field, the dipole
+iterations, polarization forces, reductions); the device structures are rebuilt every REBUILD_EVERY steps inside the timed
+region, as LAMMPS' delay-10 schedule would.
 
   value  : whole-job atom-steps/s with inputs resident in HBM (device pointers through the C ABI)
   e2e    : same metric through the C ABI with HOST buffers (pinned), H2D of x/mu and D2H of f/mu/E inside
-  roofline: dominant kernel k_sweep_cached (one dipole iteration): bytes it must move through HBM per launch
-            (20 B per pair streamed + the atom records once) over the CUDA-event duration of its
-            launches, against MEASURED_PEAKS.json hbm_gbs; SURVEY §8d's every-gather-from-HBM model beside it
+  roofline: dominant kernel k_sweep_group_tma (one dipole iteration; the Gauss-Seidel configs launch it once per colour,
+            8 launches = one iteration): bytes it must move through HBM per iteration (36 B per pair-group row entry
+            streamed + the atom records once) over the CUDA-event duration of an iteration, against
+            MEASURED_PEAKS.json hbm_gbs; SURVEY §8d's every-gather-from-HBM model beside it
   cpu_baseline: the reference binary (oracle/_ref/lmp_serial, 1 core: it is serial by design) on a bounded
-            2048-atom sample of the same fluid, else the oracle port on all host threads
-  N > 1  : ONE periodic system of 32000*N atoms, spatially decomposed into N bricks (one process per GPU):
-            ghost positions once per step, ghost dipoles once per SCF sweep (weak scaling)
+            4000-atom sample of the same fluid (all-pairs dipole semantics: it has no dipole cutoff), with the GPU run of
+            EXACTLY that sample and those semantics beside it ("same_work"); plus the oracle port of the list algorithm
+  N > 1  : before the timed run, a decomposed 32 000-atoms-per-GPU system is compared atom by atom with a single-GPU run
+            of the same global system on rank 0 -> check.mgpu_max_rel_err (must be < 1e-10)
   --impl reference: times that CPU reference arm alone.
 """
 import argparse
@@ -31,6 +46,7 @@ import tempfile
 import threading
 import time
 from pathlib import Path
+from types import SimpleNamespace
 
 import numpy as np
 
@@ -42,12 +58,14 @@ for p in (str(ROOT), str(ROOT / "tests")):
 METRIC = "atom-steps/s incl. dipole SCF"
 UNIT = "atom-steps/s"
 REBUILD_EVERY = 10
-NCELL = 20  # 4*20^3 = 32000 atoms
+NCELL = 20  # config 2: 4*20^3 = 32000 atoms per GPU
+NCELL5 = 63  # config 5: 4*63^3 = 1 000 188 atoms per GPU
 CUT_LJ, CUT_COUL, ITER = 2.5, 12.0, 30
-SAMPLE_NCELL = 8  # 2048-atom sample for the serial reference binary
+SAMPLE_NCELL = 10  # 4000-atom sample for the serial reference binary
 STYLE_WORDS = (f"{CUT_LJ} {CUT_COUL} polar_gs_ranked no fixed_iteration yes max_iterations {ITER} "
                "damp_type exponential")
-
+RANKED_WORDS = "precision 1e-11 max_iterations 200 polar_gamma 1.03 damp_type exponential"
+MOF_CELL = ROOT / "tests" / "golden" / "co2_singlepoint_step0.npz"
 
 PKG = ROOT / "lammps-induced-dipole-polarization-pair-style_b200"
 
@@ -74,14 +92,46 @@ def workloads():
 GRIDS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
 
 
-def workload_config(n_gpus, parallelism):
-    return {"workload": f"synthetic polarizable LJ+charge fluid, {4 * NCELL ** 3} atoms per GPU "
-                        f"({4 * NCELL ** 3 * n_gpus} in total), rho 0.1/A^3, "
-                        f"cut {CUT_LJ}/{CUT_COUL}, fixed_iteration yes max_iterations {ITER}, damp_type exponential, "
-                        f"polar_gs_ranked no, polar_cutoff {CUT_COUL} (neighbor-list dipole sweep)",
-            "atoms_per_gpu": 4 * NCELL ** 3, "atoms_total": 4 * NCELL ** 3 * n_gpus, "sweeps_per_step": ITER,
-            "rebuild_every": REBUILD_EVERY, "parallelism": parallelism,
-            "l2_policy": "working set (neighbor list + radial cache ~600 MB per GPU) exceeds the 126 MB L2"}
+def make_config(cfg, world):
+    """-> namespace(system, style lines, scaling, description) of BASELINE config `cfg` on `world` GPUs"""
+    W = workloads()
+    pg = GRIDS[world]
+    c = SimpleNamespace(id=cfg, pg=pg, molecular=0, coeff=["pair_coeff * * 0.1 3.0"], cut=CUT_COUL, sweeps=None)
+    if cfg in (2, 5):
+        nc = NCELL if cfg == 2 else NCELL5
+        c.sys = W.lj_charge_fluid(nc if world == 1 else tuple(nc * np.array(pg)), seed=12345)
+        c.words = f"{STYLE_WORDS} polar_cutoff {CUT_COUL}"
+        c.scaling = "weak"
+        c.sweeps = ITER
+        c.desc = (f"BASELINE config {cfg}: synthetic polarizable LJ+charge fluid, {4 * nc ** 3} atoms per GPU ({c.sys.n} in total), "
+                  f"rho 0.1/A^3, cut {CUT_LJ}/{CUT_COUL}, fixed_iteration yes max_iterations {ITER}, damp_type exponential, "
+                  f"polar_gs_ranked no, polar_cutoff {CUT_COUL} (neighbor-list dipole sweep)")
+    elif cfg == 3:
+        c.sys = W.water_box(44)
+        c.words = f"{CUT_LJ} {CUT_COUL} {RANKED_WORDS} polar_cutoff {CUT_COUL}"
+        c.coeff = ["pair_coeff 1 1 0.155 3.166", "pair_coeff 2 2 0.0 1.0"]
+        c.scaling = "strong"
+        c.desc = (f"BASELINE config 3: rigid 3-site water-like box, {c.sys.n} atoms in total, rho 0.1/A^3, cut {CUT_LJ}/{CUT_COUL}, "
+                  f"precision 1e-11, polar_gs_ranked yes (group-coloured Gauss-Seidel sweep), polar_gamma 1.03, damp_type exponential, "
+                  f"polar_cutoff {CUT_COUL}")
+    elif cfg == 4:
+        c.sys, c.cut, c.coeff = W.mof_supercell(MOF_CELL, 10)
+        c.words = f"{CUT_LJ} {c.cut} {RANKED_WORDS} damp 2.1304 polar_cutoff {c.cut}"
+        c.molecular = 1
+        c.scaling = "strong"
+        c.desc = (f"BASELINE config 4: MOF-5 + CO2 supercell (reference example cell x 10^3), {c.sys.n} atoms in total, 10 atom types, "
+                  f"bond topology, cut {CUT_LJ}/{c.cut}, zodid no, damp 2.1304, damp_type exponential, polar_gs_ranked yes, "
+                  f"precision 1e-11, polar_gamma 1.03, polar_cutoff {c.cut}")
+    else:
+        raise SystemExit(f"bench.py: unknown --config {cfg}")
+    return c
+
+
+def workload_config(c, n_gpus, parallelism):
+    return {"workload": c.desc, "baseline_config": c.id, "atoms_per_gpu": c.sys.n // n_gpus, "atoms_total": c.sys.n,
+            "sweeps_per_step": c.sweeps if c.sweeps else "to convergence", "rebuild_every": REBUILD_EVERY,
+            "parallelism": parallelism,
+            "l2_policy": "working set (neighbor list + radial cache, ~19 KB per atom) exceeds the 126 MB L2"}
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -148,12 +198,19 @@ run {steps}
 """)
 
 
-def run_reference_binary(steps, warmup):
-    """Times oracle/_ref/lmp_serial (the repaired, otherwise unmodified reference) on the 2048-atom sample."""
+def sample_description(n):
+    return (f"{n}-atom sample of the BASELINE config 2/5 fluid (same density 0.1/A^3, cut {CUT_LJ}/{CUT_COUL}, fixed_iteration yes "
+            f"max_iterations {ITER}, damp_type exponential, polar_gs_ranked no), dipole-dipole over ALL minimum-image pairs: the "
+            "reference has no dipole cutoff and is O(N^2) with a dense 3Nx3N matrix (72 N^2 bytes), so it cannot run the GPU arm's "
+            "sizes")
+
+
+def run_reference_binary(steps, warmup, ncell=SAMPLE_NCELL):
+    """Times oracle/_ref/lmp_serial (the repaired, otherwise unmodified reference) on the sample."""
     lmp = ROOT / "oracle" / "_ref" / "lmp_serial"
     if not lmp.exists():
         return None
-    sysm = workloads().lj_charge_fluid(SAMPLE_NCELL)
+    sysm = workloads().lj_charge_fluid(ncell)
     work = Path(tempfile.mkdtemp(prefix="polb200_refarm_"))
     try:
         write_lammps_case(work, sysm, None, steps + warmup)
@@ -169,14 +226,18 @@ def run_reference_binary(steps, warmup):
         nsteps = steps + warmup
         # run N = N+1 force evaluations (setup + N steps); the Pair timer covers the N steps
         per_step = pair_s / max(nsteps, 1)
+        epol = None
+        rows = re.findall(r"^\s*(\d+)\s+(-?[0-9.eE+-]+)\s+(-?[0-9.eE+-]+)\s+(-?[0-9.eE+-]+)\s+(-?[0-9.eE+-]+)\s*$", log, flags=re.M)
+        if rows:
+            epol = float(rows[0][4])  # step 0
         return {"atoms": sysm.n, "s_per_step": per_step, "value": sysm.n / per_step, "wall_s": wall,
-                "steps": nsteps}
+                "steps": nsteps, "epol_step0": epol}
     finally:
         shutil.rmtree(work, ignore_errors=True)
 
 
 def run_port_sample(nthreads=0, target_s=10.0):
-    """Oracle port (truncated list algorithm, OpenMP) on a row sample of the full 32k workload."""
+    """Oracle port (truncated list algorithm, OpenMP) on a row sample of the 32k-atom fluid."""
     import polhelpers as H
     from oracle import polref as P
     sysm = H.lj_charge_fluid(NCELL)
@@ -197,20 +258,24 @@ def reference_arm(args):
     ref = run_reference_binary(args.steps, args.warmup)
     if ref and "value" in ref:
         kind, cores, value = "reference", 1, ref["value"]
-        sample = (f"oracle/_ref/lmp_serial (repaired reference, serial by design) on a {ref['atoms']}-atom sample of the "
-                  f"same fluid (same density/cutoffs/keywords), {ref['steps']} MD steps, Pair timer; the reference is "
-                  f"O(N^2) with a dense 3Nx3N matrix, so its per-atom cost at 32000 atoms would be ~{(4 * NCELL ** 3 / ref['atoms']):.0f}x higher "
-                  "and needs 74 GB")
+        natoms = ref["atoms"]
+        sample = (f"oracle/_ref/lmp_serial (repaired reference, serial by design), {ref['steps']} MD steps, Pair timer, on a "
+                  + sample_description(natoms))
         ms = ref["s_per_step"] * 1e3
     else:
         port = run_port_sample()
         kind, cores, value = "port", port["threads"], port["value"]
-        sample = f"oracle port rows sample: {port['rows']} of 32000 atoms, polarization stages only"
+        natoms = port["rows"]
+        sample = (f"oracle port (list algorithm with polar_cutoff {CUT_COUL}, OpenMP), rows sample: {port['rows']} of the 32000 atoms "
+                  "of BASELINE config 2, polarization stages only")
         ms = port["seconds"] * 1e3
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args.gpus, "cpu"),
+            "config": {"workload": sample, "atoms_total": natoms, "atoms_per_gpu": None, "parallelism": "cpu, 1 core",
+                       "same_config_as_gpu_arm": False,
+                       "note": "the GPU arm's headline runs 1 000 188 atoms per GPU with the polar_cutoff extension; its line "
+                               "carries cpu_baseline.same_work = the GPU timed on exactly this sample with these semantics"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.time() - t0}
@@ -220,19 +285,258 @@ def reference_arm(args):
 # ----------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------
-def make_style(pb, sysm, device):
+def make_style(pb, c, device, words=None):
     # g_ewald as `kspace_style ewald 1e-4` would set it: the product's own Ewald::init (polb200_ewald_init)
     ew = pb.Ewald(device=device)
-    g = ew.init(1e-4, sysm.q, CUT_COUL, sysm.boxlo, sysm.boxhi).g_ewald
+    g = ew.init(1e-4, c.sys.q, c.cut, c.sys.boxlo, c.sys.boxhi).g_ewald
     ew.close()
     s = pb.PairStyle(device=device)
-    s.set_ntypes(2)
-    s.command(f"pair_style lj/cut/coul/long/polarization {STYLE_WORDS} polar_cutoff {CUT_COUL}")
-    s.command("pair_coeff 1 1 0.1 3.0")
-    s.command("pair_coeff 2 2 0.1 3.0")
-    s.init(g_ewald=g, molecular=0)
-    s.set_box(sysm.boxlo, sysm.boxhi)
+    s.set_ntypes(int(c.sys.ntypes))
+    s.command("pair_style lj/cut/coul/long/polarization " + (words or c.words))
+    for line in c.coeff:
+        s.command(line)
+    s.init(g_ewald=g, molecular=c.molecular)
+    s.set_box(c.sys.boxlo, c.sys.boxhi)
     return s
+
+
+class Run:
+    """one workload on this rank: owned atoms, device-resident and pinned host copies"""
+
+    def __init__(self, pb, torch, dist, c, rank, world, local, comm=True):
+        self.pb, self.torch, self.dist, self.c = pb, torch, dist, c
+        self.rank, self.world, self.local = rank, world, local
+        g = c.sys
+        self.style = make_style(pb, c, local)
+        dev = torch.device("cuda", local)
+        if world > 1 and comm:
+            box = [pb.comm_create_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            self.style.comm_init(rank, world, box[0], c.pg)
+            lo, hi = self.style.subdomain()
+            own = np.nonzero(np.all((g.x >= lo) & (g.x < hi), axis=1))[0]
+        else:
+            own = np.arange(g.n)
+        self.own = own
+        n = self.n = len(own)
+        take = lambda a: np.ascontiguousarray(a[own])
+        self.h = dict(x=take(g.x), q=take(g.q), type=take(g.type), alpha=take(g.alpha), tag=take(g.tag),
+                      molecule=take(g.molecule))
+        self.maxspecial = 0
+        if getattr(g, "special", None) is not None:
+            self.h["nspecial"], self.h["special"] = take(g.nspecial), take(g.special)
+            self.maxspecial = g.special.shape[1]
+        # device-resident inputs
+        f64, i32 = torch.float64, torch.int32
+        t = self.t = {k: torch.tensor(v, dtype=f64 if v.dtype == np.float64 else i32, device=dev).contiguous()
+                      for k, v in self.h.items()}
+        for k in ("mu", "f", "ef_static"):
+            t[k] = torch.zeros((n, 3), dtype=f64, device=dev)
+        self.ptrs = {k: v.data_ptr() for k, v in t.items()}
+        torch.cuda.synchronize()
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def step_dev(self, k):
+        self.t["f"].zero_()
+        self.torch.cuda.synchronize()
+        return self.style.compute_device(self.n, self.ptrs, eflag=1, vflag=2, ago=k % REBUILD_EVERY, maxspecial=self.maxspecial)
+
+    def pin_host(self):
+        torch = self.torch
+        self.p = {k: torch.tensor(self.h["x"] if k == "x" else np.zeros((self.n, 3)), dtype=torch.float64).pin_memory().numpy()
+                  for k in ("x", "mu", "f", "ef")}
+
+    def step_host(self, k):
+        p, h = self.p, self.h
+        p["f"][:] = 0.0
+        return self.style.compute(p["x"], h["q"], h["type"], h["alpha"], p["mu"], p["f"], molecule=h["molecule"], tag=h["tag"],
+                                  ef_static=p["ef"], nspecial=h.get("nspecial"), special=h.get("special"), eflag=1, vflag=2,
+                                  ago=k % REBUILD_EVERY)
+
+    def measure(self, steps, warmup, clocks=False, e2e=True):
+        """-> dict of this rank's measurements (times are max-reduced over the ranks by the caller)"""
+        pb, style = self.pb, self.style
+        for k in range(warmup):
+            res = self.step_dev(k)
+        polar_pairs = int(style.debug_fetch("polar_pairs", np.uint64, 1)[0])
+        group_stats = style.debug_fetch("group_stats", np.float64, 4)
+        comm_stats = style.debug_fetch("comm_stats", np.float64, 5)
+        style.set_option("time_sweeps", 1.0)
+        style.launch_count(reset=True)
+        sampler = ClockSampler(self.local) if clocks and self.rank == 0 else None
+        if sampler:
+            sampler.start()
+        self.barrier()
+        t0 = time.perf_counter()
+        dev_ms, stage, iters = 0.0, np.zeros(5), 0
+        for k in range(steps):
+            res = self.step_dev(k)
+            dev_ms += res.ms_total
+            iters += res.iterations
+            stage += [res.ms_neigh, res.ms_pair, res.ms_scf, res.ms_force, res.ms_total]
+        self.barrier()
+        wall = time.perf_counter() - t0
+        out = SimpleNamespace(wall=wall, launches=style.launch_count(), sweep=style.debug_fetch("sweep_timing", np.float64, 2),
+                              clocks=sampler.stop() if sampler else None, eng_pol=res.eng_pol, res=res, stage=stage / steps,
+                              dev_ms=dev_ms / steps, iterations=iters / steps, polar_pairs=polar_pairs, group_stats=group_stats,
+                              comm_stats=comm_stats, wall_e2e=None)
+        style.set_option("time_sweeps", 0.0)
+        if e2e:
+            # ---- end to end through the C ABI with host (pinned) buffers ----
+            self.pin_host()
+            for k in range(max(1, warmup // 2)):
+                self.step_host(k)
+            self.barrier()
+            t1 = time.perf_counter()
+            for k in range(steps):
+                r2 = self.step_host(k)
+            self.barrier()
+            out.wall_e2e = time.perf_counter() - t1
+            assert abs(r2.eng_pol - out.eng_pol) <= 1e-9 * abs(out.eng_pol), (r2.eng_pol, out.eng_pol)
+        return out
+
+    def reduce(self, m):
+        """times: max over ranks; atoms / energy / pairs: sums (per-rank partials by LAMMPS convention)"""
+        torch, dist = self.torch, self.dist
+        dev = torch.device("cuda", self.local)
+        times = torch.tensor([m.wall, m.wall_e2e or 0.0], dtype=torch.float64, device=dev)
+        sums = torch.tensor([float(self.n), m.eng_pol, float(m.polar_pairs)], dtype=torch.float64, device=dev)
+        if self.world > 1:
+            dist.all_reduce(times, op=dist.ReduceOp.MAX)
+            dist.all_reduce(sums)
+        m.wall, m.wall_e2e = float(times[0]), float(times[1]) or None
+        m.total_atoms, m.eng_pol_total = int(sums[0]), float(sums[1])
+        return m
+
+    def roofline(self, m, peaks, traffic_file=None):
+        n, world = self.n, self.world
+        peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+        sweep_ms = float(m.sweep[0]) / max(float(m.sweep[1]), 1.0)
+        # Bytes one iteration of the dominant kernel must move through HBM (DESIGN.md §4).  k_sweep_group_tma: one warp per
+        # pair group (two cell-row neighbours); per group-row entry it streams, exactly once, 4 B of neighbour index + 32 B
+        # of cached radial scalars {s1a,s2a,s1b,s2b}; the 32-B position and dipole records of the owned+ghost atoms are
+        # gathered hundreds of times each but from L2/L1, so they count once; plus E_static in and the new dipole out per
+        # owned atom.  (Per-atom fallback kernel k_sweep_cached: 20 B per pair instead.)
+        nghost = int(m.res.nghost)
+        grouped = bool(m.group_stats[3]) and m.group_stats[1] > 0
+        entries = float(m.group_stats[1]) if grouped else float(m.polar_pairs)
+        alg_bytes = (36.0 if grouped else 20.0) * entries + 64.0 * (n + nghost) + 64.0 * n
+        achieved = alg_bytes / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else None
+        kernel = "k_sweep_group_tma" if grouped else "k_sweep_cached"
+        gs = self.c.sweeps is None
+        traffic = None
+        if traffic_file is not None and traffic_file.exists() and world == 1:
+            t = json.loads(traffic_file.read_text())
+            for e in (t if isinstance(t, list) else [t]):
+                if e.get("kernel") == kernel and e.get("atoms") == n and bool(e.get("gauss_seidel", False)) == gs:
+                    traffic = e["dram_bytes_per_launch"] * (e.get("launches_per_iteration", 1))
+        survey_bytes = 52.0 * m.polar_pairs + 104.0 * n  # SURVEY §8d: every gather charged to HBM
+        return {"bound": "hbm",
+                "kernel": kernel + (" (one dipole iteration = one launch per colour of the group-coloured Gauss-Seidel sweep + commits)"
+                                    if gs else " (one dipole iteration over the neighbor list = one launch)"),
+                "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs if achieved else None,
+                "traffic": traffic,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650",
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "bytes_model": ("36 B per group-row entry streamed (index + cached radial scalars of both members)"
+                                if grouped else "20 B/pair streamed (index + cached radial scalars)") +
+                               " + 64 B per owned+ghost atom (position and dipole records, read once) + 64 B per "
+                               "owned atom (E_static in, dipole out)",
+                "group_row_entries": entries if grouped else None,
+                "pairs_in_cutoff": m.polar_pairs, "launch_ms": sweep_ms,
+                "bytes_per_pair": alg_bytes / max(m.polar_pairs, 1),
+                "gpairs_per_s": m.polar_pairs / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else None,
+                "survey_8d_model": {"bytes": survey_bytes,
+                                    "achieved": survey_bytes / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else None,
+                                    "note": "52 B/pair + 104 B/atom with every neighbour gather charged to HBM; "
+                                            "exceeds the HBM peak because the gathers are L2/L1 hits"}}
+
+    def close(self):
+        self.style.close()
+
+
+def summary(run, m, steps, peaks):
+    """compact record of a secondary workload measured in the same process"""
+    return {"workload": run.c.desc, "value": m.total_atoms * steps / m.wall, "unit": UNIT, "ms_per_step": m.wall / steps * 1e3,
+            "e2e_value": m.total_atoms * steps / m.wall_e2e if m.wall_e2e else None,
+            "iterations_per_step": m.iterations, "us_per_dipole_iteration": float(m.sweep[0]) / max(float(m.sweep[1]), 1.0) * 1e3,
+            "stage_ms": {"neigh_refresh": m.stage[0], "pair_field": m.stage[1], "scf": m.stage[2], "pol_force": m.stage[3]},
+            "gpu_launches": int(m.launches), "roofline": run.roofline(m, peaks, ROOT / "profiles" / "ncu_traffic.json"),
+            "check": {"eng_pol": m.eng_pol_total}}
+
+
+def mgpu_parity(pb, torch, dist, rank, world, local):
+    """decomposed run of a 32 000-atoms-per-GPU fluid (converged Jacobi + one fixed-sweep run) against the single-GPU run
+    of the same global system on rank 0: max relative error of dipoles, static fields and forces over ALL atoms"""
+    c = make_config(2, world)
+    worst = 0.0
+    detail = {}
+    for label, words in (("fixed30", c.words), ("ranked", f"{CUT_LJ} {CUT_COUL} {RANKED_WORDS} polar_cutoff {CUT_COUL}")):
+        c.words = words
+        run = Run(pb, torch, dist, c, rank, world, local)
+        run.pin_host()
+        for k in range(2):  # a rebuild step and a step on stale lists
+            r = run.step_host(k)
+        parts = dict(own=run.own, mu=run.p["mu"].copy(), ef=run.p["ef"].copy(), f=run.p["f"].copy(), it=r.iterations)
+        allp = [None] * world if rank == 0 else None
+        dist.gather_object(parts, allp, dst=0)
+        run.close()
+        if rank == 0:
+            g = c.sys
+            MU, EF, F = np.zeros((g.n, 3)), np.zeros((g.n, 3)), np.zeros((g.n, 3))
+            for p_ in allp:
+                MU[p_["own"]], EF[p_["own"]], F[p_["own"]] = p_["mu"], p_["ef"], p_["f"]
+            one = Run(pb, torch, dist, c, 0, 1, local, comm=False)
+            one.pin_host()
+            for k in range(2):
+                r1 = one.step_host(k)
+            rel = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())
+            e = dict(mu=rel(MU, one.p["mu"]), ef=rel(EF, one.p["ef"]), f=rel(F, one.p["f"]),
+                     iterations=[int(allp[0]["it"]), int(r1.iterations)])
+            one.close()
+            detail[label] = e
+            if label == "fixed30":  # Jacobi: per-iteration parity; the Gauss-Seidel colouring differs between decompositions
+                worst = max(worst, e["mu"], e["ef"], e["f"])
+                assert e["iterations"][0] == e["iterations"][1]
+            else:
+                worst = max(worst, e["ef"])
+                detail[label]["mu_abs"] = float(np.abs(MU - one.p["mu"]).max())
+                assert detail[label]["mu_abs"] < 20 * 1e-11, detail  # tolerance parity of the GS modes (BASELINE.json)
+        dist.barrier()
+    if rank == 0:
+        assert worst < 1e-10, f"multi-GPU parity failed: {detail}"
+    return worst, detail
+
+
+def same_work_on_gpu(pb, local, ref):
+    """the reference arm's sample with the reference's semantics (all-pairs dipoles, no polar_cutoff) on the GPU"""
+    c = make_config(2, 1)
+    c.sys = workloads().lj_charge_fluid(SAMPLE_NCELL)
+    s = make_style(pb, c, local, words=STYLE_WORDS)
+    n = c.sys.n
+    mu, f, ef = np.zeros((n, 3)), np.zeros((n, 3)), np.zeros((n, 3))
+    h = [np.ascontiguousarray(a) for a in (c.sys.x, c.sys.q, c.sys.type, c.sys.alpha)]
+    for k in range(3):
+        s.compute(h[0], h[1], h[2], h[3], mu, f, ef_static=ef, ago=0)
+    t0 = time.perf_counter()
+    nrep = 10
+    for k in range(nrep):
+        mu[:] = 0.0
+        r = s.compute(h[0], h[1], h[2], h[3], mu, f, ef_static=ef, ago=0 if k % REBUILD_EVERY == 0 else 1)
+    dt = (time.perf_counter() - t0) / nrep
+    s.close()
+    out = {"atoms": n, "gpu_ms_per_step": dt * 1e3, "gpu_value": n / dt, "semantics": "exact mode: all minimum-image pairs, host buffers",
+           "gpu_eng_pol": r.eng_pol}
+    if ref:
+        out["speedup_vs_reference"] = (n / dt) / ref["value"]
+        if ref.get("epol_step0") is not None:
+            out["reference_eng_pol_step0"] = ref["epol_step0"]
+    return out
 
 
 def gpu_arm(args):
@@ -248,205 +552,89 @@ def gpu_arm(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    # N GPUs: ONE periodic system of 32000*N atoms cut into N bricks (spatial decomposition, weak scaling);
-    # every rank generates the same global system and keeps the atoms of its own brick
-    pg = GRIDS.get(world)
-    if pg is None:
+    if world not in GRIDS:
         raise SystemExit(f"bench.py: no brick grid defined for {world} GPUs (use 1, 2, 4 or 8)")
-    gsys = workloads().lj_charge_fluid(NCELL if world == 1 else tuple(NCELL * np.array(pg)), seed=12345)
-    style = make_style(pb, gsys, local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        box = [pb.comm_create_id() if rank == 0 else None]
-        dist.broadcast_object_list(box, src=0)
-        style.comm_init(rank, world, box[0], pg)
-        lo, hi = style.subdomain()
-        own = np.nonzero(np.all((gsys.x >= lo) & (gsys.x < hi), axis=1))[0]
+    peaks = {}
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peaks = json.loads(pk.read_text())
+
+    # multi-GPU parity before the timed run (every rank takes part)
+    mgpu = None
+    if world > 1 and not args.no_parity:
+        mgpu = mgpu_parity(pb, torch, dist, rank, world, local)
+
+    c = make_config(args.config, world)
+    run = Run(pb, torch, dist, c, rank, world, local)
+    n = run.n
+    m = run.reduce(run.measure(args.steps, args.warmup, clocks=True))
+    style = run.style
+    comm_stats = m.comm_stats
+
+    also = {}
+    if world == 1 and args.config == 5 and not args.no_also:
+        run.close()
+        run_alive = False
+        for cfg in (2, 3):
+            r2 = Run(pb, torch, dist, make_config(cfg, 1), rank, 1, local)
+            m2 = r2.reduce(r2.measure(args.steps, args.warmup))
+            also[f"config{cfg}"] = summary(r2, m2, args.steps, peaks)
+            r2.close()
     else:
-        own = np.arange(gsys.n)
-
-    class Owned:
-        pass
-    sysm = Owned()
-    sysm.x, sysm.q, sysm.type, sysm.alpha, sysm.tag = (np.ascontiguousarray(gsys.x[own]), np.ascontiguousarray(gsys.q[own]),
-                                                       np.ascontiguousarray(gsys.type[own]), np.ascontiguousarray(gsys.alpha[own]),
-                                                       np.ascontiguousarray(gsys.tag[own]))
-    n = sysm.n = len(own)
-
-    # device-resident inputs
-    t_x = torch.tensor(sysm.x, dtype=torch.float64, device=dev).contiguous()
-    t_q = torch.tensor(sysm.q, dtype=torch.float64, device=dev)
-    t_type = torch.tensor(sysm.type, dtype=torch.int32, device=dev)
-    t_alpha = torch.tensor(sysm.alpha, dtype=torch.float64, device=dev)
-    t_tag = torch.tensor(sysm.tag, dtype=torch.int32, device=dev)
-    t_mu = torch.zeros((n, 3), dtype=torch.float64, device=dev)
-    t_f = torch.zeros((n, 3), dtype=torch.float64, device=dev)
-    t_ef = torch.zeros((n, 3), dtype=torch.float64, device=dev)
-    ptrs = dict(x=t_x.data_ptr(), q=t_q.data_ptr(), type=t_type.data_ptr(), alpha=t_alpha.data_ptr(),
-                tag=t_tag.data_ptr(), mu=t_mu.data_ptr(), f=t_f.data_ptr(), ef_static=t_ef.data_ptr())
-    torch.cuda.synchronize()
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def step_dev(k):
-        t_f.zero_()
-        torch.cuda.synchronize()
-        return style.compute_device(n, ptrs, eflag=1, vflag=2, ago=k % REBUILD_EVERY)
-
-    # ---- resident-in-HBM throughput ----
-    for k in range(args.warmup):
-        res = step_dev(k)
-    polar_pairs = int(style.debug_fetch("polar_pairs", np.uint64, 1)[0])
-    group_stats = style.debug_fetch("group_stats", np.float64, 4)
-    comm_stats = style.debug_fetch("comm_stats", np.float64, 5)
-    pb.lib().polb200_set_option(style._h, b"time_sweeps", 1.0)
-    style.launch_count(reset=True)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    barrier()
-    t0 = time.perf_counter()
-    dev_ms = 0.0
-    stage = np.zeros(5)
-    for k in range(args.steps):
-        res = step_dev(k)
-        dev_ms += res.ms_total
-        stage += [res.ms_neigh, res.ms_pair, res.ms_scf, res.ms_force, res.ms_total]
-    barrier()
-    wall = time.perf_counter() - t0
-    launches = style.launch_count()
-    sweep = style.debug_fetch("sweep_timing", np.float64, 2)
-    pb.lib().polb200_set_option(style._h, b"time_sweeps", 0.0)
-    clocks = sampler.stop() if rank == 0 else None
-    eng_pol = res.eng_pol
-
-    # ---- end to end through the C ABI with host (pinned) buffers ----
-    h_x = torch.tensor(sysm.x, dtype=torch.float64).pin_memory().numpy()
-    h_mu = torch.zeros((n, 3), dtype=torch.float64).pin_memory().numpy()
-    h_f = torch.zeros((n, 3), dtype=torch.float64).pin_memory().numpy()
-    h_ef = torch.zeros((n, 3), dtype=torch.float64).pin_memory().numpy()
-    h_q = np.ascontiguousarray(sysm.q)
-    h_type = np.ascontiguousarray(sysm.type)
-    h_alpha = np.ascontiguousarray(sysm.alpha)
-    h_tag = np.ascontiguousarray(sysm.tag)
-
-    def step_host(k):
-        h_f[:] = 0.0
-        return style.compute(h_x, h_q, h_type, h_alpha, h_mu, h_f, tag=h_tag, ef_static=h_ef, eflag=1, vflag=2,
-                             ago=k % REBUILD_EVERY)
-
-    for k in range(max(1, args.warmup // 2)):
-        step_host(k)
-    barrier()
-    t1 = time.perf_counter()
-    for k in range(args.steps):
-        r2 = step_host(k)
-    barrier()
-    wall_e2e = time.perf_counter() - t1
-    assert abs(r2.eng_pol - eng_pol) <= 1e-9 * abs(eng_pol)
-
-    # max over ranks (times), sum over ranks (atoms, energy: per-rank partials by LAMMPS convention)
-    times = torch.tensor([wall, wall_e2e], dtype=torch.float64, device=dev)
-    sums = torch.tensor([float(n), eng_pol, float(polar_pairs)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-        dist.all_reduce(sums)
-    wall, wall_e2e = float(times[0]), float(times[1])
-    eng_pol_total = float(sums[1])
+        run_alive = True
 
     if rank == 0:
-        total_atoms = int(sums[0])
-        assert total_atoms == gsys.n
-        value = total_atoms * args.steps / wall
-        e2e_value = total_atoms * args.steps / wall_e2e
-        peaks = {}
-        pk = ROOT / "MEASURED_PEAKS.json"
-        if pk.exists():
-            peaks = json.loads(pk.read_text())
-        peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
-        sweep_ms = float(sweep[0]) / max(float(sweep[1]), 1.0)
-        # Bytes one launch of the dominant kernel must move through HBM.  Default kernel
-        # k_sweep_group_tma: one warp per pair group (two cell-row neighbours); per group-row entry it streams,
-        # exactly once, 4 B of neighbour index + 32 B of cached radial scalars {s1a,s2a,s1b,s2b}; the 32-B position
-        # and dipole records of the owned+ghost atoms are gathered hundreds of times each but from L2/L1, so they
-        # count once; plus E_static in and the new dipole out per owned atom.  (Per-atom fallback kernel
-        # k_sweep_cached: 20 B per pair instead.)
-        nghost = int(res.nghost)
-        grouped = bool(group_stats[3]) and group_stats[1] > 0
-        entries = float(group_stats[1]) if grouped else float(polar_pairs)
-        alg_bytes = (36.0 if grouped else 20.0) * entries + 64.0 * (n + nghost) + 64.0 * n
-        achieved = alg_bytes / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else None
-        # measured DRAM traffic of the same kernel on the same workload (one `ncu --set full` capture, per launch)
-        traffic = None
-        tf = ROOT / "profiles" / "ncu_traffic.json"
-        if tf.exists() and world == 1:
-            t = json.loads(tf.read_text())
-            if t.get("kernel") == ("k_sweep_group_tma" if grouped else "k_sweep_cached") and t.get("atoms") == n:
-                traffic = t["dram_bytes_per_launch"]
-        # SURVEY §8d's matrix-free model (every gather charged to HBM): 52 B per pair + 104 B per atom
-        survey_bytes = 52.0 * polar_pairs + 104.0 * n
+        assert m.total_atoms == c.sys.n
+        value = m.total_atoms * args.steps / m.wall
+        e2e_value = m.total_atoms * args.steps / m.wall_e2e
+        roof = run.roofline(m, peaks, ROOT / "profiles" / "ncu_traffic.json")
         # CPU baseline on a bounded sample (rank 0, N=1 only)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             ref = run_reference_binary(1, 1)
             if ref and "value" in ref:
                 cpu = {"value": ref["value"], "unit": UNIT, "cores": 1, "kind": "reference",
-                       "sample": f"oracle/_ref/lmp_serial on a {ref['atoms']}-atom sample of the same fluid, "
-                                 f"{ref['steps']} steps, {ref['s_per_step']:.3f} s/step (reference is O(N^2): ~"
-                                 f"{4 * NCELL ** 3 // ref['atoms']}x more per atom at 32000 atoms)"}
+                       "sample": f"oracle/_ref/lmp_serial, {ref['steps']} steps, {ref['s_per_step']:.3f} s/step, on a "
+                                 + sample_description(ref["atoms"])}
+                cpu["same_work"] = same_work_on_gpu(pb, local, ref)
             port = run_port_sample(target_s=8.0)
             cpu_port = {"value": port["value"], "unit": UNIT, "cores": port["threads"], "kind": "port",
-                        "sample": f"oracle port (list algorithm, OpenMP), {port['rows']} of 32000 rows, polarization stages"}
+                        "sample": f"oracle port (list algorithm with polar_cutoff {CUT_COUL}, OpenMP), {port['rows']} of the 32000 rows "
+                                  "of BASELINE config 2, polarization stages"}
             if cpu is None:
                 cpu = cpu_port
             else:
                 cpu["port"] = cpu_port
+        pg = c.pg
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(world, "single" if world == 1 else
+            "warmup": args.warmup, "ms_per_step": m.wall / args.steps * 1e3, "higher_is_better": True,
+            "scaling": c.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(c, world, "single" if world == 1 else
                                       f"spatial decomposition, {pg[0]}x{pg[1]}x{pg[2]} bricks, one process per GPU; ghost positions "
-                                      f"once per step (NCCL), ghost dipoles once per sweep ("
+                                      f"once per step, ghost dipoles once per sweep ("
                                       + ("stored by the sweep kernel into peer memory over NVLink + signal/wait barrier"
                                          if int(comm_stats[3]) else "NCCL send/recv") + ")"),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 48 * n, "d2h_bytes_per_step": 72 * n + 192,
-                    "ms_per_step": wall_e2e / args.steps * 1e3},
-            "gpu_launches": int(launches),
-            "us_per_dipole_iteration": sweep_ms * 1e3,
-            "device_ms_per_step": dev_ms / args.steps,
-            "stage_ms": {"neigh_refresh": stage[0] / args.steps, "pair_field": stage[1] / args.steps,
-                         "scf": stage[2] / args.steps, "pol_force": stage[3] / args.steps},
-            "roofline": {"bound": "hbm", "kernel": ("k_sweep_group_tma" if grouped else "k_sweep_cached") +
-                                                    " (one dipole iteration over the neighbor list)",
-                         "achieved": achieved, "peak": peak_gbs,
-                         "unit": "GB/s", "frac": achieved / peak_gbs if achieved else None, "traffic": traffic,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650",
-                         "algorithmic_bytes_per_launch": alg_bytes,
-                         "bytes_model": ("36 B per group-row entry streamed (index + cached radial scalars of both members)"
-                                         if grouped else "20 B/pair streamed (index + cached radial scalars)") +
-                                        " + 64 B per owned+ghost atom (position and dipole records, read once) + 64 B per "
-                                        "owned atom (E_static in, dipole out)",
-                         "group_row_entries": entries if grouped else None,
-                         "pairs_in_cutoff": polar_pairs, "launch_ms": sweep_ms,
-                         "gpairs_per_s": polar_pairs / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else None,
-                         "survey_8d_model": {"bytes": survey_bytes,
-                                             "achieved": survey_bytes / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else None,
-                                             "note": "52 B/pair + 104 B/atom with every neighbour gather charged to HBM; "
-                                                     "exceeds the HBM peak because the gathers are L2/L1 hits"}},
-            "cpu_baseline": cpu, "clocks": clocks,
+                    "ms_per_step": m.wall_e2e / args.steps * 1e3},
+            "gpu_launches": int(m.launches),
+            "us_per_dipole_iteration": roof["launch_ms"] * 1e3,
+            "iterations_per_step": m.iterations,
+            "device_ms_per_step": m.dev_ms,
+            "stage_ms": {"neigh_refresh": m.stage[0], "pair_field": m.stage[1], "scf": m.stage[2], "pol_force": m.stage[3]},
+            "roofline": roof,
+            "cpu_baseline": cpu, "clocks": m.clocks,
             "halo": None if world == 1 else {"rank0_owned": n, "rank0_send_slots": int(comm_stats[0]),
                                              "rank0_ghosts": int(comm_stats[1]), "bytes_per_sweep_rank0": 32 * int(comm_stats[0]),
+                                             "model_24B_x_ghosts": 24 * int(comm_stats[1]),
                                              "peer_push": bool(int(comm_stats[3]))},
-            "check": {"eng_pol": eng_pol_total, "iterations": res.iterations},
+            "check": {"eng_pol": m.eng_pol_total, "iterations": m.res.iterations,
+                      "mgpu_max_rel_err": mgpu[0] if mgpu else None, "mgpu_detail": mgpu[1] if mgpu else None},
+            "also": also or None,
         }
         print(json.dumps(line))
-    style.close()
+    if run_alive:
+        run.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -454,10 +642,13 @@ def gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--config", type=int, default=5, choices=[2, 3, 4, 5])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the multi-GPU parity stage (N > 1)")
+    ap.add_argument("--no-also", action="store_true", help="N = 1: skip the secondary measurements of configs 2 and 3")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

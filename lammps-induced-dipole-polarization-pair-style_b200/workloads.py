@@ -59,3 +59,32 @@ def water_box(nmol_side, seed=2, rho=0.1):
     alpha = np.where(typ == 1, 0.837, 0.496)
     mol = np.repeat(np.arange(1, nmol + 1, dtype=np.int32), 3)
     return _bundle(x, q, typ, mol, alpha, [L, L, L], 2)
+
+
+def mof_supercell(cell_npz, R):
+    """BASELINE config 4 shape: the reference's MOF-5 + CO2 example cell (924 atoms, 10 atom types, bond topology as special
+    lists, 101 molecules; the arrays of `cell_npz` as dumped from the reference run, tests/golden/co2_singlepoint_step0.npz)
+    replicated R x R x R like LAMMPS `replicate` would (new atom ids and molecule ids per image).  Returns (system,
+    cut_coul, pair_coeff lines)."""
+    fx = dict(np.load(cell_npz, allow_pickle=False))
+    n0 = fx["x"].shape[0]
+    prd = fx["boxhi"] - fx["boxlo"]
+    nmol0 = int(fx["molecule"].max())
+    xs, tags, mols, specs = [], [], [], []
+    r = 0
+    for ix in range(R):
+        for iy in range(R):
+            for iz in range(R):
+                xs.append(fx["x"] - fx["boxlo"] + np.array([ix, iy, iz]) * prd)
+                tags.append(fx["tag"] + r * n0)
+                mols.append(np.where(fx["molecule"] > 0, fx["molecule"] + r * nmol0, 0))
+                specs.append(np.where(fx["special"] > 0, fx["special"] + r * n0, 0))
+                r += 1
+    rep = R ** 3
+    sysm = SimpleNamespace(x=np.ascontiguousarray(np.concatenate(xs)), q=np.tile(fx["q"], rep),
+                           type=np.tile(fx["type"], rep).astype(np.int32), alpha=np.tile(fx["alpha"], rep),
+                           tag=np.concatenate(tags).astype(np.int32), molecule=np.concatenate(mols).astype(np.int32),
+                           nspecial=np.ascontiguousarray(np.tile(fx["nspecial"], (rep, 1)).astype(np.int32)),
+                           special=np.ascontiguousarray(np.concatenate(specs).astype(np.int32)), boxlo=np.zeros(3),
+                           boxhi=prd * R, ntypes=int(fx["ntypes"]), n=n0 * rep, periodic=np.ones(3, dtype=np.int32))
+    return sysm, 12.8345, str(fx["pair_coeff"]).splitlines()

@@ -70,32 +70,9 @@ def sample_check(x, q, alpha, mu, ef, boxlen, samples, rng, mol=None):
 
 
 def mof_supercell(R):
-    """BASELINE config 4 shape: the reference's MOF-5 + CO2 example cell (tests/golden/co2_singlepoint_step0.npz: 924 atoms,
-    10 atom types, bond topology as special lists, 101 molecules) replicated R x R x R like LAMMPS `replicate` would
-    (new atom ids and molecule ids per image)."""
-    from types import SimpleNamespace
-    fx = dict(np.load(ROOT / "tests" / "golden" / "co2_singlepoint_step0.npz", allow_pickle=False))
-    n0 = fx["x"].shape[0]
-    prd = fx["boxhi"] - fx["boxlo"]
-    nmol0 = int(fx["molecule"].max())
-    xs, tags, mols, specs = [], [], [], []
-    r = 0
-    for ix in range(R):
-        for iy in range(R):
-            for iz in range(R):
-                xs.append(fx["x"] - fx["boxlo"] + np.array([ix, iy, iz]) * prd)
-                tags.append(fx["tag"] + r * n0)
-                mols.append(np.where(fx["molecule"] > 0, fx["molecule"] + r * nmol0, 0))
-                specs.append(np.where(fx["special"] > 0, fx["special"] + r * n0, 0))
-                r += 1
-    rep = R ** 3
-    sysm = SimpleNamespace(x=np.ascontiguousarray(np.concatenate(xs)), q=np.tile(fx["q"], rep), type=np.tile(fx["type"], rep).astype(np.int32),
-                           alpha=np.tile(fx["alpha"], rep), tag=np.concatenate(tags).astype(np.int32),
-                           molecule=np.concatenate(mols).astype(np.int32), nspecial=np.tile(fx["nspecial"], (rep, 1)).astype(np.int32),
-                           special=np.concatenate(specs).astype(np.int32), boxlo=np.zeros(3), boxhi=prd * R,
-                           ntypes=int(fx["ntypes"]), n=n0 * rep)
-    # the device expects tags in caller order only for lookups: keep arrays in tag order (already are)
-    return dict(sys=sysm, cut=12.8345, pair_coeff=str(fx["pair_coeff"]).splitlines())
+    """BASELINE config 4 shape (workloads.mof_supercell)"""
+    sysm, cut, coeff = bench.workloads().mof_supercell(ROOT / "tests" / "golden" / "co2_singlepoint_step0.npz", R)
+    return dict(sys=sysm, cut=cut, pair_coeff=coeff)
 
 
 def main():
