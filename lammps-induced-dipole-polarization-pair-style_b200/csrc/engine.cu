@@ -78,6 +78,8 @@ struct polb200_handle {
   // 20 / 21: per-atom rows + radial cache (also the ranked colouring sweep); 6: matrix-free; 0: first version
   int sweep_variant = 41;
   bool use_tight = true;         // per-step tight list
+  int gpf_minb = 4;              // resident CTAs per SM asked of the grouped force kernel (4: 128 registers, no spills; measured faster than 5)
+  bool use_group_pairs = true;   // LJ + Coulomb + field and polarization forces on the pair-group rows when they qualify
   bool gs_blocked = true;        // exact-mode Gauss-Seidel as blocked forward substitution (false: one atom at a time)
   DBuf<double4> gsR;
   bool l2_evict_first = true;    // TMA row streams are marked evict-first in L2
@@ -141,6 +143,7 @@ struct polb200_handle {
   HPinned<int> h_ctl;
   DBuf<double> slice;
   cudaEvent_t ev_it[2] = {};
+  bool rmin_fused = false;       // this step's group cache also produced rmin
   const int *scf_stop = nullptr; // non-null while the iterations of a precision-mode solve are being enqueued
   int scf_lag = 1;               // iterations enqueued ahead of the host's look at the stop flag (0: test every iteration)
   DBuf<double2> s12;             // per-step radial cache aligned with the tight list
@@ -619,7 +622,7 @@ static int launch_cached(polb200_handle *h, int beg, int end, const int *order, 
 
 // per-step radial cache of the pair-group rows (k_group_cache), built by the first sweep of a step.  Returns false
 // (and drops the groups) when the cache does not fit comfortably in free HBM.
-static bool ensure_group_cache(polb200_handle *h, const DevParams &P)
+static bool ensure_group_cache(polb200_handle *h, const DevParams &P, bool with_rmin = false)
 {
   if (!h->groups_built) return false;
   if (h->group_cache_valid) return true;
@@ -640,12 +643,15 @@ static bool ensure_group_cache(polb200_handle *h, const DevParams &P)
   if (chunked) h->gcrec.ensure(need_b + 64, 1.0);
   else { h->tgneigh.ensure(h->gneigh.cap); h->s12ab.ensure(h->gneigh.cap); }
   const int ngb = cdiv(h->ngroups, WARPS_PER_BLOCK);
-#define GC(DA, CK) \
-  LAUNCH(h, (k_group_cache<DA, CK>), ngb, BLOCK, h->ngroups, P, h->group_first.p, h->group_two.p, h->growstart.p, h->gcount.p, \
-         h->gneigh.p, h->xq.p, h->tgneigh.p, h->tgcount.p, h->s12ab.p, h->gcstart.p, h->gcrec.p)
-  if (damp) { if (chunked) GC(true, true); else GC(true, false); }
-  else { if (chunked) GC(false, true); else GC(false, false); }
+#define GC(DA, CK, RM) \
+  LAUNCH(h, (k_group_cache<DA, CK, RM>), ngb, BLOCK, h->ngroups, P, h->group_first.p, h->group_two.p, h->growstart.p, h->gcount.p, \
+         h->gneigh.p, h->xq.p, h->tgneigh.p, h->tgcount.p, h->s12ab.p, h->gcstart.p, h->gcrec.p, (const double4 *)h->mua.p, \
+         (const int2 *)h->tm.p, h->rmin_bits.p)
+  if (with_rmin && chunked) { if (damp) GC(true, true, true); else GC(false, true, true); }
+  else if (damp) { if (chunked) GC(true, true, false); else GC(true, false, false); }
+  else { if (chunked) GC(false, true, false); else GC(false, false, false); }
 #undef GC
+  h->rmin_fused = with_rmin && chunked;
   h->group_cache_valid = true;
   return true;
 }
@@ -891,7 +897,31 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
   AllPairRows A{n, h->perm.p};
   h->s12_valid = false;
   h->group_cache_valid = false;
-  if (h->use_tight) {
+  h->rmin_fused = false;
+  // how this step's sweeps and pair kernels run
+  const bool gs_mode = !st.zodid && (st.polar_gs || st.polar_gs_ranked);
+  // list-mode Gauss-Seidel: group-coloured sweep on the TMA pair-group kernel (default), or -- with an explicit
+  // gs_chunks setting, without pair groups, or when their cache does not fit -- per-atom chunks of the ranked order
+  bool coloured = gs_mode && list_mode && st.gs_chunks == 0 && h->groups_built && h->sweep_variant >= 40;
+  // LJ + Coulomb + field and the polarization forces on the pair-group rows: every interaction of the step must
+  // reach exactly as far as the dipole cutoff (the tight group rows hold the partners inside it), no special bonds,
+  // no exclusion rules, no per-atom / pairwise tallies
+  bool grouped_pf = list_mode && h->groups_built && h->sweep_variant >= 40 && h->use_group_pairs && !h->molecular &&
+                    h->excl.n == 0 && !eflag_atom && !vflag_atom && !vpair &&
+                    std::max(st.cutforce, st.cut_coul) <= st.polar_cutoff;
+  if (coloured || grouped_pf) {
+    // steps that keep their colouring only report rmin: the group cache produces it on the way
+    const bool fuse_rmin = coloured && st.polar_gs_ranked && h->colours_valid;
+    if (fuse_rmin) {
+      h->rmin_bits.ensure(1);
+      const unsigned long long init = (unsigned long long)0x408F400000000000ull;  // bits of 1000.0 (pol.cpp:196)
+      CUDA_CHECK(cudaMemcpyAsync(h->rmin_bits.p, &init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+    }
+    if (!ensure_group_cache(h, P, fuse_rmin)) coloured = grouped_pf = false;
+  }
+  const bool jacobi_groups = !gs_mode && h->groups_built;
+  const bool need_tight = h->use_tight && !(grouped_pf && (st.zodid || coloured || jacobi_groups));
+  if (need_tight) {
     // every pair kernel of this step only needs partners within the largest interaction cutoff
     double reach = st.cutforce > st.cut_coul ? st.cutforce : st.cut_coul;
     h->tneigh.ensure(h->neigh.cap);
@@ -908,7 +938,14 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
   }
   // ---- stage 2: LJ + Coulomb (+ static field) ----
 #define PAIR_ARGS n, P, h->xq.p, h->tm.p, L, h->f_pair.p, h->ef.p, h->partial.p, ea_ptr, vp_ptr, h->excl, h->exb.p, h->g_owner.p
-  if (h->excl.n > 0) {  // neigh_modify exclude: separate instantiations, the default kernels are untouched
+  const int ngroupblocks = cdiv(h->ngroups, GPF_WARPS);
+  if (grouped_pf) {
+    h->partial.ensure((size_t)ngroupblocks * 16 + 64);
+#define PG(EV) LAUNCH(h, (k_pair_group<EV, 4>), ngroupblocks, GPF_WARPS * 32, h->ngroups, P, h->group_first.p, h->group_two.p, h->tgcount.p, \
+                      h->gcstart.p, h->gcrec.p, h->xq.p, h->tm.p, h->f_pair.p, h->ef.p, h->partial.p)
+    if (evflag) PG(true); else PG(false);
+#undef PG
+  } else if (h->excl.n > 0) {  // neigh_modify exclude: separate instantiations, the default kernels are untouched
     if (list_mode) {
       if (evflag) LAUNCH(h, (k_pair<true, true, true>), nrowblocks, BLOCK, PAIR_ARGS);
       else LAUNCH(h, (k_pair<false, true, true>), nrowblocks, BLOCK, PAIR_ARGS);
@@ -924,7 +961,7 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
     else LAUNCH(h, (k_pair<false, false, false>), nrowblocks, BLOCK, PAIR_ARGS);
   }
 #undef PAIR_ARGS
-  if (evflag) reduce_partials<NPAIR_PART>(h, nrowblocks, h->scal.p + S_PAIR, 0);
+  if (evflag) reduce_partials<NPAIR_PART>(h, grouped_pf ? ngroupblocks : nrowblocks, h->scal.p + S_PAIR, 0);
   if (!list_mode) LAUNCH(h, k_static_allpairs, nrowblocks, BLOCK, n, P, h->xq.p, h->tm.p, h->perm.p, h->ef.p);
   if (!st.use_previous) LAUNCH(h, k_init_mu, cdiv(n, 256), 256, n, st.polar_gamma, h->ef.p, h->mua.p);
   ghost_update(h, false, h->mua.p);
@@ -934,11 +971,7 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
   int iterations = 0;
   bool diverged = false;
   if (!st.zodid) {
-    const bool gs = st.polar_gs || st.polar_gs_ranked;
-    // list-mode Gauss-Seidel: group-coloured sweep on the TMA pair-group kernel (default), or -- with an explicit
-    // gs_chunks setting, without pair groups, or when their cache does not fit -- per-atom chunks of the ranked order
-    const bool coloured = gs && list_mode && st.gs_chunks == 0 && h->groups_built && h->sweep_variant >= 40 &&
-                          ensure_group_cache(h, P);
+    const bool gs = gs_mode;
     // Gauss-Seidel visits atoms in the CALLER's index order (ranked_array = identity, pol.cpp:1127),
     // i.e. position c -> cell-sorted index invperm[c]; Jacobi does not care about the order.
     const int *order = gs ? h->invperm.p : nullptr;
@@ -946,10 +979,12 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
       // rank metric + stable descending sort, ties by caller index (pol.cpp:192-227,1127-1143)
       h->rmin_bits.ensure(1);
       h->metric.ensure(n); h->metric2.ensure(n); h->ranked.ensure(n); h->ranked_in.ensure(n);
-      const unsigned long long init = (unsigned long long)0x408F400000000000ull;  // bits of 1000.0
-      CUDA_CHECK(cudaMemcpyAsync(h->rmin_bits.p, &init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
       ListRows Lfull{h->rowstart.p, h->neigh.p, nullptr};
-      LAUNCH(h, k_rmin, nrowblocks, BLOCK, n, Lfull, h->xq.p, h->mua.p, h->tm.p, h->rmin_bits.p);
+      if (!h->rmin_fused) {
+        const unsigned long long init = (unsigned long long)0x408F400000000000ull;  // bits of 1000.0
+        CUDA_CHECK(cudaMemcpyAsync(h->rmin_bits.p, &init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+        LAUNCH(h, k_rmin, nrowblocks, BLOCK, n, Lfull, h->xq.p, h->mua.p, h->tm.p, h->rmin_bits.p);
+      }
       if (comm) comm_allreduce(h, h->rmin_bits.p, 1, ncclUint64, ncclMin);  // positive doubles order like their bits
       // (rmin travels to the host with the step's scalars: no synchronisation here)
       CUDA_CHECK(cudaMemcpyAsync(h->scal.p + S_RMIN, h->rmin_bits.p, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
@@ -1167,7 +1202,15 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
   } while (0)
   // the reference tallies polarization energies whenever eflag is set, virial via F.r or pairwise
   const bool ev4 = evflag;
-  if (list_mode) {
+  if (grouped_pf) {
+#define FG4(EV) LAUNCH(h, (k_polforce_group<EV, 4>), ngroupblocks, GPF_WARPS * 32, h->ngroups, P, h->group_first.p, h->group_two.p, h->tgcount.p, \
+                       h->gcstart.p, h->gcrec.p, h->xq.p, h->mua.p, h->tm.p, h->f_pol.p, h->partial.p)
+#define FG(EV) if (h->gpf_minb == 4) FG4(EV); else LAUNCH(h, (k_polforce_group<EV, 5>), ngroupblocks, GPF_WARPS * 32, h->ngroups, P, h->group_first.p, h->group_two.p, h->tgcount.p, \
+                      h->gcstart.p, h->gcrec.p, h->xq.p, h->mua.p, h->tm.p, h->f_pol.p, h->partial.p)
+    if (ev4) { FG(true); } else { FG(false); }
+#undef FG
+#undef FG4
+  } else if (list_mode) {
     if (!ev4) POLFORCE(true, false, false);
     else if (vpair) POLFORCE(true, true, true);
     else POLFORCE(true, true, false);
@@ -1177,7 +1220,7 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
     else POLFORCE(false, true, false);
   }
 #undef POLFORCE
-  if (ev4) reduce_partials<NPOL_PART>(h, nrowblocks, h->scal.p + S_POL, 0);
+  if (ev4) reduce_partials<NPOL_PART>(h, grouped_pf ? ngroupblocks : nrowblocks, h->scal.p + S_POL, 0);
 
   // ---- stage 5: outputs ----
   h->c_f.ensure((size_t)3 * n); h->c_ef.ensure((size_t)3 * n);
@@ -1408,6 +1451,8 @@ int polb200_create(polb200_t **out, int device)
   h->device = device;
   if (const char *v = getenv("POLB200_SWEEP_VARIANT")) h->sweep_variant = atoi(v);  // experiments only
   if (const char *v = getenv("POLB200_USE_PUSH")) h->use_push = atoi(v) != 0;
+  if (const char *v = getenv("POLB200_GPF_MINB")) h->gpf_minb = atoi(v);
+  if (const char *v = getenv("POLB200_GROUP_PAIRS")) h->use_group_pairs = atoi(v) != 0;
   if (const char *v = getenv("POLB200_XSORT_BITS")) h->xsort_bits = atoi(v);
   if (const char *v = getenv("POLB200_BIN_DIV")) h->bin_div = atof(v);
   int rc = guarded(h, [&] {
@@ -1665,6 +1710,14 @@ int polb200_set_option(polb200_t *h, const char *name, double value)
   }
   if (!strcmp(name, "use_push")) {
     h->use_push = value != 0.0;
+    return POLB200_OK;
+  }
+  if (!strcmp(name, "gpf_minb")) {
+    h->gpf_minb = (int)value;
+    return POLB200_OK;
+  }
+  if (!strcmp(name, "use_group_pairs")) {
+    h->use_group_pairs = value != 0.0;
     return POLB200_OK;
   }
   if (!strcmp(name, "use_tight")) {

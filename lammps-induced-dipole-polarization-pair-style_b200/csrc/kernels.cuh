@@ -164,17 +164,17 @@ __device__ __forceinline__ int sort_key_of(const Grid &g, double x, double y, do
 
 // block-level fixed-order reduction of NV per-warp values; lane 0 of each warp holds its value.
 // Thread 0 returns with the block total in out[0..NV).
-template <int NV>
+template <int NV, int NWARPS = WARPS_PER_BLOCK>
 __device__ __forceinline__ void block_reduce_store(double (&v)[NV], double *block_out)
 {
-  __shared__ double sm[WARPS_PER_BLOCK][NV];
+  __shared__ double sm[NWARPS][NV];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane == 0)
     for (int k = 0; k < NV; k++) sm[warp][k] = v[k];
   __syncthreads();
   if (threadIdx.x < NV) {
     double s = 0.0;
-    for (int w = 0; w < WARPS_PER_BLOCK; w++) s += sm[w][threadIdx.x];
+    for (int w = 0; w < NWARPS; w++) s += sm[w][threadIdx.x];
     block_out[(size_t)blockIdx.x * NV + threadIdx.x] = s;
   }
 }
@@ -1656,13 +1656,17 @@ __global__ void k_group_chunk_count(int ngroups, const int *__restrict__ rowcoun
 
 // per step: entries inside the dipole cutoff of either member at the current positions, compacted, with the
 // radial scalars {s1a, s2a, s1b, s2b} of both members (zero for a member the entry does not belong to)
-template <bool DAMP, bool CHUNKED>
+// RMIN: also the closest inter-molecular pair of polarizable atoms (the rmin of the rank metric, pol.cpp:196-212, over
+// the partners inside the dipole cutoff), so that steps that only report rmin need no pass of their own over the list.
+// The distance of a candidate is evaluated with the reference's un-fused expression, like k_rmin.
+template <bool DAMP, bool CHUNKED, bool RMIN = false>
 __global__ void __launch_bounds__(BLOCK)
 k_group_cache(int ngroups, DevParams P, const int *__restrict__ group_first, const int *__restrict__ group_two,
               const unsigned long long *__restrict__ rowstart, const int *__restrict__ rowcount,
               const int *__restrict__ neigh, const double4 *__restrict__ xq, int *__restrict__ tneigh,
               int *__restrict__ tcount, double4 *__restrict__ s12ab, const unsigned long long *__restrict__ cstart,
-              unsigned char *__restrict__ crec)
+              unsigned char *__restrict__ crec, const double4 *__restrict__ mua = nullptr, const int2 *__restrict__ tm = nullptr,
+              unsigned long long *__restrict__ rmin_bits = nullptr)
 {
   const int lane = threadIdx.x & 31;
   const int g = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
@@ -1673,6 +1677,13 @@ k_group_cache(int ngroups, DevParams P, const int *__restrict__ group_first, con
   const double4 xa = xq[a], xb = xq[b];
   const double cutsq = P.pc.polar_cutsq;
   const unsigned long long beg = rowstart[g], end = beg + (unsigned long long)rowcount[g];
+  double best = 1000.0, guard = 1.0e6;  // pol.cpp:196; guard = best^2 with a margin for the fused distance
+  double ala = 0.0, alb = 0.0;
+  int mola = 0, molb = 0;
+  if (RMIN) {
+    ala = mua[a].w; alb = mua[b].w;
+    mola = tm[a].y; molb = tm[b].y;
+  }
   int n = 0;
   for (unsigned long long k0 = beg; k0 < end; k0 += 32) {
     const unsigned long long k = k0 + lane;
@@ -1690,6 +1701,21 @@ k_group_cache(int ngroups, DevParams P, const int *__restrict__ group_first, con
       ok = ina || inb;
       if (ina) radial_scalars<DAMP>(P.pc, ra, sc.x, sc.y);
       if (inb) radial_scalars<DAMP>(P.pc, rb, sc.z, sc.w);
+      if (RMIN && ((ina && ra < guard) || (inb && rb < guard))) {
+        const double aj = mua[j].w;
+        const int molj = tm[j].y;
+        if (aj > 0) {
+          if (ina && ala > 0 && (mola != molj || mola == 0)) {
+            const double r = sqrt(rsq_nofma(xa.x - xj.x, xa.y - xj.y, xa.z - xj.z));
+            if (best > r) best = r;
+          }
+          if (inb && alb > 0 && (molb != molj || molb == 0)) {
+            const double r = sqrt(rsq_nofma(xb.x - xj.x, xb.y - xj.y, xb.z - xj.z));
+            if (best > r) best = r;
+          }
+          guard = best * best * 1.000001;
+        }
+      }
     }
     const unsigned m = __ballot_sync(FULL, ok);
     if (ok) {
@@ -1707,6 +1733,11 @@ k_group_cache(int ngroups, DevParams P, const int *__restrict__ group_first, con
     n += __popc(m);
   }
   if (lane == 0) tcount[g] = n;
+  if (RMIN) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = fmin(best, __shfl_down_sync(FULL, best, o));
+    if (lane == 0 && best < 1000.0) atomicMin(rmin_bits, (unsigned long long)__double_as_longlong(best));
+  }
 }
 
 // one Jacobi dipole iteration, one warp per group of two atoms (rows in cell-sorted order only)
@@ -2038,6 +2069,181 @@ k_sweep_group_tma(int ngroups, const int *__restrict__ group_first, const int *_
         push_row(push_b, nbx, nby, nbz, alb);
       }
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// stages 2 and 4 on the pair-group rows
+// ---------------------------------------------------------------------------------------------------
+// When every interaction of the step reaches exactly as far as the dipole cutoff (max pair cutoff == cut_coul ==
+// polar_cutoff: the shape of all BASELINE configs), the per-step tight group rows that the sweep streams hold every
+// partner the LJ + Coulomb + static-field kernel and the polarization-force kernel need.  One warp serves the two
+// members of a group: each gathered position / dipole / type record feeds two pair evaluations (half the gathers of the
+// per-atom kernels), the per-atom tight list (k_tighten) is not built at all, and the index stream is the 256-byte index
+// block of every 2304-byte chunk record.
+__device__ __forceinline__ const int *group_index_ptr(const unsigned char *__restrict__ recs, int k)
+{
+  return reinterpret_cast<const int *>(recs + (size_t)(k >> 6) * GCHUNK_BYTES + GCHUNK * 32) + (k & 63);
+}
+
+constexpr int GPF_WARPS = 4;  // warps per CTA of the two kernels below: 5 CTAs of 128 threads per SM leave 102 registers
+template <bool EVFLAG, int MINB>
+__global__ void __launch_bounds__(GPF_WARPS * 32, MINB)
+k_pair_group(int ngroups, DevParams P, const int *__restrict__ group_first, const int *__restrict__ group_two,
+             const int *__restrict__ tcount, const unsigned long long *__restrict__ cstart,
+             const unsigned char *__restrict__ crec, const double4 *__restrict__ xq, const int2 *__restrict__ tm,
+             double4 *__restrict__ f_pair, double4 *__restrict__ ef, double *__restrict__ partial)
+{
+  const int lane = threadIdx.x & 31;
+  const int g = blockIdx.x * GPF_WARPS + (threadIdx.x >> 5);
+  double acc[NPAIR_PART] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (g < ngroups) {
+    const int a = group_first[g];
+    const bool two = (group_two[g] & 1) != 0;
+    const int b = two ? a + 1 : a;
+    const double4 xa = xq[a], xb = xq[b];
+    const int2 tma = tm[a], tmb = tm[b];
+    const int n1 = P.pc.ntypes + 1;
+    double fax = 0, fay = 0, faz = 0, fbx = 0, fby = 0, fbz = 0;
+    double eax = 0, eay = 0, eaz = 0, ebx = 0, eby = 0, ebz = 0;
+    const int cnt = tcount[g];
+    const unsigned char *__restrict__ recs = crec + cstart[g] * GCHUNK_BYTES;
+    int jA = lane < cnt ? __ldcs(group_index_ptr(recs, lane)) : 0;
+    int jB = lane + 32 < cnt ? __ldcs(group_index_ptr(recs, lane + 32)) : 0;
+    auto one = [&](const double4 &xi, const int2 &tmi, const double4 &xj, const int2 &tmj, double &fx, double &fy, double &fz,
+                   double &ex, double &ey, double &ez) {
+      const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+      const double rsq = rsq_nofma(dx, dy, dz);
+      const int ij = tmi.x * n1 + tmj.x;
+      if (rsq < P.lj.cutsq[ij]) {
+        double evdwl, ecoul;
+        const double fpair = lj_coul_pair(P.pc, P.lj, P.tb, ij, rsq, xi.w, xj.w, 0, EVFLAG, evdwl, ecoul);
+        fx += dx * fpair;
+        fy += dy * fpair;
+        fz += dz * fpair;
+        if (EVFLAG) {
+          acc[0] += evdwl;
+          acc[1] += ecoul;
+          acc[2] += dx * dx * fpair;
+          acc[3] += dy * dy * fpair;
+          acc[4] += dz * dz * fpair;
+          acc[5] += dx * dy * fpair;
+          acc[6] += dx * dz * fpair;
+          acc[7] += dy * dz * fpair;
+        }
+      }
+      if (rsq <= P.pc.cut_coulsq && (tmi.y != tmj.y || tmi.y == 0)) {
+        const double sc = static_field_scalar(P.pc, rsq) * xj.w;
+        ex += sc * dx;
+        ey += sc * dy;
+        ez += sc * dz;
+      }
+    };
+    for (int k = lane; k < cnt; k += 32) {
+      const int jC = k + 64 < cnt ? __ldcs(group_index_ptr(recs, k + 64)) : 0;
+      const int j = jA;
+      jA = jB;
+      jB = jC;
+      const double4 xj = ld4(xq + j);
+      const int2 tmj = tm[j];
+      if (j != a) one(xa, tma, xj, tmj, fax, fay, faz, eax, eay, eaz);
+      if (two && j != b) one(xb, tmb, xj, tmj, fbx, fby, fbz, ebx, eby, ebz);
+    }
+    fax = warp_sum(fax); fay = warp_sum(fay); faz = warp_sum(faz);
+    eax = warp_sum(eax); eay = warp_sum(eay); eaz = warp_sum(eaz);
+    if (two) {
+      fbx = warp_sum(fbx); fby = warp_sum(fby); fbz = warp_sum(fbz);
+      ebx = warp_sum(ebx); eby = warp_sum(eby); ebz = warp_sum(ebz);
+    }
+    if (lane == 0) {
+      f_pair[a] = make_double4(fax, fay, faz, 0.0);
+      ef[a] = make_double4(eax * P.pc.kq, eay * P.pc.kq, eaz * P.pc.kq, 0.0);  // pol.cpp:372-374
+      if (two) {
+        f_pair[b] = make_double4(fbx, fby, fbz, 0.0);
+        ef[b] = make_double4(ebx * P.pc.kq, eby * P.pc.kq, ebz * P.pc.kq, 0.0);
+      }
+    }
+  }
+  if (EVFLAG) {
+#pragma unroll
+    for (int k = 0; k < NPAIR_PART; k++) acc[k] = 0.5 * warp_sum(acc[k]);
+    block_reduce_store<NPAIR_PART, GPF_WARPS>(acc, partial);
+  }
+}
+
+template <bool EVFLAG, int MINB>
+__global__ void __launch_bounds__(GPF_WARPS * 32, MINB)
+k_polforce_group(int ngroups, DevParams P, const int *__restrict__ group_first, const int *__restrict__ group_two,
+                 const int *__restrict__ tcount, const unsigned long long *__restrict__ cstart,
+                 const unsigned char *__restrict__ crec, const double4 *__restrict__ xq, const double4 *__restrict__ mua,
+                 const int2 *__restrict__ tm, double4 *__restrict__ f_pol, double *__restrict__ partial)
+{
+  const int lane = threadIdx.x & 31;
+  const int g = blockIdx.x * GPF_WARPS + (threadIdx.x >> 5);
+  double acc[NPOL_PART] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (g < ngroups) {
+    const int a = group_first[g];
+    const bool two = (group_two[g] & 1) != 0;
+    const int b = two ? a + 1 : a;
+    const double4 xa = xq[a], xb = xq[b];
+    const double4 ma = mua[a], mb = mua[b];
+    const int mola = tm[a].y, molb = tm[b].y;
+    const bool molecules = P.pc.has_molecules != 0;
+    double fax = 0, fay = 0, faz = 0, fbx = 0, fby = 0, fbz = 0;
+    const int cnt = tcount[g];
+    const unsigned char *__restrict__ recs = crec + cstart[g] * GCHUNK_BYTES;
+    const double reach = fmax(P.pc.cut_coulsq, P.pc.polar_cutsq);
+    int jA = lane < cnt ? __ldcs(group_index_ptr(recs, lane)) : 0;
+    int jB = lane + 32 < cnt ? __ldcs(group_index_ptr(recs, lane + 32)) : 0;
+    const bool damp = P.pc.damping_exponential != 0;
+    auto one = [&](const double4 &xi, const double4 &mi, int moli, const double4 &xj, const double4 &mj, int molj, double &fx,
+                   double &fy, double &fz) {
+      const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+      if (dx * dx + dy * dy + dz * dz < reach) {
+        const bool inter = !molecules || (moli != molj) || moli == 0;
+        double px, py, pz, uef, udd;
+        pol_force_pair_fast(P.pc, damp, dx, dy, dz, xi.w, xj.w, mi.w, mj.w, mi.x, mi.y, mi.z, mj.x, mj.y, mj.z, inter, EVFLAG,
+                            px, py, pz, uef, udd);
+        fx += px; fy += py; fz += pz;
+        if (EVFLAG) {
+          acc[1] += 0.5 * uef;  // every pair is visited from both of its atoms
+          acc[2] += 0.5 * udd;
+        }
+      }
+    };
+    for (int k = lane; k < cnt; k += 32) {
+      const int jC = k + 64 < cnt ? __ldcs(group_index_ptr(recs, k + 64)) : 0;
+      const int j = jA;
+      jA = jB;
+      jB = jC;
+      const double4 xj = ld4(xq + j);
+      const double4 mj = ld4(mua + j);
+      const int molj = molecules ? tm[j].y : 0;
+      if (j != a) one(xa, ma, mola, xj, mj, molj, fax, fay, faz);
+      if (two && j != b) one(xb, mb, molb, xj, mj, molj, fbx, fby, fbz);
+    }
+    fax = warp_sum(fax); fay = warp_sum(fay); faz = warp_sum(faz);
+    if (two) { fbx = warp_sum(fbx); fby = warp_sum(fby); fbz = warp_sum(fbz); }
+    if (lane == 0) {
+      f_pol[a] = make_double4(fax, fay, faz, 0.0);
+      if (two) f_pol[b] = make_double4(fbx, fby, fbz, 0.0);
+      if (EVFLAG) {
+        if (ma.w != 0.0) acc[0] = 0.5 * (ma.x * ma.x + ma.y * ma.y + ma.z * ma.z) / ma.w;  // pol.cpp:432-433
+        // F.r virial of the reference (src/pair.cpp:1495-1543): polarization forces act on owned atoms
+        acc[3] += fax * xa.x; acc[4] += fay * xa.y; acc[5] += faz * xa.z;
+        acc[6] += fay * xa.x; acc[7] += faz * xa.x; acc[8] += faz * xa.y;
+        if (two) {
+          if (mb.w != 0.0) acc[0] += 0.5 * (mb.x * mb.x + mb.y * mb.y + mb.z * mb.z) / mb.w;
+          acc[3] += fbx * xb.x; acc[4] += fby * xb.y; acc[5] += fbz * xb.z;
+          acc[6] += fby * xb.x; acc[7] += fbz * xb.x; acc[8] += fbz * xb.y;
+        }
+      }
+    }
+  }
+  if (EVFLAG) {
+#pragma unroll
+    for (int k = 0; k < NPOL_PART; k++) acc[k] = warp_sum(acc[k]);
+    block_reduce_store<NPOL_PART, GPF_WARPS>(acc, partial);
   }
 }
 

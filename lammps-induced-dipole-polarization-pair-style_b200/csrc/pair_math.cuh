@@ -124,17 +124,21 @@ PB_HD double lj_coul_pair(const PairConsts &pc, const LJCoeffs &lj, const CoulTa
   const double EWALD_F = 1.12837917, EWALD_P = 0.3275911;
   const double A1 = 0.254829592, A2 = -0.284496736, A3 = 1.421413741, A4 = -1.453152027, A5 = 1.061405429;
   const double factor_lj = pc.special_lj[sb], factor_coul = pc.special_coul[sb];
-  const double r2inv = 1.0 / rsq;
+  // one reciprocal square root feeds 1/r^2 and r (the reference divides and takes the root separately, pol.cpp:254-262;
+  // the results agree to a few ulp, far inside the 1e-10 parity bar) -- a division and a square root cost ~4x more
+  // FP64 issue slots each than the rsqrt sequence
+  const double rinv = pb_rsqrt(rsq);
+  const double r2inv = rinv * rinv;
   double forcecoul = 0.0, forcelj = 0.0, r6inv = 0.0, prefactor = 0.0;
   evdwl = ecoul = 0.0;
   if (rsq < pc.cut_coulsq) {
     if (!pc.ncoultablebits || rsq <= pc.tabinnersq) {
-      const double r = sqrt(rsq);
+      const double r = rsq * rinv;
       const double grij = pc.g_ewald * r;
       const double expm2 = exp(-grij * grij);
       const double t = 1.0 / (1.0 + EWALD_P * grij);
       const double erfcv = t * (A1 + t * (A2 + t * (A3 + t * (A4 + t * A5)))) * expm2;
-      prefactor = pc.qqrd2e * qi * qj / r;
+      prefactor = pc.qqrd2e * qi * qj * rinv;
       forcecoul = prefactor * (erfcv + EWALD_F * grij * expm2);
       if (want_e) ecoul = prefactor * erfcv;
     } else {
@@ -174,9 +178,9 @@ PB_HD double lj_coul_pair(const PairConsts &pc, const LJCoeffs &lj, const CoulTa
 // returns the scalar s such that E_i += s*qj*del (caller applies the sign of the pair orientation)
 PB_HD double static_field_scalar(const PairConsts &pc, double rsq)
 {
-  const double r = sqrt(rsq);
-  const double dvdrr = 1.0 / rsq + pc.f_shift;
-  return dvdrr * 1.0 / r;
+  const double rinv = pb_rsqrt(rsq);
+  const double dvdrr = rinv * rinv + pc.f_shift;
+  return dvdrr * rinv;
 }
 
 // ---- stage 3: T_ij . mu_j for one neighbour (pol.cpp:1282-1306 + 1161-1168), matrix-free ----------------
@@ -301,6 +305,66 @@ PB_HD void pol_force_pair(const PairConsts &pc, const PolPairIn &in, bool want_e
     fx += (pre1 + pre45) * delx + pre2 * in.max_ + pre3 * in.mbx;
     fy += (pre1 + pre45) * dely + pre2 * in.may + pre3 * in.mby;
     fz += (pre1 + pre45) * delz + pre2 * in.maz + pre3 * in.mbz;
+  }
+}
+
+// Same pair, regrouped for the list-mode force kernel on the pair-group rows (the row atom is a, del = xa - xb).
+// Identities used (exact algebra, different rounding -- agreement with pol_force_pair to a few ulp per term):
+//   * the charge-dipole matrix of pol.cpp:467-475 is  M = c1 I - c2 del (x) del  with  c1 = 1 + f_shift r^2,
+//     c2 = 3/r^2 + f_shift, so both charge-dipole forces are  kq/r^3 [c1 v - c2 s del]  with
+//     v = qb mu_a - qa mu_b,  s = qb (del.mu_a) - qa (del.mu_b), and  u_ef = -ef_temp s;
+//   * the derivative terms of the exponential damping collapse:  pre4 + pre5 (pol.cpp:528-533)
+//     = (a^3/2) e^{-ar} [a (del.mu_a)(del.mu_b)/r^3 - (mu_a.mu_b)/r^2].
+// ~100 FP64 operations per pair instead of ~190: the force kernel is bound by the FP64 pipe.
+PB_HD void pol_force_pair_fast(const PairConsts &pc, bool damp, double dx, double dy, double dz, double qa, double qb,
+                               double alpha_a, double alpha_b, double max_, double may, double maz, double mbx, double mby,
+                               double mbz, bool intermolecular, bool want_e, double &fx, double &fy, double &fz,
+                               double &u_ef, double &u_dd)
+{
+  const double rsq = dx * dx + dy * dy + dz * dz;
+  const double rinv = pb_rsqrt(rsq);
+  const double r2inv = rinv * rinv;
+  const double r3inv = r2inv * rinv;
+  const double pa = max_ * dx + may * dy + maz * dz;
+  const double pb = mbx * dx + mby * dy + mbz * dz;
+  fx = fy = fz = 0.0;
+  u_ef = u_dd = 0.0;
+  if (rsq < pc.cut_coulsq && intermolecular) {
+    const double wa = alpha_a != 0.0 ? qb : 0.0;  // dipole on a feels the charge on b (pol.cpp:464)
+    const double wb = alpha_b != 0.0 ? qa : 0.0;  // dipole on b feels the charge on a (pol.cpp:487)
+    const double c1 = 1.0 + pc.f_shift * rsq, c2 = 3.0 * r2inv + pc.f_shift;
+    const double s = wa * pa - wb * pb;
+    const double k3 = pc.kq * r3inv, k3s = k3 * c2 * s, k3c = k3 * c1;
+    fx = k3c * (wa * max_ - wb * mbx) - k3s * dx;
+    fy = k3c * (wa * may - wb * mby) - k3s * dy;
+    fz = k3c * (wa * maz - wb * mbz) - k3s * dz;
+    if (want_e) u_ef = -(r2inv + pc.f_shift) * rinv * pc.kq * s;
+  }
+  const bool in_polar_cut = !(pc.polar_cutsq > 0.0) || rsq < pc.polar_cutsq;
+  if (alpha_a != 0.0 && alpha_b != 0.0 && in_polar_cut) {  // pol.cpp:512-602
+    const double pdotp = max_ * mbx + may * mby + maz * mbz;
+    const double r5inv3 = 3.0 * r3inv * r2inv;
+    const double papb = pa * pb;
+    double A, B;
+    if (damp) {
+      const double a = pc.polar_damp;
+      const double ar = a * (rsq * rinv);
+      const double t1 = exp(-ar);
+      const double t2 = 1.0 + ar + 0.5 * ar * ar;
+      const double t3 = t2 + (1.0 / 6.0) * ar * ar * ar;
+      const double w2 = 1.0 - t1 * t2, w3 = 1.0 - t1 * t3;
+      const double g = 0.5 * t1 * a * a * a;
+      A = r5inv3 * (w2 * pdotp - 5.0 * r2inv * w3 * papb) + g * (a * papb * r3inv - pdotp * r2inv);
+      B = r5inv3 * w3;
+      if (want_e) u_dd = r3inv * w2 * pdotp - B * papb;
+    } else {
+      A = r5inv3 * (pdotp - 5.0 * r2inv * papb);
+      B = r5inv3;
+      if (want_e) u_dd = r3inv * pdotp - B * papb;
+    }
+    fx += A * dx + B * (pb * max_ + pa * mbx);
+    fy += A * dy + B * (pb * may + pa * mby);
+    fz += A * dz + B * (pb * maz + pa * mbz);
   }
 }
 
