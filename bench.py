@@ -168,6 +168,19 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def nvlink_counters(index):
+    """{tx, rx} bytes moved over all NVLinks of GPU `index` so far (nvidia-smi nvlink -gt d), None when unavailable"""
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(index)], capture_output=True, text=True, timeout=20).stdout
+    except Exception:
+        return None
+    tx = [int(v) for v in re.findall(r"Data Tx:\s*(\d+)\s*KiB", out)]
+    rx = [int(v) for v in re.findall(r"Data Rx:\s*(\d+)\s*KiB", out)]
+    if not tx and not rx:
+        return None
+    return {"tx": 1024 * sum(tx), "rx": 1024 * sum(rx)}
+
+
 # ----------------------------------------------------------------------------------------------------
 # CPU reference arm
 # ----------------------------------------------------------------------------------------------------
@@ -371,20 +384,30 @@ class Run:
         sampler = ClockSampler(self.local) if clocks and self.rank == 0 else None
         if sampler:
             sampler.start()
+        bar0 = style.debug_fetch("barrier_stats", np.float64, 2) if self.world > 1 else None
+        nvl0 = nvlink_counters(self.local) if self.world > 1 and clocks else None
         self.barrier()
         t0 = time.perf_counter()
         dev_ms, stage, iters = 0.0, np.zeros(5), 0
+        rebuild_ms = []
         for k in range(steps):
             res = self.step_dev(k)
             dev_ms += res.ms_total
             iters += res.iterations
             stage += [res.ms_neigh, res.ms_pair, res.ms_scf, res.ms_force, res.ms_total]
+            if res.status & pb.STATUS_REBUILT:
+                rebuild_ms.append(res.ms_neigh)
         self.barrier()
         wall = time.perf_counter() - t0
+        nvl1 = nvlink_counters(self.local) if nvl0 else None
+        bar1 = style.debug_fetch("barrier_stats", np.float64, 2) if self.world > 1 else None
         out = SimpleNamespace(wall=wall, launches=style.launch_count(), sweep=style.debug_fetch("sweep_timing", np.float64, 2),
                               clocks=sampler.stop() if sampler else None, eng_pol=res.eng_pol, res=res, stage=stage / steps,
                               dev_ms=dev_ms / steps, iterations=iters / steps, polar_pairs=polar_pairs, group_stats=group_stats,
-                              comm_stats=comm_stats, wall_e2e=None)
+                              comm_stats=comm_stats, wall_e2e=None, rebuild_ms=rebuild_ms,
+                              nvlink={k: nvl1[k] - nvl0[k] for k in nvl0} if nvl0 and nvl1 else None,
+                              barrier_ms=(bar1[0] - bar0[0]) * 1e-6 if bar0 is not None else None,
+                              barriers=int(bar1[1] - bar0[1]) if bar0 is not None else None)
         style.set_option("time_sweeps", 0.0)
         if e2e:
             # ---- end to end through the C ABI with host (pinned) buffers ----
@@ -411,6 +434,16 @@ class Run:
             dist.all_reduce(sums)
         m.wall, m.wall_e2e = float(times[0]), float(times[1]) or None
         m.total_atoms, m.eng_pol_total = int(sums[0]), float(sums[1])
+        m.per_rank = None
+        if self.world > 1:
+            # per brick: owned atoms, ghosts, mean sweep-kernel time, time inside inter-GPU barriers, SCF stage
+            mine = torch.tensor([float(self.n), float(m.res.nghost), float(m.sweep[0]) / max(float(m.sweep[1]), 1.0) * 1e3,
+                                 m.barrier_ms or 0.0, float(m.barriers or 0), float(m.stage[2]), float(m.stage[4])],
+                                dtype=torch.float64, device=dev)
+            allr = [torch.zeros_like(mine) for _ in range(self.world)]
+            dist.all_gather(allr, mine)
+            keys = ("owned", "ghosts", "sweep_us", "barrier_ms_total", "barriers", "scf_ms_per_step", "device_ms_per_step")
+            m.per_rank = [dict(zip(keys, [float(v) for v in t.cpu()])) for t in allr]
         return m
 
     def roofline(self, m, peaks, traffic_file=None):
@@ -624,12 +657,19 @@ def gpu_arm(args):
             "iterations_per_step": m.iterations,
             "device_ms_per_step": m.dev_ms,
             "stage_ms": {"neigh_refresh": m.stage[0], "pair_field": m.stage[1], "scf": m.stage[2], "pol_force": m.stage[3]},
+            "rebuild_steps_in_timed_region": len(m.rebuild_ms),
+            "rebuild_ms_rank0": float(np.mean(m.rebuild_ms)) if m.rebuild_ms else None,
             "roofline": roof,
             "cpu_baseline": cpu, "clocks": m.clocks,
             "halo": None if world == 1 else {"rank0_owned": n, "rank0_send_slots": int(comm_stats[0]),
                                              "rank0_ghosts": int(comm_stats[1]), "bytes_per_sweep_rank0": 32 * int(comm_stats[0]),
                                              "model_24B_x_ghosts": 24 * int(comm_stats[1]),
-                                             "peer_push": bool(int(comm_stats[3]))},
+                                             "peer_push": bool(int(comm_stats[3])),
+                                             # NVLink bytes of rank 0's GPU over the timed region per dipole sweep (nvidia-smi
+                                             # nvlink counters; includes the once-per-step position halo and NCCL traffic)
+                                             "nvlink_bytes_per_sweep_rank0": None if not m.nvlink else
+                                             {k: v / max(float(m.sweep[1]), 1.0) for k, v in m.nvlink.items()},
+                                             "per_rank": m.per_rank},
             "check": {"eng_pol": m.eng_pol_total, "iterations": m.res.iterations,
                       "mgpu_max_rel_err": mgpu[0] if mgpu else None, "mgpu_detail": mgpu[1] if mgpu else None},
             "also": also or None,

@@ -1806,6 +1806,17 @@ long polb200_debug_fetch(polb200_t *h, const char *name, void *dst, long capacit
                      (double)h->comm.push.enabled, (double)h->comm.nranks};
       memcpy(dst, v, 40);
       result = 5;
+    } else if (!strcmp(name, "barrier_stats")) {  // {ns spent inside inter-GPU barriers, barriers} since comm_init (this rank)
+      if (capacity_bytes < 16) throw StyleError{POLB200_ERR_ARG, "debug_fetch: buffer too small"};
+      double v[2] = {0.0, 0.0};
+      if (h->comm.active && h->comm.flags.p) {
+        unsigned long long u[2];
+        CUDA_CHECK(cudaMemcpy(u, h->comm.flags.p + 3 * MAX_PEERS, sizeof(u), cudaMemcpyDeviceToHost));
+        v[0] = (double)u[0];
+        v[1] = (double)u[1];
+      }
+      memcpy(dst, v, 16);
+      result = 2;
     } else if (!strcmp(name, "group_stats")) {  // {groups, union entries inside the cutoff (last step), skin entries, built}
       if (capacity_bytes < 32) throw StyleError{POLB200_ERR_ARG, "debug_fetch: buffer too small"};
       double v[4] = {(double)h->ngroups, 0.0, (double)h->gpairs, h->groups_built ? 1.0 : 0.0};

@@ -1532,6 +1532,7 @@ __global__ void k_signal_wait(int rank, int nranks, unsigned long long epoch, Pe
   const int r = threadIdx.x;
   const int bank = (1 + (int)(epoch & 1ull)) * MAX_PEERS;
   unsigned long long *mine = P.flag[rank];
+  const unsigned long long t_in = global_ns();
   if (r < nranks) {
     unsigned long long *theirs = P.flag[r];
     if (change) theirs[bank + rank] = (unsigned long long)__double_as_longlong(*change);
@@ -1547,10 +1548,16 @@ __global__ void k_signal_wait(int rank, int nranks, unsigned long long epoch, Pe
     }
   }
   __syncwarp();
-  if (threadIdx.x == 0 && change) {
-    double s = 0.0;
-    for (int k = 0; k < nranks; k++) s += __longlong_as_double((long long)ld_acquire_sys(mine + bank + k));
-    *change = s;
+  if (threadIdx.x == 0) {
+    if (change) {
+      double s = 0.0;
+      for (int k = 0; k < nranks; k++) s += __longlong_as_double((long long)ld_acquire_sys(mine + bank + k));
+      *change = s;
+    }
+    // statistics (slots 3*MAX_PEERS.. of this rank's own counters): time inside barriers, number of barriers.  The brick
+    // that waits least is the one the others wait for.
+    mine[3 * MAX_PEERS] += global_ns() - t_in;
+    mine[3 * MAX_PEERS + 1] += 1ull;
   }
 }
 
