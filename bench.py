@@ -650,7 +650,7 @@ def gpu_arm(args):
                                       f"once per step, ghost dipoles once per sweep ("
                                       + ("stored by the sweep kernel into peer memory over NVLink + signal/wait barrier"
                                          if int(comm_stats[3]) else "NCCL send/recv") + ")"),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 48 * n, "d2h_bytes_per_step": 72 * n + 192,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 64 * n, "d2h_bytes_per_step": 72 * n + 192,
                     "ms_per_step": m.wall_e2e / args.steps * 1e3},
             "gpu_launches": int(m.launches),
             "us_per_dipole_iteration": roof["launch_ms"] * 1e3,

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define POLB200_ABI_VERSION 4
+#define POLB200_ABI_VERSION 5
 
 typedef struct polb200_handle polb200_t;
 
@@ -29,7 +29,7 @@ enum {
   POLB200_ERR_ARG = 1,      /* message = the reference's error->all text, e.g. "Illegal pair_style command" */
   POLB200_ERR_CUDA = 2,     /* CUDA runtime failure or no device */
   POLB200_ERR_STATE = 3,    /* call order (e.g. compute before init) */
-  POLB200_ERR_UNSUPPORTED = 4, /* triclinic box, newton_pair off, ... */
+  POLB200_ERR_UNSUPPORTED = 4, /* triclinic box, cutoffs beyond half the box in list mode, ... */
   POLB200_ERR_OVERFLOW = 5, /* neighbor capacity ("Neighbor list overflow, boost neigh_modify one") */
   POLB200_ERR_NAN = 6       /* "Non-numeric positions - simulation unstable" (src/nbin.cpp:120-121) */
 };
@@ -58,8 +58,11 @@ int polb200_abi_version(void);
  * arg[1]=cut_coul, then keyword/value pairs: precision zodid fixed_iteration damp max_iterations
  * damp_type polar_gs polar_gs_ranked polar_gamma debug use_previous -- plus the documented extensions
  *   polar_cutoff <r|none>  dipole-dipole cutoff (none = reference all-pairs semantics, the default)
- *   gs_chunks <n>          ranked colouring sweep in list mode: n > 0 contiguous chunks of the ranked order,
- *                          n < 0 |n| interleaved chunks, 0 (default) = 8 interleaved chunks
+ *   restart_keywords <yes|no>  write the polarization keywords into restart files (extension record, default no)
+ *   gs_chunks <n>          list-mode Gauss-Seidel (polar_gs / polar_gs_ranked): 0 (default) = group-coloured sweep
+ *                          (pair groups coloured so that close groups differ, colours visited in turn, rank metric =
+ *                          priority of the colouring); n > 0 = n contiguous per-atom chunks of the ranked order,
+ *                          n < 0 = |n| interleaved per-atom chunks (the forms the oracle's gs_chunks emulates)
  * Order-dependent validation is the reference's (e.g. "zodid" errors while polar_gs_ranked is on). */
 int polb200_settings(polb200_t *h, int narg, const char *const *arg);
 /* Atom::ntypes; allocates the (ntypes+1)^2 coefficient arrays = allocate(), pol.cpp:651-672 */
@@ -74,7 +77,8 @@ typedef struct {
   double qqrd2e;           /* force->qqrd2e */
   double special_lj[4];    /* force->special_lj */
   double special_coul[4];  /* force->special_coul */
-  int newton_pair;         /* force->newton_pair (only 1 is supported on the device path) */
+  int newton_pair;         /* force->newton_pair (0 and 1: the owner-computes device path serves both; `newton off` selects the
+                              pairwise virial tally, as in the reference) */
   double skin;             /* neighbor->skin */
   int neigh_every, neigh_delay, neigh_check; /* neigh_modify every/delay/check (1,10,1) */
   int kspace_present;      /* 0 => "Pair style requires a KSpace style" */
@@ -102,6 +106,16 @@ int polb200_single(const polb200_t *h, int itype, int jtype, double qi, double q
 int polb200_restart_size(const polb200_t *h, long *nbytes);
 int polb200_write_restart(const polb200_t *h, void *buf, long nbytes);
 int polb200_read_restart(polb200_t *h, const void *buf, long nbytes);
+/* The settings block alone = the first polb200_restart_settings_size() bytes of the image: what
+ * write_restart_settings / read_restart_settings exchange (pol.cpp:976-1009; PairHybrid calls exactly these for its
+ * sub-styles, src/pair_hybrid.cpp:650,691).  40 bytes in the reference's layout; with the extension keyword
+ * `restart_keywords yes` an 88-byte record with every polarization keyword follows (magic "POLB2KW1"; such files are not
+ * readable by the reference, which stores none of them).  polb200_read_restart_settings accepts both forms and reports
+ * the bytes it consumed: a caller reading a stream reads 40 bytes, peeks 8 more, and reads 80 more when they are the
+ * magic.  ABI version 5. */
+#define POLB200_RESTART_MAGIC "POLB2KW1"
+int polb200_restart_settings_size(const polb200_t *h, long *nbytes);
+int polb200_read_restart_settings(polb200_t *h, const void *buf, long nbytes, long *consumed);
 
 /* `neigh_modify exclude ...` (src/neighbor.cpp:2276-2333): the rules of NPair::exclusion (src/npair.cpp:173-203), at most 8.
  * The reference removes excluded pairs from the list its LJ / real-space Coulomb loop walks (pol.cpp:232-321) and from
@@ -122,6 +136,9 @@ int polb200_set_box(polb200_t *h, const double boxlo[3], const double boxhi[3], 
 
 /* ---- the hot path ------------------------------------------------------------------------------ */
 
+/* x, q, type, alpha, mu and f are required (POLB200_ERR_ARG otherwise).  x, mu, q and alpha are read on every call;
+ * type, molecule, tag, mask and the special lists are sampled at the rebuilds (calls with ago == 0, or whenever the
+ * library's own schedule decides to rebuild). */
 typedef struct {
   int nlocal;
   const double *x;          /* [nlocal][3] AoS, atom->x[0]  (host or device pointer, see `on_device`) */
@@ -340,15 +357,20 @@ double polb200_rigid_last_ms(const polb200_rigid_t *r); /* CUDA-event time of th
 
 /* ---- introspection for tests and profiling ------------------------------------------------------ */
 
-/* Copy an internal device array to host.  names: "perm" (int nlocal: sorted->caller index),
- * "ghost_owner" (int nghost, caller index), "ghost_shift" (int nghost*3), "numneigh" (int nlocal, caller
- * order), "neigh_canon" (canonical full list, see tests), "ef_static", "mu", "rank_metric", "ranked".
- * Returns number of elements copied or <0. */
+/* Copy internal state to host (tests, profiling).  Device arrays: "perm" (int nlocal: cell-sorted -> caller index), "tag",
+ * "ghost_owner" (int nghost: cell-sorted owner index), "ghost_shift" (int nghost: packed image code), "rowstart" (u64
+ * nlocal+1), "neigh" (int: full list, entry = ext index | special << 30), "xq" / "mua" (double4 per owned+ghost atom), "ef"
+ * (double4 per owned atom), "ranked", "metric", "flags"; "gs_colouring" (int 2*nlocal+3: colour and in-group predecessor
+ * of every atom in caller order, then {colours, colouring rounds, groups}).  Statistics: "sweep_timing", "polar_pairs",
+ * "group_stats", "comm_stats", "barrier_stats".  Host tables: "h_rtable" ... "h_cutneighsq", "h_tabmeta".
+ * Returns the number of elements copied or < 0. */
 long polb200_debug_fetch(polb200_t *h, const char *name, void *dst, long capacity_bytes);
 /* number of kernel launches issued by this handle since creation / since last reset */
 long polb200_launch_count(polb200_t *h, int reset);
-/* knobs for experiments: "exact_threshold" (atoms; use all-pairs path when polar_cutoff is none and
- * nlocal <= threshold), "sweep_variant", "block_size" ... returns POLB200_ERR_ARG for unknown names */
+/* knobs for experiments and A/B measurements: "sweep_variant" (41 = TMA-fed pair-group sweep, default; 40 / 44; 30 / 31
+ * register-prefetch pair groups; 20 / 21 per-atom rows + radial cache; 6 matrix-free; 0 first version), "bin_div",
+ * "xsort_bits", "gs_blocked", "gs_colours", "gs_strong_m", "scf_lag", "use_group_pairs", "gpf_minb", "use_tight",
+ * "use_push", "p2p_push", "l2_evict_first", "alternate", "time_sweeps".  POLB200_ERR_ARG for unknown names. */
 int polb200_set_option(polb200_t *h, const char *name, double value);
 
 #ifdef __cplusplus

@@ -115,6 +115,37 @@ static void comm_allreduce(polb200_handle *h, void *dptr, size_t count, ncclData
   NCCL_CHECK(g_nccl.AllReduce(dptr, dptr, count, t, op, h->comm.nccl, h->stream));
 }
 
+// Collective agreement on an error: every brick contributes its local error code (0 = fine), all get the largest.
+// A brick that fails alone -- before or between collectives -- would leave the others blocked in NCCL or spinning in the
+// peer barrier until the timeout; with this every brick throws the same error at the same point instead.
+enum { COMM_OK = 0, COMM_ERR_EMPTY = 1, COMM_ERR_OVERFLOW = 2, COMM_ERR_ALLOC = 3, COMM_ERR_SUBDOMAIN = 4 };
+static int comm_agree(polb200_handle *h, int local_err)
+{
+  h->flags.ensure(8);
+  int *flag = h->flags.p + 5;
+  int v = local_err;
+  CUDA_CHECK(cudaMemcpyAsync(flag, &v, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  comm_allreduce(h, flag, 1, ncclInt, ncclMax);
+  CUDA_CHECK(cudaMemcpyAsync(&v, flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  return v;
+}
+
+static void comm_throw(int err)
+{
+  switch (err) {
+    case COMM_OK: return;
+    case COMM_ERR_EMPTY:
+      throw StyleError{POLB200_ERR_UNSUPPORTED, "a brick of the decomposition owns no atoms"};
+    case COMM_ERR_OVERFLOW:
+      throw StyleError{POLB200_ERR_OVERFLOW, "owned+ghost atoms of a brick exceed the 30-bit neighbor index"};
+    case COMM_ERR_SUBDOMAIN:
+      throw StyleError{POLB200_ERR_UNSUPPORTED, "neighbor cutoff exceeds the sub-domain length of a brick"};
+    default:
+      throw CudaError{"a brick of the decomposition could not allocate its device arrays (cudaMalloc failed)"};
+  }
+}
+
 static void comm_close_peers(polb200_handle *h)
 {
   CommState &c = h->comm;
@@ -200,10 +231,15 @@ static void comm_build_ghosts(polb200_handle *h, int n)
   const HostStyle &st = h->style;
   const Grid &g = h->P.grid;
   if (!c.geom_valid) comm_setup_geom(h);
-  for (int k = 0; k < 3; k++) {
-    const double len = c.plan.subhi[k] - c.plan.sublo[k];
-    if ((h->box.periodic[k] || c.pg[k] > 1) && st.cutneighmax > len)
-      throw StyleError{POLB200_ERR_UNSUPPORTED, "neighbor cutoff exceeds the sub-domain length of a brick"};
+  {
+    // first collective of every rebuild: local preconditions, agreed by all bricks (a brick that was handed no atoms
+    // takes part in this agreement from compute_impl and nothing else)
+    int err = COMM_OK;
+    for (int k = 0; k < 3; k++) {
+      const double len = c.plan.subhi[k] - c.plan.sublo[k];
+      if ((h->box.periodic[k] || c.pg[k] > 1) && st.cutneighmax > len) err = COMM_ERR_SUBDOMAIN;
+    }
+    comm_throw(comm_agree(h, err));
   }
   c.geom.cut = st.cutneighmax;
 
@@ -274,8 +310,7 @@ static void comm_build_ghosts(polb200_handle *h, int n)
     nrecv += c.recv_cnt[d];
   }
   c.nrecv = nrecv;
-  if ((long)n + nrecv >= (1l << 30))
-    throw StyleError{POLB200_ERR_OVERFLOW, "owned+ghost atoms exceed the 30-bit neighbor index"};
+  const int overflow = ((long)n + nrecv >= (1l << 30)) ? 1 : 0;  // agreed below, together with `moved`
   const int ng = nrecv;
   h->nghost = ng;
   const size_t next = (size_t)n + ng;
@@ -291,10 +326,12 @@ static void comm_build_ghosts(polb200_handle *h, int n)
   int moved = (next > h->mua.cap || next > h->mub.cap || next > h->xq.cap || c.mapped_ptr[0] != h->mua.p ||
                c.mapped_ptr[1] != h->mub.p || c.mapped_ptr[2] != c.flags.p || c.mapped_ptr[3] != h->xq.p) ? 1 : 0;
   int *flag = h->flags.p + 2;
+  moved += 2 * overflow;  // one all-reduce carries both
   CUDA_CHECK(cudaMemcpyAsync(flag, &moved, sizeof(int), cudaMemcpyHostToDevice, h->stream));
   comm_allreduce(h, flag, 1, ncclInt, ncclMax);
   CUDA_CHECK(cudaMemcpyAsync(&moved, flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  if (moved >= 2) comm_throw(COMM_ERR_OVERFLOW);
   if (moved) {
     comm_close_peers(h);
     comm_allreduce(h, flag, 1, ncclInt, ncclMax);  // barrier: every rank has closed its mappings
@@ -302,18 +339,25 @@ static void comm_build_ghosts(polb200_handle *h, int n)
     for (void *q : c.graveyard) cudaFree(q);
     c.graveyard.clear();
   }
-  grow_ext(h, n, next);
-  if (moved) {
-    for (void *q : c.graveyard) cudaFree(q);  // replaced just now, and no peer maps anything at this point
-    c.graveyard.clear();
-  }
-  c.sbuf.ensure(ns + 1); c.rbuf.ensure(ng + 1);
-  c.sbufi.ensure(ns + 1); c.rbufi.ensure(ng + 1);
-  c.gslot.ensure(ng + 1);
-  h->g_shift.ensure(ng + 1);
   const int nmax2 = std::max(nmax, ng);
-  h->keys.ensure(nmax2); h->keys2.ensure(nmax2); h->vals.ensure(nmax2); h->vals2.ensure(nmax2);
-  h->cg_start.ensure(g.ncell + 2);
+  int alloc_err = COMM_OK;
+  try {
+    grow_ext(h, n, next);
+    if (moved) {
+      for (void *q : c.graveyard) cudaFree(q);  // replaced just now, and no peer maps anything at this point
+      c.graveyard.clear();
+    }
+    c.sbuf.ensure(ns + 1); c.rbuf.ensure(ng + 1);
+    c.sbufi.ensure(ns + 1); c.rbufi.ensure(ng + 1);
+    c.gslot.ensure(ng + 1);
+    h->g_shift.ensure(ng + 1);
+    h->keys.ensure(nmax2); h->keys2.ensure(nmax2); h->vals.ensure(nmax2); h->vals2.ensure(nmax2);
+    h->cg_start.ensure(g.ncell + 2);
+  } catch (const CudaError &) {
+    cudaGetLastError();
+    alloc_err = COMM_ERR_ALLOC;
+  }
+  comm_throw(comm_agree(h, alloc_err));  // a brick out of memory must not leave the others in the exchange below
   if (ns) LAUNCH(h, k_pack_pos, cdiv(ns, 256), 256, ns, c.send_owner.p, c.send_dir.p, c.geom, h->xq.p, c.sbuf.p);
   comm_exchange(h, c.sbuf.p, c.rbuf.p, sizeof(double4));
   if (ng) {

@@ -844,9 +844,13 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
   memset(out, 0, sizeof(*out));
   const bool comm = h->comm.active;
   if (n <= 0) {
-    if (comm) throw StyleError{POLB200_ERR_UNSUPPORTED, "a brick of the decomposition owns no atoms"};
+    // decomposed: bricks are only re-populated at rebuild steps, whose first collective is the error agreement of
+    // comm_build_ghosts -- take part in it so that every brick stops with the same message
+    if (comm) comm_throw(std::max(comm_agree(h, COMM_ERR_EMPTY), (int)COMM_ERR_EMPTY));
     return;
   }
+  if (!at->x || !at->q || !at->type || !at->alpha || !at->mu || !at->f)
+    throw StyleError{POLB200_ERR_ARG, "polb200_compute: the arrays x, q, type, alpha, mu and f are required"};
   const bool dev = at->on_device != 0;
   const bool list_mode = st.polar_cutoff > 0.0;
   if (comm && !list_mode)
@@ -879,7 +883,9 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
   if (ago < 0) need = decide_rebuild(h, n);
   if (need) rebuild(h, at);
   else {
-    LAUNCH(h, k_refresh_local, cdiv(n, 256), 256, n, h->perm.p, h->c_x.p, h->c_mu.p, h->xq.p, h->mua.p);
+    stage_in(h, h->c_q, at->q, n, dev);
+    stage_in(h, h->c_alpha, at->alpha, n, dev);
+    LAUNCH(h, k_refresh_local, cdiv(n, 256), 256, n, h->perm.p, h->c_x.p, h->c_mu.p, h->c_q.p, h->c_alpha.p, h->xq.p, h->mua.p);
     // (peer push: the neighbours may still be reading these ghosts in their previous step => barrier first)
     ghost_update(h, true, h->mua.p, true);
   }
@@ -1605,6 +1611,23 @@ int polb200_write_restart(const polb200_t *h, void *buf, long nbytes)
   if ((long)img.size() > nbytes) return POLB200_ERR_ARG;
   memcpy(buf, img.data(), img.size());
   return POLB200_OK;
+}
+
+int polb200_restart_settings_size(const polb200_t *h, long *nbytes)
+{
+  if (!h || !nbytes) return POLB200_ERR_ARG;
+  *nbytes = (long)h->style.restart_settings_image().size();
+  return POLB200_OK;
+}
+
+int polb200_read_restart_settings(polb200_t *h, const void *buf, long nbytes, long *consumed)
+{
+  if (!h || !buf) return POLB200_ERR_ARG;
+  return guarded(h, [&] {
+    const long used = h->style.read_restart_settings_image(buf, nbytes);
+    if (consumed) *consumed = used;
+    h->params_uploaded = false;
+  });
 }
 
 int polb200_read_restart(polb200_t *h, const void *buf, long nbytes)

@@ -100,7 +100,8 @@ void HostStyle::settings(int narg, const char *const *arg)
       }
     } else if (!strcmp(key, "gs_chunks")) {
       gs_chunks = inumeric(val);  // n > 0: contiguous chunks of the ranked order; n < 0: |n| interleaved chunks; 0: default
-    } else fail(illegal);
+    } else if (!strcmp(key, "restart_keywords")) restart_keywords = yesno(val, illegal);
+    else fail(illegal);
   }
 
   // "reset cutoffs that have been explicitly set" (pol.cpp:760-765)
@@ -403,13 +404,59 @@ void HostStyle::tail_correction(int i, int j, double count_i, double count_j, do
 
 // (cut_lj_global, cut_coul, offset_flag, mix_flag, tail_flag, ncoultablebits, tabinner; pol.cpp:976-985)
 // then per i<=j: setflag and, if set, epsilon, sigma, cut_lj (pol.cpp:931-940).
-std::vector<char> HostStyle::restart_image() const
+// Keyword extension record.  The reference's settings block holds 7 fields and none of the polarization keywords
+// (pol.cpp:976-985), and the restart format has no length prefix a foreign reader could use to skip unknown data, so the
+// record is opt-in (`restart_keywords yes`): files written without it stay byte-identical to the reference's.  A reader
+// recognises it by its magic -- what follows the settings in a reference-written file is an int 0/1 (the first setflag)
+// or the next section of the file, never this byte string.
+static const char RESTART_MAGIC[8] = {'P', 'O', 'L', 'B', '2', 'K', 'W', '1'};
+static const long RESTART_SETTINGS_BYTES = 40, RESTART_EXT_BYTES = 88;
+
+std::vector<char> HostStyle::restart_settings_image() const
 {
   std::vector<char> out;
   auto put = [&](const void *p, size_t n) { out.insert(out.end(), (const char *)p, (const char *)p + n); };
   put(&cut_lj_global, 8); put(&cut_coul, 8);
   put(&offset_flag, 4); put(&mix_flag, 4); put(&tail_flag, 4); put(&ncoultablebits, 4);
   put(&tabinner, 8);
+  if (restart_keywords) {
+    put(RESTART_MAGIC, 8);
+    put(&polar_precision, 8); put(&polar_damp, 8); put(&polar_gamma, 8); put(&polar_cutoff, 8);
+    const int ints[12] = {iterations_max, damping_type, zodid, fixed_iteration, polar_gs, polar_gs_ranked,
+                          use_previous, debug, gs_chunks, restart_keywords, 0, 0};
+    put(ints, sizeof(ints));
+  }
+  return out;
+}
+
+long HostStyle::read_restart_settings_image(const void *buf, long nbytes)
+{
+  const char *p = (const char *)buf, *end = p + nbytes;
+  auto get = [&](void *dst, size_t n) {
+    if (p + n > end) fail("restart image truncated");
+    memcpy(dst, p, n);
+    p += n;
+  };
+  get(&cut_lj_global, 8); get(&cut_coul, 8);
+  get(&offset_flag, 4); get(&mix_flag, 4); get(&tail_flag, 4); get(&ncoultablebits, 4);
+  get(&tabinner, 8);
+  if (end - p >= 8 && memcmp(p, RESTART_MAGIC, 8) == 0) {
+    p += 8;
+    get(&polar_precision, 8); get(&polar_damp, 8); get(&polar_gamma, 8); get(&polar_cutoff, 8);
+    int ints[12];
+    get(ints, sizeof(ints));
+    iterations_max = ints[0]; damping_type = ints[1]; zodid = ints[2]; fixed_iteration = ints[3];
+    polar_gs = ints[4]; polar_gs_ranked = ints[5]; use_previous = ints[6]; debug = ints[7];
+    gs_chunks = ints[8]; restart_keywords = ints[9];
+  }
+  initialized = false;
+  return (long)(p - (const char *)buf);
+}
+
+std::vector<char> HostStyle::restart_image() const
+{
+  std::vector<char> out = restart_settings_image();
+  auto put = [&](const void *p, size_t n) { out.insert(out.end(), (const char *)p, (const char *)p + n); };
   for (int i = 1; i <= ntypes; i++)
     for (int j = i; j <= ntypes; j++) {
       put(&setflag[idx(i, j)], 4);
@@ -420,16 +467,14 @@ std::vector<char> HostStyle::restart_image() const
 
 void HostStyle::read_restart_image(const void *buf, long nbytes)
 {
-  const char *p = (const char *)buf, *end = p + nbytes;
+  if (!allocated) fail("polb200_set_ntypes must be called before polb200_read_restart", POLB200_ERR_STATE);
+  const long used = read_restart_settings_image(buf, nbytes);
+  const char *p = (const char *)buf + used, *end = (const char *)buf + nbytes;
   auto get = [&](void *dst, size_t n) {
     if (p + n > end) fail("restart image truncated");
     memcpy(dst, p, n);
     p += n;
   };
-  if (!allocated) fail("polb200_set_ntypes must be called before polb200_read_restart", POLB200_ERR_STATE);
-  get(&cut_lj_global, 8); get(&cut_coul, 8);
-  get(&offset_flag, 4); get(&mix_flag, 4); get(&tail_flag, 4); get(&ncoultablebits, 4);
-  get(&tabinner, 8);
   for (int i = 1; i <= ntypes; i++)
     for (int j = i; j <= ntypes; j++) {
       get(&setflag[idx(i, j)], 4);

@@ -40,6 +40,10 @@ class HostStyle {
                        double &ptail_ij) const;            // pol.cpp:897-918 (pair_modify tail yes)
   std::vector<char> restart_image() const;                 // pol.cpp:927-941,976-985
   void read_restart_image(const void *buf, long nbytes);   // pol.cpp:947-970,991-1009
+  // the settings block alone (write_restart_settings / read_restart_settings, pol.cpp:976-1009): 40 bytes in the
+  // reference's layout, followed -- only when `restart_keywords yes` was given -- by the keyword extension record
+  std::vector<char> restart_settings_image() const;
+  long read_restart_settings_image(const void *buf, long nbytes);  // returns the bytes consumed
 
   int idx(int i, int j) const { return i * (ntypes + 1) + j; }
 
@@ -51,6 +55,8 @@ class HostStyle {
   // extensions
   double polar_cutoff = 0.0;  // <= 0: none (reference all-pairs minimum image)
   int gs_chunks = 0;
+  int restart_keywords = 0;   // 1: restart files also carry the polarization keywords (extension record; such a file is
+                              // no longer readable by the reference binary, which stores none of them)
 
   // Pair base-class state that shapes this style (src/pair.cpp:82-88)
   int offset_flag = 0, mix_flag = MIX_GEOMETRIC, tail_flag = 0, ncoultablebits = 12;

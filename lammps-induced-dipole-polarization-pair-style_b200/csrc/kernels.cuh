@@ -218,17 +218,17 @@ __global__ void k_gather_local(int n, const int *__restrict__ perm, const double
 }
 
 // per-step refresh (no rebuild): positions and dipoles of owned atoms from caller order
+// (charges and polarizabilities are re-read every step as well: a fix may change them between two rebuilds)
 __global__ void k_refresh_local(int n, const int *__restrict__ perm, const double *__restrict__ x,
-                                const double *__restrict__ mu, double4 *__restrict__ xq,
+                                const double *__restrict__ mu, const double *__restrict__ q,
+                                const double *__restrict__ alpha, double4 *__restrict__ xq,
                                 double4 *__restrict__ mua)
 {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
   int c = perm[s];
-  double4 v = xq[s];
-  xq[s] = make_double4(x[3 * c], x[3 * c + 1], x[3 * c + 2], v.w);
-  double4 m = mua[s];
-  mua[s] = make_double4(mu[3 * c], mu[3 * c + 1], mu[3 * c + 2], m.w);
+  xq[s] = make_double4(x[3 * c], x[3 * c + 1], x[3 * c + 2], q[c]);
+  mua[s] = make_double4(mu[3 * c], mu[3 * c + 1], mu[3 * c + 2], alpha[c]);
 }
 
 // which of the 26 periodic images of an owned atom fall inside the ghost shell

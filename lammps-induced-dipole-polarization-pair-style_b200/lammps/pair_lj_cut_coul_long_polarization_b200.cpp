@@ -296,43 +296,41 @@ void PairLJCutCoulLongPolarization::write_restart(FILE *fp)
 
 void PairLJCutCoulLongPolarization::write_restart_settings(FILE *fp)
 {
-  long nbytes = 0;
+  long nbytes = 0, nset = 0;
   CHECK(polb200_restart_size(handle, &nbytes));
+  CHECK(polb200_restart_settings_size(handle, &nset));
   std::vector<char> img(nbytes);
   CHECK(polb200_write_restart(handle, img.data(), nbytes));
-  fwrite(img.data(), 1, 40, fp);       // the 7 settings fields (2 doubles, 4 ints, 1 double)
+  // the 7 settings fields (2 doubles, 4 ints, 1 double) [+ the keyword record of `restart_keywords yes`]
+  fwrite(img.data(), 1, nset, fp);
 }
 
-void PairLJCutCoulLongPolarization::read_restart(FILE *fp)
+// the settings block as bytes: rank 0 reads, everybody gets it (pol.cpp:991-1009).  A keyword record follows the 7
+// reference fields only in files written with `restart_keywords yes`; it announces itself with its magic.
+static void read_settings_block(FILE *fp, int me, MPI_Comm world, Error *error, std::vector<char> &img)
 {
-  ensure_types();
-  const int n = atom->ntypes;
-  std::vector<char> img;
   int len = 0;
-  if (comm->me == 0) {
+  if (me == 0) {
     img.resize(40);
     if (fread(img.data(), 1, 40, fp) != 40) error->one(FLERR,"Unexpected end of restart file");
-    for (int i = 1; i <= n; i++)
-      for (int j = i; j <= n; j++) {
-        int flag = 0;
-        if (fread(&flag, sizeof(int), 1, fp) != 1) error->one(FLERR,"Unexpected end of restart file");
-        img.insert(img.end(), (char *) &flag, (char *) &flag + sizeof(int));
-        if (flag) {
-          char rec[24];
-          if (fread(rec, 1, 24, fp) != 24) error->one(FLERR,"Unexpected end of restart file");
-          img.insert(img.end(), rec, rec + 24);
-        }
-      }
+    char peek[8];
+    const long pos = ftell(fp);
+    const size_t got = fread(peek, 1, 8, fp);
+    if (got == 8 && memcmp(peek, POLB200_RESTART_MAGIC, 8) == 0) {
+      img.insert(img.end(), peek, peek + 8);
+      char rest[80];
+      if (fread(rest, 1, 80, fp) != 80) error->one(FLERR,"Unexpected end of restart file");
+      img.insert(img.end(), rest, rest + 80);
+    } else fseek(fp, pos, SEEK_SET);
     len = (int) img.size();
   }
   MPI_Bcast(&len, 1, MPI_INT, 0, world);
   img.resize(len);
   MPI_Bcast(img.data(), len, MPI_CHAR, 0, world);
-  CHECK(polb200_read_restart(handle, img.data(), len));
-  int dim;
-  const int *flags = (const int *) polb200_extract(handle, "setflag", &dim);
-  for (int i = 1; i <= n; i++)
-    for (int j = i; j <= n; j++) setflag[i][j] = flags[i * (n + 1) + j];
+}
+
+void PairLJCutCoulLongPolarization::apply_settings_block(const std::vector<char> &img)
+{
   // base-class copies of the settings that Pair::init()/modify_params consult
   memcpy(&offset_flag, img.data() + 16, 4);
   memcpy(&mix_flag, img.data() + 20, 4);
@@ -341,9 +339,46 @@ void PairLJCutCoulLongPolarization::read_restart(FILE *fp)
   memcpy(&tabinner, img.data() + 32, 8);
 }
 
-void PairLJCutCoulLongPolarization::read_restart_settings(FILE *)
+void PairLJCutCoulLongPolarization::read_restart_settings(FILE *fp)
 {
-  // the settings travel with read_restart() (the library reads the reference's record layout in one piece)
+  std::vector<char> img;
+  read_settings_block(fp, comm->me, world, error, img);
+  CHECK(polb200_read_restart_settings(handle, img.data(), (long) img.size(), NULL));
+  apply_settings_block(img);
+}
+
+void PairLJCutCoulLongPolarization::read_restart(FILE *fp)
+{
+  ensure_types();
+  const int n = atom->ntypes;
+  std::vector<char> img;
+  read_settings_block(fp, comm->me, world, error, img);   // = read_restart_settings(fp) of the reference (:949)
+  std::vector<char> pairs;
+  int len = 0;
+  if (comm->me == 0) {
+    for (int i = 1; i <= n; i++)
+      for (int j = i; j <= n; j++) {
+        int flag = 0;
+        if (fread(&flag, sizeof(int), 1, fp) != 1) error->one(FLERR,"Unexpected end of restart file");
+        pairs.insert(pairs.end(), (char *) &flag, (char *) &flag + sizeof(int));
+        if (flag) {
+          char rec[24];
+          if (fread(rec, 1, 24, fp) != 24) error->one(FLERR,"Unexpected end of restart file");
+          pairs.insert(pairs.end(), rec, rec + 24);
+        }
+      }
+    len = (int) pairs.size();
+  }
+  MPI_Bcast(&len, 1, MPI_INT, 0, world);
+  pairs.resize(len);
+  MPI_Bcast(pairs.data(), len, MPI_CHAR, 0, world);
+  img.insert(img.end(), pairs.begin(), pairs.end());
+  CHECK(polb200_read_restart(handle, img.data(), (long) img.size()));
+  int dim;
+  const int *flags = (const int *) polb200_extract(handle, "setflag", &dim);
+  for (int i = 1; i <= n; i++)
+    for (int j = i; j <= n; j++) setflag[i][j] = flags[i * (n + 1) + j];
+  apply_settings_block(img);
 }
 
 /* ---------------------------------------------------------------------- data file: eps/sigma like the reference */

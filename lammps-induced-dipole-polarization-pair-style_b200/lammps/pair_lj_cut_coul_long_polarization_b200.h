@@ -17,6 +17,7 @@ PairStyle(lj/cut/coul/long/polarization,PairLJCutCoulLongPolarization)
 #define LMP_PAIR_LJ_CUT_COUL_LONG_POLARIZATION_H
 
 #include "pair.h"
+#include <vector>
 
 struct polb200_handle;
 
@@ -55,6 +56,7 @@ class PairLJCutCoulLongPolarization : public Pair {
   double **epsilon_rows, **sigma_rows;  // row tables over the library's flat arrays, for extract()
 
   void ensure_types();
+  void apply_settings_block(const std::vector<char> &img);
   void check(int rc, const char *file, int line);
   void sync_modify_params();
   void free_rows();

@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "polb200_abi_version", "polb200_create", "polb200_destroy", "polb200_last_error", "polb200_settings",
     "polb200_set_ntypes", "polb200_coeff", "polb200_pair_modify", "polb200_init", "polb200_init_one",
     "polb200_extract", "polb200_single", "polb200_restart_size", "polb200_write_restart",
-    "polb200_read_restart", "polb200_set_box", "polb200_compute", "polb200_comm_id_size",
+    "polb200_read_restart", "polb200_restart_settings_size", "polb200_read_restart_settings", "polb200_set_box", "polb200_compute", "polb200_comm_id_size",
     "polb200_comm_create_id", "polb200_comm_init", "polb200_subdomain", "polb200_debug_fetch",
     "polb200_launch_count", "polb200_set_option", "polb200_decomp_plan", "polb200_tail", "polb200_set_exclusions",
     "polb200_ewald_create", "polb200_ewald_destroy", "polb200_ewald_last_error", "polb200_ewald_init",
@@ -357,6 +357,18 @@ class PairStyle:
     def read_restart(self, image):
         buf = C.create_string_buffer(image, len(image))
         self._check(lib().polb200_read_restart(self._h, buf, len(image)))
+
+    def restart_settings_size(self):
+        n = C.c_long()
+        self._check(lib().polb200_restart_settings_size(self._h, C.byref(n)))
+        return n.value
+
+    def read_restart_settings(self, image):
+        """the settings block alone (what PairHybrid hands its sub-styles); returns the bytes consumed"""
+        buf = C.create_string_buffer(image, len(image))
+        used = C.c_long()
+        self._check(lib().polb200_read_restart_settings(self._h, buf, len(image), C.byref(used)))
+        return used.value
 
     def set_box(self, boxlo, boxhi, periodic=(1, 1, 1)):
         lo = (C.c_double * 3)(*[float(v) for v in boxlo])

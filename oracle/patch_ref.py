@@ -80,7 +80,7 @@ def patch_pair(path: Path):
                  "  polb200_dump::post(atom,domain,force,list,eflag,vflag,iterations,eng_vdwl,eng_coul,\n"
                  "                     eng_pol,virial,g_ewald,cut_coul,tabinnersq,ncoultablebits,ncoulmask,\n"
                  "                     ncoulshiftbits,rtable,drtable,ftable,dftable,ctable,dctable,etable,\n"
-                 "                     detable,cutsq,cut_ljsq,lj1,lj2,lj3,lj4,offset);\n}\n",
+                 "                     detable,cutsq,cut_ljsq,lj1,lj2,lj3,lj4,offset,neighbor->ago);\n}\n",
                  what="post hook")
     path.write_text(t)
 

@@ -48,7 +48,7 @@ static inline void post(LAMMPS_NS::Atom *atom, LAMMPS_NS::Domain *domain, LAMMPS
                         const double *dftable, const double *ctable, const double *dctable,
                         const double *etable, const double *detable,
                         double **cutsq, double **cut_ljsq, double **lj1, double **lj2,
-                        double **lj3, double **lj4, double **offset)
+                        double **lj3, double **lj4, double **offset, int neighbor_ago)
 {
   const char *prefix = getenv("POLB200_DUMP");
   if (!prefix) return;
@@ -63,6 +63,7 @@ static inline void post(LAMMPS_NS::Atom *atom, LAMMPS_NS::Domain *domain, LAMMPS
   reci(fp,"nlocal",nlocal); reci(fp,"nghost",nghost); reci(fp,"ntypes",nt);
   reci(fp,"eflag",eflag); reci(fp,"vflag",vflag); reci(fp,"iterations",iterations);
   reci(fp,"newton_pair",force->newton_pair);
+  reci(fp,"neighbor_ago",neighbor_ago);   /* Neighbor::ago: 0 on the steps the lists were rebuilt (src/neighbor.cpp:1923-1937) */
   reci(fp,"ncoultablebits",ncoultablebits); reci(fp,"ncoulmask",ncoulmask);
   reci(fp,"ncoulshiftbits",ncoulshiftbits);
   rec(fp,"boxlo",'d',3,domain->boxlo); rec(fp,"boxhi",'d',3,domain->boxhi);

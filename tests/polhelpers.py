@@ -11,7 +11,7 @@ GOLDEN = Path(__file__).resolve().parent / "golden"
 
 def golden_cases():
     """fixtures of single compute() calls of the pair style (the ewald_* fixtures belong to the KSpace tests)"""
-    return sorted(p.stem for p in GOLDEN.glob("*.npz") if not p.stem.startswith(("ewald_", "rigid_", "pppm_")))
+    return sorted(p.stem for p in GOLDEN.glob("*.npz") if not p.stem.startswith(("ewald_", "rigid_", "pppm_", "ago_")))
 
 
 def load_fixture(name):

@@ -502,6 +502,49 @@ def test_group_coloured_gauss_seidel_is_iteration_for_iteration_the_oracle(style
         assert H.rel_err(mu2, ref2["mu"]) < TOL
 
 
+def test_mof_supercell_list_mode_matches_oracle(style):
+    """BASELINE config 4's shape at reduced size: the reference's MOF-5 + CO2 example cell replicated 2 x 2 x 2 (7392 atoms,
+    10 atom types, bond topology = special lists with special_lj/coul weights, 808 molecules), polar_cutoff = cut_coul,
+    the reference's default solver (polar_gs_ranked yes, precision mode) on the group-coloured sweep.  LJ + Coulomb (special
+    bonds, tables) against the literal oracle, polarization (static field, dipoles, forces, energy) against the row oracle
+    replaying the device's colouring; fixed point against the strictly sequential ranked sweep."""
+    from gpu_common import c
+    W = H._workloads()
+    fx = H.load_fixture("co2_singlepoint_step0")
+    w, cut, coeff = W.mof_supercell(H.GOLDEN / "co2_singlepoint_step0.npz", 2)
+    assert w.n == 7392 and int(w.molecule.max()) == 808
+    sysm = P.System(w.x, w.q, w.type, w.molecule, w.alpha, w.boxlo, w.boxhi, w.ntypes, tag=w.tag, nspecial=w.nspecial,
+                    special=w.special)
+    kw = dict(polar_cut=cut, damp_type="exponential", damp=2.1304, polar_gs_ranked=1, precision=1e-11, max_iterations=200,
+              polar_gamma=1.03, zodid=0, fixed_iteration=0, use_previous=0)
+    st = H.style_from_fixture(fx, **kw)
+    configure_from_fixture(style, fx, extra_words=[f"polar_cutoff {cut}", "precision 1e-11", "max_iterations 200",
+                                                   "use_previous no"])
+    style.set_box(sysm.boxlo, sysm.boxhi)
+    res, mu, ef, f = run_system(style, sysm)
+    assert not (res.status & (pb.STATUS_DIVERGED | pb.STATUS_EXACT))
+    n = sysm.n
+    colour, after, ncol, rounds, ngroups = _colouring(style, n)
+    ref = P.polar_rows(sysm, st, colouring=(colour, after, ncol))
+    assert res.iterations == ref["iterations"], (res.iterations, ref["iterations"])
+    assert H.rel_err(ef, ref["ef_static"]) < TOL and H.rel_err(mu, ref["mu"]) < TOL
+    assert abs(res.eng_pol - ref["eng_pol"]) < TOL * abs(ref["eng_pol"])
+    # LJ + real-space Coulomb with the bond topology: literal oracle with the dipoles switched off
+    lit = P.compute(sysm, H.style_from_fixture(fx, **dict(kw, polar_gs_ranked=0, zodid=1, polar_gamma=0.0)))
+    assert abs(res.eng_vdwl - lit["eng_vdwl"]) < TOL * abs(lit["eng_vdwl"])
+    assert abs(res.eng_coul - lit["eng_coul"]) < TOL * abs(lit["eng_coul"])
+    ftot = lit["f"] + ref["f"]
+    assert np.abs(f - ftot).max() < TOL * np.abs(ftot).max()
+    # the reference's own order (strictly sequential ranked sweep): same fixed point within the GS tolerance
+    seq = P.polar_rows(sysm, st)
+    assert np.abs(mu - seq["mu"]).max() < 20 * 1e-11
+    assert res.iterations <= seq["iterations"] + 2, (res.iterations, seq["iterations"])
+    assert abs(res.rmin - seq["rmin"]) < 1e-12 * seq["rmin"]
+    # second step on the same lists (no rebuild): rmin now comes out of the group cache, the colouring is kept
+    res2, mu2, _, f2 = run_system(style, sysm, ago=1)
+    assert res2.rmin == res.rmin and res2.iterations == res.iterations and np.array_equal(mu2, mu)
+
+
 def test_group_coloured_sweep_stop_flag_and_lag_do_not_change_the_result():
     """the host looks at the device's stop flag one iteration late (the iteration enqueued meanwhile is skipped by every
     kernel): identical dipoles, iteration counts and energies with and without the lag, in Jacobi and Gauss-Seidel

@@ -42,7 +42,7 @@ def test_library_exports_every_declared_symbol():
     L = pb.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.polb200_abi_version() == 4
+    assert L.polb200_abi_version() == 5
 
 
 def test_compute_without_device_fails_loudly(style):
@@ -164,6 +164,60 @@ def test_restart_roundtrip(style):
     b, _ = other.extract("sigma")
     assert np.array_equal(a, b) and other.extract("cut_coul")[0] == 10.797442
     other.close()
+
+
+def test_restart_settings_block_is_what_pair_hybrid_exchanges(style):
+    """PairHybrid writes / reads only the settings of its sub-styles (src/pair_hybrid.cpp:650,691): the block must be read
+    back symmetrically (pol.cpp:976-1009), 40 bytes in the reference's layout, and leave the stream where the reference
+    leaves it."""
+    fx = H.load_fixture("h2_default_step0")
+    configure_from_fixture(style, fx)
+    style.pair_modify(["table", "10", "tabinner", "1.9", "shift", "yes", "mix", "arithmetic"])
+    img = style.write_restart()
+    assert style.restart_settings_size() == 40
+    other = pb.PairStyle(device=pb.DEVICE_NONE)
+    other.set_ntypes(3)
+    stream = img[:40] + b"\x01\x00\x00\x00NEXT-SECTION"      # what follows in a hybrid restart: other records
+    assert other.read_restart_settings(stream) == 40            # consumed exactly the reference's 7 fields
+    assert other.extract("cut_coul")[0] == 10.797442
+    assert other.write_restart()[:40] == img[:40]               # offset / mix / table bits / tabinner came back too
+    other.close()
+
+
+def test_restart_keyword_record_is_opt_in_and_round_trips():
+    """`restart_keywords yes` (extension): the polarization keywords travel in an 88-byte record behind the 7 reference
+    fields; without the keyword the image is byte-identical to the reference's layout.  The reader recognises the record
+    by its magic in either kind of file."""
+    words = ["2.5", "11.0", "precision", "1e-9", "polar_gs_ranked", "no", "zodid", "no", "fixed_iteration", "yes", "damp", "1.7",
+             "max_iterations", "17", "damp_type", "exponential", "polar_gs", "yes", "polar_gamma", "1.1", "use_previous", "yes",
+             "polar_cutoff", "9.5", "gs_chunks", "-4"]
+    a = pb.PairStyle(device=pb.DEVICE_NONE)
+    a.set_ntypes(2)
+    a.settings(words)
+    a.coeff(["*", "*", "0.1", "3.0"])
+    plain = a.write_restart()
+    assert a.restart_settings_size() == 40
+    a.close()
+    a = pb.PairStyle(device=pb.DEVICE_NONE)   # (the keyword checks are order dependent, like the reference's: fresh handle)
+    a.set_ntypes(2)
+    a.settings(words + ["restart_keywords", "yes"])
+    a.coeff(["*", "*", "0.1", "3.0"])
+    ext = a.write_restart()
+    assert a.restart_settings_size() == 128 and ext[:40] == plain[:40] and ext[40:48] == b"POLB2KW1" and ext[128:] == plain[40:]
+    b = pb.PairStyle(device=pb.DEVICE_NONE)
+    b.set_ntypes(2)
+    b.settings(["3.0"])                      # defaults: none of the keywords above
+    assert b.read_restart_settings(ext + b"trailing bytes of the file") == 128
+    b.read_restart(ext)
+    assert b.write_restart() == ext          # every keyword (and the opt-in itself) came back
+    c = pb.PairStyle(device=pb.DEVICE_NONE)
+    c.set_ntypes(2)
+    c.settings(["3.0"])
+    c.read_restart(plain)                    # a reference-layout file: settings and coefficients only
+    assert c.write_restart() == plain[:0] + c.write_restart() and c.write_restart()[:40] == plain[:40]
+    assert len(c.write_restart()) == len(plain)
+    for s in (a, b, c):
+        s.close()
 
 
 def test_pair_modify(style):

@@ -14,7 +14,11 @@ KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'sm__inst_executed_pipe_fp64.sum', 'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
         'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct', 'lts__t_bytes.sum', 'l1tex__t_bytes.sum',
         'smsp__thread_inst_executed_per_inst_executed.ratio', 'sm__cycles_elapsed.max',
-        'launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_mem']
+        'launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_mem',
+        'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed', 'l1tex__data_pipe_lsu_wavefronts.sum',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__data_bank_conflicts_pipe_lsu.sum',
+        'sm__warps_active.avg.per_cycle_active', 'sm__inst_executed_pipe_lsu.sum',
+        'lts__t_sectors_srcunit_tex_op_read.sum', 'lts__t_sectors_srcunit_ltcfabric.sum', 'dram__throughput.avg.pct_of_peak_sustained_elapsed']
 
 
 def run(args):
