@@ -16,6 +16,8 @@
 #ifndef POLB200_H
 #define POLB200_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -354,6 +356,20 @@ int polb200_rigid_reset_dt(polb200_rigid_t *r, double dt);
 long polb200_rigid_fetch(polb200_rigid_t *r, const char *name, double *dst, long capacity);
 long polb200_rigid_launch_count(polb200_rigid_t *r, int reset);
 double polb200_rigid_last_ms(const polb200_rigid_t *r); /* CUDA-event time of the last per-step call */
+
+/* ---- device buffers for callers that keep their atom arrays resident ---------------------------------------------- */
+/* A caller that passes device pointers (`on_device = 1` of polb200_compute / _ewald_compute / _pppm_compute / the rigid
+ * entry points) needs device memory of its own.  A host framework without a CUDA tool chain -- the LAMMPS binding's shared
+ * device mirror of atom->x / v / f / q / mu, lammps/device_atoms_b200.h -- gets it here: plain allocation and synchronous
+ * copies on `device` (every library entry point returns with its own stream drained, so these copies are ordered with the
+ * library's work).  polb200_host_register pins a host range (faster copies); all return POLB200_OK or POLB200_ERR_CUDA. */
+enum { POLB200_COPY_H2D = 0, POLB200_COPY_D2H = 1, POLB200_COPY_D2D = 2 };
+void *polb200_dev_alloc(int device, size_t bytes);
+void polb200_dev_free(int device, void *p);
+int polb200_dev_copy(int device, void *dst, const void *src, size_t bytes, int kind);
+int polb200_dev_zero(int device, void *p, size_t bytes);
+int polb200_host_register(void *p, size_t bytes);
+int polb200_host_unregister(void *p);
 
 /* ---- introspection for tests and profiling ------------------------------------------------------ */
 

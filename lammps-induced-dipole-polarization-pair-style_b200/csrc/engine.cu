@@ -81,6 +81,16 @@ struct polb200_handle {
   int gpf_minb = 4;              // resident CTAs per SM asked of the grouped force kernel (4: 128 registers, no spills; measured faster than 5)
   bool use_group_pairs = true;   // LJ + Coulomb + field and polarization forces on the pair-group rows when they qualify
   bool gs_blocked = true;        // exact-mode Gauss-Seidel as blocked forward substitution (false: one atom at a time)
+  bool use_graphs = true;        // ... its per-block launches replayed from a CUDA graph
+  long params_version = 0;       // bumped whenever the kernel parameters (DevParams) change
+  struct SweepGraph {
+    cudaGraphExec_t exec = nullptr;
+    int n = 0, nodes = 0;
+    long version = -1;
+    const void *key[8] = {};
+  } gs_graph;
+  DBuf<double> gs_planes;        // per-step pair-tensor cache of the blocked sweep (small systems)
+  int gs_cache_max = 3000;       // ... up to this many atoms (5 n^2 doubles)
   DBuf<double4> gsR;
   bool l2_evict_first = true;    // TMA row streams are marked evict-first in L2
   bool alternate = true;         // sweeps walk the groups alternately forwards / backwards (L2 reuse of the stream tail)
@@ -229,6 +239,7 @@ static void upload_params(polb200_handle *h)
   }
   h->params_uploaded = true;
   h->have_lists = false;
+  h->params_version++;
 }
 
 static int bits_for(int n)
@@ -1047,6 +1058,12 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
     }
     h->scf_stop = ctl;
     const int *stop = ctl;
+    GsPairCache gs_cache{nullptr, 0};
+    if (sequential && h->gs_blocked && n <= h->gs_cache_max) {
+      h->gs_planes.ensure((size_t)5 * n * n);
+      LAUNCH(h, k_gs_pair_cache, nrowblocks, BLOCK, n, order, P, h->perm.p, h->xq.p, h->gs_planes.p);
+      gs_cache = GsPairCache{h->gs_planes.p, n};
+    }
 
     // one iteration `it` of the solver (Jacobi: reads the buffer of parity it, writes the other one)
     auto enqueue_iteration = [&](int it) {
@@ -1058,13 +1075,46 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
       if (sequential && h->gs_blocked) {
         // blocked forward substitution = the same sweep, N/32 dependent steps instead of N (kernels.cuh)
         h->gsR.ensure(n);
-        LAUNCH(h, k_gsb_upper, nrowblocks, BLOCK, n, order, P, h->perm.p, h->xq.p, cur, h->ef.p, h->gsR.p, stop);
+        LAUNCH(h, k_gsb_upper, nrowblocks, BLOCK, n, order, P, h->perm.p, h->xq.p, cur, h->ef.p, h->gsR.p, stop, gs_cache);
+        // one launch per block (k_gsb_step); the launches of a sweep are replayed from a CUDA graph, captured once and
+        // kept for as long as its arguments stay the same (at 750 atoms a sweep is 25 dependent kernels of a few us)
         const int nblk = cdiv(n, GSB);
-        for (int b = 0; b < nblk; b++) {
-          LAUNCH(h, k_gsb_solve, 1, GSB * 32, n, b, order, P, h->perm.p, h->xq.p, cur, h->gsR.p, chg, b == 0 ? 1 : 0, stop);
-          const int rows_after = n - (b + 1) * GSB;
-          if (rows_after > 0)
-            LAUNCH(h, k_gsb_update, cdiv(rows_after, WARPS_PER_BLOCK), BLOCK, n, b, order, P, h->perm.p, h->xq.p, cur, h->gsR.p, stop);
+        const void *key[8] = {order, h->perm.p, h->xq.p, cur, h->gsR.p, chg, stop, gs_cache.plane};
+        auto launch_steps = [&] {
+          for (int b = 0; b < nblk; b++) {
+            const int rows_after = n - (b + 1) * GSB;
+            const int grid = 1 + (b > 0 && rows_after > 0 ? cdiv(rows_after, GSB) : 0);
+            LAUNCH(h, k_gsb_step, grid, GSS_THREADS, n, b, order, P, h->perm.p, h->xq.p, cur, h->gsR.p, chg, stop, gs_cache);
+          }
+        };
+        polb200_handle::SweepGraph &G = h->gs_graph;
+        if (!h->use_graphs) launch_steps();
+        else {
+          if (!G.exec || G.n != n || G.version != h->params_version || memcmp(G.key, key, sizeof(key)) != 0) {
+            if (G.exec) cudaGraphExecDestroy(G.exec);
+            G.exec = nullptr;
+            cudaGraph_t graph = nullptr;
+            const long before = h->launches;
+            CUDA_CHECK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+            try {
+              launch_steps();
+            } catch (...) {
+              cudaStreamEndCapture(h->stream, &graph);
+              if (graph) cudaGraphDestroy(graph);
+              throw;
+            }
+            CUDA_CHECK(cudaStreamEndCapture(h->stream, &graph));
+            G.nodes = (int)(h->launches - before);
+            h->launches = before;
+            const cudaError_t ie = cudaGraphInstantiate(&G.exec, graph, 0);
+            cudaGraphDestroy(graph);
+            CUDA_CHECK(ie);
+            G.n = n;
+            G.version = h->params_version;
+            memcpy(G.key, key, sizeof(key));
+          }
+          CUDA_CHECK(cudaGraphLaunch(G.exec, h->stream));
+          h->launches += G.nodes;
         }
         summed = true;
       } else if (sequential) {
@@ -1516,6 +1566,8 @@ void polb200_destroy(polb200_t *h)
   h->gof.release(); h->gadj.release(); h->gadjn.release(); h->gcolour.release(); h->glist.release(); h->cstart_dev.release();
   h->col_export.release(); h->gmetric.release(); h->ctl.release(); h->h_ctl.release(); h->slice.release();
   for (auto &e : h->ev_it) if (e) cudaEventDestroy(e);
+  if (h->gs_graph.exec) cudaGraphExecDestroy(h->gs_graph.exec);
+  h->gs_planes.release();
   h->tm.release(); h->cnt.release(); h->rowstart.release(); h->cub_tmp.release(); h->rmin_bits.release();
   h->h_stage.release(); h->h_scal.release(); h->h_int.release();
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
@@ -1652,6 +1704,7 @@ int polb200_set_box(polb200_t *h, const double boxlo[3], const double boxhi[3], 
     }
     h->P.box = h->box;
     h->box_set = true;
+    if (changed) h->params_version++;
     if (changed) h->have_lists = false;
     if (h->comm.active && (changed || !h->comm.geom_valid)) comm_setup_geom(h);
   });
@@ -1717,6 +1770,14 @@ int polb200_set_option(polb200_t *h, const char *name, double value)
   if (!strcmp(name, "xsort_bits")) {
     h->xsort_bits = (int)value;
     h->have_lists = false;
+    return POLB200_OK;
+  }
+  if (!strcmp(name, "gs_cache_max")) {
+    h->gs_cache_max = (int)value;
+    return POLB200_OK;
+  }
+  if (!strcmp(name, "use_graphs")) {
+    h->use_graphs = value != 0.0;
     return POLB200_OK;
   }
   if (!strcmp(name, "gs_blocked")) {
@@ -1877,6 +1938,68 @@ long polb200_debug_fetch(polb200_t *h, const char *name, void *dst, long capacit
     else throw StyleError{POLB200_ERR_ARG, std::string("debug_fetch: unknown array ") + name};
   });
   return result;
+}
+
+// ---- device buffers for resident callers ------------------------------------------------------------------
+void *polb200_dev_alloc(int device, size_t bytes)
+{
+  void *p = nullptr;
+  if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+void polb200_dev_free(int device, void *p)
+{
+  if (!p) return;
+  cudaSetDevice(device);
+  cudaFree(p);
+}
+
+int polb200_dev_copy(int device, void *dst, const void *src, size_t bytes, int kind)
+{
+  if (bytes == 0) return POLB200_OK;
+  if (!dst || !src || kind < 0 || kind > 2) return POLB200_ERR_ARG;
+  const cudaMemcpyKind k = kind == POLB200_COPY_H2D ? cudaMemcpyHostToDevice
+                                                    : (kind == POLB200_COPY_D2H ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice);
+  if (cudaSetDevice(device) != cudaSuccess || cudaMemcpy(dst, src, bytes, k) != cudaSuccess) {
+    cudaGetLastError();
+    return POLB200_ERR_CUDA;
+  }
+  return POLB200_OK;
+}
+
+int polb200_dev_zero(int device, void *p, size_t bytes)
+{
+  if (bytes == 0) return POLB200_OK;
+  if (!p) return POLB200_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess || cudaMemset(p, 0, bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+    cudaGetLastError();
+    return POLB200_ERR_CUDA;
+  }
+  return POLB200_OK;
+}
+
+int polb200_host_register(void *p, size_t bytes)
+{
+  if (!p || !bytes) return POLB200_ERR_ARG;
+  if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return POLB200_ERR_CUDA;
+  }
+  return POLB200_OK;
+}
+
+int polb200_host_unregister(void *p)
+{
+  if (!p) return POLB200_ERR_ARG;
+  if (cudaHostUnregister(p) != cudaSuccess) {
+    cudaGetLastError();
+    return POLB200_ERR_CUDA;
+  }
+  return POLB200_OK;
 }
 
 // ---- multi-GPU entry points (comm.cuh) ---------------------------------------------------------------

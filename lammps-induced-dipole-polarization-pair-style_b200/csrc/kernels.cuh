@@ -2497,9 +2497,9 @@ __global__ void k_scf_check(const double *__restrict__ sum, int *ctl, double pre
 // solves the lower-triangular system  (I + alpha L) mu_new = alpha (E - U mu_old)  in ranked order.  Done atom by
 // atom that is N dependent steps (k_gs_sequential: one CTA, 8 ms per sweep set at 750 atoms).  Blocked:
 //   k_gsb_upper : R[p] = E[p] - sum over partners in LATER blocks of T mu_old          (all SMs, once per sweep)
-//   per block b : k_gsb_solve  - the 32x32 diagonal block: T of the block's pairs into shared memory, then one warp
-//                                substitutes sequentially (new dipoles of earlier atoms, old of later ones)
-//                 k_gsb_update - R[p] -= sum over the atoms of block b of T mu_new, for every p in later blocks
+//   per block b : k_gsb_step   - R[p] -= sum over the atoms of block b-1 of T mu_new for every row from block b on, then
+//                                the 32x32 diagonal block: T of the block's pairs into shared memory, one warp substitutes
+//                                sequentially (new dipoles of earlier atoms, old of later ones)
 // Same operands per atom as the sequential sweep; only the order of the additions inside one field sum differs.
 constexpr int GSB = 32;
 
@@ -2511,10 +2511,59 @@ __device__ __forceinline__ void pair_del(const Box &box, const int *__restrict__
   else min_image_del(box, xj.x, xj.y, xj.z, xs.x, xs.y, xs.z, dx, dy, dz);
 }
 
+// Per-step cache of the pair tensors in RANKED order for small systems: {s1, s2, del} of every ordered pair of ranked
+// positions (p, q), five planes of n x n doubles (22 MB at 750 atoms).  The geometry and the order are frozen during the
+// SCF, and the blocked sweep is a chain of dependent few-microsecond kernels: a square root, two divisions and an
+// exponential per pair on that chain (~2000 cycles, twice per block) were a third of a sweep.  plane == nullptr: no cache.
+struct GsPairCache {
+  const double *plane;  // [5][n][n]
+  int n;
+  __device__ __forceinline__ bool on() const { return plane != nullptr; }
+  __device__ __forceinline__ void load(int p, int q, double &s1, double &s2, double &dx, double &dy, double &dz) const
+  {
+    const size_t nn = (size_t)n * n, k = (size_t)p * n + q;
+    s1 = plane[k]; s2 = plane[nn + k]; dx = plane[2 * nn + k]; dy = plane[3 * nn + k]; dz = plane[4 * nn + k];
+  }
+};
+
+__global__ void __launch_bounds__(BLOCK)
+k_gs_pair_cache(int n, const int *__restrict__ order, DevParams P, const int *__restrict__ perm,
+                const double4 *__restrict__ xq, double *__restrict__ plane)
+{
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (p >= n) return;
+  const int s = order ? order[p] : p;
+  const double4 xs = xq[s];
+  const size_t nn = (size_t)n * n;
+  for (int q = lane; q < n; q += 32) {
+    double dx = 0, dy = 0, dz = 0, s1 = 0, s2 = 0;
+    if (q != p) {
+      const int j = order ? order[q] : q;
+      pair_del(P.box, perm, s, j, xs, ld4(xq + j), dx, dy, dz);
+      induced_field_scalars(P.pc, dx * dx + dy * dy + dz * dz, s1, s2);
+    }
+    const size_t k = (size_t)p * n + q;
+    plane[k] = s1; plane[nn + k] = s2; plane[2 * nn + k] = dx; plane[3 * nn + k] = dy; plane[4 * nn + k] = dz;
+  }
+}
+
+// e -= T(p, q) mu  from the cache
+__device__ __forceinline__ void cached_field_pair(const GsPairCache &C, int p, int q, double mx, double my, double mz,
+                                                  double &ex, double &ey, double &ez)
+{
+  double s1, s2, dx, dy, dz;
+  C.load(p, q, s1, s2, dx, dy, dz);
+  const double dm = dx * mx + dy * my + dz * mz;
+  ex -= s1 * mx + s2 * dm * dx;
+  ey -= s1 * my + s2 * dm * dy;
+  ez -= s1 * mz + s2 * dm * dz;
+}
+
 __global__ void __launch_bounds__(BLOCK)
 k_gsb_upper(int n, const int *__restrict__ order, DevParams P, const int *__restrict__ perm,
             const double4 *__restrict__ xq, const double4 *__restrict__ mua, const double4 *__restrict__ ef,
-            double4 *__restrict__ R, const int *stop = nullptr)
+            double4 *__restrict__ R, const int *stop = nullptr, GsPairCache C = GsPairCache{nullptr, 0})
 {
   const int lane = threadIdx.x & 31;
   const int p = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
@@ -2526,11 +2575,14 @@ k_gsb_upper(int n, const int *__restrict__ order, DevParams P, const int *__rest
   if (mua[s].w != 0.0)
     for (int q = q0 + lane; q < n; q += 32) {
       const int j = order ? order[q] : q;
-      const double4 xj = ld4(xq + j);
-      double dx, dy, dz;
-      pair_del(P.box, perm, s, j, xs, xj, dx, dy, dz);
       const double4 mj = ld4_cg(mua + j);
-      induced_field_pair(P.pc, dx, dy, dz, dx * dx + dy * dy + dz * dz, mj.x, mj.y, mj.z, ex, ey, ez);
+      if (C.on()) cached_field_pair(C, p, q, mj.x, mj.y, mj.z, ex, ey, ez);
+      else {
+        const double4 xj = ld4(xq + j);
+        double dx, dy, dz;
+        pair_del(P.box, perm, s, j, xs, xj, dx, dy, dz);
+        induced_field_pair(P.pc, dx, dy, dz, dx * dx + dy * dy + dz * dz, mj.x, mj.y, mj.z, ex, ey, ez);
+      }
     }
   ex = warp_sum(ex);
   ey = warp_sum(ey);
@@ -2541,86 +2593,103 @@ k_gsb_upper(int n, const int *__restrict__ order, DevParams P, const int *__rest
   }
 }
 
-// one CTA of GSB warps: thread (w, v) owns the pair (block atom w, block atom v)
-__global__ void __launch_bounds__(GSB * 32)
-k_gsb_solve(int n, int b, const int *__restrict__ order, DevParams P, const int *__restrict__ perm,
-            const double4 *__restrict__ xq, double4 *__restrict__ mua, const double4 *__restrict__ R,
-            double *__restrict__ change_out, int first_block, const int *stop = nullptr)
+// One launch per block instead of two: step b = "subtract block b-1's contribution from every row from block b on" fused
+// with "solve block b".  CTA 0 (32 warps) first brings the 32 rows of block b up to date (warp w owns row w), then forms the
+// block's pair tensors (thread (w, v) owns pair (w, v)) and substitutes; the other CTAs update the rows after block b.  The
+// rows after block b are not needed before the next launch, so nothing waits inside the kernel.  Same operands per atom as
+// the sequential sweep.  The launches of a sweep are replayed from a CUDA graph (engine.cu): at 750 atoms a sweep is
+// 25 dependent kernels of a few microseconds each.
+constexpr int GSS_THREADS = GSB * 32;
+__global__ void __launch_bounds__(GSS_THREADS)
+k_gsb_step(int n, int b, const int *__restrict__ order, DevParams P, const int *__restrict__ perm,
+           const double4 *__restrict__ xq, double4 *__restrict__ mua, double4 *__restrict__ R,
+           double *__restrict__ change_out, const int *stop = nullptr, GsPairCache C = GsPairCache{nullptr, 0})
 {
   if (scf_stopped(stop)) return;
   __shared__ double sT[GSB][GSB][5];  // s1, s2, dx, dy, dz of every pair of the block
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int p0 = b * GSB, cnt = min(GSB, n - p0);
+  // 1. rows from block b on: R[p] -= sum over the atoms of block b-1 of T mu_new (block b-1 is complete)
+  if (b > 0) {
+    const int p = blockIdx.x == 0 ? p0 + warp : p0 + GSB + (blockIdx.x - 1) * GSB + warp;
+    if (p < n && (blockIdx.x > 0 || warp < cnt)) {
+      const int s = order ? order[p] : p;
+      const int q = (b - 1) * GSB + lane;
+      const int j = order ? order[q] : q;
+      double ex = 0, ey = 0, ez = 0;
+      if (ld4_cg(mua + s).w != 0.0) {
+        const double4 mj = ld4_cg(mua + j);
+        if (C.on()) cached_field_pair(C, p, q, mj.x, mj.y, mj.z, ex, ey, ez);
+        else {
+          const double4 xs = xq[s], xj = ld4(xq + j);
+          double dx, dy, dz;
+          pair_del(P.box, perm, s, j, xs, xj, dx, dy, dz);
+          induced_field_pair(P.pc, dx, dy, dz, dx * dx + dy * dy + dz * dz, mj.x, mj.y, mj.z, ex, ey, ez);
+        }
+      }
+      ex = warp_sum(ex);
+      ey = warp_sum(ey);
+      ez = warp_sum(ez);
+      if (lane == 0) {
+        const double4 r = ld4_cg(R + p);
+        R[p] = make_double4(r.x + ex, r.y + ey, r.z + ez, 0.0);
+      }
+    }
+  }
+  if (blockIdx.x != 0) return;
+  // 2. CTA 0: the diagonal block
   if (warp < cnt && lane < cnt && warp != lane) {
-    const int s = order ? order[p0 + warp] : p0 + warp, j = order ? order[p0 + lane] : p0 + lane;
-    const double4 xs = xq[s], xj = xq[j];
     double dx, dy, dz, s1, s2;
-    pair_del(P.box, perm, s, j, xs, xj, dx, dy, dz);
-    induced_field_scalars(P.pc, dx * dx + dy * dy + dz * dz, s1, s2);
+    if (C.on()) C.load(p0 + warp, p0 + lane, s1, s2, dx, dy, dz);
+    else {
+      const int s = order ? order[p0 + warp] : p0 + warp, j = order ? order[p0 + lane] : p0 + lane;
+      const double4 xs = xq[s], xj = xq[j];
+      pair_del(P.box, perm, s, j, xs, xj, dx, dy, dz);
+      induced_field_scalars(P.pc, dx * dx + dy * dy + dz * dz, s1, s2);
+    }
     sT[warp][lane][0] = s1; sT[warp][lane][1] = s2;
     sT[warp][lane][2] = dx; sT[warp][lane][3] = dy; sT[warp][lane][4] = dz;
   }
-  __syncthreads();
+  __syncthreads();  // (also orders the R updates of step 1 before the reads below)
   if (warp != 0) return;
-  // forward substitution: lane v carries the dipole of block atom v (old until its turn, new afterwards)
+  // Forward substitution in COLUMN form: lane v keeps the running field of block atom v; when atom w has its new dipole
+  // it is broadcast and every lane subtracts T(v,w) mu_w from its own field -- no warp reduction on the critical path (a
+  // reduction per atom made this loop ten times longer than everything else in the kernel).  T(v,w) is read as sT[w][v]
+  // (T is even in del; consecutive lanes, 2-way bank conflicts instead of 32-way).
   const int sv = lane < cnt ? (order ? order[p0 + lane] : p0 + lane) : 0;
   double4 mv = lane < cnt ? ld4_cg(mua + sv) : make_double4(0, 0, 0, 0);
-  const double4 rv = lane < cnt ? R[p0 + lane] : make_double4(0, 0, 0, 0);
+  const double4 rv = lane < cnt ? ld4_cg(R + p0 + lane) : make_double4(0, 0, 0, 0);
+  double ax = rv.x, ay = rv.y, az = rv.z;
+  auto subtract = [&](int w, double mx, double my, double mz) {  // field of lane's atom -= T(lane, w) (mx, my, mz)
+    const double s1 = sT[w][lane][0], s2 = sT[w][lane][1];
+    const double dx = sT[w][lane][2], dy = sT[w][lane][3], dz = sT[w][lane][4];
+    const double t = s2 * (dx * mx + dy * my + dz * mz);
+    ax -= fma(t, dx, s1 * mx);
+    ay -= fma(t, dy, s1 * my);
+    az -= fma(t, dz, s1 * mz);
+  };
+  // old dipoles of the atoms AFTER each lane's atom (independent steps: they pipeline)
+  for (int u = 1; u < cnt; u++) {
+    const double mx = __shfl_sync(FULL, mv.x, u), my = __shfl_sync(FULL, mv.y, u), mz = __shfl_sync(FULL, mv.z, u);
+    if (lane < u) subtract(u, mx, my, mz);
+  }
   double change = 0.0;
   for (int w = 0; w < cnt; w++) {
-    double ex = 0, ey = 0, ez = 0;
-    if (lane < cnt && lane != w) {
-      const double s1 = sT[w][lane][0], s2 = sT[w][lane][1];
-      const double dx = sT[w][lane][2], dy = sT[w][lane][3], dz = sT[w][lane][4];
-      const double dm = dx * mv.x + dy * mv.y + dz * mv.z;
-      ex = -(s1 * mv.x + s2 * dm * dx);
-      ey = -(s1 * mv.y + s2 * dm * dy);
-      ez = -(s1 * mv.z + s2 * dm * dz);
-    }
-    ex = warp_sum(ex);
-    ey = warp_sum(ey);
-    ez = warp_sum(ez);
-    ex = __shfl_sync(FULL, ex, 0);
-    ey = __shfl_sync(FULL, ey, 0);
-    ez = __shfl_sync(FULL, ez, 0);
+    double nx = 0, ny = 0, nz = 0;
     if (lane == w) {
       // alpha == 0: the field sum is skipped by the sequential kernel too; the product is zero either way
-      const double nx = mv.w * (rv.x + ex), ny = mv.w * (rv.y + ey), nz = mv.w * (rv.z + ez);
+      nx = mv.w * ax, ny = mv.w * ay, nz = mv.w * az;
       change += (nx - mv.x) * (nx - mv.x) + (ny - mv.y) * (ny - mv.y) + (nz - mv.z) * (nz - mv.z);
       mv = make_double4(nx, ny, nz, mv.w);
     }
+    nx = __shfl_sync(FULL, nx, w);
+    ny = __shfl_sync(FULL, ny, w);
+    nz = __shfl_sync(FULL, nz, w);
+    if (lane > w && lane < cnt) subtract(w, nx, ny, nz);
   }
   if (lane < cnt) mua[sv] = mv;
   change = warp_sum(change);
-  if (lane == 0) change_out[0] = first_block ? change : change_out[0] + change;
-}
-
-__global__ void __launch_bounds__(BLOCK)
-k_gsb_update(int n, int b, const int *__restrict__ order, DevParams P, const int *__restrict__ perm,
-             const double4 *__restrict__ xq, const double4 *__restrict__ mua, double4 *__restrict__ R,
-             const int *stop = nullptr)
-{
-  const int lane = threadIdx.x & 31;
-  const int p = (b + 1) * GSB + blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-  if (p >= n || scf_stopped(stop)) return;
-  const int s = order ? order[p] : p;
-  const int q = b * GSB + lane;  // block b is complete: GSB atoms (only the last block can be short, and it has no later rows)
-  const int j = order ? order[q] : q;
-  const double4 xs = xq[s], xj = ld4(xq + j);
-  double ex = 0, ey = 0, ez = 0;
-  if (mua[s].w != 0.0) {
-    double dx, dy, dz;
-    pair_del(P.box, perm, s, j, xs, xj, dx, dy, dz);
-    const double4 mj = ld4_cg(mua + j);
-    induced_field_pair(P.pc, dx, dy, dz, dx * dx + dy * dy + dz * dz, mj.x, mj.y, mj.z, ex, ey, ez);
-  }
-  ex = warp_sum(ex);
-  ey = warp_sum(ey);
-  ez = warp_sum(ez);
-  if (lane == 0) {
-    double4 r = R[p];
-    R[p] = make_double4(r.x + ex, r.y + ey, r.z + ez, 0.0);
-  }
+  if (lane == 0) change_out[0] = b == 0 ? change : change_out[0] + change;
 }
 
 }  // namespace polb200

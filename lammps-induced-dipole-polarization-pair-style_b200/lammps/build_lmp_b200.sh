@@ -3,7 +3,8 @@
 #   lammps/_build/lmp_b200  =  reference host framework (LAMMPS 16Mar2018, from a scratch copy of
 #   $POLB200_REFERENCE/src, repaired exactly like the oracle build: oracle/build_ref.sh steps 1-3 without the
 #   dump hooks)  +  pair_lj_cut_coul_long_polarization_b200.{h,cpp}  +  ewald_b200.{h,cpp}  +  pppm_b200.{h,cpp}  +
-#   fix_rigid_nh_b200.{h,cpp}  +  atom_vec_full_polar_b200.{h,cpp}  +  compute_polarization_atom_b200.{h,cpp}  +  libpolb200.so.
+#   fix_rigid_nh_b200.{h,cpp}  +  atom_vec_full_polar_b200.{h,cpp}  +  compute_polarization_atom_b200.{h,cpp}  +
+#   device_atoms_b200.h  +  libpolb200.so.
 #   (the oracle's 12-line AtomVecFull patch is NOT used here: the committed atom style replaces it)
 # An unchanged input script (polarization/examples/*) then drives the CUDA path.  Nothing of the reference is
 # copied into this repository; the binary lands in lammps/_build/ (git-ignored, travels to the GPU box).
@@ -28,6 +29,7 @@ if [ -x "$OUT/lmp_b200" ] && [ "$OUT/lmp_b200" -nt "$HERE/pair_lj_cut_coul_long_
    && [ "$OUT/lmp_b200" -nt "$HERE/compute_polarization_atom_b200.cpp" ] && [ "$OUT/lmp_b200" -nt "$HERE/compute_polarization_atom_b200.h" ] \
    && [ "$OUT/lmp_b200" -nt "$HERE/pppm_b200.cpp" ] && [ "$OUT/lmp_b200" -nt "$HERE/pppm_b200.h" ] \
    && [ "$OUT/lmp_b200" -nt "$HERE/fix_rigid_nh_b200.cpp" ] && [ "$OUT/lmp_b200" -nt "$HERE/fix_rigid_nh_b200.h" ] \
+   && [ "$OUT/lmp_b200" -nt "$HERE/device_atoms_b200.h" ] \
    && [ "$OUT/lmp_b200" -nt "$ROOT/include/polb200.h" ] && [ -z "${POLB200_LMP_REBUILD:-}" ]; then
   echo "build_lmp_b200: $OUT/lmp_b200 is up to date"
   exit 0
@@ -68,6 +70,8 @@ rm -f pppm_cg.* pppm_stagger.* pppm_tip4p.*     # derived from the reference's c
 cp "$HERE/fix_rigid_nh_b200.h" fix_rigid_nve.h
 cp "$HERE/fix_rigid_nh_b200.cpp" fix_rigid_nve.cpp
 rm -f fix_rigid_nvt.h fix_rigid_nvt.cpp
+# shared device mirror of atom->x / v / f / q / mu for the three styles above (second half)
+cp "$HERE/device_atoms_b200.h" .
 cp "$ROOT/include/polb200.h" .
 make -j"$JOBS" serial LIB="-L$PKG -lpolb200 -Wl,-rpath,'\$\$ORIGIN/../..'" > "$W/build.log" 2>&1 || { tail -40 "$W/build.log"; exit 1; }
 cp lmp_serial "$OUT/lmp_b200"

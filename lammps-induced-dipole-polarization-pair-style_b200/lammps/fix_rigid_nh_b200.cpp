@@ -18,6 +18,7 @@
 #include "memory.h"
 #include "update.h"
 #include "polb200.h"
+#include "device_atoms_b200.h"
 
 using namespace LAMMPS_NS;
 using namespace FixConst;
@@ -134,6 +135,7 @@ int FixRigidNHB200::setmask()
   mask |= INITIAL_INTEGRATE;
   mask |= FINAL_INTEGRATE;
   mask |= PRE_NEIGHBOR;
+  mask |= PRE_EXCHANGE;                     // device-resident atoms: host copies made current before the host re-orders them
   if (tstat_flag) mask |= THERMO_ENERGY;   // fix_rigid_nh.cpp:196-203
   return mask;
 }
@@ -163,6 +165,7 @@ void FixRigidNHB200::init()
   if (strstr(update->integrate_style,"respa"))
     error->all(FLERR,"fix rigid/nve|nvt (B200) does not support run_style respa");
   fill_work();
+  DeviceAtomsB200::instance().evaluate(lmp);   // may this run keep its atoms on the device? (device_atoms_b200.h)
   polb200_rigid_params p;
   memset(&p, 0, sizeof(p));
   p.thermostat = tstat_flag;
@@ -203,28 +206,64 @@ void FixRigidNHB200::setup(int vflag)
   if (evflag && vflag_global && polb200_rigid_virial(handle, virial) != POLB200_OK) fail();
 }
 
+/* device-resident atoms (device_atoms_b200.h): the integrator works on the shared device mirror; the host gets the new
+   positions every step (Neighbor::decide reads them) and the new velocities / forces on output steps only */
+
 void FixRigidNHB200::initial_integrate(int vflag)
 {
+  DeviceAtomsB200 &da = DeviceAtomsB200::instance();
+  const bool resident = da.resident && atom->nlocal > 0;
   polb200_rigid_atoms a;
   a.nlocal = atom->nlocal; a.tag = atom->tag; a.x = atom->x[0]; a.v = atom->v[0]; a.f = atom->f[0]; a.on_device = 0;
+  if (resident) {
+    da.ensure_xv(lmp);
+    a.tag = da.tag; a.x = da.x; a.v = da.v; a.f = da.f; a.on_device = 1;
+  }
   if (vflag) v_setup(vflag);
   else evflag = 0;
   double delta = update->ntimestep - update->beginstep;       // fix_rigid_nh.cpp:1109-1115
   if (delta != 0.0) delta /= update->endstep - update->beginstep;
   t_target = t_start + delta * (t_stop-t_start);
   if (polb200_rigid_initial_integrate(handle, &a, evflag && vflag_global, delta) != POLB200_OK) fail();
+  if (resident) {
+    da.v_host_current = false;
+    da.download_x(lmp);
+  }
 }
 
 void FixRigidNHB200::final_integrate()
 {
+  DeviceAtomsB200 &da = DeviceAtomsB200::instance();
+  const bool resident = da.resident && atom->nlocal > 0 && da.xv_on_device;
   polb200_rigid_atoms a;
   a.nlocal = atom->nlocal; a.tag = atom->tag; a.x = atom->x[0]; a.v = atom->v[0]; a.f = atom->f[0]; a.on_device = 0;
+  if (resident) {
+    a.tag = da.tag; a.x = da.x; a.v = da.v; a.f = da.f; a.on_device = 1;
+  }
   if (polb200_rigid_final_integrate(handle, &a) != POLB200_OK) fail();
   if (evflag && vflag_global && polb200_rigid_virial(handle, virial) != POLB200_OK) fail();
+  if (resident) {
+    da.v_host_current = false;
+    if (da.output_step(lmp)) {
+      da.download_v(lmp);
+      da.download_f(lmp);
+    }
+  }
+}
+
+/* re-neighboring step, before Domain::pbc / Comm::exchange / Atom::sort touch the host arrays: the host copies of the
+   velocities and dipoles must be the current ones */
+
+void FixRigidNHB200::pre_exchange()
+{
+  DeviceAtomsB200 &da = DeviceAtomsB200::instance();
+  if (da.resident) da.before_reneighbor(lmp);
 }
 
 void FixRigidNHB200::pre_neighbor()
 {
+  DeviceAtomsB200 &da = DeviceAtomsB200::instance();
+  if (da.resident) da.after_reneighbor();   // the atoms may have been wrapped and re-ordered: the host is authoritative
   if (!setupflag) return;
   if (polb200_rigid_pre_neighbor(handle, atom->nlocal, atom->tag, atom->image, 0) != POLB200_OK) fail();
 }

@@ -36,6 +36,7 @@ class FixRigidNHB200 : public Fix {
   void setup_pre_neighbor();
   void initial_integrate(int);
   void final_integrate();
+  void pre_exchange();
   void pre_neighbor();
   int dof(int);
   void deform(int);

@@ -30,6 +30,7 @@
 #include "neighbor.h"
 #include "update.h"
 #include "polb200.h"
+#include "device_atoms_b200.h"
 
 using namespace LAMMPS_NS;
 
@@ -167,6 +168,7 @@ void PairLJCutCoulLongPolarization::init_style()
   env.polarizability_flag = atom->static_polarizability_flag;
   env.molecular = atom->molecular;
   CHECK(polb200_init(handle, &env));
+  DeviceAtomsB200::instance().evaluate(lmp);   // may this run keep its atoms on the device? (device_atoms_b200.h)
   if (domain->triclinic)
     error->all(FLERR,"Pair style lj/cut/coul/long/polarization (B200) requires an orthogonal box");
   // no NeighRequest: the library builds its own cell-sorted device list from atom->x on the steps where
@@ -200,10 +202,30 @@ void PairLJCutCoulLongPolarization::compute(int eflag, int vflag)
   int periodic[3] = {domain->xperiodic, domain->yperiodic, domain->zperiodic};
   CHECK(polb200_set_box(handle, domain->boxlo, domain->boxhi, periodic));
 
+  // device-resident atoms (device_atoms_b200.h): the pair style reads x / q / mu from and adds its forces to the shared
+  // device mirror; per-atom tallies (eatom / vatom are host arrays of Pair) take the host-buffer path for that step
+  DeviceAtomsB200 &da = DeviceAtomsB200::instance();
+  const bool resident = da.resident && !update->setupflag && atom->nlocal > 0;
+  const bool resident_call = resident && !eflag_atom && !vflag_atom;
+  if (resident) {
+    da.ensure_xv(lmp);
+    da.ensure_static(lmp);
+    if (!resident_call) da.download_mu(lmp);
+  }
+
   polb200_atoms a;
   memset(&a, 0, sizeof(a));
   a.nlocal = atom->nlocal;
-  if (a.nlocal > 0) {
+  if (resident_call) {
+    da.zero_f(lmp);                      // Verlet::force_clear cleared the host copy; the pair style is the first contributor
+    a.x = da.x; a.q = da.q; a.type = da.type; a.molecule = da.molecule; a.tag = da.tag; a.alpha = da.alpha;
+    a.mu = da.mu; a.ef_static = da.ef; a.f = da.f; a.mask = da.mask;
+    if (da.maxspecial > 0) {
+      a.nspecial = da.nspecial;
+      a.special = da.special;
+      a.maxspecial = da.maxspecial;
+    }
+  } else if (a.nlocal > 0) {
     a.x = atom->x[0];
     a.q = atom->q;
     a.type = atom->type;
@@ -219,7 +241,7 @@ void PairLJCutCoulLongPolarization::compute(int eflag, int vflag)
       a.maxspecial = atom->maxspecial;
     }
   }
-  a.on_device = 0;
+  a.on_device = resident_call ? 1 : 0;
   // `neigh_modify exclude` (src/neighbor.cpp:2276-2333): LAMMPS' own pair list is not used, so the rules travel to the
   // device list on every re-neighboring step (NPair::exclusion, src/npair.cpp:173-203)
   if (neighbor->ago == 0) {
@@ -236,12 +258,22 @@ void PairLJCutCoulLongPolarization::compute(int eflag, int vflag)
       nexclude_sent = (int) rules.size();
     }
   }
-  a.mask = atom->mask;
+  if (!resident_call) a.mask = atom->mask;
   a.eatom = eflag_atom ? eatom : NULL;           // Pair::eatom / vatom, zeroed by ev_setup (src/pair.cpp:789-804)
   a.vatom = (vflag_atom && a.nlocal > 0) ? vatom[0] : NULL;
 
   polb200_result res;
   CHECK(polb200_compute(handle, &a, eflag, vflag, neighbor->ago, &res));
+  if (resident_call) {
+    da.mu_host_current = false;
+    if (da.output_step(lmp)) da.download_mu(lmp);
+  } else if (resident) {
+    // host-buffer call inside a resident run: the mirror takes over its results (atom->f holds the pair forces only,
+    // Verlet::force_clear zeroed it before)
+    da.static_on_device = false;
+    da.ensure_static(lmp);       // (mu, ef: the host copies are the new ones)
+    da.upload_f(lmp);
+  }
 
   if (res.status & POLB200_STATUS_DIVERGED)
     error->warning(FLERR,"Number of iterations exceeding max_iterations, setting dipoles to alpha*E");

@@ -17,6 +17,7 @@
 #include "force.h"
 #include "pair.h"
 #include "polb200.h"
+#include "device_atoms_b200.h"
 
 using namespace LAMMPS_NS;
 
@@ -133,9 +134,14 @@ void PPPM::compute(int eflag, int vflag)
   if (qsqsum == 0.0 || atom->nlocal == 0) return;
 
   double e = 0.0, v[6];
-  if (polb200_pppm_compute(handle, atom->nlocal, atom->x[0], atom->q, atom->f[0], eflag_global, vflag_global ? 1 : 0, 0,
+  // device-resident atoms (device_atoms_b200.h): positions and charges are read from, forces added to the shared mirror
+  DeviceAtomsB200 &da = DeviceAtomsB200::instance();
+  const bool resident = da.resident && !update->setupflag && da.xv_on_device && da.static_on_device;
+  if (polb200_pppm_compute(handle, atom->nlocal, resident ? da.x : atom->x[0], resident ? da.q : atom->q, resident ? da.f : atom->f[0],
+      eflag_global, vflag_global ? 1 : 0, resident ? 1 : 0,
                            &e, v) != POLB200_OK)
     error->all(FLERR, polb200_pppm_last_error(handle));
+  if (resident) da.f_host_current = false;
   if (eflag_global) energy += e;
   if (vflag_global)
     for (int k = 0; k < 6; k++) virial[k] += v[k];

@@ -25,7 +25,8 @@ ABI_SYMBOLS = [
     "polb200_extract", "polb200_single", "polb200_restart_size", "polb200_write_restart",
     "polb200_read_restart", "polb200_restart_settings_size", "polb200_read_restart_settings", "polb200_set_box", "polb200_compute", "polb200_comm_id_size",
     "polb200_comm_create_id", "polb200_comm_init", "polb200_subdomain", "polb200_debug_fetch",
-    "polb200_launch_count", "polb200_set_option", "polb200_decomp_plan", "polb200_tail", "polb200_set_exclusions",
+    "polb200_launch_count", "polb200_set_option", "polb200_dev_alloc", "polb200_dev_free", "polb200_dev_copy",
+    "polb200_dev_zero", "polb200_host_register", "polb200_host_unregister", "polb200_decomp_plan", "polb200_tail", "polb200_set_exclusions",
     "polb200_ewald_create", "polb200_ewald_destroy", "polb200_ewald_last_error", "polb200_ewald_init",
     "polb200_ewald_compute", "polb200_ewald_last_ms",
     "polb200_pppm_create", "polb200_pppm_destroy", "polb200_pppm_last_error", "polb200_pppm_init", "polb200_pppm_compute",
