@@ -119,15 +119,18 @@ int polb200_read_restart(polb200_t *h, const void *buf, long nbytes);
 int polb200_restart_settings_size(const polb200_t *h, long *nbytes);
 int polb200_read_restart_settings(polb200_t *h, const void *buf, long nbytes, long *consumed);
 
-/* `neigh_modify exclude ...` (src/neighbor.cpp:2276-2333): the rules of NPair::exclusion (src/npair.cpp:173-203), at most 8.
+/* `neigh_modify exclude ...` (src/neighbor.cpp:2276-2333): the rules of NPair::exclusion (src/npair.cpp:173-203), at most 32,
+ * and `neigh_modify include g` (src/neighbor.cpp:2264-2274; the list then holds pairs of two atoms of g only,
+ * src/nbin_standard.cpp:209-223, src/npair_half_bin_newton.cpp:51).
  * The reference removes excluded pairs from the list its LJ / real-space Coulomb loop walks (pol.cpp:232-321) and from
  * nothing else -- static field, dipole solve and dipole forces loop over all pairs -- and so does the device path.
  *   POLB200_EXCL_TYPE       exclude type a b            (pairs of atom types a and b, either order)
  *   POLB200_EXCL_GROUP      exclude group g1 g2         a, b = the groups' bitmasks (Group::bitmask)
  *   POLB200_EXCL_MOL_INTRA  exclude molecule/intra g    a = bitmask; both atoms in g and in the same molecule
  *   POLB200_EXCL_MOL_INTER  exclude molecule/inter g    a = bitmask; both atoms in g and in different molecules
+ *   POLB200_EXCL_INCLUDE    include g                   a = bitmask; every pair with an atom OUTSIDE g is left out
  * nrules = 0 clears them (`exclude none`).  Takes effect at the next rebuild. */
-enum { POLB200_EXCL_TYPE = 0, POLB200_EXCL_GROUP = 1, POLB200_EXCL_MOL_INTRA = 2, POLB200_EXCL_MOL_INTER = 3 };
+enum { POLB200_EXCL_TYPE = 0, POLB200_EXCL_GROUP = 1, POLB200_EXCL_MOL_INTRA = 2, POLB200_EXCL_MOL_INTER = 3, POLB200_EXCL_INCLUDE = 4 };
 typedef struct {
   int kind, a, b;
 } polb200_exclusion;

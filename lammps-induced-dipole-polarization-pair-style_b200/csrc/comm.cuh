@@ -393,6 +393,17 @@ static void comm_build_ghosts(polb200_handle *h, int n)
   }
 }
 
+// exclusion-rule bits of the ghosts: the owners' bits travel like any other per-slot record (rebuild only)
+static void comm_ghost_exbits(polb200_handle *h, int n, int ng)
+{
+  CommState &c = h->comm;
+  const int ns = c.nsend;
+  static_assert(sizeof(int2) <= sizeof(int4), "exchange buffers are sized for int4 records");
+  if (ns) LAUNCH(h, k_pack_int2, cdiv(ns, 256), 256, ns, c.send_owner.p, h->exb.p, reinterpret_cast<int2 *>(c.sbufi.p));
+  comm_exchange(h, c.sbufi.p, c.rbufi.p, sizeof(int2));
+  if (ng) LAUNCH(h, k_unpack_int2, cdiv(ng, 256), 256, ng, c.gslot.p, reinterpret_cast<const int2 *>(c.rbufi.p), h->exb.p + n);
+}
+
 // inter-GPU barrier of the peer-push path, optionally carrying this rank's partial squared change to
 // everybody: afterwards *change_inout holds the global sum (ranks added in rank order: identical everywhere)
 static void comm_signal_wait(polb200_handle *h, double *change_inout)

@@ -110,7 +110,8 @@ struct polb200_handle {
 
   // caller-order staging (device)
   DBuf<double> c_x, c_q, c_alpha, c_mu, c_f, c_ef, c_xhold;
-  DBuf<int> c_type, c_mol, c_tag, c_nspecial, c_special, c_mask, exb;
+  DBuf<int> c_type, c_mol, c_tag, c_nspecial, c_special, c_mask;
+  DBuf<int2> exb;                // exclusion-rule membership bits of owned atoms and ghosts
   ExclRules excl{};  // neigh_modify exclude rules (polb200_set_exclusions)
   // pinned host staging
   HPinned<double> h_stage;
@@ -401,16 +402,6 @@ static void rebuild(polb200_handle *h, const polb200_atoms *at)
          at->molecule ? h->c_mol.p : nullptr, at->tag ? h->c_tag.p : nullptr, h->c_alpha.p, h->c_mu.p,
          h->xq.p, h->mua.p, h->tm.p, h->tag.p, h->invperm.p, h->flags.p + 3);
 
-  if (h->excl.n > 0) {  // group-membership bits of the exclusion rules, cell-sorted order
-    bool need_mask = false;
-    for (int r = 0; r < h->excl.n; r++) need_mask |= h->excl.kind[r] != EXCL_TYPE;
-    if (need_mask && !at->mask) throw StyleError{POLB200_ERR_ARG, "neigh_modify exclude group/molecule rules need polb200_atoms.mask"};
-    if (h->comm.active) throw StyleError{POLB200_ERR_UNSUPPORTED, "neigh_modify exclude is not supported with the multi-GPU decomposition"};
-    if (need_mask) stage_in(h, h->c_mask, at->mask, n, dev);
-    h->exb.ensure(n);
-    LAUNCH(h, k_exbits, cdiv(n, 256), 256, n, h->perm.p, need_mask ? h->c_mask.p : (const int *)nullptr, h->excl, h->exb.p);
-  }
-
   // 2. ghosts: periodic images of this box (single GPU) or the boundary shells of the neighbour bricks
   int ng = 0;
   if (h->comm.active) {
@@ -458,6 +449,19 @@ static void rebuild(polb200_handle *h, const polb200_atoms *at)
       LAUNCH(h, k_cell_starts, cdiv(g.ncell + 1, 256), 256, g.ncell, ng, h->keys2.p, h->cg_start.p, g.xbits);
     } else {
       CUDA_CHECK(cudaMemsetAsync(h->cg_start.p, 0, (g.ncell + 2) * sizeof(int), h->stream));
+    }
+  }
+
+  if (h->excl.n > 0) {  // group-membership bits of the exclusion rules: owned atoms (cell-sorted order), then their ghosts
+    bool need_mask = false;
+    for (int r = 0; r < h->excl.n; r++) need_mask |= h->excl.kind[r] != EXCL_TYPE;
+    if (need_mask && !at->mask) throw StyleError{POLB200_ERR_ARG, "neigh_modify exclude group/molecule rules need polb200_atoms.mask"};
+    if (need_mask) stage_in(h, h->c_mask, at->mask, n, dev);
+    h->exb.ensure((size_t)n + ng + 1);
+    LAUNCH(h, k_exbits, cdiv(n, 256), 256, n, h->perm.p, need_mask ? h->c_mask.p : (const int *)nullptr, h->excl, h->exb.p);
+    if (ng > 0) {
+      if (h->comm.active) comm_ghost_exbits(h, n, ng);
+      else LAUNCH(h, k_exbits_ghost, cdiv(ng, 256), 256, ng, n, h->g_owner.p, h->exb.p);
     }
   }
 
@@ -1725,11 +1729,11 @@ int polb200_set_exclusions(polb200_t *h, int nrules, const polb200_exclusion *ru
 {
   if (!h || nrules < 0 || (nrules > 0 && !rules)) return POLB200_ERR_ARG;
   return guarded(h, [&] {
-    if (nrules > MAX_EXCL) throw StyleError{POLB200_ERR_UNSUPPORTED, "more than 8 neigh_modify exclude rules"};
+    if (nrules > MAX_EXCL) throw StyleError{POLB200_ERR_UNSUPPORTED, "more than 32 neigh_modify exclude / include rules"};
     ExclRules X{};
     X.n = nrules;
     for (int r = 0; r < nrules; r++) {
-      if (rules[r].kind < EXCL_TYPE || rules[r].kind > EXCL_MOL_INTER) throw StyleError{POLB200_ERR_ARG, "Illegal neigh_modify command"};
+      if (rules[r].kind < EXCL_TYPE || rules[r].kind > EXCL_INCLUDE) throw StyleError{POLB200_ERR_ARG, "Illegal neigh_modify command"};
       X.kind[r] = rules[r].kind;
       X.a[r] = rules[r].a;
       X.b[r] = rules[r].b;

@@ -463,56 +463,80 @@ constexpr int NPAIR_PART = 8;
 // `neigh_modify exclude` (NPair::exclusion, src/npair.cpp:173-203).  The reference drops excluded pairs while it builds
 // the list its LJ/Coulomb loop walks; its polarization loops never look at that list.  Here the device list stays
 // complete (rank metric, list-mode polarization need every pair) and the LJ/Coulomb part of k_pair skips the pair.
-// Per-atom group membership is pre-digested into exb[s]: bit r = mask & rule[r].a, bit 8+r = mask & rule[r].b.
-constexpr int MAX_EXCL = 8;
-enum { EXCL_TYPE = 0, EXCL_GROUP = 1, EXCL_MOL_INTRA = 2, EXCL_MOL_INTER = 3 };
+// Per-atom group membership is pre-digested into exb[atom] (owned atoms and ghosts): .x bit r = mask & rule[r].a,
+// .y bit r = mask & rule[r].b (group rules).  Up to 32 rules.
+constexpr int MAX_EXCL = 32;
+enum { EXCL_TYPE = 0, EXCL_GROUP = 1, EXCL_MOL_INTRA = 2, EXCL_MOL_INTER = 3, EXCL_INCLUDE = 4 };
 struct ExclRules {
   int n;
   int kind[MAX_EXCL], a[MAX_EXCL], b[MAX_EXCL];
 };
 
-__device__ __forceinline__ bool excl_pair(const ExclRules &X, int2 tmi, int2 tmj, int ei, int ej)
+// exb[atom] = {bits of the rules whose first mask the atom is in, bits of the group rules whose second mask it is in}
+__device__ __forceinline__ bool excl_pair(const ExclRules &X, int2 tmi, int2 tmj, int2 ei, int2 ej)
 {
   for (int r = 0; r < X.n; r++) {
-    const int ai = (ei >> r) & 1, aj = (ej >> r) & 1;
+    const int ai = (ei.x >> r) & 1, aj = (ej.x >> r) & 1;
     switch (X.kind[r]) {
       case EXCL_TYPE:
         if ((tmi.x == X.a[r] && tmj.x == X.b[r]) || (tmi.x == X.b[r] && tmj.x == X.a[r])) return true;
         break;
       case EXCL_GROUP: {
-        const int bi = (ei >> (8 + r)) & 1, bj = (ej >> (8 + r)) & 1;
+        const int bi = (ei.y >> r) & 1, bj = (ej.y >> r) & 1;
         if ((ai && bj) || (bi && aj)) return true;
         break;
       }
       case EXCL_MOL_INTRA:
         if (ai && aj && tmi.y == tmj.y) return true;
         break;
-      default:
+      case EXCL_MOL_INTER:
         if (ai && aj && tmi.y != tmj.y) return true;
+        break;
+      default:  // EXCL_INCLUDE (neigh_modify include g): the list holds pairs of two atoms of the group only
+        if (!(ai && aj)) return true;
     }
   }
   return false;
 }
 
-__global__ void k_exbits(int nloc, const int *__restrict__ perm, const int *__restrict__ mask, ExclRules X, int *__restrict__ exb)
+__global__ void k_exbits(int nloc, const int *__restrict__ perm, const int *__restrict__ mask, ExclRules X, int2 *__restrict__ exb)
 {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nloc) return;
   const int m = mask ? mask[perm[s]] : 0;
-  int e = 0;
+  unsigned ea = 0, eb = 0;
   for (int r = 0; r < X.n; r++) {
     if (X.kind[r] == EXCL_TYPE) continue;
-    if (m & X.a[r]) e |= 1 << r;
-    if (X.kind[r] == EXCL_GROUP && (m & X.b[r])) e |= 1 << (8 + r);
+    if (m & X.a[r]) ea |= 1u << r;
+    if (X.kind[r] == EXCL_GROUP && (m & X.b[r])) eb |= 1u << r;
   }
-  exb[s] = e;
+  exb[s] = make_int2((int)ea, (int)eb);
+}
+
+// periodic images inherit the bits of their owners (single GPU); bricks receive them with the halo (comm.cuh)
+__global__ void k_exbits_ghost(int ng, int nloc, const int *__restrict__ g_owner, int2 *__restrict__ exb)
+{
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < ng) exb[nloc + g] = exb[g_owner[g]];
+}
+
+__global__ void k_pack_int2(int ns, const int *__restrict__ owner, const int2 *__restrict__ src, int2 *__restrict__ sbuf)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < ns) sbuf[t] = src[owner[t]];
+}
+
+__global__ void k_unpack_int2(int ng, const int *__restrict__ gslot, const int2 *__restrict__ rbuf, int2 *__restrict__ dst)
+{
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < ng) dst[g] = rbuf[gslot[g]];
 }
 
 template <bool EVFLAG, bool FIELD, bool EXCL>
 __global__ void __launch_bounds__(BLOCK, 3)
 k_pair(int nloc, DevParams P, const double4 *__restrict__ xq, const int2 *__restrict__ tm, ListRows L,
        double4 *__restrict__ f_pair, double4 *__restrict__ ef, double *__restrict__ partial,
-       double *__restrict__ eatom_row, double *__restrict__ vatom_row, ExclRules X, const int *__restrict__ exb,
+       double *__restrict__ eatom_row, double *__restrict__ vatom_row, ExclRules X, const int2 *__restrict__ exb,
        const int *__restrict__ g_owner)
 {
   const int lane = threadIdx.x & 31;
@@ -522,7 +546,7 @@ k_pair(int nloc, DevParams P, const double4 *__restrict__ xq, const int2 *__rest
     const double4 xi = xq[s];
     const int2 tmi = tm[s];
     const int n1 = P.pc.ntypes + 1;
-    const int exi = EXCL ? exb[s] : 0;
+    const int2 exi = EXCL ? exb[s] : make_int2(0, 0);
     double fx = 0, fy = 0, fz = 0, ex = 0, ey = 0, ez = 0;
     // neighbour entries are fetched two trips ahead so that the dependent index -> gather chain of the next
     // trip overlaps this trip's arithmetic
@@ -542,7 +566,7 @@ k_pair(int nloc, DevParams P, const double4 *__restrict__ xq, const int2 *__rest
       const double rsq = rsq_nofma(dx, dy, dz);
       const int ij = tmi.x * n1 + tmj.x;
       bool skip = false;
-      if (EXCL) skip = excl_pair(X, tmi, tmj, exi, exb[j < nloc ? j : g_owner[j - nloc]]);
+      if (EXCL) skip = excl_pair(X, tmi, tmj, exi, exb[j]);
       if (!skip && rsq < P.lj.cutsq[ij]) {
         double evdwl, ecoul;
         const double fpair = lj_coul_pair(P.pc, P.lj, P.tb, ij, rsq, xi.w, xj.w, sb, EVFLAG, evdwl, ecoul);

@@ -253,6 +253,9 @@ void PairLJCutCoulLongPolarization::compute(int eflag, int vflag)
     for (int m = 0; m < neighbor->nex_mol; m++)
       rules.push_back({neighbor->ex_mol_intra[m] ? POLB200_EXCL_MOL_INTRA : POLB200_EXCL_MOL_INTER,
                        group->bitmask[neighbor->ex_mol_group[m]], 0});
+    // `neigh_modify include g` (with `atom_modify first g`): only pairs of two atoms of g reach the pair loop
+    if (neighbor->includegroup)
+      rules.push_back({POLB200_EXCL_INCLUDE, group->bitmask[neighbor->includegroup], 0});
     if (!rules.empty() || nexclude_sent > 0) {
       CHECK(polb200_set_exclusions(handle, (int) rules.size(), rules.empty() ? NULL : rules.data()));
       nexclude_sent = (int) rules.size();

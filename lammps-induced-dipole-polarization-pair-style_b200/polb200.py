@@ -59,7 +59,7 @@ class Exclusion(C.Structure):
     _fields_ = [("kind", C.c_int), ("a", C.c_int), ("b", C.c_int)]
 
 
-EXCL_KINDS = {"type": 0, "group": 1, "molecule/intra": 2, "molecule/inter": 3}
+EXCL_KINDS = {"type": 0, "group": 1, "molecule/intra": 2, "molecule/inter": 3, "include": 4}
 
 
 class Result(C.Structure):
@@ -390,7 +390,7 @@ class PairStyle:
 
     def set_exclusions(self, rules):
         """`neigh_modify exclude` rules as tuples: ("type", i, j), ("group", bit1, bit2), ("molecule/intra", bit),
-        ("molecule/inter", bit); [] clears them"""
+        ("molecule/inter", bit), ("include", bit) for `neigh_modify include`; [] clears them"""
         arr = (Exclusion * max(len(rules), 1))()
         for k, r in enumerate(rules):
             arr[k].kind, arr[k].a, arr[k].b = EXCL_KINDS[r[0]], int(r[1]), int(r[2]) if len(r) > 2 else 0

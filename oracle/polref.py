@@ -327,8 +327,12 @@ def parse_exclusions(text, group_bits):
             continue
         i = 1
         while i < len(w):
+            if w[i] == "include":   # src/neighbor.cpp:2264-2274: the list is built over the atoms of the group only
+                rules.append(("include", group_bits[w[i + 1]]))
+                i += 2
+                continue
             if w[i] != "exclude":
-                raise ValueError("only neigh_modify exclude is restated: " + line)
+                raise ValueError("only neigh_modify exclude / include are restated: " + line)
             kind = w[i + 1]
             if kind == "type":
                 rules.append(("type", int(w[i + 2]), int(w[i + 3])))
@@ -360,6 +364,8 @@ def excluded_pairs(rules, itype, jtype, imask, jmask, imol, jmol):
             ex |= ((imask & r[1]) != 0) & ((jmask & r[1]) != 0) & (imol == jmol)
         elif r[0] == "molecule/inter":
             ex |= ((imask & r[1]) != 0) & ((jmask & r[1]) != 0) & (imol != jmol)
+        elif r[0] == "include":   # src/nbin_standard.cpp:209-223 (only group atoms are binned), npair_half_bin_newton.cpp:51
+            ex |= ((imask & r[1]) == 0) | ((jmask & r[1]) == 0)
     return ex
 
 

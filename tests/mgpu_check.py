@@ -41,13 +41,14 @@ def make_style(device, sysm, words, cut_coul):
     return s
 
 
-def run(style, x, q, typ, alpha, tag, mu, ago):
+def run(style, x, q, typ, alpha, tag, mu, ago, mask=None):
     n = x.shape[0]
     f = np.zeros((n, 3))
     ef = np.zeros((n, 3))
     mu = mu.copy()
     res = style.compute(c(x, np.float64), c(q, np.float64), c(typ, np.int32), c(alpha, np.float64), mu, f,
-                        tag=c(tag, np.int32), ef_static=ef, eflag=1, vflag=2, ago=ago)
+                        tag=c(tag, np.int32), ef_static=ef, eflag=1, vflag=2, ago=ago,
+                        mask=None if mask is None else c(mask, np.int32))
     return res, mu, ef, f
 
 
@@ -77,12 +78,21 @@ def main():
              ("jacobi_fixed_push", "polar_gs_ranked no fixed_iteration yes max_iterations 12 damp_type exponential", 1, 1e-12),
              ("jacobi_precision_push", "polar_gs_ranked no precision 1e-9 max_iterations 60 damp_type exponential use_previous yes", 1, 1e-12),
              ("jacobi_precision_nccl", "polar_gs_ranked no precision 1e-9 max_iterations 60 damp_type exponential", 0, 1e-12),
-             ("gs_ranked_chunks", "precision 1e-11 max_iterations 60 damp_type exponential", 1, 5e-9)]
+             ("gs_ranked_chunks", "precision 1e-11 max_iterations 60 damp_type exponential", 1, 5e-9),
+             # neigh_modify exclude / include rules across bricks: the ghosts carry their owners' membership bits
+             ("exclusions_push", "polar_gs_ranked no fixed_iteration yes max_iterations 6 damp_type exponential", 1, 1e-12)]
+    gmask = (1 | (2 * (np.random.default_rng(3).random(sysm.n) < 0.4)) | (4 * (np.random.default_rng(4).random(sysm.n) < 0.6))).astype(np.int32)
     for name, words, push, tol in cases:
         ref = make_style(local, sysm, words, cut)
         dec = make_style(local, sysm, words, cut)
         dec.comm_init(rank, world, fresh_id(), pg)
         dec.set_option("p2p_push", push)
+        mask = None
+        if name.startswith("exclusions"):
+            rules = [("type", 1, 1), ("group", 2, 4), ("include", 4)]
+            ref.set_exclusions(rules)
+            dec.set_exclusions(rules)
+            mask = gmask
         lo, hi = dec.subdomain()
         x = sysm.x.copy()
         mu_g = np.zeros((sysm.n, 3))
@@ -98,8 +108,9 @@ def main():
                 x = sysm.boxlo + np.mod(x - sysm.boxlo, sysm.boxhi - sysm.boxlo)
                 mine = owned_mask(x, lo, hi)
                 idx = np.nonzero(mine)[0]
-            r0, mu0, ef0, f0 = run(ref, x, sysm.q, sysm.type, sysm.alpha, sysm.tag, mu_g, ago)
-            r1, mu1, ef1, f1 = run(dec, x[idx], sysm.q[idx], sysm.type[idx], sysm.alpha[idx], sysm.tag[idx], mu_g[idx], ago)
+            r0, mu0, ef0, f0 = run(ref, x, sysm.q, sysm.type, sysm.alpha, sysm.tag, mu_g, ago, mask)
+            r1, mu1, ef1, f1 = run(dec, x[idx], sysm.q[idx], sysm.type[idx], sysm.alpha[idx], sysm.tag[idx], mu_g[idx], ago,
+                                   None if mask is None else mask[idx])
             stats = dec.debug_fetch("comm_stats", np.float64, 5)
             e = torch.tensor([r1.eng_vdwl, r1.eng_coul, r1.eng_pol] + list(r1.virial[:]), dtype=torch.float64, device="cuda")
             dist.all_reduce(e)
@@ -128,6 +139,27 @@ def main():
             failures.append(name)
         ref.close()
         dec.close()
+    # a brick that fails alone must take the others with it (same error on every rank, no hang): rank 0 is handed no
+    # atoms at a rebuild step
+    dec = make_style(local, sysm, cases[0][1], cut)
+    dec.comm_init(rank, world, fresh_id(), pg)
+    lo, hi = dec.subdomain()
+    idx = np.nonzero(owned_mask(sysm.x, lo, hi))[0]
+    if rank == 0:
+        idx = idx[:0]
+    try:
+        run(dec, sysm.x[idx], sysm.q[idx], sysm.type[idx], sysm.alpha[idx], sysm.tag[idx], np.zeros((sysm.n, 3))[idx], 0)
+        msg = "no error"
+    except pb.Polb200Error as e:
+        msg = str(e)
+    agreed = "owns no atoms" in msg
+    flag = torch.tensor([0 if agreed else 1], device="cuda")
+    dist.all_reduce(flag)
+    if rank == 0:
+        print(f"[mgpu {world} ranks] empty brick -> every rank: {msg!r}: {'OK' if int(flag) == 0 else 'FAIL'}", flush=True)
+    if int(flag):
+        failures.append("error_agreement")
+    dec.close()
     dist.barrier()
     dist.destroy_process_group()
     if failures:

@@ -572,13 +572,26 @@ def test_group_coloured_sweep_stop_flag_and_lag_do_not_change_the_result():
     assert outs["polar_gs_ranked no precision 1e-9 max_iterations 5"][0].status & pb.STATUS_DIVERGED
 
 
-def test_exclusions_in_list_mode_match_oracle(style):
-    """neigh_modify exclude with polar_cutoff (neighbor-list polarization): LJ / Coulomb drop the excluded pairs, static
-    field, dipoles and dipole forces keep them -- type rule + group rule + molecule/intra rule on random group masks"""
+@pytest.mark.parametrize("ruleset", ["mixed", "include", "many"])
+def test_exclusions_in_list_mode_match_oracle(style, ruleset):
+    """neigh_modify exclude / include with polar_cutoff (neighbor-list polarization): LJ / Coulomb drop the excluded pairs,
+    static field, dipoles and dipole forces keep them -- type rule + group rule + molecule/intra rule on random group
+    masks; `neigh_modify include g` (pairs of two atoms of g only) with a molecule/inter rule; 14 rules at once (the
+    device holds up to 32)"""
     sysm = H.lj_charge_fluid(10)                       # 4000 atoms, L = 34.2 A
     rng = np.random.default_rng(17)
     mask = (1 | (2 * (rng.random(sysm.n) < 0.3)) | (4 * (rng.random(sysm.n) < 0.3)) | (8 * (rng.random(sysm.n) < 0.2))).astype(np.int32)
     rules = [("type", 1, 1), ("group", 2, 4), ("molecule/intra", 8)]
+    if ruleset == "include":
+        mask = (1 | (2 * (rng.random(sysm.n) < 0.7)) | (4 * (rng.random(sysm.n) < 0.5))).astype(np.int32)
+        rules = [("include", 2), ("molecule/inter", 4)]
+        sysm.molecule[:] = 1 + np.arange(sysm.n) // 7      # (molecule ids give molecule/inter something to separate)
+    elif ruleset == "many":
+        mask = np.ones(sysm.n, dtype=np.int32)
+        for b in range(1, 15):
+            mask |= ((rng.random(sysm.n) < 0.15) << b).astype(np.int32)
+        rules = [("group", 1 << b, 1 << (b + 1)) for b in range(1, 13)] + [("type", 2, 2), ("molecule/intra", 1 << 14)]
+        assert len(rules) == 14
     kw = dict(fixed_iteration=1, max_iterations=5, damp_type="exponential", polar_gs_ranked=0)
     st = H.fluid_style(sysm, 2.5, 12.0, polar_cut=12.0, **kw)
     ref = P.polar_rows(sysm, st)
