@@ -29,7 +29,8 @@ if [ -x "$OUT/lmp_b200" ] && [ "$OUT/lmp_b200" -nt "$HERE/pair_lj_cut_coul_long_
    && [ "$OUT/lmp_b200" -nt "$HERE/compute_polarization_atom_b200.cpp" ] && [ "$OUT/lmp_b200" -nt "$HERE/compute_polarization_atom_b200.h" ] \
    && [ "$OUT/lmp_b200" -nt "$HERE/pppm_b200.cpp" ] && [ "$OUT/lmp_b200" -nt "$HERE/pppm_b200.h" ] \
    && [ "$OUT/lmp_b200" -nt "$HERE/fix_rigid_nh_b200.cpp" ] && [ "$OUT/lmp_b200" -nt "$HERE/fix_rigid_nh_b200.h" ] \
-   && [ "$OUT/lmp_b200" -nt "$HERE/device_atoms_b200.h" ] \
+   && [ "$OUT/lmp_b200" -nt "$HERE/device_atoms_b200.h" ] && [ -x "$OUT/extract_driver_b200" ] \
+   && [ "$OUT/extract_driver_b200" -nt "$HERE/extract_driver_b200.cpp" ] \
    && [ "$OUT/lmp_b200" -nt "$ROOT/include/polb200.h" ] && [ -z "${POLB200_LMP_REBUILD:-}" ]; then
   echo "build_lmp_b200: $OUT/lmp_b200 is up to date"
   exit 0
@@ -73,7 +74,18 @@ rm -f fix_rigid_nvt.h fix_rigid_nvt.cpp
 # shared device mirror of atom->x / v / f / q / mu for the three styles above (second half)
 cp "$HERE/device_atoms_b200.h" .
 cp "$ROOT/include/polb200.h" .
+# Atom::extract learns the three per-atom arrays: what lammps_extract_atom / the Python module see
+if ! grep -q '"mu_induced"' atom.cpp; then
+  sed -i 's|^  if (strcmp(name,"mass") == 0) return (void \*) mass;|  if (strcmp(name,"static_polarizability") == 0) return (void *) static_polarizability;\n  if (strcmp(name,"mu_induced") == 0) return (void *) mu_induced;\n  if (strcmp(name,"ef_static") == 0) return (void *) ef_static;\n&|' atom.cpp
+  grep -q '"mu_induced"' atom.cpp || { echo "Atom::extract patch did not apply"; exit 1; }
+fi
 make -j"$JOBS" serial LIB="-L$PKG -lpolb200 -Wl,-rpath,'\$\$ORIGIN/../..'" > "$W/build.log" 2>&1 || { tail -40 "$W/build.log"; exit 1; }
 cp lmp_serial "$OUT/lmp_b200"
 strip "$OUT/lmp_b200"
+LMPSRC="$HERE"
+# library-interface driver (tests): the same objects without main.o
+g++ -g -O -I. -ISTUBS -c "$LMPSRC/extract_driver_b200.cpp" -o Obj_serial/extract_driver_b200.o
+g++ -g -O Obj_serial/extract_driver_b200.o $(for f in *.cpp; do [ "$f" = main.cpp ] || echo "Obj_serial/${f%.cpp}.o"; done) -LSTUBS -lmpi_stubs -L"$PKG" -lpolb200 -Wl,-rpath,'$ORIGIN/../..'  -o "$OUT/extract_driver_b200"
+strip "$OUT/extract_driver_b200"
+
 echo "build_lmp_b200: built $OUT/lmp_b200"

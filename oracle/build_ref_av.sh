@@ -18,9 +18,9 @@ if [ ! -d "$REF/src" ]; then
   exit 0
 fi
 mkdir -p "$OUT"
-if [ -x "$OUT/lmp_serial_av" ] && [ -z "${POLB200_REF_REBUILD:-}" ]; then
+if [ -x "$OUT/lmp_serial_av" ] && [ -x "$OUT/extract_driver_av" ] && [ -z "${POLB200_REF_REBUILD:-}" ]; then
   new=0
-  for f in atom_vec_full_polar_b200.h atom_vec_full_polar_b200.cpp compute_polarization_atom_b200.h compute_polarization_atom_b200.cpp; do
+  for f in atom_vec_full_polar_b200.h atom_vec_full_polar_b200.cpp compute_polarization_atom_b200.h compute_polarization_atom_b200.cpp extract_driver_b200.cpp; do
     [ "$LMPDIR/$f" -nt "$OUT/lmp_serial_av" ] && new=1
   done
   if [ $new = 0 ]; then echo "build_ref_av: $OUT/lmp_serial_av is up to date"; exit 0; fi
@@ -44,7 +44,18 @@ cd "$W/src"
 sed -i 's|^AtomStyle(full,AtomVecFull)|AtomStyle(full/stock,AtomVecFull)|' atom_vec_full.h
 cp "$LMPDIR/atom_vec_full_polar_b200.h" "$LMPDIR/atom_vec_full_polar_b200.cpp" .
 cp "$LMPDIR/compute_polarization_atom_b200.h" "$LMPDIR/compute_polarization_atom_b200.cpp" .
+# Atom::extract learns the three per-atom arrays: what lammps_extract_atom / the Python module see
+if ! grep -q '"mu_induced"' atom.cpp; then
+  sed -i 's|^  if (strcmp(name,"mass") == 0) return (void \*) mass;|  if (strcmp(name,"static_polarizability") == 0) return (void *) static_polarizability;\n  if (strcmp(name,"mu_induced") == 0) return (void *) mu_induced;\n  if (strcmp(name,"ef_static") == 0) return (void *) ef_static;\n&|' atom.cpp
+  grep -q '"mu_induced"' atom.cpp || { echo "Atom::extract patch did not apply"; exit 1; }
+fi
 make -j"$JOBS" serial > "$W/build.log" 2>&1 || { tail -40 "$W/build.log"; exit 1; }
 cp lmp_serial "$OUT/lmp_serial_av"
+LMPSRC="$LMPDIR"
+# library-interface driver (tests): the same objects without main.o
+g++ -g -O -I. -ISTUBS -c "$LMPSRC/extract_driver_b200.cpp" -o Obj_serial/extract_driver_b200.o
+g++ -g -O Obj_serial/extract_driver_b200.o $(for f in *.cpp; do [ "$f" = main.cpp ] || echo "Obj_serial/${f%.cpp}.o"; done) -LSTUBS -lmpi_stubs  -o "$OUT/extract_driver_av"
+strip "$OUT/extract_driver_av"
+
 strip "$OUT/lmp_serial_av"
 echo "build_ref_av: built $OUT/lmp_serial_av"

@@ -88,6 +88,28 @@ def test_compute_polarization_atom_exposes_the_arrays(tmp_path):
     assert H.rel_err(rows[:, 5:8], fx["ef_static"][order]) < 1e-9
 
 
+def test_library_interface_extracts_the_arrays(tmp_path):
+    """`lammps_extract_atom(lmp, "mu_induced" | "static_polarizability" | "ef_static")` -- what a C or Python driver of
+    LAMMPS sees (src/library.cpp -> Atom::extract, three names added by the build): a driver that runs the shipped example
+    through the library interface prints the arrays of the reference run"""
+    import subprocess
+    driver = LMP_AV.parent / LMP_AV.name.replace("lmp_serial_av", "extract_driver_av").replace("lmp_b200", "extract_driver_b200")
+    if not driver.exists():
+        pytest.skip(f"{driver.name} not built")
+    fx = write_h2_data(tmp_path)
+    (tmp_path / "in.case").write_text("\n".join(h2_shipped_lines(fx) + H2_DYNAMICS + ["run 0"]) + "\n")
+    r = subprocess.run([str(driver), "in.case"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    rows = np.array([[float(t) for t in l.split()] for l in r.stdout.splitlines() if l.strip()])
+    assert rows.shape == (fx["x"].shape[0], 8)
+    rows = rows[np.argsort(rows[:, 0])]
+    order = np.argsort(fx["tag"])
+    assert np.array_equal(rows[:, 0].astype(int), fx["tag"][order])
+    assert np.abs(rows[:, 1] - fx["alpha"][order]).max() == 0.0
+    assert H.rel_err(rows[:, 2:5], fx["mu_out"][order]) < 1e-9
+    assert H.rel_err(rows[:, 5:8], fx["ef_static"][order]) < 1e-9
+
+
 def test_replicate_goes_through_the_restart_records(tmp_path):
     """`replicate` packs and unpacks every atom with pack_restart / unpack_restart: the copies keep their
     polarizabilities (sum over atoms doubles)"""

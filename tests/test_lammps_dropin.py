@@ -157,7 +157,7 @@ def test_shipped_h2_example_reproduces_the_committed_log(tmp_path):
 # ---- the committed atom style inside lmp_b200 ----------------------------------------------
 
 def test_atom_style_cases_through_lmp_b200(tmp_path, monkeypatch):
-    """tests/test_atom_style.py's cases (atom sorting, restart round trip without `set`, replicate) with every style on
+    """tests/test_atom_style.py's cases (atom sorting, restart round trip without `set`, replicate, lammps_extract_atom) with every style on
     the device: the same atom style is built into lmp_b200, where pair style, Ewald and fix rigid read and write the
     arrays through the C ABI"""
     if not LMP_B200.exists():
@@ -165,7 +165,8 @@ def test_atom_style_cases_through_lmp_b200(tmp_path, monkeypatch):
     import test_atom_style as TA
     monkeypatch.setattr(TA, "LMP_AV", LMP_B200)
     for k, case in enumerate([TA.test_atom_sorting_carries_the_arrays, TA.test_restart_round_trip_keeps_polarizabilities_and_dipoles,
-                              TA.test_replicate_goes_through_the_restart_records]):
+                              TA.test_replicate_goes_through_the_restart_records,
+                              TA.test_library_interface_extracts_the_arrays]):
         work = tmp_path / f"case{k}"
         work.mkdir()
         case(work)
