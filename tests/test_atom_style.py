@@ -110,6 +110,25 @@ def test_library_interface_extracts_the_arrays(tmp_path):
     assert H.rel_err(rows[:, 5:8], fx["ef_static"][order]) < 1e-9
 
 
+def test_exchange_record_round_trips_every_atom(tmp_path):
+    """the record Comm::exchange ships when an atom changes MPI ranks (src/comm_brick.cpp:597-690) cannot occur in this
+    single-rank build: the driver packs every atom with AtomVec::pack_exchange and unpacks it as a new atom -- the copy
+    carries position, velocity, charge, ids, special list AND polarizability, dipole, static field (the trailer behind the
+    stock record), and the unpacker consumes exactly what the packer wrote"""
+    import subprocess
+    driver = LMP_AV.parent / LMP_AV.name.replace("lmp_serial_av", "extract_driver_av").replace("lmp_b200", "extract_driver_b200")
+    if not driver.exists():
+        pytest.skip(f"{driver.name} not built")
+    fx = write_h2_data(tmp_path)
+    (tmp_path / "in.case").write_text("\n".join(h2_shipped_lines(fx) + H2_DYNAMICS + ["run 1"]) + "\n")
+    r = subprocess.run([str(driver), "in.case", "exchange"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    w = r.stdout.split()
+    assert w[0] == "exchange" and int(w[2]) == fx["x"].shape[0]
+    # stock AtomVecFull record (1 length + x v tag type mask image q molecule + bonded topology) + 7 doubles of trailer
+    assert int(w[4]) >= 18 + 7 and float(w[7]) == 0.0
+
+
 def test_replicate_goes_through_the_restart_records(tmp_path):
     """`replicate` packs and unpacks every atom with pack_restart / unpack_restart: the copies keep their
     polarizabilities (sum over atoms doubles)"""

@@ -166,7 +166,7 @@ def test_atom_style_cases_through_lmp_b200(tmp_path, monkeypatch):
     monkeypatch.setattr(TA, "LMP_AV", LMP_B200)
     for k, case in enumerate([TA.test_atom_sorting_carries_the_arrays, TA.test_restart_round_trip_keeps_polarizabilities_and_dipoles,
                               TA.test_replicate_goes_through_the_restart_records,
-                              TA.test_library_interface_extracts_the_arrays]):
+                              TA.test_library_interface_extracts_the_arrays, TA.test_exchange_record_round_trips_every_atom]):
         work = tmp_path / f"case{k}"
         work.mkdir()
         case(work)
