@@ -14,6 +14,7 @@
 //   k_pppm_force   per atom: interpolate the three field grids with the same weights (fieldforce_ik)
 //   FFTs           cuFFT Z2Z (a plain library FFT, dlopen'ed so that libpolb200.so keeps no link-time dependency): one
 //                  e^{+ikr} transform of the charge grid, three e^{-ikr} transforms of the field grids, in place
+#include <cub/cub.cuh>
 #include <cuda_runtime.h>
 #include <cufft.h>
 #include <dlfcn.h>
@@ -179,6 +180,93 @@ __global__ void k_pppm_rho(int n, PppmConst C, const double *__restrict__ x, con
   }
 }
 
+// ---- the same charge assignment without atomics: bit-reproducible (every sum has a fixed order) --------------------
+// The atoms are sorted by the first grid point their stencil touches (stable radix sort: atoms of a cell stay in caller
+// order), their order weights are evaluated once, and ONE THREAD PER GRID POINT gathers what the atoms of the order^3
+// cells around it deposit there: cells in (z, y, x) order, atoms in sorted order.
+constexpr int PPPM_WSTRIDE = 3 * PPPM_MAXORDER + 2;  // weights of the three dimensions, q * delvolinv, x index of the cell
+
+__global__ void k_pppm_cellkey(int n, PppmConst C, const double *__restrict__ x, int *__restrict__ key, int *__restrict__ iota)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int c[3];
+  const double xs[3] = {x[3 * i], x[3 * i + 1], x[3 * i + 2]};
+  const int nn[3] = {C.nx, C.ny, C.nz};
+  for (int d = 0; d < 3; d++) {
+    const double u = (xs[d] - C.boxlo[d]) * C.delinv[d];
+    c[d] = wrap((int)(u + C.shift) - PPPM_OFFSET + C.nlower, nn[d]);
+  }
+  key[i] = (c[2] * C.ny + c[1]) * C.nx + c[0];
+  iota[i] = i;
+}
+
+__global__ void k_pppm_cellstart(int ncell, int n, const int *__restrict__ sorted_key, int *__restrict__ start)
+{
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > ncell) return;
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (sorted_key[mid] < c) lo = mid + 1;
+    else hi = mid;
+  }
+  start[c] = lo;
+}
+
+__global__ void k_pppm_weights_sorted(int n, PppmConst C, const int *__restrict__ order, const double *__restrict__ x,
+                                      const double *__restrict__ q, double *__restrict__ wts)
+{
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const int i = order[s];
+  int part[3];
+  double w[3][PPPM_MAXORDER];
+  pppm_weights(C, x[3 * i], x[3 * i + 1], x[3 * i + 2], part, w);
+  double *o = wts + (size_t)s * PPPM_WSTRIDE;
+  for (int d = 0; d < 3; d++)
+    for (int k = 0; k < PPPM_MAXORDER; k++) o[d * PPPM_MAXORDER + k] = k < C.order ? w[d][k] : 0.0;
+  o[3 * PPPM_MAXORDER] = C.delvolinv * q[i];
+  o[3 * PPPM_MAXORDER + 1] = (double)wrap(part[0] + C.nlower, C.nx);
+}
+
+__global__ void __launch_bounds__(256)
+k_pppm_rho_gather(PppmConst C, const int *__restrict__ start, const double *__restrict__ wts, double2 *__restrict__ grid)
+{
+  // one WARP per grid point: lane = one (z, y) cell row of the order x order rows that reach the point; the partial sums
+  // are combined by a fixed shuffle tree, so the result does not depend on anything but the data
+  const size_t total = (size_t)C.nx * C.ny * C.nz;
+  const size_t m = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (m >= total) return;
+  const int mx = (int)(m % C.nx), my = (int)((m / C.nx) % C.ny), mz = (int)(m / ((size_t)C.nx * C.ny));
+  double sum = 0.0;
+  // the cells of one (z, y) row that reach this point, cx = mx - order + 1 .. mx, are consecutive in the sorted order: one
+  // (or, across the periodic wrap, two) contiguous run(s) of atoms per row instead of `order` cell lookups
+  const int xlo = mx - C.order + 1;
+  for (int r = lane; r < C.order * C.order; r += 32) {
+    const int c = r / C.order, b = r - c * C.order;
+    const int cz = wrap(mz - c, C.nz), cy = wrap(my - b, C.ny);
+    const int row = (cz * C.ny + cy) * C.nx;
+    for (int part = 0; part < 2; part++) {
+      // part 0: cells [max(xlo,0), mx]; part 1 (only when xlo < 0): the wrapped cells [nx + xlo, nx - 1]
+      if (part == 1 && xlo >= 0) break;
+      const int c0 = part == 0 ? max(xlo, 0) : C.nx + xlo, c1 = part == 0 ? mx : C.nx - 1;
+      const int s1 = start[row + c1 + 1];
+      for (int s = start[row + c0]; s < s1; s++) {
+        const double *o = wts + (size_t)s * PPPM_WSTRIDE;
+        const int cx = (int)o[3 * PPPM_MAXORDER + 1];
+        const int a = part == 0 ? mx - cx : mx + C.nx - cx;
+        // the reference's product order (pppm.cpp:1981-1990): ((q/vol * wz) * wy) * wx
+        sum += ((o[3 * PPPM_MAXORDER] * o[2 * PPPM_MAXORDER + c]) * o[PPPM_MAXORDER + b]) * o[a];
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
+  if (lane == 0) grid[m] = make_double2(sum, 0.0);
+}
+
 constexpr int NPPPM_PART = 7;  // energy + 6 virial terms
 
 // poisson_ik (pppm.cpp:2032-2157) for one k-point, and the virial coefficients of setup (:455-480) on the fly
@@ -318,6 +406,10 @@ struct polb200_pppm {
   cufftHandle plan = 0;
   DBuf<double> greensfn, partial, out, c_x, c_q, c_f;
   DBuf<double2> work1, wx, wy, wz;
+  DBuf<int> key, key2, idx, idx2, cstart;   // atomics-free charge assignment: atoms sorted by grid cell
+  DBuf<double> wts;
+  DBuf<char> cub_tmp;
+  bool rho_atomics = false;                 // true: the first version (order^3 FP64 atomicAdd per atom; sums not reproducible)
   HPinned<double> h_out, h_f;
   float ms_last = 0.f;
 };
@@ -391,6 +483,7 @@ int polb200_pppm_create(polb200_pppm_t **out, int device)
   }
   polb200_pppm *p = new polb200_pppm();
   p->device = device;
+  if (const char *v = getenv("POLB200_PPPM_ATOMICS")) p->rho_atomics = atoi(v) != 0;  // A/B against the first version
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&p->ev[0]) != cudaSuccess || cudaEventCreate(&p->ev[1]) != cudaSuccess) {
     delete p;
@@ -581,9 +674,29 @@ int polb200_pppm_compute(polb200_pppm_t *p, int nlocal, const double *x, const d
       dx = p->c_x.p; dq = p->c_q.p; df = p->c_f.p;
     }
     const int ev = ((eflag & 1) || (vflag % 4)) ? 1 : 0;
-    CUDA_CHECK(cudaMemsetAsync(p->work1.p, 0, total * sizeof(double2), p->stream));
-    k_pppm_rho<<<cdiv(n, 128), 128, 0, p->stream>>>(n, C, dx, dq, p->work1.p);
-    PPPM_LAUNCHED(p);
+    if (p->rho_atomics) {
+      CUDA_CHECK(cudaMemsetAsync(p->work1.p, 0, total * sizeof(double2), p->stream));
+      k_pppm_rho<<<cdiv(n, 128), 128, 0, p->stream>>>(n, C, dx, dq, p->work1.p);
+      PPPM_LAUNCHED(p);
+    } else {
+      p->key.ensure(n); p->key2.ensure(n); p->idx.ensure(n); p->idx2.ensure(n); p->cstart.ensure(total + 2);
+      p->wts.ensure((size_t)n * PPPM_WSTRIDE);
+      k_pppm_cellkey<<<cdiv(n, 256), 256, 0, p->stream>>>(n, C, dx, p->key.p, p->idx.p);
+      PPPM_LAUNCHED(p);
+      int bits = 1;
+      while ((1ul << bits) < total + 1) bits++;
+      size_t bytes = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, bytes, p->key.p, p->key2.p, p->idx.p, p->idx2.p, n, 0, bits, p->stream);
+      p->cub_tmp.ensure(bytes);
+      CUDA_CHECK(cub::DeviceRadixSort::SortPairs(p->cub_tmp.p, bytes, p->key.p, p->key2.p, p->idx.p, p->idx2.p, n, 0, bits, p->stream));
+      p->launches += 3;
+      k_pppm_cellstart<<<cdiv((long)total + 1, 256), 256, 0, p->stream>>>((int)total, n, p->key2.p, p->cstart.p);
+      PPPM_LAUNCHED(p);
+      k_pppm_weights_sorted<<<cdiv(n, 128), 128, 0, p->stream>>>(n, C, p->idx2.p, dx, dq, p->wts.p);
+      PPPM_LAUNCHED(p);
+      k_pppm_rho_gather<<<cdiv((long)total * 32, 256), 256, 0, p->stream>>>(C, p->cstart.p, p->wts.p, p->work1.p);
+      PPPM_LAUNCHED(p);
+    }
     // fft1->compute(work1,work1,1): flag 1 = the e^{+ikr} transform, unscaled (fft3d.cpp:103-123) = CUFFT_INVERSE
     CUFFT_CHECK(g_cufft.ExecZ2Z(p->plan, reinterpret_cast<cufftDoubleComplex *>(p->work1.p),
                                 reinterpret_cast<cufftDoubleComplex *>(p->work1.p), CUFFT_INVERSE));

@@ -84,3 +84,30 @@ def test_device_pppm_agrees_with_device_ewald_at_equal_g():
     assert abs(ep - ee) < 1e-3 * abs(ee)
     assert np.abs(fp - fe).max() < 1e-3 * np.abs(fe).max()
     p.close(), e.close()
+
+
+def test_charge_assignment_is_bit_reproducible(monkeypatch):
+    """make_rho without atomics (atoms sorted by grid cell, one thread per grid point, fixed summation order): repeated
+    computes give bit-identical forces, energy and virial -- and the same numbers as the first version (order^3 FP64
+    atomicAdd per atom, POLB200_PPPM_ATOMICS=1) to rounding"""
+    sysm = H.water_box(16)                                       # 12288 atoms, several atoms per grid cell
+    x, q = np.ascontiguousarray(sysm.x), np.ascontiguousarray(sysm.q)
+    outs = []
+    for atomics in ("0", "0", "1"):
+        monkeypatch.setenv("POLB200_PPPM_ATOMICS", atomics)
+        p = pb.PPPM(device=0)
+        p.init(1e-5, q, 10.0, sysm.boxlo, sysm.boxhi)
+        runs = []
+        for _ in range(3):
+            f = np.zeros((sysm.n, 3))
+            e, v = p.compute(x, q, f)
+            runs.append((e, np.array(v), f))
+        p.close()
+        outs.append(runs)
+    for runs in outs[:2]:
+        for e, v, f in runs[1:]:
+            assert e == runs[0][0] and np.array_equal(v, runs[0][1]) and np.array_equal(f, runs[0][2])
+    assert outs[0][0][0] == outs[1][0][0] and np.array_equal(outs[0][0][2], outs[1][0][2])      # a second handle: same bits
+    e0, v0, f0 = outs[0][0]
+    e1, v1, f1 = outs[2][0]
+    assert abs(e0 - e1) < 1e-12 * abs(e1) and np.abs(f0 - f1).max() < 1e-11 * np.abs(f1).max()
