@@ -516,6 +516,14 @@ def mgpu_parity(pb, torch, dist, rank, world, local):
         for k in range(2):  # a rebuild step and a step on stale lists
             r = run.step_host(k)
         parts = dict(own=run.own, mu=run.p["mu"].copy(), ef=run.p["ef"].copy(), f=run.p["f"].copy(), it=r.iterations)
+        if label == "fixed30":
+            # the same decomposed system timed (device-resident inputs): the 32 000-atoms-per-GPU weak-scaling point of round 1
+            m2 = run.reduce(run.measure(20, 5, e2e=False))
+            if rank == 0:
+                detail["config2_weak"] = {"atoms_per_gpu": 4 * NCELL ** 3, "atoms_total": m2.total_atoms, "steps": 20,
+                                          "ms_per_step": m2.wall / 20 * 1e3, "value": m2.total_atoms * 20 / m2.wall,
+                                          "us_per_dipole_iteration": float(m2.sweep[0]) / max(float(m2.sweep[1]), 1.0) * 1e3,
+                                          "barrier_ms_per_step_rank0": (m2.barrier_ms or 0.0) / 20}
         allp = [None] * world if rank == 0 else None
         dist.gather_object(parts, allp, dst=0)
         run.close()
@@ -672,7 +680,7 @@ def gpu_arm(args):
                                              "per_rank": m.per_rank},
             "check": {"eng_pol": m.eng_pol_total, "iterations": m.res.iterations,
                       "mgpu_max_rel_err": mgpu[0] if mgpu else None, "mgpu_detail": mgpu[1] if mgpu else None},
-            "also": also or None,
+            "also": (also or None) if world == 1 else ({"config2_weak": mgpu[1].get("config2_weak")} if mgpu else None),
         }
         print(json.dumps(line))
     if run_alive:
