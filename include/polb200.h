@@ -242,6 +242,11 @@ int polb200_ewald_init(polb200_ewald_t *e, const polb200_ewald_setup *in, polb20
 int polb200_ewald_compute(polb200_ewald_t *e, int nlocal, const double *x, const double *q, double *f, int eflag,
                           int vflag, int on_device, double *energy, double virial[6]);
 double polb200_ewald_last_ms(const polb200_ewald_t *e);  /* CUDA-event time of the last compute */
+/* Multi-GPU (one process per GPU, any partition of the atoms, e.g. the bricks of polb200_comm_init): every rank calls this once
+ * with the same id (polb200_comm_create_id) and then polb200_ewald_init with the GLOBAL qsum / qsqsum / natoms (what
+ * KSpace::qsum_qsq all-reduces) and polb200_ewald_compute with its own atoms.  The structure factors are all-reduced over
+ * NCCL (the reference's MPI_Allreduce, ewald.cpp:395-400); energy and virial come back as per-rank partials that add up. */
+int polb200_ewald_comm_init(polb200_ewald_t *e, int rank, int nranks, const void *id_bytes);
 
 /* ---- KSpace: PPPM (second half) ---------------------------------------------------------
  * Replaces class PPPM of the reference (src/KSPACE/pppm.{h,cpp}, `kspace_style pppm <accuracy>`): ik differentiation, no
@@ -278,6 +283,10 @@ int polb200_pppm_init(polb200_pppm_t *p, const polb200_pppm_setup *in, polb200_p
 int polb200_pppm_compute(polb200_pppm_t *p, int nlocal, const double *x, const double *q, double *f, int eflag, int vflag,
                          int on_device, double *energy, double virial[6]);
 double polb200_pppm_last_ms(const polb200_pppm_t *p);
+/* Multi-GPU, as polb200_ewald_comm_init: every rank assigns the charges of its own atoms to ONE shared grid, the grid is
+ * all-reduced over NCCL (16 B per grid point and step), FFTs and the Poisson solve are replicated, every rank interpolates
+ * the forces of its own atoms.  init takes the GLOBAL qsum / qsqsum / natoms. */
+int polb200_pppm_comm_init(polb200_pppm_t *p, int rank, int nranks, const void *id_bytes);
 
 /* ---- Rigid-body integrator -----------------------------------------------------------
  * Replaces `fix rigid/nve molecule` and `fix rigid/nvt molecule` of the reference's RIGID package, the integrator of

@@ -1386,6 +1386,9 @@ struct polb200_ewald {
   HPinned<double> h_out, h_f;
   int sfac_smem_set = 0, force_smem_set = 0;
   float ms_last = 0.f;
+  // multi-GPU (polb200_ewald_comm_init): every rank holds its own atoms, the structure factors are all-reduced
+  ncclComm_t nccl = nullptr;
+  int rank = 0, nranks = 1;
 };
 
 namespace polb200 {
@@ -2129,6 +2132,7 @@ void polb200_ewald_destroy(polb200_ewald_t *e)
   e->kv.release(); e->S.release(); e->Spart.release(); e->phase.release();
   e->c_x.release(); e->c_q.release(); e->c_f.release(); e->out.release();
   e->h_out.release(); e->h_f.release();
+  if (e->nccl) g_nccl.CommDestroy(e->nccl);
   cudaEventDestroy(e->ev[0]); cudaEventDestroy(e->ev[1]);
   cudaStreamDestroy(e->stream);
   delete e;
@@ -2205,7 +2209,7 @@ int polb200_ewald_compute(polb200_ewald_t *e, int nlocal, const double *x, const
     if (energy) *energy = 0.0;
     if (virial) for (int k = 0; k < 6; k++) virial[k] = 0.0;
     const int n = nlocal, nk = e->nquads;  // the kernels walk quads of four k-vectors
-    if (e->qsqsum == 0.0 || n == 0 || nk == 0) return;  // ewald.cpp:376
+    if (e->qsqsum == 0.0 || nk == 0 || (n == 0 && !e->nccl)) return;  // ewald.cpp:376 (a rank without atoms still joins the sum)
     const double pi = 3.14159265358979323846;
     CUDA_CHECK(cudaEventRecord(e->ev[0], e->stream));
     const double *dx = x, *dq = q;
@@ -2218,6 +2222,8 @@ int polb200_ewald_compute(polb200_ewald_t *e, int nlocal, const double *x, const
       dx = e->c_x.p; dq = e->c_q.p; df = e->c_f.p;
     }
     const int slots = e->slots;
+    if (n == 0) CUDA_CHECK(cudaMemsetAsync(e->S.p, 0, (size_t)4 * nk * sizeof(double2), e->stream));
+    else {
     e->phase.ensure((size_t)3 * n * slots);
     k_ewald_phase<<<cdiv((long)3 * n, 256), 256, 0, e->stream>>>(n, dx, e->unitk[0], e->unitk[1], e->unitk[2], slots, e->phase.p);
     CUDA_CHECK(cudaGetLastError());
@@ -2236,7 +2242,12 @@ int polb200_ewald_compute(polb200_ewald_t *e, int nlocal, const double *x, const
     k_ewald_sum_slices<<<cdiv((long)4 * nk, 256), 256, 0, e->stream>>>(4 * nk, slices, e->Spart.p, e->S.p);
     CUDA_CHECK(cudaGetLastError());
     e->launches++;
+    }
+    // decomposed run: S(k) = sum over the ranks of their atoms' contributions (the reference's MPI_Allreduce of
+    // sfacrl / sfacim, ewald.cpp:395-400)
+    if (e->nccl) NCCL_CHECK(g_nccl.AllReduce(e->S.p, e->S.p, (size_t)8 * nk, ncclDouble, ncclSum, e->nccl, e->stream));
     // forces: one thread per atom with its phase rows in shared memory
+    if (n > 0) {
     int athreads = EW_ATHREADS;
     const int tile_b = EW_KTILE * (int)(sizeof(EwaldK) + 4 * sizeof(double2));
     while (athreads > 32 && athreads * 3 * slots * (int)sizeof(double2) + tile_b > 200 * 1024) athreads -= 32;
@@ -2250,6 +2261,7 @@ int polb200_ewald_compute(polb200_ewald_t *e, int nlocal, const double *x, const
                                                                           e->unitk[1], e->unitk[2], e->qqrd2e, df);
     CUDA_CHECK(cudaGetLastError());
     e->launches += 3;
+    }
     const bool ev = (eflag & 1) || (vflag % 4);
     if (ev) {
       k_ewald_energy<<<1, 256, 0, e->stream>>>(nk, e->kv.p, e->S.p, e->unitk[0], e->unitk[1], e->unitk[2],
@@ -2258,7 +2270,7 @@ int polb200_ewald_compute(polb200_ewald_t *e, int nlocal, const double *x, const
       e->launches++;
       CUDA_CHECK(cudaMemcpyAsync(e->h_out.p, e->out.p, 7 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     }
-    if (!on_device) {
+    if (!on_device && n > 0) {
       e->h_f.ensure((size_t)3 * n);
       CUDA_CHECK(cudaMemcpyAsync(e->h_f.p, e->c_f.p, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     }
@@ -2271,14 +2283,30 @@ int polb200_ewald_compute(polb200_ewald_t *e, int nlocal, const double *x, const
       if ((eflag & 1) && energy) {  // ewald.cpp:455-462
         double en = e->h_out.p[0];
         en -= e->g_ewald * e->qsqsum / sqrt(pi) + 0.5 * pi * e->qsum * e->qsum / (e->g_ewald * e->g_ewald * e->volume);
-        *energy = en * e->qqrd2e;
+        *energy = en * e->qqrd2e / e->nranks;   // every rank holds the global sums: per-rank partials that add up (thermo all-reduces)
       }
       if ((vflag % 4) && virial)
-        for (int k = 0; k < 6; k++) virial[k] = e->h_out.p[1 + k] * e->qqrd2e;  // ewald.cpp:466-474
+        for (int k = 0; k < 6; k++) virial[k] = e->h_out.p[1 + k] * e->qqrd2e / e->nranks;  // ewald.cpp:466-474
     }
   });
 }
 
 double polb200_ewald_last_ms(const polb200_ewald_t *e) { return e ? (double)e->ms_last : 0.0; }
+
+int polb200_ewald_comm_init(polb200_ewald_t *e, int rank, int nranks, const void *id_bytes)
+{
+  if (!e || !id_bytes || nranks < 1 || rank < 0 || rank >= nranks) return POLB200_ERR_ARG;
+  return ewald_guarded(e, [&] {
+    if (e->nccl) throw StyleError{POLB200_ERR_STATE, "polb200_ewald_comm_init was already called"};
+    std::string err;
+    if (!g_nccl.load(err)) throw StyleError{POLB200_ERR_UNSUPPORTED, err};
+    CUDA_CHECK(cudaSetDevice(e->device));
+    ncclUniqueId id;
+    memcpy(&id, id_bytes, sizeof(id));
+    NCCL_CHECK(g_nccl.CommInitRank(&e->nccl, nranks, id, rank));
+    e->rank = rank;
+    e->nranks = nranks;
+  });
+}
 
 }  // extern "C"

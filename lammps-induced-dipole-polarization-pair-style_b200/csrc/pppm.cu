@@ -26,6 +26,7 @@
 #include <string>
 #include <vector>
 
+#include "comm_types.h"
 #include "devbuf.h"
 #include "host_style.h"
 #include "polb200.h"
@@ -65,6 +66,7 @@ struct CufftApi {
   }
 };
 static CufftApi g_cufft;
+static NcclApi g_pppm_nccl;   // multi-GPU (polb200_pppm_comm_init): the charge grid is all-reduced, the rest is replicated
 
 struct PppmConst {
   int order, nx, ny, nz, nlower, nupper;
@@ -409,6 +411,8 @@ struct polb200_pppm {
   DBuf<int> key, key2, idx, idx2, cstart;   // atomics-free charge assignment: atoms sorted by grid cell
   DBuf<double> wts;
   DBuf<char> cub_tmp;
+  ncclComm_t nccl = nullptr;
+  int rank = 0, nranks = 1;
   bool rho_atomics = false;                 // true: the first version (order^3 FP64 atomicAdd per atom; sums not reproducible)
   HPinned<double> h_out, h_f;
   float ms_last = 0.f;
@@ -499,6 +503,7 @@ void polb200_pppm_destroy(polb200_pppm_t *p)
   cudaSetDevice(p->device);
   cudaStreamSynchronize(p->stream);
   if (p->have_plan && g_cufft.Destroy) g_cufft.Destroy(p->plan);
+  if (p->nccl) g_pppm_nccl.CommDestroy(p->nccl);
   p->greensfn.release(); p->partial.release(); p->out.release(); p->c_x.release(); p->c_q.release(); p->c_f.release();
   p->work1.release(); p->wx.release(); p->wy.release(); p->wz.release(); p->h_out.release(); p->h_f.release();
   cudaEventDestroy(p->ev[0]); cudaEventDestroy(p->ev[1]);
@@ -660,7 +665,7 @@ int polb200_pppm_compute(polb200_pppm_t *p, int nlocal, const double *x, const d
     if (energy) *energy = 0.0;
     if (virial) for (int k = 0; k < 6; k++) virial[k] = 0.0;
     const int n = nlocal;
-    if (p->qsqsum == 0.0 || n == 0) return;  // pppm.cpp:650
+    if (p->qsqsum == 0.0 || (n == 0 && !p->nccl)) return;  // pppm.cpp:650 (a rank without atoms still joins the grid sum)
     const PppmConst &C = p->C;
     const size_t total = (size_t)C.nx * C.ny * C.nz;
     CUDA_CHECK(cudaEventRecord(p->ev[0], p->stream));
@@ -674,7 +679,9 @@ int polb200_pppm_compute(polb200_pppm_t *p, int nlocal, const double *x, const d
       dx = p->c_x.p; dq = p->c_q.p; df = p->c_f.p;
     }
     const int ev = ((eflag & 1) || (vflag % 4)) ? 1 : 0;
-    if (p->rho_atomics) {
+    if (n == 0) {
+      CUDA_CHECK(cudaMemsetAsync(p->work1.p, 0, total * sizeof(double2), p->stream));
+    } else if (p->rho_atomics) {
       CUDA_CHECK(cudaMemsetAsync(p->work1.p, 0, total * sizeof(double2), p->stream));
       k_pppm_rho<<<cdiv(n, 128), 128, 0, p->stream>>>(n, C, dx, dq, p->work1.p);
       PPPM_LAUNCHED(p);
@@ -697,6 +704,12 @@ int polb200_pppm_compute(polb200_pppm_t *p, int nlocal, const double *x, const d
       k_pppm_rho_gather<<<cdiv((long)total * 32, 256), 256, 0, p->stream>>>(C, p->cstart.p, p->wts.p, p->work1.p);
       PPPM_LAUNCHED(p);
     }
+    // decomposed run: every rank assigned the charges of its own atoms; the grid is the sum (the reference folds its ghost
+    // cells with GridComm::reverse_comm, pppm.cpp:660-661 -- here the bricks share ONE grid and the FFTs are replicated)
+    if (p->nccl) {
+      const ncclResult_t rc = g_pppm_nccl.AllReduce(p->work1.p, p->work1.p, 2 * total, ncclDouble, ncclSum, p->nccl, p->stream);
+      if (rc != ncclSuccess) throw CudaError{std::string("ncclAllReduce of the PPPM charge grid: ") + g_pppm_nccl.GetErrorString(rc)};
+    }
     // fft1->compute(work1,work1,1): flag 1 = the e^{+ikr} transform, unscaled (fft3d.cpp:103-123) = CUFFT_INVERSE
     CUFFT_CHECK(g_cufft.ExecZ2Z(p->plan, reinterpret_cast<cufftDoubleComplex *>(p->work1.p),
                                 reinterpret_cast<cufftDoubleComplex *>(p->work1.p), CUFFT_INVERSE));
@@ -712,9 +725,11 @@ int polb200_pppm_compute(polb200_pppm_t *p, int nlocal, const double *x, const d
     for (DBuf<double2> *g : {&p->wx, &p->wy, &p->wz})
       CUFFT_CHECK(g_cufft.ExecZ2Z(p->plan, reinterpret_cast<cufftDoubleComplex *>(g->p), reinterpret_cast<cufftDoubleComplex *>(g->p),
                                   CUFFT_FORWARD));
-    k_pppm_force<<<cdiv(n, 128), 128, 0, p->stream>>>(n, C, p->qqrd2e, dx, dq, p->wx.p, p->wy.p, p->wz.p, df);
-    PPPM_LAUNCHED(p);
-    if (!on_device) {
+    if (n > 0) {
+      k_pppm_force<<<cdiv(n, 128), 128, 0, p->stream>>>(n, C, p->qqrd2e, dx, dq, p->wx.p, p->wy.p, p->wz.p, df);
+      PPPM_LAUNCHED(p);
+    }
+    if (!on_device && n > 0) {
       p->h_f.ensure((size_t)3 * n);
       CUDA_CHECK(cudaMemcpyAsync(p->h_f.p, p->c_f.p, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     }
@@ -729,14 +744,31 @@ int polb200_pppm_compute(polb200_pppm_t *p, int nlocal, const double *x, const d
         double en = p->h_out.p[0] * 0.5 * p->volume;
         en -= C.g_ewald * p->qsqsum / 1.77245385090551602729 +
               1.57079632679489661923 * p->qsum * p->qsum / (C.g_ewald * C.g_ewald * p->volume);
-        *energy = en * qscale;
+        *energy = en * qscale / p->nranks;   // every rank holds the global sums: per-rank partials that add up
       }
       if ((vflag % 4) && virial)
-        for (int k = 0; k < 6; k++) virial[k] = 0.5 * qscale * p->volume * p->h_out.p[1 + k];  // pppm.cpp:712-716
+        for (int k = 0; k < 6; k++) virial[k] = 0.5 * qscale * p->volume * p->h_out.p[1 + k] / p->nranks;  // pppm.cpp:712-716
     }
   });
 }
 
 double polb200_pppm_last_ms(const polb200_pppm_t *p) { return p ? (double)p->ms_last : 0.0; }
+
+int polb200_pppm_comm_init(polb200_pppm_t *p, int rank, int nranks, const void *id_bytes)
+{
+  if (!p || !id_bytes || nranks < 1 || rank < 0 || rank >= nranks) return POLB200_ERR_ARG;
+  return pppm_guarded(p, [&] {
+    if (p->nccl) throw StyleError{POLB200_ERR_STATE, "polb200_pppm_comm_init was already called"};
+    std::string err;
+    if (!g_pppm_nccl.load(err)) throw StyleError{POLB200_ERR_UNSUPPORTED, err};
+    CUDA_CHECK(cudaSetDevice(p->device));
+    ncclUniqueId id;
+    memcpy(&id, id_bytes, sizeof(id));
+    const ncclResult_t rc = g_pppm_nccl.CommInitRank(&p->nccl, nranks, id, rank);
+    if (rc != ncclSuccess) throw CudaError{std::string("ncclCommInitRank: ") + g_pppm_nccl.GetErrorString(rc)};
+    p->rank = rank;
+    p->nranks = nranks;
+  });
+}
 
 }  // extern "C"

@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "polb200_launch_count", "polb200_set_option", "polb200_dev_alloc", "polb200_dev_free", "polb200_dev_copy",
     "polb200_dev_zero", "polb200_host_register", "polb200_host_unregister", "polb200_decomp_plan", "polb200_tail", "polb200_set_exclusions",
     "polb200_ewald_create", "polb200_ewald_destroy", "polb200_ewald_last_error", "polb200_ewald_init",
-    "polb200_ewald_compute", "polb200_ewald_last_ms",
+    "polb200_ewald_compute", "polb200_ewald_last_ms", "polb200_ewald_comm_init", "polb200_pppm_comm_init",
     "polb200_pppm_create", "polb200_pppm_destroy", "polb200_pppm_last_error", "polb200_pppm_init", "polb200_pppm_compute",
     "polb200_pppm_last_ms",
     "polb200_rigid_create", "polb200_rigid_destroy", "polb200_rigid_last_error", "polb200_rigid_init",
@@ -511,6 +511,11 @@ class Ewald:
     def last_ms(self):
         return lib().polb200_ewald_last_ms(self._h)
 
+    def comm_init(self, rank, nranks, id_bytes):
+        """multi-GPU: every rank passes its own atoms to compute(); init() takes the GLOBAL charges"""
+        buf = C.create_string_buffer(id_bytes, len(id_bytes))
+        self._check(lib().polb200_ewald_comm_init(self._h, rank, nranks, buf))
+
 
 class PPPM:
     """`kspace_style pppm <accuracy>` on one GPU: the device counterpart of the reference's class PPPM
@@ -572,6 +577,11 @@ class PPPM:
 
     def last_ms(self):
         return lib().polb200_pppm_last_ms(self._h)
+
+    def comm_init(self, rank, nranks, id_bytes):
+        """multi-GPU: every rank passes its own atoms to compute(); init() takes the GLOBAL charges"""
+        buf = C.create_string_buffer(id_bytes, len(id_bytes))
+        self._check(lib().polb200_pppm_comm_init(self._h, rank, nranks, buf))
 
 
 # real units (src/update.cpp:150-170)

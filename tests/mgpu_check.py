@@ -139,6 +139,39 @@ def main():
             failures.append(name)
         ref.close()
         dec.close()
+    # KSpace on the bricks: every rank computes with ITS atoms (structure factors / charge grid all-reduced), forces of the
+    # owned atoms and the summed energy / virial against the single-GPU compute of the whole system
+    lo, hi = None, None
+    probe = make_style(local, sysm, cases[0][1], cut)
+    probe.comm_init(rank, world, fresh_id(), pg)
+    lo, hi = probe.subdomain()
+    probe.close()
+    idx = np.nonzero(owned_mask(sysm.x, lo, hi))[0]
+    for name, cls, acc in (("kspace_ewald", pb.Ewald, 1e-5), ("kspace_pppm", pb.PPPM, 1e-5)):
+        one = cls(device=local)
+        one.init(acc, sysm.q, cut, sysm.boxlo, sysm.boxhi)
+        f0 = np.zeros((sysm.n, 3))
+        e0, v0 = one.compute(c(sysm.x, np.float64), c(sysm.q, np.float64), f0)
+        one.close()
+        dec = cls(device=local)
+        dec.comm_init(rank, world, fresh_id())
+        dec.init(acc, sysm.q, cut, sysm.boxlo, sysm.boxhi)          # global charges: qsum, qsqsum, natoms of the whole system
+        f1 = np.zeros((len(idx), 3))
+        e1, v1 = dec.compute(c(sysm.x[idx], np.float64), c(sysm.q[idx], np.float64), f1)
+        dec.close()
+        ev = torch.tensor([e1] + list(v1), dtype=torch.float64, device="cuda")
+        dist.all_reduce(ev)
+        ev = ev.cpu().numpy()
+        errs = dict(f=float(np.abs(f1 - f0[idx]).max() / np.abs(f0).max()), e=abs(ev[0] - e0) / abs(e0),
+                    v=float(np.abs(ev[1:] - v0).max() / np.abs(v0).max()))
+        good = all(v < 1e-11 for v in errs.values())
+        flag = torch.tensor([0 if good else 1], device="cuda")
+        dist.all_reduce(flag)
+        if rank == 0:
+            print(f"[mgpu {world} ranks] {name}: {'OK' if int(flag) == 0 else 'FAIL'} | " + " ".join(f"{k}={v:.1e}" for k, v in errs.items()), flush=True)
+        if int(flag):
+            failures.append(name)
+
     # a brick that fails alone must take the others with it (same error on every rank, no hang): rank 0 is handed no
     # atoms at a rebuild step
     dec = make_style(local, sysm, cases[0][1], cut)
