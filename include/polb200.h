@@ -361,6 +361,15 @@ int polb200_rigid_scalar(polb200_rigid_t *r, double *scalar, double *ke_translat
  * eta_t, eta_r, eta_dot_t, eta_dot_r, interleaved in that order (4 * t_chain doubles).  set before polb200_rigid_setup. */
 int polb200_rigid_get_chain(polb200_rigid_t *r, double *state, int capacity, int *t_chain);
 int polb200_rigid_set_chain(polb200_rigid_t *r, const double *state, int t_chain);
+/* More than one process (one per GPU), the reference's scheme for `fix rigid` (fix_rigid.cpp:782-855, :1181-1262,
+ * :1605-2211): every process holds EVERY body, each atom is owned by exactly one process, and the per-body force and
+ * torque sums are all-reduced (one ncclAllReduce of 6 * nbody doubles in setup / final_integrate, where the reference has
+ * MPI_Allreduce(sum, all, 6*nbody)).  Call once BEFORE polb200_rigid_init with the bytes of polb200_comm_create_id();
+ * afterwards `nlocal` of every call is this process's own atoms (0 is allowed), init gathers the atoms of all
+ * processes and builds bit-identical bodies everywhere, dof all-reduces its member counts, the body state (scalar,
+ * chain, fetch) is the same on every process, and polb200_rigid_virial returns this process's share (sum it over the
+ * processes like any per-process virial, fix_rigid.cpp:1112-1129). */
+int polb200_rigid_comm_init(polb200_rigid_t *r, int rank, int nranks, const void *nccl_unique_id);
 /* FixRigid::reset_dt (fix_rigid.cpp:2553-2558) */
 int polb200_rigid_reset_dt(polb200_rigid_t *r, double dt);
 /* body arrays for tests / compute_array: "xcm" "vcm" "fcm" "torque" "angmom" "omega" "ex" "ey" "ez" "inertia" [nbody][3],

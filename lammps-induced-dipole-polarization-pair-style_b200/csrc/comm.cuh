@@ -237,11 +237,11 @@ static void comm_build_ghosts(polb200_handle *h, int n)
     int err = COMM_OK;
     for (int k = 0; k < 3; k++) {
       const double len = c.plan.subhi[k] - c.plan.sublo[k];
-      if ((h->box.periodic[k] || c.pg[k] > 1) && st.cutneighmax > len) err = COMM_ERR_SUBDOMAIN;
+      if ((h->box.periodic[k] || c.pg[k] > 1) && st.cutneighmax + h->atom_slack > len) err = COMM_ERR_SUBDOMAIN;
     }
     comm_throw(comm_agree(h, err));
   }
-  c.geom.cut = st.cutneighmax;
+  c.geom.cut = st.cutneighmax + h->atom_slack;
 
   // 1. send lists
   h->cnt.ensure(n + 1);

@@ -81,6 +81,9 @@ struct polb200_handle {
   int gpf_minb = 4;              // resident CTAs per SM asked of the grouped force kernel (4: 128 registers, no spills; measured faster than 5)
   bool use_group_pairs = true;   // LJ + Coulomb + field and polarization forces on the pair-group rows when they qualify
   bool gs_blocked = true;        // exact-mode Gauss-Seidel as blocked forward substitution (false: one atom at a time)
+  // Owned atoms may lie up to this far OUTSIDE the box / the brick they are handed to (a caller that keeps rigid bodies
+  // whole assigns a molecule to the brick of one of its atoms): the ghost shells are made that much deeper.
+  double atom_slack = 0.0;
   bool use_graphs = true;        // ... its per-block launches replayed from a CUDA graph
   long params_version = 0;       // bumped whenever the kernel parameters (DevParams) change
   struct SweepGraph {
@@ -266,10 +269,10 @@ static void setup_grid(polb200_handle *h)
   double cs[3];
   long ncell = 1;
   for (int d = 0; d < 3; d++) {
-    const double ext = h->box.periodic[d] ? cut : 0.0;
+    const double ext = h->box.periodic[d] ? cut + h->atom_slack : 0.0;
     const double lo = h->box.lo[d] - ext, hi = h->box.hi[d] + ext;
     // margin: owned atoms may sit up to skin/2 outside the box between rebuilds
-    const double margin = 0.5 * st.env.skin + 1e-9 * (hi - lo);
+    const double margin = 0.5 * st.env.skin + h->atom_slack + 1e-9 * (hi - lo);
     g.lo[d] = lo - margin;
     const double len = (hi + margin) - g.lo[d];
     int nc = (int)(len / binsize);
@@ -409,7 +412,7 @@ static void rebuild(polb200_handle *h, const polb200_atoms *at)
     ng = h->nghost;
   } else {
     h->cnt.ensure(n + 1); h->rowstart.ensure(n + 2);
-    LAUNCH(h, k_ghost_count, cdiv(n, 256), 256, n, h->xq.p, h->box, st.cutneighmax, h->cnt.p);
+    LAUNCH(h, k_ghost_count, cdiv(n, 256), 256, n, h->xq.p, h->box, st.cutneighmax + h->atom_slack, h->cnt.p);
     CUDA_CHECK(cudaMemsetAsync(h->cnt.p + n, 0, sizeof(unsigned long long), h->stream));
     exclusive_sum(h, n + 1, h->cnt.p, h->rowstart.p);
     unsigned long long ng64 = 0;
@@ -428,7 +431,7 @@ static void rebuild(polb200_handle *h, const polb200_atoms *at)
       h->g_owner_u.ensure(ng); h->g_shift_u.ensure(ng); h->g_owner.ensure(ng); h->g_shift.ensure(ng);
       h->keys.ensure(std::max(n, ng)); h->keys2.ensure(std::max(n, ng));
       h->vals.ensure(std::max(n, ng)); h->vals2.ensure(std::max(n, ng));
-      LAUNCH(h, k_ghost_fill, cdiv(n, 256), 256, n, h->xq.p, h->box, st.cutneighmax, g, h->rowstart.p,
+      LAUNCH(h, k_ghost_fill, cdiv(n, 256), 256, n, h->xq.p, h->box, st.cutneighmax + h->atom_slack, g, h->rowstart.p,
              h->g_owner_u.p, h->g_shift_u.p, h->keys.p, h->vals.p);
       sort_pairs(h, ng, h->keys.p, h->keys2.p, h->vals.p, h->vals2.p, bits_for(g.ncell + 1) + g.xbits);
     }
@@ -874,7 +877,7 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
                      "minimum-image interaction set does not decompose into bricks"};
   for (int d = 0; d < 3; d++) {
     if (!h->box.periodic[d]) continue;
-    if (st.cutneighmax > h->box.prd[d])
+    if (st.cutneighmax + h->atom_slack > h->box.prd[d])
       throw StyleError{POLB200_ERR_UNSUPPORTED, "neighbor cutoff exceeds the periodic box length"};
     if (list_mode && (st.polar_cutoff > h->box.half[d] || st.cut_coul > h->box.half[d]))
       throw StyleError{POLB200_ERR_UNSUPPORTED,
@@ -1781,6 +1784,12 @@ int polb200_set_option(polb200_t *h, const char *name, double value)
   }
   if (!strcmp(name, "gs_cache_max")) {
     h->gs_cache_max = (int)value;
+    return POLB200_OK;
+  }
+  if (!strcmp(name, "atom_slack")) {
+    if (!(value >= 0.0 && value <= 16.0)) return POLB200_ERR_ARG;
+    h->atom_slack = value;
+    h->have_lists = false;
     return POLB200_OK;
   }
   if (!strcmp(name, "use_graphs")) {

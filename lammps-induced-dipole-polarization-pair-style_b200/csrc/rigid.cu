@@ -25,6 +25,7 @@
 #include <string>
 #include <vector>
 
+#include "comm_types.h"
 #include "devbuf.h"
 #include "host_style.h"
 #include "polb200.h"
@@ -147,21 +148,28 @@ enum { MODE_SETUP = 0, MODE_FINAL = 1 };
 //   MODE_FINAL: second half kick of vcm and conjqm, angmom, omega   (fix_rigid_nh.cpp:706-764)
 // LANES = 1: a thread per body (molecules of a few atoms); LANES = 32: a warp per body, members strided over the
 // lanes and combined by an xor butterfly -- the same order on every run.
-template <int LANES, int MODE>
+// STAGE = 0: sum and update in one launch (every member is on this process).
+// More than one process (polb200_rigid_comm_init; the reference's MPI_Allreduce of sum[nbody][6], fix_rigid.cpp:826-827,
+// fix_rigid_nh.cpp:668-669): STAGE = 1 writes this process's partial sums over the members it owns to `sum6` and stops;
+// after the all-reduce STAGE = 2 (LANES = 1) reads the complete sums and updates the replicated body.
+template <int LANES, int MODE, int STAGE = 0>
 __global__ void __launch_bounds__(256) k_rigid_bodies(int nbody, RigidConst rc, const Chain *__restrict__ chain,
                                                      const int *__restrict__ member_first, const int *__restrict__ member_tag,
                                                      const int *__restrict__ idx_of_tag, const int *__restrict__ xcmimage,
                                                      const double *__restrict__ x, const double *__restrict__ f,
                                                      BodyFrame *__restrict__ frame, BodyDyn *__restrict__ dyn,
-                                                     double2 *__restrict__ akin)
+                                                     double2 *__restrict__ akin, double *__restrict__ sum6)
 {
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = gid / LANES, lane = gid % LANES;
   if (b >= nbody) return;
   BodyFrame F = frame[b];
   double s[6] = {0, 0, 0, 0, 0, 0};
-  for (int m = member_first[b] + lane; m < member_first[b + 1]; m += LANES) {
+  if (STAGE == 2)
+    for (int k = 0; k < 6; k++) s[k] = sum6[(size_t)6 * b + k];
+  for (int m = member_first[b] + lane; STAGE != 2 && m < member_first[b + 1]; m += LANES) {
     const int t = member_tag[m], i = idx_of_tag[t];
+    if (STAGE == 1 && i < 0) continue;  // owned by another process
     int xb, yb, zb;
     unpack_image(xcmimage[t], xb, yb, zb);
     const double fx = f[3 * i], fy = f[3 * i + 1], fz = f[3 * i + 2];
@@ -178,6 +186,10 @@ __global__ void __launch_bounds__(256) k_rigid_bodies(int nbody, RigidConst rc, 
     for (int off = LANES / 2; off > 0; off >>= 1)
       for (int k = 0; k < 6; k++) s[k] += __shfl_xor_sync(0xffffffffu, s[k], off);
     if (lane != 0) return;
+  }
+  if (STAGE == 1) {
+    for (int k = 0; k < 6; k++) sum6[(size_t)6 * b + k] = s[k];
+    return;
   }
   BodyDyn D = dyn[b];
   for (int k = 0; k < 3; k++) { D.fcm[k] = s[k]; D.torque[k] = s[3 + k]; }
@@ -568,8 +580,13 @@ struct polb200_rigid {
   DBuf<int> abody, xcmimage, member_first, member_tag, idx_of_tag, imagebody, c_tag, c_image;
   DBuf<AtomRec> arec;
   DBuf<double2> akin;
-  DBuf<double> vpart, virial, c_x, c_v, c_f, sums;
+  DBuf<double> vpart, virial, c_x, c_v, c_f, sums, sum6;
+  // more than one process (polb200_rigid_comm_init): bodies replicated, atoms owned by exactly one process
+  ncclComm_t nccl = nullptr;
+  int rank = 0, nranks = 1;
 };
+
+static NcclApi g_rigid_nccl;
 
 namespace polb200 {
 
@@ -661,22 +678,47 @@ static void stage_out(polb200_rigid *r, const polb200_rigid_atoms *a, bool x_wri
 
 static void check_atom_count(polb200_rigid *r, int n)
 {
-  if (n < r->natoms_body)
+  if (!r->nccl && n < r->natoms_body)
     throw StyleError{POLB200_ERR_ARG, "polb200_rigid: fewer atoms than the rigid bodies hold (atoms of a body must stay on this process)"};
 }
 
 template <int MODE>
 static void launch_bodies(polb200_rigid *r, const StepArrays &s, int n)
 {
+  if (r->nccl) {
+    // partial sums over the members this process owns -> all-reduce -> every process updates every body identically
+    CUDA_CHECK(cudaMemsetAsync(r->idx_of_tag.p, 0xff, (size_t)r->maxtag * sizeof(int), r->stream));
+    if (n > 0) {
+      k_rigid_index<<<cdiv(n, 256), 256, 0, r->stream>>>(n, s.tag, r->idx_of_tag.p);
+      RIGID_LAUNCHED(r);
+    }
+    r->sum6.ensure((size_t)6 * r->nbody);
+    if (r->maxmembers <= 16)
+      k_rigid_bodies<1, MODE, 1><<<cdiv(r->nbody, 256), 256, 0, r->stream>>>(r->nbody, r->rc, r->chain.p, r->member_first.p, r->member_tag.p,
+                                                                            r->idx_of_tag.p, r->xcmimage.p, s.x, s.f, r->frame.p, r->dyn.p,
+                                                                            r->akin.p, r->sum6.p);
+    else
+      k_rigid_bodies<32, MODE, 1><<<cdiv((long)r->nbody * 32, 256), 256, 0, r->stream>>>(r->nbody, r->rc, r->chain.p, r->member_first.p,
+                                                                                       r->member_tag.p, r->idx_of_tag.p, r->xcmimage.p, s.x,
+                                                                                       s.f, r->frame.p, r->dyn.p, r->akin.p, r->sum6.p);
+    RIGID_LAUNCHED(r);
+    const ncclResult_t rc = g_rigid_nccl.AllReduce(r->sum6.p, r->sum6.p, (size_t)6 * r->nbody, ncclDouble, ncclSum, r->nccl, r->stream);
+    if (rc != ncclSuccess) throw CudaError{std::string("ncclAllReduce of the body forces and torques: ") + g_rigid_nccl.GetErrorString(rc)};
+    k_rigid_bodies<1, MODE, 2><<<cdiv(r->nbody, 256), 256, 0, r->stream>>>(r->nbody, r->rc, r->chain.p, r->member_first.p, r->member_tag.p,
+                                                                          r->idx_of_tag.p, r->xcmimage.p, s.x, s.f, r->frame.p, r->dyn.p,
+                                                                          r->akin.p, r->sum6.p);
+    RIGID_LAUNCHED(r);
+    return;
+  }
   k_rigid_index<<<cdiv(n, 256), 256, 0, r->stream>>>(n, s.tag, r->idx_of_tag.p);
   RIGID_LAUNCHED(r);
   if (r->maxmembers <= 16)
     k_rigid_bodies<1, MODE><<<cdiv(r->nbody, 256), 256, 0, r->stream>>>(r->nbody, r->rc, r->chain.p, r->member_first.p, r->member_tag.p,
-                                                                       r->idx_of_tag.p, r->xcmimage.p, s.x, s.f, r->frame.p, r->dyn.p, r->akin.p);
+                                                                       r->idx_of_tag.p, r->xcmimage.p, s.x, s.f, r->frame.p, r->dyn.p, r->akin.p, nullptr);
   else
     k_rigid_bodies<32, MODE><<<cdiv((long)r->nbody * 32, 256), 256, 0, r->stream>>>(r->nbody, r->rc, r->chain.p, r->member_first.p,
                                                                                   r->member_tag.p, r->idx_of_tag.p, r->xcmimage.p, s.x, s.f,
-                                                                                  r->frame.p, r->dyn.p, r->akin.p);
+                                                                                  r->frame.p, r->dyn.p, r->akin.p, nullptr);
   RIGID_LAUNCHED(r);
 }
 
@@ -684,6 +726,14 @@ template <int XV>
 static void launch_atoms(polb200_rigid *r, const StepArrays &s, int n, double keep, double scale)
 {
   const int nb = cdiv(n, 256);
+  if (n == 0) {  // a process that owns no atom (more than one process): only the virial bookkeeping
+    if (r->evflag) {
+      r->vpart.ensure(6);
+      k_rigid_virial_sum<<<1, 192, 0, r->stream>>>(0, r->vpart.p, keep, scale, r->virial.p);
+      RIGID_LAUNCHED(r);
+    }
+    return;
+  }
   if (r->evflag) {
     r->vpart.ensure((size_t)6 * nb);
     k_rigid_atoms<XV, 1><<<nb, 256, 0, r->stream>>>(n, r->rc, s.tag, r->abody.p, r->arec.p, r->xcmimage.p, r->frame.p, s.x, s.v, s.f, r->vpart.p);
@@ -728,7 +778,8 @@ void polb200_rigid_destroy(polb200_rigid_t *r)
   r->frame.release(); r->dyn.release(); r->chain.release(); r->abody.release(); r->xcmimage.release();
   r->member_first.release(); r->member_tag.release(); r->idx_of_tag.release(); r->imagebody.release();
   r->c_tag.release(); r->c_image.release(); r->arec.release(); r->akin.release(); r->vpart.release();
-  r->virial.release(); r->c_x.release(); r->c_v.release(); r->c_f.release(); r->sums.release();
+  r->virial.release(); r->c_x.release(); r->c_v.release(); r->c_f.release(); r->sums.release(); r->sum6.release();
+  if (r->nccl) g_rigid_nccl.CommDestroy(r->nccl);
   cudaEventDestroy(r->ev[0]); cudaEventDestroy(r->ev[1]);
   cudaStreamDestroy(r->stream);
   delete r;
@@ -736,9 +787,78 @@ void polb200_rigid_destroy(polb200_rigid_t *r)
 
 const char *polb200_rigid_last_error(const polb200_rigid_t *r) { return r ? r->err.c_str() : "null handle"; }
 
+// one atom as it travels at init when the bodies are built on more than one process
+struct InitRec {
+  double mass, x[3], v[3];
+  int tag, molecule, ingroup, image;
+};
+
+static int rigid_init_impl(polb200_rigid_t *r, const polb200_rigid_params *p, int nlocal, const int *tag, const int *molecule,
+                           const int *ingroup, const double *mass, const int *image, const double *x, const double *v,
+                           polb200_rigid_info *info);
+
 int polb200_rigid_init(polb200_rigid_t *r, const polb200_rigid_params *p, int nlocal, const int *tag, const int *molecule,
                        const int *ingroup, const double *mass, const int *image, const double *x, const double *v,
                        polb200_rigid_info *info)
+{
+  if (!r || !p) return POLB200_ERR_ARG;
+  if (!r->nccl) return rigid_init_impl(r, p, nlocal, tag, molecule, ingroup, mass, image, x, v, info);
+  // More than one process: the reference builds its bodies from per-process partial sums that it all-reduces
+  // (fix_rigid.cpp:1605-2211, six MPI_Allreduce).  Here every process gathers the atom records of all processes once
+  // and runs the single-process construction on them: its sums run in atom-id order, so every process ends up with
+  // bit-identical bodies whatever the decomposition.
+  std::vector<InitRec> all;
+  int ntotal = 0;
+  const int rc = rigid_guarded(r, [&] {
+    const int n = nlocal;
+    if (n < 0 || (n > 0 && (!tag || !molecule || !mass || !image || !x || !v))) throw StyleError{POLB200_ERR_ARG, "Illegal fix rigid command"};
+    CUDA_CHECK(cudaSetDevice(r->device));
+    DBuf<int> counts;
+    counts.ensure((size_t)r->nranks + 1);
+    CUDA_CHECK(cudaMemcpyAsync(counts.p + r->nranks, &n, sizeof(int), cudaMemcpyHostToDevice, r->stream));
+    ncclResult_t nr = g_rigid_nccl.AllGather(counts.p + r->nranks, counts.p, 1, ncclInt, r->nccl, r->stream);
+    if (nr != ncclSuccess) throw CudaError{std::string("ncclAllGather (rigid init): ") + g_rigid_nccl.GetErrorString(nr)};
+    std::vector<int> hc(r->nranks);
+    CUDA_CHECK(cudaMemcpyAsync(hc.data(), counts.p, (size_t)r->nranks * sizeof(int), cudaMemcpyDeviceToHost, r->stream));
+    CUDA_CHECK(cudaStreamSynchronize(r->stream));
+    counts.release();
+    const size_t nmax = (size_t)std::max(1, *std::max_element(hc.begin(), hc.end()));
+    std::vector<InitRec> mine(nmax);
+    memset(mine.data(), 0, nmax * sizeof(InitRec));
+    for (int i = 0; i < n; i++) {
+      InitRec &a = mine[i];
+      a.mass = mass[i];
+      for (int k = 0; k < 3; k++) { a.x[k] = x[3 * i + k]; a.v[k] = v[3 * i + k]; }
+      a.tag = tag[i]; a.molecule = molecule[i]; a.ingroup = ingroup ? ingroup[i] : 1; a.image = image[i];
+    }
+    DBuf<InitRec> send, recv;
+    send.ensure(nmax);
+    recv.ensure(nmax * r->nranks);
+    CUDA_CHECK(cudaMemcpyAsync(send.p, mine.data(), nmax * sizeof(InitRec), cudaMemcpyHostToDevice, r->stream));
+    nr = g_rigid_nccl.AllGather(send.p, recv.p, nmax * sizeof(InitRec), ncclChar, r->nccl, r->stream);
+    if (nr != ncclSuccess) throw CudaError{std::string("ncclAllGather (rigid init): ") + g_rigid_nccl.GetErrorString(nr)};
+    std::vector<InitRec> padded(nmax * r->nranks);
+    CUDA_CHECK(cudaMemcpyAsync(padded.data(), recv.p, padded.size() * sizeof(InitRec), cudaMemcpyDeviceToHost, r->stream));
+    CUDA_CHECK(cudaStreamSynchronize(r->stream));
+    send.release();
+    recv.release();
+    for (int k = 0; k < r->nranks; k++) all.insert(all.end(), padded.begin() + k * nmax, padded.begin() + k * nmax + hc[k]);
+    ntotal = (int)all.size();
+  });
+  if (rc != POLB200_OK) return rc;
+  std::vector<int> g_tag(ntotal), g_mol(ntotal), g_in(ntotal), g_img(ntotal);
+  std::vector<double> g_mass(ntotal), g_x((size_t)3 * ntotal), g_v((size_t)3 * ntotal);
+  for (int i = 0; i < ntotal; i++) {
+    const InitRec &a = all[i];
+    g_tag[i] = a.tag; g_mol[i] = a.molecule; g_in[i] = a.ingroup; g_img[i] = a.image; g_mass[i] = a.mass;
+    for (int k = 0; k < 3; k++) { g_x[3 * i + k] = a.x[k]; g_v[3 * i + k] = a.v[k]; }
+  }
+  return rigid_init_impl(r, p, ntotal, g_tag.data(), g_mol.data(), g_in.data(), g_mass.data(), g_img.data(), g_x.data(), g_v.data(), info);
+}
+
+static int rigid_init_impl(polb200_rigid_t *r, const polb200_rigid_params *p, int nlocal, const int *tag, const int *molecule,
+                           const int *ingroup, const double *mass, const int *image, const double *x, const double *v,
+                           polb200_rigid_info *info)
 {
   if (!r || !p) return POLB200_ERR_ARG;
   return rigid_guarded(r, [&] {
@@ -1002,6 +1122,17 @@ int polb200_rigid_dof(polb200_rigid_t *r, int nlocal, const int *tag, const int 
       const int b = r->h_abody[t];
       if (b >= 0 && (!tgroup || tgroup[i])) nall[b]++;
     }
+    if (r->nccl) {  // MPI_Allreduce(ncount, nall) of FixRigid::dof (fix_rigid.cpp:1221)
+      CUDA_CHECK(cudaSetDevice(r->device));
+      DBuf<int> d;
+      d.ensure(r->nbody);
+      CUDA_CHECK(cudaMemcpyAsync(d.p, nall.data(), (size_t)r->nbody * sizeof(int), cudaMemcpyHostToDevice, r->stream));
+      const ncclResult_t nr = g_rigid_nccl.AllReduce(d.p, d.p, r->nbody, ncclInt, ncclSum, r->nccl, r->stream);
+      if (nr != ncclSuccess) throw CudaError{std::string("ncclAllReduce (rigid dof): ") + g_rigid_nccl.GetErrorString(nr)};
+      CUDA_CHECK(cudaMemcpyAsync(nall.data(), d.p, (size_t)r->nbody * sizeof(int), cudaMemcpyDeviceToHost, r->stream));
+      CUDA_CHECK(cudaStreamSynchronize(r->stream));
+      d.release();
+    }
     int n = 0, nlinear = 0;
     for (int b = 0; b < r->nbody; b++)
       if (nall[b] == r->h_nrigid[b]) {
@@ -1076,7 +1207,7 @@ int polb200_rigid_final_integrate(polb200_rigid_t *r, const polb200_rigid_atoms 
 
 int polb200_rigid_pre_neighbor(polb200_rigid_t *r, int nlocal, const int *tag, const int *image, int on_device)
 {
-  if (!r || !tag || !image) return POLB200_ERR_ARG;
+  if (!r || nlocal < 0 || (nlocal > 0 && (!tag || !image))) return POLB200_ERR_ARG;
   return rigid_guarded(r, [&] {
     if (!r->ready) throw StyleError{POLB200_ERR_STATE, "polb200_rigid_init has not been called"};
     CUDA_CHECK(cudaSetDevice(r->device));
@@ -1090,8 +1221,10 @@ int polb200_rigid_pre_neighbor(polb200_rigid_t *r, int nlocal, const int *tag, c
     }
     k_rigid_remap<<<cdiv(r->nbody, 256), 256, 0, r->stream>>>(r->nbody, r->rc, r->frame.p, r->imagebody.p);
     RIGID_LAUNCHED(r);
-    k_rigid_image_shift<<<cdiv(n, 256), 256, 0, r->stream>>>(n, dt, di, r->abody.p, r->imagebody.p, r->xcmimage.p);
-    RIGID_LAUNCHED(r);
+    if (n > 0) {
+      k_rigid_image_shift<<<cdiv(n, 256), 256, 0, r->stream>>>(n, dt, di, r->abody.p, r->imagebody.p, r->xcmimage.p);
+      RIGID_LAUNCHED(r);
+    }
     CUDA_CHECK(cudaStreamSynchronize(r->stream));
   });
 }
@@ -1182,6 +1315,24 @@ int polb200_rigid_set_chain(polb200_rigid_t *r, const double *state, int t_chain
     }
     CUDA_CHECK(cudaMemcpyAsync(r->chain.p, &c, sizeof(Chain), cudaMemcpyHostToDevice, r->stream));
     CUDA_CHECK(cudaStreamSynchronize(r->stream));
+  });
+}
+
+int polb200_rigid_comm_init(polb200_rigid_t *r, int rank, int nranks, const void *id_bytes)
+{
+  if (!r || !id_bytes || nranks < 1 || rank < 0 || rank >= nranks) return POLB200_ERR_ARG;
+  return rigid_guarded(r, [&] {
+    if (r->nccl) throw StyleError{POLB200_ERR_STATE, "polb200_rigid_comm_init was already called"};
+    if (r->ready) throw StyleError{POLB200_ERR_STATE, "polb200_rigid_comm_init must precede polb200_rigid_init"};
+    std::string err;
+    if (!g_rigid_nccl.load(err)) throw StyleError{POLB200_ERR_UNSUPPORTED, err};
+    CUDA_CHECK(cudaSetDevice(r->device));
+    ncclUniqueId id;
+    memcpy(&id, id_bytes, sizeof(id));
+    const ncclResult_t rc = g_rigid_nccl.CommInitRank(&r->nccl, nranks, id, rank);
+    if (rc != ncclSuccess) throw CudaError{std::string("ncclCommInitRank: ") + g_rigid_nccl.GetErrorString(rc)};
+    r->rank = rank;
+    r->nranks = nranks;
   });
 }
 

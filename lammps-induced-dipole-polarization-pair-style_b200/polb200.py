@@ -34,7 +34,7 @@ ABI_SYMBOLS = [
     "polb200_rigid_create", "polb200_rigid_destroy", "polb200_rigid_last_error", "polb200_rigid_init",
     "polb200_rigid_dof", "polb200_rigid_setup", "polb200_rigid_initial_integrate", "polb200_rigid_final_integrate",
     "polb200_rigid_pre_neighbor", "polb200_rigid_virial", "polb200_rigid_scalar", "polb200_rigid_reset_dt",
-    "polb200_rigid_get_chain", "polb200_rigid_set_chain",
+    "polb200_rigid_get_chain", "polb200_rigid_set_chain", "polb200_rigid_comm_init",
     "polb200_rigid_fetch", "polb200_rigid_launch_count", "polb200_rigid_last_ms",
 ]
 
@@ -155,6 +155,16 @@ def lib():
         L.polb200_restart_size.argtypes = [C.c_void_p, C.POINTER(C.c_long)]
         L.polb200_write_restart.argtypes = [C.c_void_p, C.c_void_p, C.c_long]
         L.polb200_read_restart.argtypes = [C.c_void_p, C.c_void_p, C.c_long]
+        L.polb200_restart_settings_size.argtypes = [C.c_void_p, C.POINTER(C.c_long)]
+        L.polb200_read_restart_settings.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.POINTER(C.c_long)]
+        L.polb200_dev_alloc.argtypes = [C.c_int, C.c_size_t]
+        L.polb200_dev_alloc.restype = C.c_void_p
+        L.polb200_dev_free.argtypes = [C.c_int, C.c_void_p]
+        L.polb200_dev_copy.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+        L.polb200_dev_zero.argtypes = [C.c_int, C.c_void_p, C.c_size_t]
+        L.polb200_ewald_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.polb200_pppm_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.polb200_rigid_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.polb200_set_box.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
         L.polb200_compute.argtypes = [C.c_void_p, C.POINTER(Atoms), C.c_int, C.c_int, C.c_int, C.POINTER(Result)]
         L.polb200_debug_fetch.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_long]
@@ -648,6 +658,11 @@ class Rigid:
                                              *[None if a is None else a.ctypes.data for a in arrs], C.byref(info)))
         self.info = info
         return info
+
+    def comm_init(self, rank, nranks, id_bytes):
+        """more than one process (before init): bodies replicated, every call takes this process's own atoms"""
+        buf = C.create_string_buffer(id_bytes, len(id_bytes))
+        self._check(lib().polb200_rigid_comm_init(self._h, rank, nranks, buf))
 
     def dof(self, tag, tgroup=None):
         tag = np.ascontiguousarray(tag, dtype=np.int32)
