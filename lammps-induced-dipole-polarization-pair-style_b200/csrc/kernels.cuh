@@ -1716,22 +1716,41 @@ k_group_cache(int ngroups, DevParams P, const int *__restrict__ group_first, con
     mola = tm[a].y; molb = tm[b].y;
   }
   int n = 0;
+  // CHUNKED: the radial scalars are not evaluated by the lane that finds a partner (63 % of the skin candidates are inside
+  // the cutoff and a quarter of those for one member only, so that code ran with ~55 % of its lanes) but queued per warp
+  // as (destination, r^2) items and evaluated 32 at a time with every lane busy
+  __shared__ unsigned q_dst[CHUNKED ? WARPS_PER_BLOCK : 1][96];
+  __shared__ double q_r2[CHUNKED ? WARPS_PER_BLOCK : 1][96];
+  const int wq = CHUNKED ? (threadIdx.x >> 5) : 0;
+  int qn = 0;
+  auto drain = [&](int item) {   // item: queue slot of this lane
+    const unsigned d = q_dst[wq][item];
+    double s1, s2;
+    radial_scalars<DAMP>(P.pc, q_r2[wq][item], s1, s2);
+    const unsigned pos = d >> 1;
+    unsigned char *rec = crec + (cstart[g] + (unsigned long long)(pos / GCHUNK)) * GCHUNK_BYTES + ((d & 1u) ? GCHUNK * 16 : 0);
+    reinterpret_cast<double2 *>(rec)[pos % GCHUNK] = make_double2(s1, s2);
+  };
   for (unsigned long long k0 = beg; k0 < end; k0 += 32) {
     const unsigned long long k = k0 + lane;
-    bool ok = false;
+    bool ok = false, ina = false, inb = false;
     int j = 0;
+    double ra = 0.0, rb = 0.0;
     double4 sc = make_double4(0, 0, 0, 0);
     if (k < end) {
       j = neigh[k];
       const double4 xj = ld4(xq + j);
       double dx = xa.x - xj.x, dy = xa.y - xj.y, dz = xa.z - xj.z;
-      const double ra = dx * dx + dy * dy + dz * dz;
+      ra = dx * dx + dy * dy + dz * dz;
       dx = xb.x - xj.x, dy = xb.y - xj.y, dz = xb.z - xj.z;
-      const double rb = dx * dx + dy * dy + dz * dz;
-      const bool ina = j != a && ra < cutsq, inb = two && j != b && rb < cutsq;
+      rb = dx * dx + dy * dy + dz * dz;
+      ina = j != a && ra < cutsq;
+      inb = two && j != b && rb < cutsq;
       ok = ina || inb;
-      if (ina) radial_scalars<DAMP>(P.pc, ra, sc.x, sc.y);
-      if (inb) radial_scalars<DAMP>(P.pc, rb, sc.z, sc.w);
+      if (!CHUNKED) {
+        if (ina) radial_scalars<DAMP>(P.pc, ra, sc.x, sc.y);
+        if (inb) radial_scalars<DAMP>(P.pc, rb, sc.z, sc.w);
+      }
       if (RMIN && ((ina && ra < guard) || (inb && rb < guard))) {
         const double aj = mua[j].w;
         const int molj = tm[j].y;
@@ -1749,20 +1768,41 @@ k_group_cache(int ngroups, DevParams P, const int *__restrict__ group_first, con
       }
     }
     const unsigned m = __ballot_sync(FULL, ok);
-    if (ok) {
-      const int pos = n + __popc(m & ((1u << lane) - 1));
-      if (CHUNKED) {
+    const unsigned below = (1u << lane) - 1;
+    const int pos = n + __popc(m & below);
+    if (CHUNKED) {
+      if (ok) {
         unsigned char *rec = crec + (cstart[g] + (unsigned long long)(pos / GCHUNK)) * GCHUNK_BYTES;
-        reinterpret_cast<double2 *>(rec)[pos % GCHUNK] = make_double2(sc.x, sc.y);                 // member a
-        reinterpret_cast<double2 *>(rec + GCHUNK * 16)[pos % GCHUNK] = make_double2(sc.z, sc.w);   // member b
         reinterpret_cast<int *>(rec + GCHUNK * 32)[pos % GCHUNK] = j;
-      } else {
-        tneigh[beg + pos] = j;
-        s12ab[beg + pos] = sc;
+        if (!ina) reinterpret_cast<double2 *>(rec)[pos % GCHUNK] = make_double2(0.0, 0.0);
+        if (!inb) reinterpret_cast<double2 *>(rec + GCHUNK * 16)[pos % GCHUNK] = make_double2(0.0, 0.0);
       }
+      const unsigned ma = __ballot_sync(FULL, ina), mb = __ballot_sync(FULL, inb);
+      if (ina) {
+        const int q = qn + __popc(ma & below);
+        q_dst[wq][q] = (unsigned)pos << 1;
+        q_r2[wq][q] = ra;
+      }
+      qn += __popc(ma);
+      if (inb) {
+        const int q = qn + __popc(mb & below);
+        q_dst[wq][q] = ((unsigned)pos << 1) | 1u;
+        q_r2[wq][q] = rb;
+      }
+      qn += __popc(mb);
+      __syncwarp();
+      while (qn >= 32) {
+        drain(qn - 32 + lane);
+        qn -= 32;
+      }
+      __syncwarp();
+    } else if (ok) {
+      tneigh[beg + pos] = j;
+      s12ab[beg + pos] = sc;
     }
     n += __popc(m);
   }
+  if (CHUNKED && lane < qn) drain(lane);
   if (lane == 0) tcount[g] = n;
   if (RMIN) {
 #pragma unroll
