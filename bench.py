@@ -700,10 +700,17 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the multi-GPU parity stage (N > 1)")
     ap.add_argument("--no-also", action="store_true", help="N = 1: skip the secondary measurements of configs 2 and 3")
     args = ap.parse_args()
+    # stdout carries the ONE JSON line and nothing else: libraries that write to file descriptor 1 behind Python's back
+    # (NCCL prints its version banner there when the first communicator comes up) are sent to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(json_fd, "w", buffering=1)
     if args.impl == "reference":
         reference_arm(args)
     else:
         gpu_arm(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":
