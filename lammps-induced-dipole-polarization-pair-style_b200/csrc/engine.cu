@@ -1384,9 +1384,17 @@ struct polb200_ewald {
   double unitk[3] = {0, 0, 0};
   int kxmax = 0, kymax = 0, kzmax = 0, kmax = 0, nk = 0, nquads = 0, slots = 0;
   DBuf<EwaldK> kv;
+  // column form of the same k set (ewald.cuh, round 2): the default; the quad kernels stay as the cross-check (POLB200_EWALD_QUADS=1)
+  DBuf<EwaldCol> cols, vcols;
+  DBuf<double> ugv;
+  DBuf<int> kxyz;
+  DBuf<double2> W;
+  int nvalid = 0, kxhi_max = 0;
+  bool use_cols = true;
   DBuf<double2> S, Spart, phase;
-  DBuf<double> c_x, c_q, c_f, out;
+  DBuf<double> c_x, c_q, c_f, out, fpart;
   HPinned<double> h_out, h_f;
+  int num_sms = 148;
   int sfac_smem_set = 0, force_smem_set = 0;
   float ms_last = 0.f;
   // multi-GPU (polb200_ewald_comm_init): every rank holds its own atoms, the structure factors are all-reduced
@@ -1450,6 +1458,45 @@ static int ewald_build_kset(polb200_ewald *e, std::vector<EwaldK> &out)
       }
     }
   return real;
+}
+
+// column form: per (ky,kz) the contiguous run kx = lo..hi of the same k set; flat arrays ordered ky, kz, kx
+static int ewald_build_columns(polb200_ewald *e, std::vector<EwaldCol> &cols, std::vector<EwaldCol> &valid, std::vector<double> &ug,
+                               std::vector<int> &kxyz)
+{
+  const double pi = 3.14159265358979323846;
+  const double ginv2 = 1.0 / (e->g_ewald * e->g_ewald), preu = 4.0 * pi / e->volume;
+  cols.clear(); valid.clear(); ug.clear(); kxyz.clear();
+  e->kxhi_max = 0;
+  for (int ky = -e->kmax; ky <= e->kmax; ky++)
+    for (int kz = -e->kmax; kz <= e->kmax; kz++) {
+      EwaldCol c;
+      c.ky = (short)ky; c.kz = (short)kz; c.lo = 0; c.hi = -1; c.off = (int)ug.size(); c.pad = 0;
+      int lo = -1, hi = -1, cnt = 0;
+      double sqk;
+      for (int kx = 0; kx <= e->kmax; kx++)
+        if (ewald_in_set(e, kx, ky, kz, sqk)) {
+          if (lo < 0) lo = kx;
+          hi = kx;
+          cnt++;
+        }
+      if (lo >= 0) {
+        if (cnt != hi - lo + 1) throw StyleError{POLB200_ERR_STATE, "polb200_ewald: the k set of a (ky,kz) column is not one run of kx"};
+        c.lo = (short)lo; c.hi = (short)hi;
+        for (int kx = lo; kx <= hi; kx++) {
+          ewald_in_set(e, kx, ky, kz, sqk);
+          ug.push_back(preu * exp(-0.25 * sqk * ginv2) / sqk);
+          kxyz.push_back(kx | ((ky + 512) << 10) | ((kz + 512) << 20));
+        }
+        e->kxhi_max = std::max(e->kxhi_max, hi);
+        valid.push_back(c);
+      }
+      cols.push_back(c);
+    }
+  // the structure-factor kernel skips blocks of kx above the largest `hi` of a warp's columns: hand it the columns
+  // longest first, so that the columns of a warp are (nearly) equally long and the sphere, not the box, is evaluated
+  std::stable_sort(valid.begin(), valid.end(), [](const EwaldCol &a, const EwaldCol &b) { return a.hi > b.hi; });
+  return (int)ug.size();
 }
 
 }  // namespace polb200
@@ -2129,6 +2176,7 @@ int polb200_ewald_create(polb200_ewald_t **out, int device)
     delete e;
     return POLB200_ERR_CUDA;
   }
+  cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, device);
   *out = e;
   return POLB200_OK;
 }
@@ -2139,6 +2187,7 @@ void polb200_ewald_destroy(polb200_ewald_t *e)
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   e->kv.release(); e->S.release(); e->Spart.release(); e->phase.release();
+  e->cols.release(); e->vcols.release(); e->ugv.release(); e->kxyz.release(); e->W.release(); e->fpart.release();
   e->c_x.release(); e->c_q.release(); e->c_f.release(); e->out.release();
   e->h_out.release(); e->h_f.release();
   if (e->nccl) g_nccl.CommDestroy(e->nccl);
@@ -2196,6 +2245,24 @@ int polb200_ewald_init(polb200_ewald_t *e, const polb200_ewald_setup *in, polb20
     e->out.ensure(8);
     e->h_out.ensure(8);
     if (!ks.empty()) CUDA_CHECK(cudaMemcpy(e->kv.p, ks.data(), ks.size() * sizeof(EwaldK), cudaMemcpyHostToDevice));
+    {
+      if (e->kmax >= 512) throw StyleError{POLB200_ERR_UNSUPPORTED, "polb200_ewald: kmax >= 512"};
+      std::vector<EwaldCol> cols, valid;
+      std::vector<double> ug;
+      std::vector<int> kxyz;
+      const int nkc = ewald_build_columns(e, cols, valid, ug, kxyz);
+      if (nkc != e->nk) throw StyleError{POLB200_ERR_STATE, "polb200_ewald: column form and quad form of the k set differ"};
+      e->nvalid = (int)valid.size();
+      e->cols.ensure(cols.size() + 1); e->vcols.ensure(valid.size() + 1); e->ugv.ensure(ug.size() + 1); e->kxyz.ensure(kxyz.size() + 1);
+      e->W.ensure(ug.size() + 1);
+      CUDA_CHECK(cudaMemcpy(e->cols.p, cols.data(), cols.size() * sizeof(EwaldCol), cudaMemcpyHostToDevice));
+      if (!valid.empty()) {
+        CUDA_CHECK(cudaMemcpy(e->vcols.p, valid.data(), valid.size() * sizeof(EwaldCol), cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(e->ugv.p, ug.data(), ug.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(e->kxyz.p, kxyz.data(), kxyz.size() * sizeof(int), cudaMemcpyHostToDevice));
+      }
+      if (const char *v = getenv("POLB200_EWALD_QUADS")) e->use_cols = atoi(v) == 0;
+    }
     e->ready = true;
     if (info) {
       info->g_ewald = g;
@@ -2217,7 +2284,8 @@ int polb200_ewald_compute(polb200_ewald_t *e, int nlocal, const double *x, const
     CUDA_CHECK(cudaSetDevice(e->device));
     if (energy) *energy = 0.0;
     if (virial) for (int k = 0; k < 6; k++) virial[k] = 0.0;
-    const int n = nlocal, nk = e->nquads;  // the kernels walk quads of four k-vectors
+    const bool cols = e->use_cols;
+    const int n = nlocal, nk = cols ? e->nk : e->nquads;  // quad kernels walk quads of four k-vectors, column kernels the nk real ones
     if (e->qsqsum == 0.0 || nk == 0 || (n == 0 && !e->nccl)) return;  // ewald.cpp:376 (a rank without atoms still joins the sum)
     const double pi = 3.14159265358979323846;
     CUDA_CHECK(cudaEventRecord(e->ev[0], e->stream));
@@ -2231,11 +2299,54 @@ int polb200_ewald_compute(polb200_ewald_t *e, int nlocal, const double *x, const
       dx = e->c_x.p; dq = e->c_q.p; df = e->c_f.p;
     }
     const int slots = e->slots;
-    if (n == 0) CUDA_CHECK(cudaMemsetAsync(e->S.p, 0, (size_t)4 * nk * sizeof(double2), e->stream));
+    const size_t s_slots = cols ? (size_t)nk : (size_t)4 * nk;   // complex entries of S
+    if (n == 0) CUDA_CHECK(cudaMemsetAsync(e->S.p, 0, s_slots * sizeof(double2), e->stream));
     else {
     e->phase.ensure((size_t)3 * n * slots);
     k_ewald_phase<<<cdiv((long)3 * n, 256), 256, 0, e->stream>>>(n, dx, e->unitk[0], e->unitk[1], e->unitk[2], slots, e->phase.p);
     CUDA_CHECK(cudaGetLastError());
+    if (cols) {
+      // structure factors, column form: threads = columns, slices of atoms over grid.y until the machine is full
+      const int nkx = e->kxhi_max + 1;
+      const int NK = nkx <= 8 ? 8 : (nkx <= 16 ? 16 : (nkx <= 24 ? 24 : 32));
+      const int ncol = NK <= 24 ? 2 : 1;
+      const int kblocks = cdiv(e->nvalid, EWC_THREADS * ncol);
+      const int smem = 2 * (EWC_TILE * NK + 2 * EWC_TILE * slots + EWC_TILE) * (int)sizeof(double2);   // two tile buffers
+      int slices = 1;
+      for (int kxbase = 0; kxbase < nkx; kxbase += 32) {
+#define SF(NKX, CO)                                                                                                          \
+  do {                                                                                                                       \
+    auto kern = k_ewald_sfac_col<NKX, CO>;                                                                                   \
+    static int set = 0;                                                                                                      \
+    if (smem > set) {                                                                                                        \
+      CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                             \
+      set = smem;                                                                                                            \
+    }                                                                                                                        \
+    /* slices of atoms over grid.y: exactly one wave of resident CTAs (a partial second wave cost 40 %) */                  \
+    int occ = 1;                                                                                                             \
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, EWC_THREADS, smem));                                \
+    slices = std::max(1, std::min(cdiv(n, 2 * EWC_TILE), std::max(1, occ) * e->num_sms / kblocks));                          \
+    e->Spart.ensure((size_t)(slices + cdiv(slices, 16)) * nk + 4);                                                           \
+    kern<<<dim3(kblocks, slices), EWC_THREADS, smem, e->stream>>>(n, e->nvalid, nk, e->vcols.p, dq, e->phase.p, slots, kxbase, \
+                                                                  e->Spart.p);                                                \
+  } while (0)
+        if (NK == 8) SF(8, 2);
+        else if (NK == 16) SF(16, 2);
+        else if (NK == 24) SF(24, 2);
+        else SF(32, 1);
+#undef SF
+        CUDA_CHECK(cudaGetLastError());
+        e->launches++;
+      }
+      // slices -> groups of 16 -> S, fixed order
+      const int ngroups = cdiv(slices, 16);
+      double2 *gsum = e->Spart.p + (size_t)slices * nk;
+      k_ewald_sum_groups<<<dim3(cdiv(nk, 128), ngroups), 128, 0, e->stream>>>(nk, slices, 16, e->Spart.p, gsum);
+      CUDA_CHECK(cudaGetLastError());
+      k_ewald_sum_groups<<<dim3(cdiv(nk, 128), 1), 128, 0, e->stream>>>(nk, ngroups, ngroups, gsum, e->S.p);
+      CUDA_CHECK(cudaGetLastError());
+      e->launches += 2;
+    } else {
 
     // structure factors: k-vectors x atom slices (enough CTAs to fill the machine, few enough atomics)
     const int kblocks = cdiv(nk, EW_KTHREADS);
@@ -2252,11 +2363,36 @@ int polb200_ewald_compute(polb200_ewald_t *e, int nlocal, const double *x, const
     CUDA_CHECK(cudaGetLastError());
     e->launches++;
     }
+    }
     // decomposed run: S(k) = sum over the ranks of their atoms' contributions (the reference's MPI_Allreduce of
     // sfacrl / sfacim, ewald.cpp:395-400)
-    if (e->nccl) NCCL_CHECK(g_nccl.AllReduce(e->S.p, e->S.p, (size_t)8 * nk, ncclDouble, ncclSum, e->nccl, e->stream));
+    if (e->nccl) NCCL_CHECK(g_nccl.AllReduce(e->S.p, e->S.p, 2 * s_slots, ncclDouble, ncclSum, e->nccl, e->stream));
     // forces: one thread per atom with its phase rows in shared memory
-    if (n > 0) {
+    if (n > 0 && cols) {
+      const int side = 2 * e->kmax + 1;
+      const int smem = side * (e->kmax + 1) * (int)sizeof(double2) + side * (int)sizeof(EwaldCol);
+      if (smem > 200 * 1024) throw StyleError{POLB200_ERR_UNSUPPORTED, "Ewald kmax too large for the device force kernel"};
+      if (smem > e->force_smem_set) {
+        CUDA_CHECK(cudaFuncSetAttribute(k_ewald_force_col, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        e->force_smem_set = smem;
+      }
+      k_ewald_w<<<cdiv(nk, 256), 256, 0, e->stream>>>(nk, e->ugv.p, e->S.p, e->W.p);
+      CUDA_CHECK(cudaGetLastError());
+      // small systems: the ky rows are split over grid.y until ~16 warps per SM are in flight
+      const int athreads = EWC_THREADS;
+      const int ablocks = cdiv(n, athreads);
+      const int fslices = std::max(1, std::min(side, (4 * e->num_sms) / ablocks));
+      if (fslices > 1) e->fpart.ensure((size_t)fslices * 3 * n);
+      k_ewald_force_col<<<dim3(ablocks, fslices), athreads, smem, e->stream>>>(n, e->kmax, e->cols.p, e->W.p, dq, e->phase.p, slots,
+                                                                               e->unitk[0], e->unitk[1], e->unitk[2], e->qqrd2e, df, e->fpart.p);
+      CUDA_CHECK(cudaGetLastError());
+      if (fslices > 1) {
+        k_ewald_force_sum<<<cdiv((long)3 * n, 256), 256, 0, e->stream>>>((long)3 * n, fslices, e->fpart.p, df);
+        CUDA_CHECK(cudaGetLastError());
+        e->launches++;
+      }
+      e->launches += 3;
+    } else if (n > 0) {
     int athreads = EW_ATHREADS;
     const int tile_b = EW_KTILE * (int)(sizeof(EwaldK) + 4 * sizeof(double2));
     while (athreads > 32 && athreads * 3 * slots * (int)sizeof(double2) + tile_b > 200 * 1024) athreads -= 32;
@@ -2273,6 +2409,10 @@ int polb200_ewald_compute(polb200_ewald_t *e, int nlocal, const double *x, const
     }
     const bool ev = (eflag & 1) || (vflag % 4);
     if (ev) {
+      if (cols)
+        k_ewald_energy_col<<<1, 256, 0, e->stream>>>(nk, e->ugv.p, e->kxyz.p, e->S.p, e->unitk[0], e->unitk[1], e->unitk[2],
+                                                     1.0 / (e->g_ewald * e->g_ewald), e->out.p);
+      else
       k_ewald_energy<<<1, 256, 0, e->stream>>>(nk, e->kv.p, e->S.p, e->unitk[0], e->unitk[1], e->unitk[2],
                                                1.0 / (e->g_ewald * e->g_ewald), e->out.p);
       CUDA_CHECK(cudaGetLastError());
