@@ -80,6 +80,7 @@ struct polb200_handle {
   bool use_tight = true;         // per-step tight list
   int gpf_minb = 4;              // resident CTAs per SM asked of the grouped force kernel (4: 128 registers, no spills; measured faster than 5)
   bool use_group_pairs = true;   // LJ + Coulomb + field and polarization forces on the pair-group rows when they qualify
+  int gs_cluster = 16;           // exact-mode blocked Gauss-Seidel: CTAs of the cluster that walks the blocks in one launch (0: one launch per block)
   bool gs_blocked = true;        // exact-mode Gauss-Seidel as blocked forward substitution (false: one atom at a time)
   // Owned atoms may lie up to this far OUTSIDE the box / the brick they are handed to (a caller that keeps rigid bodies
   // whole assigns a molecule to the brick of one of its atoms): the ghost shells are made that much deeper.
@@ -1086,6 +1087,44 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
         // one launch per block (k_gsb_step); the launches of a sweep are replayed from a CUDA graph, captured once and
         // kept for as long as its arguments stay the same (at 750 atoms a sweep is 25 dependent kernels of a few us)
         const int nblk = cdiv(n, GSB);
+        // the lower-triangular part in one launch by a thread-block cluster (k_gsb_cluster) when the device can schedule it
+        bool by_cluster = false;
+        if (h->gs_cluster > 0 && nblk > 1) {
+          int ncta = std::min(h->gs_cluster, 16);
+          while (ncta > 1 && (ncta - 1) * GSB >= 2 * n) ncta /= 2;   // no more helpers than rows to update
+          static int nonportable = -1;
+          if (nonportable < 0) {
+            nonportable = cudaFuncSetAttribute(k_gsb_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess ? 1 : 0;
+            CUDA_CHECK(cudaFuncSetAttribute(k_gsb_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, GSC_SMEM));
+          }
+          if (!nonportable) ncta = std::min(ncta, 8);
+          cudaLaunchConfig_t cfg = {};
+          cudaLaunchAttribute attr[1];
+          bool launched = false;
+          for (; ncta >= 2 && !launched; ncta /= 2) {
+            cfg.gridDim = dim3(ncta);
+            cfg.blockDim = dim3(GSS_THREADS);
+            cfg.dynamicSmemBytes = GSC_SMEM;
+            cfg.stream = h->stream;
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = ncta;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            int nclusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, k_gsb_cluster, &cfg) != cudaSuccess || nclusters < 1) {
+              cudaGetLastError();
+              continue;
+            }
+            CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_gsb_cluster, n, order, P, (const int *)h->perm.p, (const double4 *)h->xq.p, cur, h->gsR.p, chg,
+                                          stop, gs_cache));
+            h->launches++;
+            launched = true;
+          }
+          by_cluster = launched;
+        }
+        if (!by_cluster) {
         const void *key[8] = {order, h->perm.p, h->xq.p, cur, h->gsR.p, chg, stop, gs_cache.plane};
         auto launch_steps = [&] {
           for (int b = 0; b < nblk; b++) {
@@ -1122,6 +1161,7 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
           }
           CUDA_CHECK(cudaGraphLaunch(G.exec, h->stream));
           h->launches += G.nodes;
+        }
         }
         summed = true;
       } else if (sequential) {
@@ -1566,6 +1606,7 @@ int polb200_create(polb200_t **out, int device)
   if (const char *v = getenv("POLB200_USE_PUSH")) h->use_push = atoi(v) != 0;
   if (const char *v = getenv("POLB200_GPF_MINB")) h->gpf_minb = atoi(v);
   if (const char *v = getenv("POLB200_GROUP_PAIRS")) h->use_group_pairs = atoi(v) != 0;
+  if (const char *v = getenv("POLB200_GS_CLUSTER")) h->gs_cluster = std::max(0, std::min(16, atoi(v)));
   if (const char *v = getenv("POLB200_XSORT_BITS")) h->xsort_bits = atoi(v);
   if (const char *v = getenv("POLB200_BIN_DIV")) h->bin_div = atof(v);
   int rc = guarded(h, [&] {
@@ -1865,6 +1906,11 @@ int polb200_set_option(polb200_t *h, const char *name, double value)
   }
   if (!strcmp(name, "use_group_pairs")) {
     h->use_group_pairs = value != 0.0;
+    return POLB200_OK;
+  }
+  if (!strcmp(name, "gs_cluster")) {
+    if (value < 0.0 || value > 16.0) return POLB200_ERR_ARG;
+    h->gs_cluster = (int)value;
     return POLB200_OK;
   }
   if (!strcmp(name, "use_tight")) {

@@ -2756,4 +2756,178 @@ k_gsb_step(int n, int b, const int *__restrict__ order, DevParams P, const int *
   if (lane == 0) change_out[0] = b == 0 ? change : change_out[0] + change;
 }
 
+// The whole lower-triangular part of a sweep in ONE launch: a thread-block cluster walks the blocks.  The chain of
+// k_gsb_step launches costs ~10 us per block (25 dependent launches at 750 atoms = 0.24 ms per sweep, the largest item of
+// the reference's shipped examples); what a step really needs is ~2 us of dependent work.  Per block b:
+//   CTA 0   : rows of block b  -=  T mu_new of block b-1 (warp w owns row w), tensors of the diagonal block into shared
+//             memory, one warp substitutes (as k_gsb_step), new dipoles to global memory;
+//   helpers : (CTAs 1..) rows of the blocks AFTER b  -=  T mu_new of block b-1 -- at the same time as CTA 0 solves block b;
+//   barrier.cluster (release / acquire): block b's dipoles and the helpers' row updates are visible to the next step.
+// The rows of block b+1 have then received every block before b from the helpers and get block b from CTA 0 itself.
+// Same operands per atom and the same order of additions inside a row as the chain of k_gsb_step launches.
+__device__ __forceinline__ void cluster_sync_all()
+{
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_cta_rank()
+{
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ unsigned cluster_num_ctas()
+{
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+
+// dynamic shared memory of k_gsb_cluster: two diagonal tiles, two off-diagonal tiles, the block's right-hand sides and its
+// new dipoles
+constexpr int GSC_TILE = GSB * GSB * 5;                                   // doubles per tile
+constexpr int GSC_SMEM = (4 * GSC_TILE + 2 * GSB * 3) * (int)sizeof(double);
+
+__global__ void __launch_bounds__(GSS_THREADS)
+k_gsb_cluster(int n, const int *__restrict__ order, DevParams P, const int *__restrict__ perm,
+              const double4 *__restrict__ xq, double4 *__restrict__ mua, double4 *__restrict__ R,
+              double *__restrict__ change_out, const int *stop, GsPairCache C)
+{
+  if (scf_stopped(stop)) return;   // the flag is stable while this kernel runs: every CTA takes the same branch
+  extern __shared__ double gsc[];
+  // CTA 0 keeps everything the NEXT block needs that does not depend on dipoles in shared memory, fetched by its 31 idle
+  // warps while warp 0 substitutes: the tensors of the next diagonal block (sD) and of the pairs (row of the next block,
+  // atom of this block) (sO).  After the barrier a step is then: read 32 right-hand sides, one shared-memory pass, substitute.
+  double *sD = gsc, *sO = gsc + 2 * GSC_TILE, *sR = gsc + 4 * GSC_TILE, *sMu = sR + GSB * 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rank = (int)cluster_cta_rank(), helpers = (int)cluster_num_ctas() - 1;
+  const int nblk = (n + GSB - 1) / GSB;
+  double total = 0.0;   // lane 0 of CTA 0, warp 0: squared change of the sweep, block sums added in block order (as k_gsb_step)
+  // {s1, s2, del} of the pair (position p, position q) of the sweep order
+  auto tensor = [&](int p, int q, double *t) {
+    double dx = 0, dy = 0, dz = 0, s1 = 0, s2 = 0;
+    if (p < n && q < n && p != q) {
+      if (C.on()) C.load(p, q, s1, s2, dx, dy, dz);
+      else {
+        const int s = order ? order[p] : p, j = order ? order[q] : q;
+        pair_del(P.box, perm, s, j, xq[s], xq[j], dx, dy, dz);
+        induced_field_scalars(P.pc, dx * dx + dy * dy + dz * dz, s1, s2);
+      }
+    }
+    t[0] = s1; t[1] = s2; t[2] = dx; t[3] = dy; t[4] = dz;
+  };
+  // tiles of block b into buffer (b & 1): diagonal (b, b) and off-diagonal (rows of b, atoms of b - 1); row r by warp r0 + r
+  auto prefetch = [&](int b, int w0, int nw) {
+    const int p0 = b * GSB;
+    double *d = sD + (b & 1) * GSC_TILE, *o = sO + (b & 1) * GSC_TILE;
+    for (int r = warp - w0; r < GSB; r += nw) {
+      if (r < 0) continue;
+      tensor(p0 + r, p0 + lane, d + (r * GSB + lane) * 5);
+      if (b > 0) tensor(p0 + r, p0 - GSB + lane, o + (r * GSB + lane) * 5);
+    }
+  };
+  // helpers: R[p] -= sum over the atoms of block c of T(p, q) mu_new[q]  (global memory, coherent loads)
+  auto apply = [&](int p, int c) {
+    const int s = order ? order[p] : p;
+    const int q = c * GSB + lane;   // block c is complete, hence full
+    const int j = order ? order[q] : q;
+    double ex = 0, ey = 0, ez = 0;
+    if (ld4_cg(mua + s).w != 0.0) {
+      const double4 mj = ld4_cg(mua + j);
+      if (C.on()) cached_field_pair(C, p, q, mj.x, mj.y, mj.z, ex, ey, ez);
+      else {
+        const double4 xs = xq[s], xj = ld4(xq + j);
+        double dx, dy, dz;
+        pair_del(P.box, perm, s, j, xs, xj, dx, dy, dz);
+        induced_field_pair(P.pc, dx, dy, dz, dx * dx + dy * dy + dz * dz, mj.x, mj.y, mj.z, ex, ey, ez);
+      }
+    }
+    ex = warp_sum(ex);
+    ey = warp_sum(ey);
+    ez = warp_sum(ez);
+    if (lane == 0) {
+      const double4 r = ld4_cg(R + p);
+      R[p] = make_double4(r.x + ex, r.y + ey, r.z + ez, 0.0);
+    }
+  };
+  if (rank == 0) {
+    prefetch(0, 0, GSB);
+    __syncthreads();
+  }
+  for (int b = 0; b < nblk; b++) {
+    const int p0 = b * GSB, cnt = min(GSB, n - p0);
+    if (rank != 0) {
+      // the rows after block b get block b-1's new dipoles while CTA 0 works on block b
+      if (b > 0)
+        for (int p = p0 + GSB + (rank - 1) * GSB + warp; p < n; p += helpers * GSB) apply(p, b - 1);
+    } else {
+      // (warp 0: the block's old dipoles travel while the right-hand sides are formed)
+      const int sv = (warp == 0 && lane < cnt) ? (order ? order[p0 + lane] : p0 + lane) : 0;
+      double4 mv = (warp == 0 && lane < cnt) ? ld4_cg(mua + sv) : make_double4(0, 0, 0, 0);
+      // 1. right-hand sides of the block's rows: what the helpers and k_gsb_upper left in R, minus block b-1 (shared memory)
+      if (warp < cnt) {
+        const int s = order ? order[p0 + warp] : p0 + warp;
+        const double4 r = ld4_cg(R + p0 + warp);
+        double ex = 0, ey = 0, ez = 0;
+        if (b > 0 && ld4_cg(mua + s).w != 0.0) {
+          const double *t = sO + (b & 1) * GSC_TILE + (warp * GSB + lane) * 5;
+          const double mx = sMu[lane * 3], my = sMu[lane * 3 + 1], mz = sMu[lane * 3 + 2];
+          const double dm = t[2] * mx + t[3] * my + t[4] * mz;
+          ex -= t[0] * mx + t[1] * dm * t[2];
+          ey -= t[0] * my + t[1] * dm * t[3];
+          ez -= t[0] * mz + t[1] * dm * t[4];
+        }
+        ex = warp_sum(ex);
+        ey = warp_sum(ey);
+        ez = warp_sum(ez);
+        if (lane == 0) {
+          sR[warp * 3] = r.x + ex;
+          sR[warp * 3 + 1] = r.y + ey;
+          sR[warp * 3 + 2] = r.z + ez;
+        }
+      }
+      __syncthreads();
+      if (warp == 0) {
+        // 2. forward substitution in column form (see k_gsb_step)
+        const double *sT = sD + (b & 1) * GSC_TILE;
+        double ax = lane < cnt ? sR[lane * 3] : 0.0, ay = lane < cnt ? sR[lane * 3 + 1] : 0.0, az = lane < cnt ? sR[lane * 3 + 2] : 0.0;
+        auto subtract = [&](int w, double mx, double my, double mz) {   // T(lane, w) read as sT[w][lane] (even in del)
+          const double *t = sT + (w * GSB + lane) * 5;
+          const double q = t[1] * (t[2] * mx + t[3] * my + t[4] * mz);
+          ax -= fma(q, t[2], t[0] * mx);
+          ay -= fma(q, t[3], t[0] * my);
+          az -= fma(q, t[4], t[0] * mz);
+        };
+        for (int u = 1; u < cnt; u++) {
+          const double mx = __shfl_sync(FULL, mv.x, u), my = __shfl_sync(FULL, mv.y, u), mz = __shfl_sync(FULL, mv.z, u);
+          if (lane < u) subtract(u, mx, my, mz);
+        }
+        double change = 0.0;
+        for (int w = 0; w < cnt; w++) {
+          double nx = 0, ny = 0, nz = 0;
+          if (lane == w) {
+            nx = mv.w * ax, ny = mv.w * ay, nz = mv.w * az;
+            change += (nx - mv.x) * (nx - mv.x) + (ny - mv.y) * (ny - mv.y) + (nz - mv.z) * (nz - mv.z);
+            mv = make_double4(nx, ny, nz, mv.w);
+          }
+          nx = __shfl_sync(FULL, nx, w);
+          ny = __shfl_sync(FULL, ny, w);
+          nz = __shfl_sync(FULL, nz, w);
+          if (lane > w && lane < cnt) subtract(w, nx, ny, nz);
+        }
+        if (lane < cnt) {
+          mua[sv] = mv;
+          sMu[lane * 3] = mv.x; sMu[lane * 3 + 1] = mv.y; sMu[lane * 3 + 2] = mv.z;
+        }
+        change = warp_sum(change);
+        total = b == 0 ? change : total + change;
+      } else if (b + 1 < nblk) {
+        prefetch(b + 1, 1, GSB - 1);   // 3. meanwhile: the tiles of the next block into the other buffer
+      }
+      __syncthreads();
+    }
+    cluster_sync_all();
+  }
+  if (rank == 0 && warp == 0 && lane == 0) change_out[0] = total;
+}
+
 }  // namespace polb200

@@ -12,7 +12,7 @@ import polhelpers as H
 from gpu_common import pb, configure_from_fixture, run_fixture
 
 fx = H.load_fixture(sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("--") else "h2_default_step0")
-for opts in (({},) if "--one" in sys.argv else ({}, {"use_graphs": 0}, {"scf_lag": 0})):
+for opts in (({},) if "--one" in sys.argv else ({}, {"gs_cluster": 8}, {"gs_cluster": 0}, {"gs_cluster": 0, "use_graphs": 0}, {"scf_lag": 0})):
     s = pb.PairStyle(device=0)
     configure_from_fixture(s, fx)
     for k, v in opts.items():
