@@ -406,8 +406,12 @@ long polb200_debug_fetch(polb200_t *h, const char *name, void *dst, long capacit
 long polb200_launch_count(polb200_t *h, int reset);
 /* knobs for experiments and A/B measurements: "sweep_variant" (41 = TMA-fed pair-group sweep, default; 40 / 44; 30 / 31
  * register-prefetch pair groups; 20 / 21 per-atom rows + radial cache; 6 matrix-free; 0 first version), "bin_div",
- * "xsort_bits", "gs_blocked", "gs_colours", "gs_strong_m", "scf_lag", "use_group_pairs", "gpf_minb", "use_tight",
- * "use_push", "p2p_push", "l2_evict_first", "alternate", "time_sweeps".  POLB200_ERR_ARG for unknown names. */
+ * "xsort_bits", "gs_blocked", "gs_cluster" (CTAs of the cluster kernel of the exact-mode Gauss-Seidel sweep, default 16;
+ * 0 = one launch per block), "gs_cache_max", "use_graphs", "gs_colours", "gs_strong_m", "scf_lag", "use_group_pairs",
+ * "gpf_minb", "use_tight", "use_push", "p2p_push", "l2_evict_first", "alternate", "time_sweeps".
+ * One option is part of the multi-GPU interface rather than a knob: "atom_slack" (Angstrom, 0..16, default 0) lets a
+ * decomposed caller hand a brick atoms up to that far OUTSIDE its sub-domain (whole molecules kept on one process): ghost
+ * shells, send lists and the cell grid reach cutneighmax + slack.  POLB200_ERR_ARG for unknown names. */
 int polb200_set_option(polb200_t *h, const char *name, double value);
 
 #ifdef __cplusplus
