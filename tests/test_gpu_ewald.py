@@ -77,3 +77,25 @@ def test_device_ewald_is_bit_reproducible():
         outs.append((energy, f.copy(), virial))
     for energy, f, virial in outs[1:]:
         assert energy == outs[0][0] and np.array_equal(f, outs[0][1]) and np.array_equal(virial, outs[0][2])
+
+
+def test_column_kernels_equal_the_quad_kernels(monkeypatch):
+    """Two realisations of the same sums (ewald.cuh): the column form (default) and round 1's quad form
+    (POLB200_EWALD_QUADS=1, read at init).  Energy, forces and virial must agree to rounding, also for an atom count that is
+    no multiple of a tile and on a non-cubic box (different kmax per dimension)."""
+    sysm = H.lj_charge_fluid((12, 9, 7))
+    keep = np.arange(sysm.n) % 97 != 5
+    x, q = np.ascontiguousarray(sysm.x[keep]), np.ascontiguousarray(sysm.q[keep])
+    out = []
+    for quads in ("0", "1"):
+        monkeypatch.setenv("POLB200_EWALD_QUADS", quads)
+        e = pb.Ewald(device=0)
+        info = e.init(1e-5, q, 10.0, sysm.boxlo, sysm.boxhi)
+        f = np.zeros_like(x)
+        energy, virial = e.compute(x, q, f)
+        e.close()
+        out.append((info.kcount, energy, f, np.array(virial)))
+    assert out[0][0] == out[1][0]
+    assert abs(out[0][1] - out[1][1]) < 1e-12 * abs(out[1][1])
+    assert np.abs(out[0][2] - out[1][2]).max() < 1e-12 * np.abs(out[1][2]).max()
+    assert H.rel_err(out[0][3], out[1][3]) < 1e-11

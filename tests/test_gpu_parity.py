@@ -240,6 +240,26 @@ def test_sequential_gs_is_iteration_for_iteration_the_oracle(style, words):
     assert np.abs(f - ref["f"]).max() < TOL * np.abs(ref["f"]).max()
 
 
+@pytest.mark.parametrize("case", ["h2_default_step0", "methane_default_step0"])
+def test_cluster_sweep_equals_the_launch_chain(case):
+    """Exact-mode Gauss-Seidel: the 16-CTA cluster kernel that walks the blocks of a sweep in one launch (default) and the
+    chain of one launch per block evaluate the same substitution -- same iteration count, dipoles and forces to rounding."""
+    fx = H.load_fixture(case)
+    out = []
+    for cluster in (16, 8, 0):
+        s = pb.PairStyle(device=0)
+        configure_from_fixture(s, fx)
+        s.set_option("gs_cluster", cluster)
+        res, mu, ef, f = run_fixture(s, fx)
+        out.append((res.iterations, mu, f, res.eng_pol))
+        s.close()
+    for it, mu, f, e in out[:2]:
+        assert it == out[2][0]
+        assert H.rel_err(mu, out[2][1]) < 1e-12
+        assert np.abs(f - out[2][2]).max() < 1e-12 * np.abs(out[2][2]).max()
+        assert abs(e - out[2][3]) < 1e-12 * abs(out[2][3])
+
+
 def _fluid_style_on_device(style, sysm, g_ewald, words):
     style.set_ntypes(2)
     style.command("pair_style lj/cut/coul/long/polarization 2.5 12.0 " + words)
