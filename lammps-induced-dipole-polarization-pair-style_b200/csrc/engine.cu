@@ -2354,8 +2354,8 @@ int polb200_ewald_compute(polb200_ewald_t *e, int nlocal, const double *x, const
     if (cols) {
       // structure factors, column form: threads = columns, slices of atoms over grid.y until the machine is full
       const int nkx = e->kxhi_max + 1;
-      const int NK = nkx <= 8 ? 8 : (nkx <= 16 ? 16 : (nkx <= 24 ? 24 : 32));
-      const int ncol = NK <= 24 ? 2 : 1;
+      const int NK = std::min(32, 4 * cdiv(nkx, 4));   // kx held in registers per pass (multiples of 4, at most 32)
+      const int ncol = (NK <= 16 || NK == 24) ? 2 : 1;  // columns per thread (measured: 20 kx are better served by one + look-ahead)
       const int kblocks = cdiv(e->nvalid, EWC_THREADS * ncol);
       const int smem = 2 * (EWC_TILE * NK + 2 * EWC_TILE * slots + EWC_TILE) * (int)sizeof(double2);   // two tile buffers
       int slices = 1;
@@ -2368,18 +2368,28 @@ int polb200_ewald_compute(polb200_ewald_t *e, int nlocal, const double *x, const
       CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                             \
       set = smem;                                                                                                            \
     }                                                                                                                        \
-    /* slices of atoms over grid.y: exactly one wave of resident CTAs (a partial second wave cost 40 %) */                  \
+    /* slices of atoms over grid.y.  The columns are sorted by length, so the CTAs of a slice differ in work (a CTA's    */ \
+    /* four warps do not: no waiting at the tile barrier): several waves of CTAs let the hardware scheduler level that   */ \
+    /* out; for small systems exactly one wave (a partial second wave cost 40 %)                                         */ \
     int occ = 1;                                                                                                             \
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, EWC_THREADS, smem));                                \
-    slices = std::max(1, std::min(cdiv(n, 2 * EWC_TILE), std::max(1, occ) * e->num_sms / kblocks));                          \
+    const int wave = std::max(1, occ) * e->num_sms;                                                                          \
+    slices = std::max(1, wave / kblocks);                                                                                    \
+    if (n >= 8 * EWC_TILE * 4 * slices) slices *= 4;                                                                         \
     e->Spart.ensure((size_t)(slices + cdiv(slices, 16)) * nk + 4);                                                           \
     kern<<<dim3(kblocks, slices), EWC_THREADS, smem, e->stream>>>(n, e->nvalid, nk, e->vcols.p, dq, e->phase.p, slots, kxbase, \
                                                                   e->Spart.p);                                                \
   } while (0)
-        if (NK == 8) SF(8, 2);
-        else if (NK == 16) SF(16, 2);
-        else if (NK == 24) SF(24, 2);
-        else SF(32, 1);
+        switch (NK) {
+          case 4: SF(4, 2); break;
+          case 8: SF(8, 2); break;
+          case 12: SF(12, 2); break;
+          case 16: SF(16, 2); break;
+          case 20: SF(20, 1); break;
+          case 24: SF(24, 2); break;
+          case 28: SF(28, 1); break;
+          default: SF(32, 1); break;
+        }
 #undef SF
         CUDA_CHECK(cudaGetLastError());
         e->launches++;

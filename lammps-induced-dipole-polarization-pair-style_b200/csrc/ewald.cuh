@@ -324,18 +324,29 @@ k_ewald_sfac_col(int n, int nvalid, int nk, const EwaldCol *__restrict__ vcol, c
         p[c].y *= qi;
       }
       const double2 *ex = sx + t * NKX;
+      // the four Ex of a block are read one block ahead of their use (same address in every lane: broadcasts); without
+      // that every block began by waiting for its shared-memory reads
+      double2 ecur[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) ecur[k] = ex[k];
 #pragma unroll
       for (int kb = 0; kb < NKX; kb += 4) {
         if (kb > whi) break;   // warp-uniform
+        double2 enext[4];
 #pragma unroll
-        for (int k = kb; k < kb + 4; k++) {
-          const double2 e = ex[k];   // same address in every lane: broadcast
+        for (int k = 0; k < 4; k++) enext[k] = (kb + 4 < NKX && NKX * COLS <= 32) ? ex[kb + 4 + k] : make_double2(0.0, 0.0);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          // (with more than 32 complex accumulators per thread there is no register left for the look-ahead)
+          const double2 e = NKX * COLS <= 32 ? ecur[k] : ex[kb + k];
 #pragma unroll
           for (int c = 0; c < COLS; c++) {
-            acc[c][k].x = fma(e.x, p[c].x, fma(-e.y, p[c].y, acc[c][k].x));
-            acc[c][k].y = fma(e.x, p[c].y, fma(e.y, p[c].x, acc[c][k].y));
+            acc[c][kb + k].x = fma(e.x, p[c].x, fma(-e.y, p[c].y, acc[c][kb + k].x));
+            acc[c][kb + k].y = fma(e.x, p[c].y, fma(e.y, p[c].x, acc[c][kb + k].y));
           }
         }
+#pragma unroll
+        for (int k = 0; k < 4; k++) ecur[k] = enext[k];
       }
     }
     __syncthreads();   // the next iteration's prefetch overwrites this buffer's sibling, the one after it this buffer
