@@ -195,6 +195,16 @@ int polb200_compute(polb200_t *h, const polb200_atoms *atoms, int eflag, int vfl
 /* Size of the opaque NCCL unique id the ranks must share (rank 0 creates it). */
 int polb200_comm_id_size(void);
 int polb200_comm_create_id(void *id_bytes);
+/* The all-pairs (exact) mode on several GPUs -- SURVEY 8e's caveat: that interaction set (every minimum-image pair, no
+ * dipole cutoff; what the reference computes, pol.cpp:1243-1316) does not decompose into bricks, so it is shared as a 1-D
+ * row partition instead.  EVERY process passes the WHOLE system to polb200_compute (identical arrays); the O(N^2) stages --
+ * static field, Jacobi dipole sweeps, polarization forces -- are computed for the process's rows and all-gathered
+ * (dipoles: 24 N bytes per sweep, as double4 records), the O(N) stages and the sequential Gauss-Seidel sweeps run
+ * replicated, and every process returns the full, identical result (do not sum it over the processes).  Rows are handed
+ * out in blocks of the kernels' row-block size, so all fixed-order reductions see the partial sums of a single-GPU run:
+ * results and iteration counts are bit-identical to one GPU.  Not combinable with polb200_comm_init / polar_cutoff,
+ * no per-atom tallies.  nccl_unique_id as for polb200_comm_init. */
+int polb200_comm_init_replicated(polb200_t *h, int rank, int nranks, const void *nccl_unique_id);
 /* Join a communicator of nranks processes; procgrid = bricks per dimension (px*py*pz == nranks). */
 int polb200_comm_init(polb200_t *h, int rank, int nranks, const void *id_bytes, const int procgrid[3]);
 /* Sub-domain owned by this rank, valid after polb200_set_box + polb200_comm_init. */

@@ -80,6 +80,14 @@ struct polb200_handle {
   bool use_tight = true;         // per-step tight list
   int gpf_minb = 4;              // resident CTAs per SM asked of the grouped force kernel (4: 128 registers, no spills; measured faster than 5)
   bool use_group_pairs = true;   // LJ + Coulomb + field and polarization forces on the pair-group rows when they qualify
+  // all-pairs (exact) mode on several GPUs (polb200_comm_init_replicated): every process holds the whole system, the O(N^2)
+  // stages are shared by rows and all-gathered (SURVEY 8e caveat)
+  struct ExactShare {
+    ncclComm_t nccl = nullptr;
+    int rank = 0, nranks = 1;
+    bool active = false;
+  } xr;
+  DBuf<double> xg;               // all-gather scratch
   int gs_cluster = 16;           // exact-mode blocked Gauss-Seidel: CTAs of the cluster that walks the blocks in one launch (0: one launch per block)
   bool gs_blocked = true;        // exact-mode Gauss-Seidel as blocked forward substitution (false: one atom at a time)
   // Owned atoms may lie up to this far OUTSIDE the box / the brick they are handed to (a caller that keeps rigid bodies
@@ -875,7 +883,29 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
   if (comm && !list_mode)
     throw StyleError{POLB200_ERR_UNSUPPORTED,
                      "spatial decomposition needs a dipole cutoff (polar_cutoff <r>): the reference's all-pairs "
-                     "minimum-image interaction set does not decompose into bricks"};
+                     "minimum-image interaction set does not decompose into bricks (polb200_comm_init_replicated shares it by rows)"};
+  // all-pairs mode shared by rows: every process holds the whole system (polb200_comm_init_replicated)
+  const bool xsplit = h->xr.active;
+  if (xsplit && list_mode)
+    throw StyleError{POLB200_ERR_UNSUPPORTED, "polb200_comm_init_replicated shares the all-pairs mode; with polar_cutoff use polb200_comm_init (bricks)"};
+  if (xsplit && (eflag_atom || vflag_atom))
+    throw StyleError{POLB200_ERR_UNSUPPORTED, "per-atom tallies are not available when the all-pairs mode is shared by several GPUs"};
+  // rows of this process: equal chunks, multiples of the row-block size, so that every per-block partial sum is the
+  // single-GPU one and the fixed-order reductions give the same bits on every process
+  const int xchunk = xsplit ? cdiv(cdiv(n, h->xr.nranks), WARPS_PER_BLOCK) * WARPS_PER_BLOCK : n;
+  const int xr0 = xsplit ? std::min(n, h->xr.rank * xchunk) : 0, xr1 = xsplit ? std::min(n, xr0 + xchunk) : n;
+  // all-gather of `per_row` doubles per row (or per row block: rows = blocks) of an array whose rows [lo, hi) this process wrote
+  auto xgather = [&](double *arr, int per_row, int chunk_rows, int lo, int hi, int total_rows) {
+    const size_t cnt = (size_t)chunk_rows * per_row;
+    h->xg.ensure(cnt * h->xr.nranks + 8);
+    double *mine = h->xg.p + cnt * h->xr.rank;
+    CUDA_CHECK(cudaMemsetAsync(mine, 0, cnt * sizeof(double), h->stream));
+    if (hi > lo)
+      CUDA_CHECK(cudaMemcpyAsync(mine, arr + (size_t)lo * per_row, (size_t)(hi - lo) * per_row * sizeof(double), cudaMemcpyDeviceToDevice,
+                                 h->stream));
+    NCCL_CHECK(g_nccl.AllGather(mine, h->xg.p, cnt, ncclDouble, h->xr.nccl, h->stream));
+    CUDA_CHECK(cudaMemcpyAsync(arr, h->xg.p, (size_t)total_rows * per_row * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  };
   for (int d = 0; d < 3; d++) {
     if (!h->box.periodic[d]) continue;
     if (st.cutneighmax + h->atom_slack > h->box.prd[d])
@@ -987,7 +1017,10 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
   }
 #undef PAIR_ARGS
   if (evflag) reduce_partials<NPAIR_PART>(h, grouped_pf ? ngroupblocks : nrowblocks, h->scal.p + S_PAIR, 0);
-  if (!list_mode) LAUNCH(h, k_static_allpairs, nrowblocks, BLOCK, n, P, h->xq.p, h->tm.p, h->perm.p, h->ef.p);
+  if (!list_mode) {
+    if (xr1 > xr0) LAUNCH(h, k_static_allpairs, cdiv(xr1 - xr0, WARPS_PER_BLOCK), BLOCK, n, P, h->xq.p, h->tm.p, h->perm.p, h->ef.p, xr0, xr1);
+    if (xsplit) xgather(reinterpret_cast<double *>(h->ef.p), 4, xchunk, xr0, xr1, n);
+  }
   if (!st.use_previous) LAUNCH(h, k_init_mu, cdiv(n, 256), 256, n, st.polar_gamma, h->ef.p, h->mua.p);
   ghost_update(h, false, h->mua.p);
   CUDA_CHECK(cudaEventRecord(h->ev[2], h->stream));
@@ -1171,7 +1204,16 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
         sweep_event(h);
         nparts = nrowblocks;
         if (list_mode) nparts = launch_list_sweep(h, 0, n, order, P, L, A, cur, nxt, want_change, push);
-        else LAUNCH(h, (k_sweep<false>), nrowblocks, BLOCK, 0, n, order, P, L, A, h->xq.p, cur, h->ef.p, nxt, h->partial.p, stop);
+        else if (!xsplit) LAUNCH(h, (k_sweep<false>), nrowblocks, BLOCK, 0, n, order, P, L, A, h->xq.p, cur, h->ef.p, nxt, h->partial.p, stop);
+        else {
+          // this process's rows, then every process gets all new dipoles (24 N bytes per sweep; the arrays carry alpha
+          // along) and all per-block squared changes: the reduction below sees the blocks of the single-GPU launch
+          const int bchunk = xchunk / WARPS_PER_BLOCK, b0 = xr0 / WARPS_PER_BLOCK, b1 = cdiv(xr1, WARPS_PER_BLOCK);
+          if (xr1 > xr0)
+            LAUNCH(h, (k_sweep<false>), b1 - b0, BLOCK, xr0, xr1, order, P, L, A, h->xq.p, cur, h->ef.p, nxt, h->partial.p + b0, stop);
+          xgather(reinterpret_cast<double *>(nxt), 4, xchunk, xr0, xr1, n);
+          if (want_change) xgather(h->partial.p, 1, bchunk, b0, b1, nrowblocks);
+        }
         sweep_event(h);
       } else if (coloured) {
         // group-coloured sweep: the colours in turn; Jacobi inside a colour (staging array + commit)
@@ -1255,7 +1297,7 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
       for (int it = 0; it < nsweeps; it++) enqueue_iteration(it);
       iterations = itmax;
     } else {
-      const int lag = (comm && !h->comm.push.enabled) ? 0 : h->scf_lag;
+      const int lag = ((comm && !h->comm.push.enabled) || xsplit) ? 0 : h->scf_lag;
       int it = 0;
       const int *seen = nullptr;
       while (!seen) {
@@ -1298,10 +1340,19 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
   do {                                                                                                                   \
     if (vflag_atom)                                                                                                      \
       LAUNCH(h, (k_polforce<LISTM, EV, VP, true>), nrowblocks, BLOCK, n, P, L, A, h->xq.p, h->mua.p, h->tm.p, h->f_pol.p, \
-             h->partial.p, vq_ptr);                                                                                      \
-    else                                                                                                                 \
+             h->partial.p, vq_ptr, 0);                                                                                   \
+    else if (!xsplit)                                                                                                    \
       LAUNCH(h, (k_polforce<LISTM, EV, VP, false>), nrowblocks, BLOCK, n, P, L, A, h->xq.p, h->mua.p, h->tm.p,            \
-             h->f_pol.p, h->partial.p, (double *)nullptr);                                                               \
+             h->f_pol.p, h->partial.p, (double *)nullptr, 0);                                                            \
+    else {                                                                                                               \
+      /* all-pairs mode shared by rows: own rows, then all forces and all per-block energy / virial partials */         \
+      const int bchunk = xchunk / WARPS_PER_BLOCK, b0 = xr0 / WARPS_PER_BLOCK, b1 = cdiv(xr1, WARPS_PER_BLOCK);           \
+      if (xr1 > xr0)                                                                                                     \
+        LAUNCH(h, (k_polforce<LISTM, EV, VP, false>), b1 - b0, BLOCK, xr1, P, L, A, h->xq.p, h->mua.p, h->tm.p,          \
+               h->f_pol.p, h->partial.p + (size_t)b0 * NPOL_PART, (double *)nullptr, xr0);                               \
+      xgather(reinterpret_cast<double *>(h->f_pol.p), 4, xchunk, xr0, xr1, n);                                           \
+      if (EV) xgather(h->partial.p, NPOL_PART, bchunk, b0, b1, nrowblocks);                                              \
+    }                                                                                                                    \
   } while (0)
   // the reference tallies polarization energies whenever eflag is set, virial via F.r or pairwise
   const bool ev4 = evflag;
@@ -1648,6 +1699,9 @@ void polb200_destroy(polb200_t *h)
     if (c.nccl) g_nccl.CommDestroy(c.nccl);
     c.active = false;
   }
+  if (h->xr.nccl) g_nccl.CommDestroy(h->xr.nccl);
+  h->xr = polb200_handle::ExactShare{};
+  h->xg.release();
   for (auto *b : {&h->c_x, &h->c_q, &h->c_alpha, &h->c_mu, &h->c_f, &h->c_ef, &h->c_xhold, &h->d_coeff,
                   &h->d_tables, &h->partial, &h->scal, &h->metric, &h->metric2, &h->ea_row, &h->va_pair_row,
                   &h->va_pol_row, &h->c_eatom, &h->c_vatom})
@@ -2128,12 +2182,31 @@ int polb200_comm_create_id(void *id_bytes)
   return POLB200_OK;
 }
 
+int polb200_comm_init_replicated(polb200_t *h, int rank, int nranks, const void *id_bytes)
+{
+  if (!h || !id_bytes) return POLB200_ERR_ARG;
+  return guarded(h, [&] {
+    if (h->device == POLB200_DEVICE_NONE) throw CudaError{"polb200_comm_init_replicated needs a CUDA device"};
+    if (h->comm.active || h->xr.active) throw StyleError{POLB200_ERR_STATE, "a communicator was already set up for this handle"};
+    if (nranks < 1 || rank < 0 || rank >= nranks || nranks > 64) throw StyleError{POLB200_ERR_ARG, "Bad grid of processors"};
+    std::string err;
+    if (!g_nccl.load(err)) throw StyleError{POLB200_ERR_UNSUPPORTED, err};
+    CUDA_CHECK(cudaSetDevice(h->device));
+    ncclUniqueId id;
+    memcpy(&id, id_bytes, sizeof(id));
+    NCCL_CHECK(g_nccl.CommInitRank(&h->xr.nccl, nranks, id, rank));
+    h->xr.rank = rank;
+    h->xr.nranks = nranks;
+    h->xr.active = true;
+  });
+}
+
 int polb200_comm_init(polb200_t *h, int rank, int nranks, const void *id_bytes, const int procgrid[3])
 {
   if (!h || !id_bytes || !procgrid) return POLB200_ERR_ARG;
   return guarded(h, [&] {
     if (h->device == POLB200_DEVICE_NONE) throw CudaError{"polb200_comm_init needs a CUDA device"};
-    if (h->comm.active) throw StyleError{POLB200_ERR_STATE, "polb200_comm_init was already called"};
+    if (h->comm.active || h->xr.active) throw StyleError{POLB200_ERR_STATE, "polb200_comm_init was already called"};
     if (nranks < 1 || rank < 0 || rank >= nranks || procgrid[0] * procgrid[1] * procgrid[2] != nranks || nranks > 64)
       throw StyleError{POLB200_ERR_ARG, "Bad grid of processors"};
     std::string err;

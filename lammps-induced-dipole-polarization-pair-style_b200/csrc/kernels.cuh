@@ -624,11 +624,12 @@ k_pair(int nloc, DevParams P, const double4 *__restrict__ xq, const int2 *__rest
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(BLOCK)
 k_static_allpairs(int nloc, DevParams P, const double4 *__restrict__ xq, const int2 *__restrict__ tm,
-                  const int *__restrict__ perm, double4 *__restrict__ ef)
+                  const int *__restrict__ perm, double4 *__restrict__ ef, int row0, int row_end)
 {
+  // rows [row0, row_end) of the nloc atoms (the whole system unless the all-pairs work is shared by several GPUs)
   const int lane = threadIdx.x & 31;
-  const int s = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-  if (s >= nloc) return;
+  const int s = row0 + blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (s >= row_end) return;
   const double4 xi = xq[s];
   const int moli = tm[s].y, ci = perm[s];
   double ex = 0, ey = 0, ez = 0;
@@ -1138,10 +1139,11 @@ template <bool LIST, bool EVFLAG, bool VPAIR, bool VATOM = false>
 __global__ void __launch_bounds__(BLOCK, 3)
 k_polforce(int nloc, DevParams P, ListRows L, AllPairRows A, const double4 *__restrict__ xq,
            const double4 *__restrict__ mua, const int2 *__restrict__ tm, double4 *__restrict__ f_pol,
-           double *__restrict__ partial, double *__restrict__ vatom_row = nullptr)
+           double *__restrict__ partial, double *__restrict__ vatom_row, int row0)
 {
+  // rows [row0, nloc): row0 = 0 unless the all-pairs work is shared by several GPUs (then `partial` is offset alike)
   const int lane = threadIdx.x & 31;
-  const int s = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const int s = row0 + blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   double acc[NPOL_PART] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   if (s < nloc) {
     const double4 xi = xq[s];

@@ -34,7 +34,7 @@ ABI_SYMBOLS = [
     "polb200_rigid_create", "polb200_rigid_destroy", "polb200_rigid_last_error", "polb200_rigid_init",
     "polb200_rigid_dof", "polb200_rigid_setup", "polb200_rigid_initial_integrate", "polb200_rigid_final_integrate",
     "polb200_rigid_pre_neighbor", "polb200_rigid_virial", "polb200_rigid_scalar", "polb200_rigid_reset_dt",
-    "polb200_rigid_get_chain", "polb200_rigid_set_chain", "polb200_rigid_comm_init",
+    "polb200_rigid_get_chain", "polb200_rigid_set_chain", "polb200_rigid_comm_init", "polb200_comm_init_replicated",
     "polb200_rigid_fetch", "polb200_rigid_launch_count", "polb200_rigid_last_ms",
 ]
 
@@ -165,6 +165,7 @@ def lib():
         L.polb200_ewald_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.polb200_pppm_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.polb200_rigid_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.polb200_comm_init_replicated.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.polb200_set_box.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
         L.polb200_compute.argtypes = [C.c_void_p, C.POINTER(Atoms), C.c_int, C.c_int, C.c_int, C.POINTER(Result)]
         L.polb200_debug_fetch.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_long]
@@ -391,6 +392,11 @@ class PairStyle:
     def comm_init(self, rank, nranks, id_bytes, procgrid):
         buf = C.create_string_buffer(id_bytes, len(id_bytes))
         self._check(lib().polb200_comm_init(self._h, rank, nranks, buf, (C.c_int * 3)(*[int(v) for v in procgrid])))
+
+    def comm_init_replicated(self, rank, nranks, id_bytes):
+        """all-pairs (exact) mode shared by rows: every process passes the whole system and gets the whole result"""
+        buf = C.create_string_buffer(id_bytes, len(id_bytes))
+        self._check(lib().polb200_comm_init_replicated(self._h, rank, nranks, buf))
 
     def subdomain(self):
         lo = (C.c_double * 3)()

@@ -5,7 +5,9 @@ parity-checked path) and its brick of the same system through the decomposed pat
 fields and forces must agree, energies and virial after summing over ranks.
 
 Cases: Jacobi fixed-iteration (NCCL halo and fused peer push), Jacobi precision mode (iteration counts
-equal), ranked colouring sweep (tolerance), a step without rebuild after moving atoms, and a rebuild.
+equal), ranked colouring sweep (tolerance), a step without rebuild after moving atoms, and a rebuild; exclusion rules and
+atom_slack across bricks; decomposed Ewald / PPPM; the all-pairs (exact) mode shared by rows (bit-identical to one GPU);
+collective error agreement.
 Prints one line per case and exits non-zero on failure.  Used by tests/test_multi_gpu.py (gpu marker).
 """
 import os
@@ -179,6 +181,43 @@ def main():
         dist.all_reduce(flag)
         if rank == 0:
             print(f"[mgpu {world} ranks] {name}: {'OK' if int(flag) == 0 else 'FAIL'} | " + " ".join(f"{k}={v:.1e}" for k, v in errs.items()), flush=True)
+        if int(flag):
+            failures.append(name)
+
+    # the all-pairs (exact) mode shared by rows (polb200_comm_init_replicated): every rank holds the whole system; the result
+    # must equal the single-GPU one BIT FOR BIT (same per-block partial sums, same fixed-order reductions), on every rank
+    small = H.lj_charge_fluid(6, seed=31)
+    keep = np.arange(small.n) != 17          # 863 atoms: the last rank's chunk is short, the last row block partial
+    xs, qs, ts, als, tags = small.x[keep], small.q[keep], small.type[keep], small.alpha[keep], np.arange(1, keep.sum() + 1)
+    g_small = P.ewald_g(1e-4, qs, 9.0, small.boxlo, small.boxhi)
+    for name, words in (("exact_jacobi_fixed", "polar_gs_ranked no fixed_iteration yes max_iterations 9 damp_type exponential"),
+                        ("exact_jacobi_precision", "polar_gs_ranked no precision 1e-10 max_iterations 80 damp_type exponential"),
+                        ("exact_gs_ranked", "precision 1e-11 max_iterations 60 damp_type exponential")):
+        outs = []
+        for shared in (False, True):
+            s = pb.PairStyle(device=local)
+            s.set_ntypes(2)
+            s.command(f"pair_style lj/cut/coul/long/polarization 2.5 9.0 {words}")
+            s.command("pair_coeff 1 1 0.1 3.0")
+            s.command("pair_coeff 2 2 0.1 3.0")
+            s.init(g_ewald=g_small, molecular=0)
+            s.set_box(small.boxlo, small.boxhi)
+            if shared:
+                s.comm_init_replicated(rank, world, fresh_id())
+            mu = np.zeros((len(xs), 3))
+            res = None
+            for step in range(2):            # second step: use of the previous dipoles, lists re-used
+                res, mu, ef, f = run(s, xs + 0.01 * step, qs, ts, als, tags, mu, step)
+            outs.append((res, mu, ef, f))
+            s.close()
+        (r0, mu0, ef0, f0), (r1, mu1, ef1, f1) = outs
+        good = (r0.iterations == r1.iterations and np.array_equal(mu0, mu1) and np.array_equal(ef0, ef1) and np.array_equal(f0, f1)
+                and r0.eng_pol == r1.eng_pol and r0.eng_coul == r1.eng_coul and list(r0.virial[:]) == list(r1.virial[:]))
+        flag = torch.tensor([0 if good else 1], device="cuda")
+        dist.all_reduce(flag)
+        if rank == 0:
+            print(f"[mgpu {world} ranks] {name}: {'OK' if int(flag) == 0 else 'FAIL'} | {len(xs)} atoms, iterations {r1.iterations}/{r0.iterations}, "
+                  f"max |dmu| {np.abs(mu1 - mu0).max():.1e}, max |df| {np.abs(f1 - f0).max():.1e}, E_pol {r1.eng_pol:.10f} / {r0.eng_pol:.10f}", flush=True)
         if int(flag):
             failures.append(name)
 
