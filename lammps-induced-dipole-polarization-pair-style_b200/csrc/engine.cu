@@ -959,12 +959,16 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
   // gs_chunks setting, without pair groups, or when their cache does not fit -- per-atom chunks of the ranked order
   bool coloured = gs_mode && list_mode && st.gs_chunks == 0 && h->groups_built && h->sweep_variant >= 40;
   // LJ + Coulomb + field and the polarization forces on the pair-group rows: every interaction of the step must
-  // reach exactly as far as the dipole cutoff (the tight group rows hold the partners inside it), no special bonds,
-  // no exclusion rules, no per-atom / pairwise tallies
-  bool grouped_pf = list_mode && h->groups_built && h->sweep_variant >= 40 && h->use_group_pairs && !h->molecular &&
-                    h->excl.n == 0 && !eflag_atom && !vflag_atom && !vpair &&
-                    std::max(st.cutforce, st.cut_coul) <= st.polar_cutoff;
-  if (coloured || grouped_pf) {
+  // reach exactly as far as the dipole cutoff (the tight group rows hold the partners inside it), no exclusion rules,
+  // no per-atom / pairwise tallies.  The pair kernel also needs "no special bonds" (the group rows carry no special-bond
+  // classes); the polarization forces only look at molecule ids, so molecular systems (BASELINE config 4) take the
+  // grouped force kernel with the per-atom pair kernel.
+  const bool grouped_force_ok = list_mode && h->groups_built && h->sweep_variant >= 40 && h->use_group_pairs &&
+                                h->excl.n == 0 && !eflag_atom && !vflag_atom && !vpair &&
+                                std::max(st.cutforce, st.cut_coul) <= st.polar_cutoff;
+  bool grouped_pf = grouped_force_ok && !h->molecular;   // stage 2 on the group rows
+  bool grouped_force = grouped_force_ok;                 // stage 4 on the group rows
+  if (coloured || grouped_force) {
     // steps that keep their colouring only report rmin: the group cache produces it on the way
     const bool fuse_rmin = coloured && st.polar_gs_ranked && h->colours_valid;
     if (fuse_rmin) {
@@ -972,7 +976,7 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
       const unsigned long long init = (unsigned long long)0x408F400000000000ull;  // bits of 1000.0 (pol.cpp:196)
       CUDA_CHECK(cudaMemcpyAsync(h->rmin_bits.p, &init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
     }
-    if (!ensure_group_cache(h, P, fuse_rmin)) coloured = grouped_pf = false;
+    if (!ensure_group_cache(h, P, fuse_rmin)) coloured = grouped_pf = grouped_force = false;
   }
   const bool jacobi_groups = !gs_mode && h->groups_built;
   const bool need_tight = h->use_tight && !(grouped_pf && (st.zodid || coloured || jacobi_groups));
@@ -1356,7 +1360,7 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
   } while (0)
   // the reference tallies polarization energies whenever eflag is set, virial via F.r or pairwise
   const bool ev4 = evflag;
-  if (grouped_pf) {
+  if (grouped_force) {
 #define FG4(EV) LAUNCH(h, (k_polforce_group<EV, 4>), ngroupblocks, GPF_WARPS * 32, h->ngroups, P, h->group_first.p, h->group_two.p, h->tgcount.p, \
                        h->gcstart.p, h->gcrec.p, h->xq.p, h->mua.p, h->tm.p, h->f_pol.p, h->partial.p)
 #define FG(EV) if (h->gpf_minb == 4) FG4(EV); else LAUNCH(h, (k_polforce_group<EV, 5>), ngroupblocks, GPF_WARPS * 32, h->ngroups, P, h->group_first.p, h->group_two.p, h->tgcount.p, \
@@ -1374,7 +1378,7 @@ static void compute_impl(polb200_handle *h, const polb200_atoms *at, int eflag, 
     else POLFORCE(false, true, false);
   }
 #undef POLFORCE
-  if (ev4) reduce_partials<NPOL_PART>(h, grouped_pf ? ngroupblocks : nrowblocks, h->scal.p + S_POL, 0);
+  if (ev4) reduce_partials<NPOL_PART>(h, grouped_force ? ngroupblocks : nrowblocks, h->scal.p + S_POL, 0);
 
   // ---- stage 5: outputs ----
   h->c_f.ensure((size_t)3 * n); h->c_ef.ensure((size_t)3 * n);
