@@ -2786,8 +2786,9 @@ __device__ __forceinline__ unsigned cluster_num_ctas()
 
 // dynamic shared memory of k_gsb_cluster: two diagonal tiles, two off-diagonal tiles, the block's right-hand sides and its
 // new dipoles
-constexpr int GSC_TILE = GSB * GSB * 5;                                   // doubles per tile
-constexpr int GSC_SMEM = (4 * GSC_TILE + 2 * GSB * 3) * (int)sizeof(double);
+constexpr int GSC_TILE = GSB * GSB * 5;                                   // doubles per off-diagonal tile: {s1, s2, del}
+constexpr int GSC_DTILE = GSB * GSB * 6;                                  // per diagonal tile: the symmetric 3x3 tensor of a pair
+constexpr int GSC_SMEM = (2 * GSC_DTILE + 2 * GSC_TILE + 2 * GSB * 3) * (int)sizeof(double);
 
 __global__ void __launch_bounds__(GSS_THREADS)
 k_gsb_cluster(int n, const int *__restrict__ order, DevParams P, const int *__restrict__ perm,
@@ -2799,7 +2800,7 @@ k_gsb_cluster(int n, const int *__restrict__ order, DevParams P, const int *__re
   // CTA 0 keeps everything the NEXT block needs that does not depend on dipoles in shared memory, fetched by its 31 idle
   // warps while warp 0 substitutes: the tensors of the next diagonal block (sD) and of the pairs (row of the next block,
   // atom of this block) (sO).  After the barrier a step is then: read 32 right-hand sides, one shared-memory pass, substitute.
-  double *sD = gsc, *sO = gsc + 2 * GSC_TILE, *sR = gsc + 4 * GSC_TILE, *sMu = sR + GSB * 3;
+  double *sD = gsc, *sO = gsc + 2 * GSC_DTILE, *sR = sO + 2 * GSC_TILE, *sMu = sR + GSB * 3;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rank = (int)cluster_cta_rank(), helpers = (int)cluster_num_ctas() - 1;
   const int nblk = (n + GSB - 1) / GSB;
@@ -2820,10 +2821,16 @@ k_gsb_cluster(int n, const int *__restrict__ order, DevParams P, const int *__re
   // tiles of block b into buffer (b & 1): diagonal (b, b) and off-diagonal (rows of b, atoms of b - 1); row r by warp r0 + r
   auto prefetch = [&](int b, int w0, int nw) {
     const int p0 = b * GSB;
-    double *d = sD + (b & 1) * GSC_TILE, *o = sO + (b & 1) * GSC_TILE;
+    double *d = sD + (b & 1) * GSC_DTILE, *o = sO + (b & 1) * GSC_TILE;
     for (int r = warp - w0; r < GSB; r += nw) {
       if (r < 0) continue;
-      tensor(p0 + r, p0 + lane, d + (r * GSB + lane) * 5);
+      // diagonal tile: T = s1 I + s2 del del^T as six numbers, so that a substitution step is three short FMA chains
+      // (the substitution is one dependent chain of 32 steps: two FP64 latencies less per step)
+      double t[5];
+      tensor(p0 + r, p0 + lane, t);
+      double *m = d + (r * GSB + lane) * 6;
+      m[0] = fma(t[1] * t[2], t[2], t[0]); m[1] = fma(t[1] * t[3], t[3], t[0]); m[2] = fma(t[1] * t[4], t[4], t[0]);
+      m[3] = t[1] * t[2] * t[3]; m[4] = t[1] * t[2] * t[4]; m[5] = t[1] * t[3] * t[4];
       if (b > 0) tensor(p0 + r, p0 - GSB + lane, o + (r * GSB + lane) * 5);
     }
   };
@@ -2890,14 +2897,13 @@ k_gsb_cluster(int n, const int *__restrict__ order, DevParams P, const int *__re
       __syncthreads();
       if (warp == 0) {
         // 2. forward substitution in column form (see k_gsb_step)
-        const double *sT = sD + (b & 1) * GSC_TILE;
+        const double *sT = sD + (b & 1) * GSC_DTILE;
         double ax = lane < cnt ? sR[lane * 3] : 0.0, ay = lane < cnt ? sR[lane * 3 + 1] : 0.0, az = lane < cnt ? sR[lane * 3 + 2] : 0.0;
-        auto subtract = [&](int w, double mx, double my, double mz) {   // T(lane, w) read as sT[w][lane] (even in del)
-          const double *t = sT + (w * GSB + lane) * 5;
-          const double q = t[1] * (t[2] * mx + t[3] * my + t[4] * mz);
-          ax -= fma(q, t[2], t[0] * mx);
-          ay -= fma(q, t[3], t[0] * my);
-          az -= fma(q, t[4], t[0] * mz);
+        auto subtract = [&](int w, double mx, double my, double mz) {   // T(lane, w) read as sT[w][lane] (T is symmetric in the pair)
+          const double *t = sT + (w * GSB + lane) * 6;   // xx yy zz xy xz yz
+          ax -= fma(t[4], mz, fma(t[3], my, t[0] * mx));
+          ay -= fma(t[5], mz, fma(t[1], my, t[3] * mx));
+          az -= fma(t[2], mz, fma(t[5], my, t[4] * mx));
         };
         for (int u = 1; u < cnt; u++) {
           const double mx = __shfl_sync(FULL, mv.x, u), my = __shfl_sync(FULL, mv.y, u), mz = __shfl_sync(FULL, mv.z, u);
