@@ -99,3 +99,26 @@ def test_column_kernels_equal_the_quad_kernels(monkeypatch):
     assert abs(out[0][1] - out[1][1]) < 1e-12 * abs(out[1][1])
     assert np.abs(out[0][2] - out[1][2]).max() < 1e-12 * np.abs(out[1][2]).max()
     assert H.rel_err(out[0][3], out[1][3]) < 1e-11
+
+
+def test_more_kx_than_one_register_block(monkeypatch):
+    """kmax = 36 (tight accuracy, short real-space cutoff): the structure-factor kernel holds 32 kx per pass, so this
+    k set needs two passes; the force kernel's recurrences run 73 steps.  Against the oracle's direct sums and the quad
+    kernels."""
+    sysm = H.lj_charge_fluid(4)                                  # 256 atoms, 97 634 k-vectors
+    prd = sysm.boxhi - sysm.boxlo
+    plan = P.ewald_plan(1e-10, sysm.q, 2.5, prd)
+    assert max(plan.kxmax, plan.kymax, plan.kzmax) > 32
+    ref = P.ewald_compute(plan, sysm.x, sysm.q, prd)
+    x, q = np.ascontiguousarray(sysm.x), np.ascontiguousarray(sysm.q)
+    for quads in ("0", "1"):
+        monkeypatch.setenv("POLB200_EWALD_QUADS", quads)
+        e = pb.Ewald(device=0)
+        info = e.init(1e-10, q, 2.5, sysm.boxlo, sysm.boxhi)
+        assert info.kcount == plan.kcount
+        f = np.zeros_like(x)
+        energy, virial = e.compute(x, q, f)
+        e.close()
+        assert abs(energy - ref["energy"]) < 1e-10 * abs(ref["energy"])
+        assert np.abs(f - ref["f"]).max() < 1e-10 * np.abs(ref["f"]).max()
+        assert H.rel_err(virial, ref["virial"]) < 1e-9
