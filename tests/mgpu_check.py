@@ -190,9 +190,13 @@ def main():
     keep = np.arange(small.n) != 17          # 863 atoms: the last rank's chunk is short, the last row block partial
     xs, qs, ts, als, tags = small.x[keep], small.q[keep], small.type[keep], small.alpha[keep], np.arange(1, keep.sum() + 1)
     g_small = P.ewald_g(1e-4, qs, 9.0, small.boxlo, small.boxhi)
+    full = (xs, qs, ts, als, tags)
     for name, words in (("exact_jacobi_fixed", "polar_gs_ranked no fixed_iteration yes max_iterations 9 damp_type exponential"),
                         ("exact_jacobi_precision", "polar_gs_ranked no precision 1e-10 max_iterations 80 damp_type exponential"),
-                        ("exact_gs_ranked", "precision 1e-11 max_iterations 60 damp_type exponential")):
+                        ("exact_gs_ranked", "precision 1e-11 max_iterations 60 damp_type exponential"),
+                        # five atoms: fewer row blocks than processes, the last processes own no row at all
+                        ("exact_tiny", "polar_gs_ranked no precision 1e-10 max_iterations 80 damp_type exponential")):
+        xs, qs, ts, als, tags = (a[:5] for a in full) if name == "exact_tiny" else full
         outs = []
         for shared in (False, True):
             s = pb.PairStyle(device=local)
